@@ -1,0 +1,173 @@
+/* smore_b200 -- C ABI of the B200-native sampled-SGD backend for SMORe.
+ *
+ * This is the drop-in boundary. The reference has no FFI of its own: every model calls the
+ * pronet core once per sample on host slices. Crossing a cgo / ctypes boundary per sample is impossible when the
+ * rows live in HBM, so the seam moves up one level, to the model method set that every reference CLI uses
+ *     New(); LoadEdgeList(file, undirected); Init(dim, ...); Train(...); SaveWeights(file)
+ * (Go: cmd/line/main.go:54-67, cmd/bpr/main.go:42-55, cmd/deepwalk/main.go:44-57;
+ *  C++: cli/line.cpp:71-76, cli/bpr.cpp:58-63, cli/warp.cpp:55-60, cli/hoprec.cpp:69-75, cli/deepwalk.cpp:72-77,
+ *  cli/walklets.cpp:70-75). Each entry point below names the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types. Every call returns 0 on success or a negative
+ * SMORE_E_* code; smore_last_error() returns the message for the calling thread. Handles own all device memory;
+ * the caller keeps ownership of every host buffer it passes (the library copies). There is NO CPU fallback: every
+ * compute call fails with SMORE_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef SMORE_B200_H
+#define SMORE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smore_graph_s* smore_graph_t;
+typedef struct smore_model_s* smore_model_t;
+
+enum {
+    SMORE_OK = 0,
+    SMORE_E_INVALID = -1, /* bad argument */
+    SMORE_E_CUDA = -2,    /* CUDA runtime error / no device */
+    SMORE_E_IO = -3,      /* file could not be opened / parsed */
+    SMORE_E_NOMEM = -4,
+    SMORE_E_UNSUPPORTED = -5
+};
+
+/* Which of the two reference code bases a call reproduces (they differ: SURVEY.md §8c divergence table). */
+enum { SMORE_SEM_CPP = 0, /* src/ + cli/  (proNet-core) */ SMORE_SEM_GO = 1 /* pkg/pronet + internal/models */ };
+
+/* Negative-table weighting (C++: proNet::negative_method, src/proNet.cpp:486-509; BPR/WARP/HBPR ctors use no_degrees).
+ * Go always uses DEGREES (pronet.go:242-249). */
+enum { SMORE_NEG_DEGREES = 0, SMORE_NEG_IN_DEGREES = 1, SMORE_NEG_NO_DEGREES = 2 };
+
+/* Execution mode. DETERMINISTIC = one warp consuming Philox stream `stream_base` sequentially: the reference at
+ * -threads 1 fed the same draws. HOGWILD = grid-wide racing updates, warp w consumes stream `stream_base + w`. */
+enum { SMORE_MODE_DETERMINISTIC = 0, SMORE_MODE_HOGWILD = 1 };
+
+/* Stored element type of the embedding tables (the reference stores double). */
+enum { SMORE_F32 = 0, SMORE_F64 = 1 };
+
+/* Sampler selector for smore_graph_get_alias / smore_sample_debug. */
+enum { SMORE_AT_VERTEX = 0, SMORE_AT_NEGATIVE = 1, SMORE_AT_CONTEXT = 2 /* C++ only */ };
+enum { SMORE_SAMPLE_SOURCE = 0, SMORE_SAMPLE_NEGATIVE = 1, SMORE_SAMPLE_TARGET = 2, SMORE_SAMPLE_SOURCE_TARGET = 3 };
+
+/* ---- library ---------------------------------------------------------------------------------------------------- */
+
+/* Selects the CUDA device used by handles created afterwards by this thread/process (default: current device).
+ * Fails unless the device is compute capability 10.x. */
+int smore_init(int device_id);
+const char* smore_last_error(void);
+const char* smore_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t smore_kernel_launches(void);
+
+/* ---- graph: replaces proNet::LoadEdgeList + BuildAliasMethod (src/proNet.cpp:115-236, :410-542) and
+ *             ProNet.LoadEdgeList + buildGraph (pkg/pronet/pronet.go:112-249) ------------------------------------- */
+
+/* From a host CSR in REFERENCE INSERTION ORDER (per-vertex adjacency in file order, duplicates kept, reverse entries
+ * appended in place when undirected). row_off has V+1 entries. n_lines is the reference's MAX_line / MaxLine
+ * (C++: E; Go: number of edge lines, not doubled); pass <=0 for E. The library builds the reference's alias tables
+ * bit-exactly on the host (same Vose LIFO pairing order, same pow/normalisation expression) and uploads packed
+ * integer-threshold tables. */
+int smore_graph_create(int64_t V, int64_t E, const int64_t* row_off, const int32_t* col, const double* weight,
+                       int64_t n_lines, int semantics, int negative_method, smore_graph_t* out);
+
+/* Text ingest exactly as the reference does it: whitespace-separated `src dst weight`, ids in first-appearance order
+ * (src before dst), malformed lines skipped (src/proNet.cpp:171-190; pronet.go:128-155). */
+int smore_graph_load_edge_list(const char* path, int undirected, int semantics, int negative_method,
+                               smore_graph_t* out);
+
+/* HOP-Rec field metadata: proNet::LoadFieldMeta (src/proNet.cpp:330-408): `vertex field` lines, field ids in
+ * first-appearance order; HOP-Rec treats field 0 as "user" (src/model/HBPR.cpp:98). */
+int smore_graph_load_field(smore_graph_t g, const char* path);
+int smore_graph_set_field(smore_graph_t g, const int32_t* field /* V entries */);
+
+int smore_graph_info(smore_graph_t g, int64_t* V, int64_t* E, int64_t* n_lines);
+/* Host copy of the CSR the graph was built from (ingest parity). Any pointer may be NULL. */
+int smore_graph_get_csr(smore_graph_t g, int64_t* row_off, int32_t* col, double* weight);
+/* NULL when the graph was created from a CSR (no names). */
+const char* smore_graph_vertex_name(smore_graph_t g, int64_t vid);
+/* Parity hook: the fp64 alias table as the reference holds it (AliasTable{alias, prob}, src/proNet.h:88-93). */
+int smore_graph_get_alias(smore_graph_t g, int which, double* prob, int64_t* alias);
+int smore_graph_get_field(smore_graph_t g, int32_t* field);
+void smore_graph_destroy(smore_graph_t g);
+
+/* Parity hook: run the DEVICE samplers on one warp over Philox stream (seed, stream), n draws, ids to `out`
+ * (2n ids for SOURCE_TARGET). `arg` = source vertices for SMORE_SAMPLE_TARGET. Replaces SourceSample /
+ * TargetSample(v) / NegativeSample (src/proNet.cpp:623-683; pronet.go:252-289). words_used may be NULL. */
+int smore_sample_debug(smore_graph_t g, int which, uint64_t seed, uint64_t stream, int64_t n, const int64_t* arg,
+                       int64_t* out, uint64_t* words_used);
+
+/* Parity hook: device RandomWalk + SkipGrams (mode 0, window w0) / ScaleSkipGrams (mode 1, w0..w1) from `start`
+ * on stream (seed, stream) (src/proNet.cpp:704-724, :769-809, :928-987; pronet.go:292-333). Writes the walk
+ * (<= steps+1 ids) and up to `cap` (vertex, context) pairs; *n_pairs gets the true pair count. */
+int smore_walk_debug(smore_graph_t g, uint64_t seed, uint64_t stream, int64_t start, int steps, int mode, int w0, int w1,
+                     int64_t* walk, int64_t* walk_len, int64_t* pair_v, int64_t* pair_c, int64_t cap, int64_t* n_pairs);
+
+/* ---- embedding store: replaces the models' vector<vector<double>> / [][]float64 tables
+ *      (src/model/LINE.h:22-24, LINE.cpp:49-97; internal/models/line/line.go:44-70) ------------------------------- */
+
+/* n_tables: 1 (LINE-1, BPR/WARP/HOP-Rec C++: one shared table) or 2 (vertex + context). Rows are dense [V x dim]. */
+int smore_model_create(smore_graph_t g, int dim, int n_tables, int dtype, smore_model_t* out);
+/* random != 0: (U - 0.5) / dim with U = k * 2^-32 from Philox stream (seed, 2^62 + table) -- the reference's
+ * (rand()/RAND_MAX - 0.5)/dim (LINE.cpp:83) with a reproducible generator; random == 0: zeros (LINE.cpp:92). */
+int smore_model_init(smore_model_t m, int table, int random, uint64_t seed);
+int smore_model_set_rows(smore_model_t m, int table, int64_t first, int64_t n, const double* host);
+int smore_model_get_rows(smore_model_t m, int table, int64_t first, int64_t n, double* host);
+int smore_model_set_rows_f32(smore_model_t m, int table, int64_t first, int64_t n, const float* host);
+int smore_model_get_rows_f32(smore_model_t m, int table, int64_t first, int64_t n, float* host);
+/* Raw device pointer of a table (row-major [V x dim] of dtype) for zero-copy consumers on the same device. */
+int smore_model_device_ptr(smore_model_t m, int table, void** ptr);
+void smore_model_destroy(smore_model_t m);
+
+/* Text writer: "<V> <dim>\n" then `name v0 v1 ...` per vertex in id order, VERTEX table only.
+ * format 0 = C++ iostream default (%g, 6 significant digits; src/model/LINE.cpp:13-47),
+ * format 1 = Go "%.6f" (internal/models/line/line.go:209-233). */
+int smore_model_save_weights(smore_model_t m, int table, const char* path, int format);
+
+/* ---- training: each call replaces one reference Train() body ------------------------------------------------------ */
+
+typedef struct {
+    int semantics;        /* SMORE_SEM_* (must match the graph's) */
+    int mode;             /* SMORE_MODE_* */
+    uint64_t seed;        /* Philox key */
+    uint64_t stream_base; /* first sampler stream id */
+    double alpha;         /* initial learning rate (-alpha) */
+    uint64_t total;       /* C++: sample_times*1e6 (LINE.cpp:119) ; Go: sample_times*MaxLine (line.go:85) */
+    int negative_samples; /* -negative_samples (LINE / skip-gram) */
+    int order;            /* LINE: 1 or 2 */
+    double lambda;        /* Go BPR L2 (bpr.go, -lambda) */
+    int walk_times, walk_steps, window_min, window_max; /* DeepWalk: window_max = -window_size; Walklets: both */
+    int max_warps;        /* HOGWILD: cap on concurrent warps (0 = fill the device) */
+    int64_t max_walks;    /* DeepWalk/Walklets: stop after this many walks (<0: all walk_times*V) */
+} smore_train_params;
+
+/* Fills `p` with the reference CLI defaults (cmd/line/main.go:13-21, cli/line.cpp:56-64). */
+void smore_train_params_default(smore_train_params* p);
+
+/* LINE::Train (src/model/LINE.cpp:100-195) / LINE.Train (internal/models/line/line.go:73-150):
+ * SourceSample -> TargetSample -> UpdatePair (1 + K context rows), LR decay every 10000 samples. */
+int smore_train_line(smore_model_t m, const smore_train_params* p);
+/* BPR::Train (src/model/BPR.cpp:55-107, 5-negative UpdateBPRPair proNet.cpp:1406-1455) /
+ * BPR.Train (internal/models/bpr/bpr.go:61-131, optimizer.go:87-117). */
+int smore_train_bpr(smore_model_t m, const smore_train_params* p);
+/* WARP::Train (src/model/WARP.cpp:55-107, UpdateWARPPair proNet.cpp:1353-1403). C++ only. */
+int smore_train_warp(smore_model_t m, const smore_train_params* p);
+/* HBPR::Train (src/model/HBPR.cpp:63-130, UpdateFBPRPair proNet.cpp:1458-1515). C++ only; needs field data. */
+int smore_train_hoprec(smore_model_t m, const smore_train_params* p);
+/* DeepWalk::Train (src/model/DeepWalk.cpp:98-155) / DeepWalk.Train (internal/models/deepwalk/deepwalk.go:61-141):
+ * on-device RandomWalk + SkipGrams + UpdatePairs. */
+int smore_train_deepwalk(smore_model_t m, const smore_train_params* p);
+/* Walklets::Train (src/model/Walklets.cpp:6-64): RandomWalk + ScaleSkipGrams + UpdatePairs. C++ only. */
+int smore_train_walklets(smore_model_t m, const smore_train_params* p);
+
+/* Counters of the last train call on this model: samples (or walks) done, pair updates done, Philox words consumed
+ * by stream `stream_base`, mean negatives scanned (WARP), device milliseconds of the kernels. Any may be NULL. */
+int smore_train_stats(smore_model_t m, uint64_t* samples, uint64_t* pair_updates, uint64_t* words_stream0,
+                      double* warp_mean_tries, double* kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMORE_B200_H */

@@ -1,0 +1,269 @@
+"""ctypes binding of include/smore_b200.h -- the same entry points a cgo host would bind.
+
+The shared library is the product; this module only loads it and marshals numpy buffers. There is no fallback:
+if the library is missing, or a call fails (no sm_100 device, bad argument ...), a SmoreError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libsmore_b200.so")
+
+SEM_CPP, SEM_GO = 0, 1
+NEG_DEGREES, NEG_IN_DEGREES, NEG_NO_DEGREES = 0, 1, 2
+MODE_DETERMINISTIC, MODE_HOGWILD = 0, 1
+F32, F64 = 0, 1
+AT_VERTEX, AT_NEGATIVE, AT_CONTEXT = 0, 1, 2
+SAMPLE_SOURCE, SAMPLE_NEGATIVE, SAMPLE_TARGET, SAMPLE_SOURCE_TARGET = 0, 1, 2, 3
+
+u64, i64, f64, vp = C.c_uint64, C.c_int64, C.c_double, C.c_void_p
+
+# Every symbol include/smore_b200.h declares (tests check the library exports each one).
+EXPORTS = [
+    "smore_init", "smore_last_error", "smore_version", "smore_kernel_launches",
+    "smore_graph_create", "smore_graph_load_edge_list", "smore_graph_load_field", "smore_graph_set_field",
+    "smore_graph_info", "smore_graph_get_csr", "smore_graph_vertex_name", "smore_graph_get_alias",
+    "smore_graph_get_field", "smore_graph_destroy", "smore_sample_debug", "smore_walk_debug",
+    "smore_model_create", "smore_model_init", "smore_model_set_rows", "smore_model_get_rows",
+    "smore_model_set_rows_f32", "smore_model_get_rows_f32", "smore_model_device_ptr", "smore_model_destroy",
+    "smore_model_save_weights", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
+    "smore_train_warp", "smore_train_hoprec", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
+]
+
+
+class SmoreError(RuntimeError):
+    pass
+
+
+class TrainParams(C.Structure):
+    _fields_ = [
+        ("semantics", C.c_int), ("mode", C.c_int), ("seed", u64), ("stream_base", u64), ("alpha", f64),
+        ("total", u64), ("negative_samples", C.c_int), ("order", C.c_int), ("lambda_", f64),
+        ("walk_times", C.c_int), ("walk_steps", C.c_int), ("window_min", C.c_int), ("window_max", C.c_int),
+        ("max_warps", C.c_int), ("max_walks", i64),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SmoreError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(make -C smore_b200/csrc). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.smore_last_error.restype = C.c_char_p
+        L.smore_version.restype = C.c_char_p
+        L.smore_kernel_launches.restype = u64
+        L.smore_init.argtypes = [C.c_int]
+        L.smore_graph_create.argtypes = [i64, i64, vp, vp, vp, i64, C.c_int, C.c_int, C.POINTER(vp)]
+        L.smore_graph_load_edge_list.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.smore_graph_load_field.argtypes = [vp, C.c_char_p]
+        L.smore_graph_set_field.argtypes = [vp, vp]
+        L.smore_graph_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+        L.smore_graph_get_csr.argtypes = [vp, vp, vp, vp]
+        L.smore_graph_vertex_name.argtypes = [vp, i64]
+        L.smore_graph_vertex_name.restype = C.c_char_p
+        L.smore_graph_get_alias.argtypes = [vp, C.c_int, vp, vp]
+        L.smore_graph_get_field.argtypes = [vp, vp]
+        L.smore_graph_destroy.argtypes = [vp]
+        L.smore_graph_destroy.restype = None
+        L.smore_sample_debug.argtypes = [vp, C.c_int, u64, u64, i64, vp, vp, C.POINTER(u64)]
+        L.smore_walk_debug.argtypes = [vp, u64, u64, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(i64), vp, vp,
+                                       i64, C.POINTER(i64)]
+        L.smore_model_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.smore_model_init.argtypes = [vp, C.c_int, C.c_int, u64]
+        for name in ("smore_model_set_rows", "smore_model_get_rows", "smore_model_set_rows_f32",
+                     "smore_model_get_rows_f32"):
+            getattr(L, name).argtypes = [vp, C.c_int, i64, i64, vp]
+        L.smore_model_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.smore_model_destroy.argtypes = [vp]
+        L.smore_model_destroy.restype = None
+        L.smore_model_save_weights.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
+        L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
+        L.smore_train_params_default.restype = None
+        for name in ("smore_train_line", "smore_train_bpr", "smore_train_warp", "smore_train_hoprec",
+                     "smore_train_deepwalk", "smore_train_walklets"):
+            getattr(L, name).argtypes = [vp, C.POINTER(TrainParams)]
+        L.smore_train_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(f64),
+                                        C.POINTER(f64)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SmoreError(f"smore_b200 error {rc}: {lib().smore_last_error().decode()}")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(vp) if a is not None else None
+
+
+def default_params() -> TrainParams:
+    p = TrainParams()
+    lib().smore_train_params_default(C.byref(p))
+    return p
+
+
+def kernel_launches() -> int:
+    return int(lib().smore_kernel_launches())
+
+
+class Graph:
+    """CSR + alias tables resident in HBM (smore_graph_t)."""
+
+    def __init__(self, handle):
+        self.h = handle
+        V, E, n = i64(), i64(), i64()
+        check(lib().smore_graph_info(self.h, C.byref(V), C.byref(E), C.byref(n)))
+        self.V, self.E, self.n_lines = V.value, E.value, n.value
+
+    @classmethod
+    def from_csr(cls, row_off, col, w, semantics=SEM_CPP, negative_method=NEG_DEGREES, n_lines=0):
+        row_off = np.ascontiguousarray(row_off, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        h = vp()
+        check(lib().smore_graph_create(len(row_off) - 1, len(col), _ptr(row_off), _ptr(col), _ptr(w), n_lines, semantics,
+                                       negative_method, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_edge_list(cls, path, undirected, semantics=SEM_CPP, negative_method=NEG_DEGREES):
+        h = vp()
+        check(lib().smore_graph_load_edge_list(os.fsencode(path), int(undirected), semantics, negative_method,
+                                               C.byref(h)))
+        return cls(h)
+
+    def close(self):
+        if self.h:
+            lib().smore_graph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_field(self, path):
+        check(lib().smore_graph_load_field(self.h, os.fsencode(path)))
+
+    def set_field(self, field):
+        f = np.ascontiguousarray(field, dtype=np.int32)
+        assert len(f) == self.V
+        check(lib().smore_graph_set_field(self.h, _ptr(f)))
+
+    def field(self):
+        f = np.zeros(self.V, dtype=np.int32)
+        check(lib().smore_graph_get_field(self.h, _ptr(f)))
+        return f
+
+    def csr(self):
+        off = np.zeros(self.V + 1, dtype=np.int64)
+        col = np.zeros(self.E, dtype=np.int32)
+        w = np.zeros(self.E)
+        check(lib().smore_graph_get_csr(self.h, _ptr(off), _ptr(col), _ptr(w)))
+        return off, col, w
+
+    def names(self):
+        out = []
+        for v in range(self.V):
+            s = lib().smore_graph_vertex_name(self.h, v)
+            out.append(s.decode() if s is not None else None)
+        return out
+
+    def alias(self, which):
+        n = self.E if which == AT_CONTEXT else self.V
+        prob = np.zeros(n)
+        alias = np.zeros(n, dtype=np.int64)
+        check(lib().smore_graph_get_alias(self.h, which, _ptr(prob), _ptr(alias)))
+        return prob, alias
+
+    def sample(self, which, seed, stream, n, arg=None):
+        out = np.zeros(2 * n if which == SAMPLE_SOURCE_TARGET else n, dtype=np.int64)
+        a = np.ascontiguousarray(arg, dtype=np.int64) if arg is not None else None
+        used = u64()
+        check(lib().smore_sample_debug(self.h, which, seed, stream, n, _ptr(a), _ptr(out), C.byref(used)))
+        return out, used.value
+
+    def walk_pairs(self, seed, stream, start, steps, mode, w0, w1=0, cap=1 << 16):
+        walk = np.zeros(steps + 1, dtype=np.int64)
+        wl, npairs = i64(), i64()
+        pv = np.zeros(cap, dtype=np.int64)
+        pc = np.zeros(cap, dtype=np.int64)
+        check(lib().smore_walk_debug(self.h, seed, stream, start, steps, mode, w0, w1, _ptr(walk), C.byref(wl), _ptr(pv),
+                                     _ptr(pc), cap, C.byref(npairs)))
+        n = min(npairs.value, cap)
+        return walk[: wl.value], pv[:n], pc[:n]
+
+
+class Model:
+    """Embedding tables in HBM (smore_model_t) + the train entry points."""
+
+    def __init__(self, graph: Graph, dim, n_tables=2, dtype=F32):
+        self.graph = graph
+        self.dim, self.n_tables, self.dtype = dim, n_tables, dtype
+        self.h = vp()
+        check(lib().smore_model_create(graph.h, dim, n_tables, dtype, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().smore_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self, table, random=True, seed=1):
+        check(lib().smore_model_init(self.h, table, int(random), seed))
+
+    def set_rows(self, table, W, first=0):
+        if W.dtype == np.float32:
+            W = np.ascontiguousarray(W)
+            check(lib().smore_model_set_rows_f32(self.h, table, first, W.shape[0], _ptr(W)))
+        else:
+            W = np.ascontiguousarray(W, dtype=np.float64)
+            check(lib().smore_model_set_rows(self.h, table, first, W.shape[0], _ptr(W)))
+
+    def get_rows(self, table, first=0, n=None, dtype=np.float64, out=None):
+        n = self.graph.V - first if n is None else n
+        W = out if out is not None else np.zeros((n, self.dim), dtype=dtype)
+        fn = lib().smore_model_get_rows_f32 if W.dtype == np.float32 else lib().smore_model_get_rows
+        check(fn(self.h, table, first, n, _ptr(W)))
+        return W
+
+    def device_ptr(self, table):
+        p = vp()
+        check(lib().smore_model_device_ptr(self.h, table, C.byref(p)))
+        return p.value
+
+    def save_weights(self, path, table=0, fmt=0):
+        check(lib().smore_model_save_weights(self.h, table, os.fsencode(path), fmt))
+
+    def _train(self, fn, p):
+        check(fn(self.h, C.byref(p)))
+        return self.stats()
+
+    def train_line(self, p): return self._train(lib().smore_train_line, p)
+    def train_bpr(self, p): return self._train(lib().smore_train_bpr, p)
+    def train_warp(self, p): return self._train(lib().smore_train_warp, p)
+    def train_hoprec(self, p): return self._train(lib().smore_train_hoprec, p)
+    def train_deepwalk(self, p): return self._train(lib().smore_train_deepwalk, p)
+    def train_walklets(self, p): return self._train(lib().smore_train_walklets, p)
+
+    def stats(self):
+        s, pr, w0, ms, tr = u64(), u64(), u64(), f64(), f64()
+        check(lib().smore_train_stats(self.h, C.byref(s), C.byref(pr), C.byref(w0), C.byref(tr), C.byref(ms)))
+        return {"samples": s.value, "pair_updates": pr.value, "words_stream0": w0.value, "mean_tries": tr.value,
+                "kernel_ms": ms.value}

@@ -1,0 +1,282 @@
+// Device-side building blocks of the sampled-SGD hot path (sm_100a).
+//
+//   DrawRing   per-warp Philox sub-stream staged in shared memory (256-word ring, refilled 128 words at a time
+//              with one Philox block per lane), consumed strictly sequentially -> a warp is one reference "worker".
+//   samplers   alias draws with packed {u32 threshold, u32 alias} entries: integer-only, bit-exact with the
+//              reference's `random_gen(0,1) < prob` under the replayed stream (include/smore_b200.h).
+//   RowT       one embedding row spread over the 32 lanes as 128-bit (or narrower) vectors: coalesced
+//              ld.global.cg / st.global.cg, dot products by xor-shuffle butterflies.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "philox.cuh"
+
+namespace smore {
+
+constexpr int kMonitor = 10000;  // reference MONITOR (src/proNet.h:32)
+constexpr int kSigmoidTable = 1000;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Graph view
+// ---------------------------------------------------------------------------------------------------------------
+struct GraphDev {
+    int64_t V, E;
+    const int64_t* row_off;    // V+1
+    const int32_t* col;        // E
+    const uint2* vertex_at;    // V   {thr, alias}
+    const uint2* negative_at;  // V
+    const uint2* ctx_at;       // E   C++ semantics: per-vertex sub-tables, alias already a vertex id
+    const double* prefix;      // E   Go semantics: running sum of weights inside each vertex' slice
+    const int32_t* field;      // V   (HOP-Rec)
+    int sem;                   // SMORE_SEM_*
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-warp draw ring
+// ---------------------------------------------------------------------------------------------------------------
+struct DrawRing {
+    uint32_t* buf;  // 256 words of shared memory owned by this warp
+    uint64_t pos;   // next unread word (warp-uniform)
+    uint64_t base;  // words [base, base+256) are resident, base % 128 == 0
+    uint64_t seed, stream;
+    int lane;
+
+    __device__ __forceinline__ void fill_half(uint64_t first) {
+        U4 r = philox_block(seed, stream, (first >> 2) + (uint64_t)lane);
+        uint32_t slot = ((uint32_t)first & 255u) + 4u * (uint32_t)lane;
+        *reinterpret_cast<uint4*>(buf + slot) = make_uint4(r.x, r.y, r.z, r.w);
+    }
+    __device__ __forceinline__ void init(uint32_t* smem, uint64_t seed_, uint64_t stream_, uint64_t pos0, int lane_) {
+        buf = smem;
+        seed = seed_;
+        stream = stream_;
+        lane = lane_;
+        pos = pos0;
+        base = pos0 & ~127ull;
+        fill_half(base);
+        fill_half(base + 128);
+        __syncwarp();
+    }
+    // After ensure() at least 128 words starting at pos are resident.
+    __device__ __forceinline__ void ensure() {
+        while (pos >= base + 128) {
+            __syncwarp();
+            fill_half(base + 256);
+            base += 128;
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t i) const { return buf[((uint32_t)pos + i) & 255u]; }
+    __device__ __forceinline__ void advance(uint32_t n) { pos += n; }
+};
+
+__device__ __forceinline__ uint32_t index_draw(uint32_t k, uint32_t n) { return __umulhi(k, n); }
+
+__device__ __forceinline__ uint32_t alias_pick(const uint2* __restrict__ at, uint32_t idx, uint32_t kp) {
+    uint2 e = __ldg(at + idx);
+    return kp < e.x ? idx : e.y;
+}
+
+// SourceSample: C++ draws p then index (src/proNet.cpp:649-650); Go index then p (alias.go:99-100). 2 words.
+__device__ __forceinline__ uint32_t source_sample(const GraphDev& g, uint32_t w0, uint32_t w1) {
+    uint32_t kp = g.sem == 0 ? w0 : w1;
+    uint32_t ki = g.sem == 0 ? w1 : w0;
+    return alias_pick(g.vertex_at, index_draw(ki, (uint32_t)g.V), kp);
+}
+
+// NegativeSample: index then p in both trees (src/proNet.cpp:625-626; alias.go:99-100). 2 words.
+__device__ __forceinline__ uint32_t negative_sample(const GraphDev& g, uint32_t w0, uint32_t w1) {
+    return alias_pick(g.negative_at, index_draw(w0, (uint32_t)g.V), w1);
+}
+
+// TargetSample(v). C++ (src/proNet.cpp:671-683): p, then index into the vertex' alias slice: 2 words, O(1).
+// Go (pronet.go:257-284): one Float64, CDF scan with `r <= cum`: 1 word; here a binary search over the running sums
+// (same fp64 additions in the same order, so the same boundary decisions). Returns -1 on a sink (no words used).
+__device__ __forceinline__ int64_t target_sample(const GraphDev& g, int64_t v, uint32_t w0, uint32_t w1, int& used) {
+    int64_t off = __ldg(g.row_off + v);
+    int64_t br = __ldg(g.row_off + v + 1) - off;
+    if (br == 0) {
+        used = 0;
+        return -1;
+    }
+    if (g.sem == 0) {
+        used = 2;
+        int64_t j = off + (int64_t)index_draw(w1, (uint32_t)br);
+        uint2 e = __ldg(g.ctx_at + j);
+        return w0 < e.x ? (int64_t)__ldg(g.col + j) : (int64_t)e.y;
+    }
+    used = 1;
+    double total = __ldg(g.prefix + off + br - 1);
+    double r = __dmul_rn((double)w0 * (1.0 / 4294967296.0), total);
+    int64_t lo = 0, hi = br - 1;  // first e with r <= prefix[e]; falls back to the last neighbour
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (r <= __ldg(g.prefix + off + mid)) hi = mid;
+        else lo = mid + 1;
+    }
+    return (int64_t)__ldg(g.col + off + lo);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sigmoid LUT (src/proNet.cpp:52-71): 1001 entries over [-8, 8], truncating index, hard 0/1 outside.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T fast_sigmoid(const T* __restrict__ lut, T x);
+
+template <>
+__device__ __forceinline__ double fast_sigmoid<double>(const double* __restrict__ lut, double x) {
+    if (x < -8.0) return 0.0;
+    if (x > 8.0) return 1.0;
+    // (x + 8) * 1000 / 8 / 2 : the two divisions are exact (powers of two), so this is the reference's value
+    return lut[(int)(__dmul_rn(__dadd_rn(x, 8.0), 1000.0) * 0.0625)];
+}
+template <>
+__device__ __forceinline__ float fast_sigmoid<float>(const float* __restrict__ lut, float x) {
+    if (x < -8.0f) return 0.0f;
+    if (x > 8.0f) return 1.0f;
+    return lut[(int)(__fmul_rn(__fadd_rn(x, 8.0f), 1000.0f) * 0.0625f)];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rows
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+struct VecIO;
+template <>
+struct VecIO<float, 4> {
+    static __device__ __forceinline__ void ld(const float* p, float* x) {
+        float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* x) {
+        __stcg(reinterpret_cast<float4*>(p), make_float4(x[0], x[1], x[2], x[3]));
+    }
+};
+template <>
+struct VecIO<float, 2> {
+    static __device__ __forceinline__ void ld(const float* p, float* x) {
+        float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+        x[0] = v.x; x[1] = v.y;
+    }
+    static __device__ __forceinline__ void st(float* p, const float* x) {
+        __stcg(reinterpret_cast<float2*>(p), make_float2(x[0], x[1]));
+    }
+};
+template <>
+struct VecIO<float, 1> {
+    static __device__ __forceinline__ void ld(const float* p, float* x) { x[0] = __ldcg(p); }
+    static __device__ __forceinline__ void st(float* p, const float* x) { __stcg(p, x[0]); }
+};
+template <>
+struct VecIO<double, 2> {
+    static __device__ __forceinline__ void ld(const double* p, double* x) {
+        double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+        x[0] = v.x; x[1] = v.y;
+    }
+    static __device__ __forceinline__ void st(double* p, const double* x) {
+        __stcg(reinterpret_cast<double2*>(p), make_double2(x[0], x[1]));
+    }
+};
+template <>
+struct VecIO<double, 1> {
+    static __device__ __forceinline__ void ld(const double* p, double* x) { x[0] = __ldcg(p); }
+    static __device__ __forceinline__ void st(double* p, const double* x) { __stcg(p, x[0]); }
+};
+
+// Row layout over a warp: element index of lane l, chunk c, slot j = (c*32 + l)*VEC + j. A given element of ANY row is
+// always owned by the same lane, so in-place read-modify-write sequences on aliasing rows keep the reference's
+// per-element program order without fences.
+template <typename T_, int VEC_, int NCH_, bool MASKED_>
+struct RowCfg {
+    using T = T_;
+    static constexpr int VEC = VEC_;
+    static constexpr int NCH = NCH_;
+    static constexpr bool MASKED = MASKED_;  // dim not a multiple of 32*VEC (VEC == 1 then)
+    static constexpr int EPL = VEC_ * NCH_;
+};
+
+template <class C>
+struct Row {
+    typename C::T x[C::EPL];
+
+    __device__ __forceinline__ void load(const typename C::T* base, int lane, int dim) {
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c) {
+            int idx = (c * 32 + lane) * C::VEC;
+            if (!C::MASKED || idx < dim) VecIO<typename C::T, C::VEC>::ld(base + idx, x + c * C::VEC);
+            else {
+#pragma unroll
+                for (int j = 0; j < C::VEC; ++j) x[c * C::VEC + j] = 0;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(typename C::T* base, int lane, int dim) const {
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c) {
+            int idx = (c * 32 + lane) * C::VEC;
+            if (!C::MASKED || idx < dim) VecIO<typename C::T, C::VEC>::st(base + idx, x + c * C::VEC);
+        }
+    }
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) x[e] = 0;
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+template <class C>
+__device__ __forceinline__ typename C::T dot_partial(const Row<C>& a, const Row<C>& b) {
+    typename C::T s = 0;
+#pragma unroll
+    for (int e = 0; e < C::EPL; ++e) s += a.x[e] * b.x[e];
+    return s;
+}
+
+template <class C>
+__device__ __forceinline__ typename C::T dot(const Row<C>& a, const Row<C>& b) {
+    return warp_sum(dot_partial(a, b));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Learning-rate schedule. The reference refreshes alpha every MONITOR samples of a worker from a shared progress
+// counter (src/model/LINE.cpp:177-187; line.go:133-142). With W concurrent warps each warp estimates global progress
+// as count*W; tick t happens when count*W crosses t*MONITOR and sets
+//     alpha_t = max(alpha*1e-4, alpha * (1 - (t - lag)*MONITOR / total))
+// lag = 1 for the C++ LINE/BPR/WARP/HBPR loops (they read current_sample before bumping it), 0 for the C++ walk models
+// and every Go loop. W = 1 reproduces the reference's single-thread schedule exactly.
+// ---------------------------------------------------------------------------------------------------------------
+struct Sched {
+    double alpha0;
+    double total;  // as the reference converts it: (double)total
+    uint64_t W;
+    int lag;
+};
+
+struct WarpState {
+    uint64_t pos;        // stream position
+    uint64_t count;      // reference loop counter
+    uint64_t next_tick;  // count at which the next LR refresh happens
+    double alpha;        // current learning rate
+    uint64_t pairs;      // pair updates done (stats)
+    uint64_t tries;      // WARP: negatives scanned (stats)
+};
+
+__device__ __forceinline__ void sched_tick(WarpState& st, const Sched& s) {
+    if (st.count >= st.next_tick) {
+        uint64_t t = (st.count * s.W) / kMonitor;
+        double a = s.alpha0 * (1.0 - (double)((t - (uint64_t)s.lag) * kMonitor) / s.total);
+        double amin = s.alpha0 * 0.0001;
+        st.alpha = a < amin ? amin : a;
+        st.next_tick = ((t + 1) * kMonitor + s.W - 1) / s.W;
+    }
+}
+
+}  // namespace smore

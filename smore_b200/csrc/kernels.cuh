@@ -1,0 +1,522 @@
+// Hot-path kernels (sm_100a): warp-per-worker Hogwild SGD over embedding rows in HBM.
+//
+// One warp == one reference worker thread: it owns a Philox sub-stream, draws (source, target, negatives) from the
+// alias tables, gathers the 2+K rows with 128-bit loads, does dot / sigmoid-LUT / axpy in registers and scatters
+// the rows back. DETERMINISTIC mode is the same kernel with a single warp.
+//
+// Row aliasing: the reference updates rows in place and in order, so a sample whose rows repeat (negative == positive,
+// LINE-1 self pair, BPR pos == neg ...) sees its own earlier writes. Each update therefore has a FAST path (all rows
+// of the sample distinct: every gather is issued up front, maximum memory-level parallelism) and an ORDERED path
+// (some rows repeat: rows are re-read from memory in the reference's order; an element is always owned by the same
+// lane, so plain program order reproduces the reference's in-place semantics).
+#pragma once
+#include "device_core.cuh"
+
+namespace smore {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kBlockThreads = kWarpsPerBlock * 32;
+constexpr int kCtxChunk = 6;      // context rows gathered per batch (1 positive + 5 negatives = the default K)
+constexpr int kMaxWalkLen = 256;  // walk_steps + 1 <= kMaxWalkLen
+
+template <typename T>
+struct TrainArgs {
+    GraphDev g;
+    T* Wv;
+    T* Wc;
+    int dim;
+    int same_table;  // Wv == Wc
+    const T* lut;    // 1001-entry sigmoid table in global memory (copied to shared)
+    uint64_t seed, stream_base;
+    Sched sched;
+    WarpState* state;
+    int n_warps;
+    uint64_t jobs;  // loop trips per warp in this launch
+    int K;
+    int order;
+    T lambda;
+    // walk models
+    const int32_t* keys;  // start vertices of this launch (already shuffled / identity)
+    int64_t n_walks;      // walks in this launch; warp w takes walks w, w+W, ...
+    int steps, w0, w1, walklets;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// skip-gram pair update, C++ semantics: proNet::UpdatePair + Opt_SigmoidSGD (src/proNet.cpp:1784-1809, :1312-1330).
+// my_id: lane 0 holds the positive context, lane 1+n negative n; nrows = K+1 <= 32.
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T* Wc, int dim, bool same_table,
+                                                const typename C::T* lut, int64_t v1, int64_t my_id, int nrows,
+                                                typename C::T alpha, int lane) {
+    using T = typename C::T;
+    bool active = lane < nrows;
+    unsigned peers = __match_any_sync(kFull, active ? my_id : (int64_t)(-1 - lane));
+    bool dup = __any_sync(kFull, (active && __popc(peers) > 1) || (active && same_table && my_id == v1));
+    T* pv = Wv + v1 * dim;
+    if (!dup) {
+        Row<C> v, back;
+        v.load(pv, lane, dim);
+        back.zero();
+        for (int base = 0; base < nrows; base += kCtxChunk) {
+            Row<C> c[kCtxChunk];
+            int64_t ids[kCtxChunk];
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) {
+                ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
+                if (base + r < nrows) c[r].load(Wc + ids[r] * dim, lane, dim);
+            }
+            T f[kCtxChunk];
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) f[r] = (base + r < nrows) ? dot_partial(v, c[r]) : (T)0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int r = 0; r < kCtxChunk; ++r) f[r] += __shfl_xor_sync(kFull, f[r], o);
+            }
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) {
+                if (base + r < nrows) {
+                    T label = (base + r == 0) ? (T)1 : (T)0;
+                    T g = (label - fast_sigmoid<T>(lut, f[r])) * alpha;
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) {
+                        back.x[e] += g * c[r].x[e];
+                        c[r].x[e] += g * v.x[e];
+                    }
+                    c[r].store(Wc + ids[r] * dim, lane, dim);
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) v.x[e] += back.x[e];
+        v.store(pv, lane, dim);
+    } else {
+        Row<C> back;
+        back.zero();
+        for (int r = 0; r < nrows; ++r) {
+            int64_t cid = __shfl_sync(kFull, my_id, r);
+            T* pc = Wc + cid * dim;
+            Row<C> v, c;
+            v.load(pv, lane, dim);
+            c.load(pc, lane, dim);
+            T f = dot(v, c);
+            T label = (r == 0) ? (T)1 : (T)0;
+            T g = (label - fast_sigmoid<T>(lut, f)) * alpha;
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                back.x[e] += g * c.x[e];
+                c.x[e] += g * v.x[e];
+            }
+            c.store(pc, lane, dim);
+        }
+        Row<C> v;
+        v.load(pv, lane, dim);
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) v.x[e] += back.x[e];
+        v.store(pv, lane, dim);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// skip-gram pair update, Go semantics: ProNet.UpdatePair + sgdUpdate (pkg/pronet/optimizer.go:21-84) and, with
+// skip_source, LINE.updateFirstOrder (internal/models/line/line.go:153-200). Negatives equal to the context (or the
+// source) are skipped; the positive context row is written last.
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T* Wc, int dim, bool same_table,
+                                               bool skip_source, const typename C::T* lut, int64_t v1, int64_t my_id,
+                                               int nrows, typename C::T alpha, int lane) {
+    using T = typename C::T;
+    int64_t ctx = __shfl_sync(kFull, my_id, 0);
+    bool active = lane < nrows;
+    bool skipped = active && lane > 0 && (my_id == ctx || (skip_source && my_id == v1));
+    unsigned skipmask = __ballot_sync(kFull, skipped);
+    bool live = active && !skipped;
+    unsigned peers = __match_any_sync(kFull, live ? my_id : (int64_t)(-1 - lane));
+    bool dup = __any_sync(kFull, (live && __popc(peers) > 1) || (live && same_table && my_id == v1));
+    T* pv = Wv + v1 * dim;
+    T* pp = Wc + ctx * dim;
+    if (!dup) {
+        Row<C> v, vgrad, pos, cgrad;
+        v.load(pv, lane, dim);
+        pos.load(pp, lane, dim);
+        {
+            T g = alpha * ((T)1 - fast_sigmoid<T>(lut, dot(v, pos)));
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                vgrad.x[e] = g * pos.x[e];
+                cgrad.x[e] = g * v.x[e];
+            }
+        }
+        for (int base = 1; base < nrows; base += kCtxChunk) {
+            Row<C> c[kCtxChunk];
+            int64_t ids[kCtxChunk];
+            bool ok[kCtxChunk];
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) {
+                ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
+                ok[r] = (base + r < nrows) && !((skipmask >> ((base + r) & 31)) & 1u);
+                if (ok[r]) c[r].load(Wc + ids[r] * dim, lane, dim);
+            }
+            T f[kCtxChunk];
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) f[r] = ok[r] ? dot_partial(v, c[r]) : (T)0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int r = 0; r < kCtxChunk; ++r) f[r] += __shfl_xor_sync(kFull, f[r], o);
+            }
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) {
+                if (ok[r]) {
+                    T g = alpha * ((T)0 - fast_sigmoid<T>(lut, f[r]));
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) {
+                        vgrad.x[e] += g * c[r].x[e];
+                        c[r].x[e] += g * v.x[e];
+                    }
+                    c[r].store(Wc + ids[r] * dim, lane, dim);
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) {
+            v.x[e] += vgrad.x[e];
+            pos.x[e] += cgrad.x[e];
+        }
+        v.store(pv, lane, dim);
+        pos.store(pp, lane, dim);
+    } else {
+        Row<C> vgrad, cgrad;
+        {
+            Row<C> v, pos;
+            v.load(pv, lane, dim);
+            pos.load(pp, lane, dim);
+            T g = alpha * ((T)1 - fast_sigmoid<T>(lut, dot(v, pos)));
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                vgrad.x[e] = g * pos.x[e];
+                cgrad.x[e] = g * v.x[e];
+            }
+        }
+        for (int r = 1; r < nrows; ++r) {
+            if ((skipmask >> r) & 1u) continue;
+            int64_t cid = __shfl_sync(kFull, my_id, r);
+            T* pc = Wc + cid * dim;
+            Row<C> v, c;
+            v.load(pv, lane, dim);
+            c.load(pc, lane, dim);
+            T g = alpha * ((T)0 - fast_sigmoid<T>(lut, dot(v, c)));
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                vgrad.x[e] += g * c.x[e];
+                c.x[e] += g * v.x[e];
+            }
+            c.store(pc, lane, dim);
+        }
+        // per element: vertex row first, then context row (optimizer.go:54-57), through memory so that
+        // a self pair on a shared table accumulates both.
+        Row<C> v;
+        v.load(pv, lane, dim);
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) v.x[e] += vgrad.x[e];
+        v.store(pv, lane, dim);
+        Row<C> pos;
+        pos.load(pp, lane, dim);
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) pos.x[e] += cgrad.x[e];
+        pos.store(pp, lane, dim);
+    }
+}
+
+// Draw the K negatives of one pair from ring words [off, off+2K) into lanes 1..K; lane 0 keeps `ctx`.
+__device__ __forceinline__ int64_t draw_pair_ids(const GraphDev& g, const DrawRing& ring, uint32_t off, int64_t ctx,
+                                                 int K, int lane) {
+    int64_t my = ctx;
+    if (lane >= 1 && lane <= K) {
+        uint32_t w0 = ring.peek(off + 2u * (uint32_t)(lane - 1));
+        uint32_t w1 = ring.peek(off + 2u * (uint32_t)(lane - 1) + 1u);
+        my = (int64_t)negative_sample(g, w0, w1);
+    }
+    return my;
+}
+
+template <typename T>
+__device__ __forceinline__ const T* stage_lut(const T* lut_global, T* lut_shared) {
+    for (int i = threadIdx.x; i <= kSigmoidTable; i += blockDim.x) lut_shared[i] = lut_global[i];
+    __syncthreads();
+    return lut_shared;
+}
+
+// Shared memory layout of every training kernel: [kWarpsPerBlock][256] u32 draw rings, then the LUT, then
+// (walk kernels) per-warp walk buffers.
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+// ---------------------------------------------------------------------------------------------------------------
+// LINE: LINE::Train (src/model/LINE.cpp:100-195) / LINE.Train (internal/models/line/line.go:73-150)
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_line(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
+    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
+    const T* lut = stage_lut<T>(a.lut, lut_s);
+    int lane = threadIdx.x & 31;
+    int wib = threadIdx.x >> 5;
+    int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    DrawRing ring;
+    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
+    const GraphDev& g = a.g;
+    const bool go = g.sem != 0;
+    const uint32_t neg_off = go ? 3u : 4u;
+    const int nrows = a.K + 1;
+    for (uint64_t it = 0; it < a.jobs; ++it) {
+        ring.ensure();
+        // negatives first (independent loads), then the dependent source -> target chain on lane 0
+        int64_t my = draw_pair_ids(g, ring, neg_off, -1, a.K, lane);
+        int64_t v1 = -1, v2 = -1;
+        int used = 0;
+        if (lane == 0) {
+            v1 = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
+            int u;
+            v2 = target_sample(g, v1, ring.peek(2), ring.peek(3), u);
+            used = 2 + u;
+        }
+        v1 = __shfl_sync(kFull, v1, 0);
+        v2 = __shfl_sync(kFull, v2, 0);
+        used = __shfl_sync(kFull, used, 0);
+        if (v2 < 0) {  // sink source: Go skips the sample without counting it (line.go:121-124); C++ never draws one
+            ring.advance((uint32_t)used);
+            continue;
+        }
+        ring.advance(neg_off + 2u * (uint32_t)a.K);
+        if (lane == 0) my = v2;
+        T alpha = (T)st.alpha;
+        if (!go) update_pair_cpp<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, lut, v1, my, nrows, alpha, lane);
+        else update_pair_go<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, a.order == 1, lut, v1, my, nrows, alpha, lane);
+        st.count++;
+        st.pairs++;
+        sched_tick(st, a.sched);
+    }
+    st.pos = ring.pos;
+    if (lane == 0) a.state[w] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// On-device walks: RandomWalk (src/proNet.cpp:704-724 / pronet.go:292-307). Lane 0 walks; ids go to shared memory.
+// Returns the walk length (warp-uniform).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int random_walk(const GraphDev& g, DrawRing& ring, int64_t start, int steps, int32_t* walk,
+                                           int lane) {
+    int len = 1;
+    if (lane == 0) walk[0] = (int32_t)start;
+    int64_t next = start;
+    const bool go = g.sem != 0;
+    for (int s0 = 0; s0 < steps; s0 += 32) {  // <= 64 words per batch of 32 steps: one ensure() covers it
+        ring.ensure();
+        int nb = min(32, steps - s0);
+        uint32_t used = 0;
+        int stop = 0;
+        if (lane == 0) {
+            for (int s = 0; s < nb; ++s) {
+                if (!go) {
+                    int64_t br = __ldg(g.row_off + next + 1) - __ldg(g.row_off + next);
+                    if (br == 0) {
+                        if (next == start) { stop = 1; break; }
+                        next = start;
+                    }
+                }
+                int u;
+                int64_t n = target_sample(g, next, ring.peek(used), ring.peek(used + 1), u);
+                if (n < 0) { stop = 1; break; }  // Go: dead end stops the walk
+                used += (uint32_t)u;
+                walk[len++] = (int32_t)n;
+                next = n;
+            }
+        }
+        used = __shfl_sync(kFull, used, 0);
+        stop = __shfl_sync(kFull, stop, 0);
+        next = __shfl_sync(kFull, next, 0);
+        len = __shfl_sync(kFull, len, 0);
+        ring.advance(used);
+        if (stop) break;
+    }
+    __syncwarp();
+    return len;
+}
+
+// SkipGrams' per-centre window draw (src/proNet.cpp:783): reduce[i] = index(window)+1, one word per position.
+__device__ __forceinline__ void draw_windows(DrawRing& ring, int len, int window, uint8_t* reduce, int lane) {
+    for (int i0 = 0; i0 < len; i0 += 128) {
+        ring.ensure();
+        int nb = min(128, len - i0);
+        for (int i = lane; i < nb; i += 32) reduce[i0 + i] = (uint8_t)(index_draw(ring.peek((uint32_t)i), (uint32_t)window) + 1u);
+        ring.advance((uint32_t)nb);
+    }
+    __syncwarp();
+}
+
+// DeepWalk / Walklets: DeepWalk::Train (src/model/DeepWalk.cpp:133-150), Walklets::Train (Walklets.cpp:42-60),
+// DeepWalk.Train (deepwalk.go:110-134). One warp per walk; pairs are enumerated in-warp and never touch HBM.
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_walk(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
+    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
+    int32_t* walks = reinterpret_cast<int32_t*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t) + 1008 * sizeof(T));
+    uint8_t* reduces = reinterpret_cast<uint8_t*>(walks + kWarpsPerBlock * kMaxWalkLen);
+    const T* lut = stage_lut<T>(a.lut, lut_s);
+    int lane = threadIdx.x & 31;
+    int wib = threadIdx.x >> 5;
+    int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    int32_t* walk = walks + wib * kMaxWalkLen;
+    uint8_t* reduce = reduces + wib * kMaxWalkLen;
+    WarpState st = a.state[w];
+    DrawRing ring;
+    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
+    const GraphDev& g = a.g;
+    const bool go = g.sem != 0;
+    const int nrows = a.K + 1;
+    for (int64_t wi = w; wi < a.n_walks; wi += a.n_warps) {
+        int64_t start = (int64_t)__ldg(a.keys + wi);
+        int len = random_walk(g, ring, start, a.steps, walk, lane);
+        if (!go && !a.walklets) draw_windows(ring, len, a.w1, reduce, lane);
+        T alpha = (T)st.alpha;
+        for (int i = 0; i < len; ++i) {
+            int64_t vi = walk[i];
+            // the (up to two) index ranges of contexts for centre i
+            int lo[2], hi[2];
+            if (a.walklets) {  // ScaleSkipGrams (src/proNet.cpp:939-978)
+                lo[0] = max(i - a.w1, 0); hi[0] = max(i - a.w0, 0);
+                lo[1] = min(i + a.w0, len - 1); hi[1] = min(i + a.w1, len - 1);
+            } else if (!go) {  // SkipGrams (src/proNet.cpp:781-801)
+                int r = reduce[i];
+                lo[0] = max(i - r, 0); hi[0] = min(i + r, len - 1);
+                lo[1] = 1; hi[1] = 0;
+            } else {  // pronet.go:314-329
+                lo[0] = max(i - a.w1, 0); hi[0] = min(i + a.w1 + 1, len) - 1;
+                lo[1] = 1; hi[1] = 0;
+            }
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                for (int j = lo[part]; j <= hi[part]; ++j) {
+                    if (j == i) continue;
+                    ring.ensure();
+                    int64_t my = draw_pair_ids(g, ring, 0u, (int64_t)walk[j], a.K, lane);
+                    ring.advance(2u * (uint32_t)a.K);
+                    if (!go) update_pair_cpp<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, lut, vi, my, nrows, alpha, lane);
+                    else update_pair_go<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, false, lut, vi, my, nrows, alpha, lane);
+                    st.pairs++;
+                }
+            }
+        }
+        st.count++;
+        sched_tick(st, a.sched);
+        __syncwarp();
+    }
+    st.pos = ring.pos;
+    if (lane == 0) a.state[w] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Parity hooks
+// ---------------------------------------------------------------------------------------------------------------
+// One warp replays n sampler calls on stream (seed, stream). which: 0 source, 1 negative, 2 target(arg), 3 source+target.
+__global__ void k_sample_debug(GraphDev g, int which, uint64_t seed, uint64_t stream, int64_t n, const int64_t* arg,
+                               int64_t* out, uint64_t* words_used) {
+    __shared__ __align__(16) uint32_t ringbuf[256];
+    int lane = threadIdx.x;
+    DrawRing ring;
+    ring.init(ringbuf, seed, stream, 0, lane);
+    for (int64_t i = 0; i < n; ++i) {
+        ring.ensure();
+        int64_t r0 = -1, r1 = -1;
+        uint32_t used = 0;
+        if (lane == 0) {
+            if (which == 0) { r0 = source_sample(g, ring.peek(0), ring.peek(1)); used = 2; }
+            else if (which == 1) { r0 = negative_sample(g, ring.peek(0), ring.peek(1)); used = 2; }
+            else if (which == 2) { int u; r0 = target_sample(g, arg[i], ring.peek(0), ring.peek(1), u); used = u; }
+            else {
+                r0 = source_sample(g, ring.peek(0), ring.peek(1));
+                int u;
+                r1 = target_sample(g, r0, ring.peek(2), ring.peek(3), u);
+                used = 2 + u;
+            }
+            if (which == 3) { out[2 * i] = r0; out[2 * i + 1] = r1; }
+            else out[i] = r0;
+        }
+        used = __shfl_sync(kFull, used, 0);
+        ring.advance(used);
+    }
+    if (lane == 0 && words_used) *words_used = ring.pos;
+}
+
+// One warp: RandomWalk + pair enumeration exactly as k_walk does it, pairs written out instead of applied.
+__global__ void k_walk_debug(GraphDev g, uint64_t seed, uint64_t stream, int64_t start, int steps, int mode, int w0,
+                             int w1, int64_t* walk_out, int64_t* walk_len, int64_t* pv, int64_t* pc, int64_t cap,
+                             int64_t* n_pairs) {
+    __shared__ __align__(16) uint32_t ringbuf[256];
+    __shared__ int32_t walk[kMaxWalkLen];
+    __shared__ uint8_t reduce[kMaxWalkLen];
+    int lane = threadIdx.x;
+    DrawRing ring;
+    ring.init(ringbuf, seed, stream, 0, lane);
+    int len = random_walk(g, ring, start, steps, walk, lane);
+    const bool go = g.sem != 0;
+    if (!go && mode == 0) draw_windows(ring, len, w0, reduce, lane);
+    if (lane == 0) {
+        *walk_len = len;
+        for (int i = 0; i < len; ++i) walk_out[i] = walk[i];
+        int64_t np = 0;
+        for (int i = 0; i < len; ++i) {
+            int lo[2], hi[2];
+            if (mode == 1) {
+                lo[0] = max(i - w1, 0); hi[0] = max(i - w0, 0);
+                lo[1] = min(i + w0, len - 1); hi[1] = min(i + w1, len - 1);
+            } else if (!go) {
+                int r = reduce[i];
+                lo[0] = max(i - r, 0); hi[0] = min(i + r, len - 1);
+                lo[1] = 1; hi[1] = 0;
+            } else {
+                lo[0] = max(i - w0, 0); hi[0] = min(i + w0 + 1, len) - 1;
+                lo[1] = 1; hi[1] = 0;
+            }
+            for (int part = 0; part < 2; ++part)
+                for (int j = lo[part]; j <= hi[part]; ++j) {
+                    if (j == i) continue;
+                    if (np < cap) { pv[np] = walk[i]; pc[np] = walk[j]; }
+                    ++np;
+                }
+        }
+        *n_pairs = np;
+    }
+}
+
+// Table init: (U - 0.5) / dim, U = k * 2^-32, k = word e of stream (seed, kInitStreamBase + table) for element e.
+template <typename T>
+__global__ void k_init_table(T* W, int64_t n_elems, int dim, uint64_t seed, uint64_t stream, int random) {
+    int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one Philox block (4 elements) per thread
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; blk * 4 < n_elems; blk += stride) {
+        U4 r = philox_block(seed, stream, (uint64_t)blk);
+        uint32_t k[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t e = blk * 4 + j;
+            if (e < n_elems) W[e] = random ? (T)(((double)k[j] * (1.0 / 4294967296.0) - 0.5) / (double)dim) : (T)0;
+        }
+    }
+}
+
+template <typename TD, typename TS>
+__global__ void k_convert(TD* dst, const TS* src, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = (TD)src[i];
+}
+
+}  // namespace smore

@@ -1,0 +1,548 @@
+// Pairwise-ranking kernels: BPR (Go and C++ variants), WARP, HOP-Rec. Same warp-per-worker scheme as kernels.cuh.
+//
+// Every variant first resolves ALL the draws of a sample (they depend on the alias tables / field array only, never on
+// the embeddings), then gathers every row it will touch in one batch (FAST path, rows distinct) or replays the
+// reference's in-place order through memory (ORDERED path, some rows coincide).
+#pragma once
+#include "kernels.cuh"
+
+namespace smore {
+
+enum RankKind { RANK_BPR = 0, RANK_WARP = 1, RANK_HOPREC = 2 };
+
+template <typename T>
+__device__ __forceinline__ T ldv(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
+template <typename T>
+__device__ __forceinline__ void stv(T* p, T v) { *reinterpret_cast<volatile T*>(p) = v; }
+
+// Calls f(e, idx) for every element this lane owns: e = register slot, idx = element index inside the row.
+template <class C, class F>
+__device__ __forceinline__ void for_owned(int lane, int dim, F&& f) {
+#pragma unroll
+    for (int c = 0; c < C::NCH; ++c) {
+#pragma unroll
+        for (int j = 0; j < C::VEC; ++j) {
+            int idx = (c * 32 + lane) * C::VEC + j;
+            if (!C::MASKED || idx < dim) f(c * C::VEC + j, idx);
+        }
+    }
+}
+
+// Lane-parallel rejection sampling: attempt t uses ring words [t*wpa, (t+1)*wpa). `draw(w0, w1)` proposes a vertex,
+// `ok(v)` accepts. Consumes exactly the words the sequential reference loop would. wpa in {1, 2}.
+template <class Draw, class Ok>
+__device__ __forceinline__ int64_t reject_sample(DrawRing& ring, int lane, uint32_t wpa, Draw&& draw, Ok&& ok) {
+    for (;;) {
+        ring.ensure();
+        uint32_t w0 = ring.peek((uint32_t)lane * wpa);
+        uint32_t w1 = ring.peek((uint32_t)lane * wpa + (wpa - 1u));
+        int64_t cand = draw(w0, w1);
+        unsigned acc = __ballot_sync(kFull, ok(cand));
+        if (acc) {
+            int first = __ffs(acc) - 1;
+            ring.advance((uint32_t)(first + 1) * wpa);
+            return __shfl_sync(kFull, cand, first);
+        }
+        ring.advance(32u * wpa);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Go BPR: BPR.Train (internal/models/bpr/bpr.go:84-131) + UpdateBPRPair (pkg/pronet/optimizer.go:87-117).
+// Words per sample: source (idx, p), target (1), negative (idx, p).
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_bpr_go(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
+    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
+    const T* lut = stage_lut<T>(a.lut, lut_s);
+    int lane = threadIdx.x & 31;
+    int wib = threadIdx.x >> 5;
+    int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    DrawRing ring;
+    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
+    const GraphDev& g = a.g;
+    const int dim = a.dim;
+    for (uint64_t it = 0; it < a.jobs; ++it) {
+        ring.ensure();
+        int64_t neg = -1, user = -1, pos = -1;
+        int used = 0;
+        if (lane == 1) neg = (int64_t)negative_sample(g, ring.peek(3), ring.peek(4));
+        if (lane == 0) {
+            user = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
+            int u;
+            pos = target_sample(g, user, ring.peek(2), 0u, u);
+            used = 2 + u;
+        }
+        user = __shfl_sync(kFull, user, 0);
+        pos = __shfl_sync(kFull, pos, 0);
+        neg = __shfl_sync(kFull, neg, 1);
+        used = __shfl_sync(kFull, used, 0);
+        if (pos < 0) {
+            ring.advance((uint32_t)used);
+            continue;
+        }
+        ring.advance(5u);
+        const T alpha = (T)st.alpha;
+        const T la = a.lambda * alpha;  // lambda*alpha*w evaluates left to right
+        T* pv = a.Wv + user * dim;
+        T* pp = a.Wc + pos * dim;
+        T* pn = a.Wc + neg * dim;
+        const bool same = pos == neg;
+        const bool valias = a.same_table && (user == pos || user == neg);
+        if (!valias) {
+            Row<C> v, p, n;
+            v.load(pv, lane, dim);
+            p.load(pp, lane, dim);
+            n.load(pn, lane, dim);
+            T ps = dot_partial(v, p), ns = dot_partial(v, n);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ps += __shfl_xor_sync(kFull, ps, o);
+                ns += __shfl_xor_sync(kFull, ns, o);
+            }
+            const T gc = alpha * fast_sigmoid<T>(lut, ns - ps);
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                T vg = gc * (p.x[e] - n.x[e]);
+                T pg = gc * v.x[e];
+                T ng = -gc * v.x[e];
+                v.x[e] += vg - la * v.x[e];
+                p.x[e] += pg - la * p.x[e];
+                T ncur = same ? p.x[e] : n.x[e];  // pos == neg: the second write lands on the already-updated row
+                n.x[e] = ncur + (ng - la * ncur);
+            }
+            v.store(pv, lane, dim);
+            if (!same) p.store(pp, lane, dim);
+            n.store(pn, lane, dim);
+        } else {
+            // single shared table with the user row coinciding with an item row: replay through memory
+            Row<C> v, p, n;
+            v.load(pv, lane, dim);
+            p.load(pp, lane, dim);
+            n.load(pn, lane, dim);
+            const T gc = alpha * fast_sigmoid<T>(lut, dot(v, n) - dot(v, p));
+            for_owned<C>(lane, dim, [&](int, int idx) {
+                T vg = gc * (ldv(pp + idx) - ldv(pn + idx));
+                T pg = gc * ldv(pv + idx);
+                T ng = -gc * ldv(pv + idx);
+                stv(pv + idx, ldv(pv + idx) + (vg - la * ldv(pv + idx)));
+                stv(pp + idx, ldv(pp + idx) + (pg - la * ldv(pp + idx)));
+                stv(pn + idx, ldv(pn + idx) + (ng - la * ldv(pn + idx)));
+            });
+        }
+        st.count++;
+        st.pairs++;
+        sched_tick(st, a.sched);
+    }
+    st.pos = ring.pos;
+    if (lane == 0) a.state[w] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One BPR-style round shared by the C++ ranking updates, ORDERED flavour (rows re-read from memory, per-element
+// writes in the reference's order: src/proNet.cpp:1426-1440 / :1485-1504 / :1371-1391).
+// Returns false if the round was margin-gated away. verr accumulates in registers (it is a local vector in the
+// reference too).
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ bool ordered_round(typename C::T* pv, typename C::T* pi, typename C::T* pj, int dim, int lane,
+                                              const typename C::T* lut, typename C::T alpha, bool gated,
+                                              typename C::T margin, Row<C>& verr) {
+    using T = typename C::T;
+    Row<C> v, ri, rj, cvec;
+    v.load(pv, lane, dim);
+    ri.load(pi, lane, dim);
+    rj.load(pj, lane, dim);
+#pragma unroll
+    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = ri.x[e] - rj.x[e];
+    T f = dot(v, cvec);
+    if (gated && f > margin) return false;
+    const T g = fast_sigmoid<T>(lut, (T)0 - f) * alpha;
+    const T c = alpha * (T)0.0025;
+    for_owned<C>(lane, dim, [&](int e, int idx) {
+        verr.x[e] += g * cvec.x[e];
+        const T cerr = g * v.x[e];
+        stv(pi + idx, ldv(pi + idx) - c * ldv(pi + idx));
+        stv(pj + idx, ldv(pj + idx) - c * ldv(pj + idx));
+        stv(pi + idx, ldv(pi + idx) + cerr);
+        stv(pj + idx, ldv(pj + idx) - cerr);
+    });
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C++ BPR: BPR::Train (src/model/BPR.cpp:85-103) + UpdateBPRPair (src/proNet.cpp:1406-1455): 5 rounds, the first
+// with the caller's negative. 14 words per sample: source (p, idx), target (p, idx), 5 x negative (idx, p).
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_bpr_cpp(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
+    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
+    const T* lut = stage_lut<T>(a.lut, lut_s);
+    int lane = threadIdx.x & 31;
+    int wib = threadIdx.x >> 5;
+    int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    DrawRing ring;
+    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
+    const GraphDev& g = a.g;
+    const int dim = a.dim;
+    T* W = a.Wv;
+    for (uint64_t it = 0; it < a.jobs; ++it) {
+        ring.ensure();
+        // lanes 2..6 hold the 5 negatives, lane 0 the user, lane 1 the positive item
+        int64_t my = -1 - lane;
+        if (lane >= 2 && lane < 7) my = (int64_t)negative_sample(g, ring.peek(4u + 2u * (uint32_t)(lane - 2)), ring.peek(5u + 2u * (uint32_t)(lane - 2)));
+        int64_t v1 = -1, v2 = -1;
+        if (lane == 0) {
+            v1 = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
+            int u;
+            v2 = target_sample(g, v1, ring.peek(2), ring.peek(3), u);
+        }
+        v1 = __shfl_sync(kFull, v1, 0);
+        v2 = __shfl_sync(kFull, v2, 0);
+        ring.advance(14u);
+        if (v2 < 0) continue;  // never drawn by the reference (sources have out-degree > 0)
+        if (lane == 0) my = v1;
+        if (lane == 1) my = v2;
+        const T alpha = (T)st.alpha;
+        const T c = alpha * (T)0.0025;
+        unsigned peers = __match_any_sync(kFull, my);
+        bool dup = __any_sync(kFull, lane < 7 && __popc(peers) > 1);
+        T* pv = W + v1 * dim;
+        T* pi = W + v2 * dim;
+        if (!dup) {
+            Row<C> v, ri, rj[5], verr;
+            int64_t jid[5];
+            v.load(pv, lane, dim);
+            ri.load(pi, lane, dim);
+#pragma unroll
+            for (int n = 0; n < 5; ++n) {
+                jid[n] = __shfl_sync(kFull, my, 2 + n);
+                rj[n].load(W + jid[n] * dim, lane, dim);
+            }
+            verr.zero();
+#pragma unroll
+            for (int n = 0; n < 5; ++n) {
+                Row<C> cvec;
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) cvec.x[e] = ri.x[e] - rj[n].x[e];
+                const T f = dot(v, cvec);
+                const T gg = fast_sigmoid<T>(lut, (T)0 - f) * alpha;
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) {
+                    verr.x[e] += gg * cvec.x[e];
+                    const T cerr = gg * v.x[e];
+                    ri.x[e] -= c * ri.x[e];
+                    rj[n].x[e] -= c * rj[n].x[e];
+                    ri.x[e] += cerr;
+                    rj[n].x[e] -= cerr;
+                }
+                rj[n].store(W + jid[n] * dim, lane, dim);
+            }
+            const T cv = alpha * (T)0.025;
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                v.x[e] -= cv * v.x[e];
+                v.x[e] += verr.x[e];
+            }
+            ri.store(pi, lane, dim);
+            v.store(pv, lane, dim);
+        } else {
+            Row<C> verr;
+            verr.zero();
+            for (int n = 0; n < 5; ++n) {
+                int64_t j = __shfl_sync(kFull, my, 2 + n);
+                ordered_round<C>(pv, pi, W + j * dim, dim, lane, lut, alpha, false, (T)0, verr);
+            }
+            const T cv = alpha * (T)0.025;
+            for_owned<C>(lane, dim, [&](int e, int idx) {
+                stv(pv + idx, ldv(pv + idx) - cv * ldv(pv + idx));
+                stv(pv + idx, ldv(pv + idx) + verr.x[e]);
+            });
+        }
+        st.count++;
+        st.pairs += 5;
+        sched_tick(st, a.sched);
+    }
+    st.pos = ring.pos;
+    if (lane == 0) a.state[w] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// WARP: WARP::Train (src/model/WARP.cpp:85-103) + UpdateWARPPair (src/proNet.cpp:1353-1403): scan up to 32
+// negatives, first one with margin f < 1 triggers a single BPR step on three rows. Words: source (p, idx),
+// target (p, idx), negative (idx, p), then (idx, p) per further negative actually scanned.
+// Candidates are evaluated in batches of kWarpBatch rows gathered together; rows do not change before the (single)
+// update, so speculative gathers beyond the first violator are exact, only wasted.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWarpBatch = 4;
+
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_warp(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
+    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
+    const T* lut = stage_lut<T>(a.lut, lut_s);
+    int lane = threadIdx.x & 31;
+    int wib = threadIdx.x >> 5;
+    int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    DrawRing ring;
+    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
+    const GraphDev& g = a.g;
+    const int dim = a.dim;
+    T* W = a.Wv;
+    for (uint64_t it = 0; it < a.jobs; ++it) {
+        ring.ensure();
+        int64_t v1 = -1, v2 = -1;
+        if (lane == 0) {
+            v1 = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
+            int u;
+            v2 = target_sample(g, v1, ring.peek(2), ring.peek(3), u);
+        }
+        v1 = __shfl_sync(kFull, v1, 0);
+        v2 = __shfl_sync(kFull, v2, 0);
+        if (v2 < 0) {
+            ring.advance(6u);
+            continue;
+        }
+        const T alpha = (T)st.alpha;
+        T* pv = W + v1 * dim;
+        T* pi = W + v2 * dim;
+        Row<C> v, ri;
+        v.load(pv, lane, dim);
+        ri.load(pi, lane, dim);
+        int scanned = 0;  // negatives evaluated so far
+        bool hit = false;
+        // candidate n lives at ring words 4+2n, 5+2n
+        for (int base = 0; base < 32 && !hit; base += (base == 0 ? 1 : kWarpBatch)) {
+            const int nb = base == 0 ? 1 : min(kWarpBatch, 32 - base);
+            int64_t cand = -1;
+            if (lane < nb) cand = (int64_t)negative_sample(g, ring.peek(4u + 2u * (uint32_t)(base + lane)), ring.peek(5u + 2u * (uint32_t)(base + lane)));
+            Row<C> rj[kWarpBatch];
+            int64_t jid[kWarpBatch];
+            T f[kWarpBatch];
+#pragma unroll
+            for (int r = 0; r < kWarpBatch; ++r) {
+                jid[r] = __shfl_sync(kFull, cand, r);
+                if (r < nb) rj[r].load(W + jid[r] * dim, lane, dim);
+            }
+#pragma unroll
+            for (int r = 0; r < kWarpBatch; ++r) {
+                T s = 0;
+                if (r < nb) {
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) s += v.x[e] * (ri.x[e] - rj[r].x[e]);
+                }
+                f[r] = s;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int r = 0; r < kWarpBatch; ++r) f[r] += __shfl_xor_sync(kFull, f[r], o);
+            }
+#pragma unroll
+            for (int r = 0; r < kWarpBatch; ++r) {
+                if (r < nb && !hit) {
+                    ++scanned;
+                    if (f[r] < (T)1) {
+                        hit = true;
+                        const int64_t j = jid[r];
+                        T* pj = W + j * dim;
+                        const T c = alpha * (T)0.0025;
+                        if (j != v2 && j != v1 && v1 != v2) {
+                            const T gg = fast_sigmoid<T>(lut, (T)0 - f[r]) * alpha;
+#pragma unroll
+                            for (int e = 0; e < C::EPL; ++e) {
+                                const T cvec = ri.x[e] - rj[r].x[e];
+                                const T verr = gg * cvec;
+                                const T cerr = gg * v.x[e];
+                                ri.x[e] -= c * ri.x[e];
+                                rj[r].x[e] -= c * rj[r].x[e];
+                                v.x[e] -= c * v.x[e];
+                                ri.x[e] += cerr;
+                                rj[r].x[e] -= cerr;
+                                v.x[e] += verr;
+                            }
+                            ri.store(pi, lane, dim);
+                            rj[r].store(pj, lane, dim);
+                            v.store(pv, lane, dim);
+                        } else {
+                            // coinciding rows: the reference's per-element order through memory (proNet.cpp:1380-1391).
+                            // Opt_BPRSGD recomputes f from the same (unchanged) rows, so f[r] is its value.
+                            const T gg = fast_sigmoid<T>(lut, (T)0 - f[r]) * alpha;
+                            for_owned<C>(lane, dim, [&](int e, int idx) {
+                                const T cvec = ri.x[e] - rj[r].x[e];
+                                const T verr = gg * cvec;
+                                const T cerr = gg * v.x[e];
+                                stv(pi + idx, ldv(pi + idx) - c * ldv(pi + idx));
+                                stv(pj + idx, ldv(pj + idx) - c * ldv(pj + idx));
+                                stv(pv + idx, ldv(pv + idx) - c * ldv(pv + idx));
+                                stv(pi + idx, ldv(pi + idx) + cerr);
+                                stv(pj + idx, ldv(pj + idx) - cerr);
+                                stv(pv + idx, ldv(pv + idx) + verr);
+                            });
+                        }
+                    }
+                }
+            }
+        }
+        ring.advance(4u + 2u * (uint32_t)scanned);
+        st.count++;
+        st.pairs++;
+        st.tries += (uint64_t)scanned;
+        sched_tick(st, a.sched);
+    }
+    st.pos = ring.pos;
+    if (lane == 0) a.state[w] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// HOP-Rec: HBPR::Train (src/model/HBPR.cpp:93-126) + UpdateFBPRPair (src/proNet.cpp:1458-1515).
+// Per sampled user: for hop w = 1..walk_steps: item at hop w, field-matched negative, 5 margin-gated BPR rounds
+// (rounds > 0 draw UNIFORM negatives with field rejection), learning rate alpha/w, margin 1/w.
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_hoprec(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
+    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
+    const T* lut = stage_lut<T>(a.lut, lut_s);
+    int lane = threadIdx.x & 31;
+    int wib = threadIdx.x >> 5;
+    int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    DrawRing ring;
+    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
+    const GraphDev& g = a.g;
+    const int dim = a.dim;
+    T* W = a.Wv;
+    const uint32_t V32 = (uint32_t)g.V;
+    for (uint64_t it = 0; it < a.jobs; ++it) {
+        // user: SourceSample until field == 0 (HBPR.cpp:97-99)
+        int64_t vid = reject_sample(ring, lane, 2u,
+                                    [&](uint32_t w0, uint32_t w1) { return (int64_t)source_sample(g, w0, w1); },
+                                    [&](int64_t c) { return __ldg(g.field + c) == 0; });
+        int64_t cid = -1;
+        bool dead = false;
+        for (int hop = 1; hop <= a.steps && !dead; ++hop) {
+            // item at this hop: 1 TargetSample for hop 1, two more for every further hop (HBPR.cpp:100,105-109)
+            ring.ensure();
+            int64_t c = cid;
+            uint32_t used = 0;
+            if (lane == 0) {
+                int u;
+                if (hop == 1) {
+                    c = target_sample(g, vid, ring.peek(0), ring.peek(1), u);
+                    used = 2;
+                } else {
+                    c = target_sample(g, c, ring.peek(0), ring.peek(1), u);
+                    used = 2;
+                    if (c >= 0) {
+                        c = target_sample(g, c, ring.peek(2), ring.peek(3), u);
+                        used = 4;
+                    }
+                }
+            }
+            cid = __shfl_sync(kFull, c, 0);
+            ring.advance(__shfl_sync(kFull, used, 0));
+            if (cid < 0) {  // sink: the reference would index row -1; abandon the sample
+                dead = true;
+                break;
+            }
+            const int cfield = __ldg(g.field + cid);
+            // caller's negative: NegativeSample until same field as the item (HBPR.cpp:110-112)
+            int64_t jid[5];
+            jid[0] = reject_sample(ring, lane, 2u,
+                                   [&](uint32_t w0, uint32_t w1) { return (int64_t)negative_sample(g, w0, w1); },
+                                   [&](int64_t x) { return __ldg(g.field + x) == cfield; });
+            // rounds 1..4: uniform vertex until same field (proNet.cpp:1477-1482), 1 word per attempt
+#pragma unroll
+            for (int r = 1; r < 5; ++r)
+                jid[r] = reject_sample(ring, lane, 1u,
+                                       [&](uint32_t w0, uint32_t) { return (int64_t)index_draw(w0, V32); },
+                                       [&](int64_t x) { return __ldg(g.field + x) == cfield; });
+            const T alpha = (T)(st.alpha / (double)hop);
+            const T margin = (T)(1.0 / (double)hop);
+            const T cdec = alpha * (T)0.0025;
+            T* pv = W + vid * dim;
+            T* pi = W + cid * dim;
+            bool dup = vid == cid;
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                dup = dup || jid[r] == vid || jid[r] == cid;
+#pragma unroll
+                for (int s = 0; s < r; ++s) dup = dup || jid[r] == jid[s];
+            }
+            Row<C> verr;
+            verr.zero();
+            T up = 0;
+            if (!dup) {
+                Row<C> v, ri, rj[5];
+                v.load(pv, lane, dim);
+                ri.load(pi, lane, dim);
+#pragma unroll
+                for (int r = 0; r < 5; ++r) rj[r].load(W + jid[r] * dim, lane, dim);
+                bool ri_dirty = false;
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    Row<C> cvec;
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = ri.x[e] - rj[r].x[e];
+                    const T f = dot(v, cvec);
+                    if (!(f > margin)) {
+                        const T gg = fast_sigmoid<T>(lut, (T)0 - f) * alpha;
+                        up += (T)1;
+#pragma unroll
+                        for (int e = 0; e < C::EPL; ++e) {
+                            verr.x[e] += gg * cvec.x[e];
+                            const T cerr = gg * v.x[e];
+                            ri.x[e] -= cdec * ri.x[e];
+                            rj[r].x[e] -= cdec * rj[r].x[e];
+                            ri.x[e] += cerr;
+                            rj[r].x[e] -= cerr;
+                        }
+                        rj[r].store(W + jid[r] * dim, lane, dim);
+                        ri_dirty = true;
+                    }
+                }
+                if (ri_dirty) ri.store(pi, lane, dim);
+                if (up > (T)0) {
+                    const T cv = alpha * (T)0.025;
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) {
+                        v.x[e] -= cv * v.x[e];
+                        v.x[e] += verr.x[e] / up;
+                    }
+                    v.store(pv, lane, dim);
+                }
+            } else {
+                for (int r = 0; r < 5; ++r)
+                    if (ordered_round<C>(pv, pi, W + jid[r] * dim, dim, lane, lut, alpha, true, margin, verr)) up += (T)1;
+                if (up > (T)0) {
+                    const T cv = alpha * (T)0.025;
+                    for_owned<C>(lane, dim, [&](int e, int idx) {
+                        stv(pv + idx, ldv(pv + idx) - cv * ldv(pv + idx));
+                        stv(pv + idx, ldv(pv + idx) + verr.x[e] / up);
+                    });
+                }
+            }
+            st.pairs += 5;
+        }
+        st.count++;
+        sched_tick(st, a.sched);
+    }
+    st.pos = ring.pos;
+    if (lane == 0) a.state[w] = st;
+}
+
+}  // namespace smore

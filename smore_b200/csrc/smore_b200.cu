@@ -1,0 +1,844 @@
+// C-ABI implementation (include/smore_b200.h): handles, HBM layout, kernel launches. No CPU fallback anywhere.
+#include "../../include/smore_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "host_graph.h"
+#include "kernels.cuh"
+#include "ranking_kernels.cuh"
+
+using namespace smore;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+int g_device = -1;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(SMORE_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(SMORE_E_CUDA, "no CUDA device available (%s); smore_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    int dev = g_device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(SMORE_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    CU(cudaSetDevice(dev));
+    g_device = dev;
+    return SMORE_OK;
+}
+
+template <typename T>
+int dev_alloc_copy(T** d, const T* h, size_t n) {
+    *d = nullptr;
+    if (n == 0) return SMORE_OK;
+    CU(cudaMalloc((void**)d, n * sizeof(T)));
+    CU(cudaMemcpy(*d, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return SMORE_OK;
+}
+
+}  // namespace
+
+struct smore_graph_s {
+    int sem = 0, neg_method = 0;
+    int64_t V = 0, E = 0, n_lines = 0;
+    std::vector<int64_t> row_off;
+    std::vector<int32_t> col;
+    std::vector<double> w;
+    std::vector<std::string> names;
+    std::vector<int32_t> field;
+    bool has_field = false;
+    AliasHost vertex_at, negative_at, ctx_at;
+    // device
+    int64_t* d_row_off = nullptr;
+    int32_t* d_col = nullptr;
+    uint2 *d_vat = nullptr, *d_nat = nullptr, *d_cat = nullptr;
+    double* d_prefix = nullptr;
+    int32_t* d_field = nullptr;
+    double* d_lut64 = nullptr;
+    float* d_lut32 = nullptr;
+
+    GraphDev view() const {
+        GraphDev g;
+        g.V = V; g.E = E;
+        g.row_off = d_row_off; g.col = d_col;
+        g.vertex_at = d_vat; g.negative_at = d_nat; g.ctx_at = d_cat;
+        g.prefix = d_prefix; g.field = d_field; g.sem = sem;
+        return g;
+    }
+    ~smore_graph_s() {
+        cudaFree(d_row_off); cudaFree(d_col); cudaFree(d_vat); cudaFree(d_nat); cudaFree(d_cat);
+        cudaFree(d_prefix); cudaFree(d_field); cudaFree(d_lut64); cudaFree(d_lut32);
+    }
+};
+
+struct smore_model_s {
+    smore_graph_t g = nullptr;
+    int dim = 0, n_tables = 0, dtype = 0;
+    void* tab[2] = {nullptr, nullptr};
+    WarpState* d_state = nullptr;
+    int state_cap = 0;
+    int32_t* d_keys = nullptr;
+    int64_t keys_cap = 0;
+    // stats of the last train call
+    uint64_t st_samples = 0, st_pairs = 0, st_words0 = 0, st_tries = 0;
+    double st_ms = 0;
+    size_t elem() const { return dtype == SMORE_F64 ? 8 : 4; }
+    ~smore_model_s() {
+        cudaFree(tab[0]); cudaFree(tab[1]); cudaFree(d_state); cudaFree(d_keys);
+    }
+};
+
+namespace {
+
+int upload_graph(smore_graph_s* g) {
+    const int64_t V = g->V, E = g->E;
+    if (int rc = dev_alloc_copy(&g->d_row_off, g->row_off.data(), (size_t)V + 1)) return rc;
+    if (int rc = dev_alloc_copy(&g->d_col, g->col.data(), (size_t)E)) return rc;
+    auto pack_table = [&](const AliasHost& t, std::vector<uint2>& out) {
+        out.resize(t.prob.size());
+        for (size_t i = 0; i < t.prob.size(); ++i) {
+            PackedAlias p = pack_alias(t.prob[i], t.alias[i], (uint32_t)i);
+            out[i] = make_uint2(p.thr, p.alias);
+        }
+    };
+    std::vector<uint2> packed;
+    pack_table(g->vertex_at, packed);
+    if (int rc = dev_alloc_copy(&g->d_vat, packed.data(), packed.size())) return rc;
+    pack_table(g->negative_at, packed);
+    if (int rc = dev_alloc_copy(&g->d_nat, packed.data(), packed.size())) return rc;
+    if (g->sem == SMORE_SEM_CPP) {
+        // context table: alias entries are already vertex ids (src/proNet.cpp:530-534); "self" = the entry's own target
+        packed.resize((size_t)E);
+        for (int64_t e = 0; e < E; ++e) {
+            PackedAlias p = pack_alias(g->ctx_at.prob[(size_t)e], g->ctx_at.alias[(size_t)e], (uint32_t)g->col[(size_t)e]);
+            packed[(size_t)e] = make_uint2(p.thr, p.alias);
+        }
+        if (int rc = dev_alloc_copy(&g->d_cat, packed.data(), packed.size())) return rc;
+    } else {
+        std::vector<double> prefix((size_t)E);
+        for (int64_t v = 0; v < V; ++v) {
+            double cum = 0.0;  // pronet.go:274-281: cumWeight += w in adjacency order
+            for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) {
+                cum += g->w[(size_t)e];
+                prefix[(size_t)e] = cum;
+            }
+        }
+        if (int rc = dev_alloc_copy(&g->d_prefix, prefix.data(), prefix.size())) return rc;
+    }
+    g->field.assign((size_t)V, 0);
+    if (int rc = dev_alloc_copy(&g->d_field, g->field.data(), (size_t)V)) return rc;
+    // sigmoid LUT: InitSigmoid (src/proNet.cpp:52-60) incl. its one-past-the-end entry; pronet.go:90-95
+    double lut[kSigmoidTable + 1];
+    float lutf[kSigmoidTable + 1];
+    for (int i = 0; i != kSigmoidTable + 1; i++) {
+        double x = i * 2.0 * 8.0 / kSigmoidTable - 8.0;
+        lut[i] = 1.0 / (1.0 + std::exp(-x));
+        lutf[i] = (float)lut[i];
+    }
+    if (int rc = dev_alloc_copy(&g->d_lut64, lut, kSigmoidTable + 1)) return rc;
+    if (int rc = dev_alloc_copy(&g->d_lut32, lutf, kSigmoidTable + 1)) return rc;
+    return SMORE_OK;
+}
+
+int build_graph(smore_graph_s* g) {
+    const int64_t V = g->V, E = g->E;
+    if (V <= 0 || V >= (1ll << 31)) return fail(SMORE_E_INVALID, "V=%lld out of range", (long long)V);
+    for (int64_t e = 0; e < E; ++e)
+        if (g->col[(size_t)e] < 0 || g->col[(size_t)e] >= V) return fail(SMORE_E_INVALID, "col[%lld] out of range", (long long)e);
+    for (int64_t v = 0; v < V; ++v)
+        if (g->row_off[(size_t)v + 1] < g->row_off[(size_t)v] || g->row_off[(size_t)v + 1] - g->row_off[(size_t)v] >= (1ll << 32))
+            return fail(SMORE_E_INVALID, "row_off not monotone / degree too large at %lld", (long long)v);
+    if (g->row_off[0] != 0 || g->row_off[(size_t)V] != E) return fail(SMORE_E_INVALID, "row_off[0]/row_off[V] inconsistent with E");
+    // degrees in the reference's accumulation order (src/proNet.cpp:423-446; pronet.go:198-212)
+    std::vector<double> out_deg((size_t)V, 0.0), in_deg((size_t)V, 0.0), dist((size_t)V);
+    for (int64_t v = 0; v < V; ++v)
+        for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) out_deg[(size_t)v] += g->w[(size_t)e];
+    for (int64_t e = 0; e < E; ++e) in_deg[(size_t)g->col[(size_t)e]] += g->w[(size_t)e];
+    if (g->sem == SMORE_SEM_CPP) {
+        g->vertex_at = alias_method_cpp(out_deg.data(), V);  // vertex_method "out_degrees" (src/proNet.cpp:458-464)
+        for (int64_t v = 0; v < V; ++v) {
+            if (g->neg_method == SMORE_NEG_DEGREES) dist[(size_t)v] = in_deg[(size_t)v] + out_deg[(size_t)v];
+            else if (g->neg_method == SMORE_NEG_IN_DEGREES) dist[(size_t)v] = in_deg[(size_t)v];
+            else dist[(size_t)v] = in_deg[(size_t)v] == 0 ? 0 : 1;
+        }
+        g->negative_at = alias_method_cpp(dist.data(), V);
+        g->ctx_at.prob.resize((size_t)E);
+        g->ctx_at.alias.resize((size_t)E);
+        for (int64_t v = 0; v < V; ++v) {  // per-vertex sub-tables in CSR order (src/proNet.cpp:519-536)
+            const int64_t o = g->row_off[(size_t)v], b = g->row_off[(size_t)v + 1] - o;
+            if (b == 0) continue;
+            AliasHost sub = alias_method_cpp(g->w.data() + o, b);
+            for (int64_t i = 0; i < b; ++i) {
+                g->ctx_at.prob[(size_t)(o + i)] = sub.prob[(size_t)i];
+                g->ctx_at.alias[(size_t)(o + i)] = sub.alias[(size_t)i] != -1 ? (int64_t)g->col[(size_t)(o + sub.alias[(size_t)i])] : -1;
+            }
+        }
+    } else {
+        g->vertex_at = alias_method_go(out_deg.data(), V, 1.0);  // pronet.go:224-230
+        for (int64_t v = 0; v < V; ++v) dist[(size_t)v] = in_deg[(size_t)v] + out_deg[(size_t)v];
+        g->negative_at = alias_method_go(dist.data(), V, 0.75);  // pronet.go:242-249
+    }
+    return upload_graph(g);
+}
+
+// ---- row-layout dispatch ------------------------------------------------------------------------------------
+struct Launch {
+    int blocks = 0, warps = 0;
+};
+
+template <class K>
+int pick_grid(K kernel, size_t smem, int max_warps, uint64_t work_items, Launch& out) {
+    int dev = 0, sms = 0, occ = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlockThreads, smem));
+    if (occ < 1) return fail(SMORE_E_CUDA, "kernel does not fit on an SM");
+    int64_t warps = (int64_t)sms * occ * kWarpsPerBlock;  // persistent grid: every CTA resident, a multiple of the SM count
+    if (max_warps > 0) warps = std::min<int64_t>(warps, max_warps);
+    warps = std::min<int64_t>(warps, (int64_t)std::max<uint64_t>(work_items, 1));
+    out.warps = (int)warps;
+    out.blocks = (int)((warps + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    return SMORE_OK;
+}
+
+// F is a generic lambda taking a RowCfg tag.
+template <typename T, class F>
+int dispatch_dim(int dim, F&& f) {
+    constexpr int V16 = 16 / (int)sizeof(T);  // elements per 128-bit vector
+    if (dim <= 0) return fail(SMORE_E_INVALID, "dim must be positive");
+    if (dim % (32 * V16) == 0) {
+        int nch = dim / (32 * V16);
+        if (nch == 1) return f(RowCfg<T, V16, 1, false>{});
+        if (nch == 2) return f(RowCfg<T, V16, 2, false>{});
+        if (nch == 4) return f(RowCfg<T, V16, 4, false>{});
+    }
+    if (V16 == 4 && dim == 64) return f(RowCfg<T, 2, 1, false>{});
+    if (dim <= 32) return f(RowCfg<T, 1, 1, true>{});
+    if (dim <= 64) return f(RowCfg<T, 1, 2, true>{});
+    if (dim <= 128) return f(RowCfg<T, 1, 4, true>{});
+    return fail(SMORE_E_UNSUPPORTED, "dim=%d unsupported (<=128, or a multiple of %d up to %d)", dim, 32 * V16, 128 * V16);
+}
+
+int ensure_state(smore_model_s* m, int warps) {
+    if (warps > m->state_cap) {
+        cudaFree(m->d_state);
+        m->d_state = nullptr;
+        CU(cudaMalloc((void**)&m->d_state, (size_t)warps * sizeof(WarpState)));
+        m->state_cap = warps;
+    }
+    return SMORE_OK;
+}
+
+int check_train(smore_model_s* m, const smore_train_params* p, int need_tables) {
+    if (!m || !p) return fail(SMORE_E_INVALID, "null model/params");
+    if (p->semantics != m->g->sem) return fail(SMORE_E_INVALID, "params.semantics (%d) != graph semantics (%d)", p->semantics, m->g->sem);
+    if (m->n_tables < need_tables) return fail(SMORE_E_INVALID, "model has %d tables, this trainer needs %d", m->n_tables, need_tables);
+    if (p->mode != SMORE_MODE_DETERMINISTIC && p->mode != SMORE_MODE_HOGWILD) return fail(SMORE_E_INVALID, "bad mode");
+    if (!(p->alpha > 0)) return fail(SMORE_E_INVALID, "alpha must be > 0");
+    return ensure_device();
+}
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int start() {
+        CU(cudaEventCreate(&a));
+        CU(cudaEventCreate(&b));
+        CU(cudaEventRecord(a, 0));
+        return SMORE_OK;
+    }
+    int stop(double* ms) {
+        CU(cudaEventRecord(b, 0));
+        CU(cudaEventSynchronize(b));
+        float f = 0;
+        CU(cudaEventElapsedTime(&f, a, b));
+        *ms = f;
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        a = b = nullptr;
+        return SMORE_OK;
+    }
+    ~Timer() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+int collect_stats(smore_model_s* m, int warps) {
+    std::vector<WarpState> st((size_t)warps);
+    CU(cudaMemcpy(st.data(), m->d_state, st.size() * sizeof(WarpState), cudaMemcpyDeviceToHost));
+    m->st_pairs = m->st_tries = 0;
+    for (auto& s : st) {
+        m->st_pairs += s.pairs;
+        m->st_tries += s.tries;
+    }
+    m->st_words0 = st[0].pos;
+    return SMORE_OK;
+}
+
+template <typename T>
+TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps, double total, int lag, int vtab, int ctab) {
+    TrainArgs<T> a{};
+    a.g = m->g->view();
+    a.Wv = (T*)m->tab[vtab];
+    a.Wc = (T*)m->tab[ctab];
+    a.dim = m->dim;
+    a.same_table = vtab == ctab;
+    a.lut = sizeof(T) == 8 ? (const T*)m->g->d_lut64 : (const T*)m->g->d_lut32;
+    a.seed = p->seed;
+    a.stream_base = p->stream_base;
+    a.sched = Sched{p->alpha, total, (uint64_t)warps, lag};
+    a.state = m->d_state;
+    a.n_warps = warps;
+    a.K = p->negative_samples;
+    a.order = p->order;
+    a.lambda = (T)p->lambda;
+    return a;
+}
+
+int init_state(smore_model_s* m, int warps, uint64_t count0, double alpha) {
+    std::vector<WarpState> st((size_t)warps);
+    for (int w = 0; w < warps; ++w) {
+        st[(size_t)w] = WarpState{0, count0, ((uint64_t)kMonitor + (uint64_t)warps - 1) / (uint64_t)warps, alpha, 0, 0};
+    }
+    if (int rc = ensure_state(m, warps)) return rc;
+    CU(cudaMemcpy(m->d_state, st.data(), st.size() * sizeof(WarpState), cudaMemcpyHostToDevice));
+    return SMORE_OK;
+}
+
+constexpr size_t smem_rings = (size_t)kWarpsPerBlock * 256 * sizeof(uint32_t);
+template <typename T>
+constexpr size_t smem_line() { return smem_rings + 1008 * sizeof(T); }
+template <typename T>
+constexpr size_t smem_walk() { return smem_line<T>() + (size_t)kWarpsPerBlock * kMaxWalkLen * (sizeof(int32_t) + 1); }
+
+// ---- LINE -----------------------------------------------------------------------------------------------------
+template <typename T>
+int train_line_t(smore_model_s* m, const smore_train_params* p) {
+    const int vtab = 0, ctab = p->order == 1 ? 0 : 1;
+    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
+        using C = decltype(cfg);
+        auto kern = k_line<C>;
+        const size_t smem = smem_line<T>();
+        const bool cpp = p->semantics == SMORE_SEM_CPP;
+        Launch L;
+        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
+        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
+        // jobs = total / workers (LINE.cpp:124); the C++ loop starts count at 1 and runs while count < jobs
+        const uint64_t jobs = p->total / (uint64_t)L.warps;
+        const uint64_t trips = cpp ? (jobs > 0 ? jobs - 1 : 0) : jobs;
+        if (int rc = init_state(m, L.warps, cpp ? 1 : 0, p->alpha)) return rc;
+        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)p->total, cpp ? 1 : 0, vtab, ctab);
+        a.jobs = trips;
+        Timer t;
+        if (int rc = t.start()) return rc;
+        kern<<<L.blocks, kBlockThreads, smem>>>(a);
+        g_launches++;
+        CU(cudaGetLastError());
+        if (int rc = t.stop(&m->st_ms)) return rc;
+        m->st_samples = trips * (uint64_t)L.warps;
+        return collect_stats(m, L.warps);
+    });
+}
+
+// ---- DeepWalk / Walklets ----------------------------------------------------------------------------------------
+template <typename T>
+int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets) {
+    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
+        using C = decltype(cfg);
+        auto kern = k_walk<C>;
+        const size_t smem = smem_walk<T>();
+        const bool cpp = p->semantics == SMORE_SEM_CPP;
+        const int64_t V = m->g->V;
+        Launch L;
+        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
+        else if (int rc = pick_grid(kern, smem, p->max_warps, (uint64_t)V, L)) return rc;
+        const double total = (double)((unsigned long long)p->walk_times * (unsigned long long)V);
+        if (int rc = init_state(m, L.warps, 0, p->alpha)) return rc;
+        TrainArgs<T> a = base_args<T>(m, p, L.warps, total, 0, 0, 1);
+        a.steps = p->walk_steps;
+        a.w0 = p->window_min;
+        a.w1 = p->window_max;
+        a.walklets = walklets;
+        if (m->keys_cap < V) {
+            cudaFree(m->d_keys);
+            m->d_keys = nullptr;
+            CU(cudaMalloc((void**)&m->d_keys, (size_t)V * sizeof(int32_t)));
+            m->keys_cap = V;
+        }
+        a.keys = m->d_keys;
+        std::vector<int32_t> keys((size_t)V);
+        HostStream shuffle(p->seed, kShuffleStream);
+        int64_t walks_left = p->max_walks >= 0 ? p->max_walks : (int64_t)p->walk_times * V;
+        uint64_t done = 0;
+        m->st_ms = 0;
+        for (int t = 0; t < p->walk_times && walks_left > 0; ++t) {
+            // per-epoch Fisher-Yates (DeepWalk.cpp:124-131 with libc rand() := shuffle-stream word >> 1;
+            // deepwalk.go:84-92 with rand.Int63n(n) := umulhi32(word, n)). Walklets draws it but walks in id order.
+            for (int64_t v = 0; v < V; ++v) keys[(size_t)v] = (int32_t)v;
+            for (int64_t v = 0; v < V; ++v) {
+                uint32_t k = shuffle.next();
+                int64_t j = cpp ? (int64_t)(int)(v + (int64_t)(k >> 1) % (V - v)) : v + (int64_t)(((uint64_t)k * (uint64_t)(V - v)) >> 32);
+                std::swap(keys[(size_t)v], keys[(size_t)j]);
+            }
+            if (walklets)
+                for (int64_t v = 0; v < V; ++v) keys[(size_t)v] = (int32_t)v;
+            CU(cudaMemcpy(m->d_keys, keys.data(), (size_t)V * sizeof(int32_t), cudaMemcpyHostToDevice));
+            a.n_walks = std::min<int64_t>(V, walks_left);
+            Timer tm;
+            double ms = 0;
+            if (int rc = tm.start()) return rc;
+            kern<<<L.blocks, kBlockThreads, smem>>>(a);
+            g_launches++;
+            CU(cudaGetLastError());
+            if (int rc = tm.stop(&ms)) return rc;
+            m->st_ms += ms;
+            walks_left -= a.n_walks;
+            done += (uint64_t)a.n_walks;
+        }
+        m->st_samples = done;
+        return collect_stats(m, L.warps);
+    });
+}
+
+// ---- BPR / WARP / HOP-Rec -------------------------------------------------------------------------------------
+template <typename T>
+int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind) {
+    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
+        using C = decltype(cfg);
+        const bool cpp = p->semantics == SMORE_SEM_CPP;
+        void (*kern)(TrainArgs<T>) = kind == RANK_WARP ? k_warp<C> : kind == RANK_HOPREC ? k_hoprec<C> : cpp ? k_bpr_cpp<C> : k_bpr_go<C>;
+        const size_t smem = smem_line<T>();
+        Launch L;
+        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
+        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
+        // BPR.cpp:73-85 / WARP.cpp / HBPR.cpp: jobs = total / workers, count from 0; bpr.go: sample_times*MaxLine trips
+        const uint64_t trips = p->total / (uint64_t)L.warps;
+        if (int rc = init_state(m, L.warps, 0, p->alpha)) return rc;
+        const int ctab = (kind == RANK_BPR && !cpp) ? 1 : 0;  // the C++ ranking models pass one table for both roles
+        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)p->total, cpp ? 1 : 0, 0, ctab);
+        a.jobs = trips;
+        a.steps = p->walk_steps;
+        Timer t;
+        if (int rc = t.start()) return rc;
+        kern<<<L.blocks, kBlockThreads, smem>>>(a);
+        g_launches++;
+        CU(cudaGetLastError());
+        if (int rc = t.stop(&m->st_ms)) return rc;
+        m->st_samples = trips * (uint64_t)L.warps;
+        return collect_stats(m, L.warps);
+    });
+}
+
+}  // namespace
+
+namespace {
+template <typename TH>
+int rows_io(smore_model_t m, int table, int64_t first, int64_t n, TH* host, bool to_device) {
+    if (!m || table < 0 || table >= m->n_tables || !host) return fail(SMORE_E_INVALID, "bad model/table/buffer");
+    if (first < 0 || n < 0 || first + n > m->g->V) return fail(SMORE_E_INVALID, "row range out of bounds");
+    if (n == 0) return SMORE_OK;
+    if (int rc = ensure_device()) return rc;
+    const int64_t cnt = n * (int64_t)m->dim;
+    const bool same = (m->dtype == SMORE_F64) == (sizeof(TH) == 8);
+    char* dptr = (char*)m->tab[table] + (size_t)first * (size_t)m->dim * m->elem();
+    if (same) {
+        if (to_device) CU(cudaMemcpy(dptr, host, (size_t)cnt * sizeof(TH), cudaMemcpyHostToDevice));
+        else CU(cudaMemcpy((void*)host, dptr, (size_t)cnt * sizeof(TH), cudaMemcpyDeviceToHost));
+        return SMORE_OK;
+    }
+    // dtype conversion on the device through a staging buffer
+    TH* stage = nullptr;
+    CU(cudaMalloc((void**)&stage, (size_t)cnt * sizeof(TH)));
+    const int blocks = (int)std::min<int64_t>((cnt + 255) / 256, 148 * 16);
+    int rc = SMORE_OK;
+    if (to_device) {
+        cudaError_t e = cudaMemcpy(stage, host, (size_t)cnt * sizeof(TH), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            if (m->dtype == SMORE_F64) k_convert<double, TH><<<blocks, 256>>>((double*)dptr, stage, cnt);
+            else k_convert<float, TH><<<blocks, 256>>>((float*)dptr, stage, cnt);
+            g_launches++;
+            e = cudaDeviceSynchronize();
+        }
+        if (e != cudaSuccess) rc = fail(SMORE_E_CUDA, "set_rows: %s", cudaGetErrorString(e));
+    } else {
+        if (m->dtype == SMORE_F64) k_convert<TH, double><<<blocks, 256>>>(stage, (const double*)dptr, cnt);
+        else k_convert<TH, float><<<blocks, 256>>>(stage, (const float*)dptr, cnt);
+        g_launches++;
+        cudaError_t e = cudaMemcpy((void*)host, stage, (size_t)cnt * sizeof(TH), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(SMORE_E_CUDA, "get_rows: %s", cudaGetErrorString(e));
+    }
+    cudaFree(stage);
+    return rc;
+}
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+const char* smore_last_error(void) { return g_err.c_str(); }
+const char* smore_version(void) { return "smore_b200 0.1 (sm_100a)"; }
+uint64_t smore_kernel_launches(void) { return g_launches.load(); }
+
+int smore_init(int device_id) {
+    g_device = device_id;
+    return ensure_device();
+}
+
+void smore_train_params_default(smore_train_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->semantics = SMORE_SEM_CPP;
+    p->mode = SMORE_MODE_HOGWILD;
+    p->seed = 1;
+    p->alpha = 0.025;
+    p->total = 10ull * 1000000ull;
+    p->negative_samples = 5;
+    p->order = 2;
+    p->lambda = 0.001;
+    p->walk_times = 10;
+    p->walk_steps = 40;
+    p->window_min = 1;
+    p->window_max = 5;
+    p->max_walks = -1;
+}
+
+int smore_graph_create(int64_t V, int64_t E, const int64_t* row_off, const int32_t* col, const double* weight,
+                       int64_t n_lines, int semantics, int negative_method, smore_graph_t* out) {
+    if (!row_off || (!col && E > 0) || (!weight && E > 0) || !out) return fail(SMORE_E_INVALID, "null argument");
+    if (semantics != SMORE_SEM_CPP && semantics != SMORE_SEM_GO) return fail(SMORE_E_INVALID, "bad semantics");
+    if (negative_method < 0 || negative_method > 2) return fail(SMORE_E_INVALID, "bad negative_method");
+    if (int rc = ensure_device()) return rc;
+    smore_graph_s* g = new smore_graph_s();
+    g->sem = semantics;
+    g->neg_method = semantics == SMORE_SEM_GO ? SMORE_NEG_DEGREES : negative_method;
+    g->V = V;
+    g->E = E;
+    g->n_lines = n_lines > 0 ? n_lines : E;
+    g->row_off.assign(row_off, row_off + V + 1);
+    g->col.assign(col, col + E);
+    g->w.assign(weight, weight + E);
+    int rc = build_graph(g);
+    if (rc) { delete g; return rc; }
+    *out = g;
+    return SMORE_OK;
+}
+
+int smore_graph_load_edge_list(const char* path, int undirected, int semantics, int negative_method, smore_graph_t* out) {
+    if (!path || !out) return fail(SMORE_E_INVALID, "null argument");
+    if (semantics != SMORE_SEM_CPP && semantics != SMORE_SEM_GO) return fail(SMORE_E_INVALID, "bad semantics");
+    if (int rc = ensure_device()) return rc;
+    EdgeList el;
+    std::string err;
+    if (!load_edge_list(path, undirected != 0, el, err)) return fail(SMORE_E_IO, "%s", err.c_str());
+    if (el.names.empty()) return fail(SMORE_E_IO, "no edges in %s", path);
+    smore_graph_s* g = new smore_graph_s();
+    g->sem = semantics;
+    g->neg_method = semantics == SMORE_SEM_GO ? SMORE_NEG_DEGREES : negative_method;
+    g->V = (int64_t)el.names.size();
+    g->E = (int64_t)el.col.size();
+    // C++: MAX_line counts CSR entries (doubled when undirected, src/proNet.cpp:230-231); Go: edge lines (pronet.go:164)
+    g->n_lines = semantics == SMORE_SEM_CPP ? g->E : el.n_lines;
+    g->row_off = std::move(el.row_off);
+    g->col = std::move(el.col);
+    g->w = std::move(el.w);
+    g->names = std::move(el.names);
+    int rc = build_graph(g);
+    if (rc) { delete g; return rc; }
+    *out = g;
+    return SMORE_OK;
+}
+
+int smore_graph_set_field(smore_graph_t g, const int32_t* field) {
+    if (!g || !field) return fail(SMORE_E_INVALID, "null argument");
+    g->field.assign(field, field + g->V);
+    g->has_field = true;
+    CU(cudaMemcpy(g->d_field, g->field.data(), (size_t)g->V * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return SMORE_OK;
+}
+
+int smore_graph_load_field(smore_graph_t g, const char* path) {
+    if (!g || !path) return fail(SMORE_E_INVALID, "null argument");
+    if (g->names.empty()) return fail(SMORE_E_INVALID, "graph has no vertex names (created from CSR); use smore_graph_set_field");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(SMORE_E_IO, "cannot open field file: %s", path);
+    std::map<std::string, int32_t> name_to_id;
+    for (size_t i = 0; i < g->names.size(); ++i) name_to_id.emplace(g->names[i], (int32_t)i);
+    std::map<std::string, int32_t> meta_idx;  // field ids in first-appearance order (src/proNet.cpp:368-372)
+    std::vector<int32_t> field((size_t)g->V, 0);
+    char v[1024], meta[1024];
+    while (fscanf(f, "%1023s %1023s", v, meta) == 2) {
+        auto it = meta_idx.find(meta);
+        if (it == meta_idx.end()) it = meta_idx.emplace(meta, (int32_t)meta_idx.size()).first;
+        auto vit = name_to_id.find(v);
+        if (vit != name_to_id.end()) field[(size_t)vit->second] = it->second;
+    }
+    fclose(f);
+    return smore_graph_set_field(g, field.data());
+}
+
+int smore_graph_info(smore_graph_t g, int64_t* V, int64_t* E, int64_t* n_lines) {
+    if (!g) return fail(SMORE_E_INVALID, "null graph");
+    if (V) *V = g->V;
+    if (E) *E = g->E;
+    if (n_lines) *n_lines = g->n_lines;
+    return SMORE_OK;
+}
+
+int smore_graph_get_csr(smore_graph_t g, int64_t* row_off, int32_t* col, double* weight) {
+    if (!g) return fail(SMORE_E_INVALID, "null graph");
+    if (row_off) memcpy(row_off, g->row_off.data(), g->row_off.size() * sizeof(int64_t));
+    if (col) memcpy(col, g->col.data(), g->col.size() * sizeof(int32_t));
+    if (weight) memcpy(weight, g->w.data(), g->w.size() * sizeof(double));
+    return SMORE_OK;
+}
+
+const char* smore_graph_vertex_name(smore_graph_t g, int64_t vid) {
+    if (!g || vid < 0 || vid >= (int64_t)g->names.size()) return nullptr;
+    return g->names[(size_t)vid].c_str();
+}
+
+int smore_graph_get_alias(smore_graph_t g, int which, double* prob, int64_t* alias) {
+    if (!g) return fail(SMORE_E_INVALID, "null graph");
+    const AliasHost* t = which == SMORE_AT_VERTEX ? &g->vertex_at : which == SMORE_AT_NEGATIVE ? &g->negative_at : which == SMORE_AT_CONTEXT ? &g->ctx_at : nullptr;
+    if (!t) return fail(SMORE_E_INVALID, "bad table selector");
+    if (which == SMORE_AT_CONTEXT && g->sem != SMORE_SEM_CPP) return fail(SMORE_E_UNSUPPORTED, "context alias table exists only under C++ semantics");
+    if (prob) memcpy(prob, t->prob.data(), t->prob.size() * sizeof(double));
+    if (alias) memcpy(alias, t->alias.data(), t->alias.size() * sizeof(int64_t));
+    return SMORE_OK;
+}
+
+int smore_graph_get_field(smore_graph_t g, int32_t* field) {
+    if (!g || !field) return fail(SMORE_E_INVALID, "null argument");
+    memcpy(field, g->field.data(), g->field.size() * sizeof(int32_t));
+    return SMORE_OK;
+}
+
+void smore_graph_destroy(smore_graph_t g) { delete g; }
+
+int smore_sample_debug(smore_graph_t g, int which, uint64_t seed, uint64_t stream, int64_t n, const int64_t* arg,
+                       int64_t* out, uint64_t* words_used) {
+    if (!g || !out || n < 0) return fail(SMORE_E_INVALID, "bad argument");
+    if (which < 0 || which > 3) return fail(SMORE_E_INVALID, "bad sampler selector");
+    if (which == SMORE_SAMPLE_TARGET && !arg) return fail(SMORE_E_INVALID, "TARGET needs source vertices");
+    if (int rc = ensure_device()) return rc;
+    const int64_t n_out = which == 3 ? 2 * n : n;
+    int64_t *d_arg = nullptr, *d_out = nullptr;
+    uint64_t* d_used = nullptr;
+    if (arg) {
+        for (int64_t i = 0; i < n; ++i)
+            if (arg[i] < 0 || arg[i] >= g->V) return fail(SMORE_E_INVALID, "arg[%lld] out of range", (long long)i);
+        CU(cudaMalloc((void**)&d_arg, (size_t)std::max<int64_t>(n, 1) * 8));
+        CU(cudaMemcpy(d_arg, arg, (size_t)n * 8, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMalloc((void**)&d_out, (size_t)std::max<int64_t>(n_out, 1) * 8));
+    CU(cudaMalloc((void**)&d_used, 8));
+    k_sample_debug<<<1, 32>>>(g->view(), which, seed, stream, n, d_arg, d_out, d_used);
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, d_out, (size_t)n_out * 8, cudaMemcpyDeviceToHost));
+    if (words_used) CU(cudaMemcpy(words_used, d_used, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_arg); cudaFree(d_out); cudaFree(d_used);
+    return SMORE_OK;
+}
+
+int smore_walk_debug(smore_graph_t g, uint64_t seed, uint64_t stream, int64_t start, int steps, int mode, int w0, int w1,
+                     int64_t* walk, int64_t* walk_len, int64_t* pair_v, int64_t* pair_c, int64_t cap, int64_t* n_pairs) {
+    if (!g || !walk || !walk_len || !n_pairs) return fail(SMORE_E_INVALID, "null argument");
+    if (start < 0 || start >= g->V) return fail(SMORE_E_INVALID, "start out of range");
+    if (steps < 0 || steps + 1 > kMaxWalkLen) return fail(SMORE_E_UNSUPPORTED, "walk_steps must be < %d", kMaxWalkLen);
+    if (mode == 0 && (w0 < 1 || w0 > 255)) return fail(SMORE_E_INVALID, "window must be in [1,255]");
+    if (mode == 1 && g->sem != SMORE_SEM_CPP) return fail(SMORE_E_UNSUPPORTED, "ScaleSkipGrams exists only under C++ semantics");
+    if (int rc = ensure_device()) return rc;
+    int64_t *d_walk, *d_len, *d_pv, *d_pc, *d_np;
+    const int64_t c = std::max<int64_t>(cap, 1);
+    CU(cudaMalloc((void**)&d_walk, (size_t)(steps + 1) * 8));
+    CU(cudaMalloc((void**)&d_len, 8));
+    CU(cudaMalloc((void**)&d_np, 8));
+    CU(cudaMalloc((void**)&d_pv, (size_t)c * 8));
+    CU(cudaMalloc((void**)&d_pc, (size_t)c * 8));
+    k_walk_debug<<<1, 32>>>(g->view(), seed, stream, start, steps, mode, w0, w1, d_walk, d_len, d_pv, d_pc, cap, d_np);
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(walk_len, d_len, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(n_pairs, d_np, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(walk, d_walk, (size_t)(*walk_len) * 8, cudaMemcpyDeviceToHost));
+    const int64_t ncopy = std::min<int64_t>(*n_pairs, cap);
+    if (pair_v && ncopy > 0) CU(cudaMemcpy(pair_v, d_pv, (size_t)ncopy * 8, cudaMemcpyDeviceToHost));
+    if (pair_c && ncopy > 0) CU(cudaMemcpy(pair_c, d_pc, (size_t)ncopy * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_walk); cudaFree(d_len); cudaFree(d_np); cudaFree(d_pv); cudaFree(d_pc);
+    return SMORE_OK;
+}
+
+// ---- embedding store ----------------------------------------------------------------------------------------------
+int smore_model_create(smore_graph_t g, int dim, int n_tables, int dtype, smore_model_t* out) {
+    if (!g || !out) return fail(SMORE_E_INVALID, "null argument");
+    if (n_tables < 1 || n_tables > 2) return fail(SMORE_E_INVALID, "n_tables must be 1 or 2");
+    if (dtype != SMORE_F32 && dtype != SMORE_F64) return fail(SMORE_E_INVALID, "bad dtype");
+    if (dim <= 0) return fail(SMORE_E_INVALID, "dim must be positive");
+    if (int rc = ensure_device()) return rc;
+    smore_model_s* m = new smore_model_s();
+    m->g = g;
+    m->dim = dim;
+    m->n_tables = n_tables;
+    m->dtype = dtype;
+    for (int t = 0; t < n_tables; ++t) {
+        size_t bytes = (size_t)g->V * (size_t)dim * m->elem();
+        cudaError_t e = cudaMalloc(&m->tab[t], bytes);
+        if (e != cudaSuccess) {
+            delete m;
+            return fail(SMORE_E_NOMEM, "cudaMalloc of %zu bytes for table %d failed: %s", bytes, t, cudaGetErrorString(e));
+        }
+        cudaMemset(m->tab[t], 0, bytes);
+    }
+    *out = m;
+    return SMORE_OK;
+}
+
+void smore_model_destroy(smore_model_t m) { delete m; }
+
+int smore_model_init(smore_model_t m, int table, int random, uint64_t seed) {
+    if (!m || table < 0 || table >= m->n_tables) return fail(SMORE_E_INVALID, "bad model/table");
+    if (int rc = ensure_device()) return rc;
+    const int64_t n = m->g->V * (int64_t)m->dim;
+    const int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, 148 * 16);
+    if (m->dtype == SMORE_F64) k_init_table<double><<<blocks, 256>>>((double*)m->tab[table], n, m->dim, seed, kInitStreamBase + (uint64_t)table, random);
+    else k_init_table<float><<<blocks, 256>>>((float*)m->tab[table], n, m->dim, seed, kInitStreamBase + (uint64_t)table, random);
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return SMORE_OK;
+}
+
+
+int smore_model_set_rows(smore_model_t m, int table, int64_t first, int64_t n, const double* host) {
+    return rows_io<double>(m, table, first, n, const_cast<double*>(host), true);
+}
+int smore_model_get_rows(smore_model_t m, int table, int64_t first, int64_t n, double* host) {
+    return rows_io<double>(m, table, first, n, host, false);
+}
+int smore_model_set_rows_f32(smore_model_t m, int table, int64_t first, int64_t n, const float* host) {
+    return rows_io<float>(m, table, first, n, const_cast<float*>(host), true);
+}
+int smore_model_get_rows_f32(smore_model_t m, int table, int64_t first, int64_t n, float* host) {
+    return rows_io<float>(m, table, first, n, host, false);
+}
+
+int smore_model_device_ptr(smore_model_t m, int table, void** ptr) {
+    if (!m || table < 0 || table >= m->n_tables || !ptr) return fail(SMORE_E_INVALID, "bad model/table");
+    *ptr = m->tab[table];
+    return SMORE_OK;
+}
+
+int smore_model_save_weights(smore_model_t m, int table, const char* path, int format) {
+    if (!m || !path || table < 0 || table >= m->n_tables) return fail(SMORE_E_INVALID, "bad argument");
+    const int64_t V = m->g->V;
+    const int dim = m->dim;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(SMORE_E_IO, "cannot create %s", path);
+    fprintf(f, "%lld %d\n", (long long)V, dim);
+    const int64_t chunk = std::max<int64_t>(1, (64ll << 20) / ((int64_t)dim * 8));
+    std::vector<double> rows((size_t)chunk * (size_t)dim);
+    std::string line;
+    char num[64];
+    for (int64_t first = 0; first < V; first += chunk) {
+        const int64_t n = std::min(chunk, V - first);
+        int rc = smore_model_get_rows(m, table, first, n, rows.data());
+        if (rc) { fclose(f); return rc; }
+        for (int64_t r = 0; r < n; ++r) {
+            line.clear();
+            if (!m->g->names.empty()) line += m->g->names[(size_t)(first + r)];
+            else line += std::to_string(first + r);
+            for (int d = 0; d < dim; ++d) {
+                // format 0: ostream << double at default precision == "%g" (LINE.cpp:37); format 1: "%.6f" (line.go:226)
+                int len = snprintf(num, sizeof(num), format == 0 ? " %g" : " %.6f", rows[(size_t)r * dim + d]);
+                line.append(num, (size_t)len);
+            }
+            line += '\n';
+            fwrite(line.data(), 1, line.size(), f);
+        }
+    }
+    fclose(f);
+    return SMORE_OK;
+}
+
+// ---- training -----------------------------------------------------------------------------------------------------
+int smore_train_line(smore_model_t m, const smore_train_params* p) {
+    if (int rc = check_train(m, p, p && p->order == 1 ? 1 : 2)) return rc;
+    if (p->negative_samples < 0 || p->negative_samples > 31) return fail(SMORE_E_UNSUPPORTED, "negative_samples must be in [0,31]");
+    if (p->order != 1 && p->order != 2) return fail(SMORE_E_INVALID, "order must be 1 or 2");
+    return m->dtype == SMORE_F64 ? train_line_t<double>(m, p) : train_line_t<float>(m, p);
+}
+
+static int train_walk_common(smore_model_t m, const smore_train_params* p, int walklets) {
+    if (int rc = check_train(m, p, 2)) return rc;
+    if (p->negative_samples < 0 || p->negative_samples > 31) return fail(SMORE_E_UNSUPPORTED, "negative_samples must be in [0,31]");
+    if (p->walk_steps < 0 || p->walk_steps + 1 > kMaxWalkLen) return fail(SMORE_E_UNSUPPORTED, "walk_steps must be < %d", kMaxWalkLen);
+    if (p->window_max < 1 || p->window_max > 255) return fail(SMORE_E_INVALID, "window must be in [1,255]");
+    if (walklets && (p->window_min < 0 || p->window_min > p->window_max)) return fail(SMORE_E_INVALID, "need 0 <= window_min <= window_max");
+    if (walklets && p->semantics != SMORE_SEM_CPP) return fail(SMORE_E_UNSUPPORTED, "Walklets exists only in the C++ tree");
+    if (p->walk_times < 1) return fail(SMORE_E_INVALID, "walk_times must be >= 1");
+    return m->dtype == SMORE_F64 ? train_walk_t<double>(m, p, walklets) : train_walk_t<float>(m, p, walklets);
+}
+int smore_train_deepwalk(smore_model_t m, const smore_train_params* p) { return train_walk_common(m, p, 0); }
+int smore_train_walklets(smore_model_t m, const smore_train_params* p) { return train_walk_common(m, p, 1); }
+
+int smore_train_bpr(smore_model_t m, const smore_train_params* p) {
+    if (int rc = check_train(m, p, p && p->semantics == SMORE_SEM_GO ? 2 : 1)) return rc;
+    return m->dtype == SMORE_F64 ? train_ranking_t<double>(m, p, RANK_BPR) : train_ranking_t<float>(m, p, RANK_BPR);
+}
+int smore_train_warp(smore_model_t m, const smore_train_params* p) {
+    if (int rc = check_train(m, p, 1)) return rc;
+    if (p->semantics != SMORE_SEM_CPP) return fail(SMORE_E_UNSUPPORTED, "WARP exists only in the C++ tree");
+    return m->dtype == SMORE_F64 ? train_ranking_t<double>(m, p, RANK_WARP) : train_ranking_t<float>(m, p, RANK_WARP);
+}
+int smore_train_hoprec(smore_model_t m, const smore_train_params* p) {
+    if (int rc = check_train(m, p, 1)) return rc;
+    if (p->semantics != SMORE_SEM_CPP) return fail(SMORE_E_UNSUPPORTED, "HOP-Rec exists only in the C++ tree");
+    if (!m->g->has_field) return fail(SMORE_E_INVALID, "HOP-Rec needs field data (smore_graph_load_field / set_field)");
+    if (p->walk_steps < 1) return fail(SMORE_E_INVALID, "walk_steps must be >= 1");
+    return m->dtype == SMORE_F64 ? train_ranking_t<double>(m, p, RANK_HOPREC) : train_ranking_t<float>(m, p, RANK_HOPREC);
+}
+
+int smore_train_stats(smore_model_t m, uint64_t* samples, uint64_t* pair_updates, uint64_t* words_stream0,
+                      double* warp_mean_tries, double* kernel_ms) {
+    if (!m) return fail(SMORE_E_INVALID, "null model");
+    if (samples) *samples = m->st_samples;
+    if (pair_updates) *pair_updates = m->st_pairs;
+    if (words_stream0) *words_stream0 = m->st_words0;
+    if (warp_mean_tries) *warp_mean_tries = m->st_samples ? (double)m->st_tries / (double)m->st_samples : 0.0;
+    if (kernel_ms) *kernel_ms = m->st_ms;
+    return SMORE_OK;
+}
+
+}  // extern "C"
