@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- edge updates/sec of the sampled-SGD hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm: CUDA hot path through the C ABI
+  python bench.py --impl reference --steps K --warmup W    # reference arm: the reference's own CPU code
+
+Workload (config.workload): BASELINE.json configs[1] -- LINE 2nd order, dim 128, K = 5 negatives, synthetic power-law
+graph with 1M vertices / 10M weighted edges (undirected -> 20M CSR entries), C++-tree semantics, fp32 tables.
+A "step" is one Hogwild pass of `--batch` edge updates (default 2^24) over that graph. Tables (2 x 512 MB) plus graph
+(~0.5 GB) exceed the 126 MB L2, so no L2 flush is needed between steps.
+
+value : updates/s with graph + tables resident in HBM (timed: K train calls, CUDA events on the launching stream,
+        barrier + synchronize on both sides, max over ranks).
+e2e   : the same metric through the C ABI the way a host Train() call sees it: every step uploads both embedding
+        tables from pinned HOST memory, trains, and reads the vertex table back to the host.
+roofline : algorithmic bytes per update (2*(K+2)*D*4 + 76 = 7244 B) x updates / kernel time (the
+        library's own CUDA events around the kernel) against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline : the reference's CPU implementation timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM, K, V_TARGET, N_EDGES, GRAPH_SEED = 128, 5, 1_000_000, 10_000_000, 20261018
+ALGO_BYTES = 2 * (K + 2) * DIM * 4 + 76
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload_name(V, E):
+    return (f"LINE-2 dim={DIM} K={K} Hogwild fp32, synthetic power-law graph V={V} E_lines={N_EDGES} "
+            f"(undirected, {E} CSR entries) [BASELINE configs[1]]")
+
+
+def make_graph(scale=1.0):
+    from smore_b200 import synth
+
+    t0 = time.time()
+    nv, ne = int(V_TARGET * scale), int(N_EDGES * scale)
+    src, dst, w = synth.power_law_edges(nv, ne, GRAPH_SEED)
+    off, col, ww, labels = synth.csr_from_edges(src, dst, w, undirected=True)
+    log(f"[bench] graph: V={len(off) - 1} E={len(col)} generated in {time.time() - t0:.1f}s")
+    return (src, dst, w), (off, col, ww)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_baseline(edges, csr, seconds_target=12.0, cores=None):
+    """Reference CPU path on this box's host cores: the compiled reference (kind "reference": unmodified sources, its own
+    flags -Ofast -fopenmp and its own RNG) when oracle/_ref travelled here, else the oracle restatement (kind "port")."""
+    from oracle import bindings as B
+
+    cores = cores or os.cpu_count() or 1
+    if B.ref_available(fast=True):
+        src, dst, w = edges
+        tmp = tempfile.NamedTemporaryFile(suffix=".txt", delete=False)
+        tmp.close()
+        t0 = time.time()
+        B.write_edge_list_fast(tmp.name, src, dst, w)
+        ref = B.Ref(B.K_LINE, tmp.name, True, DIM, order=2, fast=True)
+        os.unlink(tmp.name)
+        log(f"[bench] reference loaded the graph in {time.time() - t0:.1f}s (V={ref.V})")
+        # LINE::Train granularity is sample_times x 1e6 updates; calibrate on 1M, then one bounded run
+        t0 = time.time()
+        ref.train(1, K, alpha=0.025, workers=cores)
+        t1 = time.time() - t0
+        s = int(max(1, min(64, seconds_target / max(t1, 1e-3))))
+        t0 = time.time()
+        ref.train(s, K, alpha=0.025, workers=cores)
+        dt = time.time() - t0
+        updates = s * 1_000_000
+        return {"value": updates / dt, "unit": "updates/s", "cores": cores, "kind": "reference",
+                "sample": f"LINE::Train(sample_times={s}) = {updates} updates on the same graph, {cores} OpenMP threads, "
+                          f"{dt:.1f}s (compiled from the unmodified reference sources with its own flags)"}
+    off, col, ww = csr
+    g = B.OracleGraph(B.SEM_CPP, off, col, ww)
+    rng = np.random.RandomState(0)
+    Wv = (rng.random_sample((g.V, DIM)) - 0.5) / DIM
+    Wc = np.zeros((g.V, DIM))
+    n = 200_000 * cores
+    t = g.time_line_cpp(Wv, Wc, K, 0.025, n, 1, cores)
+    n = int(n * max(1.0, seconds_target / max(t, 1e-3)))
+    t = g.time_line_cpp(Wv, Wc, K, 0.025, n, 1, cores)
+    return {"value": n / t, "unit": "updates/s", "cores": cores, "kind": "port",
+            "sample": f"{n} updates of the oracle restatement (oracle/smore_oracle.cpp, -O2 -fopenmp), {cores} threads, {t:.1f}s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    edges, csr = make_graph(args.scale)
+    per_step = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline(edges, csr, seconds_target=per_step)
+        if i >= args.warmup:
+            vals.append(base["value"])
+    v = float(np.mean(vals)) if vals else base["value"]
+    base["value"] = v
+    V, E = len(csr[0]) - 1, len(csr[1])
+    print(json.dumps({
+        "impl": "reference", "metric": "edge_updates_per_sec", "value": v, "unit": "updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(V, E)},
+        "cpu_baseline": base, "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from smore_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: smore_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    capi.check(capi.lib().smore_init(local))
+
+    edges, csr = make_graph(args.scale)
+    off, col, ww = csr
+    t0 = time.time()
+    g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP)
+    log(f"[bench] rank {rank}: alias tables built + uploaded in {time.time() - t0:.1f}s")
+    m = capi.Model(g, DIM, 2, capi.F32)
+    m.init(0, True, seed=1)
+    m.init(1, False, seed=1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    p = capi.default_params()
+    p.semantics, p.mode, p.seed, p.alpha = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 0.025
+    p.negative_samples, p.order, p.total = K, 2, args.batch
+    step_no = [0]
+
+    def step():
+        # fresh Philox sub-streams every step (stream ids never repeat across steps / ranks)
+        p.stream_base = (step_no[0] * world + rank) * (1 << 20)
+        step_no[0] += 1
+        return m.train_line(p)
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(args.warmup):
+        step()
+    launches0 = capi.kernel_launches()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    updates = 0
+    kernel_ms = 0.0
+    for _ in range(args.steps):
+        st = step()
+        updates += st["samples"]
+        kernel_ms += st["kernel_ms"]
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    launches = capi.kernel_launches() - launches0
+
+    # ---- e2e: host buffers in, host buffers out, every step ----
+    V = g.V
+    hv = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
+    hc = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
+    m.get_rows(0, out=hv.numpy())
+    m.get_rows(1, out=hc.numpy())
+    hout = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        m.set_rows(0, hv.numpy())
+        m.set_rows(1, hc.numpy())
+        st = step()
+        m.get_rows(0, out=hout.numpy())
+        return st
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_updates = 0
+    for _ in range(args.steps):
+        e2e_updates += e2e_step()["samples"]
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    stats = torch.tensor([ms, e2e_ms, float(updates), float(e2e_updates), kernel_ms, float(launches)], dtype=torch.float64,
+                         device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_ms, kernel_ms = mx[0].item(), mx[1].item(), mx[4].item()
+        updates, e2e_updates, launches = sm[2].item(), sm[3].item(), sm[5].item()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+    # dominant kernel = k_line: per-rank algorithmic bytes / its own CUDA-event time
+    per_rank_updates = updates / world
+    achieved = per_rank_updates * ALGO_BYTES / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_k_line.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = {
+        "metric": "edge_updates_per_sec", "value": updates / (ms * 1e-3), "unit": "updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(g.V, g.E), "updates_per_step_per_gpu": args.batch,
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (weak scaling)",
+                   "l2": "working set (1.0 GB tables + 0.5 GB graph) exceeds the 126 MB L2; no flush between steps"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "k_line<float,4,1>", "algorithmic_bytes_per_update": ALGO_BYTES,
+                     "peak_source": peak_src},
+        "e2e": {"value": e2e_updates / (e2e_ms * 1e-3), "unit": "updates/s",
+                "h2d_bytes_per_step": 2 * V * DIM * 4, "d2h_bytes_per_step": V * DIM * 4,
+                "note": "per step: both tables uploaded from pinned host memory, Train call, vertex table read back"},
+        "gpu_launches": int(launches), "clocks": clk,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline(edges, csr)
+        except Exception as ex:  # the baseline is reporting only; never lose the GPU line
+            out["cpu_baseline"] = {"value": None, "unit": "updates/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 24, help="edge updates per step per GPU")
+    ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = configs[1])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -114,6 +114,7 @@ class Oracle:
             L.orc_update_fbpr_pair_cpp.restype = u64
             L.orc_time_line_cpp.argtypes = [vp, vp, vp, C.c_int, C.c_int, f64, u64, u64, C.c_int]
             L.orc_time_line_cpp.restype = f64
+            L.orc_write_edge_list.argtypes = [C.c_char_p, vp, vp, vp, i64]
             cls._lib = L
         return cls._lib
 
@@ -418,6 +419,15 @@ class Ref:
     def save_weights(self, path):
         with quiet():
             self.L.ref_save_weights(self.h, path.encode())
+
+
+def write_edge_list_fast(path, src, dst, w):
+    """Same format as write_edge_list (names "v<label>"), written from C for multi-million-line files."""
+    src = np.ascontiguousarray(src, dtype=np.int64)
+    dst = np.ascontiguousarray(dst, dtype=np.int64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    if Oracle.lib().orc_write_edge_list(os.fsencode(path), _ptr(src), _ptr(dst), _ptr(w), len(src)) != 0:
+        raise OSError(f"cannot write {path}")
 
 
 def write_edge_list(path, src, dst, w, names=None):

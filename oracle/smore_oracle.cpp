@@ -837,6 +837,17 @@ uint64_t orc_update_fbpr_pair_cpp(void* h, double* W, int64_t v, int64_t ci, int
     return d.s.pos;
 }
 
+// Text edge list for the compiled reference's LoadEdgeList ("v<src> v<dst> <weight>" per line; bench/test helper).
+int orc_write_edge_list(const char* path, const int64_t* src, const int64_t* dst, const double* w, int64_t n) {
+    FILE* f = fopen(path, "wb");
+    if (!f) return -1;
+    std::vector<char> buf(1 << 22);
+    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    for (int64_t i = 0; i < n; ++i) fprintf(f, "v%lld v%lld %g\n", (long long)src[i], (long long)dst[i], w[i]);
+    fclose(f);
+    return 0;
+}
+
 // ---- multi-threaded Hogwild timing leg (bench.py cpu_baseline "port"): LINE-2 C++ semantics, one stream per thread,
 // per-thread schedule as in LINE.cpp:162-191 with `workers` threads.
 double orc_time_line_cpp(void* h, double* Wv, double* Wc, int dim, int K, double alpha, uint64_t total, uint64_t seed,
