@@ -47,24 +47,24 @@ struct TrainArgs {
 // ---------------------------------------------------------------------------------------------------------------
 template <class C>
 __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T* Wc, int dim, bool same_table,
-                                                const typename C::T* lut, int64_t v1, int64_t my_id, int nrows,
+                                                const typename C::T* lut, int v1, int my_id, int nrows,
                                                 typename C::T alpha, int lane) {
     using T = typename C::T;
     bool active = lane < nrows;
-    unsigned peers = __match_any_sync(kFull, active ? my_id : (int64_t)(-1 - lane));
+    unsigned peers = __match_any_sync(kFull, active ? my_id : (-1 - lane));
     bool dup = __any_sync(kFull, (active && __popc(peers) > 1) || (active && same_table && my_id == v1));
-    T* pv = Wv + v1 * dim;
+    T* pv = Wv + (size_t)v1 * dim;
     if (!dup) {
         Row<C> v, back;
         v.load(pv, lane, dim);
         back.zero();
         for (int base = 0; base < nrows; base += kCtxChunk) {
             Row<C> c[kCtxChunk];
-            int64_t ids[kCtxChunk];
+            int ids[kCtxChunk];
 #pragma unroll
             for (int r = 0; r < kCtxChunk; ++r) {
                 ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
-                if (base + r < nrows) c[r].load(Wc + ids[r] * dim, lane, dim);
+                if (base + r < nrows) c[r].load(Wc + (size_t)ids[r] * dim, lane, dim);
             }
             T f[kCtxChunk];
 #pragma unroll
@@ -84,7 +84,7 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
                         back.x[e] += g * c[r].x[e];
                         c[r].x[e] += g * v.x[e];
                     }
-                    c[r].store(Wc + ids[r] * dim, lane, dim);
+                    c[r].store(Wc + (size_t)ids[r] * dim, lane, dim);
                 }
             }
         }
@@ -95,8 +95,8 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
         Row<C> back;
         back.zero();
         for (int r = 0; r < nrows; ++r) {
-            int64_t cid = __shfl_sync(kFull, my_id, r);
-            T* pc = Wc + cid * dim;
+            int cid = __shfl_sync(kFull, my_id, r);
+            T* pc = Wc + (size_t)cid * dim;
             Row<C> v, c;
             v.load(pv, lane, dim);
             c.load(pc, lane, dim);
@@ -125,18 +125,18 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
 // ---------------------------------------------------------------------------------------------------------------
 template <class C>
 __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T* Wc, int dim, bool same_table,
-                                               bool skip_source, const typename C::T* lut, int64_t v1, int64_t my_id,
+                                               bool skip_source, const typename C::T* lut, int v1, int my_id,
                                                int nrows, typename C::T alpha, int lane) {
     using T = typename C::T;
-    int64_t ctx = __shfl_sync(kFull, my_id, 0);
+    int ctx = __shfl_sync(kFull, my_id, 0);
     bool active = lane < nrows;
     bool skipped = active && lane > 0 && (my_id == ctx || (skip_source && my_id == v1));
     unsigned skipmask = __ballot_sync(kFull, skipped);
     bool live = active && !skipped;
-    unsigned peers = __match_any_sync(kFull, live ? my_id : (int64_t)(-1 - lane));
+    unsigned peers = __match_any_sync(kFull, live ? my_id : (-1 - lane));
     bool dup = __any_sync(kFull, (live && __popc(peers) > 1) || (live && same_table && my_id == v1));
-    T* pv = Wv + v1 * dim;
-    T* pp = Wc + ctx * dim;
+    T* pv = Wv + (size_t)v1 * dim;
+    T* pp = Wc + (size_t)ctx * dim;
     if (!dup) {
         Row<C> v, vgrad, pos, cgrad;
         v.load(pv, lane, dim);
@@ -151,13 +151,13 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
         }
         for (int base = 1; base < nrows; base += kCtxChunk) {
             Row<C> c[kCtxChunk];
-            int64_t ids[kCtxChunk];
+            int ids[kCtxChunk];
             bool ok[kCtxChunk];
 #pragma unroll
             for (int r = 0; r < kCtxChunk; ++r) {
                 ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
                 ok[r] = (base + r < nrows) && !((skipmask >> ((base + r) & 31)) & 1u);
-                if (ok[r]) c[r].load(Wc + ids[r] * dim, lane, dim);
+                if (ok[r]) c[r].load(Wc + (size_t)ids[r] * dim, lane, dim);
             }
             T f[kCtxChunk];
 #pragma unroll
@@ -176,7 +176,7 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
                         vgrad.x[e] += g * c[r].x[e];
                         c[r].x[e] += g * v.x[e];
                     }
-                    c[r].store(Wc + ids[r] * dim, lane, dim);
+                    c[r].store(Wc + (size_t)ids[r] * dim, lane, dim);
                 }
             }
         }
@@ -202,8 +202,8 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
         }
         for (int r = 1; r < nrows; ++r) {
             if ((skipmask >> r) & 1u) continue;
-            int64_t cid = __shfl_sync(kFull, my_id, r);
-            T* pc = Wc + cid * dim;
+            int cid = __shfl_sync(kFull, my_id, r);
+            T* pc = Wc + (size_t)cid * dim;
             Row<C> v, c;
             v.load(pv, lane, dim);
             c.load(pc, lane, dim);
@@ -231,13 +231,13 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
 }
 
 // Draw the K negatives of one pair from ring words [off, off+2K) into lanes 1..K; lane 0 keeps `ctx`.
-__device__ __forceinline__ int64_t draw_pair_ids(const GraphDev& g, const DrawRing& ring, uint32_t off, int64_t ctx,
-                                                 int K, int lane) {
-    int64_t my = ctx;
+__device__ __forceinline__ int draw_pair_ids(const GraphDev& g, const DrawRing& ring, uint32_t off, int ctx,
+                                             int K, int lane) {
+    int my = ctx;
     if (lane >= 1 && lane <= K) {
         uint32_t w0 = ring.peek(off + 2u * (uint32_t)(lane - 1));
         uint32_t w1 = ring.peek(off + 2u * (uint32_t)(lane - 1) + 1u);
-        my = (int64_t)negative_sample(g, w0, w1);
+        my = (int)negative_sample(g, w0, w1);
     }
     return my;
 }
@@ -255,53 +255,101 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 
 // ---------------------------------------------------------------------------------------------------------------
 // LINE: LINE::Train (src/model/LINE.cpp:100-195) / LINE.Train (internal/models/line/line.go:73-150)
+//
+// A sample consumes a FIXED number of stream words (C++: p,idx | p,idx | K x (idx,p) = 4+2K; Go: idx,p | r |
+// K x (idx,p) = 3+2K), so sample s of a worker owns words [s*wps, (s+1)*wps) of its stream. The warp therefore resolves
+// 32 samples at a time, one per lane: the Philox words of the batch are generated cooperatively into shared memory,
+// every lane walks its own source -> target chain and looks up its K negatives (32 dependent chains in flight per warp
+// instead of one), ids are parked in shared memory, and the warp then applies the 32 updates in stream order.
+// (A source is never a sink -- zero out-weight gets alias probability 0 -- so the "skip" branch of line.go:121-124,
+// which would shorten a sample to 2 words, cannot fire; if it ever did the sample is dropped at fixed width.)
+// Shared memory: LUT | per warp: word buffer [32*wps + 8] | ids [32*(K+2)].
 // ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int line_wps(int go, int K) { return (go ? 3 : 4) + 2 * K; }
+__host__ __device__ inline int line_wbuf_words(int go, int K) { return ((32 * line_wps(go, K) + 8 + 3) / 4) * 4; }
+template <typename T>
+inline size_t line_smem_bytes(int go, int K) {
+    return 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(line_wbuf_words(go, K) + 32 * (K + 2)) * 4;
+}
+
+// resident CTAs per SM the register allocator must allow: 3 while a row costs <= 16 B per lane (fp32 dim <= 128)
 template <class C>
-__global__ void __launch_bounds__(kBlockThreads) k_line(TrainArgs<typename C::T> a) {
+constexpr int line_min_blocks() {
+    return C::EPL * (int)sizeof(typename C::T) <= 16 ? 3 : C::EPL * (int)sizeof(typename C::T) <= 32 ? 2 : 1;
+}
+
+template <class C, bool GO>
+__global__ void __launch_bounds__(kBlockThreads, line_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
     using T = typename C::T;
-    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
-    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
+    T* lut_s = reinterpret_cast<T*>(smem_raw);
     const T* lut = stage_lut<T>(a.lut, lut_s);
-    int lane = threadIdx.x & 31;
-    int wib = threadIdx.x >> 5;
-    int w = blockIdx.x * kWarpsPerBlock + wib;
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kWarpsPerBlock + wib;
     if (w >= a.n_warps) return;
+    const int K = a.K;
+    const int wps = line_wps(GO, K);
+    const int wcap = line_wbuf_words(GO, K);
+    const int idw = K + 2;
+    uint32_t* wbuf = reinterpret_cast<uint32_t*>(smem_raw + 1008 * sizeof(T)) + (size_t)wib * (wcap + 32 * idw);
+    int* ids = reinterpret_cast<int*>(wbuf + wcap);
     WarpState st = a.state[w];
-    DrawRing ring;
-    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
     const GraphDev& g = a.g;
-    const bool go = g.sem != 0;
-    const uint32_t neg_off = go ? 3u : 4u;
-    const int nrows = a.K + 1;
-    for (uint64_t it = 0; it < a.jobs; ++it) {
-        ring.ensure();
-        // negatives first (independent loads), then the dependent source -> target chain on lane 0
-        int64_t my = draw_pair_ids(g, ring, neg_off, -1, a.K, lane);
-        int64_t v1 = -1, v2 = -1;
-        int used = 0;
-        if (lane == 0) {
-            v1 = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
+    const uint64_t stream = a.stream_base + (uint64_t)w;
+    const uint32_t V32 = (uint32_t)g.V;
+    const int nrows = K + 1;
+    for (uint64_t done = 0; done < a.jobs; done += 32) {
+        const int nb = (int)min((uint64_t)32, a.jobs - done);
+        // 1. Philox words of the batch -> shared
+        const uint64_t first_blk = st.pos >> 2;
+        const int nblk = (int)(((st.pos + (uint64_t)(nb * wps) + 3) >> 2) - first_blk);
+        __syncwarp();
+        for (int b = lane; b < nblk; b += 32) {
+            U4 r = philox_block(a.seed, stream, first_blk + (uint64_t)b);
+            *reinterpret_cast<uint4*>(wbuf + 4 * b) = make_uint4(r.x, r.y, r.z, r.w);
+        }
+        __syncwarp();
+        // 2. one sample per lane: negatives (independent lookups) first, then the source -> target chain
+        if (lane < nb) {
+            const uint32_t* wd = wbuf + ((uint32_t)st.pos & 3u) + lane * wps;
+            int* my_ids = ids + lane * idw;
+            const int noff = GO ? 3 : 4;
+            for (int n0 = 0; n0 < K; n0 += 8) {
+                uint32_t idx[8];
+                uint2 e[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (n0 + j < K) {
+                        idx[j] = index_draw(wd[noff + 2 * (n0 + j)], V32);
+                        e[j] = __ldg(g.negative_at + idx[j]);
+                    }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (n0 + j < K) my_ids[2 + n0 + j] = (int)(wd[noff + 2 * (n0 + j) + 1] < e[j].x ? idx[j] : e[j].y);
+            }
+            const int v1 = (int)source_sample(g, wd[0], wd[1]);
             int u;
-            v2 = target_sample(g, v1, ring.peek(2), ring.peek(3), u);
-            used = 2 + u;
+            const int v2 = (int)target_sample(g, v1, wd[2], GO ? 0u : wd[3], u);
+            my_ids[0] = v1;
+            my_ids[1] = v2;
         }
-        v1 = __shfl_sync(kFull, v1, 0);
-        v2 = __shfl_sync(kFull, v2, 0);
-        used = __shfl_sync(kFull, used, 0);
-        if (v2 < 0) {  // sink source: Go skips the sample without counting it (line.go:121-124); C++ never draws one
-            ring.advance((uint32_t)used);
-            continue;
+        st.pos += (uint64_t)(nb * wps);
+        __syncwarp();
+        // 3. the updates, in stream order
+        for (int s = 0; s < nb; ++s) {
+            const int* sid = ids + s * idw;
+            const int v1 = sid[0];
+            const int v2 = sid[1];
+            const int my = lane < nrows ? sid[1 + lane] : (-1 - lane);
+            if (v2 < 0) continue;
+            const T alpha = (T)st.alpha;
+            if (!GO) update_pair_cpp<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, lut, v1, my, nrows, alpha, lane);
+            else update_pair_go<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, a.order == 1, lut, v1, my, nrows, alpha, lane);
+            st.count++;
+            st.pairs++;
+            sched_tick(st, a.sched);
         }
-        ring.advance(neg_off + 2u * (uint32_t)a.K);
-        if (lane == 0) my = v2;
-        T alpha = (T)st.alpha;
-        if (!go) update_pair_cpp<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, lut, v1, my, nrows, alpha, lane);
-        else update_pair_go<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, a.order == 1, lut, v1, my, nrows, alpha, lane);
-        st.count++;
-        st.pairs++;
-        sched_tick(st, a.sched);
     }
-    st.pos = ring.pos;
     if (lane == 0) a.state[w] = st;
 }
 
@@ -387,7 +435,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_walk(TrainArgs<typename C::T>
         if (!go && !a.walklets) draw_windows(ring, len, a.w1, reduce, lane);
         T alpha = (T)st.alpha;
         for (int i = 0; i < len; ++i) {
-            int64_t vi = walk[i];
+            int vi = walk[i];
             // the (up to two) index ranges of contexts for centre i
             int lo[2], hi[2];
             if (a.walklets) {  // ScaleSkipGrams (src/proNet.cpp:939-978)
@@ -406,7 +454,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_walk(TrainArgs<typename C::T>
                 for (int j = lo[part]; j <= hi[part]; ++j) {
                     if (j == i) continue;
                     ring.ensure();
-                    int64_t my = draw_pair_ids(g, ring, 0u, (int64_t)walk[j], a.K, lane);
+                    int my = draw_pair_ids(g, ring, 0u, walk[j], a.K, lane);
                     ring.advance(2u * (uint32_t)a.K);
                     if (!go) update_pair_cpp<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, lut, vi, my, nrows, alpha, lane);
                     else update_pair_go<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, false, lut, vi, my, nrows, alpha, lane);

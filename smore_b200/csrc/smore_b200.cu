@@ -43,6 +43,8 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 int ensure_device() {
+    static thread_local int checked_dev = -2;
+    if (checked_dev == g_device && g_device >= 0) return SMORE_OK;  // cudaGetDeviceProperties costs milliseconds
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
@@ -56,6 +58,7 @@ int ensure_device() {
         return fail(SMORE_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
     CU(cudaSetDevice(dev));
     g_device = dev;
+    checked_dev = dev;
     return SMORE_OK;
 }
 
@@ -349,9 +352,10 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
     const int vtab = 0, ctab = p->order == 1 ? 0 : 1;
     return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
         using C = decltype(cfg);
-        auto kern = k_line<C>;
-        const size_t smem = smem_line<T>();
         const bool cpp = p->semantics == SMORE_SEM_CPP;
+        void (*kern)(TrainArgs<T>) = cpp ? k_line<C, false> : k_line<C, true>;
+        const size_t smem = line_smem_bytes<T>(cpp ? 0 : 1, p->negative_samples);
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
         else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
