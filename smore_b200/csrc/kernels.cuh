@@ -18,6 +18,10 @@ constexpr int kWarpsPerBlock = 8;
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 constexpr int kCtxChunk = 6;      // context rows gathered per batch (1 positive + 5 negatives = the default K)
 constexpr int kMaxWalkLen = 256;  // walk_steps + 1 <= kMaxWalkLen
+#ifndef SMORE_LINE_PREFETCH
+#define SMORE_LINE_PREFETCH 2
+#endif
+constexpr int kLinePrefetch = SMORE_LINE_PREFETCH;  // L2 prefetch distance (samples) inside a batch
 
 template <typename T>
 struct TrainArgs {
@@ -335,8 +339,21 @@ __global__ void __launch_bounds__(kBlockThreads, line_min_blocks<C>()) k_line(Tr
         }
         st.pos += (uint64_t)(nb * wps);
         __syncwarp();
-        // 3. the updates, in stream order
+        // 3. the updates, in stream order; rows of the sample kLinePrefetch ahead are pulled into L2 meanwhile
+        const int lines_per_row = (a.dim * (int)sizeof(T) + 127) >> 7;
+        const int pf_total = idw * lines_per_row;
         for (int s = 0; s < nb; ++s) {
+            if (s + kLinePrefetch < nb) {
+                const int* pid = ids + (s + kLinePrefetch) * idw;
+                for (int t = lane; t < pf_total; t += 32) {
+                    const int r = t / lines_per_row, ln = t - r * lines_per_row;
+                    const int id = pid[r];
+                    if (id >= 0) {
+                        const char* p = reinterpret_cast<const char*>((r == 0 ? a.Wv : a.Wc) + (size_t)id * a.dim) + (ln << 7);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                    }
+                }
+            }
             const int* sid = ids + s * idw;
             const int v1 = sid[0];
             const int v2 = sid[1];
