@@ -1,0 +1,307 @@
+// Batch-sampled trainers: LINE, BPR (Go), BPR (C++).
+//
+// In these loops a sample consumes a FIXED number of stream words:
+//     C++:  SourceSample p,idx | TargetSample p,idx | K x NegativeSample idx,p      = 4 + 2K   (src/proNet.cpp:623-683)
+//     Go :  aliasSample idx,p  | TargetSample r     | K x aliasSample idx,p         = 3 + 2K   (alias.go:93-106,
+//                                                                                               pronet.go:257-284)
+// so sample s of a worker owns words [s*wps, (s+1)*wps) of its stream and the draws of different samples are
+// independent of each other and of the embeddings. The warp resolves 32 samples at a time, ONE PER LANE: the Philox
+// words of the batch are generated cooperatively into shared memory, every lane walks its own source -> target chain
+// and looks up its K negatives (32 dependent lookup chains in flight per warp instead of one), the ids are parked in
+// shared memory, and the warp then applies the 32 updates in stream order while prefetching the rows of the sample
+// kLinePrefetch ahead into L2. Word accounting is identical to a worker that samples one at a time, which is what the
+// DETERMINISTIC mode (one warp) relies on.
+// (A source is never a sink -- zero out-weight gets alias probability 0 -- so the Go "skip" branch of line.go:121-124 /
+// bpr.go:103-106, which would shorten a sample to 2 words, cannot fire; if it ever did the sample is dropped at fixed
+// width.)
+//
+// Shared memory: sigmoid LUT | per warp: word buffer [32*wps + 8] | ids [32*(K+2)]  (ids row = v1, v2, neg_0..neg_K-1)
+#pragma once
+#include "kernels.cuh"
+#include "ranking_kernels.cuh"
+
+namespace smore {
+
+__host__ __device__ inline int batch_wps(int go, int K) { return (go ? 3 : 4) + 2 * K; }
+__host__ __device__ inline int batch_wbuf_words(int go, int K) { return ((32 * batch_wps(go, K) + 8 + 3) / 4) * 4; }
+template <typename T>
+inline size_t batch_smem_bytes(int go, int K) {
+    return 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(batch_wbuf_words(go, K) + 32 * (K + 2)) * 4;
+}
+
+// resident CTAs per SM the register allocator must allow: 3 while a row costs <= 16 B per lane (fp32 dim <= 128)
+template <class C>
+constexpr int batch_min_blocks() {
+    return C::EPL * (int)sizeof(typename C::T) <= 16 ? 3 : C::EPL * (int)sizeof(typename C::T) <= 32 ? 2 : 1;
+}
+
+struct Batch {
+    uint32_t* wbuf;
+    int* ids;
+    int K, wps, idw;
+};
+
+template <typename T>
+__device__ __forceinline__ Batch batch_init(int go, int K, int wib) {
+    Batch b;
+    b.K = K;
+    b.wps = batch_wps(go, K);
+    b.idw = K + 2;
+    const int wcap = batch_wbuf_words(go, K);
+    b.wbuf = reinterpret_cast<uint32_t*>(smem_raw + 1008 * sizeof(T)) + (size_t)wib * (wcap + 32 * b.idw);
+    b.ids = reinterpret_cast<int*>(b.wbuf + wcap);
+    return b;
+}
+
+// Stages 1+2: words of samples [st.pos/wps, +nb) -> shared; one sample per lane -> ids. Advances st.pos.
+template <bool GO>
+__device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, uint64_t seed, uint64_t stream,
+                                             WarpState& st, int nb, int lane) {
+    const uint64_t first_blk = st.pos >> 2;
+    const int nblk = (int)(((st.pos + (uint64_t)(nb * b.wps) + 3) >> 2) - first_blk);
+    __syncwarp();
+    for (int k = lane; k < nblk; k += 32) {
+        U4 r = philox_block(seed, stream, first_blk + (uint64_t)k);
+        *reinterpret_cast<uint4*>(b.wbuf + 4 * k) = make_uint4(r.x, r.y, r.z, r.w);
+    }
+    __syncwarp();
+    if (lane < nb) {
+        const uint32_t* wd = b.wbuf + ((uint32_t)st.pos & 3u) + lane * b.wps;
+        int* my_ids = b.ids + lane * b.idw;
+        const uint32_t V32 = (uint32_t)g.V;
+        constexpr int noff = GO ? 3 : 4;
+        // negatives first: independent lookups, issued 8 at a time
+        for (int n0 = 0; n0 < b.K; n0 += 8) {
+            uint32_t idx[8];
+            uint2 e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n0 + j < b.K) {
+                    idx[j] = index_draw(wd[noff + 2 * (n0 + j)], V32);
+                    e[j] = __ldg(g.negative_at + idx[j]);
+                }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n0 + j < b.K) my_ids[2 + n0 + j] = (int)(wd[noff + 2 * (n0 + j) + 1] < e[j].x ? idx[j] : e[j].y);
+        }
+        // then the dependent source -> target chain
+        const int v1 = (int)source_sample(g, wd[0], wd[1]);
+        int u;
+        const int v2 = (int)target_sample(g, v1, wd[2], GO ? 0u : wd[3], u);
+        my_ids[0] = v1;
+        my_ids[1] = v2;
+    }
+    st.pos += (uint64_t)(nb * b.wps);
+    __syncwarp();
+}
+
+// L2 prefetch of every row of one sample (ids row `pid`: slot 0 lives in Wv, the others in Wc).
+template <typename T>
+__device__ __forceinline__ void prefetch_sample(const T* Wv, const T* Wc, const int* pid, int idw, int dim, int lane) {
+    const int lines_per_row = (dim * (int)sizeof(T) + 127) >> 7;
+    const int total = idw * lines_per_row;
+    for (int t = lane; t < total; t += 32) {
+        const int r = t / lines_per_row, ln = t - r * lines_per_row;
+        const int id = pid[r];
+        if (id >= 0) {
+            const char* p = reinterpret_cast<const char*>((r == 0 ? Wv : Wc) + (size_t)id * dim) + (ln << 7);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LINE: LINE::Train (src/model/LINE.cpp:100-195) / LINE.Train (internal/models/line/line.go:73-150)
+// ---------------------------------------------------------------------------------------------------------------
+template <class C, bool GO>
+__global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    const Batch b = batch_init<T>(GO, a.K, wib);
+    WarpState st = a.state[w];
+    const uint64_t stream = a.stream_base + (uint64_t)w;
+    const int nrows = a.K + 1;
+    for (uint64_t done = 0; done < a.jobs; done += 32) {
+        const int nb = (int)min((uint64_t)32, a.jobs - done);
+        batch_sample<GO>(a.g, b, a.seed, stream, st, nb, lane);
+        for (int s = 0; s < nb; ++s) {
+            if (s + kLinePrefetch < nb) prefetch_sample<T>(a.Wv, a.Wc, b.ids + (s + kLinePrefetch) * b.idw, b.idw, a.dim, lane);
+            const int* sid = b.ids + s * b.idw;
+            const int v1 = sid[0];
+            const int v2 = sid[1];
+            const int my = lane < nrows ? sid[1 + lane] : (-1 - lane);  // lane 0: positive context, lane 1+n: negative n
+            if (v2 < 0) continue;
+            const T alpha = (T)st.alpha;
+            if (!GO) update_pair_cpp<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, lut, v1, my, nrows, alpha, lane);
+            else update_pair_go<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, a.order == 1, lut, v1, my, nrows, alpha, lane);
+            st.count++;
+            st.pairs++;
+            sched_tick(st, a.sched);
+        }
+    }
+    if (lane == 0) a.state[w] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Go BPR: BPR.Train (internal/models/bpr/bpr.go:84-131) + UpdateBPRPair (pkg/pronet/optimizer.go:87-117).
+// 5 words per sample (K = 1); ids row = user, pos, neg. Users live in Wv, items in Wc.
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    const Batch b = batch_init<T>(1, 1, wib);
+    WarpState st = a.state[w];
+    const uint64_t stream = a.stream_base + (uint64_t)w;
+    const int dim = a.dim;
+    for (uint64_t done = 0; done < a.jobs; done += 32) {
+        const int nb = (int)min((uint64_t)32, a.jobs - done);
+        batch_sample<true>(a.g, b, a.seed, stream, st, nb, lane);
+        for (int s = 0; s < nb; ++s) {
+            if (s + kLinePrefetch < nb) prefetch_sample<T>(a.Wv, a.Wc, b.ids + (s + kLinePrefetch) * b.idw, b.idw, dim, lane);
+            const int* sid = b.ids + s * b.idw;
+            const int user = sid[0], pos = sid[1], neg = sid[2];
+            if (pos < 0) continue;
+            const T alpha = (T)st.alpha;
+            const T la = a.lambda * alpha;  // lambda*alpha*w evaluates left to right
+            T* pv = a.Wv + (size_t)user * dim;
+            T* pp = a.Wc + (size_t)pos * dim;
+            T* pn = a.Wc + (size_t)neg * dim;
+            const bool same = pos == neg;
+            const bool valias = a.same_table && (user == pos || user == neg);
+            Row<C> v, p, n;
+            v.load(pv, lane, dim);
+            p.load(pp, lane, dim);
+            n.load(pn, lane, dim);
+            T ps = dot_partial(v, p), ns = dot_partial(v, n);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ps += __shfl_xor_sync(kFull, ps, o);
+                ns += __shfl_xor_sync(kFull, ns, o);
+            }
+            const T gc = alpha * fast_sigmoid<T>(lut, ns - ps);
+            if (!valias) {
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) {
+                    const T vg = gc * (p.x[e] - n.x[e]);
+                    const T pg = gc * v.x[e];
+                    const T ng = -gc * v.x[e];
+                    v.x[e] += vg - la * v.x[e];
+                    p.x[e] += pg - la * p.x[e];
+                    const T ncur = same ? p.x[e] : n.x[e];  // pos == neg: the second write lands on the updated row
+                    n.x[e] = ncur + (ng - la * ncur);
+                }
+                v.store(pv, lane, dim);
+                if (!same) p.store(pp, lane, dim);
+                n.store(pn, lane, dim);
+            } else {
+                // one shared table and the user row coincides with an item row: replay through memory
+                for_owned<C>(lane, dim, [&](int, int idx) {
+                    const T vg = gc * (ldv(pp + idx) - ldv(pn + idx));
+                    const T pg = gc * ldv(pv + idx);
+                    const T ng = -gc * ldv(pv + idx);
+                    stv(pv + idx, ldv(pv + idx) + (vg - la * ldv(pv + idx)));
+                    stv(pp + idx, ldv(pp + idx) + (pg - la * ldv(pp + idx)));
+                    stv(pn + idx, ldv(pn + idx) + (ng - la * ldv(pn + idx)));
+                });
+            }
+            st.count++;
+            st.pairs++;
+            sched_tick(st, a.sched);
+        }
+    }
+    if (lane == 0) a.state[w] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C++ BPR: BPR::Train (src/model/BPR.cpp:85-103) + UpdateBPRPair (src/proNet.cpp:1406-1455): 5 rounds, the first
+// with the caller's negative. 14 words per sample (K = 5); ids row = user, item, j0..j4; one shared table.
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_cpp(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    const Batch b = batch_init<T>(0, 5, wib);
+    WarpState st = a.state[w];
+    const uint64_t stream = a.stream_base + (uint64_t)w;
+    const int dim = a.dim;
+    T* W = a.Wv;
+    for (uint64_t done = 0; done < a.jobs; done += 32) {
+        const int nb = (int)min((uint64_t)32, a.jobs - done);
+        batch_sample<false>(a.g, b, a.seed, stream, st, nb, lane);
+        for (int s = 0; s < nb; ++s) {
+            if (s + kLinePrefetch < nb) prefetch_sample<T>(W, W, b.ids + (s + kLinePrefetch) * b.idw, b.idw, dim, lane);
+            const int* sid = b.ids + s * b.idw;
+            const int v1 = sid[0], v2 = sid[1];
+            if (v2 < 0) continue;
+            const int my = lane < 7 ? sid[lane] : (-1 - lane);
+            const unsigned peers = __match_any_sync(kFull, my);
+            const bool dup = __any_sync(kFull, lane < 7 && __popc(peers) > 1);
+            const T alpha = (T)st.alpha;
+            const T c = alpha * (T)0.0025;
+            const T cv = alpha * (T)0.025;
+            T* pv = W + (size_t)v1 * dim;
+            T* pi = W + (size_t)v2 * dim;
+            if (!dup) {
+                Row<C> v, ri, rj[5], verr;
+                v.load(pv, lane, dim);
+                ri.load(pi, lane, dim);
+#pragma unroll
+                for (int n = 0; n < 5; ++n) rj[n].load(W + (size_t)sid[2 + n] * dim, lane, dim);
+                verr.zero();
+#pragma unroll
+                for (int n = 0; n < 5; ++n) {
+                    Row<C> cvec;
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = ri.x[e] - rj[n].x[e];
+                    const T f = dot(v, cvec);
+                    const T gg = fast_sigmoid<T>(lut, (T)0 - f) * alpha;
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) {
+                        verr.x[e] += gg * cvec.x[e];
+                        const T cerr = gg * v.x[e];
+                        ri.x[e] -= c * ri.x[e];
+                        rj[n].x[e] -= c * rj[n].x[e];
+                        ri.x[e] += cerr;
+                        rj[n].x[e] -= cerr;
+                    }
+                    rj[n].store(W + (size_t)sid[2 + n] * dim, lane, dim);
+                }
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) {
+                    v.x[e] -= cv * v.x[e];
+                    v.x[e] += verr.x[e];
+                }
+                ri.store(pi, lane, dim);
+                v.store(pv, lane, dim);
+            } else {
+                Row<C> verr;
+                verr.zero();
+                for (int n = 0; n < 5; ++n)
+                    ordered_round<C>(pv, pi, W + (size_t)sid[2 + n] * dim, dim, lane, lut, alpha, false, (T)0, verr);
+                for_owned<C>(lane, dim, [&](int e, int idx) {
+                    stv(pv + idx, ldv(pv + idx) - cv * ldv(pv + idx));
+                    stv(pv + idx, ldv(pv + idx) + verr.x[e]);
+                });
+            }
+            st.count++;
+            st.pairs += 5;
+            sched_tick(st, a.sched);
+        }
+    }
+    if (lane == 0) a.state[w] = st;
+}
+
+}  // namespace smore

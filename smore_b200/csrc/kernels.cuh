@@ -258,119 +258,6 @@ __device__ __forceinline__ const T* stage_lut(const T* lut_global, T* lut_shared
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
 // ---------------------------------------------------------------------------------------------------------------
-// LINE: LINE::Train (src/model/LINE.cpp:100-195) / LINE.Train (internal/models/line/line.go:73-150)
-//
-// A sample consumes a FIXED number of stream words (C++: p,idx | p,idx | K x (idx,p) = 4+2K; Go: idx,p | r |
-// K x (idx,p) = 3+2K), so sample s of a worker owns words [s*wps, (s+1)*wps) of its stream. The warp therefore resolves
-// 32 samples at a time, one per lane: the Philox words of the batch are generated cooperatively into shared memory,
-// every lane walks its own source -> target chain and looks up its K negatives (32 dependent chains in flight per warp
-// instead of one), ids are parked in shared memory, and the warp then applies the 32 updates in stream order.
-// (A source is never a sink -- zero out-weight gets alias probability 0 -- so the "skip" branch of line.go:121-124,
-// which would shorten a sample to 2 words, cannot fire; if it ever did the sample is dropped at fixed width.)
-// Shared memory: LUT | per warp: word buffer [32*wps + 8] | ids [32*(K+2)].
-// ---------------------------------------------------------------------------------------------------------------
-__host__ __device__ inline int line_wps(int go, int K) { return (go ? 3 : 4) + 2 * K; }
-__host__ __device__ inline int line_wbuf_words(int go, int K) { return ((32 * line_wps(go, K) + 8 + 3) / 4) * 4; }
-template <typename T>
-inline size_t line_smem_bytes(int go, int K) {
-    return 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(line_wbuf_words(go, K) + 32 * (K + 2)) * 4;
-}
-
-// resident CTAs per SM the register allocator must allow: 3 while a row costs <= 16 B per lane (fp32 dim <= 128)
-template <class C>
-constexpr int line_min_blocks() {
-    return C::EPL * (int)sizeof(typename C::T) <= 16 ? 3 : C::EPL * (int)sizeof(typename C::T) <= 32 ? 2 : 1;
-}
-
-template <class C, bool GO>
-__global__ void __launch_bounds__(kBlockThreads, line_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
-    using T = typename C::T;
-    T* lut_s = reinterpret_cast<T*>(smem_raw);
-    const T* lut = stage_lut<T>(a.lut, lut_s);
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int w = blockIdx.x * kWarpsPerBlock + wib;
-    if (w >= a.n_warps) return;
-    const int K = a.K;
-    const int wps = line_wps(GO, K);
-    const int wcap = line_wbuf_words(GO, K);
-    const int idw = K + 2;
-    uint32_t* wbuf = reinterpret_cast<uint32_t*>(smem_raw + 1008 * sizeof(T)) + (size_t)wib * (wcap + 32 * idw);
-    int* ids = reinterpret_cast<int*>(wbuf + wcap);
-    WarpState st = a.state[w];
-    const GraphDev& g = a.g;
-    const uint64_t stream = a.stream_base + (uint64_t)w;
-    const uint32_t V32 = (uint32_t)g.V;
-    const int nrows = K + 1;
-    for (uint64_t done = 0; done < a.jobs; done += 32) {
-        const int nb = (int)min((uint64_t)32, a.jobs - done);
-        // 1. Philox words of the batch -> shared
-        const uint64_t first_blk = st.pos >> 2;
-        const int nblk = (int)(((st.pos + (uint64_t)(nb * wps) + 3) >> 2) - first_blk);
-        __syncwarp();
-        for (int b = lane; b < nblk; b += 32) {
-            U4 r = philox_block(a.seed, stream, first_blk + (uint64_t)b);
-            *reinterpret_cast<uint4*>(wbuf + 4 * b) = make_uint4(r.x, r.y, r.z, r.w);
-        }
-        __syncwarp();
-        // 2. one sample per lane: negatives (independent lookups) first, then the source -> target chain
-        if (lane < nb) {
-            const uint32_t* wd = wbuf + ((uint32_t)st.pos & 3u) + lane * wps;
-            int* my_ids = ids + lane * idw;
-            const int noff = GO ? 3 : 4;
-            for (int n0 = 0; n0 < K; n0 += 8) {
-                uint32_t idx[8];
-                uint2 e[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (n0 + j < K) {
-                        idx[j] = index_draw(wd[noff + 2 * (n0 + j)], V32);
-                        e[j] = __ldg(g.negative_at + idx[j]);
-                    }
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (n0 + j < K) my_ids[2 + n0 + j] = (int)(wd[noff + 2 * (n0 + j) + 1] < e[j].x ? idx[j] : e[j].y);
-            }
-            const int v1 = (int)source_sample(g, wd[0], wd[1]);
-            int u;
-            const int v2 = (int)target_sample(g, v1, wd[2], GO ? 0u : wd[3], u);
-            my_ids[0] = v1;
-            my_ids[1] = v2;
-        }
-        st.pos += (uint64_t)(nb * wps);
-        __syncwarp();
-        // 3. the updates, in stream order; rows of the sample kLinePrefetch ahead are pulled into L2 meanwhile
-        const int lines_per_row = (a.dim * (int)sizeof(T) + 127) >> 7;
-        const int pf_total = idw * lines_per_row;
-        for (int s = 0; s < nb; ++s) {
-            if (s + kLinePrefetch < nb) {
-                const int* pid = ids + (s + kLinePrefetch) * idw;
-                for (int t = lane; t < pf_total; t += 32) {
-                    const int r = t / lines_per_row, ln = t - r * lines_per_row;
-                    const int id = pid[r];
-                    if (id >= 0) {
-                        const char* p = reinterpret_cast<const char*>((r == 0 ? a.Wv : a.Wc) + (size_t)id * a.dim) + (ln << 7);
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                    }
-                }
-            }
-            const int* sid = ids + s * idw;
-            const int v1 = sid[0];
-            const int v2 = sid[1];
-            const int my = lane < nrows ? sid[1 + lane] : (-1 - lane);
-            if (v2 < 0) continue;
-            const T alpha = (T)st.alpha;
-            if (!GO) update_pair_cpp<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, lut, v1, my, nrows, alpha, lane);
-            else update_pair_go<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, a.order == 1, lut, v1, my, nrows, alpha, lane);
-            st.count++;
-            st.pairs++;
-            sched_tick(st, a.sched);
-        }
-    }
-    if (lane == 0) a.state[w] = st;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // On-device walks: RandomWalk (src/proNet.cpp:704-724 / pronet.go:292-307). Lane 0 walks; ids go to shared memory.
 // Returns the walk length (warp-uniform).
 // ---------------------------------------------------------------------------------------------------------------

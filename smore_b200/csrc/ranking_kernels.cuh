@@ -48,101 +48,6 @@ __device__ __forceinline__ int64_t reject_sample(DrawRing& ring, int lane, uint3
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Go BPR: BPR.Train (internal/models/bpr/bpr.go:84-131) + UpdateBPRPair (pkg/pronet/optimizer.go:87-117).
-// Words per sample: source (idx, p), target (1), negative (idx, p).
-// ---------------------------------------------------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(kBlockThreads) k_bpr_go(TrainArgs<typename C::T> a) {
-    using T = typename C::T;
-    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
-    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
-    const T* lut = stage_lut<T>(a.lut, lut_s);
-    int lane = threadIdx.x & 31;
-    int wib = threadIdx.x >> 5;
-    int w = blockIdx.x * kWarpsPerBlock + wib;
-    if (w >= a.n_warps) return;
-    WarpState st = a.state[w];
-    DrawRing ring;
-    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
-    const GraphDev& g = a.g;
-    const int dim = a.dim;
-    for (uint64_t it = 0; it < a.jobs; ++it) {
-        ring.ensure();
-        int64_t neg = -1, user = -1, pos = -1;
-        int used = 0;
-        if (lane == 1) neg = (int64_t)negative_sample(g, ring.peek(3), ring.peek(4));
-        if (lane == 0) {
-            user = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
-            int u;
-            pos = target_sample(g, user, ring.peek(2), 0u, u);
-            used = 2 + u;
-        }
-        user = __shfl_sync(kFull, user, 0);
-        pos = __shfl_sync(kFull, pos, 0);
-        neg = __shfl_sync(kFull, neg, 1);
-        used = __shfl_sync(kFull, used, 0);
-        if (pos < 0) {
-            ring.advance((uint32_t)used);
-            continue;
-        }
-        ring.advance(5u);
-        const T alpha = (T)st.alpha;
-        const T la = a.lambda * alpha;  // lambda*alpha*w evaluates left to right
-        T* pv = a.Wv + user * dim;
-        T* pp = a.Wc + pos * dim;
-        T* pn = a.Wc + neg * dim;
-        const bool same = pos == neg;
-        const bool valias = a.same_table && (user == pos || user == neg);
-        if (!valias) {
-            Row<C> v, p, n;
-            v.load(pv, lane, dim);
-            p.load(pp, lane, dim);
-            n.load(pn, lane, dim);
-            T ps = dot_partial(v, p), ns = dot_partial(v, n);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                ps += __shfl_xor_sync(kFull, ps, o);
-                ns += __shfl_xor_sync(kFull, ns, o);
-            }
-            const T gc = alpha * fast_sigmoid<T>(lut, ns - ps);
-#pragma unroll
-            for (int e = 0; e < C::EPL; ++e) {
-                T vg = gc * (p.x[e] - n.x[e]);
-                T pg = gc * v.x[e];
-                T ng = -gc * v.x[e];
-                v.x[e] += vg - la * v.x[e];
-                p.x[e] += pg - la * p.x[e];
-                T ncur = same ? p.x[e] : n.x[e];  // pos == neg: the second write lands on the already-updated row
-                n.x[e] = ncur + (ng - la * ncur);
-            }
-            v.store(pv, lane, dim);
-            if (!same) p.store(pp, lane, dim);
-            n.store(pn, lane, dim);
-        } else {
-            // single shared table with the user row coinciding with an item row: replay through memory
-            Row<C> v, p, n;
-            v.load(pv, lane, dim);
-            p.load(pp, lane, dim);
-            n.load(pn, lane, dim);
-            const T gc = alpha * fast_sigmoid<T>(lut, dot(v, n) - dot(v, p));
-            for_owned<C>(lane, dim, [&](int, int idx) {
-                T vg = gc * (ldv(pp + idx) - ldv(pn + idx));
-                T pg = gc * ldv(pv + idx);
-                T ng = -gc * ldv(pv + idx);
-                stv(pv + idx, ldv(pv + idx) + (vg - la * ldv(pv + idx)));
-                stv(pp + idx, ldv(pp + idx) + (pg - la * ldv(pp + idx)));
-                stv(pn + idx, ldv(pn + idx) + (ng - la * ldv(pn + idx)));
-            });
-        }
-        st.count++;
-        st.pairs++;
-        sched_tick(st, a.sched);
-    }
-    st.pos = ring.pos;
-    if (lane == 0) a.state[w] = st;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // One BPR-style round shared by the C++ ranking updates, ORDERED flavour (rows re-read from memory, per-element
 // writes in the reference's order: src/proNet.cpp:1426-1440 / :1485-1504 / :1371-1391).
 // Returns false if the round was margin-gated away. verr accumulates in registers (it is a local vector in the
@@ -172,107 +77,6 @@ __device__ __forceinline__ bool ordered_round(typename C::T* pv, typename C::T* 
         stv(pj + idx, ldv(pj + idx) - cerr);
     });
     return true;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// C++ BPR: BPR::Train (src/model/BPR.cpp:85-103) + UpdateBPRPair (src/proNet.cpp:1406-1455): 5 rounds, the first
-// with the caller's negative. 14 words per sample: source (p, idx), target (p, idx), 5 x negative (idx, p).
-// ---------------------------------------------------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(kBlockThreads) k_bpr_cpp(TrainArgs<typename C::T> a) {
-    using T = typename C::T;
-    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
-    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
-    const T* lut = stage_lut<T>(a.lut, lut_s);
-    int lane = threadIdx.x & 31;
-    int wib = threadIdx.x >> 5;
-    int w = blockIdx.x * kWarpsPerBlock + wib;
-    if (w >= a.n_warps) return;
-    WarpState st = a.state[w];
-    DrawRing ring;
-    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
-    const GraphDev& g = a.g;
-    const int dim = a.dim;
-    T* W = a.Wv;
-    for (uint64_t it = 0; it < a.jobs; ++it) {
-        ring.ensure();
-        // lanes 2..6 hold the 5 negatives, lane 0 the user, lane 1 the positive item
-        int64_t my = -1 - lane;
-        if (lane >= 2 && lane < 7) my = (int64_t)negative_sample(g, ring.peek(4u + 2u * (uint32_t)(lane - 2)), ring.peek(5u + 2u * (uint32_t)(lane - 2)));
-        int64_t v1 = -1, v2 = -1;
-        if (lane == 0) {
-            v1 = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
-            int u;
-            v2 = target_sample(g, v1, ring.peek(2), ring.peek(3), u);
-        }
-        v1 = __shfl_sync(kFull, v1, 0);
-        v2 = __shfl_sync(kFull, v2, 0);
-        ring.advance(14u);
-        if (v2 < 0) continue;  // never drawn by the reference (sources have out-degree > 0)
-        if (lane == 0) my = v1;
-        if (lane == 1) my = v2;
-        const T alpha = (T)st.alpha;
-        const T c = alpha * (T)0.0025;
-        unsigned peers = __match_any_sync(kFull, my);
-        bool dup = __any_sync(kFull, lane < 7 && __popc(peers) > 1);
-        T* pv = W + v1 * dim;
-        T* pi = W + v2 * dim;
-        if (!dup) {
-            Row<C> v, ri, rj[5], verr;
-            int64_t jid[5];
-            v.load(pv, lane, dim);
-            ri.load(pi, lane, dim);
-#pragma unroll
-            for (int n = 0; n < 5; ++n) {
-                jid[n] = __shfl_sync(kFull, my, 2 + n);
-                rj[n].load(W + jid[n] * dim, lane, dim);
-            }
-            verr.zero();
-#pragma unroll
-            for (int n = 0; n < 5; ++n) {
-                Row<C> cvec;
-#pragma unroll
-                for (int e = 0; e < C::EPL; ++e) cvec.x[e] = ri.x[e] - rj[n].x[e];
-                const T f = dot(v, cvec);
-                const T gg = fast_sigmoid<T>(lut, (T)0 - f) * alpha;
-#pragma unroll
-                for (int e = 0; e < C::EPL; ++e) {
-                    verr.x[e] += gg * cvec.x[e];
-                    const T cerr = gg * v.x[e];
-                    ri.x[e] -= c * ri.x[e];
-                    rj[n].x[e] -= c * rj[n].x[e];
-                    ri.x[e] += cerr;
-                    rj[n].x[e] -= cerr;
-                }
-                rj[n].store(W + jid[n] * dim, lane, dim);
-            }
-            const T cv = alpha * (T)0.025;
-#pragma unroll
-            for (int e = 0; e < C::EPL; ++e) {
-                v.x[e] -= cv * v.x[e];
-                v.x[e] += verr.x[e];
-            }
-            ri.store(pi, lane, dim);
-            v.store(pv, lane, dim);
-        } else {
-            Row<C> verr;
-            verr.zero();
-            for (int n = 0; n < 5; ++n) {
-                int64_t j = __shfl_sync(kFull, my, 2 + n);
-                ordered_round<C>(pv, pi, W + j * dim, dim, lane, lut, alpha, false, (T)0, verr);
-            }
-            const T cv = alpha * (T)0.025;
-            for_owned<C>(lane, dim, [&](int e, int idx) {
-                stv(pv + idx, ldv(pv + idx) - cv * ldv(pv + idx));
-                stv(pv + idx, ldv(pv + idx) + verr.x[e]);
-            });
-        }
-        st.count++;
-        st.pairs += 5;
-        sched_tick(st, a.sched);
-    }
-    st.pos = ring.pos;
-    if (lane == 0) a.state[w] = st;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

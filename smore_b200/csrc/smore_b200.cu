@@ -14,8 +14,7 @@
 #include <vector>
 
 #include "host_graph.h"
-#include "kernels.cuh"
-#include "ranking_kernels.cuh"
+#include "batch_kernels.cuh"
 
 using namespace smore;
 
@@ -354,7 +353,7 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
         using C = decltype(cfg);
         const bool cpp = p->semantics == SMORE_SEM_CPP;
         void (*kern)(TrainArgs<T>) = cpp ? k_line<C, false> : k_line<C, true>;
-        const size_t smem = line_smem_bytes<T>(cpp ? 0 : 1, p->negative_samples);
+        const size_t smem = batch_smem_bytes<T>(cpp ? 0 : 1, p->negative_samples);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
@@ -443,7 +442,7 @@ int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind) {
         using C = decltype(cfg);
         const bool cpp = p->semantics == SMORE_SEM_CPP;
         void (*kern)(TrainArgs<T>) = kind == RANK_WARP ? k_warp<C> : kind == RANK_HOPREC ? k_hoprec<C> : cpp ? k_bpr_cpp<C> : k_bpr_go<C>;
-        const size_t smem = smem_line<T>();
+        const size_t smem = kind != RANK_BPR ? smem_line<T>() : cpp ? batch_smem_bytes<T>(0, 5) : batch_smem_bytes<T>(1, 1);
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
         else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;

@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""Per-model throughput of the hot path on one B200 (diagnostic companion of bench.py; same timing rules).
+
+Prints one JSON line per model: updates/s (pair updates for the skip-gram models, samples for the ranking models),
+algorithmic GB/s (SURVEY.md §8d byte model) and the fraction of the measured HBM peak.
+Graph sizes are the BASELINE.json configs scaled by --scale (configs[3] is always scaled: 500M interactions do not
+fit the host-side numpy generator's time budget).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from smore_b200 import capi, synth  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def run(name, model, fn, p, bytes_per_unit, unit_key, steps, warmup):
+    for i in range(warmup):
+        p.stream_base = i * (1 << 20)
+        fn(p)
+    ms, units, tries = 0.0, 0, 0.0
+    for i in range(steps):
+        p.stream_base = (warmup + i) * (1 << 20)
+        st = fn(p)
+        ms += st["kernel_ms"]
+        units += st[unit_key]
+        tries = st["mean_tries"]
+    b = bytes_per_unit(tries) if callable(bytes_per_unit) else bytes_per_unit
+    gbs = units * b / (ms * 1e-3) / 1e9
+    print(json.dumps({"model": name, "units_per_s": units / (ms * 1e-3), "unit": unit_key, "ms_per_step": ms / steps,
+                      "algorithmic_bytes_per_unit": b, "algorithmic_GBps": gbs, "frac_of_measured_hbm": gbs / peak(),
+                      "mean_tries": tries}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    only = set(a.only.split(",")) if a.only else None
+
+    def want(n):
+        return only is None or n in only
+
+    base = capi.default_params()
+    base.mode, base.seed = capi.MODE_HOGWILD, 1
+
+    # ---- configs[0]: BPR dim 64, 10k users x 10k items, 1M edges (and the same graph at dim 128) ----
+    if want("bpr_go") or want("bpr_cpp"):
+        src, dst, w = synth.bipartite_edges(10_000, 10_000, 1_000_000, 7)
+        off, col, ww, _ = synth.csr_from_edges(src, dst, w, False)
+        for dim in (64, 128):
+            if want("bpr_go"):
+                g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_GO, n_lines=len(src))
+                m = capi.Model(g, dim, 2, capi.F32)
+                m.init(0, True, 1), m.init(1, True, 2)
+                p = capi.default_params()
+                p.semantics, p.mode, p.seed, p.total, p.lambda_ = capi.SEM_GO, capi.MODE_HOGWILD, 1, 1 << 25, 0.001
+                run(f"bpr_go_d{dim}_c1", m, m.train_bpr, p, 6 * dim * 4 + 40, "samples", a.steps, a.warmup)
+            if want("bpr_cpp"):
+                g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP, negative_method=capi.NEG_NO_DEGREES)
+                m = capi.Model(g, dim, 1, capi.F32)
+                m.init(0, True, 1)
+                p = capi.default_params()
+                p.semantics, p.mode, p.seed, p.total = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 1 << 24
+                run(f"bpr_cpp_d{dim}_c1", m, m.train_bpr, p, 14 * dim * 4 + 60, "samples", a.steps, a.warmup)
+
+    # ---- a large bipartite graph (configs[3] scaled): BPR at dim 128 out of L2, WARP, HOP-Rec ----
+    if want("bpr_go_big") or want("warp") or want("hoprec") or want("bpr_cpp_big"):
+        nu, ni, ne = int(1_000_000 * a.scale), int(200_000 * a.scale), int(20_000_000 * a.scale)
+        t0 = time.time()
+        src, dst, w = synth.bipartite_edges(nu, ni, ne, 9)
+        dim = 128
+        if want("bpr_go_big"):
+            off, col, ww, _ = synth.csr_from_edges(src, dst, w, False)
+            g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_GO, n_lines=len(src))
+            m = capi.Model(g, dim, 2, capi.F32)
+            m.init(0, True, 1), m.init(1, True, 2)
+            p = capi.default_params()
+            p.semantics, p.mode, p.seed, p.total, p.lambda_ = capi.SEM_GO, capi.MODE_HOGWILD, 1, 1 << 25, 0.001
+            run(f"bpr_go_d{dim}_big", m, m.train_bpr, p, 6 * dim * 4 + 40, "samples", a.steps, a.warmup)
+            del m, g
+        if want("bpr_cpp_big") or want("warp"):
+            off, col, ww, _ = synth.csr_from_edges(src, dst, w, False)
+            g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP, negative_method=capi.NEG_NO_DEGREES)
+            if want("bpr_cpp_big"):
+                m = capi.Model(g, dim, 1, capi.F32)
+                m.init(0, True, 1)
+                p = capi.default_params()
+                p.semantics, p.mode, p.seed, p.total = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 1 << 24
+                run(f"bpr_cpp_d{dim}_big", m, m.train_bpr, p, 14 * dim * 4 + 60, "samples", a.steps, a.warmup)
+            if want("warp"):
+                m = capi.Model(g, dim, 1, capi.F32)
+                m.init(0, True, 1)
+                p = capi.default_params()
+                p.semantics, p.mode, p.seed, p.total = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 1 << 24
+                # (2 + tries) rows read, 3 written when violated; early in training every sample violates
+                run(f"warp_d{dim}_big", m, m.train_warp, p, lambda tr: (2 + tr) * dim * 4 + 3 * dim * 4 + 40, "samples",
+                    a.steps, a.warmup)
+            del m, g
+        if want("hoprec"):
+            off, col, ww, labels = synth.csr_from_edges(src, dst, w, True)
+            g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP, negative_method=capi.NEG_NO_DEGREES)
+            g.set_field((labels >= nu).astype(np.int32))
+            m = capi.Model(g, dim, 1, capi.F32)
+            m.init(0, True, 1)
+            p = capi.default_params()
+            p.semantics, p.mode, p.seed, p.total, p.walk_steps = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 1 << 22, 5
+            # per hop: user + item + 5 negatives read, up to all 7 written: counted per FBPR round-group ("pair_updates"/5)
+            run(f"hoprec_d{dim}_big", m, m.train_hoprec, p, 5 * 14 * dim * 4, "samples", a.steps, a.warmup)
+
+    # ---- configs[2]: DeepWalk dim 128, walk_steps 40, window 5 (V scaled; one epoch slice per step) ----
+    if want("deepwalk") or want("walklets"):
+        nv = int(1_000_000 * a.scale)
+        src, dst, w = synth.power_law_edges(nv, 5 * nv, 11)
+        off, col, ww, _ = synth.csr_from_edges(src, dst, w, True)
+        g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP)
+        dim = 128
+        for nm in ("deepwalk", "walklets"):
+            if not want(nm):
+                continue
+            m = capi.Model(g, dim, 2, capi.F32)
+            m.init(0, True, 1), m.init(1, True, 2)
+            p = capi.default_params()
+            p.semantics, p.mode, p.seed = capi.SEM_CPP, capi.MODE_HOGWILD, 1
+            p.walk_times, p.walk_steps, p.window_min, p.window_max, p.max_walks = 1, 40, (2 if nm == "walklets" else 1), 5, 200_000
+            run(f"{nm}_d{dim}", m, m.train_deepwalk if nm == "deepwalk" else m.train_walklets, p, 2 * 7 * dim * 4 + 76,
+                "pair_updates", a.steps, a.warmup)
+
+
+if __name__ == "__main__":
+    main()
