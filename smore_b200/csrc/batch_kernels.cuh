@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go
             const int user = sid[0], pos = sid[1], neg = sid[2];
             if (pos < 0) continue;
             const T alpha = (T)st.alpha;
-            const T la = a.lambda * alpha;  // lambda*alpha*w evaluates left to right
+            using A = Ar<T>;
+            const T la = A::mul(a.lambda, alpha);  // lambda*alpha*w evaluates left to right
             T* pv = a.Wv + (size_t)user * dim;
             T* pp = a.Wc + (size_t)pos * dim;
             T* pn = a.Wc + (size_t)neg * dim;
@@ -181,23 +182,20 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go
             v.load(pv, lane, dim);
             p.load(pp, lane, dim);
             n.load(pn, lane, dim);
-            T ps = dot_partial(v, p), ns = dot_partial(v, n);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                ps += __shfl_xor_sync(kFull, ps, o);
-                ns += __shfl_xor_sync(kFull, ns, o);
-            }
-            const T gc = alpha * fast_sigmoid<T>(lut, ns - ps);
+            Row<C> pn2[2] = {p, n};
+            T sc[2];
+            dots<C, 2>(v, pn2, 2, sc);  // posScore, negScore (optimizer.go:95-100)
+            const T gc = A::mul(alpha, fast_sigmoid<T>(lut, A::sub(sc[1], sc[0])));
             if (!valias) {
 #pragma unroll
                 for (int e = 0; e < C::EPL; ++e) {
-                    const T vg = gc * (p.x[e] - n.x[e]);
-                    const T pg = gc * v.x[e];
-                    const T ng = -gc * v.x[e];
-                    v.x[e] += vg - la * v.x[e];
-                    p.x[e] += pg - la * p.x[e];
+                    const T vg = A::mul(gc, A::sub(p.x[e], n.x[e]));
+                    const T pg = A::mul(gc, v.x[e]);
+                    const T ng = A::mul(-gc, v.x[e]);
+                    v.x[e] = A::add(v.x[e], A::msub(vg, la, v.x[e]));  // w += grad - (lambda*alpha)*w
+                    p.x[e] = A::add(p.x[e], A::msub(pg, la, p.x[e]));
                     const T ncur = same ? p.x[e] : n.x[e];  // pos == neg: the second write lands on the updated row
-                    n.x[e] = ncur + (ng - la * ncur);
+                    n.x[e] = A::add(ncur, A::msub(ng, la, ncur));
                 }
                 v.store(pv, lane, dim);
                 if (!same) p.store(pp, lane, dim);
@@ -205,12 +203,12 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go
             } else {
                 // one shared table and the user row coincides with an item row: replay through memory
                 for_owned<C>(lane, dim, [&](int, int idx) {
-                    const T vg = gc * (ldv(pp + idx) - ldv(pn + idx));
-                    const T pg = gc * ldv(pv + idx);
-                    const T ng = -gc * ldv(pv + idx);
-                    stv(pv + idx, ldv(pv + idx) + (vg - la * ldv(pv + idx)));
-                    stv(pp + idx, ldv(pp + idx) + (pg - la * ldv(pp + idx)));
-                    stv(pn + idx, ldv(pn + idx) + (ng - la * ldv(pn + idx)));
+                    const T vg = A::mul(gc, A::sub(ldv(pp + idx), ldv(pn + idx)));
+                    const T pg = A::mul(gc, ldv(pv + idx));
+                    const T ng = A::mul(-gc, ldv(pv + idx));
+                    stv(pv + idx, A::add(ldv(pv + idx), A::msub(vg, la, ldv(pv + idx))));
+                    stv(pp + idx, A::add(ldv(pp + idx), A::msub(pg, la, ldv(pp + idx))));
+                    stv(pn + idx, A::add(ldv(pn + idx), A::msub(ng, la, ldv(pn + idx))));
                 });
             }
             st.count++;
@@ -249,9 +247,10 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_cp
             const int my = lane < 7 ? sid[lane] : (-1 - lane);
             const unsigned peers = __match_any_sync(kFull, my);
             const bool dup = __any_sync(kFull, lane < 7 && __popc(peers) > 1);
+            using A = Ar<T>;
             const T alpha = (T)st.alpha;
-            const T c = alpha * (T)0.0025;
-            const T cv = alpha * (T)0.025;
+            const T c = A::mul(alpha, (T)0.0025);  // alpha*0.0025*w evaluates left to right
+            const T cv = A::mul(alpha, (T)0.025);
             T* pv = W + (size_t)v1 * dim;
             T* pi = W + (size_t)v2 * dim;
             if (!dup) {
@@ -265,24 +264,24 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_cp
                 for (int n = 0; n < 5; ++n) {
                     Row<C> cvec;
 #pragma unroll
-                    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = ri.x[e] - rj[n].x[e];
+                    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = A::sub(ri.x[e], rj[n].x[e]);
                     const T f = dot(v, cvec);
-                    const T gg = fast_sigmoid<T>(lut, (T)0 - f) * alpha;
+                    const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f)), alpha);
 #pragma unroll
                     for (int e = 0; e < C::EPL; ++e) {
-                        verr.x[e] += gg * cvec.x[e];
-                        const T cerr = gg * v.x[e];
-                        ri.x[e] -= c * ri.x[e];
-                        rj[n].x[e] -= c * rj[n].x[e];
-                        ri.x[e] += cerr;
-                        rj[n].x[e] -= cerr;
+                        verr.x[e] = A::madd(verr.x[e], gg, cvec.x[e]);
+                        const T cerr = A::mul(gg, v.x[e]);
+                        ri.x[e] = A::msub(ri.x[e], c, ri.x[e]);
+                        rj[n].x[e] = A::msub(rj[n].x[e], c, rj[n].x[e]);
+                        ri.x[e] = A::add(ri.x[e], cerr);
+                        rj[n].x[e] = A::sub(rj[n].x[e], cerr);
                     }
                     rj[n].store(W + (size_t)sid[2 + n] * dim, lane, dim);
                 }
 #pragma unroll
                 for (int e = 0; e < C::EPL; ++e) {
-                    v.x[e] -= cv * v.x[e];
-                    v.x[e] += verr.x[e];
+                    v.x[e] = A::msub(v.x[e], cv, v.x[e]);
+                    v.x[e] = A::add(v.x[e], verr.x[e]);
                 }
                 ri.store(pi, lane, dim);
                 v.store(pv, lane, dim);
@@ -292,8 +291,8 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_cp
                 for (int n = 0; n < 5; ++n)
                     ordered_round<C>(pv, pi, W + (size_t)sid[2 + n] * dim, dim, lane, lut, alpha, false, (T)0, verr);
                 for_owned<C>(lane, dim, [&](int e, int idx) {
-                    stv(pv + idx, ldv(pv + idx) - cv * ldv(pv + idx));
-                    stv(pv + idx, ldv(pv + idx) + verr.x[e]);
+                    stv(pv + idx, A::msub(ldv(pv + idx), cv, ldv(pv + idx)));
+                    stv(pv + idx, A::add(ldv(pv + idx), verr.x[e]));
                 });
             }
             st.count++;

@@ -225,6 +225,35 @@ struct Row {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Arithmetic policy.
+//   float  : throughput path. Products may contract into FMAs, dot products are lane-partial sums + xor butterfly.
+//   double : PARITY path. Every operation is the reference's operation: separately rounded multiply and add (the
+//            reference is built for baseline x86-64, which has no FMA) and dot products summed in index order
+//            d = 0..D-1 (src/proNet.cpp:1317-1318), so the deterministic fp64 mode reproduces the compiled reference
+//            bit for bit. It is slower (a serial chain of D additions per dot) and is not what bench.py measures.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Ar;
+template <>
+struct Ar<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float div(float a, float b) { return a / b; }
+    static __device__ __forceinline__ float madd(float c, float a, float b) { return c + a * b; }  // c + a*b
+    static __device__ __forceinline__ float msub(float c, float a, float b) { return c - a * b; }  // c - a*b
+};
+template <>
+struct Ar<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double madd(double c, double a, double b) { return __dadd_rn(c, __dmul_rn(a, b)); }
+    static __device__ __forceinline__ double msub(double c, double a, double b) { return __dsub_rn(c, __dmul_rn(a, b)); }
+};
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
@@ -232,17 +261,54 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
-template <class C>
-__device__ __forceinline__ typename C::T dot_partial(const Row<C>& a, const Row<C>& b) {
-    typename C::T s = 0;
+// N dot products v . c[r] at once (r < n valid rows; the others return 0). Result is warp-uniform.
+template <class C, int N>
+__device__ __forceinline__ void dots(const Row<C>& v, const Row<C>* c, int n, typename C::T* f) {
+    using T = typename C::T;
+    if constexpr (sizeof(T) == 4) {
 #pragma unroll
-    for (int e = 0; e < C::EPL; ++e) s += a.x[e] * b.x[e];
-    return s;
+        for (int r = 0; r < N; ++r) {
+            T s = 0;
+            if (r < n) {
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) s += v.x[e] * c[r].x[e];
+            }
+            f[r] = s;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int r = 0; r < N; ++r) f[r] += __shfl_xor_sync(kFull, f[r], o);
+        }
+    } else {
+        // index order: chunk, lane, slot (element = (chunk*32 + lane)*VEC + slot); every lane replays the same chain
+        T prod[N][C::EPL];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            f[r] = 0;
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) prod[r][e] = r < n ? Ar<T>::mul(v.x[e], c[r].x[e]) : (T)0;
+        }
+#pragma unroll
+        for (int ch = 0; ch < C::NCH; ++ch) {
+            for (int l = 0; l < 32; ++l) {
+#pragma unroll
+                for (int j = 0; j < C::VEC; ++j) {
+#pragma unroll
+                    for (int r = 0; r < N; ++r) {
+                        if (r < n) f[r] = Ar<T>::add(f[r], __shfl_sync(kFull, prod[r][ch * C::VEC + j], l));
+                    }
+                }
+            }
+        }
+    }
 }
 
 template <class C>
 __device__ __forceinline__ typename C::T dot(const Row<C>& a, const Row<C>& b) {
-    return warp_sum(dot_partial(a, b));
+    typename C::T f[1];
+    dots<C, 1>(a, &b, 1, f);
+    return f[0];
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -54,6 +54,7 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
                                                 const typename C::T* lut, int v1, int my_id, int nrows,
                                                 typename C::T alpha, int lane) {
     using T = typename C::T;
+    using A = Ar<T>;
     bool active = lane < nrows;
     unsigned peers = __match_any_sync(kFull, active ? my_id : (-1 - lane));
     bool dup = __any_sync(kFull, (active && __popc(peers) > 1) || (active && same_table && my_id == v1));
@@ -71,29 +72,23 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
                 if (base + r < nrows) c[r].load(Wc + (size_t)ids[r] * dim, lane, dim);
             }
             T f[kCtxChunk];
-#pragma unroll
-            for (int r = 0; r < kCtxChunk; ++r) f[r] = (base + r < nrows) ? dot_partial(v, c[r]) : (T)0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int r = 0; r < kCtxChunk; ++r) f[r] += __shfl_xor_sync(kFull, f[r], o);
-            }
+            dots<C, kCtxChunk>(v, c, nrows - base, f);
 #pragma unroll
             for (int r = 0; r < kCtxChunk; ++r) {
                 if (base + r < nrows) {
                     T label = (base + r == 0) ? (T)1 : (T)0;
-                    T g = (label - fast_sigmoid<T>(lut, f[r])) * alpha;
+                    T g = A::mul(A::sub(label, fast_sigmoid<T>(lut, f[r])), alpha);  // (label - f) * alpha
 #pragma unroll
                     for (int e = 0; e < C::EPL; ++e) {
-                        back.x[e] += g * c[r].x[e];
-                        c[r].x[e] += g * v.x[e];
+                        back.x[e] = A::madd(back.x[e], g, c[r].x[e]);  // loss_vertex += g * w_context
+                        c[r].x[e] = A::madd(c[r].x[e], g, v.x[e]);     // w_context   += g * w_vertex (in place)
                     }
                     c[r].store(Wc + (size_t)ids[r] * dim, lane, dim);
                 }
             }
         }
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) v.x[e] += back.x[e];
+        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
         v.store(pv, lane, dim);
     } else {
         Row<C> back;
@@ -106,18 +101,18 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
             c.load(pc, lane, dim);
             T f = dot(v, c);
             T label = (r == 0) ? (T)1 : (T)0;
-            T g = (label - fast_sigmoid<T>(lut, f)) * alpha;
+            T g = A::mul(A::sub(label, fast_sigmoid<T>(lut, f)), alpha);
 #pragma unroll
             for (int e = 0; e < C::EPL; ++e) {
-                back.x[e] += g * c.x[e];
-                c.x[e] += g * v.x[e];
+                back.x[e] = A::madd(back.x[e], g, c.x[e]);
+                c.x[e] = A::madd(c.x[e], g, v.x[e]);
             }
             c.store(pc, lane, dim);
         }
         Row<C> v;
         v.load(pv, lane, dim);
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) v.x[e] += back.x[e];
+        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
         v.store(pv, lane, dim);
     }
 }
@@ -132,6 +127,7 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
                                                bool skip_source, const typename C::T* lut, int v1, int my_id,
                                                int nrows, typename C::T alpha, int lane) {
     using T = typename C::T;
+    using A = Ar<T>;
     int ctx = __shfl_sync(kFull, my_id, 0);
     bool active = lane < nrows;
     bool skipped = active && lane > 0 && (my_id == ctx || (skip_source && my_id == v1));
@@ -146,11 +142,11 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
         v.load(pv, lane, dim);
         pos.load(pp, lane, dim);
         {
-            T g = alpha * ((T)1 - fast_sigmoid<T>(lut, dot(v, pos)));
+            T g = A::mul(alpha, A::sub((T)1, fast_sigmoid<T>(lut, dot(v, pos))));  // alpha * (label - pred)
 #pragma unroll
             for (int e = 0; e < C::EPL; ++e) {
-                vgrad.x[e] = g * pos.x[e];
-                cgrad.x[e] = g * v.x[e];
+                vgrad.x[e] = A::mul(g, pos.x[e]);
+                cgrad.x[e] = A::mul(g, v.x[e]);
             }
         }
         for (int base = 1; base < nrows; base += kCtxChunk) {
@@ -162,23 +158,18 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
                 ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
                 ok[r] = (base + r < nrows) && !((skipmask >> ((base + r) & 31)) & 1u);
                 if (ok[r]) c[r].load(Wc + (size_t)ids[r] * dim, lane, dim);
+                else c[r].zero();
             }
             T f[kCtxChunk];
-#pragma unroll
-            for (int r = 0; r < kCtxChunk; ++r) f[r] = ok[r] ? dot_partial(v, c[r]) : (T)0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int r = 0; r < kCtxChunk; ++r) f[r] += __shfl_xor_sync(kFull, f[r], o);
-            }
+            dots<C, kCtxChunk>(v, c, nrows - base, f);
 #pragma unroll
             for (int r = 0; r < kCtxChunk; ++r) {
                 if (ok[r]) {
-                    T g = alpha * ((T)0 - fast_sigmoid<T>(lut, f[r]));
+                    T g = A::mul(alpha, A::sub((T)0, fast_sigmoid<T>(lut, f[r])));
 #pragma unroll
                     for (int e = 0; e < C::EPL; ++e) {
-                        vgrad.x[e] += g * c[r].x[e];
-                        c[r].x[e] += g * v.x[e];
+                        vgrad.x[e] = A::madd(vgrad.x[e], g, c[r].x[e]);
+                        c[r].x[e] = A::add(c[r].x[e], A::mul(g, v.x[e]));  // wContext[neg] += negGrad
                     }
                     c[r].store(Wc + (size_t)ids[r] * dim, lane, dim);
                 }
@@ -186,8 +177,8 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
         }
 #pragma unroll
         for (int e = 0; e < C::EPL; ++e) {
-            v.x[e] += vgrad.x[e];
-            pos.x[e] += cgrad.x[e];
+            v.x[e] = A::add(v.x[e], vgrad.x[e]);
+            pos.x[e] = A::add(pos.x[e], cgrad.x[e]);
         }
         v.store(pv, lane, dim);
         pos.store(pp, lane, dim);
@@ -197,11 +188,11 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
             Row<C> v, pos;
             v.load(pv, lane, dim);
             pos.load(pp, lane, dim);
-            T g = alpha * ((T)1 - fast_sigmoid<T>(lut, dot(v, pos)));
+            T g = A::mul(alpha, A::sub((T)1, fast_sigmoid<T>(lut, dot(v, pos))));
 #pragma unroll
             for (int e = 0; e < C::EPL; ++e) {
-                vgrad.x[e] = g * pos.x[e];
-                cgrad.x[e] = g * v.x[e];
+                vgrad.x[e] = A::mul(g, pos.x[e]);
+                cgrad.x[e] = A::mul(g, v.x[e]);
             }
         }
         for (int r = 1; r < nrows; ++r) {
@@ -211,11 +202,11 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
             Row<C> v, c;
             v.load(pv, lane, dim);
             c.load(pc, lane, dim);
-            T g = alpha * ((T)0 - fast_sigmoid<T>(lut, dot(v, c)));
+            T g = A::mul(alpha, A::sub((T)0, fast_sigmoid<T>(lut, dot(v, c))));
 #pragma unroll
             for (int e = 0; e < C::EPL; ++e) {
-                vgrad.x[e] += g * c.x[e];
-                c.x[e] += g * v.x[e];
+                vgrad.x[e] = A::madd(vgrad.x[e], g, c.x[e]);
+                c.x[e] = A::add(c.x[e], A::mul(g, v.x[e]));
             }
             c.store(pc, lane, dim);
         }
@@ -224,12 +215,12 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
         Row<C> v;
         v.load(pv, lane, dim);
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) v.x[e] += vgrad.x[e];
+        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], vgrad.x[e]);
         v.store(pv, lane, dim);
         Row<C> pos;
         pos.load(pp, lane, dim);
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) pos.x[e] += cgrad.x[e];
+        for (int e = 0; e < C::EPL; ++e) pos.x[e] = A::add(pos.x[e], cgrad.x[e]);
         pos.store(pp, lane, dim);
     }
 }

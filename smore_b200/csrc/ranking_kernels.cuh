@@ -1,8 +1,9 @@
-// Pairwise-ranking kernels: BPR (Go and C++ variants), WARP, HOP-Rec. Same warp-per-worker scheme as kernels.cuh.
+// Pairwise-ranking kernels with data-dependent draw counts: WARP and HOP-Rec (warp-per-worker over a DrawRing), plus
+// the helpers the ranking updates share. (BPR has a fixed draw count per sample and lives in batch_kernels.cuh.)
 //
-// Every variant first resolves ALL the draws of a sample (they depend on the alias tables / field array only, never on
-// the embeddings), then gathers every row it will touch in one batch (FAST path, rows distinct) or replays the
-// reference's in-place order through memory (ORDERED path, some rows coincide).
+// Every variant first resolves the draws of a sample (they depend on the alias tables / field array only, never on the
+// embeddings), then gathers every row it will touch in one batch (FAST path, rows distinct) or replays the reference's
+// in-place order through memory (ORDERED path, some rows coincide).
 #pragma once
 #include "kernels.cuh"
 
@@ -48,40 +49,40 @@ __device__ __forceinline__ int64_t reject_sample(DrawRing& ring, int lane, uint3
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One BPR-style round shared by the C++ ranking updates, ORDERED flavour (rows re-read from memory, per-element
-// writes in the reference's order: src/proNet.cpp:1426-1440 / :1485-1504 / :1371-1391).
-// Returns false if the round was margin-gated away. verr accumulates in registers (it is a local vector in the
-// reference too).
+// One BPR-style round of the C++ ranking updates, ORDERED flavour (rows re-read from memory, per-element writes in the
+// reference's order: src/proNet.cpp:1426-1440 / :1485-1504). Returns false if the round was margin-gated away
+// (Opt_FBPRSGD, :1023). verr accumulates in registers (it is a local vector in the reference too).
 // ---------------------------------------------------------------------------------------------------------------
 template <class C>
 __device__ __forceinline__ bool ordered_round(typename C::T* pv, typename C::T* pi, typename C::T* pj, int dim, int lane,
                                               const typename C::T* lut, typename C::T alpha, bool gated,
                                               typename C::T margin, Row<C>& verr) {
     using T = typename C::T;
+    using A = Ar<T>;
     Row<C> v, ri, rj, cvec;
     v.load(pv, lane, dim);
     ri.load(pi, lane, dim);
     rj.load(pj, lane, dim);
 #pragma unroll
-    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = ri.x[e] - rj.x[e];
-    T f = dot(v, cvec);
+    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = A::sub(ri.x[e], rj.x[e]);
+    const T f = dot(v, cvec);
     if (gated && f > margin) return false;
-    const T g = fast_sigmoid<T>(lut, (T)0 - f) * alpha;
-    const T c = alpha * (T)0.0025;
+    const T g = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f)), alpha);
+    const T c = A::mul(alpha, (T)0.0025);
     for_owned<C>(lane, dim, [&](int e, int idx) {
-        verr.x[e] += g * cvec.x[e];
-        const T cerr = g * v.x[e];
-        stv(pi + idx, ldv(pi + idx) - c * ldv(pi + idx));
-        stv(pj + idx, ldv(pj + idx) - c * ldv(pj + idx));
-        stv(pi + idx, ldv(pi + idx) + cerr);
-        stv(pj + idx, ldv(pj + idx) - cerr);
+        verr.x[e] = A::madd(verr.x[e], g, cvec.x[e]);
+        const T cerr = A::mul(g, v.x[e]);
+        stv(pi + idx, A::msub(ldv(pi + idx), c, ldv(pi + idx)));
+        stv(pj + idx, A::msub(ldv(pj + idx), c, ldv(pj + idx)));
+        stv(pi + idx, A::add(ldv(pi + idx), cerr));
+        stv(pj + idx, A::sub(ldv(pj + idx), cerr));
     });
     return true;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // WARP: WARP::Train (src/model/WARP.cpp:85-103) + UpdateWARPPair (src/proNet.cpp:1353-1403): scan up to 32
-// negatives, first one with margin f < 1 triggers a single BPR step on three rows. Words: source (p, idx),
+// negatives, the first one with margin f < 1 triggers a single BPR step on three rows. Words: source (p, idx),
 // target (p, idx), negative (idx, p), then (idx, p) per further negative actually scanned.
 // Candidates are evaluated in batches of kWarpBatch rows gathered together; rows do not change before the (single)
 // update, so speculative gathers beyond the first violator are exact, only wasted.
@@ -91,6 +92,7 @@ constexpr int kWarpBatch = 4;
 template <class C>
 __global__ void __launch_bounds__(kBlockThreads) k_warp(TrainArgs<typename C::T> a) {
     using T = typename C::T;
+    using A = Ar<T>;
     uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
     T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
     const T* lut = stage_lut<T>(a.lut, lut_s);
@@ -131,28 +133,19 @@ __global__ void __launch_bounds__(kBlockThreads) k_warp(TrainArgs<typename C::T>
             const int nb = base == 0 ? 1 : min(kWarpBatch, 32 - base);
             int64_t cand = -1;
             if (lane < nb) cand = (int64_t)negative_sample(g, ring.peek(4u + 2u * (uint32_t)(base + lane)), ring.peek(5u + 2u * (uint32_t)(base + lane)));
-            Row<C> rj[kWarpBatch];
+            Row<C> cvec[kWarpBatch];  // context_vec = w[i] - w[j] (proNet.cpp:1373)
             int64_t jid[kWarpBatch];
             T f[kWarpBatch];
 #pragma unroll
             for (int r = 0; r < kWarpBatch; ++r) {
                 jid[r] = __shfl_sync(kFull, cand, r);
-                if (r < nb) rj[r].load(W + jid[r] * dim, lane, dim);
-            }
-#pragma unroll
-            for (int r = 0; r < kWarpBatch; ++r) {
-                T s = 0;
                 if (r < nb) {
+                    cvec[r].load(W + jid[r] * dim, lane, dim);
 #pragma unroll
-                    for (int e = 0; e < C::EPL; ++e) s += v.x[e] * (ri.x[e] - rj[r].x[e]);
+                    for (int e = 0; e < C::EPL; ++e) cvec[r].x[e] = A::sub(ri.x[e], cvec[r].x[e]);
                 }
-                f[r] = s;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int r = 0; r < kWarpBatch; ++r) f[r] += __shfl_xor_sync(kFull, f[r], o);
-            }
+            dots<C, kWarpBatch>(v, cvec, nb, f);
 #pragma unroll
             for (int r = 0; r < kWarpBatch; ++r) {
                 if (r < nb && !hit) {
@@ -161,38 +154,37 @@ __global__ void __launch_bounds__(kBlockThreads) k_warp(TrainArgs<typename C::T>
                         hit = true;
                         const int64_t j = jid[r];
                         T* pj = W + j * dim;
-                        const T c = alpha * (T)0.0025;
+                        const T c = A::mul(alpha, (T)0.0025);
+                        // Opt_BPRSGD recomputes f from the same (unchanged) rows, so f[r] is its value (:1380 -> :1059)
+                        const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f[r])), alpha);
                         if (j != v2 && j != v1 && v1 != v2) {
-                            const T gg = fast_sigmoid<T>(lut, (T)0 - f[r]) * alpha;
+                            Row<C> rj;
+                            rj.load(pj, lane, dim);  // only the difference was kept; the row is an L2 hit now
 #pragma unroll
                             for (int e = 0; e < C::EPL; ++e) {
-                                const T cvec = ri.x[e] - rj[r].x[e];
-                                const T verr = gg * cvec;
-                                const T cerr = gg * v.x[e];
-                                ri.x[e] -= c * ri.x[e];
-                                rj[r].x[e] -= c * rj[r].x[e];
-                                v.x[e] -= c * v.x[e];
-                                ri.x[e] += cerr;
-                                rj[r].x[e] -= cerr;
-                                v.x[e] += verr;
+                                const T verr = A::mul(gg, cvec[r].x[e]);
+                                const T cerr = A::mul(gg, v.x[e]);
+                                ri.x[e] = A::msub(ri.x[e], c, ri.x[e]);
+                                rj.x[e] = A::msub(rj.x[e], c, rj.x[e]);
+                                v.x[e] = A::msub(v.x[e], c, v.x[e]);
+                                ri.x[e] = A::add(ri.x[e], cerr);
+                                rj.x[e] = A::sub(rj.x[e], cerr);
+                                v.x[e] = A::add(v.x[e], verr);
                             }
                             ri.store(pi, lane, dim);
-                            rj[r].store(pj, lane, dim);
+                            rj.store(pj, lane, dim);
                             v.store(pv, lane, dim);
                         } else {
-                            // coinciding rows: the reference's per-element order through memory (proNet.cpp:1380-1391).
-                            // Opt_BPRSGD recomputes f from the same (unchanged) rows, so f[r] is its value.
-                            const T gg = fast_sigmoid<T>(lut, (T)0 - f[r]) * alpha;
+                            // coinciding rows: the reference's per-element order through memory (proNet.cpp:1382-1391)
                             for_owned<C>(lane, dim, [&](int e, int idx) {
-                                const T cvec = ri.x[e] - rj[r].x[e];
-                                const T verr = gg * cvec;
-                                const T cerr = gg * v.x[e];
-                                stv(pi + idx, ldv(pi + idx) - c * ldv(pi + idx));
-                                stv(pj + idx, ldv(pj + idx) - c * ldv(pj + idx));
-                                stv(pv + idx, ldv(pv + idx) - c * ldv(pv + idx));
-                                stv(pi + idx, ldv(pi + idx) + cerr);
-                                stv(pj + idx, ldv(pj + idx) - cerr);
-                                stv(pv + idx, ldv(pv + idx) + verr);
+                                const T verr = A::mul(gg, cvec[r].x[e]);
+                                const T cerr = A::mul(gg, v.x[e]);
+                                stv(pi + idx, A::msub(ldv(pi + idx), c, ldv(pi + idx)));
+                                stv(pj + idx, A::msub(ldv(pj + idx), c, ldv(pj + idx)));
+                                stv(pv + idx, A::msub(ldv(pv + idx), c, ldv(pv + idx)));
+                                stv(pi + idx, A::add(ldv(pi + idx), cerr));
+                                stv(pj + idx, A::sub(ldv(pj + idx), cerr));
+                                stv(pv + idx, A::add(ldv(pv + idx), verr));
                             });
                         }
                     }
@@ -217,6 +209,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_warp(TrainArgs<typename C::T>
 template <class C>
 __global__ void __launch_bounds__(kBlockThreads) k_hoprec(TrainArgs<typename C::T> a) {
     using T = typename C::T;
+    using A = Ar<T>;
     uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
     T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
     const T* lut = stage_lut<T>(a.lut, lut_s);
@@ -275,9 +268,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_hoprec(TrainArgs<typename C::
                 jid[r] = reject_sample(ring, lane, 1u,
                                        [&](uint32_t w0, uint32_t) { return (int64_t)index_draw(w0, V32); },
                                        [&](int64_t x) { return __ldg(g.field + x) == cfield; });
-            const T alpha = (T)(st.alpha / (double)hop);
+            const T alpha = (T)(st.alpha / (double)hop);  // _alpha/w, margin/w (HBPR.cpp:113)
             const T margin = (T)(1.0 / (double)hop);
-            const T cdec = alpha * (T)0.0025;
+            const T cdec = A::mul(alpha, (T)0.0025);
+            const T cv = A::mul(alpha, (T)0.025);
             T* pv = W + vid * dim;
             T* pi = W + cid * dim;
             bool dup = vid == cid;
@@ -301,19 +295,19 @@ __global__ void __launch_bounds__(kBlockThreads) k_hoprec(TrainArgs<typename C::
                 for (int r = 0; r < 5; ++r) {
                     Row<C> cvec;
 #pragma unroll
-                    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = ri.x[e] - rj[r].x[e];
+                    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = A::sub(ri.x[e], rj[r].x[e]);
                     const T f = dot(v, cvec);
                     if (!(f > margin)) {
-                        const T gg = fast_sigmoid<T>(lut, (T)0 - f) * alpha;
+                        const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f)), alpha);
                         up += (T)1;
 #pragma unroll
                         for (int e = 0; e < C::EPL; ++e) {
-                            verr.x[e] += gg * cvec.x[e];
-                            const T cerr = gg * v.x[e];
-                            ri.x[e] -= cdec * ri.x[e];
-                            rj[r].x[e] -= cdec * rj[r].x[e];
-                            ri.x[e] += cerr;
-                            rj[r].x[e] -= cerr;
+                            verr.x[e] = A::madd(verr.x[e], gg, cvec.x[e]);
+                            const T cerr = A::mul(gg, v.x[e]);
+                            ri.x[e] = A::msub(ri.x[e], cdec, ri.x[e]);
+                            rj[r].x[e] = A::msub(rj[r].x[e], cdec, rj[r].x[e]);
+                            ri.x[e] = A::add(ri.x[e], cerr);
+                            rj[r].x[e] = A::sub(rj[r].x[e], cerr);
                         }
                         rj[r].store(W + jid[r] * dim, lane, dim);
                         ri_dirty = true;
@@ -321,11 +315,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_hoprec(TrainArgs<typename C::
                 }
                 if (ri_dirty) ri.store(pi, lane, dim);
                 if (up > (T)0) {
-                    const T cv = alpha * (T)0.025;
 #pragma unroll
                     for (int e = 0; e < C::EPL; ++e) {
-                        v.x[e] -= cv * v.x[e];
-                        v.x[e] += verr.x[e] / up;
+                        v.x[e] = A::msub(v.x[e], cv, v.x[e]);
+                        v.x[e] = A::add(v.x[e], A::div(verr.x[e], up));
                     }
                     v.store(pv, lane, dim);
                 }
@@ -333,10 +326,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_hoprec(TrainArgs<typename C::
                 for (int r = 0; r < 5; ++r)
                     if (ordered_round<C>(pv, pi, W + jid[r] * dim, dim, lane, lut, alpha, true, margin, verr)) up += (T)1;
                 if (up > (T)0) {
-                    const T cv = alpha * (T)0.025;
                     for_owned<C>(lane, dim, [&](int e, int idx) {
-                        stv(pv + idx, ldv(pv + idx) - cv * ldv(pv + idx));
-                        stv(pv + idx, ldv(pv + idx) + verr.x[e] / up);
+                        stv(pv + idx, A::msub(ldv(pv + idx), cv, ldv(pv + idx)));
+                        stv(pv + idx, A::add(ldv(pv + idx), A::div(verr.x[e], up)));
                     });
                 }
             }

@@ -75,9 +75,9 @@ def test_line_train_1m(order):
         m.set_rows(1, G["g300_init_c"])
     st = m.train_line(params(total=1000000, order=order))
     assert st["words_stream0"] == int(G[f"line{order}_words"])
-    assert rel_err(m.get_rows(0), G[f"line{order}_v"]) < 1e-5
+    assert rel_err(m.get_rows(0), G[f"line{order}_v"]) == 0.0
     if order == 2:
-        assert rel_err(m.get_rows(1), G["line2_c"]) < 1e-5
+        assert rel_err(m.get_rows(1), G["line2_c"]) == 0.0
 
 
 @pytest.mark.parametrize("walklets", [0, 1])
@@ -90,7 +90,7 @@ def test_walk_models(walklets):
     p = params(walk_times=3, walk_steps=20, window_min=2 if walklets else 1, window_max=4 if walklets else 5)
     st = m.train_walklets(p) if walklets else m.train_deepwalk(p)
     assert st["words_stream0"] == int(G[f"{nm}_words"])
-    assert rel_err(m.get_rows(0), G[f"{nm}_v"]) < 1e-5 and rel_err(m.get_rows(1), G[f"{nm}_c"]) < 1e-5
+    assert rel_err(m.get_rows(0), G[f"{nm}_v"]) == 0.0 and rel_err(m.get_rows(1), G[f"{nm}_c"]) == 0.0
 
 
 def test_ranking_models():
@@ -101,7 +101,7 @@ def test_ranking_models():
         m.set_rows(0, G[f"{nm}_init"])
         st = (m.train_bpr if nm == "bpr" else m.train_warp)(params(total=1000000))
         assert st["words_stream0"] == int(G[f"{nm}_words"])
-        assert rel_err(m.get_rows(0), G[f"{nm}_v"]) < 1e-5
+        assert rel_err(m.get_rows(0), G[f"{nm}_v"]) == 0.0
     off, col, ww, _ = B.edges_to_csr(G["bip_src"], G["bip_dst"], G["bip_w"], 1)
     g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP, negative_method=capi.NEG_NO_DEGREES)
     g.set_field(G["hoprec_field"])
@@ -109,4 +109,4 @@ def test_ranking_models():
     m.set_rows(0, G["hoprec_init"])
     st = m.train_hoprec(params(total=1000000, walk_steps=3))
     assert st["words_stream0"] == int(G["hoprec_words"])
-    assert rel_err(m.get_rows(0), G["hoprec_v"]) < 1e-5
+    assert rel_err(m.get_rows(0), G["hoprec_v"]) == 0.0
