@@ -1,0 +1,208 @@
+// Host-side mirror of the reference CLIs on top of the C ABI (include/smore_b200.h).
+//
+//   smore <model> -train net.txt -save rep.txt [flags]      model in {line, deepwalk, walklets, bpr, warp, hoprec}
+//   (or invoke through a symlink named after the model: `line -train ...`)
+//
+// Flag names, defaults and the four-call sequence LoadEdgeList -> Init -> Train -> SaveWeights are those of
+// cmd/{line,deepwalk,bpr}/main.go (Go tree) and cli/{line,deepwalk,walklets,bpr,warp,hoprec}.cpp (C++ tree). Both flag
+// spellings are accepted (`-undirected 1` as the C++ ArgPos parser takes it, `-undirected=false` / bare `-undirected`
+// as Go's flag package does). Extra flags: -semantics {go,cpp} (which tree's maths; default go where a Go CLI exists),
+// -mode {hogwild,deterministic}, -seed N, -dtype {f32,f64}. -threads is accepted and ignored: the workers are GPU warps.
+// The Go toolchain is not available in the build image; INTEGRATION.md has the cgo binding that calls the same ABI.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "../../include/smore_b200.h"
+
+namespace {
+
+struct Args {
+    std::map<std::string, std::string> kv;
+    bool has(const std::string& k) const { return kv.count(k) != 0; }
+    std::string str(const std::string& k, const std::string& d) const { return has(k) ? kv.at(k) : d; }
+    long num(const std::string& k, long d) const { return has(k) ? atol(kv.at(k).c_str()) : d; }
+    double real(const std::string& k, double d) const { return has(k) ? atof(kv.at(k).c_str()) : d; }
+    bool flag(const std::string& k, bool d) const {
+        if (!has(k)) return d;
+        const std::string& v = kv.at(k);
+        return !(v == "0" || v == "false" || v == "False" || v == "FALSE" || v == "f");
+    }
+};
+
+bool looks_bool(const char* s) {
+    static const char* vals[] = {"0", "1", "true", "false", "True", "False", "TRUE", "FALSE", "t", "f"};
+    for (const char* v : vals)
+        if (!strcmp(s, v)) return true;
+    return false;
+}
+
+Args parse(int argc, char** argv, int first) {
+    Args a;
+    for (int i = first; i < argc; ++i) {
+        const char* s = argv[i];
+        if (s[0] != '-') continue;
+        while (*s == '-') ++s;
+        std::string key(s), val;
+        size_t eq = key.find('=');
+        if (eq != std::string::npos) {
+            val = key.substr(eq + 1);
+            key = key.substr(0, eq);
+        } else if (key == "undirected") {  // Go bool flag: bare means true; C++: `-undirected 1`
+            if (i + 1 < argc && looks_bool(argv[i + 1])) val = argv[++i];
+            else val = "true";
+        } else if (i + 1 < argc) {
+            val = argv[++i];
+        }
+        a.kv[key] = val;
+    }
+    return a;
+}
+
+int die(const char* what) {
+    fprintf(stderr, "smore: %s: %s\n", what, smore_last_error());
+    return 1;
+}
+
+void usage() {
+    printf("[smore_b200]\n\tB200-native SMORe trainers (LINE, DeepWalk, Walklets, BPR, WARP, HOP-Rec)\n\n"
+           "Usage:\n\tsmore <line|deepwalk|walklets|bpr|warp|hoprec> -train net.txt -save rep.txt [options]\n\n"
+           "Options Description:\n"
+           "\t-train <string>\n\t\tTrain the Network data\n"
+           "\t-save <string>\n\t\tSave the representation data\n"
+           "\t-field <string>\n\t\tField data (hoprec)\n"
+           "\t-dimensions <int>\n\t\tDimension of vertex representation; default is 64\n"
+           "\t-undirected <bool>\n\t\tWhether the edge is undirected; default is 1 (line, deepwalk, walklets), 0 (bpr, warp)\n"
+           "\t-negative_samples <int>\n\t\tNumber of negative examples; default is 5\n"
+           "\t-order <int>\n\t\tLINE: order of proximity (1 or 2); default is 2\n"
+           "\t-sample_times <int>\n\t\tNumber of training samples (cpp: *Million, go: *edge lines); default is 10\n"
+           "\t-walk_times <int> -walk_steps <int> -window_size <int> -window_min <int> -window_max <int>\n"
+           "\t-lambda <float>\n\t\tGo BPR regularisation; default is 0.001\n"
+           "\t-alpha <float>\n\t\tInit learning rate; default is 0.025\n"
+           "\t-threads <int>\n\t\tAccepted for compatibility; workers are GPU warps\n"
+           "\t-semantics <go|cpp> -mode <hogwild|deterministic> -seed <int> -dtype <f32|f64> -device <int>\n");
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    std::string model;
+    int first = 1;
+    const char* base = strrchr(argv[0], '/');
+    base = base ? base + 1 : argv[0];
+    for (const char* m : {"line", "deepwalk", "walklets", "bpr", "warp", "hoprec"})
+        if (!strcmp(base, m)) model = m;
+    if (model.empty()) {
+        if (argc < 2 || argv[1][0] == '-') {
+            usage();
+            return argc < 2 ? 0 : 1;
+        }
+        model = argv[1];
+        first = 2;
+    }
+    if (argc <= first) {
+        usage();
+        return 0;
+    }
+    Args a = parse(argc, argv, first);
+    const bool has_go_cli = model == "line" || model == "deepwalk" || model == "bpr";
+    if (!has_go_cli && model != "walklets" && model != "warp" && model != "hoprec") {
+        fprintf(stderr, "smore: unknown model '%s'\n", model.c_str());
+        return 1;
+    }
+    const std::string sem_s = a.str("semantics", has_go_cli ? "go" : "cpp");
+    const int sem = sem_s == "go" ? SMORE_SEM_GO : SMORE_SEM_CPP;
+    if (sem == SMORE_SEM_GO && !has_go_cli) {
+        fprintf(stderr, "smore: %s exists only in the C++ tree; use -semantics cpp\n", model.c_str());
+        return 1;
+    }
+    const std::string train = a.str("train", ""), save = a.str("save", "");
+    if (train.empty() || save.empty()) {
+        usage();
+        return 1;
+    }
+    const bool ranking = model == "bpr" || model == "warp" || model == "hoprec";
+    // defaults: cmd/line/main.go:15-21, cmd/deepwalk/main.go:13-22, cmd/bpr/main.go:13-20, cli/*.cpp
+    const int dim = (int)a.num("dimensions", 64);
+    const bool undirected = model == "hoprec" ? true : a.flag("undirected", !(model == "bpr" || model == "warp"));
+    const int sample_times = (int)a.num("sample_times", 10);
+    const int dtype = a.str("dtype", "f32") == "f64" ? SMORE_F64 : SMORE_F32;
+
+    if (smore_init((int)a.num("device", 0))) return die("init");
+    const int neg_method = (sem == SMORE_SEM_CPP && ranking) ? SMORE_NEG_NO_DEGREES : SMORE_NEG_DEGREES;  // BPR.cpp:4-7
+    smore_graph_t g = nullptr;
+    if (smore_graph_load_edge_list(train.c_str(), undirected, sem, neg_method, &g)) return die("LoadEdgeList");
+    int64_t V = 0, E = 0, n_lines = 0;
+    smore_graph_info(g, &V, &E, &n_lines);
+    printf("Graph loaded: %lld vertices, %lld edge lines, %lld adjacency entries\n", (long long)V,
+           (long long)(sem == SMORE_SEM_GO ? n_lines : (undirected ? n_lines / 2 : n_lines)), (long long)E);
+    if (model == "hoprec") {
+        if (!a.has("field")) {
+            fprintf(stderr, "smore: hoprec needs -field\n");
+            return 1;
+        }
+        if (smore_graph_load_field(g, a.str("field", "").c_str())) return die("LoadFieldMeta");
+    }
+
+    smore_train_params p;
+    smore_train_params_default(&p);
+    p.semantics = sem;
+    p.mode = a.str("mode", "hogwild") == "deterministic" ? SMORE_MODE_DETERMINISTIC : SMORE_MODE_HOGWILD;
+    p.seed = (uint64_t)a.num("seed", 1);
+    p.alpha = a.real("alpha", 0.025);
+    p.negative_samples = (int)a.num("negative_samples", 5);
+    p.order = a.num("order", 2) == 1 ? 1 : 2;
+    p.lambda = a.real("lambda", 0.001);
+    p.walk_times = (int)a.num("walk_times", 10);
+    // cli/deepwalk.cpp:56 defaults walk_steps to 5 (sic), cli/walklets.cpp:54 and cmd/deepwalk/main.go:20 to 40
+    p.walk_steps = (int)a.num("walk_steps", model == "hoprec" ? 5 : (model == "deepwalk" && sem == SMORE_SEM_CPP ? 5 : 40));
+    p.window_min = (int)a.num("window_min", model == "walklets" ? 2 : 1);
+    p.window_max = (int)a.num(model == "walklets" ? "window_max" : "window_size", 5);
+    // LINE.cpp:119 (sample_times * 1e6) vs line.go:85 (sample_times * MaxLine)
+    p.total = sem == SMORE_SEM_CPP ? (uint64_t)sample_times * 1000000ull : (uint64_t)sample_times * (uint64_t)n_lines;
+
+    // tables: Go models own wVertex + wContext, both random (line.go:52-69); C++ LINE-2: context zeros (LINE.cpp:92),
+    // LINE-1 / BPR / WARP / HOP-Rec: one table (LINE.cpp:73-84, BPR.cpp:44-51), DeepWalk: both random (DeepWalk.cpp:44-56)
+    int n_tables = 2;
+    if (sem == SMORE_SEM_CPP && (ranking || (model == "line" && p.order == 1))) n_tables = 1;
+    if (sem == SMORE_SEM_GO && model == "line" && p.order == 1) n_tables = 1;
+    smore_model_t m = nullptr;
+    if (smore_model_create(g, dim, n_tables, dtype, &m)) return die("Init");
+    printf("Model Setting:\n\tdimension:\t\t%d\n", dim);
+    if (smore_model_init(m, 0, 1, p.seed)) return die("Init");
+    if (n_tables == 2) {
+        const bool ctx_random = !(sem == SMORE_SEM_CPP && model == "line");
+        if (smore_model_init(m, 1, ctx_random ? 1 : 0, p.seed)) return die("Init");
+    }
+
+    printf("Model:\n\t[%s] (%s semantics, %s, %s)\n", model.c_str(), sem_s.c_str(),
+           p.mode == SMORE_MODE_HOGWILD ? "hogwild" : "deterministic", dtype == SMORE_F64 ? "f64" : "f32");
+    printf("Learning Parameters:\n\tsample_times:\t\t%d\n\tnegative_samples:\t%d\n\talpha:\t\t\t%g\n", sample_times,
+           p.negative_samples, p.alpha);
+    if (a.has("threads")) printf("\tworkers:\t\t-threads %ld ignored: workers are GPU warps\n", a.num("threads", 1));
+    printf("Start Training:\n");
+    int rc;
+    if (model == "line") rc = smore_train_line(m, &p);
+    else if (model == "deepwalk") rc = smore_train_deepwalk(m, &p);
+    else if (model == "walklets") rc = smore_train_walklets(m, &p);
+    else if (model == "bpr") rc = smore_train_bpr(m, &p);
+    else if (model == "warp") rc = smore_train_warp(m, &p);
+    else rc = smore_train_hoprec(m, &p);
+    if (rc) return die("Train");
+    uint64_t samples = 0, pairs = 0;
+    double ms = 0;
+    smore_train_stats(m, &samples, &pairs, nullptr, nullptr, &ms);
+    printf("\tAlpha: %.6f\tProgress: 100.00 %%\n", p.alpha * 0.0001);
+    printf("\t%llu samples, %llu pair updates in %.1f ms on the device (%.1f M updates/s)\n",
+           (unsigned long long)samples, (unsigned long long)pairs, ms, ms > 0 ? pairs / ms / 1e3 : 0.0);
+
+    printf("Save Model:\n");
+    // number format: C++ iostream default (%g) vs Go "%.6f" (LINE.cpp:37, line.go:226)
+    if (smore_model_save_weights(m, 0, save.c_str(), sem == SMORE_SEM_GO ? 1 : 0)) return die("SaveWeights");
+    printf("\tSave to <%s>\n", save.c_str());
+    smore_model_destroy(m);
+    smore_graph_destroy(g);
+    return 0;
+}
