@@ -121,6 +121,25 @@ int smore_model_get_rows_f32(smore_model_t m, int table, int64_t first, int64_t 
 int smore_model_device_ptr(smore_model_t m, int table, void** ptr);
 void smore_model_destroy(smore_model_t m);
 
+/* ---- row sharding across the GPUs of one NVSwitch box: one process per GPU. New with this backend --
+ * the reference is single-process shared memory (src/model/LINE.cpp:162 OpenMP workers on one table).
+ *
+ * Vertex v is owned by rank v & (world-1) (world in {1,2,4,8}); its local row is v >> log2(world). After
+ * smore_graph_set_shard the graph's source and negative alias tables cover the OWNED vertices only (owner-computes: a rank
+ * draws sources from its own vertices and its negatives from its own shard), the CSR stays replicated, and
+ * smore_model_create allocates only the owned rows. The positive context row of a sample may live on any rank: kernels
+ * reach it with plain 128-bit loads/stores through CUDA-IPC peer mappings (NVLink). smore_train_line then runs
+ * round(total * source_mass_fraction) samples on this rank, so the union over ranks reproduces the global source
+ * distribution. set_rows / get_rows / init address LOCAL rows. */
+int smore_graph_set_shard(smore_graph_t g, int rank, int world);
+int smore_graph_shard_info(smore_graph_t g, int* rank, int* world, int64_t* n_local, double* source_mass_fraction);
+/* 64-byte cudaIpcMemHandle_t of this rank's shard of `table` (exchange with the host's own transport, e.g.
+ * torch.distributed all_gather), then connect every peer: handles = world x 64 bytes, indexed by rank. */
+int smore_model_ipc_handle(smore_model_t m, int table, void* handle64);
+int smore_model_open_peers(smore_model_t m, int table, const void* handles);
+/* Same-process variant (several shards on one device, used by tests): raw device pointers indexed by rank. */
+int smore_model_set_peer_ptrs(smore_model_t m, int table, void* const* ptrs);
+
 /* Text writer: "<V> <dim>\n" then `name v0 v1 ...` per vertex in id order, VERTEX table only.
  * format 0 = C++ iostream default (%g, 6 significant digits; src/model/LINE.cpp:13-47),
  * format 1 = Go "%.6f" (internal/models/line/line.go:209-233). */

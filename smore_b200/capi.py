@@ -30,7 +30,8 @@ EXPORTS = [
     "smore_graph_get_field", "smore_graph_destroy", "smore_sample_debug", "smore_walk_debug",
     "smore_model_create", "smore_model_init", "smore_model_set_rows", "smore_model_get_rows",
     "smore_model_set_rows_f32", "smore_model_get_rows_f32", "smore_model_device_ptr", "smore_model_destroy",
-    "smore_model_save_weights", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
+    "smore_graph_set_shard", "smore_graph_shard_info", "smore_model_ipc_handle", "smore_model_open_peers",
+    "smore_model_set_peer_ptrs", "smore_model_save_weights", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
     "smore_train_warp", "smore_train_hoprec", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
 ]
 
@@ -86,6 +87,11 @@ def lib():
         L.smore_model_destroy.argtypes = [vp]
         L.smore_model_destroy.restype = None
         L.smore_model_save_weights.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
+        L.smore_graph_set_shard.argtypes = [vp, C.c_int, C.c_int]
+        L.smore_graph_shard_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64), C.POINTER(f64)]
+        L.smore_model_ipc_handle.argtypes = [vp, C.c_int, vp]
+        L.smore_model_open_peers.argtypes = [vp, C.c_int, vp]
+        L.smore_model_set_peer_ptrs.argtypes = [vp, C.c_int, vp]
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
         L.smore_train_params_default.restype = None
         for name in ("smore_train_line", "smore_train_bpr", "smore_train_warp", "smore_train_hoprec",
@@ -152,6 +158,16 @@ class Graph:
             self.close()
         except Exception:
             pass
+
+    def set_shard(self, rank, world):
+        """Row-shard: this rank owns vertices v with v % world == rank (world in {1,2,4,8})."""
+        check(lib().smore_graph_set_shard(self.h, rank, world))
+        return self.shard_info()
+
+    def shard_info(self):
+        r, w, n, f = C.c_int(), C.c_int(), i64(), f64()
+        check(lib().smore_graph_shard_info(self.h, C.byref(r), C.byref(w), C.byref(n), C.byref(f)))
+        return {"rank": r.value, "world": w.value, "n_local": n.value, "source_mass_fraction": f.value}
 
     def load_field(self, path):
         check(lib().smore_graph_load_field(self.h, os.fsencode(path)))
@@ -236,12 +252,30 @@ class Model:
             W = np.ascontiguousarray(W, dtype=np.float64)
             check(lib().smore_model_set_rows(self.h, table, first, W.shape[0], _ptr(W)))
 
+    @property
+    def rows(self):
+        return self.graph.shard_info()["n_local"]
+
     def get_rows(self, table, first=0, n=None, dtype=np.float64, out=None):
-        n = self.graph.V - first if n is None else n
+        n = self.rows - first if n is None else n
         W = out if out is not None else np.zeros((n, self.dim), dtype=dtype)
         fn = lib().smore_model_get_rows_f32 if W.dtype == np.float32 else lib().smore_model_get_rows
         check(fn(self.h, table, first, n, _ptr(W)))
         return W
+
+    def ipc_handle(self, table) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        check(lib().smore_model_ipc_handle(self.h, table, C.cast(buf, vp)))
+        return bytes(buf)
+
+    def open_peers(self, table, handles: bytes):
+        """handles = world x 64 bytes (cudaIpcMemHandle_t per rank, in rank order)."""
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        check(lib().smore_model_open_peers(self.h, table, C.cast(buf, vp)))
+
+    def set_peer_ptrs(self, table, ptrs):
+        arr = (vp * len(ptrs))(*[vp(p) for p in ptrs])
+        check(lib().smore_model_set_peer_ptrs(self.h, table, C.cast(arr, vp)))
 
     def device_ptr(self, table):
         p = vp()

@@ -68,7 +68,7 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
     if (lane < nb) {
         const uint32_t* wd = b.wbuf + ((uint32_t)st.pos & 3u) + lane * b.wps;
         int* my_ids = b.ids + lane * b.idw;
-        const uint32_t V32 = (uint32_t)g.V;
+        const uint32_t V32 = g.n_neg;
         constexpr int noff = GO ? 3 : 4;
         // negatives first: independent lookups, issued 8 at a time
         for (int n0 = 0; n0 < b.K; n0 += 8) {
@@ -82,7 +82,7 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
                 }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (n0 + j < b.K) my_ids[2 + n0 + j] = (int)(wd[noff + 2 * (n0 + j) + 1] < e[j].x ? idx[j] : e[j].y);
+                if (n0 + j < b.K) my_ids[2 + n0 + j] = (int)g.global_id(wd[noff + 2 * (n0 + j) + 1] < e[j].x ? idx[j] : e[j].y);
         }
         // then the dependent source -> target chain
         const int v1 = (int)source_sample(g, wd[0], wd[1]);
@@ -95,9 +95,25 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
     __syncwarp();
 }
 
-// L2 prefetch of every row of one sample (ids row `pid`: slot 0 lives in Wv, the others in Wc).
+// L2 prefetch of every row of one sample (ids row `pid`: slot 0 lives in the vertex table, the others in the context
+// table). Rows of a peer shard are skipped: peer addresses bypass the local L2.
 template <typename T>
-__device__ __forceinline__ void prefetch_sample(const T* Wv, const T* Wc, const int* pid, int idw, int dim, int lane) {
+__device__ __forceinline__ void prefetch_sample(const TableView<T>& tv, const TableView<T>& tc, int rank, const int* pid,
+                                                int idw, int lane) {
+    const int lines_per_row = (tv.dim * (int)sizeof(T) + 127) >> 7;
+    const int total = idw * lines_per_row;
+    for (int t = lane; t < total; t += 32) {
+        const int r = t / lines_per_row, ln = t - r * lines_per_row;
+        const int id = pid[r];
+        if (id >= 0 && (id & tv.mask) == rank) {
+            const char* p = reinterpret_cast<const char*>(r == 0 ? tv.row(id) : tc.row(id)) + (ln << 7);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void prefetch_local(const T* Wv, const T* Wc, const int* pid, int idw, int dim, int lane) {
     const int lines_per_row = (dim * (int)sizeof(T) + 127) >> 7;
     const int total = idw * lines_per_row;
     for (int t = lane; t < total; t += 32) {
@@ -117,6 +133,8 @@ template <class C, bool GO>
 __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
     using T = typename C::T;
     const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
+    TableView<T> tv, tc;
+    stage_views<T>(a, tv, tc);
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int w = blockIdx.x * kWarpsPerBlock + wib;
@@ -129,15 +147,15 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
         const int nb = (int)min((uint64_t)32, a.jobs - done);
         batch_sample<GO>(a.g, b, a.seed, stream, st, nb, lane);
         for (int s = 0; s < nb; ++s) {
-            if (s + kLinePrefetch < nb) prefetch_sample<T>(a.Wv, a.Wc, b.ids + (s + kLinePrefetch) * b.idw, b.idw, a.dim, lane);
+            if (s + kLinePrefetch < nb) prefetch_sample<T>(tv, tc, a.g.shard_rank, b.ids + (s + kLinePrefetch) * b.idw, b.idw, lane);
             const int* sid = b.ids + s * b.idw;
             const int v1 = sid[0];
             const int v2 = sid[1];
             const int my = lane < nrows ? sid[1 + lane] : (-1 - lane);  // lane 0: positive context, lane 1+n: negative n
             if (v2 < 0) continue;
             const T alpha = (T)st.alpha;
-            if (!GO) update_pair_cpp<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, lut, v1, my, nrows, alpha, lane);
-            else update_pair_go<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, a.order == 1, lut, v1, my, nrows, alpha, lane);
+            if (!GO) update_pair_cpp<C>(tv, tc, a.dim, a.same_table != 0, lut, v1, my, nrows, alpha, lane);
+            else update_pair_go<C>(tv, tc, a.dim, a.same_table != 0, a.order == 1, lut, v1, my, nrows, alpha, lane);
             st.count++;
             st.pairs++;
             sched_tick(st, a.sched);
@@ -166,7 +184,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go
         const int nb = (int)min((uint64_t)32, a.jobs - done);
         batch_sample<true>(a.g, b, a.seed, stream, st, nb, lane);
         for (int s = 0; s < nb; ++s) {
-            if (s + kLinePrefetch < nb) prefetch_sample<T>(a.Wv, a.Wc, b.ids + (s + kLinePrefetch) * b.idw, b.idw, dim, lane);
+            if (s + kLinePrefetch < nb) prefetch_local<T>(a.Wv, a.Wc, b.ids + (s + kLinePrefetch) * b.idw, b.idw, dim, lane);
             const int* sid = b.ids + s * b.idw;
             const int user = sid[0], pos = sid[1], neg = sid[2];
             if (pos < 0) continue;
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_cp
         const int nb = (int)min((uint64_t)32, a.jobs - done);
         batch_sample<false>(a.g, b, a.seed, stream, st, nb, lane);
         for (int s = 0; s < nb; ++s) {
-            if (s + kLinePrefetch < nb) prefetch_sample<T>(W, W, b.ids + (s + kLinePrefetch) * b.idw, b.idw, dim, lane);
+            if (s + kLinePrefetch < nb) prefetch_local<T>(W, W, b.ids + (s + kLinePrefetch) * b.idw, b.idw, dim, lane);
             const int* sid = b.ids + s * b.idw;
             const int v1 = sid[0], v2 = sid[1];
             if (v2 < 0) continue;

@@ -31,6 +31,22 @@ struct GraphDev {
     const double* prefix;      // E   Go semantics: running sum of weights inside each vertex' slice
     const int32_t* field;      // V   (HOP-Rec)
     int sem;                   // SMORE_SEM_*
+    // Row sharding (multi-GPU, one process per GPU): vertex v is owned by rank v & (world-1), its local row is
+    // v >> shard_shift. vertex_at / negative_at then cover the OWNED vertices only (n_src = n_neg = owned count, entries
+    // are local indices); world == 1: n_src = n_neg = V, shard_shift = shard_rank = 0 and ids are global already.
+    uint32_t n_src, n_neg;
+    int shard_shift, shard_rank;
+    __device__ __forceinline__ uint32_t global_id(uint32_t local) const { return (local << shard_shift) + (uint32_t)shard_rank; }
+};
+
+// A (possibly row-sharded) embedding table: base[r] = rank r's shard (the local cudaMalloc, or a CUDA-IPC peer mapping
+// reached over NVLink). Bases live in shared memory: a dynamically indexed kernel-parameter array would be demoted
+// to local memory.
+template <typename T>
+struct TableView {
+    T* const* base;
+    int shift, mask, dim;
+    __device__ __forceinline__ T* row(int id) const { return base[id & mask] + (size_t)(id >> shift) * dim; }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -83,12 +99,12 @@ __device__ __forceinline__ uint32_t alias_pick(const uint2* __restrict__ at, uin
 __device__ __forceinline__ uint32_t source_sample(const GraphDev& g, uint32_t w0, uint32_t w1) {
     uint32_t kp = g.sem == 0 ? w0 : w1;
     uint32_t ki = g.sem == 0 ? w1 : w0;
-    return alias_pick(g.vertex_at, index_draw(ki, (uint32_t)g.V), kp);
+    return g.global_id(alias_pick(g.vertex_at, index_draw(ki, g.n_src), kp));
 }
 
 // NegativeSample: index then p in both trees (src/proNet.cpp:625-626; alias.go:99-100). 2 words.
 __device__ __forceinline__ uint32_t negative_sample(const GraphDev& g, uint32_t w0, uint32_t w1) {
-    return alias_pick(g.negative_at, index_draw(w0, (uint32_t)g.V), w1);
+    return g.global_id(alias_pick(g.negative_at, index_draw(w0, g.n_neg), w1));
 }
 
 // TargetSample(v). C++ (src/proNet.cpp:671-683): p, then index into the vertex' alias slice: 2 words, O(1).

@@ -18,6 +18,7 @@ constexpr int kWarpsPerBlock = 8;
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 constexpr int kCtxChunk = 6;      // context rows gathered per batch (1 positive + 5 negatives = the default K)
 constexpr int kMaxWalkLen = 256;  // walk_steps + 1 <= kMaxWalkLen
+constexpr int kMaxWorld = 8;      // ranks of one NVSwitch box
 #ifndef SMORE_LINE_PREFETCH
 #define SMORE_LINE_PREFETCH 2
 #endif
@@ -26,8 +27,11 @@ constexpr int kLinePrefetch = SMORE_LINE_PREFETCH;  // L2 prefetch distance (sam
 template <typename T>
 struct TrainArgs {
     GraphDev g;
-    T* Wv;
+    T* Wv;  // local shard (== the whole table when world == 1)
     T* Wc;
+    T* peer_v[kMaxWorld];  // rank r's shard of the vertex / context table (peer_x[rank] == Wx)
+    T* peer_c[kMaxWorld];
+    int world_shift, world_mask;
     int dim;
     int same_table;  // Wv == Wc
     const T* lut;    // 1001-entry sigmoid table in global memory (copied to shared)
@@ -50,7 +54,8 @@ struct TrainArgs {
 // my_id: lane 0 holds the positive context, lane 1+n negative n; nrows = K+1 <= 32.
 // ---------------------------------------------------------------------------------------------------------------
 template <class C>
-__device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T* Wc, int dim, bool same_table,
+__device__ __forceinline__ void update_pair_cpp(const TableView<typename C::T>& tv,
+                                                const TableView<typename C::T>& tc, int dim, bool same_table,
                                                 const typename C::T* lut, int v1, int my_id, int nrows,
                                                 typename C::T alpha, int lane) {
     using T = typename C::T;
@@ -58,7 +63,7 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
     bool active = lane < nrows;
     unsigned peers = __match_any_sync(kFull, active ? my_id : (-1 - lane));
     bool dup = __any_sync(kFull, (active && __popc(peers) > 1) || (active && same_table && my_id == v1));
-    T* pv = Wv + (size_t)v1 * dim;
+    T* pv = tv.row(v1);
     if (!dup) {
         Row<C> v, back;
         v.load(pv, lane, dim);
@@ -69,7 +74,7 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
 #pragma unroll
             for (int r = 0; r < kCtxChunk; ++r) {
                 ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
-                if (base + r < nrows) c[r].load(Wc + (size_t)ids[r] * dim, lane, dim);
+                if (base + r < nrows) c[r].load(tc.row(ids[r]), lane, dim);
             }
             T f[kCtxChunk];
             dots<C, kCtxChunk>(v, c, nrows - base, f);
@@ -83,7 +88,7 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
                         back.x[e] = A::madd(back.x[e], g, c[r].x[e]);  // loss_vertex += g * w_context
                         c[r].x[e] = A::madd(c[r].x[e], g, v.x[e]);     // w_context   += g * w_vertex (in place)
                     }
-                    c[r].store(Wc + (size_t)ids[r] * dim, lane, dim);
+                    c[r].store(tc.row(ids[r]), lane, dim);
                 }
             }
         }
@@ -95,7 +100,7 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
         back.zero();
         for (int r = 0; r < nrows; ++r) {
             int cid = __shfl_sync(kFull, my_id, r);
-            T* pc = Wc + (size_t)cid * dim;
+            T* pc = tc.row(cid);
             Row<C> v, c;
             v.load(pv, lane, dim);
             c.load(pc, lane, dim);
@@ -123,7 +128,8 @@ __device__ __forceinline__ void update_pair_cpp(typename C::T* Wv, typename C::T
 // source) are skipped; the positive context row is written last.
 // ---------------------------------------------------------------------------------------------------------------
 template <class C>
-__device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T* Wc, int dim, bool same_table,
+__device__ __forceinline__ void update_pair_go(const TableView<typename C::T>& tv,
+                                                const TableView<typename C::T>& tc, int dim, bool same_table,
                                                bool skip_source, const typename C::T* lut, int v1, int my_id,
                                                int nrows, typename C::T alpha, int lane) {
     using T = typename C::T;
@@ -135,8 +141,8 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
     bool live = active && !skipped;
     unsigned peers = __match_any_sync(kFull, live ? my_id : (-1 - lane));
     bool dup = __any_sync(kFull, (live && __popc(peers) > 1) || (live && same_table && my_id == v1));
-    T* pv = Wv + (size_t)v1 * dim;
-    T* pp = Wc + (size_t)ctx * dim;
+    T* pv = tv.row(v1);
+    T* pp = tc.row(ctx);
     if (!dup) {
         Row<C> v, vgrad, pos, cgrad;
         v.load(pv, lane, dim);
@@ -157,7 +163,7 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
             for (int r = 0; r < kCtxChunk; ++r) {
                 ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
                 ok[r] = (base + r < nrows) && !((skipmask >> ((base + r) & 31)) & 1u);
-                if (ok[r]) c[r].load(Wc + (size_t)ids[r] * dim, lane, dim);
+                if (ok[r]) c[r].load(tc.row(ids[r]), lane, dim);
                 else c[r].zero();
             }
             T f[kCtxChunk];
@@ -171,7 +177,7 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
                         vgrad.x[e] = A::madd(vgrad.x[e], g, c[r].x[e]);
                         c[r].x[e] = A::add(c[r].x[e], A::mul(g, v.x[e]));  // wContext[neg] += negGrad
                     }
-                    c[r].store(Wc + (size_t)ids[r] * dim, lane, dim);
+                    c[r].store(tc.row(ids[r]), lane, dim);
                 }
             }
         }
@@ -198,7 +204,7 @@ __device__ __forceinline__ void update_pair_go(typename C::T* Wv, typename C::T*
         for (int r = 1; r < nrows; ++r) {
             if ((skipmask >> r) & 1u) continue;
             int cid = __shfl_sync(kFull, my_id, r);
-            T* pc = Wc + (size_t)cid * dim;
+            T* pc = tc.row(cid);
             Row<C> v, c;
             v.load(pv, lane, dim);
             c.load(pc, lane, dim);
@@ -242,6 +248,22 @@ __device__ __forceinline__ const T* stage_lut(const T* lut_global, T* lut_shared
     for (int i = threadIdx.x; i <= kSigmoidTable; i += blockDim.x) lut_shared[i] = lut_global[i];
     __syncthreads();
     return lut_shared;
+}
+
+// Peer shard bases -> shared memory (static indices only: a dynamically indexed parameter array goes to local memory),
+// and the two table views built on them. Must be called by the whole CTA.
+template <typename T>
+__device__ __forceinline__ void stage_views(const TrainArgs<T>& a, TableView<T>& tv, TableView<T>& tc) {
+    __shared__ T* s_base[2][kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+        if (threadIdx.x == r) {
+            s_base[0][r] = a.peer_v[r];
+            s_base[1][r] = a.peer_c[r];
+        }
+    __syncthreads();
+    tv = TableView<T>{s_base[0], a.world_shift, a.world_mask, a.dim};
+    tc = TableView<T>{s_base[1], a.world_shift, a.world_mask, a.dim};
 }
 
 // Shared memory layout of every training kernel: [kWarpsPerBlock][256] u32 draw rings, then the LUT, then
@@ -312,6 +334,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_walk(TrainArgs<typename C::T>
     int32_t* walks = reinterpret_cast<int32_t*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t) + 1008 * sizeof(T));
     uint8_t* reduces = reinterpret_cast<uint8_t*>(walks + kWarpsPerBlock * kMaxWalkLen);
     const T* lut = stage_lut<T>(a.lut, lut_s);
+    TableView<T> tv, tc;
+    stage_views<T>(a, tv, tc);
     int lane = threadIdx.x & 31;
     int wib = threadIdx.x >> 5;
     int w = blockIdx.x * kWarpsPerBlock + wib;
@@ -351,8 +375,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_walk(TrainArgs<typename C::T>
                     ring.ensure();
                     int my = draw_pair_ids(g, ring, 0u, walk[j], a.K, lane);
                     ring.advance(2u * (uint32_t)a.K);
-                    if (!go) update_pair_cpp<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, lut, vi, my, nrows, alpha, lane);
-                    else update_pair_go<C>(a.Wv, a.Wc, a.dim, a.same_table != 0, false, lut, vi, my, nrows, alpha, lane);
+                    if (!go) update_pair_cpp<C>(tv, tc, a.dim, a.same_table != 0, lut, vi, my, nrows, alpha, lane);
+                    else update_pair_go<C>(tv, tc, a.dim, a.same_table != 0, false, lut, vi, my, nrows, alpha, lane);
                     st.pairs++;
                 }
             }
@@ -439,19 +463,23 @@ __global__ void k_walk_debug(GraphDev g, uint64_t seed, uint64_t stream, int64_t
     }
 }
 
-// Table init: (U - 0.5) / dim, U = k * 2^-32, k = word e of stream (seed, kInitStreamBase + table) for element e.
+// Table init: (U - 0.5) / dim, U = k * 2^-32, k = word e of stream (seed, kInitStreamBase + table) for GLOBAL element e
+// (row-sharded tables: local row l is global row (l << shift) + rank, so the values do not depend on the sharding).
 template <typename T>
-__global__ void k_init_table(T* W, int64_t n_elems, int dim, uint64_t seed, uint64_t stream, int random) {
-    int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one Philox block (4 elements) per thread
+__global__ void k_init_table(T* W, int64_t n_elems, int dim, uint64_t seed, uint64_t stream, int random, int shift, int rank) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; blk * 4 < n_elems; blk += stride) {
-        U4 r = philox_block(seed, stream, (uint64_t)blk);
-        uint32_t k[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int64_t e = blk * 4 + j;
-            if (e < n_elems) W[e] = random ? (T)(((double)k[j] * (1.0 / 4294967296.0) - 0.5) / (double)dim) : (T)0;
+    for (; i < n_elems; i += stride) {
+        if (!random) {
+            W[i] = (T)0;
+            continue;
         }
+        const int64_t l = i / dim, d = i - l * dim;
+        const uint64_t ge = (uint64_t)(((l << shift) + rank) * dim + d);
+        U4 r = philox_block(seed, stream, ge >> 2);
+        const uint32_t lane = (uint32_t)(ge & 3);
+        const uint32_t k = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+        W[i] = (T)(((double)k * (1.0 / 4294967296.0) - 0.5) / (double)dim);
     }
 }
 

@@ -82,6 +82,11 @@ struct smore_graph_s {
     std::vector<int32_t> field;
     bool has_field = false;
     AliasHost vertex_at, negative_at, ctx_at;
+    std::vector<double> out_deg, in_deg;
+    // row sharding (one process per GPU): this rank owns vertices v with (v & (world-1)) == rank
+    int rank = 0, world = 1, shift = 0;
+    int64_t n_local = 0;            // owned vertices
+    double src_mass_frac = 1.0;     // share of the global source-sampling mass owned by this rank
     // device
     int64_t* d_row_off = nullptr;
     int32_t* d_col = nullptr;
@@ -97,6 +102,8 @@ struct smore_graph_s {
         g.row_off = d_row_off; g.col = d_col;
         g.vertex_at = d_vat; g.negative_at = d_nat; g.ctx_at = d_cat;
         g.prefix = d_prefix; g.field = d_field; g.sem = sem;
+        g.n_src = g.n_neg = (uint32_t)n_local;
+        g.shard_shift = shift; g.shard_rank = rank;
         return g;
     }
     ~smore_graph_s() {
@@ -109,6 +116,9 @@ struct smore_model_s {
     smore_graph_t g = nullptr;
     int dim = 0, n_tables = 0, dtype = 0;
     void* tab[2] = {nullptr, nullptr};
+    int64_t rows = 0;                          // rows held locally (V when not sharded)
+    void* peer[2][kMaxWorld] = {};             // shard bases per rank (peer[t][rank] == tab[t])
+    bool peer_opened[2][kMaxWorld] = {};       // CUDA-IPC mappings to close
     WarpState* d_state = nullptr;
     int state_cap = 0;
     int32_t* d_keys = nullptr;
@@ -118,6 +128,9 @@ struct smore_model_s {
     double st_ms = 0;
     size_t elem() const { return dtype == SMORE_F64 ? 8 : 4; }
     ~smore_model_s() {
+        for (int t = 0; t < 2; ++t)
+            for (int r = 0; r < kMaxWorld; ++r)
+                if (peer_opened[t][r]) cudaIpcCloseMemHandle(peer[t][r]);
         cudaFree(tab[0]); cudaFree(tab[1]); cudaFree(d_state); cudaFree(d_keys);
     }
 };
@@ -184,7 +197,11 @@ int build_graph(smore_graph_s* g) {
             return fail(SMORE_E_INVALID, "row_off not monotone / degree too large at %lld", (long long)v);
     if (g->row_off[0] != 0 || g->row_off[(size_t)V] != E) return fail(SMORE_E_INVALID, "row_off[0]/row_off[V] inconsistent with E");
     // degrees in the reference's accumulation order (src/proNet.cpp:423-446; pronet.go:198-212)
-    std::vector<double> out_deg((size_t)V, 0.0), in_deg((size_t)V, 0.0), dist((size_t)V);
+    g->n_local = V;
+    g->out_deg.assign((size_t)V, 0.0);
+    g->in_deg.assign((size_t)V, 0.0);
+    std::vector<double>&out_deg = g->out_deg, &in_deg = g->in_deg;
+    std::vector<double> dist((size_t)V);
     for (int64_t v = 0; v < V; ++v)
         for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) out_deg[(size_t)v] += g->w[(size_t)e];
     for (int64_t e = 0; e < E; ++e) in_deg[(size_t)g->col[(size_t)e]] += g->w[(size_t)e];
@@ -263,8 +280,13 @@ int ensure_state(smore_model_s* m, int warps) {
     return SMORE_OK;
 }
 
-int check_train(smore_model_s* m, const smore_train_params* p, int need_tables) {
+int check_train(smore_model_s* m, const smore_train_params* p, int need_tables, bool shard_ok = false) {
     if (!m || !p) return fail(SMORE_E_INVALID, "null model/params");
+    if (m->g->world > 1 && !shard_ok) return fail(SMORE_E_UNSUPPORTED, "this trainer does not run on a row-sharded graph yet (LINE does)");
+    if (m->g->world > 1)
+        for (int t = 0; t < m->n_tables; ++t)
+            for (int r = 0; r < m->g->world; ++r)
+                if (!m->peer[t][r]) return fail(SMORE_E_INVALID, "table %d: shard of rank %d not connected (smore_model_open_peers)", t, r);
     if (p->semantics != m->g->sem) return fail(SMORE_E_INVALID, "params.semantics (%d) != graph semantics (%d)", p->semantics, m->g->sem);
     if (m->n_tables < need_tables) return fail(SMORE_E_INVALID, "model has %d tables, this trainer needs %d", m->n_tables, need_tables);
     if (p->mode != SMORE_MODE_DETERMINISTIC && p->mode != SMORE_MODE_HOGWILD) return fail(SMORE_E_INVALID, "bad mode");
@@ -315,6 +337,12 @@ TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps,
     a.g = m->g->view();
     a.Wv = (T*)m->tab[vtab];
     a.Wc = (T*)m->tab[ctab];
+    for (int r = 0; r < kMaxWorld; ++r) {
+        a.peer_v[r] = (T*)m->peer[vtab][r];
+        a.peer_c[r] = (T*)m->peer[ctab][r];
+    }
+    a.world_shift = m->g->shift;
+    a.world_mask = m->g->world - 1;
     a.dim = m->dim;
     a.same_table = vtab == ctab;
     a.lut = sizeof(T) == 8 ? (const T*)m->g->d_lut64 : (const T*)m->g->d_lut32;
@@ -358,11 +386,13 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
         else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
+        // row-sharded: this rank draws sources from its own vertices only and runs its share of the global total
+        const uint64_t total_local = m->g->world == 1 ? p->total : (uint64_t)llround((double)p->total * m->g->src_mass_frac);
         // jobs = total / workers (LINE.cpp:124); the C++ loop starts count at 1 and runs while count < jobs
-        const uint64_t jobs = p->total / (uint64_t)L.warps;
+        const uint64_t jobs = total_local / (uint64_t)L.warps;
         const uint64_t trips = cpp ? (jobs > 0 ? jobs - 1 : 0) : jobs;
         if (int rc = init_state(m, L.warps, cpp ? 1 : 0, p->alpha)) return rc;
-        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)p->total, cpp ? 1 : 0, vtab, ctab);
+        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)total_local, cpp ? 1 : 0, vtab, ctab);
         a.jobs = trips;
         Timer t;
         if (int rc = t.start()) return rc;
@@ -470,7 +500,7 @@ namespace {
 template <typename TH>
 int rows_io(smore_model_t m, int table, int64_t first, int64_t n, TH* host, bool to_device) {
     if (!m || table < 0 || table >= m->n_tables || !host) return fail(SMORE_E_INVALID, "bad model/table/buffer");
-    if (first < 0 || n < 0 || first + n > m->g->V) return fail(SMORE_E_INVALID, "row range out of bounds");
+    if (first < 0 || n < 0 || first + n > m->rows) return fail(SMORE_E_INVALID, "row range out of bounds (the model holds %lld rows)", (long long)m->rows);
     if (n == 0) return SMORE_OK;
     if (int rc = ensure_device()) return rc;
     const int64_t cnt = n * (int64_t)m->dim;
@@ -715,16 +745,108 @@ int smore_model_create(smore_graph_t g, int dim, int n_tables, int dtype, smore_
     m->dim = dim;
     m->n_tables = n_tables;
     m->dtype = dtype;
+    m->rows = g->n_local;  // == V unless the graph is row-sharded
     for (int t = 0; t < n_tables; ++t) {
-        size_t bytes = (size_t)g->V * (size_t)dim * m->elem();
+        size_t bytes = (size_t)std::max<int64_t>(m->rows, 1) * (size_t)dim * m->elem();
         cudaError_t e = cudaMalloc(&m->tab[t], bytes);
         if (e != cudaSuccess) {
             delete m;
             return fail(SMORE_E_NOMEM, "cudaMalloc of %zu bytes for table %d failed: %s", bytes, t, cudaGetErrorString(e));
         }
         cudaMemset(m->tab[t], 0, bytes);
+        m->peer[t][g->rank] = m->tab[t];
     }
     *out = m;
+    return SMORE_OK;
+}
+
+// ---- row sharding across the GPUs of one box (one process per GPU) ---------------------------------------------------
+int smore_graph_set_shard(smore_graph_t g, int rank, int world) {
+    if (!g) return fail(SMORE_E_INVALID, "null graph");
+    if (world < 1 || world > kMaxWorld || (world & (world - 1))) return fail(SMORE_E_INVALID, "world must be 1, 2, 4 or 8");
+    if (rank < 0 || rank >= world) return fail(SMORE_E_INVALID, "rank out of range");
+    if (int rc = ensure_device()) return rc;
+    int shift = 0;
+    while ((1 << shift) < world) ++shift;
+    const int64_t V = g->V;
+    const int64_t nl = (V - rank + world - 1) / world;
+    if (nl <= 0) return fail(SMORE_E_INVALID, "rank %d owns no vertex", rank);
+    // shard-local source and negative tables over the owned vertices (local index l <-> vertex l*world + rank), built with
+    // the same alias construction as the global ones; owner-computes: this rank draws sources from its own vertices only
+    std::vector<double> src((size_t)nl), neg((size_t)nl);
+    const double pw = g->sem == SMORE_SEM_CPP ? 0.75 : 1.0;  // C++ applies 0.75 to every table (proNet.cpp:558)
+    double mass_all = 0, mass_own = 0;
+    for (int64_t v = 0; v < V; ++v) {
+        const double x = g->out_deg[(size_t)v] > 0 ? std::pow(g->out_deg[(size_t)v], pw) : 0.0;
+        mass_all += x;
+        if ((v & (world - 1)) == rank) mass_own += x;
+    }
+    for (int64_t l = 0; l < nl; ++l) {
+        const int64_t v = l * world + rank;
+        src[(size_t)l] = g->out_deg[(size_t)v];
+        const double in = g->in_deg[(size_t)v], out = g->out_deg[(size_t)v];
+        if (g->sem == SMORE_SEM_GO || g->neg_method == SMORE_NEG_DEGREES) neg[(size_t)l] = in + out;
+        else if (g->neg_method == SMORE_NEG_IN_DEGREES) neg[(size_t)l] = in;
+        else neg[(size_t)l] = in == 0 ? 0 : 1;
+    }
+    g->vertex_at = g->sem == SMORE_SEM_CPP ? alias_method_cpp(src.data(), nl) : alias_method_go(src.data(), nl, 1.0);
+    g->negative_at = g->sem == SMORE_SEM_CPP ? alias_method_cpp(neg.data(), nl) : alias_method_go(neg.data(), nl, 0.75);
+    std::vector<uint2> packed((size_t)nl);
+    auto upload = [&](const AliasHost& t, uint2** d) -> int {
+        for (int64_t i = 0; i < nl; ++i) {
+            PackedAlias pa = pack_alias(t.prob[(size_t)i], t.alias[(size_t)i], (uint32_t)i);
+            packed[(size_t)i] = make_uint2(pa.thr, pa.alias);
+        }
+        cudaFree(*d);
+        return dev_alloc_copy(d, packed.data(), packed.size());
+    };
+    if (int rc = upload(g->vertex_at, &g->d_vat)) return rc;
+    if (int rc = upload(g->negative_at, &g->d_nat)) return rc;
+    g->rank = rank;
+    g->world = world;
+    g->shift = shift;
+    g->n_local = nl;
+    g->src_mass_frac = mass_all > 0 ? mass_own / mass_all : 1.0 / world;
+    return SMORE_OK;
+}
+
+int smore_graph_shard_info(smore_graph_t g, int* rank, int* world, int64_t* n_local, double* source_mass_fraction) {
+    if (!g) return fail(SMORE_E_INVALID, "null graph");
+    if (rank) *rank = g->rank;
+    if (world) *world = g->world;
+    if (n_local) *n_local = g->n_local;
+    if (source_mass_fraction) *source_mass_fraction = g->src_mass_frac;
+    return SMORE_OK;
+}
+
+int smore_model_ipc_handle(smore_model_t m, int table, void* handle64) {
+    if (!m || table < 0 || table >= m->n_tables || !handle64) return fail(SMORE_E_INVALID, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, m->tab[table]));
+    memcpy(handle64, &h, 64);
+    return SMORE_OK;
+}
+
+int smore_model_open_peers(smore_model_t m, int table, const void* handles) {
+    if (!m || table < 0 || table >= m->n_tables || !handles) return fail(SMORE_E_INVALID, "bad argument");
+    if (int rc = ensure_device()) return rc;
+    for (int r = 0; r < m->g->world; ++r) {
+        if (r == m->g->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * r, 64);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        m->peer[table][r] = p;
+        m->peer_opened[table][r] = true;
+    }
+    return SMORE_OK;
+}
+
+int smore_model_set_peer_ptrs(smore_model_t m, int table, void* const* ptrs) {
+    if (!m || table < 0 || table >= m->n_tables || !ptrs) return fail(SMORE_E_INVALID, "bad argument");
+    for (int r = 0; r < m->g->world; ++r)
+        if (r != m->g->rank) m->peer[table][r] = ptrs[r];
     return SMORE_OK;
 }
 
@@ -733,10 +855,11 @@ void smore_model_destroy(smore_model_t m) { delete m; }
 int smore_model_init(smore_model_t m, int table, int random, uint64_t seed) {
     if (!m || table < 0 || table >= m->n_tables) return fail(SMORE_E_INVALID, "bad model/table");
     if (int rc = ensure_device()) return rc;
-    const int64_t n = m->g->V * (int64_t)m->dim;
-    const int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, 148 * 16);
-    if (m->dtype == SMORE_F64) k_init_table<double><<<blocks, 256>>>((double*)m->tab[table], n, m->dim, seed, kInitStreamBase + (uint64_t)table, random);
-    else k_init_table<float><<<blocks, 256>>>((float*)m->tab[table], n, m->dim, seed, kInitStreamBase + (uint64_t)table, random);
+    const int64_t n = m->rows * (int64_t)m->dim;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256 + 1, 148 * 16);
+    const int sh = m->g->shift, rk = m->g->rank;  // a shard initialises its rows with the words of their GLOBAL position
+    if (m->dtype == SMORE_F64) k_init_table<double><<<blocks, 256>>>((double*)m->tab[table], n, m->dim, seed, kInitStreamBase + (uint64_t)table, random, sh, rk);
+    else k_init_table<float><<<blocks, 256>>>((float*)m->tab[table], n, m->dim, seed, kInitStreamBase + (uint64_t)table, random, sh, rk);
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
@@ -765,6 +888,7 @@ int smore_model_device_ptr(smore_model_t m, int table, void** ptr) {
 
 int smore_model_save_weights(smore_model_t m, int table, const char* path, int format) {
     if (!m || !path || table < 0 || table >= m->n_tables) return fail(SMORE_E_INVALID, "bad argument");
+    if (m->g->world > 1) return fail(SMORE_E_UNSUPPORTED, "save_weights on a row-sharded model: gather the shards with get_rows");
     const int64_t V = m->g->V;
     const int dim = m->dim;
     FILE* f = fopen(path, "wb");
@@ -797,7 +921,7 @@ int smore_model_save_weights(smore_model_t m, int table, const char* path, int f
 
 // ---- training -----------------------------------------------------------------------------------------------------
 int smore_train_line(smore_model_t m, const smore_train_params* p) {
-    if (int rc = check_train(m, p, p && p->order == 1 ? 1 : 2)) return rc;
+    if (int rc = check_train(m, p, p && p->order == 1 ? 1 : 2, true)) return rc;
     if (p->negative_samples < 0 || p->negative_samples > 31) return fail(SMORE_E_UNSUPPORTED, "negative_samples must be in [0,31]");
     if (p->order != 1 && p->order != 2) return fail(SMORE_E_INVALID, "order must be 1 or 2");
     return m->dtype == SMORE_F64 ? train_line_t<double>(m, p) : train_line_t<float>(m, p);
