@@ -160,6 +160,9 @@ typedef struct {
     int walk_times, walk_steps, window_min, window_max; /* DeepWalk: window_max = -window_size; Walklets: both */
     int max_warps;        /* HOGWILD: cap on concurrent warps (0 = fill the device) */
     int64_t max_walks;    /* DeepWalk/Walklets: stop after this many walks (<0: all walk_times*V) */
+    /* Chunked training: this call is one piece of a longer LR schedule of sched_total units (same unit as `total`;
+     * walk models: walks), sched_offset of which are already done. 0/0: the call is the whole schedule. */
+    uint64_t sched_total, sched_offset;
 } smore_train_params;
 
 /* Fills `p` with the reference CLI defaults (cmd/line/main.go:13-21, cli/line.cpp:56-64). */

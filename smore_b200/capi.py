@@ -45,7 +45,7 @@ class TrainParams(C.Structure):
         ("semantics", C.c_int), ("mode", C.c_int), ("seed", u64), ("stream_base", u64), ("alpha", f64),
         ("total", u64), ("negative_samples", C.c_int), ("order", C.c_int), ("lambda_", f64),
         ("walk_times", C.c_int), ("walk_steps", C.c_int), ("window_min", C.c_int), ("window_max", C.c_int),
-        ("max_warps", C.c_int), ("max_walks", i64),
+        ("max_warps", C.c_int), ("max_walks", i64), ("sched_total", u64), ("sched_offset", u64),
     ]
 
 

@@ -340,6 +340,7 @@ struct Sched {
     double total;  // as the reference converts it: (double)total
     uint64_t W;
     int lag;
+    double offset;  // samples of the (possibly longer) schedule already done before this call; 0 for a whole run
 };
 
 struct WarpState {
@@ -354,7 +355,7 @@ struct WarpState {
 __device__ __forceinline__ void sched_tick(WarpState& st, const Sched& s) {
     if (st.count >= st.next_tick) {
         uint64_t t = (st.count * s.W) / kMonitor;
-        double a = s.alpha0 * (1.0 - (double)((t - (uint64_t)s.lag) * kMonitor) / s.total);
+        double a = s.alpha0 * (1.0 - (s.offset + (double)((t - (uint64_t)s.lag) * kMonitor)) / s.total);
         double amin = s.alpha0 * 0.0001;
         st.alpha = a < amin ? amin : a;
         st.next_tick = ((t + 1) * kMonitor + s.W - 1) / s.W;

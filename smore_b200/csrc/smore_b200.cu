@@ -332,7 +332,8 @@ int collect_stats(smore_model_s* m, int warps) {
 }
 
 template <typename T>
-TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps, double total, int lag, int vtab, int ctab) {
+TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps, double total, int lag, int vtab, int ctab,
+                       double scale = 1.0 /* row-sharded: this rank's share of the schedule units */) {
     TrainArgs<T> a{};
     a.g = m->g->view();
     a.Wv = (T*)m->tab[vtab];
@@ -348,7 +349,9 @@ TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps,
     a.lut = sizeof(T) == 8 ? (const T*)m->g->d_lut64 : (const T*)m->g->d_lut32;
     a.seed = p->seed;
     a.stream_base = p->stream_base;
-    a.sched = Sched{p->alpha, total, (uint64_t)warps, lag};
+    // a call may be one chunk of a longer LR schedule (sched_total / sched_offset, in the same units as `total`)
+    const double sched_total = p->sched_total ? (double)p->sched_total * scale : total;
+    a.sched = Sched{p->alpha, sched_total, (uint64_t)warps, lag, (double)p->sched_offset * scale};
     a.state = m->d_state;
     a.n_warps = warps;
     a.K = p->negative_samples;
@@ -357,7 +360,11 @@ TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps,
     return a;
 }
 
-int init_state(smore_model_s* m, int warps, uint64_t count0, double alpha) {
+int init_state(smore_model_s* m, int warps, uint64_t count0, double alpha, const smore_train_params* p = nullptr) {
+    if (p && p->sched_total && p->sched_offset) {  // resume a longer schedule: alpha_t = alpha * max(1e-4, 1 - done/total)
+        const double a = alpha * (1.0 - (double)p->sched_offset / (double)p->sched_total);
+        alpha = a < alpha * 0.0001 ? alpha * 0.0001 : a;
+    }
     std::vector<WarpState> st((size_t)warps);
     for (int w = 0; w < warps; ++w) {
         st[(size_t)w] = WarpState{0, count0, ((uint64_t)kMonitor + (uint64_t)warps - 1) / (uint64_t)warps, alpha, 0, 0};
@@ -391,8 +398,9 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
         // jobs = total / workers (LINE.cpp:124); the C++ loop starts count at 1 and runs while count < jobs
         const uint64_t jobs = total_local / (uint64_t)L.warps;
         const uint64_t trips = cpp ? (jobs > 0 ? jobs - 1 : 0) : jobs;
-        if (int rc = init_state(m, L.warps, cpp ? 1 : 0, p->alpha)) return rc;
-        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)total_local, cpp ? 1 : 0, vtab, ctab);
+        if (int rc = init_state(m, L.warps, cpp ? 1 : 0, p->alpha, p)) return rc;
+        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)total_local, cpp ? 1 : 0, vtab, ctab,
+                                      m->g->world == 1 ? 1.0 : m->g->src_mass_frac);
         a.jobs = trips;
         Timer t;
         if (int rc = t.start()) return rc;
@@ -418,7 +426,7 @@ int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets) {
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
         else if (int rc = pick_grid(kern, smem, p->max_warps, (uint64_t)V, L)) return rc;
         const double total = (double)((unsigned long long)p->walk_times * (unsigned long long)V);
-        if (int rc = init_state(m, L.warps, 0, p->alpha)) return rc;
+        if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
         TrainArgs<T> a = base_args<T>(m, p, L.warps, total, 0, 0, 1);
         a.steps = p->walk_steps;
         a.w0 = p->window_min;
@@ -478,7 +486,7 @@ int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind) {
         else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
         // BPR.cpp:73-85 / WARP.cpp / HBPR.cpp: jobs = total / workers, count from 0; bpr.go: sample_times*MaxLine trips
         const uint64_t trips = p->total / (uint64_t)L.warps;
-        if (int rc = init_state(m, L.warps, 0, p->alpha)) return rc;
+        if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
         const int ctab = (kind == RANK_BPR && !cpp) ? 1 : 0;  // the C++ ranking models pass one table for both roles
         TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)p->total, cpp ? 1 : 0, 0, ctab);
         a.jobs = trips;

@@ -108,8 +108,7 @@ def test_sharded_training_quality_matches_unsharded():
         for r, mr in enumerate(ms):
             p = _params(total // rounds, 100 + k)
             p.stream_base = r * (1 << 20)
-            # LR decays over the whole run: emulate by scaling alpha per round (each call restarts its own schedule)
-            p.alpha = 0.025 * max(1e-4, 1.0 - k / rounds)
+            p.sched_total, p.sched_offset = total, k * (total // rounds)  # one LR schedule over all the rounds
             done += mr.train_line(p)["samples"]
     assert 0.9 * total <= done <= total
     Wv, Wc = np.zeros((V, dim)), np.zeros((V, dim))
