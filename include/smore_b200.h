@@ -124,13 +124,16 @@ void smore_model_destroy(smore_model_t m);
 /* ---- row sharding across the GPUs of one NVSwitch box: one process per GPU. New with this backend --
  * the reference is single-process shared memory (src/model/LINE.cpp:162 OpenMP workers on one table).
  *
- * Vertex v is owned by rank v & (world-1) (world in {1,2,4,8}); its local row is v >> log2(world). After
- * smore_graph_set_shard the graph's source and negative alias tables cover the OWNED vertices only (owner-computes: a rank
- * draws sources from its own vertices and its negatives from its own shard), the CSR stays replicated, and
- * smore_model_create allocates only the owned rows. The positive context row of a sample may live on any rank: kernels
- * reach it with plain 128-bit loads/stores through CUDA-IPC peer mappings (NVLink). smore_train_line then runs
- * round(total * source_mass_fraction) samples on this rank, so the union over ranks reproduces the global source
- * distribution. set_rows / get_rows / init address LOCAL rows. */
+ * Vertex v is owned by rank v & (world-1) (world in {1,2,4,8}); its local row is v >> log2(world). The rank that owns
+ * the POSITIVE CONTEXT of a sample computes it: after smore_graph_set_shard the rank holds an alias table over the CSR
+ * entries whose target it owns, weighted by P(source) * P(target | source) of the unsharded samplers, so the union over
+ * ranks -- rank r running round(total * mass_r) samples, mass_r reported as source_mass_fraction -- reproduces the
+ * global edge distribution exactly; negatives are drawn from the owned vertices only (stratified by the shard of the
+ * positive, the PyTorch-BigGraph scheme). Context rows are therefore always local; the vertex row of a sample may
+ * live on any rank and is reached with plain 128-bit loads/stores through CUDA-IPC peer mappings (NVLink). The CSR
+ * stays replicated; smore_model_create allocates only the owned rows; set_rows / get_rows / init address LOCAL rows.
+ * (Drawing negatives from the SOURCE's shard instead collapses the embedding: a vertex then never meets a negative
+ * from another shard -- measured AUC 0.52 vs 0.92.) */
 int smore_graph_set_shard(smore_graph_t g, int rank, int world);
 int smore_graph_shard_info(smore_graph_t g, int* rank, int* world, int64_t* n_local, double* source_mass_fraction);
 /* 64-byte cudaIpcMemHandle_t of this rank's shard of `table` (exchange with the host's own transport, e.g.

@@ -22,7 +22,8 @@
 
 namespace smore {
 
-__host__ __device__ inline int batch_wps(int go, int K) { return (go ? 3 : 4) + 2 * K; }
+// sharded: one edge draw (idx, p) replaces the source + target draws
+__host__ __device__ inline int batch_wps(int go, int K) { return (go == 2 ? 2 : go ? 3 : 4) + 2 * K; }
 __host__ __device__ inline int batch_wbuf_words(int go, int K) { return ((32 * batch_wps(go, K) + 8 + 3) / 4) * 4; }
 template <typename T>
 inline size_t batch_smem_bytes(int go, int K) {
@@ -69,7 +70,8 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
         const uint32_t* wd = b.wbuf + ((uint32_t)st.pos & 3u) + lane * b.wps;
         int* my_ids = b.ids + lane * b.idw;
         const uint32_t V32 = g.n_neg;
-        constexpr int noff = GO ? 3 : 4;
+        const bool sharded = g.edge_at != nullptr;
+        const int noff = sharded ? 2 : GO ? 3 : 4;
         // negatives first: independent lookups, issued 8 at a time
         for (int n0 = 0; n0 < b.K; n0 += 8) {
             uint32_t idx[8];
@@ -84,12 +86,19 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
             for (int j = 0; j < 8; ++j)
                 if (n0 + j < b.K) my_ids[2 + n0 + j] = (int)g.global_id(wd[noff + 2 * (n0 + j) + 1] < e[j].x ? idx[j] : e[j].y);
         }
-        // then the dependent source -> target chain
-        const int v1 = (int)source_sample(g, wd[0], wd[1]);
-        int u;
-        const int v2 = (int)target_sample(g, v1, wd[2], GO ? 0u : wd[3], u);
-        my_ids[0] = v1;
-        my_ids[1] = v2;
+        if (!sharded) {
+            // then the dependent source -> target chain
+            const int v1 = (int)source_sample(g, wd[0], wd[1]);
+            int u;
+            const int v2 = (int)target_sample(g, v1, wd[2], GO ? 0u : wd[3], u);
+            my_ids[0] = v1;
+            my_ids[1] = v2;
+        } else {
+            // one draw over this rank's edge table: (idx, p) -> local edge -> (source anywhere, target owned here)
+            const uint32_t le = alias_pick(g.edge_at, index_draw(wd[0], g.n_edge_local), wd[1]);
+            my_ids[0] = __ldg(g.edge_src + le);
+            my_ids[1] = __ldg(g.edge_dst + le);
+        }
     }
     st.pos += (uint64_t)(nb * b.wps);
     __syncwarp();
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
     const int wib = threadIdx.x >> 5;
     const int w = blockIdx.x * kWarpsPerBlock + wib;
     if (w >= a.n_warps) return;
-    const Batch b = batch_init<T>(GO, a.K, wib);
+    const Batch b = batch_init<T>(a.g.edge_at ? 2 : (GO ? 1 : 0), a.K, wib);
     WarpState st = a.state[w];
     const uint64_t stream = a.stream_base + (uint64_t)w;
     const int nrows = a.K + 1;

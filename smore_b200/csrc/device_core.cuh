@@ -32,9 +32,16 @@ struct GraphDev {
     const int32_t* field;      // V   (HOP-Rec)
     int sem;                   // SMORE_SEM_*
     // Row sharding (multi-GPU, one process per GPU): vertex v is owned by rank v & (world-1), its local row is
-    // v >> shard_shift. vertex_at / negative_at then cover the OWNED vertices only (n_src = n_neg = owned count, entries
-    // are local indices); world == 1: n_src = n_neg = V, shard_shift = shard_rank = 0 and ids are global already.
-    uint32_t n_src, n_neg;
+    // v >> shard_shift. The rank that owns the POSITIVE CONTEXT of a sample computes it: edge_at is an alias table over
+    // the CSR entries whose target this rank owns (probability = P(source) * P(target | source) of the unsharded
+    // samplers, so the union over ranks is the global edge distribution), edge_src / edge_dst give the endpoints, and
+    // negative_at covers the owned vertices only (n_neg entries, local indices): negatives come from the same shard as
+    // the positive. world == 1: edge_at == nullptr, n_neg = V, shard_shift = shard_rank = 0.
+    const uint2* edge_at;
+    const int32_t* edge_src;
+    const int32_t* edge_dst;
+    uint32_t n_edge_local;
+    uint32_t n_neg;
     int shard_shift, shard_rank;
     __device__ __forceinline__ uint32_t global_id(uint32_t local) const { return (local << shard_shift) + (uint32_t)shard_rank; }
 };
@@ -99,7 +106,7 @@ __device__ __forceinline__ uint32_t alias_pick(const uint2* __restrict__ at, uin
 __device__ __forceinline__ uint32_t source_sample(const GraphDev& g, uint32_t w0, uint32_t w1) {
     uint32_t kp = g.sem == 0 ? w0 : w1;
     uint32_t ki = g.sem == 0 ? w1 : w0;
-    return g.global_id(alias_pick(g.vertex_at, index_draw(ki, g.n_src), kp));
+    return alias_pick(g.vertex_at, index_draw(ki, (uint32_t)g.V), kp);
 }
 
 // NegativeSample: index then p in both trees (src/proNet.cpp:625-626; alias.go:99-100). 2 words.

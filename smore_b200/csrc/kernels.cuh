@@ -407,7 +407,12 @@ __global__ void k_sample_debug(GraphDev g, int which, uint64_t seed, uint64_t st
             if (which == 0) { r0 = source_sample(g, ring.peek(0), ring.peek(1)); used = 2; }
             else if (which == 1) { r0 = negative_sample(g, ring.peek(0), ring.peek(1)); used = 2; }
             else if (which == 2) { int u; r0 = target_sample(g, arg[i], ring.peek(0), ring.peek(1), u); used = u; }
-            else {
+            else if (g.edge_at) {  // row-sharded graph: one draw over this rank's edge table
+                uint32_t le = alias_pick(g.edge_at, index_draw(ring.peek(0), g.n_edge_local), ring.peek(1));
+                r0 = __ldg(g.edge_src + le);
+                r1 = __ldg(g.edge_dst + le);
+                used = 2;
+            } else {
                 r0 = source_sample(g, ring.peek(0), ring.peek(1));
                 int u;
                 r1 = target_sample(g, r0, ring.peek(2), ring.peek(3), u);

@@ -90,7 +90,9 @@ struct smore_graph_s {
     // device
     int64_t* d_row_off = nullptr;
     int32_t* d_col = nullptr;
-    uint2 *d_vat = nullptr, *d_nat = nullptr, *d_cat = nullptr;
+    uint2 *d_vat = nullptr, *d_nat = nullptr, *d_cat = nullptr, *d_eat = nullptr;
+    int32_t *d_esrc = nullptr, *d_edst = nullptr;
+    int64_t n_edge_local = 0;
     double* d_prefix = nullptr;
     int32_t* d_field = nullptr;
     double* d_lut64 = nullptr;
@@ -102,13 +104,15 @@ struct smore_graph_s {
         g.row_off = d_row_off; g.col = d_col;
         g.vertex_at = d_vat; g.negative_at = d_nat; g.ctx_at = d_cat;
         g.prefix = d_prefix; g.field = d_field; g.sem = sem;
-        g.n_src = g.n_neg = (uint32_t)n_local;
+        g.n_neg = (uint32_t)n_local;
+        g.edge_at = d_eat; g.edge_src = d_esrc; g.edge_dst = d_edst; g.n_edge_local = (uint32_t)n_edge_local;
         g.shard_shift = shift; g.shard_rank = rank;
         return g;
     }
     ~smore_graph_s() {
         cudaFree(d_row_off); cudaFree(d_col); cudaFree(d_vat); cudaFree(d_nat); cudaFree(d_cat);
         cudaFree(d_prefix); cudaFree(d_field); cudaFree(d_lut64); cudaFree(d_lut32);
+        cudaFree(d_eat); cudaFree(d_esrc); cudaFree(d_edst);
     }
 };
 
@@ -388,7 +392,7 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
         using C = decltype(cfg);
         const bool cpp = p->semantics == SMORE_SEM_CPP;
         void (*kern)(TrainArgs<T>) = cpp ? k_line<C, false> : k_line<C, true>;
-        const size_t smem = batch_smem_bytes<T>(cpp ? 0 : 1, p->negative_samples);
+        const size_t smem = batch_smem_bytes<T>(m->g->world > 1 ? 2 : cpp ? 0 : 1, p->negative_samples);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
@@ -779,37 +783,68 @@ int smore_graph_set_shard(smore_graph_t g, int rank, int world) {
     const int64_t V = g->V;
     const int64_t nl = (V - rank + world - 1) / world;
     if (nl <= 0) return fail(SMORE_E_INVALID, "rank %d owns no vertex", rank);
-    // shard-local source and negative tables over the owned vertices (local index l <-> vertex l*world + rank), built with
-    // the same alias construction as the global ones; owner-computes: this rank draws sources from its own vertices only
-    std::vector<double> src((size_t)nl), neg((size_t)nl);
-    const double pw = g->sem == SMORE_SEM_CPP ? 0.75 : 1.0;  // C++ applies 0.75 to every table (proNet.cpp:558)
+    if (world == 1) return SMORE_OK;  // nothing to shard: the reference's own samplers stay in place
+    // The rank that owns the positive context computes the sample. Edge table: every CSR entry (v1 -> v2) with v2 owned
+    // here, weighted by the probability the unsharded samplers give it: P(source = v1) * P(target = v2 | v1)
+    //   C++: out_deg(v1)^0.75 / sum  *  w_e^0.75 / sum_{e' of v1} w_e'^0.75   (AliasMethod applies 0.75 to every table)
+    //   Go : out_deg(v1) / sum       *  w_e / out_deg(v1)
+    // so the union of the ranks' samples, rank r running total * mass_r of them, is the global edge distribution.
+    // Negative table: the owned vertices only (local index l <-> vertex l*world + rank), same construction as the global
+    // one: negatives are stratified by the shard of the positive.
+    const double pw = g->sem == SMORE_SEM_CPP ? 0.75 : 1.0;
+    std::vector<double> psrc((size_t)V), nrm((size_t)V, 0.0);
+    double src_sum = 0;
+    for (int64_t v = 0; v < V; ++v) {
+        psrc[(size_t)v] = g->out_deg[(size_t)v] > 0 ? std::pow(g->out_deg[(size_t)v], pw) : 0.0;
+        src_sum += psrc[(size_t)v];
+        for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) nrm[(size_t)v] += std::pow(g->w[(size_t)e], pw);
+    }
+    std::vector<double> pe;
+    std::vector<int32_t> esrc, edst;
     double mass_all = 0, mass_own = 0;
     for (int64_t v = 0; v < V; ++v) {
-        const double x = g->out_deg[(size_t)v] > 0 ? std::pow(g->out_deg[(size_t)v], pw) : 0.0;
-        mass_all += x;
-        if ((v & (world - 1)) == rank) mass_own += x;
+        if (nrm[(size_t)v] <= 0 || src_sum <= 0) continue;
+        const double pv = psrc[(size_t)v] / src_sum / nrm[(size_t)v];
+        for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) {
+            const double pr = pv * std::pow(g->w[(size_t)e], pw);
+            mass_all += pr;
+            if ((g->col[(size_t)e] & (world - 1)) == rank) {
+                mass_own += pr;
+                pe.push_back(pr);
+                esrc.push_back((int32_t)v);
+                edst.push_back(g->col[(size_t)e]);
+            }
+        }
     }
+    const int64_t ne = (int64_t)pe.size();
+    if (ne == 0) return fail(SMORE_E_INVALID, "rank %d owns no edge target", rank);
+    std::vector<double> neg((size_t)nl);
     for (int64_t l = 0; l < nl; ++l) {
         const int64_t v = l * world + rank;
-        src[(size_t)l] = g->out_deg[(size_t)v];
         const double in = g->in_deg[(size_t)v], out = g->out_deg[(size_t)v];
         if (g->sem == SMORE_SEM_GO || g->neg_method == SMORE_NEG_DEGREES) neg[(size_t)l] = in + out;
         else if (g->neg_method == SMORE_NEG_IN_DEGREES) neg[(size_t)l] = in;
         else neg[(size_t)l] = in == 0 ? 0 : 1;
     }
-    g->vertex_at = g->sem == SMORE_SEM_CPP ? alias_method_cpp(src.data(), nl) : alias_method_go(src.data(), nl, 1.0);
+    AliasHost edge_at = alias_method_go(pe.data(), ne, 1.0);  // plain Vose on the edge probabilities
     g->negative_at = g->sem == SMORE_SEM_CPP ? alias_method_cpp(neg.data(), nl) : alias_method_go(neg.data(), nl, 0.75);
-    std::vector<uint2> packed((size_t)nl);
+    std::vector<uint2> packed;
     auto upload = [&](const AliasHost& t, uint2** d) -> int {
-        for (int64_t i = 0; i < nl; ++i) {
-            PackedAlias pa = pack_alias(t.prob[(size_t)i], t.alias[(size_t)i], (uint32_t)i);
-            packed[(size_t)i] = make_uint2(pa.thr, pa.alias);
+        packed.resize(t.prob.size());
+        for (size_t i = 0; i < t.prob.size(); ++i) {
+            PackedAlias pa = pack_alias(t.prob[i], t.alias[i], (uint32_t)i);
+            packed[i] = make_uint2(pa.thr, pa.alias);
         }
         cudaFree(*d);
         return dev_alloc_copy(d, packed.data(), packed.size());
     };
-    if (int rc = upload(g->vertex_at, &g->d_vat)) return rc;
+    if (int rc = upload(edge_at, &g->d_eat)) return rc;
     if (int rc = upload(g->negative_at, &g->d_nat)) return rc;
+    cudaFree(g->d_esrc);
+    cudaFree(g->d_edst);
+    if (int rc = dev_alloc_copy(&g->d_esrc, esrc.data(), esrc.size())) return rc;
+    if (int rc = dev_alloc_copy(&g->d_edst, edst.data(), edst.size())) return rc;
+    g->n_edge_local = ne;
     g->rank = rank;
     g->world = world;
     g->shift = shift;

@@ -42,7 +42,7 @@ def test_sharded_init_and_mass_fractions():
     full = capi.Model(g0, 8, 1, capi.F64)
     full.init(0, True, SEED)
     W = full.get_rows(0)
-    world, fr = 4, []
+    world, fr, pairs = 4, [], []
     for r in range(world):
         g = capi.Graph.from_csr(off, col, ww)
         info = g.set_shard(r, world)
@@ -52,11 +52,21 @@ def test_sharded_init_and_mass_fractions():
         m = capi.Model(g, 8, 1, capi.F64)
         m.init(0, True, SEED)
         assert np.array_equal(m.get_rows(0), W[rows])  # init does not depend on the sharding
-        # shard-local samplers only ever return owned vertices
-        s, _ = g.sample(capi.SAMPLE_SOURCE, SEED, r, 5000)
+        # the rank samples edges whose TARGET it owns, and negatives among its own vertices
+        st, _ = g.sample(capi.SAMPLE_SOURCE_TARGET, SEED, r, 20000)
         n, _ = g.sample(capi.SAMPLE_NEGATIVE, SEED, r, 5000)
-        assert (s % world == r).all() and (n % world == r).all()
+        assert (st[1::2] % world == r).all() and (n % world == r).all()
+        pairs.append(st.reshape(-1, 2))
     assert abs(sum(fr) - 1.0) < 1e-12
+    # union of the ranks' edge samples (weighted by their mass) ~ the unsharded source->target distribution:
+    # compare per-source-vertex frequencies on the hottest sources
+    ref, _ = g0.sample(capi.SAMPLE_SOURCE_TARGET, SEED, 99, 80000)
+    ref_cnt = np.bincount(ref[0::2], minlength=g0.V) / 80000
+    mix = np.zeros(g0.V)
+    for f, pr in zip(fr, pairs):
+        mix += f * np.bincount(pr[:, 0], minlength=g0.V) / len(pr)
+    hot = np.argsort(-ref_cnt)[:20]
+    assert np.allclose(mix[hot], ref_cnt[hot], rtol=0.15, atol=2e-3)
 
 
 def _sbm():
