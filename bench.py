@@ -195,10 +195,21 @@ def run_ours(args):
     off, col, ww = csr
     t0 = time.time()
     g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP)
+    sharded = world > 1 and args.parallelism == "sharded"
+    if sharded:
+        # row-sharded store: this rank owns vertices v % world == rank, computes the samples whose positive
+        # context it owns, and reaches remote vertex rows over NVLink peer mappings. No data-path collective.
+        info = g.set_shard(rank, world)
+        log(f"[bench] rank {rank}: shard {info}")
     log(f"[bench] rank {rank}: alias tables built + uploaded in {time.time() - t0:.1f}s")
     m = capi.Model(g, DIM, 2, capi.F32)
     m.init(0, True, seed=1)
     m.init(1, False, seed=1)
+    if sharded:
+        from smore_b200 import dist as sdist
+
+        sdist.connect_peers(m)
+        dist.barrier()
 
     def barrier():
         torch.cuda.synchronize()
@@ -208,13 +219,16 @@ def run_ours(args):
 
     p = capi.default_params()
     p.semantics, p.mode, p.seed, p.alpha = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 0.025
-    p.negative_samples, p.order, p.total = K, 2, args.batch
+    # sharded: `total` is the GLOBAL update count of the step; each rank runs its mass share (~ batch per GPU)
+    p.negative_samples, p.order, p.total = K, 2, args.batch * (world if sharded else 1)
     step_no = [0]
 
     def step():
         # fresh Philox sub-streams every step (stream ids never repeat across steps / ranks)
         p.stream_base = (step_no[0] * world + rank) * (1 << 20)
         step_no[0] += 1
+        if sharded:
+            dist.barrier()  # ranks enter the step together (control plane only)
         return m.train_line(p)
 
     # ---- value: inputs resident in HBM ----
@@ -239,7 +253,7 @@ def run_ours(args):
     launches = capi.kernel_launches() - launches0
 
     # ---- e2e: host buffers in, host buffers out, every step ----
-    V = g.V
+    V = m.rows  # local rows (== g.V unless sharded)
     hv = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
     hc = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
     m.get_rows(0, out=hv.numpy())
@@ -298,7 +312,10 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(g.V, g.E), "updates_per_step_per_gpu": args.batch,
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (weak scaling)",
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"tables row-sharded over {world} GPUs, context-owner computes, remote vertex rows over NVLink "
+                       f"peer mappings (CUDA IPC), no data-path collective" if sharded
+                       else f"{world} independent replicas (weak scaling)"),
                    "l2": "working set (1.0 GB tables + 0.5 GB graph) exceeds the 126 MB L2; no flush between steps"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "k_line<float,4,1>", "algorithmic_bytes_per_update": ALGO_BYTES,
@@ -327,6 +344,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 24, help="edge updates per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="sharded", choices=["sharded", "replicas"], help="N>1 only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -138,7 +138,7 @@ def _ipc_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     off, col, ww, test_s, test_d, train_adj = _sbm()
-    V, dim, total = len(off) - 1, 32, 6_000_000
+    V, dim, total = len(off) - 1, 32, 14_000_000  # LINE-2 from zero contexts needs > 6M updates to take off here
     capi.check(capi.lib().smore_init(0))  # both ranks share device 0: IPC mappings work within one device too
     g = capi.Graph.from_csr(off, col, ww)
     g.set_shard(rank, world)
