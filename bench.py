@@ -41,7 +41,7 @@ def log(*a):
 
 
 def workload_name(V, E):
-    return (f"LINE-2 dim={DIM} K={K} Hogwild fp32, synthetic power-law graph V={V} E_lines={N_EDGES} "
+    return (f"LINE-2 dim={DIM} K={K} Hogwild fp32, synthetic power-law graph V={V} E_lines={E // 2} "
             f"(undirected, {E} CSR entries) [BASELINE configs[1]]")
 
 
@@ -112,44 +112,56 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline(edges, csr, seconds_target=12.0, cores=None):
+class CpuReference:
     """Reference CPU path on this box's host cores: the compiled reference (kind "reference": unmodified sources, its own
-    flags -Ofast -fopenmp and its own RNG) when oracle/_ref travelled here, else the oracle restatement (kind "port")."""
-    from oracle import bindings as B
+    flags -Ofast -fopenmp and its own RNG) when oracle/_ref travelled here, else the oracle restatement (kind "port").
+    The graph is ingested once; timed() then runs bounded samples of LINE::Train."""
 
-    cores = cores or os.cpu_count() or 1
-    if B.ref_available(fast=True):
-        src, dst, w = edges
-        tmp = tempfile.NamedTemporaryFile(suffix=".txt", delete=False)
-        tmp.close()
-        t0 = time.time()
-        B.write_edge_list_fast(tmp.name, src, dst, w)
-        ref = B.Ref(B.K_LINE, tmp.name, True, DIM, order=2, fast=True)
-        os.unlink(tmp.name)
-        log(f"[bench] reference loaded the graph in {time.time() - t0:.1f}s (V={ref.V})")
-        # LINE::Train granularity is sample_times x 1e6 updates; calibrate on 1M, then one bounded run
-        t0 = time.time()
-        ref.train(1, K, alpha=0.025, workers=cores)
-        t1 = time.time() - t0
-        s = int(max(1, min(64, seconds_target / max(t1, 1e-3))))
-        t0 = time.time()
-        ref.train(s, K, alpha=0.025, workers=cores)
-        dt = time.time() - t0
+    def __init__(self, edges, csr, cores=None):
+        from oracle import bindings as B
+
+        self.B = B
+        self.cores = cores or os.cpu_count() or 1
+        self.kind = "reference" if B.ref_available(fast=True) else "port"
+        if self.kind == "reference":
+            src, dst, w = edges
+            tmp = tempfile.NamedTemporaryFile(suffix=".txt", delete=False)
+            tmp.close()
+            t0 = time.time()
+            B.write_edge_list_fast(tmp.name, src, dst, w)
+            self.ref = B.Ref(B.K_LINE, tmp.name, True, DIM, order=2, fast=True)
+            os.unlink(tmp.name)
+            log(f"[bench] reference ingested the graph in {time.time() - t0:.1f}s (V={self.ref.V})")
+            t0 = time.time()
+            self.ref.train(1, K, alpha=0.025, workers=self.cores)  # LINE::Train granularity: sample_times x 1e6 updates
+            self.sec_per_million = time.time() - t0
+        else:
+            off, col, ww = csr
+            self.g = B.OracleGraph(B.SEM_CPP, off, col, ww)
+            rng = np.random.RandomState(0)
+            self.Wv = (rng.random_sample((self.g.V, DIM)) - 0.5) / DIM
+            self.Wc = np.zeros((self.g.V, DIM))
+            t = self.g.time_line_cpp(self.Wv, self.Wc, K, 0.025, 1_000_000, 1, self.cores)
+            self.sec_per_million = t
+
+    def timed(self, seconds_target):
+        s = int(max(1, min(256, seconds_target / max(self.sec_per_million, 1e-3))))
         updates = s * 1_000_000
-        return {"value": updates / dt, "unit": "updates/s", "cores": cores, "kind": "reference",
-                "sample": f"LINE::Train(sample_times={s}) = {updates} updates on the same graph, {cores} OpenMP threads, "
-                          f"{dt:.1f}s (compiled from the unmodified reference sources with its own flags)"}
-    off, col, ww = csr
-    g = B.OracleGraph(B.SEM_CPP, off, col, ww)
-    rng = np.random.RandomState(0)
-    Wv = (rng.random_sample((g.V, DIM)) - 0.5) / DIM
-    Wc = np.zeros((g.V, DIM))
-    n = 200_000 * cores
-    t = g.time_line_cpp(Wv, Wc, K, 0.025, n, 1, cores)
-    n = int(n * max(1.0, seconds_target / max(t, 1e-3)))
-    t = g.time_line_cpp(Wv, Wc, K, 0.025, n, 1, cores)
-    return {"value": n / t, "unit": "updates/s", "cores": cores, "kind": "port",
-            "sample": f"{n} updates of the oracle restatement (oracle/smore_oracle.cpp, -O2 -fopenmp), {cores} threads, {t:.1f}s"}
+        if self.kind == "reference":
+            t0 = time.time()
+            self.ref.train(s, K, alpha=0.025, workers=self.cores)
+            dt = time.time() - t0
+            what = (f"LINE::Train(sample_times={s}) = {updates} updates on the same graph, {self.cores} OpenMP threads, "
+                    f"{dt:.1f}s (compiled from the unmodified reference sources with its own flags -Ofast -fopenmp)")
+        else:
+            dt = self.g.time_line_cpp(self.Wv, self.Wc, K, 0.025, updates, 1, self.cores)
+            what = (f"{updates} updates of the oracle restatement (oracle/smore_oracle.cpp, -O2 -fopenmp), "
+                    f"{self.cores} threads, {dt:.1f}s")
+        return {"value": updates / dt, "unit": "updates/s", "cores": self.cores, "kind": self.kind, "sample": what}
+
+
+def cpu_baseline(edges, csr, seconds_target=12.0):
+    return CpuReference(edges, csr).timed(seconds_target)
 
 
 def run_reference(args):
@@ -157,19 +169,23 @@ def run_reference(args):
     if rank != 0:
         return
     edges, csr = make_graph(args.scale)
-    per_step = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    vals = []
+    cpu = CpuReference(edges, csr)
+    per_step = max(3.0, min(15.0, 100.0 / max(1, args.steps + args.warmup)))
+    vals, secs = [], []
     base = None
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(edges, csr, seconds_target=per_step)
+        t0 = time.time()
+        base = cpu.timed(per_step)
         if i >= args.warmup:
             vals.append(base["value"])
+            secs.append(time.time() - t0)
     v = float(np.mean(vals)) if vals else base["value"]
     base["value"] = v
     V, E = len(csr[0]) - 1, len(csr[1])
     print(json.dumps({
         "impl": "reference", "metric": "edge_updates_per_sec", "value": v, "unit": "updates/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)) if secs else None,
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(V, E)},
         "cpu_baseline": base, "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
