@@ -25,9 +25,12 @@ namespace smore {
 // sharded: one edge draw (idx, p) replaces the source + target draws
 __host__ __device__ inline int batch_wps(int go, int K) { return (go == 2 ? 2 : go ? 3 : 4) + 2 * K; }
 __host__ __device__ inline int batch_wbuf_words(int go, int K) { return ((32 * batch_wps(go, K) + 8 + 3) / 4) * 4; }
+constexpr int kStageDepth = 4;  // vertex rows of a row-sharded table staged ahead per warp (cp.async ring)
 template <typename T>
-inline size_t batch_smem_bytes(int go, int K) {
-    return 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(batch_wbuf_words(go, K) + 32 * (K + 2)) * 4;
+inline size_t batch_smem_bytes(int go, int K, int stage_row_elems = 0) {
+    size_t base = 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(batch_wbuf_words(go, K) + 32 * (K + 2)) * 4;
+    base = (base + 15) & ~(size_t)15;
+    return base + (size_t)kWarpsPerBlock * kStageDepth * (size_t)stage_row_elems * sizeof(T);
 }
 
 // resident CTAs per SM the register allocator must allow: 3 while a row costs <= 16 B per lane (fp32 dim <= 128)
@@ -148,27 +151,54 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
     const int wib = threadIdx.x >> 5;
     const int w = blockIdx.x * kWarpsPerBlock + wib;
     if (w >= a.n_warps) return;
-    const Batch b = batch_init<T>(a.g.edge_at ? 2 : (GO ? 1 : 0), a.K, wib);
+    const int bmode = a.g.edge_at ? 2 : (GO ? 1 : 0);
+    const Batch b = batch_init<T>(bmode, a.K, wib);
     WarpState st = a.state[w];
     const uint64_t stream = a.stream_base + (uint64_t)w;
     const int nrows = a.K + 1;
+    // row-sharded: the vertex row of a sample usually lives on another GPU; its ~2-3 us NVLink load is taken off the
+    // critical path by staging the rows of the next kStageDepth-1 samples into a per-warp shared-memory ring
+    const bool staged = a.world_mask != 0;
+    constexpr int kRowElems = C::EPL * 32;
+    T* vstage = nullptr;
+    if (staged) {
+        size_t off = 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(batch_wbuf_words(bmode, a.K) + 32 * (a.K + 2)) * 4;
+        off = (off + 15) & ~(size_t)15;
+        vstage = reinterpret_cast<T*>(smem_raw + off) + (size_t)wib * kStageDepth * kRowElems;
+    }
     for (uint64_t done = 0; done < a.jobs; done += 32) {
         const int nb = (int)min((uint64_t)32, a.jobs - done);
         batch_sample<GO>(a.g, b, a.seed, stream, st, nb, lane);
+        if (staged) {
+#pragma unroll
+            for (int s = 0; s < kStageDepth - 1; ++s) {
+                if (s < nb) row_stage_async<C>(vstage + (s % kStageDepth) * kRowElems, tv.row(b.ids[s * b.idw]), lane, a.dim);
+                cp_async_commit();
+            }
+        }
         for (int s = 0; s < nb; ++s) {
             if (s + kLinePrefetch < nb) prefetch_sample<T>(tv, tc, a.g.shard_rank, b.ids + (s + kLinePrefetch) * b.idw, b.idw, lane);
             const int* sid = b.ids + s * b.idw;
             const int v1 = sid[0];
             const int v2 = sid[1];
             const int my = lane < nrows ? sid[1 + lane] : (-1 - lane);  // lane 0: positive context, lane 1+n: negative n
+            Row<C> vrow;
+            if (staged) {
+                const int s2 = s + kStageDepth - 1;
+                if (s2 < nb) row_stage_async<C>(vstage + (s2 % kStageDepth) * kRowElems, tv.row(b.ids[s2 * b.idw]), lane, a.dim);
+                cp_async_commit();
+                cp_async_wait<kStageDepth - 1>();
+                row_from_smem<C>(vrow, vstage + (s % kStageDepth) * kRowElems, lane, a.dim);
+            }
             if (v2 < 0) continue;
             const T alpha = (T)st.alpha;
-            if (!GO) update_pair_cpp<C>(tv, tc, a.dim, a.same_table != 0, lut, v1, my, nrows, alpha, lane);
-            else update_pair_go<C>(tv, tc, a.dim, a.same_table != 0, a.order == 1, lut, v1, my, nrows, alpha, lane);
+            if (!GO) update_pair_cpp<C>(tv, tc, a.dim, a.same_table != 0, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr);
+            else update_pair_go<C>(tv, tc, a.dim, a.same_table != 0, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr);
             st.count++;
             st.pairs++;
             sched_tick(st, a.sched);
         }
+        if (staged) cp_async_wait<0>();
     }
     if (lane == 0) a.state[w] = st;
 }

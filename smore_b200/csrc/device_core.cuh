@@ -277,6 +277,37 @@ struct Ar<double> {
     static __device__ __forceinline__ double msub(double c, double a, double b) { return __dsub_rn(c, __dmul_rn(a, b)); }
 };
 
+// Asynchronous global -> shared staging of one row (each lane copies exactly the vectors it owns, so a lane only ever
+// waits for its own copies: cp.async.wait_group, no warp barrier). Works on peer-mapped (NVLink) addresses, which the
+// local L2 cannot prefetch.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <class C>
+__device__ __forceinline__ void row_stage_async(typename C::T* slot, const typename C::T* src, int lane, int dim) {
+#pragma unroll
+    for (int c = 0; c < C::NCH; ++c) {
+        int idx = (c * 32 + lane) * C::VEC;
+        if (!C::MASKED || idx < dim) cp_async<C::VEC * (int)sizeof(typename C::T)>(slot + idx, src + idx);
+    }
+}
+template <class C>
+__device__ __forceinline__ void row_from_smem(Row<C>& r, const typename C::T* slot, int lane, int dim) {
+#pragma unroll
+    for (int c = 0; c < C::NCH; ++c) {
+        int idx = (c * 32 + lane) * C::VEC;
+#pragma unroll
+        for (int j = 0; j < C::VEC; ++j) r.x[c * C::VEC + j] = (!C::MASKED || idx < dim) ? slot[idx + j] : (typename C::T)0;
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -57,7 +57,7 @@ template <class C>
 __device__ __forceinline__ void update_pair_cpp(const TableView<typename C::T>& tv,
                                                 const TableView<typename C::T>& tc, int dim, bool same_table,
                                                 const typename C::T* lut, int v1, int my_id, int nrows,
-                                                typename C::T alpha, int lane) {
+                                                typename C::T alpha, int lane, const Row<C>* vpre = nullptr) {
     using T = typename C::T;
     using A = Ar<T>;
     bool active = lane < nrows;
@@ -66,7 +66,8 @@ __device__ __forceinline__ void update_pair_cpp(const TableView<typename C::T>& 
     T* pv = tv.row(v1);
     if (!dup) {
         Row<C> v, back;
-        v.load(pv, lane, dim);
+        if (vpre) v = *vpre;  // staged ahead of time (remote shard): a few samples stale, Hogwild-tolerated
+        else v.load(pv, lane, dim);
         back.zero();
         for (int base = 0; base < nrows; base += kCtxChunk) {
             Row<C> c[kCtxChunk];
@@ -131,7 +132,7 @@ template <class C>
 __device__ __forceinline__ void update_pair_go(const TableView<typename C::T>& tv,
                                                 const TableView<typename C::T>& tc, int dim, bool same_table,
                                                bool skip_source, const typename C::T* lut, int v1, int my_id,
-                                               int nrows, typename C::T alpha, int lane) {
+                                               int nrows, typename C::T alpha, int lane, const Row<C>* vpre = nullptr) {
     using T = typename C::T;
     using A = Ar<T>;
     int ctx = __shfl_sync(kFull, my_id, 0);
@@ -145,7 +146,8 @@ __device__ __forceinline__ void update_pair_go(const TableView<typename C::T>& t
     T* pp = tc.row(ctx);
     if (!dup) {
         Row<C> v, vgrad, pos, cgrad;
-        v.load(pv, lane, dim);
+        if (vpre) v = *vpre;
+        else v.load(pv, lane, dim);
         pos.load(pp, lane, dim);
         {
             T g = A::mul(alpha, A::sub((T)1, fast_sigmoid<T>(lut, dot(v, pos))));  // alpha * (label - pred)
