@@ -141,7 +141,7 @@ __device__ __forceinline__ void prefetch_local(const T* Wv, const T* Wc, const i
 // ---------------------------------------------------------------------------------------------------------------
 // LINE: LINE::Train (src/model/LINE.cpp:100-195) / LINE.Train (internal/models/line/line.go:73-150)
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, bool GO>
+template <class C, bool GO, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
     using T = typename C::T;
     const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
     const int nrows = a.K + 1;
     // row-sharded: the vertex row of a sample usually lives on another GPU; its ~2-3 us NVLink load is taken off the
     // critical path by staging the rows of the next kStageDepth-1 samples into a per-warp shared-memory ring
-    const bool staged = a.world_mask != 0;
+    constexpr bool staged = STAGED;  // == row-sharded table (a.world_mask != 0); a template flag keeps the unsharded
+                                     // instantiation free of the staging registers
     constexpr int kRowElems = C::EPL * 32;
     T* vstage = nullptr;
-    if (staged) {
+    if constexpr (staged) {
         size_t off = 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(batch_wbuf_words(bmode, a.K) + 32 * (a.K + 2)) * 4;
         off = (off + 15) & ~(size_t)15;
         vstage = reinterpret_cast<T*>(smem_raw + off) + (size_t)wib * kStageDepth * kRowElems;
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
     for (uint64_t done = 0; done < a.jobs; done += 32) {
         const int nb = (int)min((uint64_t)32, a.jobs - done);
         batch_sample<GO>(a.g, b, a.seed, stream, st, nb, lane);
-        if (staged) {
+        if constexpr (staged) {
 #pragma unroll
             for (int s = 0; s < kStageDepth - 1; ++s) {
                 if (s < nb) row_stage_async<C>(vstage + (s % kStageDepth) * kRowElems, tv.row(b.ids[s * b.idw]), lane, a.dim);
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             const int v2 = sid[1];
             const int my = lane < nrows ? sid[1 + lane] : (-1 - lane);  // lane 0: positive context, lane 1+n: negative n
             Row<C> vrow;
-            if (staged) {
+            if constexpr (staged) {
                 const int s2 = s + kStageDepth - 1;
                 if (s2 < nb) row_stage_async<C>(vstage + (s2 % kStageDepth) * kRowElems, tv.row(b.ids[s2 * b.idw]), lane, a.dim);
                 cp_async_commit();
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             st.pairs++;
             sched_tick(st, a.sched);
         }
-        if (staged) cp_async_wait<0>();
+        if constexpr (staged) cp_async_wait<0>();
     }
     if (lane == 0) a.state[w] = st;
 }

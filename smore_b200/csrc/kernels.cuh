@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_walk(TrainArgs<typename C::T>
 // Parity hooks
 // ---------------------------------------------------------------------------------------------------------------
 // One warp replays n sampler calls on stream (seed, stream). which: 0 source, 1 negative, 2 target(arg), 3 source+target.
-__global__ void k_sample_debug(GraphDev g, int which, uint64_t seed, uint64_t stream, int64_t n, const int64_t* arg,
+static __global__ void k_sample_debug(GraphDev g, int which, uint64_t seed, uint64_t stream, int64_t n, const int64_t* arg,
                                int64_t* out, uint64_t* words_used) {
     __shared__ __align__(16) uint32_t ringbuf[256];
     int lane = threadIdx.x;
@@ -430,7 +430,7 @@ __global__ void k_sample_debug(GraphDev g, int which, uint64_t seed, uint64_t st
 }
 
 // One warp: RandomWalk + pair enumeration exactly as k_walk does it, pairs written out instead of applied.
-__global__ void k_walk_debug(GraphDev g, uint64_t seed, uint64_t stream, int64_t start, int steps, int mode, int w0,
+static __global__ void k_walk_debug(GraphDev g, uint64_t seed, uint64_t stream, int64_t start, int steps, int mode, int w0,
                              int w1, int64_t* walk_out, int64_t* walk_len, int64_t* pv, int64_t* pc, int64_t cap,
                              int64_t* n_pairs) {
     __shared__ __align__(16) uint32_t ringbuf[256];

@@ -1,24 +1,6 @@
-// C-ABI implementation (include/smore_b200.h): handles, HBM layout, kernel launches. No CPU fallback anywhere.
-#include "../../include/smore_b200.h"
-
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <atomic>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <map>
-#include <string>
-#include <vector>
-
-#include "host_graph.h"
-#include "batch_kernels.cuh"
-
-using namespace smore;
-
-namespace {
+// C-ABI implementation (include/smore_b200.h): handles, HBM layout, host-side graph build. No CPU fallback anywhere.
+// The trainers (kernel launches) are instantiated per element type in train_*.cu.
+#include "host_common.h"
 
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
@@ -33,13 +15,6 @@ int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
-
-#define CU(call)                                                                                        \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess)                                                                          \
-            return fail(SMORE_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
 
 int ensure_device() {
     static thread_local int checked_dev = -2;
@@ -61,83 +36,6 @@ int ensure_device() {
     return SMORE_OK;
 }
 
-template <typename T>
-int dev_alloc_copy(T** d, const T* h, size_t n) {
-    *d = nullptr;
-    if (n == 0) return SMORE_OK;
-    CU(cudaMalloc((void**)d, n * sizeof(T)));
-    CU(cudaMemcpy(*d, h, n * sizeof(T), cudaMemcpyHostToDevice));
-    return SMORE_OK;
-}
-
-}  // namespace
-
-struct smore_graph_s {
-    int sem = 0, neg_method = 0;
-    int64_t V = 0, E = 0, n_lines = 0;
-    std::vector<int64_t> row_off;
-    std::vector<int32_t> col;
-    std::vector<double> w;
-    std::vector<std::string> names;
-    std::vector<int32_t> field;
-    bool has_field = false;
-    AliasHost vertex_at, negative_at, ctx_at;
-    std::vector<double> out_deg, in_deg;
-    // row sharding (one process per GPU): this rank owns vertices v with (v & (world-1)) == rank
-    int rank = 0, world = 1, shift = 0;
-    int64_t n_local = 0;            // owned vertices
-    double src_mass_frac = 1.0;     // share of the global source-sampling mass owned by this rank
-    // device
-    int64_t* d_row_off = nullptr;
-    int32_t* d_col = nullptr;
-    uint2 *d_vat = nullptr, *d_nat = nullptr, *d_cat = nullptr, *d_eat = nullptr;
-    int32_t *d_esrc = nullptr, *d_edst = nullptr;
-    int64_t n_edge_local = 0;
-    double* d_prefix = nullptr;
-    int32_t* d_field = nullptr;
-    double* d_lut64 = nullptr;
-    float* d_lut32 = nullptr;
-
-    GraphDev view() const {
-        GraphDev g;
-        g.V = V; g.E = E;
-        g.row_off = d_row_off; g.col = d_col;
-        g.vertex_at = d_vat; g.negative_at = d_nat; g.ctx_at = d_cat;
-        g.prefix = d_prefix; g.field = d_field; g.sem = sem;
-        g.n_neg = (uint32_t)n_local;
-        g.edge_at = d_eat; g.edge_src = d_esrc; g.edge_dst = d_edst; g.n_edge_local = (uint32_t)n_edge_local;
-        g.shard_shift = shift; g.shard_rank = rank;
-        return g;
-    }
-    ~smore_graph_s() {
-        cudaFree(d_row_off); cudaFree(d_col); cudaFree(d_vat); cudaFree(d_nat); cudaFree(d_cat);
-        cudaFree(d_prefix); cudaFree(d_field); cudaFree(d_lut64); cudaFree(d_lut32);
-        cudaFree(d_eat); cudaFree(d_esrc); cudaFree(d_edst);
-    }
-};
-
-struct smore_model_s {
-    smore_graph_t g = nullptr;
-    int dim = 0, n_tables = 0, dtype = 0;
-    void* tab[2] = {nullptr, nullptr};
-    int64_t rows = 0;                          // rows held locally (V when not sharded)
-    void* peer[2][kMaxWorld] = {};             // shard bases per rank (peer[t][rank] == tab[t])
-    bool peer_opened[2][kMaxWorld] = {};       // CUDA-IPC mappings to close
-    WarpState* d_state = nullptr;
-    int state_cap = 0;
-    int32_t* d_keys = nullptr;
-    int64_t keys_cap = 0;
-    // stats of the last train call
-    uint64_t st_samples = 0, st_pairs = 0, st_words0 = 0, st_tries = 0;
-    double st_ms = 0;
-    size_t elem() const { return dtype == SMORE_F64 ? 8 : 4; }
-    ~smore_model_s() {
-        for (int t = 0; t < 2; ++t)
-            for (int r = 0; r < kMaxWorld; ++r)
-                if (peer_opened[t][r]) cudaIpcCloseMemHandle(peer[t][r]);
-        cudaFree(tab[0]); cudaFree(tab[1]); cudaFree(d_state); cudaFree(d_keys);
-    }
-};
 
 namespace {
 
@@ -236,278 +134,9 @@ int build_graph(smore_graph_s* g) {
     return upload_graph(g);
 }
 
-// ---- row-layout dispatch ------------------------------------------------------------------------------------
-struct Launch {
-    int blocks = 0, warps = 0;
-};
-
-template <class K>
-int pick_grid(K kernel, size_t smem, int max_warps, uint64_t work_items, Launch& out) {
-    int dev = 0, sms = 0, occ = 0;
-    CU(cudaGetDevice(&dev));
-    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlockThreads, smem));
-    if (occ < 1) return fail(SMORE_E_CUDA, "kernel does not fit on an SM");
-    int64_t warps = (int64_t)sms * occ * kWarpsPerBlock;  // persistent grid: every CTA resident, a multiple of the SM count
-    if (max_warps > 0) warps = std::min<int64_t>(warps, max_warps);
-    warps = std::min<int64_t>(warps, (int64_t)std::max<uint64_t>(work_items, 1));
-    out.warps = (int)warps;
-    out.blocks = (int)((warps + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    return SMORE_OK;
-}
-
-// F is a generic lambda taking a RowCfg tag.
-template <typename T, class F>
-int dispatch_dim(int dim, F&& f) {
-    constexpr int V16 = 16 / (int)sizeof(T);  // elements per 128-bit vector
-    if (dim <= 0) return fail(SMORE_E_INVALID, "dim must be positive");
-    if (dim % (32 * V16) == 0) {
-        int nch = dim / (32 * V16);
-        if (nch == 1) return f(RowCfg<T, V16, 1, false>{});
-        if (nch == 2) return f(RowCfg<T, V16, 2, false>{});
-        if (nch == 4) return f(RowCfg<T, V16, 4, false>{});
-    }
-    if (V16 == 4 && dim == 64) return f(RowCfg<T, 2, 1, false>{});
-    if (dim <= 32) return f(RowCfg<T, 1, 1, true>{});
-    if (dim <= 64) return f(RowCfg<T, 1, 2, true>{});
-    if (dim <= 128) return f(RowCfg<T, 1, 4, true>{});
-    return fail(SMORE_E_UNSUPPORTED, "dim=%d unsupported (<=128, or a multiple of %d up to %d)", dim, 32 * V16, 128 * V16);
-}
-
-int ensure_state(smore_model_s* m, int warps) {
-    if (warps > m->state_cap) {
-        cudaFree(m->d_state);
-        m->d_state = nullptr;
-        CU(cudaMalloc((void**)&m->d_state, (size_t)warps * sizeof(WarpState)));
-        m->state_cap = warps;
-    }
-    return SMORE_OK;
-}
-
-int check_train(smore_model_s* m, const smore_train_params* p, int need_tables, bool shard_ok = false) {
-    if (!m || !p) return fail(SMORE_E_INVALID, "null model/params");
-    if (m->g->world > 1 && !shard_ok) return fail(SMORE_E_UNSUPPORTED, "this trainer does not run on a row-sharded graph yet (LINE does)");
-    if (m->g->world > 1)
-        for (int t = 0; t < m->n_tables; ++t)
-            for (int r = 0; r < m->g->world; ++r)
-                if (!m->peer[t][r]) return fail(SMORE_E_INVALID, "table %d: shard of rank %d not connected (smore_model_open_peers)", t, r);
-    if (p->semantics != m->g->sem) return fail(SMORE_E_INVALID, "params.semantics (%d) != graph semantics (%d)", p->semantics, m->g->sem);
-    if (m->n_tables < need_tables) return fail(SMORE_E_INVALID, "model has %d tables, this trainer needs %d", m->n_tables, need_tables);
-    if (p->mode != SMORE_MODE_DETERMINISTIC && p->mode != SMORE_MODE_HOGWILD) return fail(SMORE_E_INVALID, "bad mode");
-    if (!(p->alpha > 0)) return fail(SMORE_E_INVALID, "alpha must be > 0");
-    return ensure_device();
-}
-
-struct Timer {
-    cudaEvent_t a = nullptr, b = nullptr;
-    int start() {
-        CU(cudaEventCreate(&a));
-        CU(cudaEventCreate(&b));
-        CU(cudaEventRecord(a, 0));
-        return SMORE_OK;
-    }
-    int stop(double* ms) {
-        CU(cudaEventRecord(b, 0));
-        CU(cudaEventSynchronize(b));
-        float f = 0;
-        CU(cudaEventElapsedTime(&f, a, b));
-        *ms = f;
-        cudaEventDestroy(a);
-        cudaEventDestroy(b);
-        a = b = nullptr;
-        return SMORE_OK;
-    }
-    ~Timer() {
-        if (a) cudaEventDestroy(a);
-        if (b) cudaEventDestroy(b);
-    }
-};
-
-int collect_stats(smore_model_s* m, int warps) {
-    std::vector<WarpState> st((size_t)warps);
-    CU(cudaMemcpy(st.data(), m->d_state, st.size() * sizeof(WarpState), cudaMemcpyDeviceToHost));
-    m->st_pairs = m->st_tries = 0;
-    for (auto& s : st) {
-        m->st_pairs += s.pairs;
-        m->st_tries += s.tries;
-    }
-    m->st_words0 = st[0].pos;
-    return SMORE_OK;
-}
-
-template <typename T>
-TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps, double total, int lag, int vtab, int ctab,
-                       double scale = 1.0 /* row-sharded: this rank's share of the schedule units */) {
-    TrainArgs<T> a{};
-    a.g = m->g->view();
-    a.Wv = (T*)m->tab[vtab];
-    a.Wc = (T*)m->tab[ctab];
-    for (int r = 0; r < kMaxWorld; ++r) {
-        a.peer_v[r] = (T*)m->peer[vtab][r];
-        a.peer_c[r] = (T*)m->peer[ctab][r];
-    }
-    a.world_shift = m->g->shift;
-    a.world_mask = m->g->world - 1;
-    a.dim = m->dim;
-    a.same_table = vtab == ctab;
-    a.lut = sizeof(T) == 8 ? (const T*)m->g->d_lut64 : (const T*)m->g->d_lut32;
-    a.seed = p->seed;
-    a.stream_base = p->stream_base;
-    // a call may be one chunk of a longer LR schedule (sched_total / sched_offset, in the same units as `total`)
-    const double sched_total = p->sched_total ? (double)p->sched_total * scale : total;
-    a.sched = Sched{p->alpha, sched_total, (uint64_t)warps, lag, (double)p->sched_offset * scale};
-    a.state = m->d_state;
-    a.n_warps = warps;
-    a.K = p->negative_samples;
-    a.order = p->order;
-    a.lambda = (T)p->lambda;
-    return a;
-}
-
-int init_state(smore_model_s* m, int warps, uint64_t count0, double alpha, const smore_train_params* p = nullptr) {
-    if (p && p->sched_total && p->sched_offset) {  // resume a longer schedule: alpha_t = alpha * max(1e-4, 1 - done/total)
-        const double a = alpha * (1.0 - (double)p->sched_offset / (double)p->sched_total);
-        alpha = a < alpha * 0.0001 ? alpha * 0.0001 : a;
-    }
-    std::vector<WarpState> st((size_t)warps);
-    for (int w = 0; w < warps; ++w) {
-        st[(size_t)w] = WarpState{0, count0, ((uint64_t)kMonitor + (uint64_t)warps - 1) / (uint64_t)warps, alpha, 0, 0};
-    }
-    if (int rc = ensure_state(m, warps)) return rc;
-    CU(cudaMemcpy(m->d_state, st.data(), st.size() * sizeof(WarpState), cudaMemcpyHostToDevice));
-    return SMORE_OK;
-}
-
-constexpr size_t smem_rings = (size_t)kWarpsPerBlock * 256 * sizeof(uint32_t);
-template <typename T>
-constexpr size_t smem_line() { return smem_rings + 1008 * sizeof(T); }
-template <typename T>
-constexpr size_t smem_walk() { return smem_line<T>() + (size_t)kWarpsPerBlock * kMaxWalkLen * (sizeof(int32_t) + 1); }
-
-// ---- LINE -----------------------------------------------------------------------------------------------------
-template <typename T>
-int train_line_t(smore_model_s* m, const smore_train_params* p) {
-    const int vtab = 0, ctab = p->order == 1 ? 0 : 1;
-    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
-        using C = decltype(cfg);
-        const bool cpp = p->semantics == SMORE_SEM_CPP;
-        void (*kern)(TrainArgs<T>) = cpp ? k_line<C, false> : k_line<C, true>;
-        const size_t smem = batch_smem_bytes<T>(m->g->world > 1 ? 2 : cpp ? 0 : 1, p->negative_samples,
-                                                m->g->world > 1 ? C::EPL * 32 : 0);
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        Launch L;
-        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
-        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
-        // row-sharded: this rank draws sources from its own vertices only and runs its share of the global total
-        const uint64_t total_local = m->g->world == 1 ? p->total : (uint64_t)llround((double)p->total * m->g->src_mass_frac);
-        // jobs = total / workers (LINE.cpp:124); the C++ loop starts count at 1 and runs while count < jobs
-        const uint64_t jobs = total_local / (uint64_t)L.warps;
-        const uint64_t trips = cpp ? (jobs > 0 ? jobs - 1 : 0) : jobs;
-        if (int rc = init_state(m, L.warps, cpp ? 1 : 0, p->alpha, p)) return rc;
-        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)total_local, cpp ? 1 : 0, vtab, ctab,
-                                      m->g->world == 1 ? 1.0 : m->g->src_mass_frac);
-        a.jobs = trips;
-        Timer t;
-        if (int rc = t.start()) return rc;
-        kern<<<L.blocks, kBlockThreads, smem>>>(a);
-        g_launches++;
-        CU(cudaGetLastError());
-        if (int rc = t.stop(&m->st_ms)) return rc;
-        m->st_samples = trips * (uint64_t)L.warps;
-        return collect_stats(m, L.warps);
-    });
-}
-
-// ---- DeepWalk / Walklets ----------------------------------------------------------------------------------------
-template <typename T>
-int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets) {
-    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
-        using C = decltype(cfg);
-        auto kern = k_walk<C>;
-        const size_t smem = smem_walk<T>();
-        const bool cpp = p->semantics == SMORE_SEM_CPP;
-        const int64_t V = m->g->V;
-        Launch L;
-        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
-        else if (int rc = pick_grid(kern, smem, p->max_warps, (uint64_t)V, L)) return rc;
-        const double total = (double)((unsigned long long)p->walk_times * (unsigned long long)V);
-        if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
-        TrainArgs<T> a = base_args<T>(m, p, L.warps, total, 0, 0, 1);
-        a.steps = p->walk_steps;
-        a.w0 = p->window_min;
-        a.w1 = p->window_max;
-        a.walklets = walklets;
-        if (m->keys_cap < V) {
-            cudaFree(m->d_keys);
-            m->d_keys = nullptr;
-            CU(cudaMalloc((void**)&m->d_keys, (size_t)V * sizeof(int32_t)));
-            m->keys_cap = V;
-        }
-        a.keys = m->d_keys;
-        std::vector<int32_t> keys((size_t)V);
-        HostStream shuffle(p->seed, kShuffleStream);
-        int64_t walks_left = p->max_walks >= 0 ? p->max_walks : (int64_t)p->walk_times * V;
-        uint64_t done = 0;
-        m->st_ms = 0;
-        for (int t = 0; t < p->walk_times && walks_left > 0; ++t) {
-            // per-epoch Fisher-Yates (DeepWalk.cpp:124-131 with libc rand() := shuffle-stream word >> 1;
-            // deepwalk.go:84-92 with rand.Int63n(n) := umulhi32(word, n)). Walklets draws it but walks in id order.
-            for (int64_t v = 0; v < V; ++v) keys[(size_t)v] = (int32_t)v;
-            for (int64_t v = 0; v < V; ++v) {
-                uint32_t k = shuffle.next();
-                int64_t j = cpp ? (int64_t)(int)(v + (int64_t)(k >> 1) % (V - v)) : v + (int64_t)(((uint64_t)k * (uint64_t)(V - v)) >> 32);
-                std::swap(keys[(size_t)v], keys[(size_t)j]);
-            }
-            if (walklets)
-                for (int64_t v = 0; v < V; ++v) keys[(size_t)v] = (int32_t)v;
-            CU(cudaMemcpy(m->d_keys, keys.data(), (size_t)V * sizeof(int32_t), cudaMemcpyHostToDevice));
-            a.n_walks = std::min<int64_t>(V, walks_left);
-            Timer tm;
-            double ms = 0;
-            if (int rc = tm.start()) return rc;
-            kern<<<L.blocks, kBlockThreads, smem>>>(a);
-            g_launches++;
-            CU(cudaGetLastError());
-            if (int rc = tm.stop(&ms)) return rc;
-            m->st_ms += ms;
-            walks_left -= a.n_walks;
-            done += (uint64_t)a.n_walks;
-        }
-        m->st_samples = done;
-        return collect_stats(m, L.warps);
-    });
-}
-
-// ---- BPR / WARP / HOP-Rec -------------------------------------------------------------------------------------
-template <typename T>
-int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind) {
-    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
-        using C = decltype(cfg);
-        const bool cpp = p->semantics == SMORE_SEM_CPP;
-        void (*kern)(TrainArgs<T>) = kind == RANK_WARP ? k_warp<C> : kind == RANK_HOPREC ? k_hoprec<C> : cpp ? k_bpr_cpp<C> : k_bpr_go<C>;
-        const size_t smem = kind != RANK_BPR ? smem_line<T>() : cpp ? batch_smem_bytes<T>(0, 5) : batch_smem_bytes<T>(1, 1);
-        Launch L;
-        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
-        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
-        // BPR.cpp:73-85 / WARP.cpp / HBPR.cpp: jobs = total / workers, count from 0; bpr.go: sample_times*MaxLine trips
-        const uint64_t trips = p->total / (uint64_t)L.warps;
-        if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
-        const int ctab = (kind == RANK_BPR && !cpp) ? 1 : 0;  // the C++ ranking models pass one table for both roles
-        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)p->total, cpp ? 1 : 0, 0, ctab);
-        a.jobs = trips;
-        a.steps = p->walk_steps;
-        Timer t;
-        if (int rc = t.start()) return rc;
-        kern<<<L.blocks, kBlockThreads, smem>>>(a);
-        g_launches++;
-        CU(cudaGetLastError());
-        if (int rc = t.stop(&m->st_ms)) return rc;
-        m->st_samples = trips * (uint64_t)L.warps;
-        return collect_stats(m, L.warps);
-    });
-}
 
 }  // namespace
+
 
 namespace {
 template <typename TH>

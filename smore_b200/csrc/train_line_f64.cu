@@ -1,0 +1,2 @@
+#include "train_line.inl"
+template int train_line_t<double>(smore_model_s*, const smore_train_params*);

@@ -1,0 +1,2 @@
+#include "train_rank.inl"
+template int train_ranking_t<double>(smore_model_s*, const smore_train_params*, int);

@@ -1,0 +1,62 @@
+// DeepWalk / Walklets trainer
+#include "host_common.h"
+
+template <typename T>
+int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets) {
+    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
+        using C = decltype(cfg);
+        auto kern = k_walk<C>;
+        const size_t smem = smem_walk<T>();
+        const bool cpp = p->semantics == SMORE_SEM_CPP;
+        const int64_t V = m->g->V;
+        Launch L;
+        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
+        else if (int rc = pick_grid(kern, smem, p->max_warps, (uint64_t)V, L)) return rc;
+        const double total = (double)((unsigned long long)p->walk_times * (unsigned long long)V);
+        if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
+        TrainArgs<T> a = base_args<T>(m, p, L.warps, total, 0, 0, 1);
+        a.steps = p->walk_steps;
+        a.w0 = p->window_min;
+        a.w1 = p->window_max;
+        a.walklets = walklets;
+        if (m->keys_cap < V) {
+            cudaFree(m->d_keys);
+            m->d_keys = nullptr;
+            CU(cudaMalloc((void**)&m->d_keys, (size_t)V * sizeof(int32_t)));
+            m->keys_cap = V;
+        }
+        a.keys = m->d_keys;
+        std::vector<int32_t> keys((size_t)V);
+        HostStream shuffle(p->seed, kShuffleStream);
+        int64_t walks_left = p->max_walks >= 0 ? p->max_walks : (int64_t)p->walk_times * V;
+        uint64_t done = 0;
+        m->st_ms = 0;
+        for (int t = 0; t < p->walk_times && walks_left > 0; ++t) {
+            // per-epoch Fisher-Yates (DeepWalk.cpp:124-131 with libc rand() := shuffle-stream word >> 1;
+            // deepwalk.go:84-92 with rand.Int63n(n) := umulhi32(word, n)). Walklets draws it but walks in id order.
+            for (int64_t v = 0; v < V; ++v) keys[(size_t)v] = (int32_t)v;
+            for (int64_t v = 0; v < V; ++v) {
+                uint32_t k = shuffle.next();
+                int64_t j = cpp ? (int64_t)(int)(v + (int64_t)(k >> 1) % (V - v)) : v + (int64_t)(((uint64_t)k * (uint64_t)(V - v)) >> 32);
+                std::swap(keys[(size_t)v], keys[(size_t)j]);
+            }
+            if (walklets)
+                for (int64_t v = 0; v < V; ++v) keys[(size_t)v] = (int32_t)v;
+            CU(cudaMemcpy(m->d_keys, keys.data(), (size_t)V * sizeof(int32_t), cudaMemcpyHostToDevice));
+            a.n_walks = std::min<int64_t>(V, walks_left);
+            Timer tm;
+            double ms = 0;
+            if (int rc = tm.start()) return rc;
+            kern<<<L.blocks, kBlockThreads, smem>>>(a);
+            g_launches++;
+            CU(cudaGetLastError());
+            if (int rc = tm.stop(&ms)) return rc;
+            m->st_ms += ms;
+            walks_left -= a.n_walks;
+            done += (uint64_t)a.n_walks;
+        }
+        m->st_samples = done;
+        return collect_stats(m, L.warps);
+    });
+}
+

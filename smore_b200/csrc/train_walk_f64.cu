@@ -1,0 +1,2 @@
+#include "train_walk.inl"
+template int train_walk_t<double>(smore_model_s*, const smore_train_params*, int);
