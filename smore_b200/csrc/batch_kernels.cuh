@@ -17,6 +17,8 @@
 //
 // Shared memory: sigmoid LUT | per warp: word buffer [32*wps + 8] | ids [32*(K+2)]  (ids row = v1, v2, neg_0..neg_K-1)
 #pragma once
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "ranking_kernels.cuh"
 
@@ -109,8 +111,8 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
 
 // L2 prefetch of every row of one sample (ids row `pid`: slot 0 lives in the vertex table, the others in the context
 // table). Rows of a peer shard are skipped: peer addresses bypass the local L2.
-template <typename T>
-__device__ __forceinline__ void prefetch_sample(const TableView<T>& tv, const TableView<T>& tc, int rank, const int* pid,
+template <typename T, class TV>
+__device__ __forceinline__ void prefetch_sample(const TV& tv, const TV& tc, int rank, const int* pid,
                                                 int idw, int lane) {
     const int lines_per_row = (tv.dim * (int)sizeof(T) + 127) >> 7;
     const int total = idw * lines_per_row;
@@ -145,8 +147,13 @@ template <class C, bool GO, bool STAGED>
 __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
     using T = typename C::T;
     const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
-    TableView<T> tv, tc;
-    stage_views<T>(a, tv, tc);
+    using TV = typename std::conditional<STAGED, TableView<T>, DirectView<T>>::type;
+    TV tv, tc;
+    if constexpr (STAGED) stage_views<T>(a, tv, tc);
+    else {
+        tv = DirectView<T>{a.Wv, a.dim};
+        tc = DirectView<T>{a.Wc, a.dim};
+    }
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int w = blockIdx.x * kWarpsPerBlock + wib;
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             }
         }
         for (int s = 0; s < nb; ++s) {
-            if (s + kLinePrefetch < nb) prefetch_sample<T>(tv, tc, a.g.shard_rank, b.ids + (s + kLinePrefetch) * b.idw, b.idw, lane);
+            if (s + kLinePrefetch < nb) prefetch_sample<T, TV>(tv, tc, a.g.shard_rank, b.ids + (s + kLinePrefetch) * b.idw, b.idw, lane);
             const int* sid = b.ids + s * b.idw;
             const int v1 = sid[0];
             const int v2 = sid[1];

@@ -55,6 +55,14 @@ struct TableView {
     int shift, mask, dim;
     __device__ __forceinline__ T* row(int id) const { return base[id & mask] + (size_t)(id >> shift) * dim; }
 };
+// The unsharded table: one base pointer, no indirection (keeps the single-GPU kernels free of the shard arithmetic).
+template <typename T>
+struct DirectView {
+    T* base0;
+    int dim;
+    static constexpr int mask = 0;
+    __device__ __forceinline__ T* row(int id) const { return base0 + (size_t)id * dim; }
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // Per-warp draw ring

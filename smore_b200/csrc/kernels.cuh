@@ -53,9 +53,9 @@ struct TrainArgs {
 // skip-gram pair update, C++ semantics: proNet::UpdatePair + Opt_SigmoidSGD (src/proNet.cpp:1784-1809, :1312-1330).
 // my_id: lane 0 holds the positive context, lane 1+n negative n; nrows = K+1 <= 32.
 // ---------------------------------------------------------------------------------------------------------------
-template <class C>
-__device__ __forceinline__ void update_pair_cpp(const TableView<typename C::T>& tv,
-                                                const TableView<typename C::T>& tc, int dim, bool same_table,
+template <class C, class TV>
+__device__ __forceinline__ void update_pair_cpp(const TV& tv,
+                                                const TV& tc, int dim, bool same_table,
                                                 const typename C::T* lut, int v1, int my_id, int nrows,
                                                 typename C::T alpha, int lane, const Row<C>* vpre = nullptr) {
     using T = typename C::T;
@@ -128,9 +128,9 @@ __device__ __forceinline__ void update_pair_cpp(const TableView<typename C::T>& 
 // skip_source, LINE.updateFirstOrder (internal/models/line/line.go:153-200). Negatives equal to the context (or the
 // source) are skipped; the positive context row is written last.
 // ---------------------------------------------------------------------------------------------------------------
-template <class C>
-__device__ __forceinline__ void update_pair_go(const TableView<typename C::T>& tv,
-                                                const TableView<typename C::T>& tc, int dim, bool same_table,
+template <class C, class TV>
+__device__ __forceinline__ void update_pair_go(const TV& tv,
+                                                const TV& tc, int dim, bool same_table,
                                                bool skip_source, const typename C::T* lut, int v1, int my_id,
                                                int nrows, typename C::T alpha, int lane, const Row<C>* vpre = nullptr) {
     using T = typename C::T;
@@ -336,8 +336,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_walk(TrainArgs<typename C::T>
     int32_t* walks = reinterpret_cast<int32_t*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t) + 1008 * sizeof(T));
     uint8_t* reduces = reinterpret_cast<uint8_t*>(walks + kWarpsPerBlock * kMaxWalkLen);
     const T* lut = stage_lut<T>(a.lut, lut_s);
-    TableView<T> tv, tc;
-    stage_views<T>(a, tv, tc);
+    const DirectView<T> tv{a.Wv, a.dim}, tc{a.Wc, a.dim};
     int lane = threadIdx.x & 31;
     int wib = threadIdx.x >> 5;
     int w = blockIdx.x * kWarpsPerBlock + wib;
