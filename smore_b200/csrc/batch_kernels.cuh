@@ -244,9 +244,12 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go
             const bool same = pos == neg;
             const bool valias = a.same_table && (user == pos || user == neg);
             Row<C> v, p, n;
-            v.load(pv, lane, dim);
-            p.load(pp, lane, dim);
-            n.load(pn, lane, dim);
+            v.load_ca(pv, lane, dim);
+            p.load_ca(pp, lane, dim);
+            n.load_ca(pn, lane, dim);
+            pin(v);
+            pin(p);
+            pin(n);
             Row<C> pn2[2] = {p, n};
             T sc[2];
             dots<C, 2>(v, pn2, 2, sc);  // posScore, negScore (optimizer.go:95-100)
@@ -312,6 +315,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_cp
             const int my = lane < 7 ? sid[lane] : (-1 - lane);
             const unsigned peers = __match_any_sync(kFull, my);
             const bool dup = __any_sync(kFull, lane < 7 && __popc(peers) > 1);
+            st.tries += dup ? 1u : 0u;  // stats: samples that took the ORDERED path (reported as mean_tries)
             using A = Ar<T>;
             const T alpha = (T)st.alpha;
             const T c = A::mul(alpha, (T)0.0025);  // alpha*0.0025*w evaluates left to right
@@ -320,10 +324,14 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_cp
             T* pi = W + (size_t)v2 * dim;
             if (!dup) {
                 Row<C> v, ri, rj[5], verr;
-                v.load(pv, lane, dim);
-                ri.load(pi, lane, dim);
+                v.load_ca(pv, lane, dim);
+                ri.load_ca(pi, lane, dim);
 #pragma unroll
-                for (int n = 0; n < 5; ++n) rj[n].load(W + (size_t)sid[2 + n] * dim, lane, dim);
+                for (int n = 0; n < 5; ++n) rj[n].load_ca(W + (size_t)sid[2 + n] * dim, lane, dim);
+                pin(v);
+                pin(ri);
+#pragma unroll
+                for (int n = 0; n < 5; ++n) pin(rj[n]);  // all seven gathers in flight before the first round
                 verr.zero();
 #pragma unroll
                 for (int n = 0; n < 5; ++n) {

@@ -181,6 +181,10 @@ struct VecIO<float, 4> {
         float4 v = __ldcg(reinterpret_cast<const float4*>(p));
         x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
     }
+    static __device__ __forceinline__ void ld_ca(const float* p, float* x) {
+        float4 v = __ldca(reinterpret_cast<const float4*>(p));
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
     static __device__ __forceinline__ void st(float* p, const float* x) {
         __stcg(reinterpret_cast<float4*>(p), make_float4(x[0], x[1], x[2], x[3]));
     }
@@ -191,6 +195,10 @@ struct VecIO<float, 2> {
         float2 v = __ldcg(reinterpret_cast<const float2*>(p));
         x[0] = v.x; x[1] = v.y;
     }
+    static __device__ __forceinline__ void ld_ca(const float* p, float* x) {
+        float2 v = __ldca(reinterpret_cast<const float2*>(p));
+        x[0] = v.x; x[1] = v.y;
+    }
     static __device__ __forceinline__ void st(float* p, const float* x) {
         __stcg(reinterpret_cast<float2*>(p), make_float2(x[0], x[1]));
     }
@@ -198,12 +206,17 @@ struct VecIO<float, 2> {
 template <>
 struct VecIO<float, 1> {
     static __device__ __forceinline__ void ld(const float* p, float* x) { x[0] = __ldcg(p); }
+    static __device__ __forceinline__ void ld_ca(const float* p, float* x) { x[0] = __ldca(p); }
     static __device__ __forceinline__ void st(float* p, const float* x) { __stcg(p, x[0]); }
 };
 template <>
 struct VecIO<double, 2> {
     static __device__ __forceinline__ void ld(const double* p, double* x) {
         double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+        x[0] = v.x; x[1] = v.y;
+    }
+    static __device__ __forceinline__ void ld_ca(const double* p, double* x) {
+        double2 v = __ldca(reinterpret_cast<const double2*>(p));
         x[0] = v.x; x[1] = v.y;
     }
     static __device__ __forceinline__ void st(double* p, const double* x) {
@@ -213,6 +226,7 @@ struct VecIO<double, 2> {
 template <>
 struct VecIO<double, 1> {
     static __device__ __forceinline__ void ld(const double* p, double* x) { x[0] = __ldcg(p); }
+    static __device__ __forceinline__ void ld_ca(const double* p, double* x) { x[0] = __ldca(p); }
     static __device__ __forceinline__ void st(double* p, const double* x) { __stcg(p, x[0]); }
 };
 
@@ -237,6 +251,20 @@ struct Row {
         for (int c = 0; c < C::NCH; ++c) {
             int idx = (c * 32 + lane) * C::VEC;
             if (!C::MASKED || idx < dim) VecIO<typename C::T, C::VEC>::ld(base + idx, x + c * C::VEC);
+            else {
+#pragma unroll
+                for (int j = 0; j < C::VEC; ++j) x[c * C::VEC + j] = 0;
+            }
+        }
+    }
+    // L1-allocating gather (ld.global.ca): a row that many warps of the SM keep re-reading (popular items of a
+    // Zipf-distributed catalogue) is served from L1 instead of queueing at its L2 slice behind everybody's writes.
+    // Stale by at most the L1 residence time; a lane's own stores still invalidate the line (same-SM coherence).
+    __device__ __forceinline__ void load_ca(const typename C::T* base, int lane, int dim) {
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c) {
+            int idx = (c * 32 + lane) * C::VEC;
+            if (!C::MASKED || idx < dim) VecIO<typename C::T, C::VEC>::ld_ca(base + idx, x + c * C::VEC);
             else {
 #pragma unroll
                 for (int j = 0; j < C::VEC; ++j) x[c * C::VEC + j] = 0;
@@ -313,6 +341,18 @@ __device__ __forceinline__ void row_from_smem(Row<C>& r, const typename C::T* sl
         int idx = (c * 32 + lane) * C::VEC;
 #pragma unroll
         for (int j = 0; j < C::VEC; ++j) r.x[c * C::VEC + j] = (!C::MASKED || idx < dim) ? slot[idx + j] : (typename C::T)0;
+    }
+}
+
+// Compiler barrier on a row's registers: forces the gathers that fill them to be ISSUED before this point. Without it
+// ptxas, squeezed by the launch-bounds register cap, sinks each row load next to its first use, which turns one
+// overlapped gather of n rows into n serialized DRAM round trips (measured on k_bpr_cpp: 4x slower).
+template <class C>
+__device__ __forceinline__ void pin(Row<C>& r) {
+#pragma unroll
+    for (int e = 0; e < C::EPL; ++e) {
+        if constexpr (sizeof(typename C::T) == 4) asm volatile("" : "+f"(r.x[e]));
+        else asm volatile("" : "+d"(r.x[e]));
     }
 }
 

@@ -60,9 +60,9 @@ __device__ __forceinline__ bool ordered_round(typename C::T* pv, typename C::T* 
     using T = typename C::T;
     using A = Ar<T>;
     Row<C> v, ri, rj, cvec;
-    v.load(pv, lane, dim);
-    ri.load(pi, lane, dim);
-    rj.load(pj, lane, dim);
+    v.load_ca(pv, lane, dim);
+    ri.load_ca(pi, lane, dim);
+    rj.load_ca(pj, lane, dim);
 #pragma unroll
     for (int e = 0; e < C::EPL; ++e) cvec.x[e] = A::sub(ri.x[e], rj.x[e]);
     const T f = dot(v, cvec);
@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_warp(TrainArgs<typename C::T>
         T* pv = W + v1 * dim;
         T* pi = W + v2 * dim;
         Row<C> v, ri;
-        v.load(pv, lane, dim);
-        ri.load(pi, lane, dim);
+        v.load_ca(pv, lane, dim);
+        ri.load_ca(pi, lane, dim);
         int scanned = 0;  // negatives evaluated so far
         bool hit = false;
         // candidate n lives at ring words 4+2n, 5+2n
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_warp(TrainArgs<typename C::T>
             for (int r = 0; r < kWarpBatch; ++r) {
                 jid[r] = __shfl_sync(kFull, cand, r);
                 if (r < nb) {
-                    cvec[r].load(W + jid[r] * dim, lane, dim);
+                    cvec[r].load_ca(W + jid[r] * dim, lane, dim);
 #pragma unroll
                     for (int e = 0; e < C::EPL; ++e) cvec[r].x[e] = A::sub(ri.x[e], cvec[r].x[e]);
                 }
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_warp(TrainArgs<typename C::T>
                         const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f[r])), alpha);
                         if (j != v2 && j != v1 && v1 != v2) {
                             Row<C> rj;
-                            rj.load(pj, lane, dim);  // only the difference was kept; the row is an L2 hit now
+                            rj.load_ca(pj, lane, dim);  // only the difference was kept; the row is an L2 hit now
 #pragma unroll
                             for (int e = 0; e < C::EPL; ++e) {
                                 const T verr = A::mul(gg, cvec[r].x[e]);
@@ -286,10 +286,14 @@ __global__ void __launch_bounds__(kBlockThreads) k_hoprec(TrainArgs<typename C::
             T up = 0;
             if (!dup) {
                 Row<C> v, ri, rj[5];
-                v.load(pv, lane, dim);
-                ri.load(pi, lane, dim);
+                v.load_ca(pv, lane, dim);
+                ri.load_ca(pi, lane, dim);
 #pragma unroll
-                for (int r = 0; r < 5; ++r) rj[r].load(W + jid[r] * dim, lane, dim);
+                for (int r = 0; r < 5; ++r) rj[r].load_ca(W + jid[r] * dim, lane, dim);
+                pin(v);
+                pin(ri);
+#pragma unroll
+                for (int r = 0; r < 5; ++r) pin(rj[r]);  // all seven gathers in flight before the first round
                 bool ri_dirty = false;
 #pragma unroll
                 for (int r = 0; r < 5; ++r) {
