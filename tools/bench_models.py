@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--only", default="")
+    ap.add_argument("--zipf", type=float, default=1.0, help="item popularity exponent of the bipartite graphs")
     a = ap.parse_args()
     only = set(a.only.split(",")) if a.only else None
 
@@ -59,7 +60,7 @@ def main():
 
     # ---- configs[0]: BPR dim 64, 10k users x 10k items, 1M edges (and the same graph at dim 128) ----
     if want("bpr_go") or want("bpr_cpp"):
-        src, dst, w = synth.bipartite_edges(10_000, 10_000, 1_000_000, 7)
+        src, dst, w = synth.bipartite_edges(10_000, 10_000, 1_000_000, 7, zipf_s=a.zipf)
         off, col, ww, _ = synth.csr_from_edges(src, dst, w, False)
         for dim in (64, 128):
             if want("bpr_go"):
@@ -81,7 +82,7 @@ def main():
     if want("bpr_go_big") or want("warp") or want("hoprec") or want("bpr_cpp_big"):
         nu, ni, ne = int(1_000_000 * a.scale), int(200_000 * a.scale), int(20_000_000 * a.scale)
         t0 = time.time()
-        src, dst, w = synth.bipartite_edges(nu, ni, ne, 9)
+        src, dst, w = synth.bipartite_edges(nu, ni, ne, 9, zipf_s=a.zipf)
         dim = 128
         if want("bpr_go_big"):
             off, col, ww, _ = synth.csr_from_edges(src, dst, w, False)
