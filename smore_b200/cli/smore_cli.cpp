@@ -183,18 +183,45 @@ int main(int argc, char** argv) {
            p.negative_samples, p.alpha);
     if (a.has("threads")) printf("\tworkers:\t\t-threads %ld ignored: workers are GPU warps\n", a.num("threads", 1));
     printf("Start Training:\n");
-    int rc;
-    if (model == "line") rc = smore_train_line(m, &p);
-    else if (model == "deepwalk") rc = smore_train_deepwalk(m, &p);
-    else if (model == "walklets") rc = smore_train_walklets(m, &p);
-    else if (model == "bpr") rc = smore_train_bpr(m, &p);
-    else if (model == "warp") rc = smore_train_warp(m, &p);
-    else rc = smore_train_hoprec(m, &p);
-    if (rc) return die("Train");
+    auto train_once = [&](const smore_train_params& q) -> int {
+        if (model == "line") return smore_train_line(m, &q);
+        if (model == "deepwalk") return smore_train_deepwalk(m, &q);
+        if (model == "walklets") return smore_train_walklets(m, &q);
+        if (model == "bpr") return smore_train_bpr(m, &q);
+        if (model == "warp") return smore_train_warp(m, &q);
+        return smore_train_hoprec(m, &q);
+    };
     uint64_t samples = 0, pairs = 0;
     double ms = 0;
-    smore_train_stats(m, &samples, &pairs, nullptr, nullptr, &ms);
-    printf("\tAlpha: %.6f\tProgress: 100.00 %%\n", p.alpha * 0.0001);
+    const bool walk_model = model == "deepwalk" || model == "walklets";
+    const int chunks = (p.mode == SMORE_MODE_HOGWILD && !walk_model && p.total >= 2000000) ? 20 : 1;
+    double last_alpha = p.alpha;
+    for (int c = 0; c < chunks; ++c) {
+        // Hogwild: the run is cut into chunks of one LR schedule so that the reference's progress line can be printed
+        // (LINE.cpp:185); the deterministic mode stays one call (one worker, the reference's exact loop).
+        smore_train_params q = p;
+        if (chunks > 1) {
+            q.total = p.total / chunks;
+            q.sched_total = p.total;
+            q.sched_offset = (uint64_t)c * q.total;
+            q.stream_base = p.stream_base + (uint64_t)c * (1ull << 24);
+        }
+        if (train_once(q)) return die("Train");
+        uint64_t s1 = 0, p1 = 0;
+        double ms1 = 0;
+        smore_train_stats(m, &s1, &p1, nullptr, nullptr, &ms1);
+        samples += s1;
+        pairs += p1;
+        ms += ms1;
+        const double done = (double)(c + 1) / chunks;
+        last_alpha = p.alpha * (1.0 - done);
+        if (last_alpha < p.alpha * 0.0001) last_alpha = p.alpha * 0.0001;
+        if (chunks > 1) {
+            printf("\tAlpha: %.6f\tProgress: %.3f %%%c", last_alpha, done * 100, 13);
+            fflush(stdout);
+        }
+    }
+    printf("\tAlpha: %.6f\tProgress: 100.00 %%\n", last_alpha);
     printf("\t%llu samples, %llu pair updates in %.1f ms on the device (%.1f M updates/s)\n",
            (unsigned long long)samples, (unsigned long long)pairs, ms, ms > 0 ? pairs / ms / 1e3 : 0.0);
 
