@@ -211,7 +211,8 @@ def run_ours(args):
     off, col, ww = csr
     t0 = time.time()
     g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP)
-    sharded = world > 1 and args.parallelism == "sharded"
+    sharded = world > 1 and args.parallelism in ("sharded", "sharded-replica")
+    replica = sharded and args.parallelism == "sharded-replica"
     if sharded:
         # row-sharded store: this rank owns vertices v % world == rank, computes the samples whose positive
         # context it owns, and reaches remote vertex rows over NVLink peer mappings. No data-path collective.
@@ -225,6 +226,8 @@ def run_ours(args):
         from smore_b200 import dist as sdist
 
         sdist.connect_peers(m)
+        if replica:
+            m.enable_replica(0)
         dist.barrier()
 
     def barrier():
@@ -245,6 +248,9 @@ def run_ours(args):
         step_no[0] += 1
         if sharded:
             dist.barrier()  # ranks enter the step together (control plane only)
+        if replica:
+            m.refresh_replica(0)  # pull the authoritative vertex rows (inside the timed region), then everyone trains
+            dist.barrier()
         return m.train_line(p)
 
     # ---- value: inputs resident in HBM ----
@@ -330,7 +336,9 @@ def run_ours(args):
         "config": {"workload": workload_name(g.V, g.E), "updates_per_step_per_gpu": args.batch,
                    "parallelism": "single GPU" if world == 1 else (
                        f"tables row-sharded over {world} GPUs, context-owner computes, remote vertex rows over NVLink "
-                       f"peer mappings (CUDA IPC), no data-path collective" if sharded
+                       f"peer mappings (CUDA IPC), no data-path collective"
+                       + (" [replica mode: vertex rows read from a local replica refreshed every step, deltas pushed with "
+                          "red.global.add]" if replica else "") if sharded
                        else f"{world} independent replicas (weak scaling)"),
                    "l2": "working set (1.0 GB tables + 0.5 GB graph) exceeds the 126 MB L2; no flush between steps"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -360,7 +368,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 24, help="edge updates per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parallelism", default="sharded", choices=["sharded", "replicas"], help="N>1 only")
+    ap.add_argument("--parallelism", default="sharded", choices=["sharded", "sharded-replica", "replicas"], help="N>1 only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

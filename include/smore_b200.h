@@ -143,6 +143,14 @@ int smore_model_open_peers(smore_model_t m, int table, const void* handles);
 /* Same-process variant (several shards on one device, used by tests): raw device pointers indexed by rank. */
 int smore_model_set_peer_ptrs(smore_model_t m, int table, void* const* ptrs);
 
+/* Optional read replica of a row-sharded table (table 0, the vertex table, for LINE): a full-size local copy indexed
+ * by global vertex id. When enabled, smore_train_line reads (and locally updates) vertex rows in the replica and pushes
+ * each row delta to the owner's shard with red.global.add over NVLink: no remote read on the sample's critical path and
+ * half the NVLink bytes, at the price of staleness bounded by the refresh period. smore_model_refresh_replica re-pulls
+ * every row from its owner; all ranks must be outside smore_train_* while any rank refreshes (host-side barrier). */
+int smore_model_enable_replica(smore_model_t m, int table);
+int smore_model_refresh_replica(smore_model_t m, int table);
+
 /* Text writer: "<V> <dim>\n" then `name v0 v1 ...` per vertex in id order, VERTEX table only.
  * format 0 = C++ iostream default (%g, 6 significant digits; src/model/LINE.cpp:13-47),
  * format 1 = Go "%.6f" (internal/models/line/line.go:209-233). */

@@ -31,7 +31,7 @@ EXPORTS = [
     "smore_model_create", "smore_model_init", "smore_model_set_rows", "smore_model_get_rows",
     "smore_model_set_rows_f32", "smore_model_get_rows_f32", "smore_model_device_ptr", "smore_model_destroy",
     "smore_graph_set_shard", "smore_graph_shard_info", "smore_model_ipc_handle", "smore_model_open_peers",
-    "smore_model_set_peer_ptrs", "smore_model_save_weights", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
+    "smore_model_set_peer_ptrs", "smore_model_enable_replica", "smore_model_refresh_replica", "smore_model_save_weights", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
     "smore_train_warp", "smore_train_hoprec", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
 ]
 
@@ -92,6 +92,8 @@ def lib():
         L.smore_model_ipc_handle.argtypes = [vp, C.c_int, vp]
         L.smore_model_open_peers.argtypes = [vp, C.c_int, vp]
         L.smore_model_set_peer_ptrs.argtypes = [vp, C.c_int, vp]
+        L.smore_model_enable_replica.argtypes = [vp, C.c_int]
+        L.smore_model_refresh_replica.argtypes = [vp, C.c_int]
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
         L.smore_train_params_default.restype = None
         for name in ("smore_train_line", "smore_train_bpr", "smore_train_warp", "smore_train_hoprec",
@@ -276,6 +278,12 @@ class Model:
     def set_peer_ptrs(self, table, ptrs):
         arr = (vp * len(ptrs))(*[vp(p) for p in ptrs])
         check(lib().smore_model_set_peer_ptrs(self.h, table, C.cast(arr, vp)))
+
+    def enable_replica(self, table=0):
+        check(lib().smore_model_enable_replica(self.h, table))
+
+    def refresh_replica(self, table=0):
+        check(lib().smore_model_refresh_replica(self.h, table))
 
     def device_ptr(self, table):
         p = vp()

@@ -111,15 +111,15 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
 
 // L2 prefetch of every row of one sample (ids row `pid`: slot 0 lives in the vertex table, the others in the context
 // table). Rows of a peer shard are skipped: peer addresses bypass the local L2.
-template <typename T, class TV>
-__device__ __forceinline__ void prefetch_sample(const TV& tv, const TV& tc, int rank, const int* pid,
+template <typename T, class TV, class TC>
+__device__ __forceinline__ void prefetch_sample(const TV& tv, const TC& tc, int rank, const int* pid,
                                                 int idw, int lane) {
     const int lines_per_row = (tv.dim * (int)sizeof(T) + 127) >> 7;
     const int total = idw * lines_per_row;
     for (int t = lane; t < total; t += 32) {
         const int r = t / lines_per_row, ln = t - r * lines_per_row;
         const int id = pid[r];
-        if (id >= 0 && (id & tv.mask) == rank) {
+        if (id >= 0 && (r == 0 ? (id & tv.mask) == (rank & tv.mask) : (id & tc.mask) == (rank & tc.mask))) {
             const char* p = reinterpret_cast<const char*>(r == 0 ? tv.row(id) : tc.row(id)) + (ln << 7);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
         }
@@ -143,14 +143,23 @@ __device__ __forceinline__ void prefetch_local(const T* Wv, const T* Wc, const i
 // ---------------------------------------------------------------------------------------------------------------
 // LINE: LINE::Train (src/model/LINE.cpp:100-195) / LINE.Train (internal/models/line/line.go:73-150)
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, bool GO, bool STAGED>
+// SHARD: 0 = one GPU; 1 = row-sharded, remote vertex rows staged over NVLink; 2 = row-sharded with a local read replica of
+// the vertex table: rows are read (and updated) in the replica, the delta is pushed to the owner with red.global.add.
+template <class C, bool GO, int SHARD>
 __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
+    constexpr bool STAGED = SHARD == 1;
     using T = typename C::T;
     const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
-    using TV = typename std::conditional<STAGED, TableView<T>, DirectView<T>>::type;
-    TV tv, tc;
-    if constexpr (STAGED) stage_views<T>(a, tv, tc);
-    else {
+    using TV = typename std::conditional<SHARD == 1, TableView<T>, DirectView<T>>::type;
+    using TC = typename std::conditional<SHARD != 0, TableView<T>, DirectView<T>>::type;
+    TV tv;
+    TC tc;
+    TableView<T> owner_v{};  // SHARD == 2: where the vertex deltas are pushed
+    if constexpr (SHARD == 1) stage_views<T>(a, tv, tc);
+    else if constexpr (SHARD == 2) {
+        stage_views<T>(a, owner_v, tc);
+        tv = DirectView<T>{a.replica_v, a.dim};
+    } else {
         tv = DirectView<T>{a.Wv, a.dim};
         tc = DirectView<T>{a.Wc, a.dim};
     }
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             }
         }
         for (int s = 0; s < nb; ++s) {
-            if (s + kLinePrefetch < nb) prefetch_sample<T, TV>(tv, tc, a.g.shard_rank, b.ids + (s + kLinePrefetch) * b.idw, b.idw, lane);
+            if (s + kLinePrefetch < nb) prefetch_sample<T>(tv, tc, a.g.shard_rank, b.ids + (s + kLinePrefetch) * b.idw, b.idw, lane);
             const int* sid = b.ids + s * b.idw;
             const int v1 = sid[0];
             const int v2 = sid[1];
@@ -200,8 +209,11 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             }
             if (v2 < 0) continue;
             const T alpha = (T)st.alpha;
-            if (!GO) update_pair_cpp<C>(tv, tc, a.dim, a.same_table != 0, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr);
-            else update_pair_go<C>(tv, tc, a.dim, a.same_table != 0, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr);
+            T* vpush = nullptr;
+            if constexpr (SHARD == 2) vpush = owner_v.row(v1);
+            const bool same = SHARD == 2 ? false : a.same_table != 0;  // replica rows never alias shard rows in memory
+            if (!GO) update_pair_cpp<C>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
+            else update_pair_go<C>(tv, tc, a.dim, same, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
             st.count++;
             st.pairs++;
             sched_tick(st, a.sched);

@@ -356,6 +356,29 @@ __device__ __forceinline__ void pin(Row<C>& r) {
     }
 }
 
+// Fire-and-forget accumulation of a row delta into (possibly peer-mapped) memory: red.global.add, performed by the L2 of
+// the GPU that owns the row (atomics travel over NVLink), so concurrent pushes from several GPUs never lose an update.
+__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+template <class C>
+__device__ __forceinline__ void row_red_add(typename C::T* base, const Row<C>& delta, int lane, int dim) {
+#pragma unroll
+    for (int c = 0; c < C::NCH; ++c) {
+        int idx = (c * 32 + lane) * C::VEC;
+        if (!C::MASKED || idx < dim) {
+            if constexpr (sizeof(typename C::T) == 4 && C::VEC == 4) {
+                red_add4(base + idx, delta.x[c * 4], delta.x[c * 4 + 1], delta.x[c * 4 + 2], delta.x[c * 4 + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < C::VEC; ++j) red_add(base + idx + j, delta.x[c * C::VEC + j]);
+            }
+        }
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

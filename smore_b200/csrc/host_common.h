@@ -92,6 +92,7 @@ struct smore_model_s {
     int64_t rows = 0;                          // rows held locally (V when not sharded)
     void* peer[2][kMaxWorld] = {};             // shard bases per rank (peer[t][rank] == tab[t])
     bool peer_opened[2][kMaxWorld] = {};       // CUDA-IPC mappings to close
+    void* replica[2] = {nullptr, nullptr};     // optional full-size local read replica of a sharded table
     WarpState* d_state = nullptr;
     int state_cap = 0;
     int32_t* d_keys = nullptr;
@@ -105,6 +106,7 @@ struct smore_model_s {
             for (int r = 0; r < kMaxWorld; ++r)
                 if (peer_opened[t][r]) cudaIpcCloseMemHandle(peer[t][r]);
         cudaFree(tab[0]); cudaFree(tab[1]); cudaFree(d_state); cudaFree(d_keys);
+        cudaFree(replica[0]); cudaFree(replica[1]);
     }
 };
 

@@ -32,6 +32,7 @@ struct TrainArgs {
     T* peer_v[kMaxWorld];  // rank r's shard of the vertex / context table (peer_x[rank] == Wx)
     T* peer_c[kMaxWorld];
     int world_shift, world_mask;
+    T* replica_v;  // row-sharded + replica mode: full-size local read copy of the vertex table (global ids), else null
     int dim;
     int same_table;  // Wv == Wc
     const T* lut;    // 1001-entry sigmoid table in global memory (copied to shared)
@@ -53,11 +54,12 @@ struct TrainArgs {
 // skip-gram pair update, C++ semantics: proNet::UpdatePair + Opt_SigmoidSGD (src/proNet.cpp:1784-1809, :1312-1330).
 // my_id: lane 0 holds the positive context, lane 1+n negative n; nrows = K+1 <= 32.
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, class TV>
+template <class C, class TV, class TC>
 __device__ __forceinline__ void update_pair_cpp(const TV& tv,
-                                                const TV& tc, int dim, bool same_table,
+                                                const TC& tc, int dim, bool same_table,
                                                 const typename C::T* lut, int v1, int my_id, int nrows,
-                                                typename C::T alpha, int lane, const Row<C>* vpre = nullptr) {
+                                                typename C::T alpha, int lane, const Row<C>* vpre = nullptr,
+                                                typename C::T* vpush = nullptr) {
     using T = typename C::T;
     using A = Ar<T>;
     bool active = lane < nrows;
@@ -96,6 +98,7 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
 #pragma unroll
         for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
         v.store(pv, lane, dim);
+        if (vpush) row_red_add<C>(vpush, back, lane, dim);  // replica mode: the delta also goes to the owner's row
     } else {
         Row<C> back;
         back.zero();
@@ -120,6 +123,7 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
 #pragma unroll
         for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
         v.store(pv, lane, dim);
+        if (vpush) row_red_add<C>(vpush, back, lane, dim);
     }
 }
 
@@ -128,11 +132,12 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
 // skip_source, LINE.updateFirstOrder (internal/models/line/line.go:153-200). Negatives equal to the context (or the
 // source) are skipped; the positive context row is written last.
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, class TV>
+template <class C, class TV, class TC>
 __device__ __forceinline__ void update_pair_go(const TV& tv,
-                                                const TV& tc, int dim, bool same_table,
+                                                const TC& tc, int dim, bool same_table,
                                                bool skip_source, const typename C::T* lut, int v1, int my_id,
-                                               int nrows, typename C::T alpha, int lane, const Row<C>* vpre = nullptr) {
+                                               int nrows, typename C::T alpha, int lane, const Row<C>* vpre = nullptr,
+                                               typename C::T* vpush = nullptr) {
     using T = typename C::T;
     using A = Ar<T>;
     int ctx = __shfl_sync(kFull, my_id, 0);
@@ -190,6 +195,7 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
         }
         v.store(pv, lane, dim);
         pos.store(pp, lane, dim);
+        if (vpush) row_red_add<C>(vpush, vgrad, lane, dim);
     } else {
         Row<C> vgrad, cgrad;
         {
@@ -225,6 +231,7 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
 #pragma unroll
         for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], vgrad.x[e]);
         v.store(pv, lane, dim);
+        if (vpush) row_red_add<C>(vpush, vgrad, lane, dim);
         Row<C> pos;
         pos.load(pp, lane, dim);
 #pragma unroll
@@ -486,6 +493,30 @@ __global__ void k_init_table(T* W, int64_t n_elems, int dim, uint64_t seed, uint
         const uint32_t lane = (uint32_t)(ge & 3);
         const uint32_t k = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
         W[i] = (T)(((double)k * (1.0 / 4294967296.0) - 0.5) / (double)dim);
+    }
+}
+
+// Replica refresh: every row of the full-size local replica is pulled from its owner's shard (peer loads over NVLink for
+// remote shards), 128 bits per thread. Row bytes must be a multiple of 16.
+template <typename T>
+struct PeerBases {
+    T* b[kMaxWorld];
+};
+template <typename T>
+__global__ void k_refresh_replica(T* replica, PeerBases<T> bases, int shift, int mask, int dim, int64_t V) {
+    const int64_t n_vec = (int64_t)dim * (int64_t)sizeof(T) / 16;
+    const int64_t total = V * n_vec;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int64_t v = i / n_vec, k = i - v * n_vec;
+        const int r = (int)(v & mask);
+        T* src_base = bases.b[0];
+#pragma unroll
+        for (int q = 1; q < kMaxWorld; ++q)
+            if (q == r) src_base = bases.b[q];
+        const uint4* src = reinterpret_cast<const uint4*>(src_base + (size_t)(v >> shift) * dim) + k;
+        reinterpret_cast<uint4*>(replica + (size_t)v * dim)[k] = __ldcg(src);
     }
 }
 

@@ -516,6 +516,41 @@ int smore_model_open_peers(smore_model_t m, int table, const void* handles) {
     return SMORE_OK;
 }
 
+int smore_model_enable_replica(smore_model_t m, int table) {
+    if (!m || table < 0 || table >= m->n_tables) return fail(SMORE_E_INVALID, "bad model/table");
+    if (m->g->world == 1) return fail(SMORE_E_INVALID, "replicas only make sense on a row-sharded graph");
+    if (((size_t)m->dim * m->elem()) % 16) return fail(SMORE_E_UNSUPPORTED, "replica rows must be a multiple of 16 bytes");
+    if (int rc = ensure_device()) return rc;
+    if (!m->replica[table]) {
+        size_t bytes = (size_t)m->g->V * (size_t)m->dim * m->elem();
+        cudaError_t e = cudaMalloc(&m->replica[table], bytes);
+        if (e != cudaSuccess) return fail(SMORE_E_NOMEM, "cudaMalloc of %zu bytes for the replica failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return SMORE_OK;
+}
+
+int smore_model_refresh_replica(smore_model_t m, int table) {
+    if (!m || table < 0 || table >= m->n_tables || !m->replica[table]) return fail(SMORE_E_INVALID, "no replica enabled for this table");
+    for (int r = 0; r < m->g->world; ++r)
+        if (!m->peer[table][r]) return fail(SMORE_E_INVALID, "shard of rank %d not connected", r);
+    if (int rc = ensure_device()) return rc;
+    const int64_t n_vec = m->g->V * (((int64_t)m->dim * (int64_t)m->elem()) / 16);
+    const int blocks = (int)std::min<int64_t>((n_vec + 255) / 256, 148 * 16);
+    if (m->dtype == SMORE_F64) {
+        PeerBases<double> pb;
+        for (int r = 0; r < kMaxWorld; ++r) pb.b[r] = (double*)m->peer[table][r];
+        k_refresh_replica<double><<<blocks, 256>>>((double*)m->replica[table], pb, m->g->shift, m->g->world - 1, m->dim, m->g->V);
+    } else {
+        PeerBases<float> pb;
+        for (int r = 0; r < kMaxWorld; ++r) pb.b[r] = (float*)m->peer[table][r];
+        k_refresh_replica<float><<<blocks, 256>>>((float*)m->replica[table], pb, m->g->shift, m->g->world - 1, m->dim, m->g->V);
+    }
+    g_launches++;
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return SMORE_OK;
+}
+
 int smore_model_set_peer_ptrs(smore_model_t m, int table, void* const* ptrs) {
     if (!m || table < 0 || table >= m->n_tables || !ptrs) return fail(SMORE_E_INVALID, "bad argument");
     for (int r = 0; r < m->g->world; ++r)

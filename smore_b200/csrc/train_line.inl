@@ -7,11 +7,12 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
     return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
         using C = decltype(cfg);
         const bool cpp = p->semantics == SMORE_SEM_CPP;
-        const bool sharded = m->g->world > 1;
-        void (*kern)(TrainArgs<T>) = cpp ? (sharded ? k_line<C, false, true> : k_line<C, false, false>)
-                                         : (sharded ? k_line<C, true, true> : k_line<C, true, false>);
+        const int shard = m->g->world == 1 ? 0 : (m->replica[vtab] ? 2 : 1);
+        void (*kern)(TrainArgs<T>) =
+            cpp ? (shard == 2 ? k_line<C, false, 2> : shard == 1 ? k_line<C, false, 1> : k_line<C, false, 0>)
+                : (shard == 2 ? k_line<C, true, 2> : shard == 1 ? k_line<C, true, 1> : k_line<C, true, 0>);
         const size_t smem = batch_smem_bytes<T>(m->g->world > 1 ? 2 : cpp ? 0 : 1, p->negative_samples,
-                                                m->g->world > 1 ? C::EPL * 32 : 0);
+                                                shard == 1 ? C::EPL * 32 : 0);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
@@ -25,6 +26,7 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
         TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)total_local, cpp ? 1 : 0, vtab, ctab,
                                       m->g->world == 1 ? 1.0 : m->g->src_mass_frac);
         a.jobs = trips;
+        a.replica_v = (T*)m->replica[vtab];
         Timer t;
         if (int rc = t.start()) return rc;
         kern<<<L.blocks, kBlockThreads, smem>>>(a);

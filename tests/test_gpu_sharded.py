@@ -132,6 +132,50 @@ def test_sharded_training_quality_matches_unsharded():
     assert abs(sh_rec - base_rec) < 0.005 + 0.05 * base_rec
 
 
+def test_replica_mode_quality_matches_unsharded():
+    """Replica + gradient-push mode (vertex rows read from a local replica refreshed once per round, deltas pushed to the
+    owner with red.global.add): same quality gate as the peer-access mode."""
+    off, col, ww, test_s, test_d, train_adj = _sbm()
+    V, dim, total = len(off) - 1, 32, 12_000_000
+    init = ((np.random.default_rng(1).random((V, dim)) - 0.5) / dim)
+    g = capi.Graph.from_csr(off, col, ww)
+    m = capi.Model(g, dim, 2, capi.F32)
+    m.set_rows(0, init), m.set_rows(1, np.zeros((V, dim)))
+    m.train_line(_params(total, 13))
+    base_auc, base_rec = evaluate(m.get_rows(0), m.get_rows(1), test_s, test_d, train_adj, np.random.default_rng(2))
+    world, rounds = 4, 20
+    ms = []
+    for r in range(world):
+        gr = capi.Graph.from_csr(off, col, ww)
+        gr.set_shard(r, world)
+        mr = capi.Model(gr, dim, 2, capi.F32)
+        rows = sdist.owned_rows(V, r, world)
+        mr.set_rows(0, init[rows]), mr.set_rows(1, np.zeros((len(rows), dim)))
+        ms.append(mr)
+    for t in range(2):
+        ptrs = [mr.device_ptr(t) for mr in ms]
+        for mr in ms:
+            mr.set_peer_ptrs(t, ptrs)
+    for mr in ms:
+        mr.enable_replica(0)
+    for k in range(rounds):
+        for mr in ms:
+            mr.refresh_replica(0)  # every rank re-pulls the authoritative rows, then all ranks train one round
+        for r, mr in enumerate(ms):
+            p = _params(total // rounds, 100 + k)
+            p.stream_base = r * (1 << 20)
+            p.sched_total, p.sched_offset = total, k * (total // rounds)
+            mr.train_line(p)
+    Wv, Wc = np.zeros((V, dim)), np.zeros((V, dim))
+    for r, mr in enumerate(ms):
+        rows = sdist.owned_rows(V, r, world)
+        Wv[rows], Wc[rows] = mr.get_rows(0), mr.get_rows(1)
+    auc_, rec_ = evaluate(Wv, Wc, test_s, test_d, train_adj, np.random.default_rng(2))
+    print(f"AUC unsharded {base_auc:.4f} replica-mode(4) {auc_:.4f} | recall@10 {base_rec:.4f} vs {rec_:.4f}")
+    assert abs(auc_ - base_auc) < 0.005
+    assert abs(rec_ - base_rec) < 0.005 + 0.05 * base_rec
+
+
 def _ipc_worker(rank, world, port, out):
     import torch.distributed as dist
 
