@@ -204,6 +204,8 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: smore_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout must carry exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.check(capi.lib().smore_init(local))
 
