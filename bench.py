@@ -56,6 +56,42 @@ def make_graph(scale=1.0):
     return (src, dst, w), (off, col, ww)
 
 
+def make_graph_torch(scale, device):
+    """Same generator as smore_b200.synth.power_law_edges + csr_from_edges(undirected), on the GPU (multi-GPU runs scale
+    the graph with the number of GPUs; 80M edges are generated in about a second instead of minutes of numpy). Vertex ids
+    are the labels themselves (no first-appearance relabelling: nothing is compared with the reference at N > 1)."""
+    import torch
+
+    t0 = time.time()
+    nv, ne = int(V_TARGET * scale), int(N_EDGES * scale)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(GRAPH_SEED)
+    p = torch.arange(1, nv + 1, device=device, dtype=torch.float64) ** (-1.0 / 1.5)
+    cdf = torch.cumsum(p, 0)
+    cdf /= cdf[-1].clone()
+    perm = torch.randperm(nv, device=device, generator=gen)
+
+    def endpoints():
+        u = torch.rand(ne, device=device, dtype=torch.float64, generator=gen)
+        return perm[torch.searchsorted(cdf, u, right=True).clamp_(max=nv - 1)]
+
+    src, dst = endpoints(), endpoints()
+    w = torch.randint(1, 6, (ne,), device=device, generator=gen).to(torch.float64)
+    es = torch.stack([src, dst], 1).reshape(-1)
+    ed = torch.stack([dst, src], 1).reshape(-1)
+    ew = torch.stack([w, w], 1).reshape(-1)
+    order = torch.argsort(es, stable=True)
+    col = ed[order].to(torch.int32).cpu().numpy()
+    ww = ew[order].cpu().numpy()
+    off = torch.zeros(nv + 1, dtype=torch.int64, device=device)
+    off[1:] = torch.cumsum(torch.bincount(es, minlength=nv), 0)
+    off = off.cpu().numpy()
+    del src, dst, w, es, ed, ew, order, perm, cdf, p
+    torch.cuda.empty_cache()
+    log(f"[bench] graph (torch/GPU): V={nv} E={len(col)} generated in {time.time() - t0:.1f}s")
+    return None, (off, col, ww)
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -209,11 +245,19 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.check(capi.lib().smore_init(local))
 
-    edges, csr = make_graph(args.scale)
+    sharded = world > 1 and args.parallelism in ("sharded", "sharded-replica")
+    # N > 1, sharded: TRUE weak scaling -- vertices, edges and updates per GPU stay fixed, so the graph grows with N
+    # (1M vertices / 10M edges per GPU; at N = 8 that is 8M vertices, 80M edges, 160M adjacency entries). On a fixed
+    # graph the global update rate of N GPUs concentrates on the same hub rows and the run measures same-line write
+    # serialisation in one GPU's L2 instead of the sharded store; --fixed-graph keeps configs[1] as is.
+    grow = sharded and not args.fixed_graph
+    if grow:
+        edges, csr = make_graph_torch(args.scale * world, torch.device("cuda", local))
+    else:
+        edges, csr = make_graph(args.scale)
     off, col, ww = csr
     t0 = time.time()
     g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP)
-    sharded = world > 1 and args.parallelism in ("sharded", "sharded-replica")
     replica = sharded and args.parallelism == "sharded-replica"
     if sharded:
         # row-sharded store: this rank owns vertices v % world == rank, computes the samples whose positive
@@ -335,14 +379,16 @@ def run_ours(args):
         "metric": "edge_updates_per_sec", "value": updates / (ms * 1e-3), "unit": "updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(g.V, g.E), "updates_per_step_per_gpu": args.batch,
+        "config": {"workload": workload_name(g.V, g.E) + (
+                       f" -- graph grown with the GPU count ({V_TARGET} vertices / {N_EDGES} edge lines per GPU)" if grow else ""),
+                   "updates_per_step_per_gpu": args.batch,
                    "parallelism": "single GPU" if world == 1 else (
                        f"tables row-sharded over {world} GPUs, context-owner computes, remote vertex rows over NVLink "
                        f"peer mappings (CUDA IPC), no data-path collective"
                        + (" [replica mode: vertex rows read from a local replica refreshed every step, deltas pushed with "
                           "red.global.add]" if replica else "") if sharded
                        else f"{world} independent replicas (weak scaling)"),
-                   "l2": "working set (1.0 GB tables + 0.5 GB graph) exceeds the 126 MB L2; no flush between steps"},
+                   "l2": "working set per GPU (1.0 GB of table rows + >= 0.5 GB graph) exceeds the 126 MB L2; no flush between steps"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "k_line<float,4,1>", "algorithmic_bytes_per_update": ALGO_BYTES,
                      "peak_source": peak_src},
@@ -370,6 +416,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 24, help="edge updates per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fixed-graph", action="store_true", help="N>1: keep the configs[1] graph instead of growing it with N")
     ap.add_argument("--parallelism", default="sharded", choices=["sharded", "sharded-replica", "replicas"], help="N>1 only")
     args = ap.parse_args()
     if args.impl == "reference":
