@@ -246,11 +246,11 @@ def run_ours(args):
     capi.check(capi.lib().smore_init(local))
 
     sharded = world > 1 and args.parallelism in ("sharded", "sharded-replica")
-    # N > 1, sharded: TRUE weak scaling -- vertices, edges and updates per GPU stay fixed, so the graph grows with N
-    # (1M vertices / 10M edges per GPU; at N = 8 that is 8M vertices, 80M edges, 160M adjacency entries). On a fixed
-    # graph the global update rate of N GPUs concentrates on the same hub rows and the run measures same-line write
-    # serialisation in one GPU's L2 instead of the sharded store; --fixed-graph keeps configs[1] as is.
-    grow = sharded and not args.fixed_graph
+    # N > 1, sharded: by default every N runs the SAME configs[1] graph (updates per GPU fixed: weak scaling in work).
+    # --grow-graph grows the graph with N instead (1M vertices / 10M edges per GPU, generated on the GPU). Measured
+    # (DESIGN.md section 7): growing helps at 2 GPUs (hub rows are hit half as often per second) but the randomly accessed
+    # PEER footprint then grows too, and fine-grained peer access falls off a cliff beyond ~1 GB of peer rows.
+    grow = sharded and args.grow_graph
     if grow:
         edges, csr = make_graph_torch(args.scale * world, torch.device("cuda", local))
     else:
@@ -416,7 +416,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 24, help="edge updates per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fixed-graph", action="store_true", help="N>1: keep the configs[1] graph instead of growing it with N")
+    ap.add_argument("--grow-graph", action="store_true", help="N>1: grow the graph with N (1M vertices per GPU)")
     ap.add_argument("--parallelism", default="sharded", choices=["sharded", "sharded-replica", "replicas"], help="N>1 only")
     args = ap.parse_args()
     if args.impl == "reference":
