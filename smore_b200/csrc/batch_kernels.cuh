@@ -212,8 +212,8 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             T* vpush = nullptr;
             if constexpr (SHARD == 2) vpush = owner_v.row(v1);
             const bool same = SHARD == 2 ? false : a.same_table != 0;  // replica rows never alias shard rows in memory
-            if (!GO) update_pair_cpp<C>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
-            else update_pair_go<C>(tv, tc, a.dim, same, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
+            if (!GO) update_pair_cpp<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
+            else update_pair_go<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
             st.count++;
             st.pairs++;
             sched_tick(st, a.sched);

@@ -54,7 +54,8 @@ struct TrainArgs {
 // skip-gram pair update, C++ semantics: proNet::UpdatePair + Opt_SigmoidSGD (src/proNet.cpp:1784-1809, :1312-1330).
 // my_id: lane 0 holds the positive context, lane 1+n negative n; nrows = K+1 <= 32.
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, class TV, class TC>
+// CTX_CA: gather the context rows with ld.global.ca (hub rows served from L1; used when sharding concentrates them)
+template <class C, class TV, class TC, bool CTX_CA = false>
 __device__ __forceinline__ void update_pair_cpp(const TV& tv,
                                                 const TC& tc, int dim, bool same_table,
                                                 const typename C::T* lut, int v1, int my_id, int nrows,
@@ -77,7 +78,10 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
 #pragma unroll
             for (int r = 0; r < kCtxChunk; ++r) {
                 ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
-                if (base + r < nrows) c[r].load(tc.row(ids[r]), lane, dim);
+                if (base + r < nrows) {
+                    if constexpr (CTX_CA) c[r].load_ca(tc.row(ids[r]), lane, dim);
+                    else c[r].load(tc.row(ids[r]), lane, dim);
+                }
             }
             T f[kCtxChunk];
             dots<C, kCtxChunk>(v, c, nrows - base, f);
@@ -132,7 +136,7 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
 // skip_source, LINE.updateFirstOrder (internal/models/line/line.go:153-200). Negatives equal to the context (or the
 // source) are skipped; the positive context row is written last.
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, class TV, class TC>
+template <class C, class TV, class TC, bool CTX_CA = false>
 __device__ __forceinline__ void update_pair_go(const TV& tv,
                                                 const TC& tc, int dim, bool same_table,
                                                bool skip_source, const typename C::T* lut, int v1, int my_id,
@@ -153,7 +157,8 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
         Row<C> v, vgrad, pos, cgrad;
         if (vpre) v = *vpre;
         else v.load(pv, lane, dim);
-        pos.load(pp, lane, dim);
+        if constexpr (CTX_CA) pos.load_ca(pp, lane, dim);
+        else pos.load(pp, lane, dim);
         {
             T g = A::mul(alpha, A::sub((T)1, fast_sigmoid<T>(lut, dot(v, pos))));  // alpha * (label - pred)
 #pragma unroll
@@ -170,7 +175,10 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
             for (int r = 0; r < kCtxChunk; ++r) {
                 ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
                 ok[r] = (base + r < nrows) && !((skipmask >> ((base + r) & 31)) & 1u);
-                if (ok[r]) c[r].load(tc.row(ids[r]), lane, dim);
+                if (ok[r]) {
+                    if constexpr (CTX_CA) c[r].load_ca(tc.row(ids[r]), lane, dim);
+                    else c[r].load(tc.row(ids[r]), lane, dim);
+                }
                 else c[r].zero();
             }
             T f[kCtxChunk];
