@@ -122,6 +122,22 @@ def main():
             # per hop: user + item + 5 negatives read, up to all 7 written: counted per FBPR round-group ("pair_updates"/5)
             run(f"hoprec_d{dim}_big", m, m.train_hoprec, p, 5 * 14 * dim * 4, "samples", a.steps, a.warmup)
 
+    # ---- configs[1] under Go semantics (CDF-scan neighbour sampling -> binary search over prefix sums, random contexts) ----
+    if want("line_go") or want("line_cpp"):
+        nv = int(1_000_000 * a.scale)
+        src, dst, w = synth.power_law_edges(nv, 10 * nv, 20261018)
+        off, col, ww, _ = synth.csr_from_edges(src, dst, w, True)
+        for nm, sem in (("line_cpp", capi.SEM_CPP), ("line_go", capi.SEM_GO)):
+            if not want(nm):
+                continue
+            g = capi.Graph.from_csr(off, col, ww, semantics=sem, n_lines=len(src) if sem == capi.SEM_GO else 0)
+            m = capi.Model(g, 128, 2, capi.F32)
+            m.init(0, True, 1), m.init(1, sem == capi.SEM_GO, 2)
+            p = capi.default_params()
+            p.semantics, p.mode, p.seed, p.total = sem, capi.MODE_HOGWILD, 1, 1 << 24
+            run(f"{nm}_d128_c2", m, m.train_line, p, 2 * 7 * 128 * 4 + 76, "samples", a.steps, a.warmup)
+            del m, g
+
     # ---- configs[2]: DeepWalk dim 128, walk_steps 40, window 5 (V scaled; one epoch slice per step) ----
     if want("deepwalk") or want("walklets"):
         nv = int(1_000_000 * a.scale)
