@@ -151,6 +151,28 @@ int smore_model_set_peer_ptrs(smore_model_t m, int table, void* const* ptrs);
 int smore_model_enable_replica(smore_model_t m, int table);
 int smore_model_refresh_replica(smore_model_t m, int table);
 
+/* Bulk-exchange mode of a row-sharded model (LINE): for graphs whose remote working set is too large for fine-grained
+ * peer access (random 512-byte accesses to peer memory collapse once a few GB of peer rows are touched).
+ * Training then proceeds in super-batches of `superbatch` samples per rank (<= 0: 2^20). Per super-batch a rank (1) files
+ * the remote vertex rows its samples will need (the sampler is counter-based, so the sources are known before the
+ * update runs) in per-owner request lists, (2) the lists, the requested rows and -- after the updates -- the modified
+ * rows travel as contiguous buffers in three all-to-alls (NCCL send/recv groups over NVLink), (3) the owner adds
+ * `returned - sent` to its row. No kernel dereferences a peer pointer: smore_model_open_peers is not needed.
+ * Replaces nothing in the reference (its tables live in one address space); it is the "NCCL all-to-all carries the
+ * remote-row batches" half of the sharded store, next to the peer-access half above. */
+int smore_model_enable_exchange(smore_model_t m, int64_t superbatch);
+/* NCCL bootstrap for the exchange mode with one process per GPU: rank 0 creates the 128-byte ncclUniqueId, the host
+ * broadcasts it with its own transport, every rank calls init (after smore_init). libnccl.so.2 is dlopen()ed here. */
+int smore_dist_nccl_unique_id(void* id128);
+int smore_dist_nccl_init(const void* id128, int rank, int world);
+int smore_dist_nccl_shutdown(void);
+/* Same algorithm with every shard in the calling process (several shards on one device; tests and single-GPU
+ * experiments): shards[r] must be rank r of n, all with the exchange mode enabled; plain device copies replace NCCL.
+ * Shard r draws from streams stream_base + (r << 20) + warp. */
+int smore_train_line_group(const smore_model_t* shards, int n, const smore_train_params* p);
+/* Counters of the last exchange-mode train call: super-batches run, remote vertex rows requested (after dedup). */
+int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows_requested);
+
 /* Text writer: "<V> <dim>\n" then `name v0 v1 ...` per vertex in id order, VERTEX table only.
  * format 0 = C++ iostream default (%g, 6 significant digits; src/model/LINE.cpp:13-47),
  * format 1 = Go "%.6f" (internal/models/line/line.go:209-233). */
@@ -180,7 +202,9 @@ typedef struct {
 void smore_train_params_default(smore_train_params* p);
 
 /* LINE::Train (src/model/LINE.cpp:100-195) / LINE.Train (internal/models/line/line.go:73-150):
- * SourceSample -> TargetSample -> UpdatePair (1 + K context rows), LR decay every 10000 samples. */
+ * SourceSample -> TargetSample -> UpdatePair (1 + K context rows), LR decay every 10000 samples.
+ * On a row-sharded model with the exchange mode enabled this call is COLLECTIVE: every rank must make it with the same
+ * `total` (each runs its share in the same number of super-batches). */
 int smore_train_line(smore_model_t m, const smore_train_params* p);
 /* BPR::Train (src/model/BPR.cpp:55-107, 5-negative UpdateBPRPair proNet.cpp:1406-1455) /
  * BPR.Train (internal/models/bpr/bpr.go:61-131, optimizer.go:87-117). */

@@ -31,7 +31,9 @@ EXPORTS = [
     "smore_model_create", "smore_model_init", "smore_model_set_rows", "smore_model_get_rows",
     "smore_model_set_rows_f32", "smore_model_get_rows_f32", "smore_model_device_ptr", "smore_model_destroy",
     "smore_graph_set_shard", "smore_graph_shard_info", "smore_model_ipc_handle", "smore_model_open_peers",
-    "smore_model_set_peer_ptrs", "smore_model_enable_replica", "smore_model_refresh_replica", "smore_model_save_weights", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
+    "smore_model_set_peer_ptrs", "smore_model_enable_replica", "smore_model_refresh_replica",
+    "smore_model_enable_exchange", "smore_dist_nccl_unique_id", "smore_dist_nccl_init", "smore_dist_nccl_shutdown",
+    "smore_train_line_group", "smore_exchange_stats", "smore_model_save_weights", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
     "smore_train_warp", "smore_train_hoprec", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
 ]
 
@@ -94,6 +96,12 @@ def lib():
         L.smore_model_set_peer_ptrs.argtypes = [vp, C.c_int, vp]
         L.smore_model_enable_replica.argtypes = [vp, C.c_int]
         L.smore_model_refresh_replica.argtypes = [vp, C.c_int]
+        L.smore_model_enable_exchange.argtypes = [vp, i64]
+        L.smore_dist_nccl_unique_id.argtypes = [vp]
+        L.smore_dist_nccl_init.argtypes = [vp, C.c_int, C.c_int]
+        L.smore_dist_nccl_shutdown.argtypes = []
+        L.smore_train_line_group.argtypes = [vp, C.c_int, C.POINTER(TrainParams)]
+        L.smore_exchange_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
         L.smore_train_params_default.restype = None
         for name in ("smore_train_line", "smore_train_bpr", "smore_train_warp", "smore_train_hoprec",
@@ -118,6 +126,28 @@ def default_params() -> TrainParams:
     p = TrainParams()
     lib().smore_train_params_default(C.byref(p))
     return p
+
+
+def train_line_group(models, p):
+    """All shards of one row-sharded model in this process (exchange mode, device copies instead of NCCL)."""
+    arr = (vp * len(models))(*[m.h for m in models])
+    check(lib().smore_train_line_group(C.cast(arr, vp), len(models), C.byref(p)))
+    return [m.stats() for m in models]
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_ubyte * 128)()
+    check(lib().smore_dist_nccl_unique_id(C.cast(buf, vp)))
+    return bytes(buf)
+
+
+def nccl_init(uid: bytes, rank: int, world: int):
+    buf = (C.c_ubyte * 128).from_buffer_copy(uid)
+    check(lib().smore_dist_nccl_init(C.cast(buf, vp), rank, world))
+
+
+def nccl_shutdown():
+    check(lib().smore_dist_nccl_shutdown())
 
 
 def kernel_launches() -> int:
@@ -284,6 +314,15 @@ class Model:
 
     def refresh_replica(self, table=0):
         check(lib().smore_model_refresh_replica(self.h, table))
+
+    def enable_exchange(self, superbatch=0):
+        """Bulk-exchange mode (row-sharded LINE): remote vertex rows move in per-super-batch all-to-alls."""
+        check(lib().smore_model_enable_exchange(self.h, superbatch))
+
+    def exchange_stats(self):
+        sb, rows = u64(), u64()
+        check(lib().smore_exchange_stats(self.h, C.byref(sb), C.byref(rows)))
+        return {"superbatches": sb.value, "rows_requested": rows.value}
 
     def device_ptr(self, table):
         p = vp()

@@ -119,7 +119,8 @@ __device__ __forceinline__ void prefetch_sample(const TV& tv, const TC& tc, int 
     for (int t = lane; t < total; t += 32) {
         const int r = t / lines_per_row, ln = t - r * lines_per_row;
         const int id = pid[r];
-        if (id >= 0 && (r == 0 ? (id & tv.mask) == (rank & tv.mask) : (id & tc.mask) == (rank & tc.mask))) {
+        // (a negative id in slot 0 is a staging row of the exchange mode: ExchView; negative elsewhere = no row)
+        if (r == 0 ? (id < 0 || (id & tv.mask) == (rank & tv.mask)) : (id >= 0 && (id & tc.mask) == (rank & tc.mask))) {
             const char* p = reinterpret_cast<const char*>(r == 0 ? tv.row(id) : tc.row(id)) + (ln << 7);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
         }
@@ -141,22 +142,120 @@ __device__ __forceinline__ void prefetch_local(const T* Wv, const T* Wc, const i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Bulk-exchange mode (row-sharded LINE on graphs whose remote working set is too large for fine-grained peer access).
+// Per super-batch and rank:   k_line_requests  -> all-to-all(request lists) -> k_gather_rows -> all-to-all(rows)
+//                          -> k_line<.., 3>    -> all-to-all(rows back)     -> k_apply_delta
+// The sampler is counter-based, so k_line_requests simply re-derives the SOURCE of every sample the update kernel is
+// about to draw (same stream words) -- no id list goes through HBM.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t exch_hash(int v) {
+    uint32_t h = (uint32_t)v * 0x9E3779B1u;
+    return h ^ (h >> 15);
+}
+
+// Returns the staging row of remote vertex v1 (filed by k_line_requests in an earlier launch).
+__device__ __forceinline__ int exch_lookup(const ExchDev& x, int v1) {
+    uint32_t h = exch_hash(v1) & x.hmask;
+    while (__ldg(x.hkey + h) != v1) h = (h + 1) & x.hmask;
+    const int hv = __ldg(x.hval + h);
+    return __ldg(x.off + (hv >> 28)) + (hv & 0x0fffffff);
+}
+
+// One lane per sample: words [pos0 + s*wps, +2) of the warp's stream -> edge draw -> source vertex; remote sources are
+// inserted into the hash, the lane that creates an entry appends the row to the owner's request list. Must be launched
+// with the grid, `jobs`, seed and stream_base of the k_line<.., 3> launch that follows; the warp states are not advanced.
+static __global__ void __launch_bounds__(kBlockThreads) k_line_requests(GraphDev g, ExchDev x, const WarpState* state,
+                                                                        int n_warps, uint64_t jobs, uint64_t seed,
+                                                                        uint64_t stream_base, int K) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (w >= n_warps) return;
+    const uint64_t pos0 = state[w].pos;
+    const uint64_t stream = stream_base + (uint64_t)w;
+    const uint64_t wps = (uint64_t)batch_wps(2, K);
+    const int mask = (1 << g.shard_shift) - 1;
+    for (uint64_t s = lane; s < jobs; s += 32) {
+        const uint64_t p0 = pos0 + s * wps;
+        const U4 b0 = philox_block(seed, stream, p0 >> 2);
+        const uint32_t sel = (uint32_t)p0 & 3u;
+        uint32_t w0 = sel == 0 ? b0.x : sel == 1 ? b0.y : sel == 2 ? b0.z : b0.w;
+        uint32_t w1 = sel == 0 ? b0.y : sel == 1 ? b0.z : b0.w;
+        if (sel == 3) w1 = philox_block(seed, stream, (p0 >> 2) + 1).x;
+        const uint32_t le = alias_pick(g.edge_at, index_draw(w0, g.n_edge_local), w1);
+        const int v1 = __ldg(g.edge_src + le);
+        const int o = v1 & mask;
+        if (o == g.shard_rank) continue;
+        uint32_t h = exch_hash(v1) & x.hmask;
+        for (;;) {
+            const int prev = atomicCAS(x.hkey + h, -1, v1);
+            if (prev == -1) {
+                const int j = atomicAdd(x.cnt + o, 1);
+                x.req[(int64_t)o * x.req_stride + j] = v1 >> g.shard_shift;
+                x.hval[h] = (o << 28) | j;
+                break;
+            }
+            if (prev == v1) break;
+            h = (h + 1) & x.hmask;
+        }
+    }
+}
+
+// Owner side: rows[i] = table[req[i]] (one warp per row; i runs over the packed request lists of all sources).
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_gather_rows(const typename C::T* __restrict__ table,
+                                                               const int32_t* __restrict__ req, int64_t n,
+                                                               typename C::T* __restrict__ rows, int dim) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < n; i += nw) {
+        Row<C> r;
+        r.load(table + (size_t)__ldg(req + i) * dim, lane, dim);
+        r.store(rows + (size_t)i * dim, lane, dim);
+    }
+}
+
+// Owner side: table[req[i]] += back[i] - sent[i] with red.global.add (two requesters may return the same row).
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_apply_delta(typename C::T* __restrict__ table,
+                                                               const int32_t* __restrict__ req, int64_t n,
+                                                               const typename C::T* __restrict__ back,
+                                                               const typename C::T* __restrict__ sent, int dim) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < n; i += nw) {
+        Row<C> a, b;
+        a.load(back + (size_t)i * dim, lane, dim);
+        b.load(sent + (size_t)i * dim, lane, dim);
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) a.x[e] = Ar<typename C::T>::sub(a.x[e], b.x[e]);
+        row_red_add<C>(table + (size_t)__ldg(req + i) * dim, a, lane, dim);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // LINE: LINE::Train (src/model/LINE.cpp:100-195) / LINE.Train (internal/models/line/line.go:73-150)
 // ---------------------------------------------------------------------------------------------------------------
 // SHARD: 0 = one GPU; 1 = row-sharded, remote vertex rows staged over NVLink; 2 = row-sharded with a local read replica of
-// the vertex table: rows are read (and updated) in the replica, the delta is pushed to the owner with red.global.add.
+// the vertex table: rows are read (and updated) in the replica, the delta is pushed to the owner with red.global.add;
+// 3 = row-sharded, bulk exchange: remote vertex rows were gathered into the local staging table a.x.wrk beforehand
+// (k_line_requests -> all-to-all -> k_gather_rows -> all-to-all), so every access of this kernel is to local HBM.
 template <class C, bool GO, int SHARD>
 __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
     constexpr bool STAGED = SHARD == 1;
     using T = typename C::T;
     const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
-    using TV = typename std::conditional<SHARD == 1, TableView<T>, DirectView<T>>::type;
-    using TC = typename std::conditional<SHARD != 0, TableView<T>, DirectView<T>>::type;
+    using TV = typename std::conditional<SHARD == 1, TableView<T>,
+                                         typename std::conditional<SHARD == 3, ExchView<T>, DirectView<T>>::type>::type;
+    using TC = typename std::conditional<SHARD == 3, OwnedView<T>,
+                                         typename std::conditional<SHARD != 0, TableView<T>, DirectView<T>>::type>::type;
     TV tv;
     TC tc;
     TableView<T> owner_v{};  // SHARD == 2: where the vertex deltas are pushed
     if constexpr (SHARD == 1) stage_views<T>(a, tv, tc);
-    else if constexpr (SHARD == 2) {
+    else if constexpr (SHARD == 3) {
+        tv = ExchView<T>{a.Wv, reinterpret_cast<T*>(a.x.wrk), a.world_shift, a.dim};
+        tc = OwnedView<T>{a.Wc, a.world_shift, a.dim};
+    } else if constexpr (SHARD == 2) {
         stage_views<T>(a, owner_v, tc);
         tv = DirectView<T>{a.replica_v, a.dim};
     } else {
@@ -186,6 +285,14 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
     for (uint64_t done = 0; done < a.jobs; done += 32) {
         const int nb = (int)min((uint64_t)32, a.jobs - done);
         batch_sample<GO>(a.g, b, a.seed, stream, st, nb, lane);
+        if constexpr (SHARD == 3) {
+            // remote source: k_line_requests filed it in the hash; its row now sits in the staging table
+            if (lane < nb) {
+                const int v1 = b.ids[lane * b.idw];
+                if ((v1 & a.world_mask) != a.g.shard_rank) b.ids[lane * b.idw] = -2 - exch_lookup(a.x, v1);
+            }
+            __syncwarp();
+        }
         if constexpr (staged) {
 #pragma unroll
             for (int s = 0; s < kStageDepth - 1; ++s) {
@@ -211,7 +318,8 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             const T alpha = (T)st.alpha;
             T* vpush = nullptr;
             if constexpr (SHARD == 2) vpush = owner_v.row(v1);
-            const bool same = SHARD == 2 ? false : a.same_table != 0;  // replica rows never alias shard rows in memory
+            // replica rows never alias shard rows in memory; nor do staging rows (v1 < 0 then never equals a context id)
+            const bool same = SHARD == 2 ? false : a.same_table != 0;
             if (!GO) update_pair_cpp<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
             else update_pair_go<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
             st.count++;

@@ -64,6 +64,27 @@ struct DirectView {
     __device__ __forceinline__ T* row(int id) const { return base0 + (size_t)id * dim; }
 };
 
+// Bulk-exchange mode of a row-sharded table, vertex side: id >= 0 is a vertex owned by this rank (row id >> shift of the
+// local shard), id < 0 names row (-2 - id) of the staging table the remote rows of the super-batch were gathered into.
+template <typename T>
+struct ExchView {
+    T* local;
+    T* wrk;
+    int shift, dim;
+    static constexpr int mask = 0;
+    __device__ __forceinline__ T* row(int id) const {
+        return id >= 0 ? local + (size_t)(id >> shift) * dim : wrk + (size_t)(-2 - id) * dim;
+    }
+};
+// ... context side: context rows of the samples a rank computes are always its own.
+template <typename T>
+struct OwnedView {
+    T* local;
+    int shift, dim;
+    static constexpr int mask = 0;
+    __device__ __forceinline__ T* row(int id) const { return local + (size_t)(id >> shift) * dim; }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // Per-warp draw ring
 // ---------------------------------------------------------------------------------------------------------------

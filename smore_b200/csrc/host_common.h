@@ -16,6 +16,7 @@
 
 #include "host_graph.h"
 #include "batch_kernels.cuh"
+#include "exchange_host.h"
 
 using namespace smore;
 
@@ -93,6 +94,7 @@ struct smore_model_s {
     void* peer[2][kMaxWorld] = {};             // shard bases per rank (peer[t][rank] == tab[t])
     bool peer_opened[2][kMaxWorld] = {};       // CUDA-IPC mappings to close
     void* replica[2] = {nullptr, nullptr};     // optional full-size local read replica of a sharded table
+    smore_exchange_s* xch = nullptr;           // bulk-exchange mode of a sharded model (smore_model_enable_exchange)
     WarpState* d_state = nullptr;
     int state_cap = 0;
     int32_t* d_keys = nullptr;
@@ -107,6 +109,7 @@ struct smore_model_s {
                 if (peer_opened[t][r]) cudaIpcCloseMemHandle(peer[t][r]);
         cudaFree(tab[0]); cudaFree(tab[1]); cudaFree(d_state); cudaFree(d_keys);
         cudaFree(replica[0]); cudaFree(replica[1]);
+        delete xch;
     }
 };
 
@@ -162,7 +165,7 @@ int ensure_state(smore_model_s* m, int warps) {
 int check_train(smore_model_s* m, const smore_train_params* p, int need_tables, bool shard_ok = false) {
     if (!m || !p) return fail(SMORE_E_INVALID, "null model/params");
     if (m->g->world > 1 && !shard_ok) return fail(SMORE_E_UNSUPPORTED, "this trainer does not run on a row-sharded graph yet (LINE does)");
-    if (m->g->world > 1)
+    if (m->g->world > 1 && !m->xch)  // (the exchange mode never dereferences a peer pointer)
         for (int t = 0; t < m->n_tables; ++t)
             for (int r = 0; r < m->g->world; ++r)
                 if (!m->peer[t][r]) return fail(SMORE_E_INVALID, "table %d: shard of rank %d not connected (smore_model_open_peers)", t, r);
@@ -265,6 +268,9 @@ constexpr size_t smem_walk() { return smem_line<T>() + (size_t)kWarpsPerBlock * 
 // one translation unit per (trainer, element type): train_*.cu
 template <typename T>
 int train_line_t(smore_model_s* m, const smore_train_params* p);
+// bulk-exchange mode: ms = the shards driven by this process (1 with the NCCL transport, all of them with the local one)
+template <typename T>
+int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p, ExchTransport& tr);
 template <typename T>
 int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets);
 template <typename T>

@@ -24,6 +24,21 @@ constexpr int kMaxWorld = 8;      // ranks of one NVSwitch box
 #endif
 constexpr int kLinePrefetch = SMORE_LINE_PREFETCH;  // L2 prefetch distance (samples) inside a batch
 
+// Bulk-exchange mode of the row-sharded store (batch_kernels.cuh, "exchange" section): the remote vertex rows a
+// super-batch needs are requested from their owners, moved with an all-to-all (NCCL over NVLink) into a contiguous local
+// staging table `wrk`, updated there, and returned to the owner, who adds the difference to its row. All peer traffic is
+// bulk and sequential; the random accesses stay in local HBM.
+struct ExchDev {
+    int32_t* hkey;       // open-addressing hash of the remote vertex ids of this super-batch: global id, -1 = empty
+    int32_t* hval;       // (owner << 28) | index into that owner's request list
+    uint32_t hmask;      // table size - 1 (power of two >= 2 x samples of a super-batch)
+    int32_t* req;        // [world][req_stride]: local row ids requested from owner o
+    int64_t req_stride;
+    int32_t* cnt;        // [kMaxWorld] requests per owner
+    const int32_t* off;  // [kMaxWorld] first wrk row of owner o's region (exclusive prefix sum of cnt)
+    void* wrk;           // staged vertex rows [sum cnt][dim]
+};
+
 template <typename T>
 struct TrainArgs {
     GraphDev g;
@@ -48,6 +63,7 @@ struct TrainArgs {
     const int32_t* keys;  // start vertices of this launch (already shuffled / identity)
     int64_t n_walks;      // walks in this launch; warp w takes walks w, w+W, ...
     int steps, w0, w1, walklets;
+    ExchDev x;  // bulk-exchange mode only
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -632,7 +632,48 @@ int smore_train_line(smore_model_t m, const smore_train_params* p) {
     if (int rc = check_train(m, p, p && p->order == 1 ? 1 : 2, true)) return rc;
     if (p->negative_samples < 0 || p->negative_samples > 31) return fail(SMORE_E_UNSUPPORTED, "negative_samples must be in [0,31]");
     if (p->order != 1 && p->order != 2) return fail(SMORE_E_INVALID, "order must be 1 or 2");
+    if (m->xch && m->g->world > 1) {  // bulk-exchange mode, one process per GPU: NCCL carries the row batches
+        ExchTransport* tr = exch_nccl_transport(m->g->rank, m->g->world);
+        if (!tr) return SMORE_E_INVALID;
+        return m->dtype == SMORE_F64 ? train_line_exchange_t<double>(&m, 1, p, *tr) : train_line_exchange_t<float>(&m, 1, p, *tr);
+    }
     return m->dtype == SMORE_F64 ? train_line_t<double>(m, p) : train_line_t<float>(m, p);
+}
+
+int smore_model_enable_exchange(smore_model_t m, int64_t superbatch) {
+    if (!m) return fail(SMORE_E_INVALID, "null model");
+    if (m->g->world == 1) return fail(SMORE_E_INVALID, "the exchange mode only makes sense on a row-sharded graph");
+    if (superbatch <= 0) superbatch = 1 << 20;
+    if (superbatch > (1ll << 27)) return fail(SMORE_E_INVALID, "superbatch must be <= 2^27 samples");
+    if (!m->xch) m->xch = new smore_exchange_s();
+    m->xch->superbatch = superbatch;
+    return SMORE_OK;
+}
+
+int smore_train_line_group(const smore_model_t* shards, int n, const smore_train_params* p) {
+    if (!shards || n < 2 || n > kMaxWorld) return fail(SMORE_E_INVALID, "need the 2..8 shards of one model");
+    smore_model_s* ms[kMaxWorld];
+    for (int r = 0; r < n; ++r) {
+        smore_model_s* m = shards[r];
+        if (!m) return fail(SMORE_E_INVALID, "null shard");
+        if (int rc = check_train(m, p, p && p->order == 1 ? 1 : 2, true)) return rc;
+        if (!m->xch) return fail(SMORE_E_INVALID, "shard %d: call smore_model_enable_exchange first", r);
+        if (m->g->world != n || m->g->rank != r) return fail(SMORE_E_INVALID, "shards[%d] is rank %d of %d", r, m->g->rank, m->g->world);
+        if (m->dim != shards[0]->dim || m->dtype != shards[0]->dtype || m->xch->superbatch != shards[0]->xch->superbatch)
+            return fail(SMORE_E_INVALID, "shards disagree on dim / dtype / superbatch");
+        ms[r] = m;
+    }
+    if (p->negative_samples < 0 || p->negative_samples > 31) return fail(SMORE_E_UNSUPPORTED, "negative_samples must be in [0,31]");
+    if (p->order != 1 && p->order != 2) return fail(SMORE_E_INVALID, "order must be 1 or 2");
+    ExchTransport* tr = exch_local_transport();
+    return ms[0]->dtype == SMORE_F64 ? train_line_exchange_t<double>(ms, n, p, *tr) : train_line_exchange_t<float>(ms, n, p, *tr);
+}
+
+int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows_requested) {
+    if (!m || !m->xch) return fail(SMORE_E_INVALID, "exchange mode not enabled on this model");
+    if (superbatches) *superbatches = m->xch->st_superbatches;
+    if (rows_requested) *rows_requested = m->xch->st_rows_moved;
+    return SMORE_OK;
 }
 
 static int train_walk_common(smore_model_t m, const smore_train_params* p, int walklets) {

@@ -1,2 +1,3 @@
 #include "train_line.inl"
 template int train_line_t<double>(smore_model_s*, const smore_train_params*);
+template int train_line_exchange_t<double>(smore_model_s**, int, const smore_train_params*, ExchTransport&);

@@ -28,6 +28,23 @@ def connect_peers(model, group=None) -> None:
         model.open_peers(t, exchange_handles(model.ipc_handle(t), group))
 
 
+def init_exchange(group=None) -> None:
+    """Bootstraps the library's own NCCL communicator (bulk-exchange mode): rank 0's ncclUniqueId is broadcast over the
+    host's process group, then every rank joins."""
+    import torch
+    import torch.distributed as dist
+
+    from . import capi
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    uid = capi.nccl_unique_id() if rank == 0 else bytes(128)
+    t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0, group=group)
+    capi.nccl_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+
 def owned_rows(V: int, rank: int, world: int) -> np.ndarray:
     """Global vertex ids of the rows rank holds, in local-row order."""
     return np.arange(rank, V, world)

@@ -212,3 +212,97 @@ def test_two_processes_cuda_ipc_on_one_device():
     print(dict(out))
     assert out["samples0"] > 0 and out["samples1"] > 0
     assert out["auc"] > 0.85  # both shards learned and every cross-shard context row was reachable
+
+
+# ---- bulk-exchange mode (smore_model_enable_exchange): remote vertex rows move in per-super-batch all-to-alls ---------
+def _exchange_shards(off, col, ww, V, dim, world, init_v, init_c, superbatch, dtype=capi.F32):
+    ms = []
+    for r in range(world):
+        gr = capi.Graph.from_csr(off, col, ww)
+        gr.set_shard(r, world)
+        mr = capi.Model(gr, dim, 2, dtype)
+        rows = sdist.owned_rows(V, r, world)
+        mr.set_rows(0, init_v[rows]), mr.set_rows(1, init_c[rows])
+        mr.enable_exchange(superbatch)
+        ms.append(mr)
+    return ms
+
+
+def test_exchange_routing_is_exact():
+    """alpha so small that no update can change a row in fp64: every table must come back bit-identical. Any mis-routed
+    request, row or delta (owner adds `returned - sent`) would show up as a changed row."""
+    src, dst, w = graphs.random_graph(2000, 30000, seed=71)
+    off, col, ww, _ = B.edges_to_csr(src, dst, w, 1)
+    V, dim, world = len(off) - 1, 24, 4
+    rng = np.random.default_rng(3)
+    init_v, init_c = (rng.random((V, dim)) - 0.5) / dim, (rng.random((V, dim)) - 0.5) / dim
+    ms = _exchange_shards(off, col, ww, V, dim, world, init_v, init_c, superbatch=5000, dtype=capi.F64)
+    p = _params(200_000, 5)
+    p.alpha = 1e-30
+    stats = capi.train_line_group(ms, p)
+    assert sum(s["samples"] for s in stats) > 150_000
+    moved = 0
+    for r, mr in enumerate(ms):
+        rows = sdist.owned_rows(V, r, world)
+        assert np.array_equal(mr.get_rows(0), init_v[rows])
+        assert np.array_equal(mr.get_rows(1), init_c[rows])
+        xs = mr.exchange_stats()
+        assert xs["superbatches"] == 10  # ceil(200000 / (5000 * 4))
+        moved += xs["rows_requested"]
+    # ~3/4 of the sources are remote; dedup inside a super-batch can only lower the count
+    assert 0.1 * 200_000 < moved <= 0.8 * 200_000
+
+
+def test_exchange_one_sample_moves_one_row():
+    """One deterministic warp per shard, one super-batch, K = 0, zero contexts, vertex rows = their own id: after one
+    sample the positive context row is 0.5 * alpha * (row of the source): the STAGED row must be the source's."""
+    src, dst, w = graphs.random_graph(400, 3000, seed=73)
+    off, col, ww, _ = B.edges_to_csr(src, dst, w, 1)
+    V, dim, world = len(off) - 1, 8, 2
+    init_v = np.repeat(np.arange(1, V + 1, dtype=np.float64)[:, None], dim, axis=1) * 1e-3
+    init_c = np.zeros((V, dim))
+    ms = _exchange_shards(off, col, ww, V, dim, world, init_v, init_c, superbatch=1 << 20, dtype=capi.F64)
+    p = _params(2 * 40, 9)
+    p.mode, p.negative_samples, p.alpha = capi.MODE_DETERMINISTIC, 0, 1.0
+    capi.train_line_group(ms, p)
+    Wv, Wc = np.zeros((V, dim)), np.zeros((V, dim))
+    for r, mr in enumerate(ms):
+        rows = sdist.owned_rows(V, r, world)
+        Wv[rows], Wc[rows] = mr.get_rows(0), mr.get_rows(1)
+    touched = np.flatnonzero(np.abs(Wc).sum(1) > 0)
+    assert len(touched) > 10
+    adj = {v: set(col[off[v]:off[v + 1]].tolist()) for v in range(V)}
+    once = 0
+    for c in touched:
+        # a context hit exactly once holds 0.5 * v_src (sigmoid LUT(0) = 0.5, label 1, alpha 1) for one of its neighbours
+        cand = Wc[c, 0] / 0.5 / 1e-3 - 1
+        v = int(round(cand))
+        if abs(cand - v) < 1e-6 and 0 <= v < V and c in adj[v]:
+            once += 1
+    assert once >= 0.5 * len(touched)
+    # vertex rows only changed through contexts that were non-zero when read: a vertex row is its id plus small terms
+    assert np.abs(Wv - init_v).max() < 1.0
+
+
+def test_exchange_mode_quality_matches_unsharded():
+    off, col, ww, test_s, test_d, train_adj = _sbm()
+    V, dim, total = len(off) - 1, 32, 12_000_000
+    init = ((np.random.default_rng(1).random((V, dim)) - 0.5) / dim)
+    g = capi.Graph.from_csr(off, col, ww)
+    m = capi.Model(g, dim, 2, capi.F32)
+    m.set_rows(0, init), m.set_rows(1, np.zeros((V, dim)))
+    m.train_line(_params(total, 13))
+    base_auc, base_rec = evaluate(m.get_rows(0), m.get_rows(1), test_s, test_d, train_adj, np.random.default_rng(2))
+    world = 4
+    ms = _exchange_shards(off, col, ww, V, dim, world, init, np.zeros((V, dim)), superbatch=1 << 15)
+    stats = capi.train_line_group(ms, _params(total, 100))
+    assert 0.9 * total <= sum(s["samples"] for s in stats) <= total
+    Wv, Wc = np.zeros((V, dim)), np.zeros((V, dim))
+    for r, mr in enumerate(ms):
+        rows = sdist.owned_rows(V, r, world)
+        Wv[rows], Wc[rows] = mr.get_rows(0), mr.get_rows(1)
+    auc_, rec_ = evaluate(Wv, Wc, test_s, test_d, train_adj, np.random.default_rng(2))
+    xs = ms[0].exchange_stats()
+    print(f"AUC unsharded {base_auc:.4f} exchange-mode(4) {auc_:.4f} | recall@10 {base_rec:.4f} vs {rec_:.4f} | {xs}")
+    assert abs(auc_ - base_auc) < 0.005
+    assert abs(rec_ - base_rec) < 0.005 + 0.05 * base_rec
