@@ -245,7 +245,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.check(capi.lib().smore_init(local))
 
-    sharded = world > 1 and args.parallelism in ("sharded", "sharded-replica")
+    sharded = world > 1 and args.parallelism in ("sharded", "sharded-replica", "sharded-exchange")
+    exchange = sharded and args.parallelism == "sharded-exchange"
     # N > 1, sharded: by default every N runs the SAME configs[1] graph (updates per GPU fixed: weak scaling in work).
     # --grow-graph grows the graph with N instead (1M vertices / 10M edges per GPU, generated on the GPU). Measured
     # (DESIGN.md section 7): growing helps at 2 GPUs (hub rows are hit half as often per second) but the randomly accessed
@@ -271,7 +272,14 @@ def run_ours(args):
     if sharded:
         from smore_b200 import dist as sdist
 
-        sdist.connect_peers(m)
+        if exchange:
+            # bulk-exchange mode: no peer mappings; the library's own NCCL communicator carries the row batches
+            sdist.init_exchange()
+            m.enable_exchange(args.superbatch, args.hot_threshold)
+            if args.hot_threshold >= 0:
+                sdist.connect_peers(m)  # hot (hub) rows stay single-copy behind the peer mappings
+        else:
+            sdist.connect_peers(m)
         if replica:
             m.enable_replica(0)
         dist.barrier()
@@ -386,7 +394,11 @@ def run_ours(args):
                        f"tables row-sharded over {world} GPUs, context-owner computes, remote vertex rows over NVLink "
                        f"peer mappings (CUDA IPC), no data-path collective"
                        + (" [replica mode: vertex rows read from a local replica refreshed every step, deltas pushed with "
-                          "red.global.add]" if replica else "") if sharded
+                          "red.global.add]" if replica else "") if sharded and not exchange
+                       else f"tables row-sharded over {world} GPUs, context-owner computes, remote vertex rows moved in "
+                            f"super-batches of {args.superbatch} samples/GPU by NCCL all-to-all (request lists, rows out, "
+                            f"rows back), owner applies the deltas; vertices expected >= {args.hot_threshold} times per super-batch "
+                            f"stay single-copy behind NVLink peer mappings ({m.exchange_stats()['hot_vertices']} of {g.V})" if exchange
                        else f"{world} independent replicas (weak scaling)"),
                    "l2": "working set per GPU (1.0 GB of table rows + >= 0.5 GB graph) exceeds the 126 MB L2; no flush between steps"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -417,7 +429,11 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grow-graph", action="store_true", help="N>1: grow the graph with N (1M vertices per GPU)")
-    ap.add_argument("--parallelism", default="sharded", choices=["sharded", "sharded-replica", "replicas"], help="N>1 only")
+    ap.add_argument("--parallelism", default="sharded", choices=["sharded", "sharded-replica", "sharded-exchange", "replicas"],
+                    help="N>1 only")
+    ap.add_argument("--superbatch", type=int, default=1 << 20, help="sharded-exchange: samples per GPU and super-batch")
+    ap.add_argument("--hot-threshold", type=float, default=0.25,
+                    help="sharded-exchange: expected source draws per super-batch above which a vertex keeps a single copy (<0: none)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

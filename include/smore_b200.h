@@ -157,21 +157,26 @@ int smore_model_refresh_replica(smore_model_t m, int table);
  * the remote vertex rows its samples will need (the sampler is counter-based, so the sources are known before the
  * update runs) in per-owner request lists, (2) the lists, the requested rows and -- after the updates -- the modified
  * rows travel as contiguous buffers in three all-to-alls (NCCL send/recv groups over NVLink), (3) the owner adds
- * `returned - sent` to its row. No kernel dereferences a peer pointer: smore_model_open_peers is not needed.
+ * `returned - sent` to its row.
+ * HOT vertices. Copies of a row on several ranks are only equivalent to Hogwild on one copy while each copy receives few
+ * updates per super-batch: once every copy runs a long update sequence of its own, the sum of the per-copy corrections
+ * overshoots (measured: 4 shards of a 12 k-vertex graph, ~11 source samples per vertex and super-batch -> held-out AUC
+ * 0.53 instead of 0.92; ~0.7 -> 0.9214). A vertex expected to be drawn as a source at least `hot_threshold` times per
+ * super-batch (all ranks together; P(source) of the unsharded sampler x superbatch x world) therefore keeps a single copy
+ * and is reached through the peer mappings exactly as in the peer-access mode (smore_model_open_peers required); the hot
+ * set is small (hubs), so its peer footprint stays below the cliff. hot_threshold < 0: no hot vertices (pure exchange,
+ * no peer mapping needed); 0: every vertex is hot (degenerates to the peer-access mode). Recommended: 0.25.
  * Replaces nothing in the reference (its tables live in one address space); it is the "NCCL all-to-all carries the
  * remote-row batches" half of the sharded store, next to the peer-access half above. */
-int smore_model_enable_exchange(smore_model_t m, int64_t superbatch);
+int smore_model_enable_exchange(smore_model_t m, int64_t superbatch, double hot_threshold);
 /* NCCL bootstrap for the exchange mode with one process per GPU: rank 0 creates the 128-byte ncclUniqueId, the host
  * broadcasts it with its own transport, every rank calls init (after smore_init). libnccl.so.2 is dlopen()ed here. */
 int smore_dist_nccl_unique_id(void* id128);
 int smore_dist_nccl_init(const void* id128, int rank, int world);
 int smore_dist_nccl_shutdown(void);
-/* Same algorithm with every shard in the calling process (several shards on one device; tests and single-GPU
- * experiments): shards[r] must be rank r of n, all with the exchange mode enabled; plain device copies replace NCCL.
- * Shard r draws from streams stream_base + (r << 20) + warp. */
-int smore_train_line_group(const smore_model_t* shards, int n, const smore_train_params* p);
-/* Counters of the last exchange-mode train call: super-batches run, remote vertex rows requested (after dedup). */
-int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows_requested);
+/* Counters of the last exchange-mode train call: super-batches run, remote vertex rows requested (after dedup); and the
+ * size of the hot set. */
+int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows_requested, int64_t* hot_vertices);
 
 /* Text writer: "<V> <dim>\n" then `name v0 v1 ...` per vertex in id order, VERTEX table only.
  * format 0 = C++ iostream default (%g, 6 significant digits; src/model/LINE.cpp:13-47),
@@ -206,6 +211,10 @@ void smore_train_params_default(smore_train_params* p);
  * On a row-sharded model with the exchange mode enabled this call is COLLECTIVE: every rank must make it with the same
  * `total` (each runs its share in the same number of super-batches). */
 int smore_train_line(smore_model_t m, const smore_train_params* p);
+/* Exchange mode with every shard in the calling process (several shards on one device; tests and single-GPU
+ * experiments): shards[r] must be rank r of n, all with the exchange mode enabled; plain device copies replace NCCL.
+ * Shard r draws from streams stream_base + (r << 20) + warp. */
+int smore_train_line_group(const smore_model_t* shards, int n, const smore_train_params* p);
 /* BPR::Train (src/model/BPR.cpp:55-107, 5-negative UpdateBPRPair proNet.cpp:1406-1455) /
  * BPR.Train (internal/models/bpr/bpr.go:61-131, optimizer.go:87-117). */
 int smore_train_bpr(smore_model_t m, const smore_train_params* p);

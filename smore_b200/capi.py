@@ -96,12 +96,12 @@ def lib():
         L.smore_model_set_peer_ptrs.argtypes = [vp, C.c_int, vp]
         L.smore_model_enable_replica.argtypes = [vp, C.c_int]
         L.smore_model_refresh_replica.argtypes = [vp, C.c_int]
-        L.smore_model_enable_exchange.argtypes = [vp, i64]
+        L.smore_model_enable_exchange.argtypes = [vp, i64, f64]
         L.smore_dist_nccl_unique_id.argtypes = [vp]
         L.smore_dist_nccl_init.argtypes = [vp, C.c_int, C.c_int]
         L.smore_dist_nccl_shutdown.argtypes = []
         L.smore_train_line_group.argtypes = [vp, C.c_int, C.POINTER(TrainParams)]
-        L.smore_exchange_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+        L.smore_exchange_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i64)]
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
         L.smore_train_params_default.restype = None
         for name in ("smore_train_line", "smore_train_bpr", "smore_train_warp", "smore_train_hoprec",
@@ -315,14 +315,16 @@ class Model:
     def refresh_replica(self, table=0):
         check(lib().smore_model_refresh_replica(self.h, table))
 
-    def enable_exchange(self, superbatch=0):
-        """Bulk-exchange mode (row-sharded LINE): remote vertex rows move in per-super-batch all-to-alls."""
-        check(lib().smore_model_enable_exchange(self.h, superbatch))
+    def enable_exchange(self, superbatch=0, hot_threshold=0.25):
+        """Bulk-exchange mode (row-sharded LINE): remote vertex rows move in per-super-batch all-to-alls; vertices
+        expected as a source >= hot_threshold times per super-batch stay single-copy behind the peer mappings
+        (hot_threshold < 0: none)."""
+        check(lib().smore_model_enable_exchange(self.h, superbatch, hot_threshold))
 
     def exchange_stats(self):
-        sb, rows = u64(), u64()
-        check(lib().smore_exchange_stats(self.h, C.byref(sb), C.byref(rows)))
-        return {"superbatches": sb.value, "rows_requested": rows.value}
+        sb, rows, hot = u64(), u64(), i64()
+        check(lib().smore_exchange_stats(self.h, C.byref(sb), C.byref(rows), C.byref(hot)))
+        return {"superbatches": sb.value, "rows_requested": rows.value, "hot_vertices": hot.value}
 
     def device_ptr(self, table):
         p = vp()

@@ -184,7 +184,7 @@ static __global__ void __launch_bounds__(kBlockThreads) k_line_requests(GraphDev
         const uint32_t le = alias_pick(g.edge_at, index_draw(w0, g.n_edge_local), w1);
         const int v1 = __ldg(g.edge_src + le);
         const int o = v1 & mask;
-        if (o == g.shard_rank) continue;
+        if (o == g.shard_rank || x.is_hot(v1)) continue;
         uint32_t h = exch_hash(v1) & x.hmask;
         for (;;) {
             const int prev = atomicCAS(x.hkey + h, -1, v1);
@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_apply_delta(typename C::T* __
 // SHARD: 0 = one GPU; 1 = row-sharded, remote vertex rows staged over NVLink; 2 = row-sharded with a local read replica of
 // the vertex table: rows are read (and updated) in the replica, the delta is pushed to the owner with red.global.add;
 // 3 = row-sharded, bulk exchange: remote vertex rows were gathered into the local staging table a.x.wrk beforehand
-// (k_line_requests -> all-to-all -> k_gather_rows -> all-to-all), so every access of this kernel is to local HBM.
+// (k_line_requests -> all-to-all -> k_gather_rows -> all-to-all), so every access of this kernel is to local HBM --
+// except the rows of HOT vertices (ExchDev::hot), which are reached through the peer mappings.
 template <class C, bool GO, int SHARD>
 __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
     constexpr bool STAGED = SHARD == 1;
@@ -253,7 +254,9 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
     TableView<T> owner_v{};  // SHARD == 2: where the vertex deltas are pushed
     if constexpr (SHARD == 1) stage_views<T>(a, tv, tc);
     else if constexpr (SHARD == 3) {
-        tv = ExchView<T>{a.Wv, reinterpret_cast<T*>(a.x.wrk), a.world_shift, a.dim};
+        TableView<T> pv, pc;
+        stage_views<T>(a, pv, pc);
+        tv = ExchView<T>{pv.base, reinterpret_cast<T*>(a.x.wrk), a.world_shift, a.world_mask, a.dim};
         tc = OwnedView<T>{a.Wc, a.world_shift, a.dim};
     } else if constexpr (SHARD == 2) {
         stage_views<T>(a, owner_v, tc);
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             // remote source: k_line_requests filed it in the hash; its row now sits in the staging table
             if (lane < nb) {
                 const int v1 = b.ids[lane * b.idw];
-                if ((v1 & a.world_mask) != a.g.shard_rank) b.ids[lane * b.idw] = -2 - exch_lookup(a.x, v1);
+                if ((v1 & a.world_mask) != a.g.shard_rank && !a.x.is_hot(v1)) b.ids[lane * b.idw] = -2 - exch_lookup(a.x, v1);
             }
             __syncwarp();
         }

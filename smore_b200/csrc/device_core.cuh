@@ -66,14 +66,14 @@ struct DirectView {
 
 // Bulk-exchange mode of a row-sharded table, vertex side: id >= 0 is a vertex owned by this rank (row id >> shift of the
 // local shard), id < 0 names row (-2 - id) of the staging table the remote rows of the super-batch were gathered into.
+// A non-negative id of another rank's vertex (a HOT row, see ExchDev::hot) goes through that rank's peer mapping.
 template <typename T>
 struct ExchView {
-    T* local;
+    T* const* base;  // shard bases per rank (shared memory); only this rank's is dereferenced unless hot rows exist
     T* wrk;
-    int shift, dim;
-    static constexpr int mask = 0;
+    int shift, mask, dim;
     __device__ __forceinline__ T* row(int id) const {
-        return id >= 0 ? local + (size_t)(id >> shift) * dim : wrk + (size_t)(-2 - id) * dim;
+        return id >= 0 ? base[id & mask] + (size_t)(id >> shift) * dim : wrk + (size_t)(-2 - id) * dim;
     }
 };
 // ... context side: context rows of the samples a rank computes are always its own.
@@ -263,6 +263,10 @@ struct RowCfg {
     static constexpr int EPL = VEC_ * NCH_;
 };
 
+// Run-time switch of the L1-allocating gathers (Row::load_ca), one copy per translation unit, set by the host before a
+// launch (host_common.h: set_l1_gather). See the hazard note at load_ca.
+static __constant__ int c_l1_gather = 1;
+
 template <class C>
 struct Row {
     typename C::T x[C::EPL];
@@ -281,7 +285,17 @@ struct Row {
     // L1-allocating gather (ld.global.ca): a row that many warps of the SM keep re-reading (popular items of a
     // Zipf-distributed catalogue) is served from L1 instead of queueing at its L2 slice behind everybody's writes.
     // Stale by at most the L1 residence time; a lane's own stores still invalidate the line (same-SM coherence).
+    // HAZARD: a row that stays L1-resident on an SM is a private replica of that SM for as long as it stays -- the SM
+    // keeps training its own copy and its full-row stores overwrite what the other SMs wrote (L1s are only invalidated
+    // at kernel boundaries). Harmless for the few genuinely hot rows of a large table (Hogwild loses most concurrent
+    // updates of such rows anyway), but a table small enough to live in the L1s turns into 148 diverging replicas:
+    // measured on a 12 k-vertex graph in 4 shards (384 KB of context rows per shard), held-out AUC 0.52 instead of
+    // 0.92. The host therefore enables the switch only for tables far larger than the aggregate L1 (set_l1_gather).
     __device__ __forceinline__ void load_ca(const typename C::T* base, int lane, int dim) {
+        if (!c_l1_gather) {
+            load(base, lane, dim);
+            return;
+        }
 #pragma unroll
         for (int c = 0; c < C::NCH; ++c) {
             int idx = (c * 32 + lane) * C::VEC;

@@ -23,6 +23,9 @@ struct DevBuf {
 struct smore_exchange_s {
     static constexpr int kW = 8;  // == kMaxWorld
     int64_t superbatch = 0;       // samples per rank and super-batch (target)
+    double hot_threshold = 0;     // a vertex expected to be a source >= this many times per super-batch (all ranks) is HOT
+    int64_t n_hot = 0;
+    DevBuf hot;                   // bitmap over vertex ids, null when n_hot == 0
     DevBuf hkey, hval, req, cnt /* [2][kW] int32: out, in */, off /* [kW] int32 */, wrk, req_in, sent, back;
     // host mirror of the super-batch in flight
     int cnt_out[kW] = {}, cnt_in[kW] = {};

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -165,7 +166,7 @@ int ensure_state(smore_model_s* m, int warps) {
 int check_train(smore_model_s* m, const smore_train_params* p, int need_tables, bool shard_ok = false) {
     if (!m || !p) return fail(SMORE_E_INVALID, "null model/params");
     if (m->g->world > 1 && !shard_ok) return fail(SMORE_E_UNSUPPORTED, "this trainer does not run on a row-sharded graph yet (LINE does)");
-    if (m->g->world > 1 && !m->xch)  // (the exchange mode never dereferences a peer pointer)
+    if (m->g->world > 1 && !(m->xch && m->xch->n_hot == 0))  // (without hot rows the exchange mode never touches a peer)
         for (int t = 0; t < m->n_tables; ++t)
             for (int r = 0; r < m->g->world; ++r)
                 if (!m->peer[t][r]) return fail(SMORE_E_INVALID, "table %d: shard of rank %d not connected (smore_model_open_peers)", t, r);
@@ -213,10 +214,21 @@ int collect_stats(smore_model_s* m, int warps) {
     return SMORE_OK;
 }
 
+// L1-allocating gathers are enabled only when the gathered table (this rank's shard) is far larger than what the L1s can
+// hold (148 SMs x <= 228 KB = 33 MB): then only genuinely hot rows stay resident. SMORE_L1_GATHER=0/1 overrides.
+constexpr size_t kL1GatherMinTableBytes = 256ull << 20;
+int set_l1_gather(const smore_model_s* m) {
+    int on = (size_t)m->rows * (size_t)m->dim * m->elem() >= kL1GatherMinTableBytes ? 1 : 0;
+    if (const char* e = getenv("SMORE_L1_GATHER")) on = atoi(e) != 0;
+    CU(cudaMemcpyToSymbol(c_l1_gather, &on, sizeof(int)));
+    return SMORE_OK;
+}
+
 template <typename T>
 TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps, double total, int lag, int vtab, int ctab,
                        double scale = 1.0 /* row-sharded: this rank's share of the schedule units */) {
     TrainArgs<T> a{};
+    set_l1_gather(m);
     a.g = m->g->view();
     a.Wv = (T*)m->tab[vtab];
     a.Wc = (T*)m->tab[ctab];

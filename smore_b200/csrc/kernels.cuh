@@ -37,6 +37,10 @@ struct ExchDev {
     int32_t* cnt;        // [kMaxWorld] requests per owner
     const int32_t* off;  // [kMaxWorld] first wrk row of owner o's region (exclusive prefix sum of cnt)
     void* wrk;           // staged vertex rows [sum cnt][dim]
+    const uint32_t* hot; // bitmap over vertex ids (null = none): HOT vertices are sampled so often that per-super-batch
+                         // copies on several ranks would each run a long update sequence whose sum overshoots; their rows
+                         // stay single-copy and are reached through the peer mappings as in the peer-access mode
+    __device__ __forceinline__ bool is_hot(int v) const { return hot && ((__ldg(hot + (v >> 5)) >> (v & 31)) & 1u); }
 };
 
 template <typename T>

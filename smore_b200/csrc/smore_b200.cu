@@ -640,13 +640,41 @@ int smore_train_line(smore_model_t m, const smore_train_params* p) {
     return m->dtype == SMORE_F64 ? train_line_t<double>(m, p) : train_line_t<float>(m, p);
 }
 
-int smore_model_enable_exchange(smore_model_t m, int64_t superbatch) {
+int smore_model_enable_exchange(smore_model_t m, int64_t superbatch, double hot_threshold) {
     if (!m) return fail(SMORE_E_INVALID, "null model");
-    if (m->g->world == 1) return fail(SMORE_E_INVALID, "the exchange mode only makes sense on a row-sharded graph");
+    smore_graph_s* g = m->g;
+    if (g->world == 1) return fail(SMORE_E_INVALID, "the exchange mode only makes sense on a row-sharded graph");
     if (superbatch <= 0) superbatch = 1 << 20;
     if (superbatch > (1ll << 27)) return fail(SMORE_E_INVALID, "superbatch must be <= 2^27 samples");
+    if (int rc = ensure_device()) return rc;
     if (!m->xch) m->xch = new smore_exchange_s();
-    m->xch->superbatch = superbatch;
+    smore_exchange_s* x = m->xch;
+    x->superbatch = superbatch;
+    x->hot_threshold = hot_threshold;
+    x->n_hot = 0;
+    if (hot_threshold >= 0) {
+        // P(source = v) of the unsharded sampler (C++: out_deg^0.75 / sum, Go: out_deg / sum) x samples of one super-batch
+        const double pw = g->sem == SMORE_SEM_CPP ? 0.75 : 1.0;
+        const int64_t V = g->V;
+        std::vector<double> ps((size_t)V);
+        double sum = 0;
+        for (int64_t v = 0; v < V; ++v) {
+            ps[(size_t)v] = g->out_deg[(size_t)v] > 0 ? std::pow(g->out_deg[(size_t)v], pw) : 0.0;
+            sum += ps[(size_t)v];
+        }
+        const double per_sb = (double)superbatch * (double)g->world;
+        std::vector<uint32_t> bits((size_t)(V + 31) / 32, 0u);
+        if (sum > 0)
+            for (int64_t v = 0; v < V; ++v)
+                if (ps[(size_t)v] / sum * per_sb >= hot_threshold && ps[(size_t)v] > 0) {
+                    bits[(size_t)(v >> 5)] |= 1u << (v & 31);
+                    x->n_hot++;
+                }
+        if (x->n_hot) {
+            if (int rc = x->hot.ensure(bits.size() * 4)) return rc;
+            CU(cudaMemcpy(x->hot.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
     return SMORE_OK;
 }
 
@@ -669,8 +697,9 @@ int smore_train_line_group(const smore_model_t* shards, int n, const smore_train
     return ms[0]->dtype == SMORE_F64 ? train_line_exchange_t<double>(ms, n, p, *tr) : train_line_exchange_t<float>(ms, n, p, *tr);
 }
 
-int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows_requested) {
+int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows_requested, int64_t* hot_vertices) {
     if (!m || !m->xch) return fail(SMORE_E_INVALID, "exchange mode not enabled on this model");
+    if (hot_vertices) *hot_vertices = m->xch->n_hot;
     if (superbatches) *superbatches = m->xch->st_superbatches;
     if (rows_requested) *rows_requested = m->xch->st_rows_moved;
     return SMORE_OK;

@@ -88,7 +88,8 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
             if (int rc = x->cnt.ensure(2 * kMaxWorld * 4)) return rc;
             if (int rc = x->off.ensure(kMaxWorld * 4)) return rc;
             s.a.x = ExchDev{(int32_t*)x->hkey.p, (int32_t*)x->hval.p, (uint32_t)(hsize - 1), (int32_t*)x->req.p,
-                            x->req_stride, (int32_t*)x->cnt.p, (const int32_t*)x->off.p, nullptr};
+                            x->req_stride, (int32_t*)x->cnt.p, (const int32_t*)x->off.p, nullptr,
+                            x->n_hot ? (const uint32_t*)x->hot.p : nullptr};
             x->st_rows_moved = 0;
             x->st_superbatches = nsb;
         }

@@ -215,7 +215,7 @@ def test_two_processes_cuda_ipc_on_one_device():
 
 
 # ---- bulk-exchange mode (smore_model_enable_exchange): remote vertex rows move in per-super-batch all-to-alls ---------
-def _exchange_shards(off, col, ww, V, dim, world, init_v, init_c, superbatch, dtype=capi.F32):
+def _exchange_shards(off, col, ww, V, dim, world, init_v, init_c, superbatch, dtype=capi.F32, hot=-1.0):
     ms = []
     for r in range(world):
         gr = capi.Graph.from_csr(off, col, ww)
@@ -223,8 +223,13 @@ def _exchange_shards(off, col, ww, V, dim, world, init_v, init_c, superbatch, dt
         mr = capi.Model(gr, dim, 2, dtype)
         rows = sdist.owned_rows(V, r, world)
         mr.set_rows(0, init_v[rows]), mr.set_rows(1, init_c[rows])
-        mr.enable_exchange(superbatch)
+        mr.enable_exchange(superbatch, hot)
         ms.append(mr)
+    if hot >= 0:  # hot rows are reached through the peer mappings
+        for t in range(2):
+            ptrs = [mr.device_ptr(t) for mr in ms]
+            for mr in ms:
+                mr.set_peer_ptrs(t, ptrs)
     return ms
 
 
@@ -253,38 +258,40 @@ def test_exchange_routing_is_exact():
     assert 0.1 * 200_000 < moved <= 0.8 * 200_000
 
 
-def test_exchange_one_sample_moves_one_row():
-    """One deterministic warp per shard, one super-batch, K = 0, zero contexts, vertex rows = their own id: after one
-    sample the positive context row is 0.5 * alpha * (row of the source): the STAGED row must be the source's."""
-    src, dst, w = graphs.random_graph(400, 3000, seed=73)
-    off, col, ww, _ = B.edges_to_csr(src, dst, w, 1)
-    V, dim, world = len(off) - 1, 8, 2
-    init_v = np.repeat(np.arange(1, V + 1, dtype=np.float64)[:, None], dim, axis=1) * 1e-3
-    init_c = np.zeros((V, dim))
-    ms = _exchange_shards(off, col, ww, V, dim, world, init_v, init_c, superbatch=1 << 20, dtype=capi.F64)
-    p = _params(2 * 40, 9)
-    p.mode, p.negative_samples, p.alpha = capi.MODE_DETERMINISTIC, 0, 1.0
-    capi.train_line_group(ms, p)
-    Wv, Wc = np.zeros((V, dim)), np.zeros((V, dim))
-    for r, mr in enumerate(ms):
-        rows = sdist.owned_rows(V, r, world)
-        Wv[rows], Wc[rows] = mr.get_rows(0), mr.get_rows(1)
-    touched = np.flatnonzero(np.abs(Wc).sum(1) > 0)
-    assert len(touched) > 10
+def test_exchange_stages_the_right_rows():
+    """K = 0, zero contexts, tiny alpha (sigmoid LUT stays in its 0.5 bin), vertex row v = [(v+1), 1, (v+1)^2, ...] * scale:
+    a context row then holds sum_i a_i * row(source_i). Contexts whose second moment equals the squared mean were fed by
+    ONE source vertex -- which must be a neighbour, whether its row was local or came through the exchange."""
+    off, col, ww, *_ = _sbm()
+    V, dim = len(off) - 1, 32
     adj = {v: set(col[off[v]:off[v + 1]].tolist()) for v in range(V)}
-    once = 0
-    for c in touched:
-        # a context hit exactly once holds 0.5 * v_src (sigmoid LUT(0) = 0.5, label 1, alpha 1) for one of its neighbours
-        cand = Wc[c, 0] / 0.5 / 1e-3 - 1
-        v = int(round(cand))
-        if abs(cand - v) < 1e-6 and 0 <= v < V and c in adj[v]:
-            once += 1
-    assert once >= 0.5 * len(touched)
-    # vertex rows only changed through contexts that were non-zero when read: a vertex row is its id plus small terms
-    assert np.abs(Wv - init_v).max() < 1.0
+    ids = np.arange(V) + 1.0
+    init_v = np.full((V, dim), 1e-4)
+    init_v[:, 0], init_v[:, 2] = ids * 1e-4, ids * ids * 1e-8
+    for world, sb, total in ((2, 1 << 15, 20000), (4, 1 << 15, 20000), (8, 1 << 11, 30000)):
+        ms = _exchange_shards(off, col, ww, V, dim, world, init_v, np.zeros((V, dim)), superbatch=sb, dtype=capi.F64)
+        p = _params(total, 9)
+        p.negative_samples, p.alpha = 0, 1e-6
+        capi.train_line_group(ms, p)
+        Wc = np.zeros((V, dim))
+        for r, mr in enumerate(ms):
+            Wc[sdist.owned_rows(V, r, world)] = mr.get_rows(1)
+        hit = np.flatnonzero(Wc[:, 1] > 0)
+        mean = Wc[hit, 0] / Wc[hit, 1]
+        var = Wc[hit, 2] / Wc[hit, 1] * 1e4 - mean * mean
+        single = np.abs(var) < 1e-6 * mean * mean + 1e-9
+        x = np.round(mean[single] - 1).astype(int)
+        good = np.array([xi in adj[c] for c, xi in zip(hit[single], x)])
+        remote = (x % world) != (hit[single] % world)
+        assert remote.sum() > 1000 and good[remote].mean() > 0.995, (world, remote.sum(), good[remote].mean())
+        assert good.mean() > 0.995
 
 
 def test_exchange_mode_quality_matches_unsharded():
+    """4 shards on one device, super-batches of 2^15 samples per shard. On this 12 k-vertex graph every vertex is drawn
+    ~11 times per super-batch, i.e. every vertex is HOT at the recommended threshold and keeps a single copy behind the
+    peer pointers; raising the threshold so that only the best-connected vertices are hot sends the rest through the
+    exchange with a super-batch small enough for the copies to stay equivalent."""
     off, col, ww, test_s, test_d, train_adj = _sbm()
     V, dim, total = len(off) - 1, 32, 12_000_000
     init = ((np.random.default_rng(1).random((V, dim)) - 0.5) / dim)
@@ -294,15 +301,18 @@ def test_exchange_mode_quality_matches_unsharded():
     m.train_line(_params(total, 13))
     base_auc, base_rec = evaluate(m.get_rows(0), m.get_rows(1), test_s, test_d, train_adj, np.random.default_rng(2))
     world = 4
-    ms = _exchange_shards(off, col, ww, V, dim, world, init, np.zeros((V, dim)), superbatch=1 << 15)
-    stats = capi.train_line_group(ms, _params(total, 100))
-    assert 0.9 * total <= sum(s["samples"] for s in stats) <= total
-    Wv, Wc = np.zeros((V, dim)), np.zeros((V, dim))
-    for r, mr in enumerate(ms):
-        rows = sdist.owned_rows(V, r, world)
-        Wv[rows], Wc[rows] = mr.get_rows(0), mr.get_rows(1)
-    auc_, rec_ = evaluate(Wv, Wc, test_s, test_d, train_adj, np.random.default_rng(2))
-    xs = ms[0].exchange_stats()
-    print(f"AUC unsharded {base_auc:.4f} exchange-mode(4) {auc_:.4f} | recall@10 {base_rec:.4f} vs {rec_:.4f} | {xs}")
-    assert abs(auc_ - base_auc) < 0.005
-    assert abs(rec_ - base_rec) < 0.005 + 0.05 * base_rec
+    for sb, hot in ((1 << 15, 0.25), (1 << 10, 0.36)):
+        ms = _exchange_shards(off, col, ww, V, dim, world, init, np.zeros((V, dim)), superbatch=sb, hot=hot)
+        stats = capi.train_line_group(ms, _params(total, 100))
+        assert 0.9 * total <= sum(s["samples"] for s in stats) <= total
+        Wv, Wc = np.zeros((V, dim)), np.zeros((V, dim))
+        for r, mr in enumerate(ms):
+            rows = sdist.owned_rows(V, r, world)
+            Wv[rows], Wc[rows] = mr.get_rows(0), mr.get_rows(1)
+        auc_, rec_ = evaluate(Wv, Wc, test_s, test_d, train_adj, np.random.default_rng(2))
+        xs = ms[0].exchange_stats()
+        print(f"sb={sb} hot>={hot}: AUC unsharded {base_auc:.4f} exchange-mode(4) {auc_:.4f} | recall@10 {base_rec:.4f} vs {rec_:.4f} | {xs}")
+        assert abs(auc_ - base_auc) < 0.005
+        assert abs(rec_ - base_rec) < 0.005 + 0.05 * base_rec
+        if hot == 0.36:
+            assert 0 < xs["hot_vertices"] < V and xs["rows_requested"] > 0  # both paths were exercised
