@@ -239,6 +239,10 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: smore_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    # stdout must carry exactly one JSON line: NCCL (torch's communicator and the library's own) prints its version banner
+    # with printf, so fd 1 points at stderr until the line is written
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         # NCCL writes its version / debug lines to stdout by default; stdout must carry exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -330,11 +334,12 @@ def run_ours(args):
 
     # ---- e2e: host buffers in, host buffers out, every step ----
     V = m.rows  # local rows (== g.V unless sharded)
-    hv = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
-    hc = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
-    m.get_rows(0, out=hv.numpy())
-    m.get_rows(1, out=hc.numpy())
-    hout = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
+    if not args.no_e2e:
+        hv = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
+        hc = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
+        m.get_rows(0, out=hv.numpy())
+        m.get_rows(1, out=hc.numpy())
+        hout = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
 
     def e2e_step():
         m.set_rows(0, hv.numpy())
@@ -343,18 +348,19 @@ def run_ours(args):
         m.get_rows(0, out=hout.numpy())
         return st
 
-    e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_updates = 0
-    for _ in range(args.steps):
-        e2e_updates += e2e_step()["samples"]
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_updates, e2e_ms = 0, float("nan")
+    if not args.no_e2e:
+        e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_updates += e2e_step()["samples"]
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
 
-    stats = torch.tensor([ms, e2e_ms, float(updates), float(e2e_updates), kernel_ms, float(launches)], dtype=torch.float64,
+    stats = torch.tensor([ms, 0.0 if args.no_e2e else e2e_ms, float(updates), float(e2e_updates), kernel_ms, float(launches)], dtype=torch.float64,
                          device="cuda")
     if world > 1:
         mx = stats.clone()
@@ -404,7 +410,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "k_line<float,4,1>", "algorithmic_bytes_per_update": ALGO_BYTES,
                      "peak_source": peak_src},
-        "e2e": {"value": e2e_updates / (e2e_ms * 1e-3), "unit": "updates/s",
+        "e2e": {"value": None if args.no_e2e else e2e_updates / (e2e_ms * 1e-3), "unit": "updates/s",
                 "h2d_bytes_per_step": 2 * V * DIM * 4, "d2h_bytes_per_step": V * DIM * 4,
                 "note": "per step: both tables uploaded from pinned host memory, Train call, vertex table read back"},
         "gpu_launches": int(launches), "clocks": clk,
@@ -414,7 +420,7 @@ def run_ours(args):
             out["cpu_baseline"] = cpu_baseline(edges, csr)
         except Exception as ex:  # the baseline is reporting only; never lose the GPU line
             out["cpu_baseline"] = {"value": None, "unit": "updates/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
-    print(json.dumps(out), flush=True)
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -428,11 +434,12 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 24, help="edge updates per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the host-buffer (e2e) leg")
     ap.add_argument("--grow-graph", action="store_true", help="N>1: grow the graph with N (1M vertices per GPU)")
     ap.add_argument("--parallelism", default="sharded", choices=["sharded", "sharded-replica", "sharded-exchange", "replicas"],
                     help="N>1 only")
     ap.add_argument("--superbatch", type=int, default=1 << 20, help="sharded-exchange: samples per GPU and super-batch")
-    ap.add_argument("--hot-threshold", type=float, default=0.25,
+    ap.add_argument("--hot-threshold", type=float, default=64.0,
                     help="sharded-exchange: expected source draws per super-batch above which a vertex keeps a single copy (<0: none)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -158,14 +158,15 @@ int smore_model_refresh_replica(smore_model_t m, int table);
  * update runs) in per-owner request lists, (2) the lists, the requested rows and -- after the updates -- the modified
  * rows travel as contiguous buffers in three all-to-alls (NCCL send/recv groups over NVLink), (3) the owner adds
  * `returned - sent` to its row.
- * HOT vertices. Copies of a row on several ranks are only equivalent to Hogwild on one copy while each copy receives few
- * updates per super-batch: once every copy runs a long update sequence of its own, the sum of the per-copy corrections
- * overshoots (measured: 4 shards of a 12 k-vertex graph, ~11 source samples per vertex and super-batch -> held-out AUC
- * 0.53 instead of 0.92; ~0.7 -> 0.9214). A vertex expected to be drawn as a source at least `hot_threshold` times per
- * super-batch (all ranks together; P(source) of the unsharded sampler x superbatch x world) therefore keeps a single copy
- * and is reached through the peer mappings exactly as in the peer-access mode (smore_model_open_peers required); the hot
- * set is small (hubs), so its peer footprint stays below the cliff. hot_threshold < 0: no hot vertices (pure exchange,
- * no peer mapping needed); 0: every vertex is hot (degenerates to the peer-access mode). Recommended: 0.25.
+ * HOT vertices. A staged copy is updated in place by every sample of its rank during the super-batch (duplicates are
+ * folded into one copy per rank), so what is stale is only the other ranks' view of the row, for one super-batch.
+ * Measured on a 12 k-vertex graph in 4 shards (worst case: every vertex is drawn 11-44 times per super-batch): held-out
+ * AUC 0.9207 / 0.9195 against 0.9218 unsharded. For extreme hubs the copies can still be avoided: a vertex expected to
+ * be drawn as a source at least `hot_threshold` times per super-batch (all ranks together; P(source) of the unsharded
+ * sampler x superbatch x world) keeps a single copy and is reached through the peer mappings exactly as in the
+ * peer-access mode (smore_model_open_peers required); the hot set is small, so its peer footprint stays below the cliff.
+ * hot_threshold < 0: no hot vertices (pure exchange, no peer mapping needed); 0: every vertex is hot (degenerates to the
+ * peer-access mode). Recommended: 64.
  * Replaces nothing in the reference (its tables live in one address space); it is the "NCCL all-to-all carries the
  * remote-row batches" half of the sharded store, next to the peer-access half above. */
 int smore_model_enable_exchange(smore_model_t m, int64_t superbatch, double hot_threshold);

@@ -315,7 +315,7 @@ class Model:
     def refresh_replica(self, table=0):
         check(lib().smore_model_refresh_replica(self.h, table))
 
-    def enable_exchange(self, superbatch=0, hot_threshold=0.25):
+    def enable_exchange(self, superbatch=0, hot_threshold=64.0):
         """Bulk-exchange mode (row-sharded LINE): remote vertex rows move in per-super-batch all-to-alls; vertices
         expected as a source >= hot_threshold times per super-batch stay single-copy behind the peer mappings
         (hot_threshold < 0: none)."""

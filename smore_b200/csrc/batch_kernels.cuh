@@ -163,14 +163,15 @@ __device__ __forceinline__ int exch_lookup(const ExchDev& x, int v1) {
 
 // One lane per sample: words [pos0 + s*wps, +2) of the warp's stream -> edge draw -> source vertex; remote sources are
 // inserted into the hash, the lane that creates an entry appends the row to the owner's request list. Must be launched
-// with the grid, `jobs`, seed and stream_base of the k_line<.., 3> launch that follows; the warp states are not advanced.
-static __global__ void __launch_bounds__(kBlockThreads) k_line_requests(GraphDev g, ExchDev x, const WarpState* state,
+// with the grid, `jobs`, seed and stream_base of the k_line<.., 3> launch it prepares. pos0 = stream position of every
+// warp at the start of that launch: a sample consumes exactly wps words, so the host knows it without reading the warp
+// states (the previous super-batch may still be running).
+static __global__ void __launch_bounds__(kBlockThreads) k_line_requests(GraphDev g, ExchDev x, uint64_t pos0,
                                                                         int n_warps, uint64_t jobs, uint64_t seed,
                                                                         uint64_t stream_base, int K) {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (w >= n_warps) return;
-    const uint64_t pos0 = state[w].pos;
     const uint64_t stream = stream_base + (uint64_t)w;
     const uint64_t wps = (uint64_t)batch_wps(2, K);
     const int mask = (1 << g.shard_shift) - 1;

@@ -20,7 +20,7 @@ namespace {
 
 constexpr int kW = smore_exchange_s::kW;
 
-void prefix(smore_exchange_s* x) {
+void prefix(ExchSet* x) {
     x->off_out[0] = x->off_in[0] = 0;
     for (int r = 0; r < kW; ++r) {
         x->off_out[r + 1] = x->off_out[r] + x->cnt_out[r];
@@ -37,11 +37,11 @@ struct Leg {
 
 // The leg of `what` that goes from shard `a` to shard `b` (both in this process: local transport) -- or, with b == null,
 // just the send half (src/bytes) and, with a == null, just the receive half (dst/bytes) as seen by the local shard.
-Leg leg(int what, smore_exchange_s* a, int ra, smore_exchange_s* b, int rb, size_t row_bytes) {
+Leg leg(int what, ExchSet* a, int64_t a_req_stride, int ra, ExchSet* b, int rb, size_t row_bytes) {
     Leg l{nullptr, nullptr, 0};
     switch (what) {
         case ExchTransport::REQ:  // requester a -> owner b
-            if (a) { l.src = (const char*)a->req.p + ((size_t)rb * (size_t)a->req_stride) * 4; l.bytes = (size_t)a->cnt_out[rb] * 4; }
+            if (a) { l.src = (const char*)a->req.p + ((size_t)rb * (size_t)a_req_stride) * 4; l.bytes = (size_t)a->cnt_out[rb] * 4; }
             if (b) { l.dst = (char*)b->req_in.p + (size_t)b->off_in[ra] * 4; l.bytes = (size_t)b->cnt_in[ra] * 4; }
             break;
         case ExchTransport::ROWS_OUT:  // owner a -> requester b
@@ -58,24 +58,25 @@ Leg leg(int what, smore_exchange_s* a, int ra, smore_exchange_s* b, int rb, size
 
 // ---- every shard in this process (tests: several shards on one device) -----------------------------------------------
 struct LocalTransport : ExchTransport {
-    int counts(smore_model_s** ms, int n) override {
+    int counts(smore_model_s** ms, int n, int b, cudaStream_t st) override {
         for (int r = 0; r < n; ++r) {
-            smore_exchange_s* x = ms[r]->xch;
+            ExchSet* x = &ms[r]->xch->set[b];
             memset(x->cnt_out, 0, sizeof(x->cnt_out));
             memset(x->cnt_in, 0, sizeof(x->cnt_in));
-            CU(cudaMemcpy(x->cnt_out, x->cnt.p, kW * sizeof(int), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpyAsync(x->cnt_out, x->cnt.p, kW * sizeof(int), cudaMemcpyDeviceToHost, st));
         }
+        CU(cudaStreamSynchronize(st));
         for (int r = 0; r < n; ++r)
-            for (int s = 0; s < n; ++s) ms[r]->xch->cnt_in[s] = ms[s]->xch->cnt_out[r];
-        for (int r = 0; r < n; ++r) prefix(ms[r]->xch);
+            for (int s = 0; s < n; ++s) ms[r]->xch->set[b].cnt_in[s] = ms[s]->xch->set[b].cnt_out[r];
+        for (int r = 0; r < n; ++r) prefix(&ms[r]->xch->set[b]);
         return SMORE_OK;
     }
-    int a2a(smore_model_s** ms, int n, int what, size_t row_bytes) override {
+    int a2a(smore_model_s** ms, int n, int b, int what, size_t row_bytes, cudaStream_t st) override {
         for (int a = 0; a < n; ++a)
-            for (int b = 0; b < n; ++b) {
-                if (a == b) continue;
-                Leg l = leg(what, ms[a]->xch, a, ms[b]->xch, b, row_bytes);
-                if (l.bytes) CU(cudaMemcpyAsync(l.dst, l.src, l.bytes, cudaMemcpyDeviceToDevice, 0));
+            for (int c = 0; c < n; ++c) {
+                if (a == c) continue;
+                Leg l = leg(what, &ms[a]->xch->set[b], ms[a]->xch->req_stride, a, &ms[c]->xch->set[b], c, row_bytes);
+                if (l.bytes) CU(cudaMemcpyAsync(l.dst, l.src, l.bytes, cudaMemcpyDeviceToDevice, st));
             }
         return SMORE_OK;
     }
@@ -119,21 +120,22 @@ int nccl_load() {
     } while (0)
 
 struct NcclTransport : ExchTransport {
-    int counts(smore_model_s** ms, int n) override {
+    int counts(smore_model_s** ms, int n, int b, cudaStream_t st) override {
         if (n != 1) return fail(SMORE_E_INVALID, "the NCCL transport drives exactly one shard per process");
-        smore_exchange_s* x = ms[0]->xch;
+        ExchSet* x = &ms[0]->xch->set[b];
         int* d_out = (int*)x->cnt.p;
         int* d_in = d_out + kW;
         const int me = g_nccl.rank;
         NC(g_nccl.GroupStart());
         for (int r = 0; r < g_nccl.world; ++r) {
             if (r == me) continue;
-            NC(g_nccl.Send(d_out + r, 1, ncclInt32, r, g_nccl.comm, 0));
-            NC(g_nccl.Recv(d_in + r, 1, ncclInt32, r, g_nccl.comm, 0));
+            NC(g_nccl.Send(d_out + r, 1, ncclInt32, r, g_nccl.comm, st));
+            NC(g_nccl.Recv(d_in + r, 1, ncclInt32, r, g_nccl.comm, st));
         }
         NC(g_nccl.GroupEnd());
         int both[2 * kW];
-        CU(cudaMemcpy(both, d_out, sizeof(both), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(both, d_out, sizeof(both), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
         memset(x->cnt_out, 0, sizeof(x->cnt_out));
         memset(x->cnt_in, 0, sizeof(x->cnt_in));
         for (int r = 0; r < g_nccl.world; ++r)
@@ -141,17 +143,18 @@ struct NcclTransport : ExchTransport {
         prefix(x);
         return SMORE_OK;
     }
-    int a2a(smore_model_s** ms, int n, int what, size_t row_bytes) override {
+    int a2a(smore_model_s** ms, int n, int b, int what, size_t row_bytes, cudaStream_t st) override {
         if (n != 1) return fail(SMORE_E_INVALID, "the NCCL transport drives exactly one shard per process");
-        smore_exchange_s* x = ms[0]->xch;
+        ExchSet* x = &ms[0]->xch->set[b];
+        const int64_t stride = ms[0]->xch->req_stride;
         const int me = g_nccl.rank;
         NC(g_nccl.GroupStart());
         for (int r = 0; r < g_nccl.world; ++r) {
             if (r == me) continue;
-            Leg s = leg(what, x, me, nullptr, r, row_bytes);   // what I send to r
-            Leg d = leg(what, nullptr, r, x, me, row_bytes);   // what I receive from r
-            if (s.bytes) NC(g_nccl.Send(s.src, s.bytes, ncclInt8, r, g_nccl.comm, 0));
-            if (d.bytes) NC(g_nccl.Recv(d.dst, d.bytes, ncclInt8, r, g_nccl.comm, 0));
+            Leg s = leg(what, x, stride, me, nullptr, r, row_bytes);  // what I send to r
+            Leg d = leg(what, nullptr, 0, r, x, me, row_bytes);       // what I receive from r
+            if (s.bytes) NC(g_nccl.Send(s.src, s.bytes, ncclInt8, r, g_nccl.comm, st));
+            if (d.bytes) NC(g_nccl.Recv(d.dst, d.bytes, ncclInt8, r, g_nccl.comm, st));
         }
         NC(g_nccl.GroupEnd());
         return SMORE_OK;

@@ -20,16 +20,22 @@ struct DevBuf {
     ~DevBuf() { cudaFree(p); }
 };
 
-struct smore_exchange_s {
+// Everything one super-batch in flight needs; two sets alternate so that the exchange of super-batch i+1 overlaps the
+// updates of super-batch i.
+struct ExchSet {
     static constexpr int kW = 8;  // == kMaxWorld
+    DevBuf hkey, hval, req, cnt /* [2][kW] int32: out, in */, off /* [kW] int32 */, wrk, req_in, sent, back;
+    int cnt_out[kW] = {}, cnt_in[kW] = {};
+    int64_t off_out[kW + 1] = {}, off_in[kW + 1] = {};
+};
+
+struct smore_exchange_s {
+    static constexpr int kW = ExchSet::kW;
     int64_t superbatch = 0;       // samples per rank and super-batch (target)
     double hot_threshold = 0;     // a vertex expected to be a source >= this many times per super-batch (all ranks) is HOT
     int64_t n_hot = 0;
     DevBuf hot;                   // bitmap over vertex ids, null when n_hot == 0
-    DevBuf hkey, hval, req, cnt /* [2][kW] int32: out, in */, off /* [kW] int32 */, wrk, req_in, sent, back;
-    // host mirror of the super-batch in flight
-    int cnt_out[kW] = {}, cnt_in[kW] = {};
-    int64_t off_out[kW + 1] = {}, off_in[kW + 1] = {};
+    ExchSet set[2];
     int64_t req_stride = 0;
     // totals of the last train call
     uint64_t st_rows_moved = 0, st_superbatches = 0;
@@ -38,9 +44,9 @@ struct smore_exchange_s {
 struct ExchTransport {
     enum { REQ = 0, ROWS_OUT = 1, ROWS_BACK = 2 };
     virtual ~ExchTransport() {}
-    // device cnt_out of every shard -> host cnt_out / cnt_in / off_out / off_in of every shard (host-synchronous)
-    virtual int counts(smore_model_s** ms, int n) = 0;
-    virtual int a2a(smore_model_s** ms, int n, int what, size_t row_bytes) = 0;
+    // device cnt_out of set b of every shard -> host cnt_out / cnt_in / off_out / off_in (synchronises `st` only)
+    virtual int counts(smore_model_s** ms, int n, int b, cudaStream_t st) = 0;
+    virtual int a2a(smore_model_s** ms, int n, int b, int what, size_t row_bytes, cudaStream_t st) = 0;
 };
 
 ExchTransport* exch_local_transport();

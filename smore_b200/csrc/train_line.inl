@@ -41,7 +41,31 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
 
 // ---- bulk-exchange mode (exchange_host.h; device side: batch_kernels.cuh) --------------------------------------------
 // Every rank runs the same number of super-batches (the collectives must match): nsb = ceil(total / (superbatch*world)),
-// and splits its own share of the samples evenly over them.
+// and splits its own share of the samples evenly over them. Two streams: `sc` carries everything that moves rows
+// (requests, gather, the three all-to-alls, apply), `su` the update kernels; two buffer sets alternate, so that while
+// super-batch i is being updated the rows of super-batch i+1 are already being requested, gathered and shipped:
+//     sc:  PREP(0)  PREP(1)  FINISH(0)  PREP(2)  FINISH(1)  ...
+//     su:  UPDATE(0)         UPDATE(1)           UPDATE(2)  ...        UPDATE(i) waits for PREP(i), FINISH(i) for UPDATE(i)
+// PREP(i+1) gathers rows that UPDATE(i) may still be changing and FINISH(i) has not yet corrected: the staged copies
+// are one super-batch staler than without the overlap; the owner still adds exactly `returned - sent`.
+namespace {
+struct ExchStreams {
+    cudaStream_t sc = nullptr, su = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, updated[2] = {nullptr, nullptr};
+    int init() {
+        if (sc) return SMORE_OK;
+        CU(cudaStreamCreate(&sc));  // blocking streams: the legacy-stream timing events order against both
+        CU(cudaStreamCreate(&su));
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaEventCreateWithFlags(&ready[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&updated[b], cudaEventDisableTiming));
+        }
+        return SMORE_OK;
+    }
+};
+ExchStreams g_xs;
+}  // namespace
+
 template <typename T>
 int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p, ExchTransport& tr) {
     smore_model_s* m0 = ms[0];
@@ -56,12 +80,17 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
         else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
+        if (int rc = g_xs.init()) return rc;
+        cudaStream_t sc = g_xs.sc, su = g_xs.su;
         const size_t row_bytes = (size_t)m0->dim * sizeof(T);
+        const uint64_t wps = (uint64_t)batch_wps(2, p->negative_samples);
         const uint64_t per_sb = (uint64_t)m0->xch->superbatch * (uint64_t)world;
         const uint64_t nsb = std::max<uint64_t>(1, (p->total + per_sb - 1) / per_sb);
         struct Shard {
             TrainArgs<T> a;
-            uint64_t trips, jobs_sb, done;
+            uint64_t trips, jobs_sb, prepared, done;  // per-warp samples: total, per super-batch, requested, launched
+            uint64_t jobs_of[2];                      // per-warp samples of the super-batch held by each buffer set
+            uint32_t hmask;
         };
         std::vector<Shard> sh((size_t)n);
         for (int i = 0; i < n; ++i) {
@@ -72,95 +101,128 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
             Shard& s = sh[(size_t)i];
             s.trips = cpp ? (jobs > 0 ? jobs - 1 : 0) : jobs;
             s.jobs_sb = (s.trips + nsb - 1) / nsb;
-            s.done = 0;
+            s.prepared = s.done = 0;
             if (int rc = init_state(m, L.warps, cpp ? 1 : 0, p->alpha, p)) return rc;
             s.a = base_args<T>(m, p, L.warps, (double)total_local, cpp ? 1 : 0, vtab, ctab, m->g->src_mass_frac);
             if (n > 1) s.a.stream_base += (uint64_t)m->g->rank << 20;  // one call drives all the shards: disjoint streams
-            // per-super-batch buffers on the requester side
             const uint64_t sb_samples = std::max<uint64_t>(1, s.jobs_sb * (uint64_t)L.warps);
             uint64_t hsize = 1024;
             while (hsize < 2 * sb_samples) hsize <<= 1;
             if (hsize > (1ull << 30)) return fail(SMORE_E_INVALID, "super-batch too large");
+            s.hmask = (uint32_t)(hsize - 1);
             x->req_stride = (int64_t)sb_samples;
-            if (int rc = x->hkey.ensure(hsize * 4)) return rc;
-            if (int rc = x->hval.ensure(hsize * 4)) return rc;
-            if (int rc = x->req.ensure((size_t)world * sb_samples * 4)) return rc;
-            if (int rc = x->cnt.ensure(2 * kMaxWorld * 4)) return rc;
-            if (int rc = x->off.ensure(kMaxWorld * 4)) return rc;
-            s.a.x = ExchDev{(int32_t*)x->hkey.p, (int32_t*)x->hval.p, (uint32_t)(hsize - 1), (int32_t*)x->req.p,
-                            x->req_stride, (int32_t*)x->cnt.p, (const int32_t*)x->off.p, nullptr,
-                            x->n_hot ? (const uint32_t*)x->hot.p : nullptr};
+            for (int b = 0; b < 2; ++b) {
+                ExchSet& e = x->set[b];
+                if (int rc = e.hkey.ensure(hsize * 4)) return rc;
+                if (int rc = e.hval.ensure(hsize * 4)) return rc;
+                if (int rc = e.req.ensure((size_t)world * sb_samples * 4)) return rc;
+                if (int rc = e.cnt.ensure(2 * kMaxWorld * 4)) return rc;
+                if (int rc = e.off.ensure(kMaxWorld * 4)) return rc;
+            }
             x->st_rows_moved = 0;
             x->st_superbatches = nsb;
         }
+        auto dev_of = [&](int i, int b) {
+            smore_exchange_s* x = ms[i]->xch;
+            ExchSet& e = x->set[b];
+            return ExchDev{(int32_t*)e.hkey.p, (int32_t*)e.hval.p, sh[(size_t)i].hmask, (int32_t*)e.req.p, x->req_stride,
+                           (int32_t*)e.cnt.p, (const int32_t*)e.off.p, e.wrk.p, x->n_hot ? (const uint32_t*)x->hot.p : nullptr};
+        };
         int dev = 0, sms = 0;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const int row_blocks = sms * 8;
-        Timer t;
-        if (int rc = t.start()) return rc;
-        for (uint64_t sb = 0; sb < nsb; ++sb) {
-            // 1. which remote vertex rows will this super-batch touch?
+
+        // PREP: which remote rows does super-batch `sb` need? -> request lists -> owners gather -> rows to the requesters
+        auto prep = [&](uint64_t sb) -> int {
+            const int b = (int)(sb & 1);
             for (int i = 0; i < n; ++i) {
                 Shard& s = sh[(size_t)i];
-                smore_exchange_s* x = ms[i]->xch;
-                s.a.jobs = std::min<uint64_t>(s.jobs_sb, s.trips - s.done);
-                CU(cudaMemsetAsync(x->hkey.p, 0xff, ((size_t)s.a.x.hmask + 1) * 4, 0));
-                CU(cudaMemsetAsync(x->cnt.p, 0, 2 * kMaxWorld * 4, 0));
-                if (s.a.jobs) {
-                    k_line_requests<<<L.blocks, kBlockThreads>>>(s.a.g, s.a.x, s.a.state, L.warps, s.a.jobs, s.a.seed,
-                                                                s.a.stream_base, s.a.K);
+                ExchSet& e = ms[i]->xch->set[b];
+                const uint64_t jobs = std::min<uint64_t>(s.jobs_sb, s.trips - s.prepared);
+                s.jobs_of[b] = jobs;
+                CU(cudaMemsetAsync(e.hkey.p, 0xff, ((size_t)s.hmask + 1) * 4, sc));
+                CU(cudaMemsetAsync(e.cnt.p, 0, 2 * kMaxWorld * 4, sc));
+                if (jobs) {
+                    k_line_requests<<<L.blocks, kBlockThreads, 0, sc>>>(s.a.g, dev_of(i, b), s.prepared * wps, L.warps, jobs,
+                                                                        s.a.seed, s.a.stream_base, s.a.K);
                     g_launches++;
                 }
+                s.prepared += jobs;
             }
             CU(cudaGetLastError());
-            if (int rc = tr.counts(ms, n)) return rc;
+            if (int rc = tr.counts(ms, n, b, sc)) return rc;
             for (int i = 0; i < n; ++i) {
                 smore_exchange_s* x = ms[i]->xch;
-                const size_t n_out = (size_t)x->off_out[kMaxWorld], n_in = (size_t)x->off_in[kMaxWorld];
-                if (int rc = x->wrk.ensure(std::max<size_t>(n_out, 1) * row_bytes)) return rc;
-                if (int rc = x->req_in.ensure(std::max<size_t>(n_in, 1) * 4)) return rc;
-                if (int rc = x->sent.ensure(std::max<size_t>(n_in, 1) * row_bytes)) return rc;
-                if (int rc = x->back.ensure(std::max<size_t>(n_in, 1) * row_bytes)) return rc;
+                ExchSet& e = x->set[b];
+                const size_t n_out = (size_t)e.off_out[kMaxWorld], n_in = (size_t)e.off_in[kMaxWorld];
+                // (a buffer that has to grow is reallocated: cudaFree waits for the whole device, rare after super-batch 0)
+                if (int rc = e.wrk.ensure(std::max<size_t>(n_out, 1) * row_bytes)) return rc;
+                if (int rc = e.req_in.ensure(std::max<size_t>(n_in, 1) * 4)) return rc;
+                if (int rc = e.sent.ensure(std::max<size_t>(n_in, 1) * row_bytes)) return rc;
+                if (int rc = e.back.ensure(std::max<size_t>(n_in, 1) * row_bytes)) return rc;
                 int32_t off32[kMaxWorld];
-                for (int r = 0; r < kMaxWorld; ++r) off32[r] = (int32_t)x->off_out[r];
-                CU(cudaMemcpyAsync(x->off.p, off32, sizeof(off32), cudaMemcpyHostToDevice, 0));
-                sh[(size_t)i].a.x.wrk = x->wrk.p;
+                for (int r = 0; r < kMaxWorld; ++r) off32[r] = (int32_t)e.off_out[r];
+                CU(cudaMemcpyAsync(e.off.p, off32, sizeof(off32), cudaMemcpyHostToDevice, sc));
                 x->st_rows_moved += n_out;
             }
-            // 2. request lists to the owners; owners gather the rows; rows to the requesters
-            if (int rc = tr.a2a(ms, n, ExchTransport::REQ, row_bytes)) return rc;
+            if (int rc = tr.a2a(ms, n, b, ExchTransport::REQ, row_bytes, sc)) return rc;
             for (int i = 0; i < n; ++i) {
-                smore_exchange_s* x = ms[i]->xch;
-                const int64_t n_in = x->off_in[kMaxWorld];
+                ExchSet& e = ms[i]->xch->set[b];
+                const int64_t n_in = e.off_in[kMaxWorld];
                 if (n_in) {
-                    k_gather_rows<C><<<row_blocks, kBlockThreads>>>((const T*)ms[i]->tab[vtab], (const int32_t*)x->req_in.p,
-                                                                    n_in, (T*)x->sent.p, ms[i]->dim);
+                    k_gather_rows<C><<<row_blocks, kBlockThreads, 0, sc>>>((const T*)ms[i]->tab[vtab], (const int32_t*)e.req_in.p,
+                                                                           n_in, (T*)e.sent.p, ms[i]->dim);
                     g_launches++;
                 }
             }
-            if (int rc = tr.a2a(ms, n, ExchTransport::ROWS_OUT, row_bytes)) return rc;
-            // 3. the updates: every row access is local
+            if (int rc = tr.a2a(ms, n, b, ExchTransport::ROWS_OUT, row_bytes, sc)) return rc;
+            CU(cudaEventRecord(g_xs.ready[b], sc));
+            return SMORE_OK;
+        };
+        // UPDATE: every row access is local (or a hot row behind a peer mapping)
+        auto update = [&](uint64_t sb) -> int {
+            const int b = (int)(sb & 1);
+            CU(cudaStreamWaitEvent(su, g_xs.ready[b], 0));
             for (int i = 0; i < n; ++i) {
                 Shard& s = sh[(size_t)i];
+                s.a.jobs = s.jobs_of[b];
+                s.a.x = dev_of(i, b);
                 if (s.a.jobs) {
-                    kern<<<L.blocks, kBlockThreads, smem>>>(s.a);
+                    kern<<<L.blocks, kBlockThreads, smem, su>>>(s.a);
                     g_launches++;
                     s.done += s.a.jobs;
                 }
             }
-            // 4. rows back to their owners, who add what changed
-            if (int rc = tr.a2a(ms, n, ExchTransport::ROWS_BACK, row_bytes)) return rc;
+            CU(cudaEventRecord(g_xs.updated[b], su));
+            return SMORE_OK;
+        };
+        // FINISH: rows back to their owners, who add what changed
+        auto finish = [&](uint64_t sb) -> int {
+            const int b = (int)(sb & 1);
+            CU(cudaStreamWaitEvent(sc, g_xs.updated[b], 0));
+            if (int rc = tr.a2a(ms, n, b, ExchTransport::ROWS_BACK, row_bytes, sc)) return rc;
             for (int i = 0; i < n; ++i) {
-                smore_exchange_s* x = ms[i]->xch;
-                const int64_t n_in = x->off_in[kMaxWorld];
+                ExchSet& e = ms[i]->xch->set[b];
+                const int64_t n_in = e.off_in[kMaxWorld];
                 if (n_in) {
-                    k_apply_delta<C><<<row_blocks, kBlockThreads>>>((T*)ms[i]->tab[vtab], (const int32_t*)x->req_in.p, n_in,
-                                                                    (const T*)x->back.p, (const T*)x->sent.p, ms[i]->dim);
+                    k_apply_delta<C><<<row_blocks, kBlockThreads, 0, sc>>>((T*)ms[i]->tab[vtab], (const int32_t*)e.req_in.p, n_in,
+                                                                           (const T*)e.back.p, (const T*)e.sent.p, ms[i]->dim);
                     g_launches++;
                 }
             }
             CU(cudaGetLastError());
+            return SMORE_OK;
+        };
+
+        Timer t;
+        if (int rc = t.start()) return rc;
+        if (int rc = prep(0)) return rc;
+        for (uint64_t sb = 0; sb < nsb; ++sb) {
+            if (int rc = update(sb)) return rc;
+            if (sb + 1 < nsb)
+                if (int rc = prep(sb + 1)) return rc;
+            if (int rc = finish(sb)) return rc;
         }
         double ms_total = 0;
         if (int rc = t.stop(&ms_total)) return rc;

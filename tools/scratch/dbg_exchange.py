@@ -20,7 +20,7 @@ def report(tag, Wv, Wc):
     a, r = evaluate(Wv, Wc, test_s, test_d, train_adj, np.random.default_rng(2))
     print(f"{tag}: AUC {a:.4f} rec {r:.4f} |dWv| {np.linalg.norm(Wv - init):.3f} |Wc| {np.linalg.norm(Wc):.3f} max|Wv| {np.abs(Wv).max():.3f}", flush=True)
 
-for world, sb, hot in ((4, 1 << 15, 0.25), (4, 1 << 15, 0.0), (4, 1 << 10, 0.36), (4, 1 << 10, -1.0), (4, 1 << 10, 1e9), (4, 1 << 12, -1.0), (4, 1<<13, -1.0), (4, 1 << 15, 12.0)):
+for world, sb, hot in ((4, 1 << 15, -1.0), (4, 1 << 17, -1.0), (8, 1 << 15, -1.0), (8, 1 << 15, 0.25)):
     ms = _exchange_shards(off, col, ww, V, dim, world, init, np.zeros((V, dim)), superbatch=sb, hot=hot)
     capi.train_line_group(ms, _params(total, 100))
     report(f"exchange world={world} sb={sb} hot={hot} {ms[0].exchange_stats()}", *collect(ms, world))
