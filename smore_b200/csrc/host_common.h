@@ -121,10 +121,11 @@ struct Launch {
 };
 
 template <class K>
-int pick_grid(K kernel, size_t smem, int max_warps, uint64_t work_items, Launch& out) {
+int pick_grid(K kernel, size_t smem, int max_warps, uint64_t work_items, Launch& out, int sms_override = 0) {
     int dev = 0, sms = 0, occ = 0;
     CU(cudaGetDevice(&dev));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (sms_override > 0) sms = sms_override;  // the kernel runs on an SM partition (green context)
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlockThreads, smem));
     if (occ < 1) return fail(SMORE_E_CUDA, "kernel does not fit on an SM");
     int64_t warps = (int64_t)sms * occ * kWarpsPerBlock;  // persistent grid: every CTA resident, a multiple of the SM count
