@@ -78,6 +78,12 @@ int smore_graph_create(int64_t V, int64_t E, const int64_t* row_off, const int32
 int smore_graph_load_edge_list(const char* path, int undirected, int semantics, int negative_method,
                                smore_graph_t* out);
 
+/* The ingest alone, on the host (no device involved; multi-threaded, SMORE_HOST_THREADS): the CSR and the vertex names
+ * smore_graph_load_edge_list would build. Two-call pattern: pass NULL arrays to get V, E, n_lines and names_bytes, then
+ * arrays of V+1 / E / E entries and a names buffer (the names in id order, each terminated by '\n'). */
+int smore_edge_list_to_csr(const char* path, int undirected, int64_t* V, int64_t* E, int64_t* n_lines, int64_t* row_off,
+                           int32_t* col, double* weight, char* names, int64_t names_cap, int64_t* names_bytes);
+
 /* HOP-Rec field metadata: proNet::LoadFieldMeta (src/proNet.cpp:330-408): `vertex field` lines, field ids in
  * first-appearance order; HOP-Rec treats field 0 as "user" (src/model/HBPR.cpp:98). */
 int smore_graph_load_field(smore_graph_t g, const char* path);
@@ -183,6 +189,10 @@ int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows
  * format 0 = C++ iostream default (%g, 6 significant digits; src/model/LINE.cpp:13-47),
  * format 1 = Go "%.6f" (internal/models/line/line.go:209-233). */
 int smore_model_save_weights(smore_model_t m, int table, const char* path, int format);
+/* The writer's formatter on host rows (no device involved; multi-threaded): `<first_id + r> v0 v1 ...\n` per row, in the
+ * number format of the chosen reference writer. Returns the byte count of the text (written to `out` when it fits in
+ * `cap`; call with out = NULL to size the buffer) or a negative error. */
+int64_t smore_format_rows(const double* rows, int64_t n, int dim, int64_t first_id, int format, char* out, int64_t cap);
 
 /* ---- training: each call replaces one reference Train() body ------------------------------------------------------ */
 

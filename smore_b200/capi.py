@@ -25,7 +25,7 @@ u64, i64, f64, vp = C.c_uint64, C.c_int64, C.c_double, C.c_void_p
 # Every symbol include/smore_b200.h declares (tests check the library exports each one).
 EXPORTS = [
     "smore_init", "smore_last_error", "smore_version", "smore_kernel_launches",
-    "smore_graph_create", "smore_graph_load_edge_list", "smore_graph_load_field", "smore_graph_set_field",
+    "smore_graph_create", "smore_graph_load_edge_list", "smore_edge_list_to_csr", "smore_graph_load_field", "smore_graph_set_field",
     "smore_graph_info", "smore_graph_get_csr", "smore_graph_vertex_name", "smore_graph_get_alias",
     "smore_graph_get_field", "smore_graph_destroy", "smore_sample_debug", "smore_walk_debug",
     "smore_model_create", "smore_model_init", "smore_model_set_rows", "smore_model_get_rows",
@@ -33,7 +33,7 @@ EXPORTS = [
     "smore_graph_set_shard", "smore_graph_shard_info", "smore_model_ipc_handle", "smore_model_open_peers",
     "smore_model_set_peer_ptrs", "smore_model_enable_replica", "smore_model_refresh_replica",
     "smore_model_enable_exchange", "smore_dist_nccl_unique_id", "smore_dist_nccl_init", "smore_dist_nccl_shutdown",
-    "smore_train_line_group", "smore_exchange_stats", "smore_model_save_weights", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
+    "smore_train_line_group", "smore_exchange_stats", "smore_model_save_weights", "smore_format_rows", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
     "smore_train_warp", "smore_train_hoprec", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
 ]
 
@@ -67,6 +67,8 @@ def lib():
         L.smore_init.argtypes = [C.c_int]
         L.smore_graph_create.argtypes = [i64, i64, vp, vp, vp, i64, C.c_int, C.c_int, C.POINTER(vp)]
         L.smore_graph_load_edge_list.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.smore_edge_list_to_csr.argtypes = [C.c_char_p, C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, vp, vp,
+                                             i64, C.POINTER(i64)]
         L.smore_graph_load_field.argtypes = [vp, C.c_char_p]
         L.smore_graph_set_field.argtypes = [vp, vp]
         L.smore_graph_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
@@ -102,6 +104,8 @@ def lib():
         L.smore_dist_nccl_shutdown.argtypes = []
         L.smore_train_line_group.argtypes = [vp, C.c_int, C.POINTER(TrainParams)]
         L.smore_exchange_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i64)]
+        L.smore_format_rows.argtypes = [vp, i64, C.c_int, i64, C.c_int, vp, i64]
+        L.smore_format_rows.restype = i64
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
         L.smore_train_params_default.restype = None
         for name in ("smore_train_line", "smore_train_bpr", "smore_train_warp", "smore_train_hoprec",
@@ -148,6 +152,33 @@ def nccl_init(uid: bytes, rank: int, world: int):
 
 def nccl_shutdown():
     check(lib().smore_dist_nccl_shutdown())
+
+
+def edge_list_to_csr(path, undirected):
+    """Host-only ingest: (row_off, col, w, names, n_lines) exactly as Graph.from_edge_list would build them."""
+    V, E, n, nb = i64(), i64(), i64(), i64()
+    check(lib().smore_edge_list_to_csr(os.fsencode(path), int(undirected), C.byref(V), C.byref(E), C.byref(n), None, None, None,
+                                       None, 0, C.byref(nb)))
+    off = np.zeros(V.value + 1, dtype=np.int64)
+    col = np.zeros(E.value, dtype=np.int32)
+    w = np.zeros(E.value)
+    names = C.create_string_buffer(max(1, nb.value))
+    check(lib().smore_edge_list_to_csr(os.fsencode(path), int(undirected), C.byref(V), C.byref(E), C.byref(n), _ptr(off), _ptr(col),
+                                       _ptr(w), C.cast(names, vp), nb.value, C.byref(nb)))
+    return off, col, w, names.raw[: nb.value].decode().split("\n")[:-1], n.value
+
+
+def format_rows(rows, first_id=0, fmt=0) -> bytes:
+    """The embedding writer's text for host rows (host-only: usable without a GPU)."""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    n, dim = rows.shape
+    need = lib().smore_format_rows(_ptr(rows), n, dim, first_id, fmt, None, 0)
+    if need < 0:
+        check(int(need))
+    buf = C.create_string_buffer(int(need))
+    got = lib().smore_format_rows(_ptr(rows), n, dim, first_id, fmt, C.cast(buf, vp), need)
+    assert got == need
+    return buf.raw[:need]
 
 
 def kernel_launches() -> int:

@@ -45,10 +45,12 @@ int upload_graph(smore_graph_s* g) {
     if (int rc = dev_alloc_copy(&g->d_col, g->col.data(), (size_t)E)) return rc;
     auto pack_table = [&](const AliasHost& t, std::vector<uint2>& out) {
         out.resize(t.prob.size());
-        for (size_t i = 0; i < t.prob.size(); ++i) {
-            PackedAlias p = pack_alias(t.prob[i], t.alias[i], (uint32_t)i);
-            out[i] = make_uint2(p.thr, p.alias);
-        }
+        parallel_for((int64_t)t.prob.size(), 1 << 16, [&](int64_t b, int64_t e, int) {
+            for (int64_t i = b; i < e; ++i) {
+                PackedAlias p = pack_alias(t.prob[(size_t)i], t.alias[(size_t)i], (uint32_t)i);
+                out[(size_t)i] = make_uint2(p.thr, p.alias);
+            }
+        });
     };
     std::vector<uint2> packed;
     pack_table(g->vertex_at, packed);
@@ -58,20 +60,24 @@ int upload_graph(smore_graph_s* g) {
     if (g->sem == SMORE_SEM_CPP) {
         // context table: alias entries are already vertex ids (src/proNet.cpp:530-534); "self" = the entry's own target
         packed.resize((size_t)E);
-        for (int64_t e = 0; e < E; ++e) {
-            PackedAlias p = pack_alias(g->ctx_at.prob[(size_t)e], g->ctx_at.alias[(size_t)e], (uint32_t)g->col[(size_t)e]);
-            packed[(size_t)e] = make_uint2(p.thr, p.alias);
-        }
+        parallel_for(E, 1 << 16, [&](int64_t b, int64_t en, int) {
+            for (int64_t e = b; e < en; ++e) {
+                PackedAlias p = pack_alias(g->ctx_at.prob[(size_t)e], g->ctx_at.alias[(size_t)e], (uint32_t)g->col[(size_t)e]);
+                packed[(size_t)e] = make_uint2(p.thr, p.alias);
+            }
+        });
         if (int rc = dev_alloc_copy(&g->d_cat, packed.data(), packed.size())) return rc;
     } else {
         std::vector<double> prefix((size_t)E);
-        for (int64_t v = 0; v < V; ++v) {
-            double cum = 0.0;  // pronet.go:274-281: cumWeight += w in adjacency order
-            for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) {
-                cum += g->w[(size_t)e];
-                prefix[(size_t)e] = cum;
+        parallel_for(V, 1 << 14, [&](int64_t vb, int64_t ve, int) {
+            for (int64_t v = vb; v < ve; ++v) {
+                double cum = 0.0;  // pronet.go:274-281: cumWeight += w in adjacency order
+                for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) {
+                    cum += g->w[(size_t)e];
+                    prefix[(size_t)e] = cum;
+                }
             }
-        }
+        });
         if (int rc = dev_alloc_copy(&g->d_prefix, prefix.data(), prefix.size())) return rc;
     }
     g->field.assign((size_t)V, 0);
@@ -104,9 +110,11 @@ int build_graph(smore_graph_s* g) {
     g->in_deg.assign((size_t)V, 0.0);
     std::vector<double>&out_deg = g->out_deg, &in_deg = g->in_deg;
     std::vector<double> dist((size_t)V);
-    for (int64_t v = 0; v < V; ++v)
-        for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) out_deg[(size_t)v] += g->w[(size_t)e];
-    for (int64_t e = 0; e < E; ++e) in_deg[(size_t)g->col[(size_t)e]] += g->w[(size_t)e];
+    parallel_for(V, 1 << 14, [&](int64_t vb, int64_t ve, int) {  // per-vertex sums keep their in-order accumulation
+        for (int64_t v = vb; v < ve; ++v)
+            for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) out_deg[(size_t)v] += g->w[(size_t)e];
+    });
+    for (int64_t e = 0; e < E; ++e) in_deg[(size_t)g->col[(size_t)e]] += g->w[(size_t)e];  // order-dependent fp sum: serial
     if (g->sem == SMORE_SEM_CPP) {
         g->vertex_at = alias_method_cpp(out_deg.data(), V);  // vertex_method "out_degrees" (src/proNet.cpp:458-464)
         for (int64_t v = 0; v < V; ++v) {
@@ -117,14 +125,30 @@ int build_graph(smore_graph_s* g) {
         g->negative_at = alias_method_cpp(dist.data(), V);
         g->ctx_at.prob.resize((size_t)E);
         g->ctx_at.alias.resize((size_t)E);
-        for (int64_t v = 0; v < V; ++v) {  // per-vertex sub-tables in CSR order (src/proNet.cpp:519-536)
-            const int64_t o = g->row_off[(size_t)v], b = g->row_off[(size_t)v + 1] - o;
-            if (b == 0) continue;
-            AliasHost sub = alias_method_cpp(g->w.data() + o, b);
-            for (int64_t i = 0; i < b; ++i) {
-                g->ctx_at.prob[(size_t)(o + i)] = sub.prob[(size_t)i];
-                g->ctx_at.alias[(size_t)(o + i)] = sub.alias[(size_t)i] != -1 ? (int64_t)g->col[(size_t)(o + sub.alias[(size_t)i])] : -1;
+        // per-vertex sub-tables in CSR order (src/proNet.cpp:519-536): independent of each other -> one slice of vertices
+        // per host thread, built in place (E pow() calls and E Vose steps: the bulk of the reference's start-up time)
+        {
+            const int nt = host_threads();
+            const int64_t per = std::max<int64_t>(1, E / (int64_t)nt);  // slices balanced by CSR entries, not by vertices
+            std::vector<int64_t> cut{0};
+            for (int k = 1; k < nt; ++k) {
+                const int64_t v = std::upper_bound(g->row_off.begin(), g->row_off.end(), per * k) - g->row_off.begin() - 1;
+                cut.push_back(std::max(cut.back(), std::min(v, V)));
             }
+            cut.push_back(V);
+            parallel_for((int64_t)cut.size() - 1, 1, [&](int64_t sb, int64_t se, int) {
+                AliasScratch sc;
+                for (int64_t s = sb; s < se; ++s)
+                    for (int64_t v = cut[(size_t)s]; v < cut[(size_t)s + 1]; ++v) {
+                        const int64_t o = g->row_off[(size_t)v], b = g->row_off[(size_t)v + 1] - o;
+                        if (b == 0) continue;
+                        double* pr = g->ctx_at.prob.data() + o;
+                        int64_t* al = g->ctx_at.alias.data() + o;
+                        alias_method_cpp_into(g->w.data() + o, b, pr, al, sc);
+                        for (int64_t i = 0; i < b; ++i)  // alias entries become vertex ids (src/proNet.cpp:530-534)
+                            if (al[i] != -1) al[i] = (int64_t)g->col[(size_t)(o + al[i])];
+                    }
+            });
         }
     } else {
         g->vertex_at = alias_method_go(out_deg.data(), V, 1.0);  // pronet.go:224-230
@@ -251,6 +275,34 @@ int smore_graph_load_edge_list(const char* path, int undirected, int semantics, 
     int rc = build_graph(g);
     if (rc) { delete g; return rc; }
     *out = g;
+    return SMORE_OK;
+}
+
+int smore_edge_list_to_csr(const char* path, int undirected, int64_t* V, int64_t* E, int64_t* n_lines, int64_t* row_off,
+                           int32_t* col, double* weight, char* names, int64_t names_cap, int64_t* names_bytes) {
+    if (!path) return fail(SMORE_E_INVALID, "null path");
+    EdgeList el;
+    std::string err;
+    if (!load_edge_list(path, undirected != 0, el, err)) return fail(SMORE_E_IO, "%s", err.c_str());
+    const int64_t nv = (int64_t)el.names.size(), ne = (int64_t)el.col.size();
+    if (V) *V = nv;
+    if (E) *E = ne;
+    if (n_lines) *n_lines = el.n_lines;
+    if (row_off) memcpy(row_off, el.row_off.data(), (size_t)(nv + 1) * sizeof(int64_t));
+    if (col) memcpy(col, el.col.data(), (size_t)ne * sizeof(int32_t));
+    if (weight) memcpy(weight, el.w.data(), (size_t)ne * sizeof(double));
+    int64_t nb = 0;
+    for (auto& s : el.names) nb += (int64_t)s.size() + 1;
+    if (names_bytes) *names_bytes = nb;
+    if (names) {
+        if (names_cap < nb) return fail(SMORE_E_INVALID, "names buffer too small (%lld < %lld)", (long long)names_cap, (long long)nb);
+        char* p = names;
+        for (auto& s : el.names) {
+            memcpy(p, s.data(), s.size());
+            p += s.size();
+            *p++ = '\n';
+        }
+    }
     return SMORE_OK;
 }
 
@@ -424,11 +476,14 @@ int smore_graph_set_shard(smore_graph_t g, int rank, int world) {
     const double pw = g->sem == SMORE_SEM_CPP ? 0.75 : 1.0;
     std::vector<double> psrc((size_t)V), nrm((size_t)V, 0.0);
     double src_sum = 0;
-    for (int64_t v = 0; v < V; ++v) {
-        psrc[(size_t)v] = g->out_deg[(size_t)v] > 0 ? std::pow(g->out_deg[(size_t)v], pw) : 0.0;
-        src_sum += psrc[(size_t)v];
-        for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) nrm[(size_t)v] += std::pow(g->w[(size_t)e], pw);
-    }
+    auto wpow = [pw](double x) { return pw == 0.75 ? pow075(x) : x; };  // pw is 0.75 (C++) or 1 (Go)
+    parallel_for(V, 1 << 14, [&](int64_t vb, int64_t ve, int) {
+        for (int64_t v = vb; v < ve; ++v) {
+            psrc[(size_t)v] = g->out_deg[(size_t)v] > 0 ? std::pow(g->out_deg[(size_t)v], pw) : 0.0;
+            for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) nrm[(size_t)v] += wpow(g->w[(size_t)e]);
+        }
+    });
+    for (int64_t v = 0; v < V; ++v) src_sum += psrc[(size_t)v];
     std::vector<double> pe;
     std::vector<int32_t> esrc, edst;
     double mass_all = 0, mass_own = 0;
@@ -436,7 +491,7 @@ int smore_graph_set_shard(smore_graph_t g, int rank, int world) {
         if (nrm[(size_t)v] <= 0 || src_sum <= 0) continue;
         const double pv = psrc[(size_t)v] / src_sum / nrm[(size_t)v];
         for (int64_t e = g->row_off[(size_t)v]; e < g->row_off[(size_t)v + 1]; ++e) {
-            const double pr = pv * std::pow(g->w[(size_t)e], pw);
+            const double pr = pv * wpow(g->w[(size_t)e]);
             mass_all += pr;
             if ((g->col[(size_t)e] & (world - 1)) == rank) {
                 mass_own += pr;
@@ -602,29 +657,40 @@ int smore_model_save_weights(smore_model_t m, int table, const char* path, int f
     FILE* f = fopen(path, "wb");
     if (!f) return fail(SMORE_E_IO, "cannot create %s", path);
     fprintf(f, "%lld %d\n", (long long)V, dim);
+    // 64 MB of rows at a time: device -> host, then every host thread formats its slice of the chunk into its own buffer
+    // (std::to_chars: the reference's number formats without the printf machinery) and the buffers are written in order
     const int64_t chunk = std::max<int64_t>(1, (64ll << 20) / ((int64_t)dim * 8));
     std::vector<double> rows((size_t)chunk * (size_t)dim);
-    std::string line;
-    char num[64];
+    std::vector<std::string> parts((size_t)host_threads());
+    const std::string* names = m->g->names.empty() ? nullptr : m->g->names.data();
     for (int64_t first = 0; first < V; first += chunk) {
         const int64_t n = std::min(chunk, V - first);
         int rc = smore_model_get_rows(m, table, first, n, rows.data());
         if (rc) { fclose(f); return rc; }
-        for (int64_t r = 0; r < n; ++r) {
-            line.clear();
-            if (!m->g->names.empty()) line += m->g->names[(size_t)(first + r)];
-            else line += std::to_string(first + r);
-            for (int d = 0; d < dim; ++d) {
-                // format 0: ostream << double at default precision == "%g" (LINE.cpp:37); format 1: "%.6f" (line.go:226)
-                int len = snprintf(num, sizeof(num), format == 0 ? " %g" : " %.6f", rows[(size_t)r * dim + d]);
-                line.append(num, (size_t)len);
-            }
-            line += '\n';
-            fwrite(line.data(), 1, line.size(), f);
-        }
+        for (auto& s : parts) s.clear();
+        parallel_for(n, 256, [&](int64_t b, int64_t e, int t) {
+            parts[(size_t)t].reserve((size_t)(e - b) * (size_t)dim * 10);
+            format_rows(rows.data() + (size_t)b * (size_t)dim, e - b, dim, names, first + b, format, parts[(size_t)t]);
+        });
+        for (auto& s : parts)
+            if (!s.empty() && fwrite(s.data(), 1, s.size(), f) != s.size()) { fclose(f); return fail(SMORE_E_IO, "short write to %s", path); }
     }
     fclose(f);
     return SMORE_OK;
+}
+
+int64_t smore_format_rows(const double* rows, int64_t n, int dim, int64_t first_id, int format, char* out, int64_t cap) {
+    if (!rows || n < 0 || dim <= 0 || (format != 0 && format != 1)) return fail(SMORE_E_INVALID, "bad argument");
+    std::vector<std::string> parts((size_t)host_threads());
+    parallel_for(n, 256, [&](int64_t b, int64_t e, int t) {
+        format_rows(rows + (size_t)b * (size_t)dim, e - b, dim, nullptr, first_id + b, format, parts[(size_t)t]);
+    });
+    int64_t total = 0;
+    for (auto& s : parts) {
+        if (out && total + (int64_t)s.size() <= cap) memcpy(out + total, s.data(), s.size());
+        total += (int64_t)s.size();
+    }
+    return total;
 }
 
 // ---- training -----------------------------------------------------------------------------------------------------
