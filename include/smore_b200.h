@@ -181,6 +181,10 @@ int smore_model_enable_exchange(smore_model_t m, int64_t superbatch, double hot_
 int smore_dist_nccl_unique_id(void* id128);
 int smore_dist_nccl_init(const void* id128, int rank, int world);
 int smore_dist_nccl_shutdown(void);
+/* Debug hook: creates the exchange mode's SM-partitioned update stream with `reserve` SMs set aside (as
+ * SMORE_EXCH_RESERVE_SMS would) and reports the device's SM count, the partition's, and on how many distinct SMs a probe
+ * kernel launched on that stream really ran. First call in a process decides the partition. */
+int smore_debug_sm_partition(int reserve, int* total_sms, int* partition_sms, int* sms_seen);
 /* Counters of the last exchange-mode train call: super-batches run, remote vertex rows requested (after dedup); and the
  * size of the hot set. */
 int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows_requested, int64_t* hot_vertices);

@@ -33,7 +33,7 @@ EXPORTS = [
     "smore_graph_set_shard", "smore_graph_shard_info", "smore_model_ipc_handle", "smore_model_open_peers",
     "smore_model_set_peer_ptrs", "smore_model_enable_replica", "smore_model_refresh_replica",
     "smore_model_enable_exchange", "smore_dist_nccl_unique_id", "smore_dist_nccl_init", "smore_dist_nccl_shutdown",
-    "smore_train_line_group", "smore_exchange_stats", "smore_model_save_weights", "smore_format_rows", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
+    "smore_train_line_group", "smore_exchange_stats", "smore_debug_sm_partition", "smore_model_save_weights", "smore_format_rows", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
     "smore_train_warp", "smore_train_hoprec", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
 ]
 
@@ -104,6 +104,7 @@ def lib():
         L.smore_dist_nccl_shutdown.argtypes = []
         L.smore_train_line_group.argtypes = [vp, C.c_int, C.POINTER(TrainParams)]
         L.smore_exchange_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i64)]
+        L.smore_debug_sm_partition.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.smore_format_rows.argtypes = [vp, i64, C.c_int, i64, C.c_int, vp, i64]
         L.smore_format_rows.restype = i64
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]

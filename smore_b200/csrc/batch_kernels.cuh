@@ -175,28 +175,47 @@ static __global__ void __launch_bounds__(kBlockThreads) k_line_requests(GraphDev
     const uint64_t stream = stream_base + (uint64_t)w;
     const uint64_t wps = (uint64_t)batch_wps(2, K);
     const int mask = (1 << g.shard_shift) - 1;
-    for (uint64_t s = lane; s < jobs; s += 32) {
-        const uint64_t p0 = pos0 + s * wps;
-        const U4 b0 = philox_block(seed, stream, p0 >> 2);
-        const uint32_t sel = (uint32_t)p0 & 3u;
-        uint32_t w0 = sel == 0 ? b0.x : sel == 1 ? b0.y : sel == 2 ? b0.z : b0.w;
-        uint32_t w1 = sel == 0 ? b0.y : sel == 1 ? b0.z : b0.w;
-        if (sel == 3) w1 = philox_block(seed, stream, (p0 >> 2) + 1).x;
-        const uint32_t le = alias_pick(g.edge_at, index_draw(w0, g.n_edge_local), w1);
-        const int v1 = __ldg(g.edge_src + le);
-        const int o = v1 & mask;
-        if (o == g.shard_rank || x.is_hot(v1)) continue;
-        uint32_t h = exch_hash(v1) & x.hmask;
-        for (;;) {
-            const int prev = atomicCAS(x.hkey + h, -1, v1);
-            if (prev == -1) {
-                const int j = atomicAdd(x.cnt + o, 1);
-                x.req[(int64_t)o * x.req_stride + j] = v1 >> g.shard_shift;
-                x.hval[h] = (o << 28) | j;
-                break;
+    for (uint64_t s0 = 0; s0 < jobs; s0 += 32) {  // warp-uniform trip count: the appends below are warp-collective
+        const uint64_t s = s0 + (uint64_t)lane;
+        bool created = false;
+        int v1 = 0, o = 0;
+        uint32_t h = 0;
+        if (s < jobs) {
+            const uint64_t p0 = pos0 + s * wps;
+            const U4 b0 = philox_block(seed, stream, p0 >> 2);
+            const uint32_t sel = (uint32_t)p0 & 3u;
+            uint32_t w0 = sel == 0 ? b0.x : sel == 1 ? b0.y : sel == 2 ? b0.z : b0.w;
+            uint32_t w1 = sel == 0 ? b0.y : sel == 1 ? b0.z : b0.w;
+            if (sel == 3) w1 = philox_block(seed, stream, (p0 >> 2) + 1).x;
+            const uint32_t le = alias_pick(g.edge_at, index_draw(w0, g.n_edge_local), w1);
+            v1 = __ldg(g.edge_src + le);
+            o = v1 & mask;
+            h = exch_hash(v1) & x.hmask;
+            if (o != g.shard_rank && !x.is_hot(v1)) {
+                for (;;) {
+                    const int prev = atomicCAS(x.hkey + h, -1, v1);
+                    if (prev == -1) {
+                        created = true;
+                        break;
+                    }
+                    if (prev == v1) break;
+                    h = (h + 1) & x.hmask;
+                }
             }
-            if (prev == v1) break;
-            h = (h + 1) & x.hmask;
+        }
+        // the lanes that created an entry append to their owner's request list: one atomicAdd per owner and warp (every
+        // creator of the device would otherwise hammer the same `world` counters)
+        __syncwarp();
+        const unsigned cm = __ballot_sync(kFull, created);
+        if (created) {
+            const unsigned grp = __match_any_sync(cm, o);
+            const int leader = __ffs(grp) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(x.cnt + o, __popc(grp));
+            base = __shfl_sync(grp, base, leader);
+            const int j = base + __popc(grp & ((1u << lane) - 1u));
+            x.req[(int64_t)o * x.req_stride + j] = v1 >> g.shard_shift;
+            x.hval[h] = (o << 28) | j;
         }
     }
 }

@@ -53,9 +53,10 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
 namespace {
 // The update kernel is persistent: its CTAs occupy every SM they are given for the whole launch, so a communication kernel
 // (NCCL send/recv, the gather / apply kernels) launched meanwhile would simply queue behind it and nothing would overlap
-// (measured: 2 GPUs, 788 -> 797 M updates/s from the two-stream pipeline alone). The update stream therefore lives in a
-// GREEN CONTEXT that owns all SMs but `reserve` (SMORE_EXCH_RESERVE_SMS; the driver rounds partitions to its
-// granularity), and the remaining SMs are always free for whatever the communication stream launches.
+// (measured with per-phase events: the all-to-all that returns the rows took 1.6 ms per super-batch, 1.3 ms of it waiting
+// for the update kernel of the next super-batch to drain). The update stream therefore lives in a GREEN CONTEXT that owns
+// all SMs but `reserve` (SMORE_EXCH_RESERVE_SMS, default 32, 0 = off; the driver rounds partitions to its granularity:
+// 32 -> a 120-SM partition on B200), and the remaining SMs are always free for whatever the communication stream launches.
 struct ExchStreams {
     cudaStream_t sc = nullptr, su = nullptr;
     cudaEvent_t ready[2] = {nullptr, nullptr}, updated[2] = {nullptr, nullptr}, all_done = nullptr;
@@ -100,7 +101,7 @@ struct ExchStreams {
     int init() {
         if (sc) return SMORE_OK;
         CU(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-        int reserve = 0;  // measured neutral on 2 GPUs (770-834 M updates/s with 0, 16, 32): off unless asked for
+        int reserve = 32;  // 2 GPUs, configs[1]: 837 M updates/s without the carve-out, 935 M with 32 SMs set aside
         if (const char* e = getenv("SMORE_EXCH_RESERVE_SMS")) reserve = atoi(e);
         if (reserve <= 0 || carve(reserve) != 0) {
             cudaGetLastError();
@@ -177,6 +178,21 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
             x->st_rows_moved = 0;
             x->st_superbatches = nsb;
         }
+        // SMORE_VERBOSE: device time of the phases on the communication stream, summed over the super-batches
+        const bool verbose = getenv("SMORE_VERBOSE") != nullptr;
+        enum { P_REQ, P_COUNTS, P_A2A_REQ, P_GATHER, P_ROWS_OUT, P_WAIT_UPD, P_ROWS_BACK, P_APPLY, P_N };
+        static const char* const pname[P_N] = {"requests", "counts", "a2a(req)", "gather", "a2a(rows out)", "wait(update)",
+                                               "a2a(rows back)", "apply"};
+        std::vector<cudaEvent_t> pev, uev;
+        std::vector<int> pkind;
+        auto mark = [&](int kind) {  // end of phase `kind` on sc (kind < 0: start marker)
+            if (!verbose) return;
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, sc);
+            pev.push_back(e);
+            pkind.push_back(kind);
+        };
         auto dev_of = [&](int i, int b) {
             smore_exchange_s* x = ms[i]->xch;
             ExchSet& e = x->set[b];
@@ -191,6 +207,7 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
         // PREP: which remote rows does super-batch `sb` need? -> request lists -> owners gather -> rows to the requesters
         auto prep = [&](uint64_t sb) -> int {
             const int b = (int)(sb & 1);
+            mark(-1);
             for (int i = 0; i < n; ++i) {
                 Shard& s = sh[(size_t)i];
                 ExchSet& e = ms[i]->xch->set[b];
@@ -206,7 +223,9 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
                 s.prepared += jobs;
             }
             CU(cudaGetLastError());
+            mark(P_REQ);
             if (int rc = tr.counts(ms, n, b, sc)) return rc;
+            mark(P_COUNTS);
             for (int i = 0; i < n; ++i) {
                 smore_exchange_s* x = ms[i]->xch;
                 ExchSet& e = x->set[b];
@@ -222,6 +241,7 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
                 x->st_rows_moved += n_out;
             }
             if (int rc = tr.a2a(ms, n, b, ExchTransport::REQ, row_bytes, sc)) return rc;
+            mark(P_A2A_REQ);
             for (int i = 0; i < n; ++i) {
                 ExchSet& e = ms[i]->xch->set[b];
                 const int64_t n_in = e.off_in[kMaxWorld];
@@ -231,7 +251,9 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
                     g_launches++;
                 }
             }
+            mark(P_GATHER);
             if (int rc = tr.a2a(ms, n, b, ExchTransport::ROWS_OUT, row_bytes, sc)) return rc;
+            mark(P_ROWS_OUT);
             CU(cudaEventRecord(g_xs.ready[b], sc));
             return SMORE_OK;
         };
@@ -239,6 +261,12 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
         auto update = [&](uint64_t sb) -> int {
             const int b = (int)(sb & 1);
             CU(cudaStreamWaitEvent(su, g_xs.ready[b], 0));
+            cudaEvent_t u0 = nullptr, u1 = nullptr;
+            if (verbose) {
+                cudaEventCreate(&u0);
+                cudaEventCreate(&u1);
+                cudaEventRecord(u0, su);
+            }
             for (int i = 0; i < n; ++i) {
                 Shard& s = sh[(size_t)i];
                 s.a.jobs = s.jobs_of[b];
@@ -249,14 +277,22 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
                     s.done += s.a.jobs;
                 }
             }
+            if (verbose) {
+                cudaEventRecord(u1, su);
+                uev.push_back(u0);
+                uev.push_back(u1);
+            }
             CU(cudaEventRecord(g_xs.updated[b], su));
             return SMORE_OK;
         };
         // FINISH: rows back to their owners, who add what changed
         auto finish = [&](uint64_t sb) -> int {
             const int b = (int)(sb & 1);
+            mark(-1);
             CU(cudaStreamWaitEvent(sc, g_xs.updated[b], 0));
+            mark(P_WAIT_UPD);
             if (int rc = tr.a2a(ms, n, b, ExchTransport::ROWS_BACK, row_bytes, sc)) return rc;
+            mark(P_ROWS_BACK);
             for (int i = 0; i < n; ++i) {
                 ExchSet& e = ms[i]->xch->set[b];
                 const int64_t n_in = e.off_in[kMaxWorld];
@@ -267,6 +303,7 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
                 }
             }
             CU(cudaGetLastError());
+            mark(P_APPLY);
             return SMORE_OK;
         };
 
@@ -288,6 +325,27 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
         CU(cudaStreamWaitEvent(0, g_xs.all_done, 0));
         double ms_total = 0;
         if (int rc = t.stop(&ms_total)) return rc;
+        if (verbose) {
+            double sum[P_N] = {};
+            for (size_t k = 1; k < pev.size(); ++k)
+                if (pkind[k] >= 0) {
+                    float f = 0;
+                    cudaEventElapsedTime(&f, pev[k - 1], pev[k]);
+                    sum[pkind[k]] += f;
+                }
+            fprintf(stderr, "[smore_b200] exchange rank %d: %llu super-batches in %.2f ms; communication stream:", m0->g->rank,
+                    (unsigned long long)nsb, ms_total);
+            for (int k = 0; k < P_N; ++k) fprintf(stderr, " %s %.2f", pname[k], sum[k]);
+            double upd = 0;
+            for (size_t k = 0; k + 1 < uev.size(); k += 2) {
+                float f = 0;
+                cudaEventElapsedTime(&f, uev[k], uev[k + 1]);
+                upd += f;
+            }
+            fprintf(stderr, " ms; update stream: k_line %.2f ms\n", upd);
+            for (cudaEvent_t e : uev) cudaEventDestroy(e);
+            for (cudaEvent_t e : pev) cudaEventDestroy(e);
+        }
         for (int i = 0; i < n; ++i) {
             ms[i]->st_ms = ms_total;
             ms[i]->st_samples = sh[(size_t)i].done * (uint64_t)L.warps;

@@ -318,3 +318,23 @@ def test_exchange_mode_quality_matches_unsharded():
             assert 0 < xs["hot_vertices"] < V and xs["rows_requested"] > 0  # both paths were exercised
         if hot < 0:
             assert xs["hot_vertices"] == 0 and xs["rows_requested"] > 0
+
+
+def _partition_worker(rank, out):
+    import ctypes as C
+
+    capi.check(capi.lib().smore_init(0))
+    t, p, s = C.c_int(), C.c_int(), C.c_int()
+    capi.check(capi.lib().smore_debug_sm_partition(32, C.byref(t), C.byref(p), C.byref(s)))
+    out.update(total=t.value, part=p.value, seen=s.value)
+
+
+def test_update_stream_runs_on_its_sm_partition():
+    """The exchange mode keeps SMs free for the communication kernels by running the persistent update kernel in a green
+    context: a probe kernel launched on that stream must stay inside the partition. (Own process: the first call decides
+    the partition for the process.)"""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_partition_worker, args=(out,), nprocs=1, join=True)
+    assert out["total"] >= 100
+    assert 0 < out["part"] < out["total"] and out["seen"] == out["part"], dict(out)
