@@ -193,6 +193,15 @@ int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows
  * format 0 = C++ iostream default (%g, 6 significant digits; src/model/LINE.cpp:13-47),
  * format 1 = Go "%.6f" (internal/models/line/line.go:209-233). */
 int smore_model_save_weights(smore_model_t m, int table, const char* path, int format);
+/* Warm start: proNet::LoadPreTrain (src/proNet.cpp:238-286), the -load_v / -load_c flags of cli/deepwalk.cpp:61-62.
+ * Text in the writer's own format; rows are matched by vertex NAME (the graph must come from an edge list), unknown
+ * names and short lines are skipped, a dimension mismatch skips the whole file (0 rows, success) as the reference does.
+ * On a row-sharded model each rank keeps the rows it owns. */
+int smore_model_load_pretrain(smore_model_t m, int table, const char* path, int64_t* rows_loaded);
+/* Binary snapshot of every table of this rank (raw rows in the stored element type + a header that pins V, dim, dtype,
+ * rank/world): save / resume for long runs -- the reference can import text embeddings but not resume. */
+int smore_model_save_checkpoint(smore_model_t m, const char* path);
+int smore_model_load_checkpoint(smore_model_t m, const char* path);
 /* The writer's formatter on host rows (no device involved; multi-threaded): `<first_id + r> v0 v1 ...\n` per row, in the
  * number format of the chosen reference writer. Returns the byte count of the text (written to `out` when it fits in
  * `cap`; call with out = NULL to size the buffer) or a negative error. */

@@ -33,7 +33,8 @@ EXPORTS = [
     "smore_graph_set_shard", "smore_graph_shard_info", "smore_model_ipc_handle", "smore_model_open_peers",
     "smore_model_set_peer_ptrs", "smore_model_enable_replica", "smore_model_refresh_replica",
     "smore_model_enable_exchange", "smore_dist_nccl_unique_id", "smore_dist_nccl_init", "smore_dist_nccl_shutdown",
-    "smore_train_line_group", "smore_exchange_stats", "smore_debug_sm_partition", "smore_model_save_weights", "smore_format_rows", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
+    "smore_train_line_group", "smore_exchange_stats", "smore_debug_sm_partition", "smore_model_save_weights", "smore_format_rows",
+    "smore_model_load_pretrain", "smore_model_save_checkpoint", "smore_model_load_checkpoint", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
     "smore_train_warp", "smore_train_hoprec", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
 ]
 
@@ -105,6 +106,9 @@ def lib():
         L.smore_train_line_group.argtypes = [vp, C.c_int, C.POINTER(TrainParams)]
         L.smore_exchange_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i64)]
         L.smore_debug_sm_partition.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.smore_model_load_pretrain.argtypes = [vp, C.c_int, C.c_char_p, C.POINTER(i64)]
+        L.smore_model_save_checkpoint.argtypes = [vp, C.c_char_p]
+        L.smore_model_load_checkpoint.argtypes = [vp, C.c_char_p]
         L.smore_format_rows.argtypes = [vp, i64, C.c_int, i64, C.c_int, vp, i64]
         L.smore_format_rows.restype = i64
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
@@ -365,6 +369,17 @@ class Model:
 
     def save_weights(self, path, table=0, fmt=0):
         check(lib().smore_model_save_weights(self.h, table, os.fsencode(path), fmt))
+
+    def load_pretrain(self, path, table=0) -> int:
+        n = i64()
+        check(lib().smore_model_load_pretrain(self.h, table, os.fsencode(path), C.byref(n)))
+        return n.value
+
+    def save_checkpoint(self, path):
+        check(lib().smore_model_save_checkpoint(self.h, os.fsencode(path)))
+
+    def load_checkpoint(self, path):
+        check(lib().smore_model_load_checkpoint(self.h, os.fsencode(path)))
 
     def _train(self, fn, p):
         check(fn(self.h, C.byref(p)))

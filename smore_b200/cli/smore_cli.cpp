@@ -82,6 +82,8 @@ void usage() {
            "\t-lambda <float>\n\t\tGo BPR regularisation; default is 0.001\n"
            "\t-alpha <float>\n\t\tInit learning rate; default is 0.025\n"
            "\t-threads <int>\n\t\tAccepted for compatibility; workers are GPU warps\n"
+           "\t-load_v <string> -load_c <string>\n\t\tPretrained vertex / context embeddings (text, matched by vertex name)\n"
+           "\t-checkpoint <string> -resume <string>\n\t\tWrite / read a binary snapshot of all tables\n"
            "\t-semantics <go|cpp> -mode <hogwild|deterministic> -seed <int> -dtype <f32|f64> -device <int>\n");
 }
 
@@ -177,6 +179,17 @@ int main(int argc, char** argv) {
         if (smore_model_init(m, 1, ctx_random ? 1 : 0, p.seed)) return die("Init");
     }
 
+    // cli/deepwalk.cpp:61-62, DeepWalk.cpp:83-92: pretrained vertex / context embeddings replace the random init
+    for (int t = 0; t < n_tables; ++t) {
+        const char* key = t == 0 ? "load_v" : "load_c";
+        if (!a.has(key)) continue;
+        int64_t n = 0;
+        printf("\tload %s pretrain:\t%s\n", t == 0 ? "vertex" : "context", a.str(key, "").c_str());
+        if (smore_model_load_pretrain(m, t, a.str(key, "").c_str(), &n)) return die("LoadPreTrain");
+        printf("\t# of Pre-train:\t\t%lld\n", (long long)n);
+    }
+    if (a.has("resume") && smore_model_load_checkpoint(m, a.str("resume", "").c_str())) return die("LoadCheckpoint");
+
     printf("Model:\n\t[%s] (%s semantics, %s, %s)\n", model.c_str(), sem_s.c_str(),
            p.mode == SMORE_MODE_HOGWILD ? "hogwild" : "deterministic", dtype == SMORE_F64 ? "f64" : "f32");
     printf("Learning Parameters:\n\tsample_times:\t\t%d\n\tnegative_samples:\t%d\n\talpha:\t\t\t%g\n", sample_times,
@@ -229,6 +242,7 @@ int main(int argc, char** argv) {
     // number format: C++ iostream default (%g) vs Go "%.6f" (LINE.cpp:37, line.go:226)
     if (smore_model_save_weights(m, 0, save.c_str(), sem == SMORE_SEM_GO ? 1 : 0)) return die("SaveWeights");
     printf("\tSave to <%s>\n", save.c_str());
+    if (a.has("checkpoint") && smore_model_save_checkpoint(m, a.str("checkpoint", "").c_str())) return die("SaveCheckpoint");
     smore_model_destroy(m);
     smore_graph_destroy(g);
     return 0;

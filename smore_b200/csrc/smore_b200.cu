@@ -2,6 +2,10 @@
 // The trainers (kernel launches) are instantiated per element type in train_*.cu.
 #include "host_common.h"
 
+#include <charconv>
+#include <string_view>
+#include <unordered_map>
+
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 int g_device = -1;
@@ -675,6 +679,183 @@ int smore_model_save_weights(smore_model_t m, int table, const char* path, int f
         for (auto& s : parts)
             if (!s.empty() && fwrite(s.data(), 1, s.size(), f) != s.size()) { fclose(f); return fail(SMORE_E_IO, "short write to %s", path); }
     }
+    fclose(f);
+    return SMORE_OK;
+}
+
+// ---- warm start and checkpoints --------------------------------------------------------------------------------------
+// proNet::LoadPreTrain (src/proNet.cpp:238-286; cli/deepwalk.cpp:61-62 -load_v / -load_c): "<n> <dim>" then `name v0 v1 ...`
+// per line; rows whose name the graph does not know are skipped, a dimension mismatch skips the whole file. (The reference
+// reads lines with fgets(…, 1000) and silently truncates longer ones, i.e. dim > ~90; that defect is not reproduced.)
+int smore_model_load_pretrain(smore_model_t m, int table, const char* path, int64_t* rows_loaded) {
+    if (!m || !path || table < 0 || table >= m->n_tables) return fail(SMORE_E_INVALID, "bad argument");
+    if (rows_loaded) *rows_loaded = 0;
+    const smore_graph_s* g = m->g;
+    if (g->names.empty()) return fail(SMORE_E_INVALID, "the graph has no vertex names (created from a CSR): nothing to match the file against");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(SMORE_E_IO, "cannot open %s", path);
+    std::string buf;
+    {
+        fseek(f, 0, SEEK_END);
+        const long size = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        buf.resize((size_t)std::max(0l, size));
+        if (size > 0 && fread(&buf[0], 1, (size_t)size, f) != (size_t)size) {
+            fclose(f);
+            return fail(SMORE_E_IO, "short read: %s", path);
+        }
+        fclose(f);
+    }
+    const char* p = buf.data();
+    const char* end = p + buf.size();
+    auto next_line = [&](const char*& b, const char*& e) -> bool {
+        if (p >= end) return false;
+        b = p;
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        e = nl ? nl : end;
+        p = nl ? nl + 1 : end;
+        return true;
+    };
+    auto next_tok = [](const char*& q, const char* e, const char*& tb, const char*& te) -> bool {
+        while (q < e && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
+        if (q >= e) return false;
+        tb = q;
+        while (q < e && !(*q == ' ' || *q == '\t' || *q == '\r')) ++q;
+        te = q;
+        return true;
+    };
+    const char *lb, *le, *tb, *te;
+    if (!next_line(lb, le)) return SMORE_OK;  // empty file: nothing loaded (the reference returns silently too)
+    long long n_hdr = 0, dim_hdr = 0;
+    {
+        const char* q = lb;
+        if (next_tok(q, le, tb, te)) n_hdr = atoll(std::string(tb, te).c_str());
+        if (next_tok(q, le, tb, te)) dim_hdr = atoll(std::string(tb, te).c_str());
+    }
+    (void)n_hdr;
+    if (dim_hdr != m->dim) return SMORE_OK;  // "Dimension not matched, Skip Loading Pre-train model." (proNet.cpp:262-264)
+    std::unordered_map<std::string_view, int64_t> ids;
+    ids.reserve(g->names.size() * 2);
+    for (size_t v = 0; v < g->names.size(); ++v) ids.emplace(std::string_view(g->names[v]), (int64_t)v);
+    // consecutive local rows are flushed as one range (a file written by save_weights is in id order: one copy per 16 MB)
+    const int64_t cap_rows = std::max<int64_t>(1, (16ll << 20) / ((int64_t)m->dim * 8));
+    std::vector<double> run;
+    run.reserve((size_t)cap_rows * (size_t)m->dim);
+    int64_t run_first = -1, run_n = 0, loaded = 0;
+    auto flush = [&]() -> int {
+        int rc = SMORE_OK;
+        if (run_n > 0) rc = smore_model_set_rows(m, table, run_first, run_n, run.data());
+        run.clear();
+        run_first = -1;
+        run_n = 0;
+        return rc;
+    };
+    std::vector<double> row((size_t)m->dim);
+    while (next_line(lb, le)) {
+        const char* q = lb;
+        if (!next_tok(q, le, tb, te)) continue;
+        auto it = ids.find(std::string_view(tb, (size_t)(te - tb)));
+        if (it == ids.end()) continue;
+        int d = 0;
+        while (d < m->dim && next_tok(q, le, tb, te)) {
+            double x = 0;
+            auto r = std::from_chars(tb, te, x);
+            if (r.ec != std::errc()) x = atof(std::string(tb, te).c_str());
+            row[(size_t)d++] = x;
+        }
+        if (d != m->dim) continue;  // short line: skipped
+        const int64_t v = it->second;
+        if ((v & (g->world - 1)) != g->rank) continue;  // row-sharded: another rank's row
+        const int64_t local = v >> g->shift;
+        if (run_n > 0 && (local != run_first + run_n || run_n >= cap_rows))
+            if (int rc = flush()) return rc;
+        if (run_n == 0) run_first = local;
+        run.insert(run.end(), row.begin(), row.end());
+        ++run_n;
+        ++loaded;
+    }
+    if (int rc = flush()) return rc;
+    if (rows_loaded) *rows_loaded = loaded;
+    return SMORE_OK;
+}
+
+namespace {
+struct CkptHeader {
+    char magic[8];  // "SMOREB2\0"
+    uint32_t version, dtype, n_tables, dim;
+    int64_t V, rows;
+    int32_t rank, world;
+};
+constexpr char kCkptMagic[8] = {'S', 'M', 'O', 'R', 'E', 'B', '2', '\0'};
+}  // namespace
+
+// Binary snapshot of this rank's rows of every table (raw, in the stored element type): the reference can import text
+// embeddings but cannot resume; a sharded run writes one file per rank.
+int smore_model_save_checkpoint(smore_model_t m, const char* path) {
+    if (!m || !path) return fail(SMORE_E_INVALID, "bad argument");
+    if (int rc = ensure_device()) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(SMORE_E_IO, "cannot create %s", path);
+    CkptHeader h{};
+    memcpy(h.magic, kCkptMagic, 8);
+    h.version = 1;
+    h.dtype = (uint32_t)m->dtype;
+    h.n_tables = (uint32_t)m->n_tables;
+    h.dim = (uint32_t)m->dim;
+    h.V = m->g->V;
+    h.rows = m->rows;
+    h.rank = m->g->rank;
+    h.world = m->g->world;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    const size_t row_bytes = (size_t)m->dim * m->elem();
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((64ull << 20) / row_bytes));
+    std::vector<char> host((size_t)chunk * row_bytes);
+    for (int t = 0; ok && t < m->n_tables; ++t)
+        for (int64_t first = 0; ok && first < m->rows; first += chunk) {
+            const int64_t n = std::min(chunk, m->rows - first);
+            cudaError_t e = cudaMemcpy(host.data(), (const char*)m->tab[t] + (size_t)first * row_bytes, (size_t)n * row_bytes, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) {
+                fclose(f);
+                return fail(SMORE_E_CUDA, "checkpoint read-back: %s", cudaGetErrorString(e));
+            }
+            ok = fwrite(host.data(), row_bytes, (size_t)n, f) == (size_t)n;
+        }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? SMORE_OK : fail(SMORE_E_IO, "short write to %s", path);
+}
+
+int smore_model_load_checkpoint(smore_model_t m, const char* path) {
+    if (!m || !path) return fail(SMORE_E_INVALID, "bad argument");
+    if (int rc = ensure_device()) return rc;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(SMORE_E_IO, "cannot open %s", path);
+    CkptHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, kCkptMagic, 8) != 0 || h.version != 1) {
+        fclose(f);
+        return fail(SMORE_E_IO, "%s is not a smore_b200 checkpoint", path);
+    }
+    if ((int)h.dtype != m->dtype || (int)h.n_tables != m->n_tables || (int)h.dim != m->dim || h.V != m->g->V || h.rows != m->rows ||
+        h.rank != m->g->rank || h.world != m->g->world) {
+        fclose(f);
+        return fail(SMORE_E_INVALID, "checkpoint %s does not match the model (V %lld dim %u tables %u dtype %u rank %d/%d)", path,
+                    (long long)h.V, h.dim, h.n_tables, h.dtype, h.rank, h.world);
+    }
+    const size_t row_bytes = (size_t)m->dim * m->elem();
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)((64ull << 20) / row_bytes));
+    std::vector<char> host((size_t)chunk * row_bytes);
+    for (int t = 0; t < m->n_tables; ++t)
+        for (int64_t first = 0; first < m->rows; first += chunk) {
+            const int64_t n = std::min(chunk, m->rows - first);
+            if (fread(host.data(), row_bytes, (size_t)n, f) != (size_t)n) {
+                fclose(f);
+                return fail(SMORE_E_IO, "checkpoint %s is truncated", path);
+            }
+            cudaError_t e = cudaMemcpy((char*)m->tab[t] + (size_t)first * row_bytes, host.data(), (size_t)n * row_bytes, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                fclose(f);
+                return fail(SMORE_E_CUDA, "checkpoint upload: %s", cudaGetErrorString(e));
+            }
+        }
     fclose(f);
     return SMORE_OK;
 }
