@@ -153,12 +153,21 @@ __device__ __forceinline__ uint32_t exch_hash(int v) {
     return h ^ (h >> 15);
 }
 
-// Returns the staging row of remote vertex v1 (filed by k_line_requests in an earlier launch).
+// Returns the staging row of remote vertex v1 (filed by k_line_requests in an earlier launch), or -1 if the vertex is
+// not in the table -- which would mean the two kernels disagreed about a sample; the probe is bounded so that such a bug
+// surfaces as an error code instead of a hung device.
 __device__ __forceinline__ int exch_lookup(const ExchDev& x, int v1) {
     uint32_t h = exch_hash(v1) & x.hmask;
-    while (__ldg(x.hkey + h) != v1) h = (h + 1) & x.hmask;
-    const int hv = __ldg(x.hval + h);
-    return __ldg(x.off + (hv >> 28)) + (hv & 0x0fffffff);
+    for (uint32_t probes = 0; probes <= x.hmask; ++probes) {
+        const int k = __ldg(x.hkey + h);
+        if (k == v1) {
+            const int hv = __ldg(x.hval + h);
+            return __ldg(x.off + (hv >> 28)) + (hv & 0x0fffffff);
+        }
+        if (k == -1) break;
+        h = (h + 1) & x.hmask;
+    }
+    return -1;
 }
 
 // One lane per sample: words [pos0 + s*wps, +2) of the warp's stream -> edge draw -> source vertex; remote sources are
@@ -312,7 +321,14 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             // remote source: k_line_requests filed it in the hash; its row now sits in the staging table
             if (lane < nb) {
                 const int v1 = b.ids[lane * b.idw];
-                if ((v1 & a.world_mask) != a.g.shard_rank && !a.x.is_hot(v1)) b.ids[lane * b.idw] = -2 - exch_lookup(a.x, v1);
+                if ((v1 & a.world_mask) != a.g.shard_rank && !a.x.is_hot(v1)) {
+                    const int row = exch_lookup(a.x, v1);
+                    if (row >= 0) b.ids[lane * b.idw] = -2 - row;
+                    else {
+                        b.ids[lane * b.idw + 1] = -1;  // drop the sample and tell the host
+                        atomicAdd(a.x.errors, 1);
+                    }
+                }
             }
             __syncwarp();
         }

@@ -35,6 +35,7 @@ struct smore_exchange_s {
     double hot_threshold = 0;     // a vertex expected to be a source >= this many times per super-batch (all ranks) is HOT
     int64_t n_hot = 0;
     DevBuf hot;                   // bitmap over vertex ids, null when n_hot == 0
+    DevBuf errors;                // one int: samples the update kernel could not resolve (must stay 0)
     ExchSet set[2];
     int64_t req_stride = 0;
     // totals of the last train call

@@ -37,6 +37,7 @@ struct ExchDev {
     int32_t* cnt;        // [kMaxWorld] requests per owner
     const int32_t* off;  // [kMaxWorld] first wrk row of owner o's region (exclusive prefix sum of cnt)
     void* wrk;           // staged vertex rows [sum cnt][dim]
+    int* errors;         // samples whose source was missing from the hash (must stay 0; checked by the host)
     const uint32_t* hot; // bitmap over vertex ids (null = none): HOT vertices are sampled so often that per-super-batch
                          // copies on several ranks would each run a long update sequence whose sum overshoots; their rows
                          // stay single-copy and are reached through the peer mappings as in the peer-access mode

@@ -175,6 +175,8 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
                 if (int rc = e.cnt.ensure(2 * kMaxWorld * 4)) return rc;
                 if (int rc = e.off.ensure(kMaxWorld * 4)) return rc;
             }
+            if (int rc = x->errors.ensure(sizeof(int))) return rc;
+            CU(cudaMemset(x->errors.p, 0, sizeof(int)));
             x->st_rows_moved = 0;
             x->st_superbatches = nsb;
         }
@@ -197,7 +199,8 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
             smore_exchange_s* x = ms[i]->xch;
             ExchSet& e = x->set[b];
             return ExchDev{(int32_t*)e.hkey.p, (int32_t*)e.hval.p, sh[(size_t)i].hmask, (int32_t*)e.req.p, x->req_stride,
-                           (int32_t*)e.cnt.p, (const int32_t*)e.off.p, e.wrk.p, x->n_hot ? (const uint32_t*)x->hot.p : nullptr};
+                           (int32_t*)e.cnt.p, (const int32_t*)e.off.p, e.wrk.p, (int*)x->errors.p,
+                           x->n_hot ? (const uint32_t*)x->hot.p : nullptr};
         };
         int dev = 0, sms = 0;
         CU(cudaGetDevice(&dev));
@@ -350,6 +353,9 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
             ms[i]->st_ms = ms_total;
             ms[i]->st_samples = sh[(size_t)i].done * (uint64_t)L.warps;
             if (int rc = collect_stats(ms[i], L.warps)) return rc;
+            int errs = 0;
+            CU(cudaMemcpy(&errs, ms[i]->xch->errors.p, sizeof(int), cudaMemcpyDeviceToHost));
+            if (errs) return fail(SMORE_E_CUDA, "exchange mode: %d samples of rank %d drew a source that was not requested (internal error)", errs, ms[i]->g->rank);
         }
         return SMORE_OK;
     });
