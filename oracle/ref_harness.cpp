@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- C-ABI harness around the UNMODIFIED compiled reference (C++ tree).
 //
 // Built by oracle/Makefile from the reference sources where they lie under /root/reference/src
-// (proNet.cpp, util.cpp, model/{LINE,DeepWalk,Walklets,BPR,WARP,HBPR}.cpp) with random.cpp replaced
+// (proNet.cpp, util.cpp, model/{LINE,DeepWalk,Walklets,BPR,WARP,HBPR,HPE}.cpp) with random.cpp replaced
 // by ref_shim.cpp; output goes to oracle/_ref/ only. Nothing here is copied from the reference: this
 // file only CALLS its public classes (src/proNet.h:109-269, src/model/*.h).
 //
@@ -16,6 +16,7 @@
 #include "model/BPR.h"
 #include "model/DeepWalk.h"
 #include "model/HBPR.h"
+#include "model/HPE.h"
 #include "model/LINE.h"
 #include "model/WARP.h"
 #include "model/Walklets.h"
@@ -25,7 +26,7 @@ extern "C" uint64_t ref_shim_pos(void);
 
 namespace {
 
-enum Kind { K_LINE = 0, K_DEEPWALK = 1, K_WALKLETS = 2, K_BPR = 3, K_WARP = 4, K_HOPREC = 5 };
+enum Kind { K_LINE = 0, K_DEEPWALK = 1, K_WALKLETS = 2, K_BPR = 3, K_WARP = 4, K_HOPREC = 5, K_HPE = 6 };
 
 struct Ref {
     int kind;
@@ -35,6 +36,7 @@ struct Ref {
     BPR* bpr = nullptr;
     WARP* warp = nullptr;
     HBPR* hbpr = nullptr;
+    HPE* hpe = nullptr;
     int dim = 0;
     int order = 2;
 
@@ -45,6 +47,7 @@ struct Ref {
             case K_WALKLETS: return wl->pnet;
             case K_BPR: return bpr->pnet;
             case K_WARP: return warp->pnet;
+            case K_HPE: return hpe->pnet;
             default: return hbpr->pnet;
         }
     }
@@ -58,6 +61,7 @@ struct Ref {
             case K_WALKLETS: return t == 0 ? &wl->w_vertex : &wl->w_context;
             case K_BPR: return t == 0 ? &bpr->w_vertex : nullptr;
             case K_WARP: return t == 0 ? &warp->w_vertex : nullptr;
+            case K_HPE: return t == 0 ? &hpe->w_vertex : &hpe->w_context;
             default: return t == 0 ? &hbpr->w_vertex : &hbpr->w_context;
         }
     }
@@ -77,6 +81,7 @@ void* ref_new(int kind) {
         case K_BPR: r->bpr = new BPR(); break;
         case K_WARP: r->warp = new WARP(); break;
         case K_HOPREC: r->hbpr = new HBPR(); break;
+        case K_HPE: r->hpe = new HPE(); break;
         default: delete r; return nullptr;
     }
     return r;
@@ -84,7 +89,7 @@ void* ref_new(int kind) {
 
 void ref_free(void* h) {
     Ref* r = (Ref*)h;
-    delete r->line; delete r->dw; delete r->wl; delete r->bpr; delete r->warp; delete r->hbpr;
+    delete r->line; delete r->dw; delete r->wl; delete r->bpr; delete r->warp; delete r->hbpr; delete r->hpe;
     delete r;
 }
 
@@ -111,6 +116,7 @@ void ref_init(void* h, int dim, int order) {
         case K_WALKLETS: r->wl->Init(dim); break;
         case K_BPR: r->bpr->Init(dim); break;
         case K_WARP: r->warp->Init(dim); break;
+        case K_HPE: r->hpe->Init(dim); break;
         default: r->hbpr->Init(dim); break;
     }
 }
@@ -242,6 +248,18 @@ void ref_train(void* h, int a, int b, int c, int d, int e, double alpha, int wor
     }
 }
 
+// HPE::Train (src/model/HPE.cpp:93-147) as cli/hpe.cpp:76 calls it
+void ref_train_hpe(void* h, int sample_times, int walk_steps, int K, double reg, double alpha, int workers) {
+    Ref* r = (Ref*)h;
+    if (r->kind == K_HPE) r->hpe->Train(sample_times, walk_steps, K, reg, alpha, workers);
+}
+
+// proNet::UpdateCommunity (src/proNet.cpp:3018-3054) on the model's own tables
+void ref_update_community(void* h, int64_t v, int64_t c, double reg, int walk_steps, int K, double alpha) {
+    Ref* r = (Ref*)h;
+    r->pnet().UpdateCommunity(*r->table(0), *r->table(1), (long)v, (long)c, r->dim, reg, walk_steps, K, alpha);
+}
+
 void ref_save_weights(void* h, const char* path) {
     Ref* r = (Ref*)h;
     switch (r->kind) {
@@ -250,6 +268,7 @@ void ref_save_weights(void* h, const char* path) {
         case K_WALKLETS: r->wl->SaveWeights(path); break;
         case K_BPR: r->bpr->SaveWeights(path); break;
         case K_WARP: r->warp->SaveWeights(path); break;
+        case K_HPE: r->hpe->SaveWeights(path); break;
         default: r->hbpr->SaveWeights(path); break;
     }
 }

@@ -323,6 +323,37 @@ struct Graph {
         }
         for (int k = 0; k < dim; ++k) rv[k] += back_err[k];
     }
+    // src/proNet.cpp:1332-1351 (HPE): the regularised variant; alpha multiplies the whole bracket
+    void opt_sigmoid_reg_sgd(const double* wv, const double* wc, double label, int dim, double alpha, double reg,
+                             double* loss_v, double* loss_c) const {
+        double f = 0;
+        for (int d = 0; d < dim; ++d) f += wv[d] * wc[d];
+        f = fast_sigmoid(f);
+        double g = (label - f);
+        for (int d = 0; d < dim; ++d) loss_v[d] += alpha * (g * wc[d] - reg * wv[d]);
+        for (int d = 0; d < dim; ++d) loss_c[d] += alpha * (g * wv[d] - reg * wc[d]);
+    }
+    // src/proNet.cpp:3018-3054: the context walks on (TargetSample) for walk_steps steps, each step one positive and K
+    // negatives against the SAME vertex row, which is updated at the end of every step
+    void update_community_cpp(double* Wv, double* Wc, int64_t vertex, int64_t context, int dim, double reg, int walk_steps,
+                              int K, double alpha, Draws& d, std::vector<double>& back_err) const {
+        double* rv = Wv + vertex * dim;
+        for (int s = 0; s < walk_steps; s++) {
+            if (s != 0) {
+                context = target_sample(context, d);
+                if (context == -1) break;
+            }
+            back_err.assign(dim, 0.0);
+            double* rc = Wc + context * dim;
+            opt_sigmoid_reg_sgd(rv, rc, 1.0, dim, alpha, reg, back_err.data(), rc);
+            for (int n = 0; n != K; ++n) {
+                int64_t c = negative_sample(d);
+                rc = Wc + c * dim;
+                opt_sigmoid_reg_sgd(rv, rc, 0.0, dim, alpha, reg, back_err.data(), rc);
+            }
+            for (int k = 0; k < dim; ++k) rv[k] += back_err[k];
+        }
+    }
     // optimizer.go:21-58 + sgdUpdate :61-84
     void update_pair_go(double* Wv, double* Wc, int64_t vertex, int64_t context, int dim, int K, double alpha, Draws& d,
                         std::vector<double>& vgrad, std::vector<double>& cgrad, std::vector<double>& ngrad) const {
@@ -689,6 +720,33 @@ uint64_t orc_train_hoprec_cpp(void* h, double* W, int dim, int walk_steps, doubl
         count++;
         sch.tick(count);
     }
+    return d.s.pos;
+}
+
+// C++ HPE: src/model/HPE.cpp:93-147 -- UpdateCommunity(v1, v2) then UpdatePair with the roles swapped (v2, v1); count from 0
+uint64_t orc_train_hpe_cpp(void* h, double* Wv, double* Wc, int dim, int walk_steps, int K, double reg, double alpha,
+                           uint64_t total, uint64_t seed, uint64_t stream) {
+    Graph* g = (Graph*)h;
+    Draws d(seed, stream);
+    CppSchedule sch(alpha, total);
+    std::vector<double> be;
+    unsigned long long count = 0;
+    while (count < total) {
+        int64_t v1 = g->source_sample(d);
+        int64_t v2 = g->target_sample(v1, d);
+        g->update_community_cpp(Wv, Wc, v1, v2, dim, reg, walk_steps, K, sch.cur, d, be);
+        g->update_pair_cpp(Wv, Wc, v2, v1, dim, K, sch.cur, d, be);
+        count++;
+        sch.tick(count);
+    }
+    return d.s.pos;
+}
+uint64_t orc_update_community_cpp(void* h, double* Wv, double* Wc, int64_t v, int64_t c, int dim, double reg, int walk_steps,
+                                  int K, double alpha, uint64_t seed, uint64_t stream) {
+    Graph* g = (Graph*)h;
+    Draws d(seed, stream);
+    std::vector<double> be;
+    g->update_community_cpp(Wv, Wc, v, c, dim, reg, walk_steps, K, alpha, d, be);
     return d.s.pos;
 }
 

@@ -1,6 +1,6 @@
 // Host-side mirror of the reference CLIs on top of the C ABI (include/smore_b200.h).
 //
-//   smore <model> -train net.txt -save rep.txt [flags]      model in {line, deepwalk, walklets, bpr, warp, hoprec}
+//   smore <model> -train net.txt -save rep.txt [flags]      model in {line, deepwalk, walklets, bpr, warp, hoprec, hpe}
 //   (or invoke through a symlink named after the model: `line -train ...`)
 //
 // Flag names, defaults and the four-call sequence LoadEdgeList -> Init -> Train -> SaveWeights are those of
@@ -68,7 +68,7 @@ int die(const char* what) {
 
 void usage() {
     printf("[smore_b200]\n\tB200-native SMORe trainers (LINE, DeepWalk, Walklets, BPR, WARP, HOP-Rec)\n\n"
-           "Usage:\n\tsmore <line|deepwalk|walklets|bpr|warp|hoprec> -train net.txt -save rep.txt [options]\n\n"
+           "Usage:\n\tsmore <line|deepwalk|walklets|bpr|warp|hoprec|hpe> -train net.txt -save rep.txt [options]\n\n"
            "Options Description:\n"
            "\t-train <string>\n\t\tTrain the Network data\n"
            "\t-save <string>\n\t\tSave the representation data\n"
@@ -80,6 +80,7 @@ void usage() {
            "\t-sample_times <int>\n\t\tNumber of training samples (cpp: *Million, go: *edge lines); default is 10\n"
            "\t-walk_times <int> -walk_steps <int> -window_size <int> -window_min <int> -window_max <int>\n"
            "\t-lambda <float>\n\t\tGo BPR regularisation; default is 0.001\n"
+           "\t-reg <float>\n\t\tHPE regularisation; default is 0.01\n"
            "\t-alpha <float>\n\t\tInit learning rate; default is 0.025\n"
            "\t-threads <int>\n\t\tAccepted for compatibility; workers are GPU warps\n"
            "\t-load_v <string> -load_c <string>\n\t\tPretrained vertex / context embeddings (text, matched by vertex name)\n"
@@ -94,7 +95,7 @@ int main(int argc, char** argv) {
     int first = 1;
     const char* base = strrchr(argv[0], '/');
     base = base ? base + 1 : argv[0];
-    for (const char* m : {"line", "deepwalk", "walklets", "bpr", "warp", "hoprec"})
+    for (const char* m : {"line", "deepwalk", "walklets", "bpr", "warp", "hoprec", "hpe"})
         if (!strcmp(base, m)) model = m;
     if (model.empty()) {
         if (argc < 2 || argv[1][0] == '-') {
@@ -110,7 +111,7 @@ int main(int argc, char** argv) {
     }
     Args a = parse(argc, argv, first);
     const bool has_go_cli = model == "line" || model == "deepwalk" || model == "bpr";
-    if (!has_go_cli && model != "walklets" && model != "warp" && model != "hoprec") {
+    if (!has_go_cli && model != "walklets" && model != "warp" && model != "hoprec" && model != "hpe") {
         fprintf(stderr, "smore: unknown model '%s'\n", model.c_str());
         return 1;
     }
@@ -156,10 +157,10 @@ int main(int argc, char** argv) {
     p.alpha = a.real("alpha", 0.025);
     p.negative_samples = (int)a.num("negative_samples", 5);
     p.order = a.num("order", 2) == 1 ? 1 : 2;
-    p.lambda = a.real("lambda", 0.001);
+    p.lambda = model == "hpe" ? a.real("reg", 0.01) : a.real("lambda", 0.001);  // cli/hpe.cpp:57
     p.walk_times = (int)a.num("walk_times", 10);
     // cli/deepwalk.cpp:56 defaults walk_steps to 5 (sic), cli/walklets.cpp:54 and cmd/deepwalk/main.go:20 to 40
-    p.walk_steps = (int)a.num("walk_steps", model == "hoprec" ? 5 : (model == "deepwalk" && sem == SMORE_SEM_CPP ? 5 : 40));
+    p.walk_steps = (int)a.num("walk_steps", model == "hoprec" || model == "hpe" ? 5 : (model == "deepwalk" && sem == SMORE_SEM_CPP ? 5 : 40));
     p.window_min = (int)a.num("window_min", model == "walklets" ? 2 : 1);
     p.window_max = (int)a.num(model == "walklets" ? "window_max" : "window_size", 5);
     // LINE.cpp:119 (sample_times * 1e6) vs line.go:85 (sample_times * MaxLine)
@@ -202,6 +203,7 @@ int main(int argc, char** argv) {
         if (model == "walklets") return smore_train_walklets(m, &q);
         if (model == "bpr") return smore_train_bpr(m, &q);
         if (model == "warp") return smore_train_warp(m, &q);
+        if (model == "hpe") return smore_train_hpe(m, &q);
         return smore_train_hoprec(m, &q);
     };
     uint64_t samples = 0, pairs = 0;

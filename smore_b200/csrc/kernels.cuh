@@ -427,6 +427,144 @@ __global__ void __launch_bounds__(kBlockThreads) k_walk(TrainArgs<typename C::T>
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// HPE. One step of proNet::UpdateCommunity (src/proNet.cpp:3028-3051) with Opt_SigmoidRegSGD
+// (:1332-1351): the regularised skip-gram step -- g = label - sigmoid(v.c) carries no alpha, the whole bracket does:
+//     loss_vertex += alpha * (g * c - reg * v)        c += alpha * (g * v - reg * c)
+// and the vertex row takes loss_vertex at the end of the step. my_id: lane 0 = the step's context, lane 1+n negative n.
+// The two tables are distinct objects in the reference (w_vertex / w_context), so only context rows can repeat.
+// ---------------------------------------------------------------------------------------------------------------
+template <class C, class TV, class TC>
+__device__ __forceinline__ void update_community_step(const TV& tv, const TC& tc, int dim, const typename C::T* lut, int v1,
+                                                      int my_id, int nrows, typename C::T alpha, typename C::T reg,
+                                                      int lane) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    const bool active = lane < nrows;
+    const unsigned peers = __match_any_sync(kFull, active ? my_id : (-1 - lane));
+    const bool dup = __any_sync(kFull, active && __popc(peers) > 1);
+    T* pv = tv.row(v1);
+    Row<C> v, back;
+    v.load(pv, lane, dim);
+    back.zero();
+    if (!dup) {
+        for (int base = 0; base < nrows; base += kCtxChunk) {
+            Row<C> c[kCtxChunk];
+            int ids[kCtxChunk];
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) {
+                ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
+                if (base + r < nrows) c[r].load(tc.row(ids[r]), lane, dim);
+            }
+            T f[kCtxChunk];
+            dots<C, kCtxChunk>(v, c, nrows - base, f);
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) {
+                if (base + r < nrows) {
+                    const T label = (base + r == 0) ? (T)1 : (T)0;
+                    const T g = A::sub(label, fast_sigmoid<T>(lut, f[r]));
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) {
+                        const T ce = c[r].x[e];
+                        back.x[e] = A::add(back.x[e], A::mul(alpha, A::sub(A::mul(g, ce), A::mul(reg, v.x[e]))));
+                        c[r].x[e] = A::add(ce, A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce))));
+                    }
+                    c[r].store(tc.row(ids[r]), lane, dim);
+                }
+            }
+        }
+    } else {
+        for (int r = 0; r < nrows; ++r) {  // a context repeats inside the step: rows re-read in the reference's order
+            const int cid = __shfl_sync(kFull, my_id, r);
+            T* pc = tc.row(cid);
+            Row<C> c;
+            c.load(pc, lane, dim);
+            const T label = (r == 0) ? (T)1 : (T)0;
+            const T g = A::sub(label, fast_sigmoid<T>(lut, dot(v, c)));
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                const T ce = c.x[e];
+                back.x[e] = A::add(back.x[e], A::mul(alpha, A::sub(A::mul(g, ce), A::mul(reg, v.x[e]))));
+                c.x[e] = A::add(ce, A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce))));
+            }
+            c.store(pc, lane, dim);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
+    v.store(pv, lane, dim);
+}
+
+// HPE::Train (src/model/HPE.cpp:121-143): SourceSample, TargetSample, UpdateCommunity(v1, v2: the context walks on for
+// walk_steps steps, one positive + K negatives per step), then UpdatePair with the roles swapped (vertex v2, context
+// v1). The number of words a sample consumes depends on the walk (a sink ends it), so draws come from the sequential
+// ring, one warp = one reference worker.
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_hpe(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
+    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
+    const T* lut = stage_lut<T>(a.lut, lut_s);
+    const DirectView<T> tv{a.Wv, a.dim}, tc{a.Wc, a.dim};
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    DrawRing ring;
+    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
+    const GraphDev& g = a.g;
+    const int nrows = a.K + 1;
+    for (uint64_t it = 0; it < a.jobs; ++it) {
+        ring.ensure();
+        int64_t v1 = 0, v2 = 0;
+        uint32_t used = 0;
+        if (lane == 0) {
+            v1 = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
+            int u;
+            v2 = target_sample(g, v1, ring.peek(2), ring.peek(3), u);
+            used = 2u + (uint32_t)u;
+        }
+        v1 = __shfl_sync(kFull, v1, 0);
+        v2 = __shfl_sync(kFull, v2, 0);
+        ring.advance(__shfl_sync(kFull, used, 0));
+        if (v2 >= 0) {  // (a source always has a neighbour: zero out-weight gets alias probability 0)
+            const T alpha = (T)st.alpha;
+            int64_t ctx = v2;
+            for (int s = 0; s < a.steps; ++s) {
+                if (s != 0) {
+                    ring.ensure();
+                    int64_t nx = -1;
+                    uint32_t un = 0;
+                    if (lane == 0) {
+                        int u;
+                        nx = target_sample(g, ctx, ring.peek(0), ring.peek(1), u);
+                        un = (uint32_t)u;
+                    }
+                    ctx = __shfl_sync(kFull, nx, 0);
+                    ring.advance(__shfl_sync(kFull, un, 0));
+                    if (ctx < 0) break;  // proNet.cpp:3033: a sink ends the walk
+                }
+                ring.ensure();
+                const int my = draw_pair_ids(g, ring, 0u, (int)ctx, a.K, lane);
+                ring.advance(2u * (uint32_t)a.K);
+                update_community_step<C>(tv, tc, a.dim, lut, (int)v1, my, nrows, alpha, a.lambda, lane);
+                st.pairs++;
+            }
+            ring.ensure();
+            const int my = draw_pair_ids(g, ring, 0u, (int)v1, a.K, lane);
+            ring.advance(2u * (uint32_t)a.K);
+            update_pair_cpp<C>(tv, tc, a.dim, false, lut, (int)v2, my, nrows, alpha, lane);
+            st.pairs++;
+        }
+        st.count++;
+        sched_tick(st, a.sched);
+        __syncwarp();
+    }
+    st.pos = ring.pos;
+    if (lane == 0) a.state[w] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Parity hooks
 // ---------------------------------------------------------------------------------------------------------------
 // One warp replays n sampler calls on stream (seed, stream). which: 0 source, 1 negative, 2 target(arg), 3 source+target.

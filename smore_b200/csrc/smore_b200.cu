@@ -965,6 +965,14 @@ static int train_walk_common(smore_model_t m, const smore_train_params* p, int w
 int smore_train_deepwalk(smore_model_t m, const smore_train_params* p) { return train_walk_common(m, p, 0); }
 int smore_train_walklets(smore_model_t m, const smore_train_params* p) { return train_walk_common(m, p, 1); }
 
+int smore_train_hpe(smore_model_t m, const smore_train_params* p) {
+    if (int rc = check_train(m, p, 2)) return rc;
+    if (p->semantics != SMORE_SEM_CPP) return fail(SMORE_E_UNSUPPORTED, "HPE with walks exists only in the C++ tree (the Go hpe model is LINE-2: use smore_train_line)");
+    if (p->negative_samples < 0 || p->negative_samples > 31) return fail(SMORE_E_UNSUPPORTED, "negative_samples must be in [0,31]");
+    if (p->walk_steps < 1) return fail(SMORE_E_INVALID, "walk_steps must be >= 1");
+    return m->dtype == SMORE_F64 ? train_hpe_t<double>(m, p) : train_hpe_t<float>(m, p);
+}
+
 int smore_train_bpr(smore_model_t m, const smore_train_params* p) {
     if (int rc = check_train(m, p, p && p->semantics == SMORE_SEM_GO ? 2 : 1)) return rc;
     return m->dtype == SMORE_F64 ? train_ranking_t<double>(m, p, RANK_BPR) : train_ranking_t<float>(m, p, RANK_BPR);

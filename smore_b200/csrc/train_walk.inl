@@ -60,3 +60,29 @@ int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets) {
     });
 }
 
+
+// HPE trainer (src/model/HPE.cpp:93-147): jobs = total / workers, count from 0, LR read before the counter bump.
+template <typename T>
+int train_hpe_t(smore_model_s* m, const smore_train_params* p) {
+    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
+        using C = decltype(cfg);
+        auto kern = k_hpe<C>;
+        const size_t smem = smem_line<T>();
+        Launch L;
+        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
+        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
+        const uint64_t trips = p->total / (uint64_t)L.warps;
+        if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
+        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)p->total, 1, 0, 1);
+        a.jobs = trips;
+        a.steps = p->walk_steps;
+        Timer t;
+        if (int rc = t.start()) return rc;
+        kern<<<L.blocks, kBlockThreads, smem>>>(a);
+        g_launches++;
+        CU(cudaGetLastError());
+        if (int rc = t.stop(&m->st_ms)) return rc;
+        m->st_samples = trips * (uint64_t)L.warps;
+        return collect_stats(m, L.warps);
+    });
+}

@@ -101,3 +101,18 @@ def test_bpr_warp_hoprec_train():
     a = G["hoprec_init"].copy()
     assert g.train_hoprec_cpp(a, 3, 0.025, 1000000, SEED, 0) == int(G["hoprec_words"])
     assert np.array_equal(a, G["hoprec_v"])
+
+
+# ---- HPE (tests/golden/golden_hpe_v1.npz, tests/golden/make_golden_hpe.py) --------------------------------------------
+GH = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_hpe_v1.npz"))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_hpe_train_golden(tag):
+    off, col, ww, _ = B.edges_to_csr(GH["g300_src"], GH["g300_dst"], GH["g300_w"], 1)
+    g = B.OracleGraph(B.SEM_CPP, off, col, ww)
+    steps, K, reg = GH[f"hpe_{tag}_args"]
+    a, c = GH["init_v"].copy(), GH["init_c"].copy()
+    pos = g.train_hpe_cpp(a, c, int(steps), int(K), float(reg), 0.025, 1000000, SEED, 0)
+    assert pos == int(GH[f"hpe_{tag}_words"])
+    assert np.array_equal(a, GH[f"hpe_{tag}_v"]) and np.array_equal(c, GH[f"hpe_{tag}_c"])

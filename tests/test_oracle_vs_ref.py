@@ -225,3 +225,30 @@ def test_update_pair_aliasing_cases(tmp_path):
             a = W.copy()
             fn_orc(a, v, ci, cj, 0.05, SEED, 3)
             assert np.array_equal(a, refb.get_rows(0))
+
+
+def test_hpe_train_and_update_community(tmp_path):
+    """HPE (SURVEY.md §8f rank 2): HPE::Train (src/model/HPE.cpp:93-147) = UpdateCommunity (src/proNet.cpp:3018-3054,
+    Opt_SigmoidRegSGD :1332-1351) + UpdatePair with the roles swapped, against the compiled reference."""
+    src, dst, w = graphs.random_graph(250, 3000, seed=23)
+    dim = 12
+    ref, (off, col, ww), _ = _mk(str(tmp_path), src, dst, w, 1, B.K_HPE, dim)
+    g = B.OracleGraph(B.SEM_CPP, off, col, ww)
+    Wv, Wc = graphs.init_tables(g.V, dim, seed=4)
+    Wc = (np.random.RandomState(5).random_sample(Wc.shape) - 0.5) / dim  # HPE::Init: both tables random (HPE.cpp:38-56)
+    # one UpdateCommunity call, incl. a sink-free 4-step walk and repeated negatives on a tiny K
+    ref.set_rows(0, Wv), ref.set_rows(1, Wc)
+    a, c = Wv.copy(), Wc.copy()
+    ref.seed(SEED, 3)
+    ref.update_community(7, int(col[off[7]]), 0.01, 4, 5, 0.025)
+    pos = g.update_community_cpp(a, c, 7, int(col[off[7]]), 0.01, 4, 5, 0.025, SEED, 3)
+    assert pos == ref.pos()
+    assert np.array_equal(a, ref.get_rows(0)) and np.array_equal(c, ref.get_rows(1))
+    # the whole Train() loop: 1M samples, walk_steps 3, K 5, reg 0.01
+    ref.set_rows(0, Wv), ref.set_rows(1, Wc)
+    a, c = Wv.copy(), Wc.copy()
+    ref.seed(SEED, 0)
+    ref.train_hpe(1, 3, 5, 0.01, alpha=0.025, workers=1)
+    pos = g.train_hpe_cpp(a, c, 3, 5, 0.01, 0.025, 1000000, SEED, 0)
+    assert pos == ref.pos()
+    assert np.array_equal(a, ref.get_rows(0)) and np.array_equal(c, ref.get_rows(1))
