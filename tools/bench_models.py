@@ -123,7 +123,7 @@ def main():
             run(f"hoprec_d{dim}_big", m, m.train_hoprec, p, 5 * 14 * dim * 4, "samples", a.steps, a.warmup)
 
     # ---- configs[1] under Go semantics (CDF-scan neighbour sampling -> binary search over prefix sums, random contexts) ----
-    if want("line_go") or want("line_cpp"):
+    if want("line_go") or want("line_cpp") or want("hpe"):
         nv = int(1_000_000 * a.scale)
         src, dst, w = synth.power_law_edges(nv, 10 * nv, 20261018)
         off, col, ww, _ = synth.csr_from_edges(src, dst, w, True)
@@ -136,6 +136,15 @@ def main():
             p = capi.default_params()
             p.semantics, p.mode, p.seed, p.total = sem, capi.MODE_HOGWILD, 1, 1 << 24
             run(f"{nm}_d128_c2", m, m.train_line, p, 2 * 7 * 128 * 4 + 76, "samples", a.steps, a.warmup)
+            del m, g
+        if want("hpe"):
+            # HPE (C++): walk_steps regularised skip-gram steps + one UpdatePair per sample = (steps + 1) x (K + 2) rows R+W
+            g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP)
+            m = capi.Model(g, 128, 2, capi.F32)
+            m.init(0, True, 1), m.init(1, True, 2)
+            p = capi.default_params()
+            p.semantics, p.mode, p.seed, p.total, p.walk_steps, p.lambda_ = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 1 << 22, 5, 0.01
+            run("hpe_d128_c2", m, m.train_hpe, p, 2 * 7 * 128 * 4 + 28, "pair_updates", a.steps, a.warmup)
             del m, g
 
     # ---- configs[2]: DeepWalk dim 128, walk_steps 40, window 5 (V scaled; one epoch slice per step) ----
