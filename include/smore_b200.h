@@ -218,7 +218,7 @@ typedef struct {
     uint64_t total;       /* C++: sample_times*1e6 (LINE.cpp:119) ; Go: sample_times*MaxLine (line.go:85) */
     int negative_samples; /* -negative_samples (LINE / skip-gram) */
     int order;            /* LINE: 1 or 2 */
-    double lambda;        /* Go BPR L2 (bpr.go, -lambda); HPE: -reg (cli/hpe.cpp:57) */
+    double lambda;        /* Go BPR L2 (bpr.go, -lambda); HPE / MF: -reg (cli/hpe.cpp:57, cli/mf.cpp:50) */
     int walk_times, walk_steps, window_min, window_max; /* DeepWalk: window_max = -window_size; Walklets: both */
     int max_warps;        /* HOGWILD: cap on concurrent warps (0 = fill the device) */
     int64_t max_walks;    /* DeepWalk/Walklets: stop after this many walks (<0: all walk_times*V) */
@@ -253,6 +253,10 @@ int smore_train_deepwalk(smore_model_t m, const smore_train_params* p);
  * context walks on for walk_steps steps; Opt_SigmoidRegSGD :1332-1351 with reg = params.lambda) -> UpdatePair with the
  * roles swapped. C++ only (the Go hpe model is LINE-2 with UpdatePair, hpe.go:97-107: use smore_train_line). */
 int smore_train_hpe(smore_model_t m, const smore_train_params* p);
+/* MF::Train (src/model/MF.cpp:50-98): SourceSample -> TargetSample -> UpdateFactorizedPair (src/proNet.cpp:2591-2614,
+ * Opt_SGD :991-1012: linear prediction, labels +1/-1, reg = params.lambda) on table 0 in both roles. C++ only; create the
+ * graph with SMORE_NEG_NO_DEGREES as the MF constructor does (MF.cpp:4-7). */
+int smore_train_mf(smore_model_t m, const smore_train_params* p);
 /* Walklets::Train (src/model/Walklets.cpp:6-64): RandomWalk + ScaleSkipGrams + UpdatePairs. C++ only. */
 int smore_train_walklets(smore_model_t m, const smore_train_params* p);
 

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- C-ABI harness around the UNMODIFIED compiled reference (C++ tree).
 //
 // Built by oracle/Makefile from the reference sources where they lie under /root/reference/src
-// (proNet.cpp, util.cpp, model/{LINE,DeepWalk,Walklets,BPR,WARP,HBPR,HPE}.cpp) with random.cpp replaced
+// (proNet.cpp, util.cpp, model/{LINE,DeepWalk,Walklets,BPR,WARP,HBPR,HPE,MF}.cpp) with random.cpp replaced
 // by ref_shim.cpp; output goes to oracle/_ref/ only. Nothing here is copied from the reference: this
 // file only CALLS its public classes (src/proNet.h:109-269, src/model/*.h).
 //
@@ -18,6 +18,7 @@
 #include "model/HBPR.h"
 #include "model/HPE.h"
 #include "model/LINE.h"
+#include "model/MF.h"
 #include "model/WARP.h"
 #include "model/Walklets.h"
 
@@ -26,7 +27,7 @@ extern "C" uint64_t ref_shim_pos(void);
 
 namespace {
 
-enum Kind { K_LINE = 0, K_DEEPWALK = 1, K_WALKLETS = 2, K_BPR = 3, K_WARP = 4, K_HOPREC = 5, K_HPE = 6 };
+enum Kind { K_LINE = 0, K_DEEPWALK = 1, K_WALKLETS = 2, K_BPR = 3, K_WARP = 4, K_HOPREC = 5, K_HPE = 6, K_MF = 7 };
 
 struct Ref {
     int kind;
@@ -37,6 +38,7 @@ struct Ref {
     WARP* warp = nullptr;
     HBPR* hbpr = nullptr;
     HPE* hpe = nullptr;
+    MF* mf = nullptr;
     int dim = 0;
     int order = 2;
 
@@ -48,6 +50,7 @@ struct Ref {
             case K_BPR: return bpr->pnet;
             case K_WARP: return warp->pnet;
             case K_HPE: return hpe->pnet;
+            case K_MF: return mf->pnet;
             default: return hbpr->pnet;
         }
     }
@@ -62,6 +65,7 @@ struct Ref {
             case K_BPR: return t == 0 ? &bpr->w_vertex : nullptr;
             case K_WARP: return t == 0 ? &warp->w_vertex : nullptr;
             case K_HPE: return t == 0 ? &hpe->w_vertex : &hpe->w_context;
+            case K_MF: return t == 0 ? &mf->w_vertex : nullptr;
             default: return t == 0 ? &hbpr->w_vertex : &hbpr->w_context;
         }
     }
@@ -82,6 +86,7 @@ void* ref_new(int kind) {
         case K_WARP: r->warp = new WARP(); break;
         case K_HOPREC: r->hbpr = new HBPR(); break;
         case K_HPE: r->hpe = new HPE(); break;
+        case K_MF: r->mf = new MF(); break;
         default: delete r; return nullptr;
     }
     return r;
@@ -89,7 +94,7 @@ void* ref_new(int kind) {
 
 void ref_free(void* h) {
     Ref* r = (Ref*)h;
-    delete r->line; delete r->dw; delete r->wl; delete r->bpr; delete r->warp; delete r->hbpr; delete r->hpe;
+    delete r->line; delete r->dw; delete r->wl; delete r->bpr; delete r->warp; delete r->hbpr; delete r->hpe; delete r->mf;
     delete r;
 }
 
@@ -117,6 +122,7 @@ void ref_init(void* h, int dim, int order) {
         case K_BPR: r->bpr->Init(dim); break;
         case K_WARP: r->warp->Init(dim); break;
         case K_HPE: r->hpe->Init(dim); break;
+        case K_MF: r->mf->Init(dim); break;
         default: r->hbpr->Init(dim); break;
     }
 }
@@ -254,6 +260,18 @@ void ref_train_hpe(void* h, int sample_times, int walk_steps, int K, double reg,
     if (r->kind == K_HPE) r->hpe->Train(sample_times, walk_steps, K, reg, alpha, workers);
 }
 
+// MF::Train (src/model/MF.cpp:50-98) as cli/mf.cpp:65 calls it
+void ref_train_mf(void* h, int sample_times, int K, double alpha, double reg, int workers) {
+    Ref* r = (Ref*)h;
+    if (r->kind == K_MF) r->mf->Train(sample_times, K, alpha, reg, workers);
+}
+
+// proNet::UpdateFactorizedPair (src/proNet.cpp:2591-2614) with one table in both roles, as MF::Train passes it
+void ref_update_factorized_pair(void* h, int64_t v, int64_t c, double reg, int K, double alpha) {
+    Ref* r = (Ref*)h;
+    r->pnet().UpdateFactorizedPair(*r->table(0), *r->table(0), (long)v, (long)c, r->dim, reg, K, alpha);
+}
+
 // proNet::UpdateCommunity (src/proNet.cpp:3018-3054) on the model's own tables
 void ref_update_community(void* h, int64_t v, int64_t c, double reg, int walk_steps, int K, double alpha) {
     Ref* r = (Ref*)h;
@@ -269,6 +287,7 @@ void ref_save_weights(void* h, const char* path) {
         case K_BPR: r->bpr->SaveWeights(path); break;
         case K_WARP: r->warp->SaveWeights(path); break;
         case K_HPE: r->hpe->SaveWeights(path); break;
+        case K_MF: r->mf->SaveWeights(path); break;
         default: r->hbpr->SaveWeights(path); break;
     }
 }

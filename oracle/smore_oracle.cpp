@@ -354,6 +354,29 @@ struct Graph {
             for (int k = 0; k < dim; ++k) rv[k] += back_err[k];
         }
     }
+    // src/proNet.cpp:991-1012 (MF): linear prediction, no sigmoid
+    void opt_sgd(const double* wv, const double* wc, double label, int dim, double alpha, double reg, double* loss_v,
+                 double* loss_c) const {
+        double f = 0;
+        for (int d = 0; d < dim; ++d) f += wv[d] * wc[d];
+        double g = (label - f);
+        for (int d = 0; d < dim; ++d) loss_v[d] += alpha * (g * wc[d] - reg * wv[d]);
+        for (int d = 0; d < dim; ++d) loss_c[d] += alpha * (g * wv[d] - reg * wc[d]);
+    }
+    // src/proNet.cpp:2591-2614: labels +1 / -1; MF::Train passes ONE table in both roles, so rows may alias
+    void update_factorized_pair_cpp(double* Wv, double* Wc, int64_t vertex, int64_t context, int dim, double reg, int K,
+                                    double alpha, Draws& d, std::vector<double>& back_err) const {
+        back_err.assign(dim, 0.0);
+        double* rv = Wv + vertex * dim;
+        double* rc = Wc + context * dim;
+        opt_sgd(rv, rc, 1.0, dim, alpha, reg, back_err.data(), rc);
+        for (int n = 0; n != K; ++n) {
+            int64_t c = negative_sample(d);
+            rc = Wc + c * dim;
+            opt_sgd(rv, rc, -1.0, dim, alpha, reg, back_err.data(), rc);
+        }
+        for (int k = 0; k < dim; ++k) rv[k] += back_err[k];
+    }
     // optimizer.go:21-58 + sgdUpdate :61-84
     void update_pair_go(double* Wv, double* Wc, int64_t vertex, int64_t context, int dim, int K, double alpha, Draws& d,
                         std::vector<double>& vgrad, std::vector<double>& cgrad, std::vector<double>& ngrad) const {
@@ -720,6 +743,32 @@ uint64_t orc_train_hoprec_cpp(void* h, double* W, int dim, int walk_steps, doubl
         count++;
         sch.tick(count);
     }
+    return d.s.pos;
+}
+
+// C++ MF: src/model/MF.cpp:50-98 (one table; negatives "no_degrees", MF.cpp:4-7; count from 0)
+uint64_t orc_train_mf_cpp(void* h, double* W, int dim, int K, double reg, double alpha, uint64_t total, uint64_t seed,
+                          uint64_t stream) {
+    Graph* g = (Graph*)h;
+    Draws d(seed, stream);
+    CppSchedule sch(alpha, total);
+    std::vector<double> be;
+    unsigned long long count = 0;
+    while (count < total) {
+        int64_t v1 = g->source_sample(d);
+        int64_t v2 = g->target_sample(v1, d);
+        g->update_factorized_pair_cpp(W, W, v1, v2, dim, reg, K, sch.cur, d, be);
+        count++;
+        sch.tick(count);
+    }
+    return d.s.pos;
+}
+uint64_t orc_update_factorized_pair_cpp(void* h, double* W, int64_t v, int64_t c, int dim, double reg, int K, double alpha,
+                                        uint64_t seed, uint64_t stream) {
+    Graph* g = (Graph*)h;
+    Draws d(seed, stream);
+    std::vector<double> be;
+    g->update_factorized_pair_cpp(W, W, v, c, dim, reg, K, alpha, d, be);
     return d.s.pos;
 }
 

@@ -1,6 +1,6 @@
 // Host-side mirror of the reference CLIs on top of the C ABI (include/smore_b200.h).
 //
-//   smore <model> -train net.txt -save rep.txt [flags]      model in {line, deepwalk, walklets, bpr, warp, hoprec, hpe}
+//   smore <model> -train net.txt -save rep.txt [flags]      model in {line, deepwalk, walklets, bpr, warp, hoprec, hpe, mf}
 //   (or invoke through a symlink named after the model: `line -train ...`)
 //
 // Flag names, defaults and the four-call sequence LoadEdgeList -> Init -> Train -> SaveWeights are those of
@@ -68,7 +68,7 @@ int die(const char* what) {
 
 void usage() {
     printf("[smore_b200]\n\tB200-native SMORe trainers (LINE, DeepWalk, Walklets, BPR, WARP, HOP-Rec)\n\n"
-           "Usage:\n\tsmore <line|deepwalk|walklets|bpr|warp|hoprec|hpe> -train net.txt -save rep.txt [options]\n\n"
+           "Usage:\n\tsmore <line|deepwalk|walklets|bpr|warp|hoprec|hpe|mf> -train net.txt -save rep.txt [options]\n\n"
            "Options Description:\n"
            "\t-train <string>\n\t\tTrain the Network data\n"
            "\t-save <string>\n\t\tSave the representation data\n"
@@ -80,7 +80,7 @@ void usage() {
            "\t-sample_times <int>\n\t\tNumber of training samples (cpp: *Million, go: *edge lines); default is 10\n"
            "\t-walk_times <int> -walk_steps <int> -window_size <int> -window_min <int> -window_max <int>\n"
            "\t-lambda <float>\n\t\tGo BPR regularisation; default is 0.001\n"
-           "\t-reg <float>\n\t\tHPE regularisation; default is 0.01\n"
+           "\t-reg <float>\n\t\tHPE / MF regularisation; default is 0.01\n"
            "\t-alpha <float>\n\t\tInit learning rate; default is 0.025\n"
            "\t-threads <int>\n\t\tAccepted for compatibility; workers are GPU warps\n"
            "\t-load_v <string> -load_c <string>\n\t\tPretrained vertex / context embeddings (text, matched by vertex name)\n"
@@ -95,7 +95,7 @@ int main(int argc, char** argv) {
     int first = 1;
     const char* base = strrchr(argv[0], '/');
     base = base ? base + 1 : argv[0];
-    for (const char* m : {"line", "deepwalk", "walklets", "bpr", "warp", "hoprec", "hpe"})
+    for (const char* m : {"line", "deepwalk", "walklets", "bpr", "warp", "hoprec", "hpe", "mf"})
         if (!strcmp(base, m)) model = m;
     if (model.empty()) {
         if (argc < 2 || argv[1][0] == '-') {
@@ -111,7 +111,7 @@ int main(int argc, char** argv) {
     }
     Args a = parse(argc, argv, first);
     const bool has_go_cli = model == "line" || model == "deepwalk" || model == "bpr";
-    if (!has_go_cli && model != "walklets" && model != "warp" && model != "hoprec" && model != "hpe") {
+    if (!has_go_cli && model != "walklets" && model != "warp" && model != "hoprec" && model != "hpe" && model != "mf") {
         fprintf(stderr, "smore: unknown model '%s'\n", model.c_str());
         return 1;
     }
@@ -126,10 +126,11 @@ int main(int argc, char** argv) {
         usage();
         return 1;
     }
-    const bool ranking = model == "bpr" || model == "warp" || model == "hoprec";
+    // (MF: one table, "no_degrees" negatives and a directed load, like the ranking models: MF.cpp:4-7, cli/mf.cpp:63)
+    const bool ranking = model == "bpr" || model == "warp" || model == "hoprec" || model == "mf";
     // defaults: cmd/line/main.go:15-21, cmd/deepwalk/main.go:13-22, cmd/bpr/main.go:13-20, cli/*.cpp
     const int dim = (int)a.num("dimensions", 64);
-    const bool undirected = model == "hoprec" ? true : a.flag("undirected", !(model == "bpr" || model == "warp"));
+    const bool undirected = model == "hoprec" ? true : a.flag("undirected", !(model == "bpr" || model == "warp" || model == "mf"));
     const int sample_times = (int)a.num("sample_times", 10);
     const int dtype = a.str("dtype", "f32") == "f64" ? SMORE_F64 : SMORE_F32;
 
@@ -157,7 +158,7 @@ int main(int argc, char** argv) {
     p.alpha = a.real("alpha", 0.025);
     p.negative_samples = (int)a.num("negative_samples", 5);
     p.order = a.num("order", 2) == 1 ? 1 : 2;
-    p.lambda = model == "hpe" ? a.real("reg", 0.01) : a.real("lambda", 0.001);  // cli/hpe.cpp:57
+    p.lambda = (model == "hpe" || model == "mf") ? a.real("reg", 0.01) : a.real("lambda", 0.001);  // cli/hpe.cpp:57
     p.walk_times = (int)a.num("walk_times", 10);
     // cli/deepwalk.cpp:56 defaults walk_steps to 5 (sic), cli/walklets.cpp:54 and cmd/deepwalk/main.go:20 to 40
     p.walk_steps = (int)a.num("walk_steps", model == "hoprec" || model == "hpe" ? 5 : (model == "deepwalk" && sem == SMORE_SEM_CPP ? 5 : 40));
@@ -204,6 +205,7 @@ int main(int argc, char** argv) {
         if (model == "bpr") return smore_train_bpr(m, &q);
         if (model == "warp") return smore_train_warp(m, &q);
         if (model == "hpe") return smore_train_hpe(m, &q);
+        if (model == "mf") return smore_train_mf(m, &q);
         return smore_train_hoprec(m, &q);
     };
     uint64_t samples = 0, pairs = 0;

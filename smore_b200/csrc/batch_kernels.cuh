@@ -269,7 +269,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_apply_delta(typename C::T* __
 // 3 = row-sharded, bulk exchange: remote vertex rows were gathered into the local staging table a.x.wrk beforehand
 // (k_line_requests -> all-to-all -> k_gather_rows -> all-to-all), so every access of this kernel is to local HBM --
 // except the rows of HOT vertices (ExchDev::hot), which are reached through the peer mappings.
-template <class C, bool GO, int SHARD>
+// KIND: 0 = skip-gram pair update (LINE), 1 = MF: the same sampling loop around UpdateFactorizedPair (MF::Train,
+// src/model/MF.cpp:70-92, draws exactly what LINE::Train draws).
+template <class C, bool GO, int SHARD, int KIND = 0>
 __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
     constexpr bool STAGED = SHARD == 1;
     using T = typename C::T;
@@ -359,7 +361,8 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             if constexpr (SHARD == 2) vpush = owner_v.row(v1);
             // replica rows never alias shard rows in memory; nor do staging rows (v1 < 0 then never equals a context id)
             const bool same = SHARD == 2 ? false : a.same_table != 0;
-            if (!GO) update_pair_cpp<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
+            if constexpr (KIND == 1) update_factorized_pair<C, TV, TC>(tv, tc, a.dim, same, v1, my, nrows, alpha, a.lambda, lane);
+            else if (!GO) update_pair_cpp<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
             else update_pair_go<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
             st.count++;
             st.pairs++;

@@ -289,4 +289,6 @@ int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets);
 template <typename T>
 int train_hpe_t(smore_model_s* m, const smore_train_params* p);
 template <typename T>
+int train_mf_t(smore_model_s* m, const smore_train_params* p);
+template <typename T>
 int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind);

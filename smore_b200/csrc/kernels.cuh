@@ -494,6 +494,81 @@ __device__ __forceinline__ void update_community_step(const TV& tv, const TC& tc
     v.store(pv, lane, dim);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// MF: proNet::UpdateFactorizedPair (src/proNet.cpp:2591-2614) with Opt_SGD (:991-1012): linear
+// prediction, labels +1 / -1, L2 term inside the bracket:
+//     g = label - v.c      loss_vertex += alpha * (g * c - reg * v)      c += alpha * (g * v - reg * c)
+// MF::Train passes ONE table in both roles (src/model/MF.cpp:78), so a context row may BE the vertex row: the ORDERED
+// path re-reads both rows from memory for every context, as the reference's references into the live table do.
+// ---------------------------------------------------------------------------------------------------------------
+template <class C, class TV, class TC>
+__device__ __forceinline__ void update_factorized_pair(const TV& tv, const TC& tc, int dim, bool same_table, int v1,
+                                                       int my_id, int nrows, typename C::T alpha, typename C::T reg,
+                                                       int lane) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    const bool active = lane < nrows;
+    const unsigned peers = __match_any_sync(kFull, active ? my_id : (-1 - lane));
+    const bool dup = __any_sync(kFull, (active && __popc(peers) > 1) || (active && same_table && my_id == v1));
+    T* pv = tv.row(v1);
+    Row<C> back;
+    back.zero();
+    if (!dup) {
+        Row<C> v;
+        v.load(pv, lane, dim);
+        for (int base = 0; base < nrows; base += kCtxChunk) {
+            Row<C> c[kCtxChunk];
+            int ids[kCtxChunk];
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) {
+                ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
+                if (base + r < nrows) c[r].load(tc.row(ids[r]), lane, dim);
+            }
+            T f[kCtxChunk];
+            dots<C, kCtxChunk>(v, c, nrows - base, f);
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) {
+                if (base + r < nrows) {
+                    const T label = (base + r == 0) ? (T)1 : (T)-1;
+                    const T g = A::sub(label, f[r]);
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) {
+                        const T ce = c[r].x[e];
+                        back.x[e] = A::add(back.x[e], A::mul(alpha, A::sub(A::mul(g, ce), A::mul(reg, v.x[e]))));
+                        c[r].x[e] = A::add(ce, A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce))));
+                    }
+                    c[r].store(tc.row(ids[r]), lane, dim);
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
+        v.store(pv, lane, dim);
+    } else {
+        for (int r = 0; r < nrows; ++r) {
+            const int cid = __shfl_sync(kFull, my_id, r);
+            T* pc = tc.row(cid);
+            Row<C> v, c;
+            v.load(pv, lane, dim);
+            c.load(pc, lane, dim);
+            const T label = (r == 0) ? (T)1 : (T)-1;
+            const T g = A::sub(label, dot(v, c));
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                const T ce = c.x[e];
+                back.x[e] = A::add(back.x[e], A::mul(alpha, A::sub(A::mul(g, ce), A::mul(reg, v.x[e]))));
+                c.x[e] = A::add(ce, A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce))));
+            }
+            c.store(pc, lane, dim);
+        }
+        Row<C> v;
+        v.load(pv, lane, dim);
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
+        v.store(pv, lane, dim);
+    }
+}
+
 // HPE::Train (src/model/HPE.cpp:121-143): SourceSample, TargetSample, UpdateCommunity(v1, v2: the context walks on for
 // walk_steps steps, one positive + K negatives per step), then UpdatePair with the roles swapped (vertex v2, context
 // v1). The number of words a sample consumes depends on the walk (a sink ends it), so draws come from the sequential

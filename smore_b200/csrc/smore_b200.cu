@@ -973,6 +973,13 @@ int smore_train_hpe(smore_model_t m, const smore_train_params* p) {
     return m->dtype == SMORE_F64 ? train_hpe_t<double>(m, p) : train_hpe_t<float>(m, p);
 }
 
+int smore_train_mf(smore_model_t m, const smore_train_params* p) {
+    if (int rc = check_train(m, p, 1)) return rc;
+    if (p->semantics != SMORE_SEM_CPP) return fail(SMORE_E_UNSUPPORTED, "MF exists only in the C++ tree");
+    if (p->negative_samples < 0 || p->negative_samples > 31) return fail(SMORE_E_UNSUPPORTED, "negative_samples must be in [0,31]");
+    return m->dtype == SMORE_F64 ? train_mf_t<double>(m, p) : train_mf_t<float>(m, p);
+}
+
 int smore_train_bpr(smore_model_t m, const smore_train_params* p) {
     if (int rc = check_train(m, p, p && p->semantics == SMORE_SEM_GO ? 2 : 1)) return rc;
     return m->dtype == SMORE_F64 ? train_ranking_t<double>(m, p, RANK_BPR) : train_ranking_t<float>(m, p, RANK_BPR);

@@ -41,6 +41,32 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
 }
 
 
+// MF trainer (src/model/MF.cpp:50-98): LINE's sampling loop, one table in both roles, jobs = total / workers counted from 0.
+template <typename T>
+int train_mf_t(smore_model_s* m, const smore_train_params* p) {
+    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
+        using C = decltype(cfg);
+        void (*kern)(TrainArgs<T>) = k_line<C, false, 0, 1>;
+        const size_t smem = batch_smem_bytes<T>(0, p->negative_samples, 0);
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        Launch L;
+        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
+        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
+        const uint64_t trips = p->total / (uint64_t)L.warps;
+        if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
+        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)p->total, 1, 0, 0);
+        a.jobs = trips;
+        Timer t;
+        if (int rc = t.start()) return rc;
+        kern<<<L.blocks, kBlockThreads, smem>>>(a);
+        g_launches++;
+        CU(cudaGetLastError());
+        if (int rc = t.stop(&m->st_ms)) return rc;
+        m->st_samples = trips * (uint64_t)L.warps;
+        return collect_stats(m, L.warps);
+    });
+}
+
 // ---- bulk-exchange mode (exchange_host.h; device side: batch_kernels.cuh) --------------------------------------------
 // Every rank runs the same number of super-batches (the collectives must match): nsb = ceil(total / (superbatch*world)),
 // and splits its own share of the samples evenly over them. Two streams: `sc` carries everything that moves rows

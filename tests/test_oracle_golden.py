@@ -116,3 +116,18 @@ def test_hpe_train_golden(tag):
     pos = g.train_hpe_cpp(a, c, int(steps), int(K), float(reg), 0.025, 1000000, SEED, 0)
     assert pos == int(GH[f"hpe_{tag}_words"])
     assert np.array_equal(a, GH[f"hpe_{tag}_v"]) and np.array_equal(c, GH[f"hpe_{tag}_c"])
+
+
+# ---- MF (tests/golden/golden_mf_v1.npz, tests/golden/make_golden_mf.py) -----------------------------------------------
+GM = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_mf_v1.npz"))
+
+
+@pytest.mark.parametrize("tag", ["bip", "small"])
+def test_mf_train_golden(tag):
+    off, col, ww, _ = B.edges_to_csr(GM[f"{tag}_src"], GM[f"{tag}_dst"], GM[f"{tag}_w"], 0)
+    g = B.OracleGraph(B.SEM_CPP, off, col, ww, neg_method=B.NEG_NO_DEGREES)
+    K, reg = GM[f"{tag}_args"]
+    a = GM[f"{tag}_init"].copy()
+    pos = g.train_mf_cpp(a, int(K), float(reg), 0.025, 1000000, SEED, 0)
+    assert pos == int(GM[f"{tag}_words"])
+    assert np.array_equal(a, GM[f"{tag}_v"])

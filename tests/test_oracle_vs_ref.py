@@ -252,3 +252,29 @@ def test_hpe_train_and_update_community(tmp_path):
     pos = g.train_hpe_cpp(a, c, 3, 5, 0.01, 0.025, 1000000, SEED, 0)
     assert pos == ref.pos()
     assert np.array_equal(a, ref.get_rows(0)) and np.array_equal(c, ref.get_rows(1))
+
+
+def test_mf_train_and_update_factorized_pair(tmp_path):
+    """MF (SURVEY.md §8f rank 3): MF::Train (src/model/MF.cpp:50-98) = UpdateFactorizedPair (src/proNet.cpp:2591-2614,
+    Opt_SGD :991-1012) on ONE table in both roles, negatives "no_degrees" (MF.cpp:4-7), against the compiled reference."""
+    src, dst, w = graphs.bipartite_graph(160, 120, 3000, seed=29)
+    dim = 12
+    ref, (off, col, ww), _ = _mk(str(tmp_path), src, dst, w, 0, B.K_MF, dim)
+    g = B.OracleGraph(B.SEM_CPP, off, col, ww, neg_method=B.NEG_NO_DEGREES)
+    W, _ = graphs.init_tables(g.V, dim, seed=6)
+    # single calls incl. the aliasing cases of a shared table: context == vertex, and an ordinary pair
+    for v, c in ((5, 5), (5, int(col[off[5]]))):
+        ref.set_rows(0, W)
+        a = W.copy()
+        ref.seed(SEED, 7)
+        ref.update_factorized_pair(v, c, 0.01, 5, 0.025)
+        pos = g.update_factorized_pair_cpp(a, v, c, 0.01, 5, 0.025, SEED, 7)
+        assert pos == ref.pos()
+        assert np.array_equal(a, ref.get_rows(0))
+    ref.set_rows(0, W)
+    a = W.copy()
+    ref.seed(SEED, 0)
+    ref.train_mf(1, 5, 0.01, alpha=0.025, workers=1)
+    pos = g.train_mf_cpp(a, 5, 0.01, 0.025, 1000000, SEED, 0)
+    assert pos == ref.pos()
+    assert np.array_equal(a, ref.get_rows(0))
