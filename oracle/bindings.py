@@ -25,7 +25,7 @@ REF_FAST_SO = os.path.join(HERE, "_ref", "libsmore_ref_fast.so")
 
 SEM_CPP, SEM_GO = 0, 1
 NEG_DEGREES, NEG_IN_DEGREES, NEG_NO_DEGREES = 0, 1, 2
-K_LINE, K_DEEPWALK, K_WALKLETS, K_BPR, K_WARP, K_HOPREC, K_HPE, K_MF = range(8)
+K_LINE, K_DEEPWALK, K_WALKLETS, K_BPR, K_WARP, K_HOPREC, K_HPE, K_MF, K_SKEWOPT = range(9)
 
 u64 = C.c_uint64
 i64 = C.c_int64
@@ -94,6 +94,10 @@ class Oracle:
             L.orc_train_warp_cpp.restype = u64
             L.orc_train_hoprec_cpp.argtypes = [vp, vp, C.c_int, C.c_int, f64, u64, u64, u64]
             L.orc_train_hoprec_cpp.restype = u64
+            L.orc_train_skewopt_cpp.argtypes = [vp, vp, C.c_int, f64, f64, C.c_int, f64, u64, u64, u64]
+            L.orc_train_skewopt_cpp.restype = u64
+            L.orc_update_sbpr_pair_cpp.argtypes = [vp, vp, i64, i64, C.c_int, f64, f64, C.c_int, f64, u64, u64]
+            L.orc_update_sbpr_pair_cpp.restype = u64
             L.orc_train_mf_cpp.argtypes = [vp, vp, C.c_int, C.c_int, f64, f64, u64, u64, u64]
             L.orc_train_mf_cpp.restype = u64
             L.orc_update_factorized_pair_cpp.argtypes = [vp, vp, i64, i64, C.c_int, f64, C.c_int, f64, u64, u64]
@@ -226,6 +230,12 @@ class OracleGraph:
     def train_hoprec_cpp(self, W, walk_steps, alpha, total, seed, stream=0):
         return self.L.orc_train_hoprec_cpp(self.h, _ptr(W), W.shape[1], walk_steps, alpha, total, seed, stream)
 
+    def train_skewopt_cpp(self, W, xi, omega, eta, alpha, total, seed, stream=0):
+        return self.L.orc_train_skewopt_cpp(self.h, _ptr(W), W.shape[1], xi, omega, eta, alpha, total, seed, stream)
+
+    def update_sbpr_pair_cpp(self, W, v, ci, xi, omega, eta, alpha, seed, stream=0):
+        return self.L.orc_update_sbpr_pair_cpp(self.h, _ptr(W), v, ci, W.shape[1], xi, omega, eta, alpha, seed, stream)
+
     def train_mf_cpp(self, W, K, reg, alpha, total, seed, stream=0):
         return self.L.orc_train_mf_cpp(self.h, _ptr(W), W.shape[1], K, reg, alpha, total, seed, stream)
 
@@ -324,6 +334,8 @@ class Ref:
             L.ref_update_fbpr_pair.argtypes = [vp, i64, i64, i64, f64, f64]
             L.ref_train.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64, C.c_int]
             L.ref_save_weights.argtypes = [vp, C.c_char_p]
+            L.ref_train_skewopt.argtypes = [vp, C.c_int, C.c_int, f64, f64, f64, f64, C.c_int, C.c_int]
+            L.ref_update_sbpr_pair.argtypes = [vp, i64, i64, f64, f64, C.c_int, f64]
             L.ref_train_mf.argtypes = [vp, C.c_int, C.c_int, f64, f64, C.c_int]
             L.ref_update_factorized_pair.argtypes = [vp, i64, i64, f64, C.c_int, f64]
             L.ref_train_hpe.argtypes = [vp, C.c_int, C.c_int, C.c_int, f64, f64, C.c_int]
@@ -440,6 +452,13 @@ class Ref:
     def train(self, a, b=0, c=0, d=0, e=0, alpha=0.025, workers=1):
         with quiet():
             self.L.ref_train(self.h, a, b, c, d, e, alpha, workers)
+
+    def train_skewopt(self, sample_times, xi, omega, eta, alpha=0.025, workers=1):
+        with quiet():
+            self.L.ref_train_skewopt(self.h, sample_times, 5, alpha, 0.01, xi, omega, eta, workers)
+
+    def update_sbpr_pair(self, v, ci, xi, omega, eta, alpha):
+        self.L.ref_update_sbpr_pair(self.h, v, ci, xi, omega, eta, alpha)
 
     def train_mf(self, sample_times, K, reg, alpha=0.025, workers=1):
         with quiet():

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- C-ABI harness around the UNMODIFIED compiled reference (C++ tree).
 //
 // Built by oracle/Makefile from the reference sources where they lie under /root/reference/src
-// (proNet.cpp, util.cpp, model/{LINE,DeepWalk,Walklets,BPR,WARP,HBPR,HPE,MF}.cpp) with random.cpp replaced
+// (proNet.cpp, util.cpp, model/{LINE,DeepWalk,Walklets,BPR,WARP,HBPR,HPE,MF,SkewOPT}.cpp) with random.cpp replaced
 // by ref_shim.cpp; output goes to oracle/_ref/ only. Nothing here is copied from the reference: this
 // file only CALLS its public classes (src/proNet.h:109-269, src/model/*.h).
 //
@@ -19,6 +19,7 @@
 #include "model/HPE.h"
 #include "model/LINE.h"
 #include "model/MF.h"
+#include "model/SkewOPT.h"
 #include "model/WARP.h"
 #include "model/Walklets.h"
 
@@ -27,7 +28,7 @@ extern "C" uint64_t ref_shim_pos(void);
 
 namespace {
 
-enum Kind { K_LINE = 0, K_DEEPWALK = 1, K_WALKLETS = 2, K_BPR = 3, K_WARP = 4, K_HOPREC = 5, K_HPE = 6, K_MF = 7 };
+enum Kind { K_LINE = 0, K_DEEPWALK = 1, K_WALKLETS = 2, K_BPR = 3, K_WARP = 4, K_HOPREC = 5, K_HPE = 6, K_MF = 7, K_SKEWOPT = 8 };
 
 struct Ref {
     int kind;
@@ -39,6 +40,7 @@ struct Ref {
     HBPR* hbpr = nullptr;
     HPE* hpe = nullptr;
     MF* mf = nullptr;
+    SPR* spr = nullptr;
     int dim = 0;
     int order = 2;
 
@@ -51,6 +53,7 @@ struct Ref {
             case K_WARP: return warp->pnet;
             case K_HPE: return hpe->pnet;
             case K_MF: return mf->pnet;
+            case K_SKEWOPT: return spr->pnet;
             default: return hbpr->pnet;
         }
     }
@@ -66,6 +69,7 @@ struct Ref {
             case K_WARP: return t == 0 ? &warp->w_vertex : nullptr;
             case K_HPE: return t == 0 ? &hpe->w_vertex : &hpe->w_context;
             case K_MF: return t == 0 ? &mf->w_vertex : nullptr;
+            case K_SKEWOPT: return t == 0 ? &spr->w_vertex : nullptr;
             default: return t == 0 ? &hbpr->w_vertex : &hbpr->w_context;
         }
     }
@@ -87,6 +91,7 @@ void* ref_new(int kind) {
         case K_HOPREC: r->hbpr = new HBPR(); break;
         case K_HPE: r->hpe = new HPE(); break;
         case K_MF: r->mf = new MF(); break;
+        case K_SKEWOPT: r->spr = new SPR(); break;
         default: delete r; return nullptr;
     }
     return r;
@@ -94,7 +99,7 @@ void* ref_new(int kind) {
 
 void ref_free(void* h) {
     Ref* r = (Ref*)h;
-    delete r->line; delete r->dw; delete r->wl; delete r->bpr; delete r->warp; delete r->hbpr; delete r->hpe; delete r->mf;
+    delete r->line; delete r->dw; delete r->wl; delete r->bpr; delete r->warp; delete r->hbpr; delete r->hpe; delete r->mf; delete r->spr;
     delete r;
 }
 
@@ -123,6 +128,7 @@ void ref_init(void* h, int dim, int order) {
         case K_WARP: r->warp->Init(dim); break;
         case K_HPE: r->hpe->Init(dim); break;
         case K_MF: r->mf->Init(dim); break;
+        case K_SKEWOPT: r->spr->Init(dim); break;
         default: r->hbpr->Init(dim); break;
     }
 }
@@ -260,6 +266,18 @@ void ref_train_hpe(void* h, int sample_times, int walk_steps, int K, double reg,
     if (r->kind == K_HPE) r->hpe->Train(sample_times, walk_steps, K, reg, alpha, workers);
 }
 
+// SPR::Train (src/model/SkewOPT.cpp) as cli/skewopt.cpp calls it
+void ref_train_skewopt(void* h, int sample_times, int K, double alpha, double reg, double xi, double omega, int eta, int workers) {
+    Ref* r = (Ref*)h;
+    if (r->kind == K_SKEWOPT) r->spr->Train(sample_times, K, alpha, reg, xi, omega, eta, workers);
+}
+
+// proNet::UpdateSBPRPair (src/proNet.cpp:1517-1566) with one table in both roles, as SPR::Train passes it
+void ref_update_sbpr_pair(void* h, int64_t v, int64_t ci, double xi, double omega, int eta, double alpha) {
+    Ref* r = (Ref*)h;
+    r->pnet().UpdateSBPRPair(*r->table(0), *r->table(0), (long)v, (long)ci, r->dim, 0.01, xi, omega, eta, alpha);
+}
+
 // MF::Train (src/model/MF.cpp:50-98) as cli/mf.cpp:65 calls it
 void ref_train_mf(void* h, int sample_times, int K, double alpha, double reg, int workers) {
     Ref* r = (Ref*)h;
@@ -288,6 +306,7 @@ void ref_save_weights(void* h, const char* path) {
         case K_WARP: r->warp->SaveWeights(path); break;
         case K_HPE: r->hpe->SaveWeights(path); break;
         case K_MF: r->mf->SaveWeights(path); break;
+        case K_SKEWOPT: r->spr->SaveWeights(path); break;
         default: r->hbpr->SaveWeights(path); break;
     }
 }

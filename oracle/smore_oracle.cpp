@@ -354,6 +354,53 @@ struct Graph {
             for (int k = 0; k < dim; ++k) rv[k] += back_err[k];
         }
     }
+    // src/proNet.cpp:1070-1098 (Skew-OPT): g = (f - xi)/omega, gated at g > 2, clamped at -2, then the eta-th power chain
+    int opt_sbpr_sgd(const double* wv, const double* wc, int dim, double xi, double omega, int eta, double alpha,
+                     double* loss_v, double* loss_c) const {
+        double f = 0, g = 0, g_in_sigmoid = 1, g_chain_diff = 1;
+        for (int d = 0; d < dim; ++d) f += wv[d] * wc[d];
+        g = (f - xi) / omega;
+        if (g > 2.0) return 0;
+        if (g < -2.0) g = -2.0;
+        for (int i = 0; i < eta; i++) g_in_sigmoid *= g;
+        g_chain_diff = g_in_sigmoid / g;
+        g = fast_sigmoid(-1 * g_in_sigmoid) * g_chain_diff / omega;
+        g *= alpha;
+        for (int d = 0; d < dim; ++d) loss_v[d] += g * wc[d];
+        for (int d = 0; d < dim; ++d) loss_c[d] += g * wv[d];
+        return 1;
+    }
+    // src/proNet.cpp:1517-1566: 16 rounds, every negative drawn here; accepted rounds decay and move both item rows,
+    // the user row moves once by the averaged error (one shared table: rows may alias)
+    void update_sbpr_pair_cpp(double* W, int64_t vertex, int64_t ci, int dim, double xi, double omega, int eta, double alpha,
+                              Draws& d, std::vector<double>& verr, std::vector<double>& cerr, std::vector<double>& cvec) const {
+        verr.assign(dim, 0.0); cerr.assign(dim, 0.0); cvec.assign(dim, 0.0);
+        double* rv = W + vertex * dim;
+        double* ri = W + ci * dim;
+        int update = 0;
+        for (int n = 0; n < 16; n++) {
+            int64_t cj = negative_sample(d);
+            double* rj = W + cj * dim;
+            for (int k = 0; k < dim; k++) {
+                cerr[k] = 0.0;
+                cvec[k] = ri[k] - rj[k];
+            }
+            if (opt_sbpr_sgd(rv, cvec.data(), dim, xi, omega, eta, alpha, verr.data(), cerr.data()) != 0) {
+                for (int k = 0; k < dim; k++) {
+                    ri[k] -= alpha * 0.01 * ri[k];
+                    rj[k] -= alpha * 0.01 * rj[k];
+                    ri[k] += cerr[k];
+                    rj[k] -= cerr[k];
+                }
+                update += 1.0;
+            }
+        }
+        if (update != 0)
+            for (int k = 0; k < dim; k++) {
+                rv[k] -= alpha * 0.01 * rv[k];
+                rv[k] += verr[k] / update;
+            }
+    }
     // src/proNet.cpp:991-1012 (MF): linear prediction, no sigmoid
     void opt_sgd(const double* wv, const double* wc, double label, int dim, double alpha, double reg, double* loss_v,
                  double* loss_c) const {
@@ -743,6 +790,32 @@ uint64_t orc_train_hoprec_cpp(void* h, double* W, int dim, int walk_steps, doubl
         count++;
         sch.tick(count);
     }
+    return d.s.pos;
+}
+
+// C++ Skew-OPT: src/model/SkewOPT.cpp (SPR::Train; one table; negatives "no_degrees"; count from 0)
+uint64_t orc_train_skewopt_cpp(void* h, double* W, int dim, double xi, double omega, int eta, double alpha, uint64_t total,
+                               uint64_t seed, uint64_t stream) {
+    Graph* g = (Graph*)h;
+    Draws d(seed, stream);
+    CppSchedule sch(alpha, total);
+    std::vector<double> a, b, c;
+    unsigned long long count = 0;
+    while (count < total) {
+        int64_t v1 = g->source_sample(d);
+        int64_t v2 = g->target_sample(v1, d);
+        g->update_sbpr_pair_cpp(W, v1, v2, dim, xi, omega, eta, sch.cur, d, a, b, c);
+        count++;
+        sch.tick(count);
+    }
+    return d.s.pos;
+}
+uint64_t orc_update_sbpr_pair_cpp(void* h, double* W, int64_t v, int64_t ci, int dim, double xi, double omega, int eta,
+                                  double alpha, uint64_t seed, uint64_t stream) {
+    Graph* g = (Graph*)h;
+    Draws d(seed, stream);
+    std::vector<double> a, b, c;
+    g->update_sbpr_pair_cpp(W, v, ci, dim, xi, omega, eta, alpha, d, a, b, c);
     return d.s.pos;
 }
 

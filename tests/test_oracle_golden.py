@@ -131,3 +131,19 @@ def test_mf_train_golden(tag):
     pos = g.train_mf_cpp(a, int(K), float(reg), 0.025, 1000000, SEED, 0)
     assert pos == int(GM[f"{tag}_words"])
     assert np.array_equal(a, GM[f"{tag}_v"])
+
+
+# ---- Skew-OPT (tests/golden/golden_skewopt_v1.npz): oracle groundwork, the kernel is the next row -----------------------
+GS = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_skewopt_v1.npz"))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_skewopt_train_golden(tag):
+    off, col, ww, _ = B.edges_to_csr(GS["bip_src"], GS["bip_dst"], GS["bip_w"], 0)
+    g = B.OracleGraph(B.SEM_CPP, off, col, ww, neg_method=B.NEG_NO_DEGREES)
+    xi, omega, eta = GS[f"{tag}_args"]
+    a = GS[f"{tag}_init"].copy()
+    pos = g.train_skewopt_cpp(a, float(xi), float(omega), int(eta), 0.025, 1000000, SEED, 0)
+    assert pos == int(GS[f"{tag}_words"])
+    assert np.array_equal(a, GS[f"{tag}_v"])
+    assert not np.array_equal(a, GS[f"{tag}_init"])

@@ -278,3 +278,31 @@ def test_mf_train_and_update_factorized_pair(tmp_path):
     pos = g.train_mf_cpp(a, 5, 0.01, 0.025, 1000000, SEED, 0)
     assert pos == ref.pos()
     assert np.array_equal(a, ref.get_rows(0))
+
+
+def test_skewopt_train_and_update_sbpr_pair(tmp_path):
+    """Skew-OPT (SURVEY.md §8f rank 3; oracle groundwork, the kernel is next): SPR::Train (src/model/SkewOPT.cpp) =
+    UpdateSBPRPair (src/proNet.cpp:1517-1566: 16 margin-gated rounds, every negative drawn inside) with Opt_SBPRSGD
+    (:1070-1098: (f - xi)/omega, gate at 2, clamp at -2, eta-th power chain), against the compiled reference."""
+    src, dst, w = graphs.bipartite_graph(160, 120, 3000, seed=37)
+    dim = 12
+    ref, (off, col, ww), _ = _mk(str(tmp_path), src, dst, w, 0, B.K_SKEWOPT, dim)
+    g = B.OracleGraph(B.SEM_CPP, off, col, ww, neg_method=B.NEG_NO_DEGREES)
+    W, _ = graphs.init_tables(g.V, dim, seed=9)
+    W = W * 40.0 + 0.01  # scores around xi/omega-scale so that rounds are gated, clamped and accepted (Init adds 0.01, SkewOPT.cpp)
+    for xi, omega, eta in ((10.0, 3.0, 3), (0.5, 0.7, 2)):
+        ref.set_rows(0, W)
+        a = W.copy()
+        ref.seed(SEED, 5)
+        ref.update_sbpr_pair(3, int(col[off[3]]), xi, omega, eta, 0.025)
+        pos = g.update_sbpr_pair_cpp(a, 3, int(col[off[3]]), xi, omega, eta, 0.025, SEED, 5)
+        assert pos == ref.pos() == 32
+        assert np.array_equal(a, ref.get_rows(0))
+    for xi, omega, eta in ((10.0, 3.0, 3), (0.5, 0.7, 2)):
+        ref.set_rows(0, W)
+        a = W.copy()
+        ref.seed(SEED, 0)
+        ref.train_skewopt(1, xi, omega, eta, alpha=0.025, workers=1)
+        pos = g.train_skewopt_cpp(a, xi, omega, eta, 0.025, 1000000, SEED, 0)
+        assert pos == ref.pos()
+        assert np.array_equal(a, ref.get_rows(0))
