@@ -225,6 +225,9 @@ typedef struct {
     /* Chunked training: this call is one piece of a longer LR schedule of sched_total units (same unit as `total`;
      * walk models: walks), sched_offset of which are already done. 0/0: the call is the whole schedule. */
     uint64_t sched_total, sched_offset;
+    /* Skew-OPT (cli/skewopt.cpp:53-54): margin shift xi, scale omega, odd power eta */
+    double xi, omega;
+    int eta;
 } smore_train_params;
 
 /* Fills `p` with the reference CLI defaults (cmd/line/main.go:13-21, cli/line.cpp:56-64). */
@@ -257,6 +260,10 @@ int smore_train_hpe(smore_model_t m, const smore_train_params* p);
  * Opt_SGD :991-1012: linear prediction, labels +1/-1, reg = params.lambda) on table 0 in both roles. C++ only; create the
  * graph with SMORE_NEG_NO_DEGREES as the MF constructor does (MF.cpp:4-7). */
 int smore_train_mf(smore_model_t m, const smore_train_params* p);
+/* SPR::Train (src/model/SkewOPT.cpp): SourceSample -> TargetSample -> UpdateSBPRPair (src/proNet.cpp:1517-1566: 16 rounds,
+ * every negative drawn inside; Opt_SBPRSGD :1070-1098 with params.xi / omega / eta) on table 0 in both roles. C++ only;
+ * graph with SMORE_NEG_NO_DEGREES (SkewOPT.cpp:4-7). */
+int smore_train_skewopt(smore_model_t m, const smore_train_params* p);
 /* Walklets::Train (src/model/Walklets.cpp:6-64): RandomWalk + ScaleSkipGrams + UpdatePairs. C++ only. */
 int smore_train_walklets(smore_model_t m, const smore_train_params* p);
 

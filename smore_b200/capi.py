@@ -35,7 +35,7 @@ EXPORTS = [
     "smore_model_enable_exchange", "smore_dist_nccl_unique_id", "smore_dist_nccl_init", "smore_dist_nccl_shutdown",
     "smore_train_line_group", "smore_exchange_stats", "smore_debug_sm_partition", "smore_model_save_weights", "smore_format_rows",
     "smore_model_load_pretrain", "smore_model_save_checkpoint", "smore_model_load_checkpoint", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
-    "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
+    "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf", "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
 ]
 
 
@@ -49,6 +49,7 @@ class TrainParams(C.Structure):
         ("total", u64), ("negative_samples", C.c_int), ("order", C.c_int), ("lambda_", f64),
         ("walk_times", C.c_int), ("walk_steps", C.c_int), ("window_min", C.c_int), ("window_max", C.c_int),
         ("max_warps", C.c_int), ("max_walks", i64), ("sched_total", u64), ("sched_offset", u64),
+        ("xi", f64), ("omega", f64), ("eta", C.c_int),
     ]
 
 
@@ -114,7 +115,7 @@ def lib():
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
         L.smore_train_params_default.restype = None
         for name in ("smore_train_line", "smore_train_bpr", "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf",
-                     "smore_train_deepwalk", "smore_train_walklets"):
+                     "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets"):
             getattr(L, name).argtypes = [vp, C.POINTER(TrainParams)]
         L.smore_train_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(f64),
                                         C.POINTER(f64)]
@@ -391,6 +392,7 @@ class Model:
     def train_hoprec(self, p): return self._train(lib().smore_train_hoprec, p)
     def train_hpe(self, p): return self._train(lib().smore_train_hpe, p)
     def train_mf(self, p): return self._train(lib().smore_train_mf, p)
+    def train_skewopt(self, p): return self._train(lib().smore_train_skewopt, p)
     def train_deepwalk(self, p): return self._train(lib().smore_train_deepwalk, p)
     def train_walklets(self, p): return self._train(lib().smore_train_walklets, p)
 

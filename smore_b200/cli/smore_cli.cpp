@@ -1,6 +1,6 @@
 // Host-side mirror of the reference CLIs on top of the C ABI (include/smore_b200.h).
 //
-//   smore <model> -train net.txt -save rep.txt [flags]      model in {line, deepwalk, walklets, bpr, warp, hoprec, hpe, mf}
+//   smore <model> -train net.txt -save rep.txt [flags]      model in {line, deepwalk, walklets, bpr, warp, hoprec, hpe, mf, skewopt}
 //   (or invoke through a symlink named after the model: `line -train ...`)
 //
 // Flag names, defaults and the four-call sequence LoadEdgeList -> Init -> Train -> SaveWeights are those of
@@ -14,6 +14,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <vector>
 
 #include "../../include/smore_b200.h"
 
@@ -68,7 +69,7 @@ int die(const char* what) {
 
 void usage() {
     printf("[smore_b200]\n\tB200-native SMORe trainers (LINE, DeepWalk, Walklets, BPR, WARP, HOP-Rec)\n\n"
-           "Usage:\n\tsmore <line|deepwalk|walklets|bpr|warp|hoprec|hpe|mf> -train net.txt -save rep.txt [options]\n\n"
+           "Usage:\n\tsmore <line|deepwalk|walklets|bpr|warp|hoprec|hpe|mf|skewopt> -train net.txt -save rep.txt [options]\n\n"
            "Options Description:\n"
            "\t-train <string>\n\t\tTrain the Network data\n"
            "\t-save <string>\n\t\tSave the representation data\n"
@@ -81,6 +82,7 @@ void usage() {
            "\t-walk_times <int> -walk_steps <int> -window_size <int> -window_min <int> -window_max <int>\n"
            "\t-lambda <float>\n\t\tGo BPR regularisation; default is 0.001\n"
            "\t-reg <float>\n\t\tHPE / MF regularisation; default is 0.01\n"
+           "\t-xi <float> -omega <float> -eta <int>\n\t\tSkew-OPT margin shift / scale / power; defaults 10, 3, 3\n"
            "\t-alpha <float>\n\t\tInit learning rate; default is 0.025\n"
            "\t-threads <int>\n\t\tAccepted for compatibility; workers are GPU warps\n"
            "\t-load_v <string> -load_c <string>\n\t\tPretrained vertex / context embeddings (text, matched by vertex name)\n"
@@ -95,7 +97,7 @@ int main(int argc, char** argv) {
     int first = 1;
     const char* base = strrchr(argv[0], '/');
     base = base ? base + 1 : argv[0];
-    for (const char* m : {"line", "deepwalk", "walklets", "bpr", "warp", "hoprec", "hpe", "mf"})
+    for (const char* m : {"line", "deepwalk", "walklets", "bpr", "warp", "hoprec", "hpe", "mf", "skewopt"})
         if (!strcmp(base, m)) model = m;
     if (model.empty()) {
         if (argc < 2 || argv[1][0] == '-') {
@@ -111,7 +113,7 @@ int main(int argc, char** argv) {
     }
     Args a = parse(argc, argv, first);
     const bool has_go_cli = model == "line" || model == "deepwalk" || model == "bpr";
-    if (!has_go_cli && model != "walklets" && model != "warp" && model != "hoprec" && model != "hpe" && model != "mf") {
+    if (!has_go_cli && model != "walklets" && model != "warp" && model != "hoprec" && model != "hpe" && model != "mf" && model != "skewopt") {
         fprintf(stderr, "smore: unknown model '%s'\n", model.c_str());
         return 1;
     }
@@ -127,10 +129,10 @@ int main(int argc, char** argv) {
         return 1;
     }
     // (MF: one table, "no_degrees" negatives and a directed load, like the ranking models: MF.cpp:4-7, cli/mf.cpp:63)
-    const bool ranking = model == "bpr" || model == "warp" || model == "hoprec" || model == "mf";
+    const bool ranking = model == "bpr" || model == "warp" || model == "hoprec" || model == "mf" || model == "skewopt";
     // defaults: cmd/line/main.go:15-21, cmd/deepwalk/main.go:13-22, cmd/bpr/main.go:13-20, cli/*.cpp
     const int dim = (int)a.num("dimensions", 64);
-    const bool undirected = model == "hoprec" ? true : a.flag("undirected", !(model == "bpr" || model == "warp" || model == "mf"));
+    const bool undirected = model == "hoprec" ? true : a.flag("undirected", !(model == "bpr" || model == "warp" || model == "mf" || model == "skewopt"));
     const int sample_times = (int)a.num("sample_times", 10);
     const int dtype = a.str("dtype", "f32") == "f64" ? SMORE_F64 : SMORE_F32;
 
@@ -159,6 +161,9 @@ int main(int argc, char** argv) {
     p.negative_samples = (int)a.num("negative_samples", 5);
     p.order = a.num("order", 2) == 1 ? 1 : 2;
     p.lambda = (model == "hpe" || model == "mf") ? a.real("reg", 0.01) : a.real("lambda", 0.001);  // cli/hpe.cpp:57
+    p.xi = a.real("xi", 10.0);  // cli/skewopt.cpp:53-54
+    p.omega = a.real("omega", 3.0);
+    p.eta = (int)a.num("eta", 3);
     p.walk_times = (int)a.num("walk_times", 10);
     // cli/deepwalk.cpp:56 defaults walk_steps to 5 (sic), cli/walklets.cpp:54 and cmd/deepwalk/main.go:20 to 40
     p.walk_steps = (int)a.num("walk_steps", model == "hoprec" || model == "hpe" ? 5 : (model == "deepwalk" && sem == SMORE_SEM_CPP ? 5 : 40));
@@ -181,6 +186,12 @@ int main(int argc, char** argv) {
         if (smore_model_init(m, 1, ctx_random ? 1 : 0, p.seed)) return die("Init");
     }
 
+    if (model == "skewopt") {  // SPR::Init adds 0.01 to every element (src/model/SkewOPT.cpp:49)
+        std::vector<double> rows((size_t)V * (size_t)dim);
+        if (smore_model_get_rows(m, 0, 0, V, rows.data())) return die("Init");
+        for (double& x : rows) x += 0.01;
+        if (smore_model_set_rows(m, 0, 0, V, rows.data())) return die("Init");
+    }
     // cli/deepwalk.cpp:61-62, DeepWalk.cpp:83-92: pretrained vertex / context embeddings replace the random init
     for (int t = 0; t < n_tables; ++t) {
         const char* key = t == 0 ? "load_v" : "load_c";
@@ -206,6 +217,7 @@ int main(int argc, char** argv) {
         if (model == "warp") return smore_train_warp(m, &q);
         if (model == "hpe") return smore_train_hpe(m, &q);
         if (model == "mf") return smore_train_mf(m, &q);
+        if (model == "skewopt") return smore_train_skewopt(m, &q);
         return smore_train_hoprec(m, &q);
     };
     uint64_t samples = 0, pairs = 0;

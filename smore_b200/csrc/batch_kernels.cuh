@@ -538,4 +538,58 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_cp
     if (lane == 0) a.state[w] = st;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Skew-OPT: SPR::Train (src/model/SkewOPT.cpp) + UpdateSBPRPair (src/proNet.cpp:1517-1566): 16 rounds, every negative
+// drawn inside the update. 36 words per sample (K = 16); ids row = user, item, j0..j15; one shared table. First version:
+// every round goes through memory in the reference's order (sbpr_round), the user row moves once at the end by the
+// averaged error.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSbprRounds = 16;
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_skewopt(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    const Batch b = batch_init<T>(0, kSbprRounds, wib);
+    WarpState st = a.state[w];
+    const uint64_t stream = a.stream_base + (uint64_t)w;
+    const int dim = a.dim;
+    T* W = a.Wv;
+    for (uint64_t done = 0; done < a.jobs; done += 32) {
+        const int nb = (int)min((uint64_t)32, a.jobs - done);
+        batch_sample<false>(a.g, b, a.seed, stream, st, nb, lane);
+        for (int s = 0; s < nb; ++s) {
+            if (s + kLinePrefetch < nb) prefetch_local<T>(W, W, b.ids + (s + kLinePrefetch) * b.idw, b.idw, dim, lane);
+            const int* sid = b.ids + s * b.idw;
+            const int v1 = sid[0], v2 = sid[1];
+            if (v2 < 0) continue;
+            const T alpha = (T)st.alpha;
+            T* pv = W + (size_t)v1 * dim;
+            T* pi = W + (size_t)v2 * dim;
+            Row<C> verr;
+            verr.zero();
+            int update = 0;
+            for (int n = 0; n < kSbprRounds; ++n)
+                if (sbpr_round<C>(pv, pi, W + (size_t)sid[2 + n] * dim, dim, lane, lut, alpha, a.xi, a.omega, a.eta, verr)) ++update;
+            if (update != 0) {
+                const T c = A::mul(alpha, (T)0.01);
+                const T up = (T)update;
+                for_owned<C>(lane, dim, [&](int e, int idx) {
+                    stv(pv + idx, A::msub(ldv(pv + idx), c, ldv(pv + idx)));
+                    stv(pv + idx, A::add(ldv(pv + idx), A::div(verr.x[e], up)));
+                });
+            }
+            st.count++;
+            st.pairs += kSbprRounds;
+            st.tries += (uint64_t)update;  // stats: accepted rounds
+            sched_tick(st, a.sched);
+        }
+    }
+    if (lane == 0) a.state[w] = st;
+}
+
 }  // namespace smore

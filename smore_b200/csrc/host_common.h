@@ -252,6 +252,9 @@ TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps,
     a.K = p->negative_samples;
     a.order = p->order;
     a.lambda = (T)p->lambda;
+    a.xi = (T)p->xi;
+    a.omega = (T)p->omega;
+    a.eta = p->eta;
     return a;
 }
 

@@ -69,6 +69,8 @@ struct TrainArgs {
     int64_t n_walks;      // walks in this launch; warp w takes walks w, w+W, ...
     int steps, w0, w1, walklets;
     ExchDev x;  // bulk-exchange mode only
+    T xi, omega;  // Skew-OPT
+    int eta;
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@
 
 namespace smore {
 
-enum RankKind { RANK_BPR = 0, RANK_WARP = 1, RANK_HOPREC = 2 };
+enum RankKind { RANK_BPR = 0, RANK_WARP = 1, RANK_HOPREC = 2, RANK_SKEWOPT = 3 };
 
 template <typename T>
 __device__ __forceinline__ T ldv(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
@@ -69,6 +69,42 @@ __device__ __forceinline__ bool ordered_round(typename C::T* pv, typename C::T* 
     if (gated && f > margin) return false;
     const T g = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f)), alpha);
     const T c = A::mul(alpha, (T)0.0025);
+    for_owned<C>(lane, dim, [&](int e, int idx) {
+        verr.x[e] = A::madd(verr.x[e], g, cvec.x[e]);
+        const T cerr = A::mul(g, v.x[e]);
+        stv(pi + idx, A::msub(ldv(pi + idx), c, ldv(pi + idx)));
+        stv(pj + idx, A::msub(ldv(pj + idx), c, ldv(pj + idx)));
+        stv(pi + idx, A::add(ldv(pi + idx), cerr));
+        stv(pj + idx, A::sub(ldv(pj + idx), cerr));
+    });
+    return true;
+}
+
+// One round of proNet::UpdateSBPRPair (src/proNet.cpp:1531-1556) with Opt_SBPRSGD (:1070-1098), through memory in the
+// reference's order (the rows of one shared table may coincide): g = (f - xi) / omega is gated at g > 2 and clamped at
+// -2, the gradient is sigmoid(-g^eta) * g^(eta-1) / omega * alpha. Returns false when the round was gated away.
+template <class C>
+__device__ __forceinline__ bool sbpr_round(typename C::T* pv, typename C::T* pi, typename C::T* pj, int dim, int lane,
+                                           const typename C::T* lut, typename C::T alpha, typename C::T xi,
+                                           typename C::T omega, int eta, Row<C>& verr) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    Row<C> v, ri, rj, cvec;
+    v.load(pv, lane, dim);
+    ri.load(pi, lane, dim);
+    rj.load(pj, lane, dim);
+#pragma unroll
+    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = A::sub(ri.x[e], rj.x[e]);
+    const T f = dot(v, cvec);
+    T g = A::div(A::sub(f, xi), omega);
+    if (g > (T)2) return false;
+    if (g < (T)-2) g = (T)-2;
+    T g_in = (T)1;
+    for (int i = 0; i < eta; ++i) g_in = A::mul(g_in, g);
+    const T chain = A::div(g_in, g);
+    g = A::div(A::mul(fast_sigmoid<T>(lut, A::mul((T)-1, g_in)), chain), omega);
+    g = A::mul(g, alpha);
+    const T c = A::mul(alpha, (T)0.01);  // alpha*0.01*w evaluates left to right
     for_owned<C>(lane, dim, [&](int e, int idx) {
         verr.x[e] = A::madd(verr.x[e], g, cvec.x[e]);
         const T cerr = A::mul(g, v.x[e]);

@@ -234,6 +234,9 @@ void smore_train_params_default(smore_train_params* p) {
     p->window_min = 1;
     p->window_max = 5;
     p->max_walks = -1;
+    p->xi = 10.0;  // cli/skewopt.cpp:53-54
+    p->omega = 3.0;
+    p->eta = 3;
 }
 
 int smore_graph_create(int64_t V, int64_t E, const int64_t* row_off, const int32_t* col, const double* weight,
@@ -984,6 +987,14 @@ int smore_train_bpr(smore_model_t m, const smore_train_params* p) {
     if (int rc = check_train(m, p, p && p->semantics == SMORE_SEM_GO ? 2 : 1)) return rc;
     return m->dtype == SMORE_F64 ? train_ranking_t<double>(m, p, RANK_BPR) : train_ranking_t<float>(m, p, RANK_BPR);
 }
+int smore_train_skewopt(smore_model_t m, const smore_train_params* p) {
+    if (int rc = check_train(m, p, 1)) return rc;
+    if (p->semantics != SMORE_SEM_CPP) return fail(SMORE_E_UNSUPPORTED, "Skew-OPT (SPR) exists only in the C++ tree");
+    if (p->eta < 1 || p->eta > 15) return fail(SMORE_E_INVALID, "eta must be in [1,15]");
+    if (!(p->omega != 0)) return fail(SMORE_E_INVALID, "omega must be non-zero");
+    return m->dtype == SMORE_F64 ? train_ranking_t<double>(m, p, RANK_SKEWOPT) : train_ranking_t<float>(m, p, RANK_SKEWOPT);
+}
+
 int smore_train_warp(smore_model_t m, const smore_train_params* p) {
     if (int rc = check_train(m, p, 1)) return rc;
     if (p->semantics != SMORE_SEM_CPP) return fail(SMORE_E_UNSUPPORTED, "WARP exists only in the C++ tree");

@@ -6,8 +6,11 @@ int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind) {
     return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
         using C = decltype(cfg);
         const bool cpp = p->semantics == SMORE_SEM_CPP;
-        void (*kern)(TrainArgs<T>) = kind == RANK_WARP ? k_warp<C> : kind == RANK_HOPREC ? k_hoprec<C> : cpp ? k_bpr_cpp<C> : k_bpr_go<C>;
-        const size_t smem = kind != RANK_BPR ? smem_line<T>() : cpp ? batch_smem_bytes<T>(0, 5) : batch_smem_bytes<T>(1, 1);
+        void (*kern)(TrainArgs<T>) = kind == RANK_WARP ? k_warp<C> : kind == RANK_HOPREC ? k_hoprec<C> : kind == RANK_SKEWOPT ? k_skewopt<C>
+                                     : cpp ? k_bpr_cpp<C> : k_bpr_go<C>;
+        const size_t smem = kind == RANK_SKEWOPT ? batch_smem_bytes<T>(0, kSbprRounds)
+                            : kind != RANK_BPR ? smem_line<T>() : cpp ? batch_smem_bytes<T>(0, 5) : batch_smem_bytes<T>(1, 1);
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
         else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
