@@ -362,8 +362,8 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             // replica rows never alias shard rows in memory; nor do staging rows (v1 < 0 then never equals a context id)
             const bool same = SHARD == 2 ? false : a.same_table != 0;
             if constexpr (KIND == 1) update_factorized_pair<C, TV, TC>(tv, tc, a.dim, same, v1, my, nrows, alpha, a.lambda, lane);
-            else if (!GO) update_pair_cpp<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
-            else update_pair_go<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush);
+            else if (!GO) update_pair_cpp<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush, SHARD == 1 && a.vred != 0);
+            else update_pair_go<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush, SHARD == 1 && a.vred != 0);
             st.count++;
             st.pairs++;
             sched_tick(st, a.sched);

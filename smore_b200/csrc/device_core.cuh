@@ -43,7 +43,10 @@ struct GraphDev {
     uint32_t n_edge_local;
     uint32_t n_neg;
     int shard_shift, shard_rank;
-    __device__ __forceinline__ uint32_t global_id(uint32_t local) const { return (local << shard_shift) + (uint32_t)shard_rank; }
+    // negative_at index -> vertex id: (l << neg_shift) + neg_rank. Shard-local negatives: neg_shift/neg_rank = the shard's;
+    // a table over all vertices (unsharded, or the sharded "global negatives" variant): 0 / 0.
+    int neg_shift, neg_rank;
+    __device__ __forceinline__ uint32_t global_id(uint32_t local) const { return (local << neg_shift) + (uint32_t)neg_rank; }
 };
 
 // A (possibly row-sharded) embedding table: base[r] = rank r's shard (the local cudaMalloc, or a CUDA-IPC peer mapping

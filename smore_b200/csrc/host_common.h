@@ -58,6 +58,10 @@ struct smore_graph_s {
     int rank = 0, world = 1, shift = 0;
     int64_t n_local = 0;            // owned vertices
     double src_mass_frac = 1.0;     // share of the global source-sampling mass owned by this rank
+    bool neg_global = false;        // sharded: negatives drawn over ALL vertices (context rows then cross NVLink too)
+    int64_t n_neg = 0;              // entries of the negative table on the device
+    int n_models = 0;               // models ever created on this graph (their row counts freeze the sharding; never decremented:
+                                    // a model may outlive its graph handle on the caller's side)
     // device
     int64_t* d_row_off = nullptr;
     int32_t* d_col = nullptr;
@@ -75,7 +79,8 @@ struct smore_graph_s {
         g.row_off = d_row_off; g.col = d_col;
         g.vertex_at = d_vat; g.negative_at = d_nat; g.ctx_at = d_cat;
         g.prefix = d_prefix; g.field = d_field; g.sem = sem;
-        g.n_neg = (uint32_t)n_local;
+        g.n_neg = (uint32_t)(n_neg ? n_neg : n_local);
+        g.neg_shift = neg_global ? 0 : shift; g.neg_rank = neg_global ? 0 : rank;
         g.edge_at = d_eat; g.edge_src = d_esrc; g.edge_dst = d_edst; g.n_edge_local = (uint32_t)n_edge_local;
         g.shard_shift = shift; g.shard_rank = rank;
         return g;
@@ -255,6 +260,8 @@ TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps,
     a.xi = (T)p->xi;
     a.omega = (T)p->omega;
     a.eta = p->eta;
+    a.vred = 1;
+    if (const char* e = getenv("SMORE_SHARD_VRED")) a.vred = atoi(e) != 0;  // A/B switch (tools/ab_sharded_quality.py)
     return a;
 }
 

@@ -71,6 +71,7 @@ struct TrainArgs {
     ExchDev x;  // bulk-exchange mode only
     T xi, omega;  // Skew-OPT
     int eta;
+    int vred;  // row-sharded peer-access mode: vertex rows take their delta with red.global.add instead of a full-row store
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -83,7 +84,7 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
                                                 const TC& tc, int dim, bool same_table,
                                                 const typename C::T* lut, int v1, int my_id, int nrows,
                                                 typename C::T alpha, int lane, const Row<C>* vpre = nullptr,
-                                                typename C::T* vpush = nullptr) {
+                                                typename C::T* vpush = nullptr, bool vred = false) {
     using T = typename C::T;
     using A = Ar<T>;
     bool active = lane < nrows;
@@ -122,9 +123,15 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
                 }
             }
         }
+        // vred (row-sharded table, rows shared with other GPUs): the row takes its DELTA with red.global.add, performed by
+        // the owner's L2 -- a full-row store of the (staged, possibly stale) copy would overwrite what the other ranks, or an
+        // earlier sample of this very warp, added to the row in the meantime
+        if (vred) row_red_add<C>(pv, back, lane, dim);
+        else {
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
-        v.store(pv, lane, dim);
+            for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
+            v.store(pv, lane, dim);
+        }
         if (vpush) row_red_add<C>(vpush, back, lane, dim);  // replica mode: the delta also goes to the owner's row
     } else {
         Row<C> back;
@@ -145,11 +152,14 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
             }
             c.store(pc, lane, dim);
         }
-        Row<C> v;
-        v.load(pv, lane, dim);
+        if (vred) row_red_add<C>(pv, back, lane, dim);
+        else {
+            Row<C> v;
+            v.load(pv, lane, dim);
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
-        v.store(pv, lane, dim);
+            for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
+            v.store(pv, lane, dim);
+        }
         if (vpush) row_red_add<C>(vpush, back, lane, dim);
     }
 }
@@ -164,7 +174,7 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
                                                 const TC& tc, int dim, bool same_table,
                                                bool skip_source, const typename C::T* lut, int v1, int my_id,
                                                int nrows, typename C::T alpha, int lane, const Row<C>* vpre = nullptr,
-                                               typename C::T* vpush = nullptr) {
+                                               typename C::T* vpush = nullptr, bool vred = false) {
     using T = typename C::T;
     using A = Ar<T>;
     int ctx = __shfl_sync(kFull, my_id, 0);
@@ -224,7 +234,8 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
             v.x[e] = A::add(v.x[e], vgrad.x[e]);
             pos.x[e] = A::add(pos.x[e], cgrad.x[e]);
         }
-        v.store(pv, lane, dim);
+        if (vred) row_red_add<C>(pv, vgrad, lane, dim);  // see update_pair_cpp
+        else v.store(pv, lane, dim);
         pos.store(pp, lane, dim);
         if (vpush) row_red_add<C>(vpush, vgrad, lane, dim);
     } else {
@@ -257,11 +268,14 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
         }
         // per element: vertex row first, then context row (optimizer.go:54-57), through memory so that
         // a self pair on a shared table accumulates both.
-        Row<C> v;
-        v.load(pv, lane, dim);
+        if (vred) row_red_add<C>(pv, vgrad, lane, dim);
+        else {
+            Row<C> v;
+            v.load(pv, lane, dim);
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], vgrad.x[e]);
-        v.store(pv, lane, dim);
+            for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], vgrad.x[e]);
+            v.store(pv, lane, dim);
+        }
         if (vpush) row_red_add<C>(vpush, vgrad, lane, dim);
         Row<C> pos;
         pos.load(pp, lane, dim);

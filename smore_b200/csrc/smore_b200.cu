@@ -244,6 +244,10 @@ int smore_graph_create(int64_t V, int64_t E, const int64_t* row_off, const int32
     if (!row_off || (!col && E > 0) || (!weight && E > 0) || !out) return fail(SMORE_E_INVALID, "null argument");
     if (semantics != SMORE_SEM_CPP && semantics != SMORE_SEM_GO) return fail(SMORE_E_INVALID, "bad semantics");
     if (negative_method < 0 || negative_method > 2) return fail(SMORE_E_INVALID, "bad negative_method");
+    // validate the shape BEFORE touching the caller's arrays: ids are int32 and index draws are 32-bit on the device
+    if (V <= 0 || V >= (1ll << 31)) return fail(SMORE_E_INVALID, "V=%lld out of range (0, 2^31)", (long long)V);
+    if (E < 0 || E >= (1ll << 32)) return fail(SMORE_E_INVALID, "E=%lld out of range [0, 2^32)", (long long)E);
+    if (row_off[0] != 0 || row_off[V] != E) return fail(SMORE_E_INVALID, "row_off[0]/row_off[V] inconsistent with E");
     if (int rc = ensure_device()) return rc;
     smore_graph_s* g = new smore_graph_s();
     g->sem = semantics;
@@ -457,6 +461,7 @@ int smore_model_create(smore_graph_t g, int dim, int n_tables, int dtype, smore_
         cudaMemset(m->tab[t], 0, bytes);
         m->peer[t][g->rank] = m->tab[t];
     }
+    g->n_models++;
     *out = m;
     return SMORE_OK;
 }
@@ -466,6 +471,7 @@ int smore_graph_set_shard(smore_graph_t g, int rank, int world) {
     if (!g) return fail(SMORE_E_INVALID, "null graph");
     if (world < 1 || world > kMaxWorld || (world & (world - 1))) return fail(SMORE_E_INVALID, "world must be 1, 2, 4 or 8");
     if (rank < 0 || rank >= world) return fail(SMORE_E_INVALID, "rank out of range");
+    if (g->n_models > 0) return fail(SMORE_E_INVALID, "%d model(s) were already created on this graph: their row counts are fixed at creation, shard the graph first", g->n_models);
     if (int rc = ensure_device()) return rc;
     int shift = 0;
     while ((1 << shift) < world) ++shift;
@@ -510,6 +516,7 @@ int smore_graph_set_shard(smore_graph_t g, int rank, int world) {
     }
     const int64_t ne = (int64_t)pe.size();
     if (ne == 0) return fail(SMORE_E_INVALID, "rank %d owns no edge target", rank);
+    if (ne >= (1ll << 32)) return fail(SMORE_E_UNSUPPORTED, "rank %d owns %lld CSR entries; the edge table is indexed with 32-bit draws", rank, (long long)ne);
     std::vector<double> neg((size_t)nl);
     for (int64_t l = 0; l < nl; ++l) {
         const int64_t v = l * world + rank;
@@ -519,7 +526,13 @@ int smore_graph_set_shard(smore_graph_t g, int rank, int world) {
         else neg[(size_t)l] = in == 0 ? 0 : 1;
     }
     AliasHost edge_at = alias_method_go(pe.data(), ne, 1.0);  // plain Vose on the edge probabilities
-    g->negative_at = g->sem == SMORE_SEM_CPP ? alias_method_cpp(neg.data(), nl) : alias_method_go(neg.data(), nl, 0.75);
+    // A/B switch (tools/ab_sharded_quality.py): keep the table over ALL vertices -- negative context rows then live on any
+    // rank and cross NVLink like the vertex rows do ("global negatives with P2P remote rows")
+    const char* gn = getenv("SMORE_SHARD_GLOBAL_NEG");
+    g->neg_global = gn && atoi(gn) != 0;
+    g->n_neg = g->neg_global ? V : nl;
+    if (!g->neg_global)
+        g->negative_at = g->sem == SMORE_SEM_CPP ? alias_method_cpp(neg.data(), nl) : alias_method_go(neg.data(), nl, 0.75);
     std::vector<uint2> packed;
     auto upload = [&](const AliasHost& t, uint2** d) -> int {
         packed.resize(t.prob.size());
@@ -531,7 +544,8 @@ int smore_graph_set_shard(smore_graph_t g, int rank, int world) {
         return dev_alloc_copy(d, packed.data(), packed.size());
     };
     if (int rc = upload(edge_at, &g->d_eat)) return rc;
-    if (int rc = upload(g->negative_at, &g->d_nat)) return rc;
+    if (!g->neg_global)
+        if (int rc = upload(g->negative_at, &g->d_nat)) return rc;
     cudaFree(g->d_esrc);
     cudaFree(g->d_edst);
     if (int rc = dev_alloc_copy(&g->d_esrc, esrc.data(), esrc.size())) return rc;

@@ -1,0 +1,169 @@
+#!/usr/bin/env python
+"""A/B matrix for the row-sharded LINE modes on ONE device (shards emulated in-process, as tests/test_gpu_sharded.py does).
+
+Question: which ingredient of the sharded peer-access mode costs link-prediction quality --
+  * the write-back of the vertex row (full-row store of a staged copy vs red.global.add of the delta), SMORE_SHARD_VRED
+  * shard-local negatives vs negatives over all vertices, SMORE_SHARD_GLOBAL_NEG
+  * the world size (2 / 4 / 8)
+Every cell is averaged over --seeds Hogwild runs; AUC and recall@10 are evaluated on ALL held-out edges (the unit tests'
+1500-source subsample has a standard error of ~5 % relative on recall@10, as large as the effect under study).
+
+Output: one JSON line per cell on stdout (and a table on stderr).
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from smore_b200 import capi, synth  # noqa: E402
+from smore_b200 import dist as sdist  # noqa: E402
+
+
+def sbm_graph(n_comm, comm_size, deg, p_in, seed):
+    rng = np.random.default_rng(seed)
+    V = n_comm * comm_size
+    n_edges = V * deg // 2
+    src = rng.integers(0, V, n_edges)
+    inside = rng.random(n_edges) < p_in
+    dst_in = (src // comm_size) * comm_size + rng.integers(0, comm_size, n_edges)
+    dst_out = rng.integers(0, V, n_edges)
+    dst = np.where(inside, dst_in, dst_out)
+    keep = src != dst
+    w = rng.integers(1, 4, n_edges).astype(np.float64)
+    return src[keep], dst[keep], w[keep]
+
+
+def make_problem(n_comm=150, comm_size=80, deg=24):
+    src, dst, w = sbm_graph(n_comm=n_comm, comm_size=comm_size, deg=deg, p_in=0.85, seed=5)
+    (ts, td, tw), (hs, hd, _) = synth.split_edges(src, dst, w, 0.10, seed=6)
+    off, col, ww, labels = synth.csr_from_edges(ts, td, tw, True)
+    lab2id = {int(l): i for i, l in enumerate(labels)}
+    ok = np.array([(int(a) in lab2id) and (int(b) in lab2id) for a, b in zip(hs, hd)])
+    test_s = np.array([lab2id[int(a)] for a in hs[ok]])
+    test_d = np.array([lab2id[int(b)] for b in hd[ok]])
+    return off, col, ww, test_s, test_d
+
+
+def auc(pos, neg):
+    s = np.concatenate([pos, neg])
+    ranks = s.argsort().argsort().astype(np.float64) + 1
+    return (ranks[: len(pos)].sum() - len(pos) * (len(pos) + 1) / 2) / (len(pos) * len(neg))
+
+
+def evaluate_full(Wv, Wc, off, col, test_s, test_d, seed=2):
+    """AUC over all held-out edges vs as many random pairs; recall@10 over EVERY held-out source."""
+    rng = np.random.default_rng(seed)
+    Wv = np.asarray(Wv, dtype=np.float32)
+    Wc = np.asarray(Wc, dtype=np.float32)
+    pos = np.einsum("ij,ij->i", Wv[test_s], Wc[test_d])
+    neg = np.einsum("ij,ij->i", Wv[test_s], Wc[rng.integers(0, len(Wc), len(test_s))])
+    a = auc(pos, neg)
+    srcs = np.unique(test_s)
+    hits = tot = 0
+    order = np.argsort(test_s, kind="stable")
+    ts, td = test_s[order], test_d[order]
+    starts = np.searchsorted(ts, srcs)
+    ends = np.searchsorted(ts, srcs, side="right")
+    for lo in range(0, len(srcs), 2048):
+        blk = srcs[lo:lo + 2048]
+        sc = Wv[blk] @ Wc.T
+        for i, s in enumerate(blk):
+            sc[i, col[off[s]:off[s + 1]]] = -np.inf
+            sc[i, s] = -np.inf
+        top = np.argpartition(-sc, 10, axis=1)[:, :10]
+        for i in range(len(blk)):
+            held = td[starts[lo + i]:ends[lo + i]]
+            hits += len(np.intersect1d(held, top[i]))
+            tot += min(len(np.unique(held)), 10)
+    return float(a), hits / tot
+
+
+def params(total, seed, max_warps):
+    p = capi.default_params()
+    p.semantics, p.mode, p.seed, p.alpha, p.total, p.negative_samples = capi.SEM_CPP, capi.MODE_HOGWILD, seed, 0.025, total, 5
+    p.max_warps = max_warps
+    return p
+
+
+def run_unsharded(prob, dim, total, seed, max_warps):
+    off, col, ww, test_s, test_d = prob
+    V = len(off) - 1
+    init = ((np.random.default_rng(1).random((V, dim)) - 0.5) / dim)
+    g = capi.Graph.from_csr(off, col, ww)
+    m = capi.Model(g, dim, 2, capi.F32)
+    m.set_rows(0, init), m.set_rows(1, np.zeros((V, dim)))
+    m.train_line(params(total, seed, max_warps))
+    return evaluate_full(m.get_rows(0), m.get_rows(1), off, col, test_s, test_d)
+
+
+def run_peer(prob, dim, total, seed, world, rounds, max_warps):
+    """Peer-access mode, ranks launched one after the other in `rounds` rounds (one LR schedule over all of them)."""
+    off, col, ww, test_s, test_d = prob
+    V = len(off) - 1
+    init = ((np.random.default_rng(1).random((V, dim)) - 0.5) / dim)
+    ms = []
+    for r in range(world):
+        gr = capi.Graph.from_csr(off, col, ww)
+        gr.set_shard(r, world)
+        mr = capi.Model(gr, dim, 2, capi.F32)
+        rows = sdist.owned_rows(V, r, world)
+        mr.set_rows(0, init[rows]), mr.set_rows(1, np.zeros((len(rows), dim)))
+        ms.append(mr)
+    for t in range(2):
+        ptrs = [mr.device_ptr(t) for mr in ms]
+        for mr in ms:
+            mr.set_peer_ptrs(t, ptrs)
+    for k in range(rounds):
+        for r, mr in enumerate(ms):
+            p = params(total // rounds, seed * 1000 + k, max_warps)
+            p.stream_base = r * (1 << 20)
+            p.sched_total, p.sched_offset = total, k * (total // rounds)
+            mr.train_line(p)
+    Wv, Wc = np.zeros((V, dim)), np.zeros((V, dim))
+    for r, mr in enumerate(ms):
+        rows = sdist.owned_rows(V, r, world)
+        Wv[rows], Wc[rows] = mr.get_rows(0), mr.get_rows(1)
+    return evaluate_full(Wv, Wc, off, col, test_s, test_d)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=3)
+    ap.add_argument("--dim", type=int, default=32)
+    ap.add_argument("--total", type=int, default=12_000_000)
+    ap.add_argument("--rounds", type=int, default=20)
+    ap.add_argument("--max-warps", type=int, default=512)
+    ap.add_argument("--worlds", default="2,4,8")
+    args = ap.parse_args()
+    prob = make_problem()
+    cells = []
+
+    def cell(name, fn):
+        res = np.array([fn(s) for s in range(1, args.seeds + 1)])
+        rec = {"cell": name, "auc_mean": res[:, 0].mean(), "auc_sd": res[:, 0].std(), "rec_mean": res[:, 1].mean(),
+               "rec_sd": res[:, 1].std(), "runs": res.tolist()}
+        cells.append(rec)
+        print(json.dumps(rec), flush=True)
+        print(f"{name:60s} AUC {rec['auc_mean']:.4f} +- {rec['auc_sd']:.4f}   recall@10 {rec['rec_mean']:.4f} +- {rec['rec_sd']:.4f}",
+              file=sys.stderr, flush=True)
+
+    for mw in sorted({args.max_warps, 0}):
+        cell(f"unsharded max_warps={mw}", lambda s: run_unsharded(prob, args.dim, args.total, 10 + s, mw))
+    for world in [int(x) for x in args.worlds.split(",")]:
+        for vred in (0, 1):
+            for gneg in (0, 1):
+                os.environ["SMORE_SHARD_VRED"] = str(vred)
+                os.environ["SMORE_SHARD_GLOBAL_NEG"] = str(gneg)
+                cell(f"peer world={world} vred={vred} global_neg={gneg} rounds={args.rounds}",
+                     lambda s: run_peer(prob, args.dim, args.total, 100 + s, world, args.rounds, args.max_warps))
+    os.environ.pop("SMORE_SHARD_VRED", None)
+    os.environ.pop("SMORE_SHARD_GLOBAL_NEG", None)
+
+
+if __name__ == "__main__":
+    main()
