@@ -189,6 +189,40 @@ int smore_debug_sm_partition(int reserve, int* total_sms, int* partition_sms, in
  * size of the hot set. */
 int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows_requested, int64_t* hot_vertices);
 
+/* ---- rotating shards: the multi-GPU mode for tables too large for fine-grained peer access ----------
+ * New with this backend (the reference trains one shared table in one address space, src/model/LINE.cpp:162-191).
+ * Both tables are row-sharded as above; the CONTEXT shard of a rank never moves. The VERTEX shard is cut into two halves
+ * (local rows [0, sub_cap) and [sub_cap, n_local)), i.e. the table into 2*world sub-parts, which travel around the ring
+ * of ranks: in episode e rank g trains the block  sources of sub-part q = (2g - e) mod 2*world  x  its own contexts
+ * (negatives: its own contexts) entirely out of local HBM with the single-GPU kernel, while the sub-part it trained in
+ * episode e-1 travels to rank g+1 as one contiguous copy-engine transfer over NVLink, hidden behind the update kernel.
+ * After 2*world episodes (a cycle) every sub-part has met every context shard once and is home again. A vertex row
+ * exists exactly once at any time (nothing stale, nothing lost); block (q, g) runs total_cycle * mass(q, g) samples per
+ * cycle, so the union of the blocks is exactly the edge distribution of the unsharded samplers.
+ *
+ * Per rank:  smore_graph_create -> smore_graph_set_shard_rotating -> smore_model_create (2 tables) -> init / set_rows ->
+ * smore_model_enable_rotation -> exchange slot handles with the NEXT rank (rot_ipc_handles / rot_open_next; same process:
+ * rot_slot_ptrs / rot_set_next_ptrs) -> for e = 0, 1, ...:
+ *        smore_rot_send_begin(m, e);  smore_train_line_episode(m, &p, e);  smore_rot_send_end(m, e);  <host barrier>
+ * The barrier is the host's (torch.distributed / MPI / a Go channel): the library makes no cross-process call here.
+ * get_rows / set_rows / init / checkpoints address LOCAL rows as for any sharded model and are valid whenever the model is
+ * at home (episode % (2*world) == 0, after the barrier); smore_train_line_episode may be skipped in an episode (e.g. to
+ * finish a partial cycle). LINE order 2 only (order 1 uses one table in both roles). */
+int smore_graph_set_shard_rotating(smore_graph_t g, int rank, int world);
+/* n_sub = 2*world; block_mass[q] / block_edges[q] (n_sub entries each, may be NULL): this rank's blocks by ring index q. */
+int smore_graph_rotation_info(smore_graph_t g, int* n_sub, int64_t* sub_cap, double* block_mass, int64_t* block_edges);
+int smore_model_enable_rotation(smore_model_t m);
+/* 3 x 64-byte cudaIpcMemHandle_t of this rank's slot buffers; open the NEXT rank's ((rank + 1) % world) with open_next. */
+int smore_model_rot_ipc_handles(smore_model_t m, void* handles192);
+int smore_model_rot_open_next(smore_model_t m, const void* handles192);
+/* Same-process variant (several shards on one device; tests): raw device pointers of the 3 slot buffers. */
+int smore_model_rot_slot_ptrs(smore_model_t m, void** ptrs3);
+int smore_model_rot_set_next_ptrs(smore_model_t m, void* const* ptrs3);
+int smore_rot_send_begin(smore_model_t m, int64_t episode);
+/* (smore_train_line_episode is declared with the trainers below) */
+int smore_rot_send_end(smore_model_t m, int64_t episode);
+int smore_rot_position(smore_model_t m, int64_t* episode, int* at_home, int* training_subpart);
+
 /* Text writer: "<V> <dim>\n" then `name v0 v1 ...` per vertex in id order, VERTEX table only.
  * format 0 = C++ iostream default (%g, 6 significant digits; src/model/LINE.cpp:13-47),
  * format 1 = Go "%.6f" (internal/models/line/line.go:209-233). */
@@ -228,7 +262,17 @@ typedef struct {
     /* Skew-OPT (cli/skewopt.cpp:53-54): margin shift xi, scale omega, odd power eta */
     double xi, omega;
     int eta;
+    /* Row-sharded LINE-2 (peer-access mode and rotating shards): how the K negatives of a sample are applied.
+     * SMORE_PAIRING_AUTO / SMORE_PAIRING_SPLIT: split samples -- the positive pair updates the edge's source, the K shard-local
+     * negatives update a second vertex drawn independently from the source distribution, which keeps the noise
+     * distribution of every vertex identical to the unsharded trainer's (one more row per update).
+     * SMORE_PAIRING_COUPLED: the reference's pairing (same vertex) with shard-local negatives; biased once a vertex has
+     * few neighbours per shard (measured: -3 points of AUC at 8 shards). Ignored on unsharded graphs. */
+    int neg_mode;
 } smore_train_params;
+#define SMORE_PAIRING_AUTO 0
+#define SMORE_PAIRING_COUPLED 1
+#define SMORE_PAIRING_SPLIT 2
 
 /* Fills `p` with the reference CLI defaults (cmd/line/main.go:13-21, cli/line.cpp:56-64). */
 void smore_train_params_default(smore_train_params* p);
@@ -242,6 +286,11 @@ int smore_train_line(smore_model_t m, const smore_train_params* p);
  * experiments): shards[r] must be rank r of n, all with the exchange mode enabled; plain device copies replace NCCL.
  * Shard r draws from streams stream_base + (r << 20) + warp. */
 int smore_train_line_group(const smore_model_t* shards, int n, const smore_train_params* p);
+/* Rotating shards (see above): one block of LINE::Train updates (src/model/LINE.cpp:162-191 restricted to the sources of
+ * the resident vertex sub-part and the contexts of this rank). p->total = samples of ALL ranks in this episode (this rank
+ * runs its block's share, total * 2*world * mass(q, rank)); p->sched_total / sched_offset in the same global unit;
+ * p->stream_base must differ between ranks and episodes. */
+int smore_train_line_episode(smore_model_t m, const smore_train_params* p, int64_t episode);
 /* BPR::Train (src/model/BPR.cpp:55-107, 5-negative UpdateBPRPair proNet.cpp:1406-1455) /
  * BPR.Train (internal/models/bpr/bpr.go:61-131, optimizer.go:87-117). */
 int smore_train_bpr(smore_model_t m, const smore_train_params* p);

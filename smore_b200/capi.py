@@ -18,6 +18,7 @@ NEG_DEGREES, NEG_IN_DEGREES, NEG_NO_DEGREES = 0, 1, 2
 MODE_DETERMINISTIC, MODE_HOGWILD = 0, 1
 F32, F64 = 0, 1
 AT_VERTEX, AT_NEGATIVE, AT_CONTEXT = 0, 1, 2
+PAIRING_AUTO, PAIRING_COUPLED, PAIRING_SPLIT = 0, 1, 2
 SAMPLE_SOURCE, SAMPLE_NEGATIVE, SAMPLE_TARGET, SAMPLE_SOURCE_TARGET = 0, 1, 2, 3
 
 u64, i64, f64, vp = C.c_uint64, C.c_int64, C.c_double, C.c_void_p
@@ -33,6 +34,9 @@ EXPORTS = [
     "smore_graph_set_shard", "smore_graph_shard_info", "smore_model_ipc_handle", "smore_model_open_peers",
     "smore_model_set_peer_ptrs", "smore_model_enable_replica", "smore_model_refresh_replica",
     "smore_model_enable_exchange", "smore_dist_nccl_unique_id", "smore_dist_nccl_init", "smore_dist_nccl_shutdown",
+    "smore_graph_set_shard_rotating", "smore_graph_rotation_info", "smore_model_enable_rotation", "smore_model_rot_ipc_handles",
+    "smore_model_rot_open_next", "smore_model_rot_slot_ptrs", "smore_model_rot_set_next_ptrs", "smore_rot_send_begin",
+    "smore_train_line_episode", "smore_rot_send_end", "smore_rot_position",
     "smore_train_line_group", "smore_exchange_stats", "smore_debug_sm_partition", "smore_model_save_weights", "smore_format_rows",
     "smore_model_load_pretrain", "smore_model_save_checkpoint", "smore_model_load_checkpoint", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
     "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf", "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
@@ -49,7 +53,7 @@ class TrainParams(C.Structure):
         ("total", u64), ("negative_samples", C.c_int), ("order", C.c_int), ("lambda_", f64),
         ("walk_times", C.c_int), ("walk_steps", C.c_int), ("window_min", C.c_int), ("window_max", C.c_int),
         ("max_warps", C.c_int), ("max_walks", i64), ("sched_total", u64), ("sched_offset", u64),
-        ("xi", f64), ("omega", f64), ("eta", C.c_int),
+        ("xi", f64), ("omega", f64), ("eta", C.c_int), ("neg_mode", C.c_int),
     ]
 
 
@@ -101,6 +105,17 @@ def lib():
         L.smore_model_enable_replica.argtypes = [vp, C.c_int]
         L.smore_model_refresh_replica.argtypes = [vp, C.c_int]
         L.smore_model_enable_exchange.argtypes = [vp, i64, f64]
+        L.smore_graph_set_shard_rotating.argtypes = [vp, C.c_int, C.c_int]
+        L.smore_graph_rotation_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(i64), vp, vp]
+        L.smore_model_enable_rotation.argtypes = [vp]
+        L.smore_model_rot_ipc_handles.argtypes = [vp, vp]
+        L.smore_model_rot_open_next.argtypes = [vp, vp]
+        L.smore_model_rot_slot_ptrs.argtypes = [vp, vp]
+        L.smore_model_rot_set_next_ptrs.argtypes = [vp, vp]
+        L.smore_rot_send_begin.argtypes = [vp, i64]
+        L.smore_train_line_episode.argtypes = [vp, C.POINTER(TrainParams), i64]
+        L.smore_rot_send_end.argtypes = [vp, i64]
+        L.smore_rot_position.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.smore_dist_nccl_unique_id.argtypes = [vp]
         L.smore_dist_nccl_init.argtypes = [vp, C.c_int, C.c_int]
         L.smore_dist_nccl_shutdown.argtypes = []
@@ -233,6 +248,19 @@ class Graph:
         check(lib().smore_graph_set_shard(self.h, rank, world))
         return self.shard_info()
 
+    def set_shard_rotating(self, rank, world):
+        """Rotating shards: as set_shard, plus one edge table per (vertex sub-part, this rank's contexts) block."""
+        check(lib().smore_graph_set_shard_rotating(self.h, rank, world))
+        return self.shard_info()
+
+    def rotation_info(self):
+        n, cap = C.c_int(), i64()
+        check(lib().smore_graph_rotation_info(self.h, C.byref(n), C.byref(cap), None, None))
+        mass = np.zeros(n.value)
+        edges = np.zeros(n.value, dtype=np.int64)
+        check(lib().smore_graph_rotation_info(self.h, C.byref(n), C.byref(cap), _ptr(mass), _ptr(edges)))
+        return {"n_sub": n.value, "sub_cap": cap.value, "block_mass": mass, "block_edges": edges}
+
     def shard_info(self):
         r, w, n, f = C.c_int(), C.c_int(), i64(), f64()
         check(lib().smore_graph_shard_info(self.h, C.byref(r), C.byref(w), C.byref(n), C.byref(f)))
@@ -362,6 +390,43 @@ class Model:
         sb, rows, hot = u64(), u64(), i64()
         check(lib().smore_exchange_stats(self.h, C.byref(sb), C.byref(rows), C.byref(hot)))
         return {"superbatches": sb.value, "rows_requested": rows.value, "hot_vertices": hot.value}
+
+    # ---- rotating shards (include/smore_b200.h) ----
+    def enable_rotation(self):
+        check(lib().smore_model_enable_rotation(self.h))
+
+    def rot_ipc_handles(self) -> bytes:
+        buf = (C.c_ubyte * 192)()
+        check(lib().smore_model_rot_ipc_handles(self.h, C.cast(buf, vp)))
+        return bytes(buf)
+
+    def rot_open_next(self, handles: bytes):
+        buf = (C.c_ubyte * 192).from_buffer_copy(handles)
+        check(lib().smore_model_rot_open_next(self.h, C.cast(buf, vp)))
+
+    def rot_slot_ptrs(self):
+        arr = (vp * 3)()
+        check(lib().smore_model_rot_slot_ptrs(self.h, C.cast(arr, vp)))
+        return [arr[k] for k in range(3)]
+
+    def rot_set_next_ptrs(self, ptrs):
+        arr = (vp * 3)(*[vp(p) for p in ptrs])
+        check(lib().smore_model_rot_set_next_ptrs(self.h, C.cast(arr, vp)))
+
+    def rot_send_begin(self, episode):
+        check(lib().smore_rot_send_begin(self.h, episode))
+
+    def train_line_episode(self, p, episode):
+        check(lib().smore_train_line_episode(self.h, C.byref(p), episode))
+        return self.stats()
+
+    def rot_send_end(self, episode):
+        check(lib().smore_rot_send_end(self.h, episode))
+
+    def rot_position(self):
+        e, h, q = i64(), C.c_int(), C.c_int()
+        check(lib().smore_rot_position(self.h, C.byref(e), C.byref(h), C.byref(q)))
+        return {"episode": e.value, "at_home": bool(h.value), "training_subpart": q.value}
 
     def device_ptr(self, table):
         p = vp()

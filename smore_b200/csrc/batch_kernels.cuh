@@ -24,13 +24,15 @@
 
 namespace smore {
 
-// sharded: one edge draw (idx, p) replaces the source + target draws
-__host__ __device__ inline int batch_wps(int go, int K) { return (go == 2 ? 2 : go ? 3 : 4) + 2 * K; }
+// batch modes: 0 = C++ draws, 1 = Go draws, 2 = sharded: one edge draw (idx, p) replaces the source + target draws,
+// 3 = sharded + split sample: edge draw, K negatives, then (idx, p) for the second vertex (ids row grows by one slot)
+__host__ __device__ inline int batch_wps(int go, int K) { return (go == 3 ? 4 : go == 2 ? 2 : go ? 3 : 4) + 2 * K; }
+__host__ __device__ inline int batch_idw(int go, int K) { return K + 2 + (go == 3 ? 1 : 0); }
 __host__ __device__ inline int batch_wbuf_words(int go, int K) { return ((32 * batch_wps(go, K) + 8 + 3) / 4) * 4; }
 constexpr int kStageDepth = 4;  // vertex rows of a row-sharded table staged ahead per warp (cp.async ring)
 template <typename T>
 inline size_t batch_smem_bytes(int go, int K, int stage_row_elems = 0) {
-    size_t base = 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(batch_wbuf_words(go, K) + 32 * (K + 2)) * 4;
+    size_t base = 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(batch_wbuf_words(go, K) + 32 * batch_idw(go, K)) * 4;
     base = (base + 15) & ~(size_t)15;
     return base + (size_t)kWarpsPerBlock * kStageDepth * (size_t)stage_row_elems * sizeof(T);
 }
@@ -45,6 +47,7 @@ struct Batch {
     uint32_t* wbuf;
     int* ids;
     int K, wps, idw;
+    bool split;
 };
 
 template <typename T>
@@ -52,7 +55,8 @@ __device__ __forceinline__ Batch batch_init(int go, int K, int wib) {
     Batch b;
     b.K = K;
     b.wps = batch_wps(go, K);
-    b.idw = K + 2;
+    b.idw = batch_idw(go, K);
+    b.split = go == 3;
     const int wcap = batch_wbuf_words(go, K);
     b.wbuf = reinterpret_cast<uint32_t*>(smem_raw + 1008 * sizeof(T)) + (size_t)wib * (wcap + 32 * b.idw);
     b.ids = reinterpret_cast<int*>(b.wbuf + wcap);
@@ -103,6 +107,8 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
             const uint32_t le = alias_pick(g.edge_at, index_draw(wd[0], g.n_edge_local), wd[1]);
             my_ids[0] = __ldg(g.edge_src + le);
             my_ids[1] = __ldg(g.edge_dst + le);
+            if (b.split)  // the vertex that takes the negatives: drawn from the source distribution, independent of the edge
+                my_ids[b.K + 2] = (int)alias_pick(g.vsrc_at, index_draw(wd[2 + 2 * b.K], g.n_vsrc), wd[3 + 2 * b.K]);
         }
     }
     st.pos += (uint64_t)(nb * b.wps);
@@ -113,15 +119,16 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
 // table). Rows of a peer shard are skipped: peer addresses bypass the local L2.
 template <typename T, class TV, class TC>
 __device__ __forceinline__ void prefetch_sample(const TV& tv, const TC& tc, int rank, const int* pid,
-                                                int idw, int lane) {
+                                                int idw, int lane, int vslot2 = -1 /* split samples: slot of the 2nd vertex */) {
     const int lines_per_row = (tv.dim * (int)sizeof(T) + 127) >> 7;
     const int total = idw * lines_per_row;
     for (int t = lane; t < total; t += 32) {
         const int r = t / lines_per_row, ln = t - r * lines_per_row;
         const int id = pid[r];
+        const bool vrow = r == 0 || r == vslot2;
         // (a negative id in slot 0 is a staging row of the exchange mode: ExchView; negative elsewhere = no row)
-        if (r == 0 ? (id < 0 || (id & tv.mask) == (rank & tv.mask)) : (id >= 0 && (id & tc.mask) == (rank & tc.mask))) {
-            const char* p = reinterpret_cast<const char*>(r == 0 ? tv.row(id) : tc.row(id)) + (ln << 7);
+        if (vrow ? (id < 0 || (id & tv.mask) == (rank & tv.mask)) : (id >= 0 && (id & tc.mask) == (rank & tc.mask))) {
+            const char* p = reinterpret_cast<const char*>(vrow ? tv.row(id) : tc.row(id)) + (ln << 7);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
         }
     }
@@ -270,7 +277,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_apply_delta(typename C::T* __
 // (k_line_requests -> all-to-all -> k_gather_rows -> all-to-all), so every access of this kernel is to local HBM --
 // except the rows of HOT vertices (ExchDev::hot), which are reached through the peer mappings.
 // KIND: 0 = skip-gram pair update (LINE), 1 = MF: the same sampling loop around UpdateFactorizedPair (MF::Train,
-// src/model/MF.cpp:70-92, draws exactly what LINE::Train draws).
+// src/model/MF.cpp:70-92, draws exactly what LINE::Train draws), 2 = LINE with split samples (row-sharded modes only:
+// update_pair_split, the K negatives go to a second, independently drawn vertex), 3 = LINE (C++ semantics) with atomic
+// row updates (red.global.add of every delta; experiment, SMORE_ROW_RED=1).
 template <class C, bool GO, int SHARD, int KIND = 0>
 __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
     constexpr bool STAGED = SHARD == 1;
@@ -300,7 +309,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
     const int wib = threadIdx.x >> 5;
     const int w = blockIdx.x * kWarpsPerBlock + wib;
     if (w >= a.n_warps) return;
-    const int bmode = a.g.edge_at ? 2 : (GO ? 1 : 0);
+    const int bmode = a.g.edge_at ? (KIND == 2 ? 3 : 2) : (GO ? 1 : 0);
     const Batch b = batch_init<T>(bmode, a.K, wib);
     WarpState st = a.state[w];
     const uint64_t stream = a.stream_base + (uint64_t)w;
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
     constexpr int kRowElems = C::EPL * 32;
     T* vstage = nullptr;
     if constexpr (staged) {
-        size_t off = 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(batch_wbuf_words(bmode, a.K) + 32 * (a.K + 2)) * 4;
+        size_t off = 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(batch_wbuf_words(bmode, a.K) + 32 * batch_idw(bmode, a.K)) * 4;
         off = (off + 15) & ~(size_t)15;
         vstage = reinterpret_cast<T*>(smem_raw + off) + (size_t)wib * kStageDepth * kRowElems;
     }
@@ -342,7 +351,8 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             }
         }
         for (int s = 0; s < nb; ++s) {
-            if (s + kLinePrefetch < nb) prefetch_sample<T>(tv, tc, a.g.shard_rank, b.ids + (s + kLinePrefetch) * b.idw, b.idw, lane);
+            if (s + kLinePrefetch < nb)
+                prefetch_sample<T>(tv, tc, a.g.shard_rank, b.ids + (s + kLinePrefetch) * b.idw, b.idw, lane, KIND == 2 ? a.K + 2 : -1);
             const int* sid = b.ids + s * b.idw;
             const int v1 = sid[0];
             const int v2 = sid[1];
@@ -362,6 +372,8 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             // replica rows never alias shard rows in memory; nor do staging rows (v1 < 0 then never equals a context id)
             const bool same = SHARD == 2 ? false : a.same_table != 0;
             if constexpr (KIND == 1) update_factorized_pair<C, TV, TC>(tv, tc, a.dim, same, v1, my, nrows, alpha, a.lambda, lane);
+            else if constexpr (KIND == 2) update_pair_split<C, TV, TC>(tv, tc, a.dim, lut, v1, sid[a.K + 2], my, nrows, alpha, lane, staged ? &vrow : nullptr, SHARD == 1 && a.vred != 0);
+            else if constexpr (KIND == 3) update_pair_cpp<C, TV, TC, false, true>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane);
             else if (!GO) update_pair_cpp<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush, SHARD == 1 && a.vred != 0);
             else update_pair_go<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush, SHARD == 1 && a.vred != 0);
             st.count++;

@@ -46,6 +46,10 @@ struct GraphDev {
     // negative_at index -> vertex id: (l << neg_shift) + neg_rank. Shard-local negatives: neg_shift/neg_rank = the shard's;
     // a table over all vertices (unsharded, or the sharded "global negatives" variant): 0 / 0.
     int neg_shift, neg_rank;
+    // split samples (kernels.cuh update_pair_split): the table the second vertex of a sample is drawn from -- the global
+    // vertex table (peer-access mode, ids = vertex ids) or the table of the resident sub-part (rotating shards, ids = rows)
+    const uint2* vsrc_at;
+    uint32_t n_vsrc;
     __device__ __forceinline__ uint32_t global_id(uint32_t local) const { return (local << neg_shift) + (uint32_t)neg_rank; }
 };
 

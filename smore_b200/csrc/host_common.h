@@ -72,6 +72,17 @@ struct smore_graph_s {
     int32_t* d_field = nullptr;
     double* d_lut64 = nullptr;
     float* d_lut32 = nullptr;
+    // rotating shards (smore_graph_set_shard_rotating; rotation.cu): the vertex table is cut into nsub = 2*world
+    // sub-parts that travel around the ring of ranks; d_eat / d_esrc / d_edst then hold one edge table PER BLOCK
+    // (sub-part q of the sources x this rank's contexts), block q at [blk_off[q], blk_off[q+1])
+    bool rotating = false;
+    int nsub = 0;
+    int64_t sub_cap = 0;              // rows of a slot buffer: first half of a shard = local rows [0, sub_cap)
+    std::vector<int64_t> blk_off;     // nsub + 1
+    std::vector<double> blk_mass;     // nsub: share of the GLOBAL edge mass in block (q, this rank)
+    std::vector<int64_t> sub_rows;    // nsub: rows of sub-part q (ring index q = 2*home + half)
+    uint2* d_vsub = nullptr;          // per sub-part: alias table of the source distribution over its rows (split samples)
+    std::vector<int64_t> vsub_off;    // nsub + 1
 
     GraphDev view() const {
         GraphDev g;
@@ -83,12 +94,36 @@ struct smore_graph_s {
         g.neg_shift = neg_global ? 0 : shift; g.neg_rank = neg_global ? 0 : rank;
         g.edge_at = d_eat; g.edge_src = d_esrc; g.edge_dst = d_edst; g.n_edge_local = (uint32_t)n_edge_local;
         g.shard_shift = shift; g.shard_rank = rank;
+        g.vsrc_at = d_vat; g.n_vsrc = (uint32_t)V;
         return g;
     }
     ~smore_graph_s() {
         cudaFree(d_row_off); cudaFree(d_col); cudaFree(d_vat); cudaFree(d_nat); cudaFree(d_cat);
         cudaFree(d_prefix); cudaFree(d_field); cudaFree(d_lut64); cudaFree(d_lut32);
-        cudaFree(d_eat); cudaFree(d_esrc); cudaFree(d_edst);
+        cudaFree(d_eat); cudaFree(d_esrc); cudaFree(d_edst); cudaFree(d_vsub);
+    }
+};
+
+// Rotating vertex table of one rank (rotation.cu). Three slot buffers of sub_cap rows take the roles
+//   T(e) = slot[e % 3]        the sub-part trained in episode e,
+//   O(e) = slot[(e + 2) % 3]  the sub-part trained in episode e-1, travelling to the next rank during episode e,
+//   I(e) = slot[(e + 1) % 3]  receives the previous rank's O(e); becomes T(e+1).
+struct smore_rotation_s {
+    void* slot[3] = {nullptr, nullptr, nullptr};
+    void* next_slot[3] = {nullptr, nullptr, nullptr};  // the next rank's slots (peer mappings, or same-process pointers)
+    bool next_opened[3] = {false, false, false};
+    cudaStream_t copy_stream = nullptr;
+    int64_t episode = 0;   // the next episode to run
+    bool sending = false;  // between send_begin and send_end
+    bool trained = false;  // train_line_episode(episode) done
+    bool at_home(int nsub) const { return nsub > 0 && episode % nsub == 0 && !sending; }
+    void* half(int h) const { return slot[(episode + (h ? 2 : 0)) % 3]; }  // valid at home only
+    ~smore_rotation_s() {
+        for (int k = 0; k < 3; ++k) {
+            if (next_opened[k]) cudaIpcCloseMemHandle(next_slot[k]);
+            cudaFree(slot[k]);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
 
@@ -101,6 +136,7 @@ struct smore_model_s {
     bool peer_opened[2][kMaxWorld] = {};       // CUDA-IPC mappings to close
     void* replica[2] = {nullptr, nullptr};     // optional full-size local read replica of a sharded table
     smore_exchange_s* xch = nullptr;           // bulk-exchange mode of a sharded model (smore_model_enable_exchange)
+    smore_rotation_s* rot = nullptr;           // rotating vertex table (smore_model_enable_rotation): tab[0] == nullptr then
     WarpState* d_state = nullptr;
     int state_cap = 0;
     int32_t* d_keys = nullptr;
@@ -116,8 +152,30 @@ struct smore_model_s {
         cudaFree(tab[0]); cudaFree(tab[1]); cudaFree(d_state); cudaFree(d_keys);
         cudaFree(replica[0]); cudaFree(replica[1]);
         delete xch;
+        delete rot;
     }
 };
+
+// Rows [first, first+n) of a table as contiguous device ranges: fn(device pointer, first local row, rows) -> rc. One range
+// for an ordinary table; a rotating table keeps the two halves of the shard in separate slot buffers and can only be
+// addressed while its sub-parts are at home (rotation.cu).
+template <class F>
+int for_row_ranges(smore_model_s* m, int table, int64_t first, int64_t n, F&& fn) {
+    const size_t row_bytes = (size_t)m->dim * m->elem();
+    if (!(m->rot && table == 0)) return fn((char*)m->tab[table] + (size_t)first * row_bytes, first, n);
+    if (!m->rot->at_home(m->g->nsub))
+        return fail(SMORE_E_INVALID, "the rotating vertex table is not at its home position (episode %lld of a %d-episode cycle)",
+                    (long long)m->rot->episode, m->g->nsub);
+    const int64_t cap = m->g->sub_cap;
+    if (first < cap) {
+        const int64_t k = std::min(n, cap - first);
+        if (int rc = fn((char*)m->rot->half(0) + (size_t)first * row_bytes, first, k)) return rc;
+        first += k;
+        n -= k;
+    }
+    if (n > 0) return fn((char*)m->rot->half(1) + (size_t)(first - cap) * row_bytes, first, n);
+    return SMORE_OK;
+}
 
 namespace {
 
@@ -171,6 +229,7 @@ int ensure_state(smore_model_s* m, int warps) {
 
 int check_train(smore_model_s* m, const smore_train_params* p, int need_tables, bool shard_ok = false) {
     if (!m || !p) return fail(SMORE_E_INVALID, "null model/params");
+    if (m->rot || m->g->rotating) return fail(SMORE_E_UNSUPPORTED, "rotating shards are trained episode by episode: smore_rot_send_begin / smore_train_line_episode / smore_rot_send_end");
     if (m->g->world > 1 && !shard_ok) return fail(SMORE_E_UNSUPPORTED, "this trainer does not run on a row-sharded graph yet (LINE does)");
     if (m->g->world > 1 && !(m->xch && m->xch->n_hot == 0))  // (without hot rows the exchange mode never touches a peer)
         for (int t = 0; t < m->n_tables; ++t)
@@ -300,5 +359,8 @@ template <typename T>
 int train_hpe_t(smore_model_s* m, const smore_train_params* p);
 template <typename T>
 int train_mf_t(smore_model_s* m, const smore_train_params* p);
+// rotating shards: one block (sub-part q of the vertex table in `vslot` x this rank's contexts), n_samples updates
+template <typename T>
+int train_line_block_t(smore_model_s* m, const smore_train_params* p, int q, void* vslot, uint64_t n_samples);
 template <typename T>
 int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind);

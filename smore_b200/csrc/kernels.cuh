@@ -79,7 +79,9 @@ struct TrainArgs {
 // my_id: lane 0 holds the positive context, lane 1+n negative n; nrows = K+1 <= 32.
 // ---------------------------------------------------------------------------------------------------------------
 // CTX_CA: gather the context rows with ld.global.ca (hub rows served from L1; used when sharding concentrates them)
-template <class C, class TV, class TC, bool CTX_CA = false>
+// RED: every row takes its delta with red.global.add instead of a store of the updated copy (atomic Hogwild: concurrent
+// updates of a row are never lost, only computed from slightly stale values).
+template <class C, class TV, class TC, bool CTX_CA = false, bool RED = false>
 __device__ __forceinline__ void update_pair_cpp(const TV& tv,
                                                 const TC& tc, int dim, bool same_table,
                                                 const typename C::T* lut, int v1, int my_id, int nrows,
@@ -117,16 +119,18 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
 #pragma unroll
                     for (int e = 0; e < C::EPL; ++e) {
                         back.x[e] = A::madd(back.x[e], g, c[r].x[e]);  // loss_vertex += g * w_context
-                        c[r].x[e] = A::madd(c[r].x[e], g, v.x[e]);     // w_context   += g * w_vertex (in place)
+                        if constexpr (RED) c[r].x[e] = A::mul(g, v.x[e]);
+                        else c[r].x[e] = A::madd(c[r].x[e], g, v.x[e]);  // w_context   += g * w_vertex (in place)
                     }
-                    c[r].store(tc.row(ids[r]), lane, dim);
+                    if constexpr (RED) row_red_add<C>(tc.row(ids[r]), c[r], lane, dim);
+                    else c[r].store(tc.row(ids[r]), lane, dim);
                 }
             }
         }
         // vred (row-sharded table, rows shared with other GPUs): the row takes its DELTA with red.global.add, performed by
         // the owner's L2 -- a full-row store of the (staged, possibly stale) copy would overwrite what the other ranks, or an
         // earlier sample of this very warp, added to the row in the meantime
-        if (vred) row_red_add<C>(pv, back, lane, dim);
+        if (RED || vred) row_red_add<C>(pv, back, lane, dim);
         else {
 #pragma unroll
             for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
@@ -282,6 +286,134 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
 #pragma unroll
         for (int e = 0; e < C::EPL; ++e) pos.x[e] = A::add(pos.x[e], cgrad.x[e]);
         pos.store(pp, lane, dim);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Split sample (row-sharded modes). With shard-local negatives the K negatives of a sample come from the shard of its
+// positive context; applied to the SAME vertex v1 they make the noise distribution depend on v1 (a vertex is only ever
+// pushed away from contexts in the shards of its own neighbours -- with 8 shards and ~20 neighbours that already costs
+// 3 points of held-out AUC, profiles/r2a_ab_sharded_quality.txt). The split sample restores the unsharded distribution
+// exactly: the positive pair (v1, ctx) is one skip-gram step with label 1, and the K negatives are one step with label 0
+// for a SECOND vertex v2 drawn from the source distribution independently of the edge. Per pair the arithmetic is
+// Opt_SigmoidSGD (src/proNet.cpp:1312-1330 / optimizer.go:61-84); both trees reduce to the same thing here because the
+// skip rules of the Go tree (negative == context) concern a pairing that no longer exists.
+// my_id: lane 0 = positive context, lane 1+n = negative n; nrows = K + 1. One more row per sample: 2 (K+3) D s bytes.
+// ---------------------------------------------------------------------------------------------------------------
+template <class C, class TV, class TC>
+__device__ __forceinline__ void update_pair_split(const TV& tv, const TC& tc, int dim, const typename C::T* lut, int v1,
+                                                  int v2, int my_id, int nrows, typename C::T alpha, int lane,
+                                                  const Row<C>* vpre, bool vred) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    const bool active = lane < nrows;
+    const unsigned peers = __match_any_sync(kFull, active ? my_id : (-1 - lane));
+    const bool dup = __any_sync(kFull, active && __popc(peers) > 1) || v1 == v2;
+    T* pv1 = tv.row(v1);
+    T* pv2 = tv.row(v2);
+    const int ctx = __shfl_sync(kFull, my_id, 0);
+    T* pp = tc.row(ctx);
+    if (!dup) {
+        Row<C> a, b, pos;
+        if (vpre) a = *vpre;
+        else a.load(pv1, lane, dim);
+        b.load(pv2, lane, dim);
+        pos.load(pp, lane, dim);
+        {   // positive pair: v1 <-> ctx
+            const T g = A::mul(A::sub((T)1, fast_sigmoid<T>(lut, dot(a, pos))), alpha);
+            Row<C> d;
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                d.x[e] = A::mul(g, pos.x[e]);
+                pos.x[e] = A::madd(pos.x[e], g, a.x[e]);
+            }
+            pos.store(pp, lane, dim);
+            if (vred) row_red_add<C>(pv1, d, lane, dim);
+            else {
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) a.x[e] = A::add(a.x[e], d.x[e]);
+                a.store(pv1, lane, dim);
+            }
+        }
+        Row<C> back;
+        back.zero();
+        for (int base = 1; base < nrows; base += kCtxChunk) {
+            Row<C> c[kCtxChunk];
+            int ids[kCtxChunk];
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) {
+                ids[r] = __shfl_sync(kFull, my_id, (base + r) & 31);
+                if (base + r < nrows) c[r].load(tc.row(ids[r]), lane, dim);
+            }
+            T f[kCtxChunk];
+            dots<C, kCtxChunk>(b, c, nrows - base, f);
+#pragma unroll
+            for (int r = 0; r < kCtxChunk; ++r) {
+                if (base + r < nrows) {
+                    const T g = A::mul(A::sub((T)0, fast_sigmoid<T>(lut, f[r])), alpha);
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) {
+                        back.x[e] = A::madd(back.x[e], g, c[r].x[e]);
+                        c[r].x[e] = A::madd(c[r].x[e], g, b.x[e]);
+                    }
+                    c[r].store(tc.row(ids[r]), lane, dim);
+                }
+            }
+        }
+        if (nrows > 1) {
+            if (vred) row_red_add<C>(pv2, back, lane, dim);
+            else {
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) b.x[e] = A::add(b.x[e], back.x[e]);
+                b.store(pv2, lane, dim);
+            }
+        }
+    } else {
+        // some rows coincide: one pair at a time through memory
+        {
+            Row<C> a, pos, d;
+            a.load(pv1, lane, dim);
+            pos.load(pp, lane, dim);
+            const T g = A::mul(A::sub((T)1, fast_sigmoid<T>(lut, dot(a, pos))), alpha);
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                d.x[e] = A::mul(g, pos.x[e]);
+                pos.x[e] = A::madd(pos.x[e], g, a.x[e]);
+            }
+            pos.store(pp, lane, dim);
+            if (vred) row_red_add<C>(pv1, d, lane, dim);
+            else {
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) a.x[e] = A::add(a.x[e], d.x[e]);
+                a.store(pv1, lane, dim);
+            }
+        }
+        Row<C> back;
+        back.zero();
+        for (int r = 1; r < nrows; ++r) {
+            const int cid = __shfl_sync(kFull, my_id, r);
+            T* pc = tc.row(cid);
+            Row<C> b, c;
+            b.load(pv2, lane, dim);
+            c.load(pc, lane, dim);
+            const T g = A::mul(A::sub((T)0, fast_sigmoid<T>(lut, dot(b, c))), alpha);
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                back.x[e] = A::madd(back.x[e], g, c.x[e]);
+                c.x[e] = A::madd(c.x[e], g, b.x[e]);
+            }
+            c.store(pc, lane, dim);
+        }
+        if (nrows > 1) {
+            if (vred) row_red_add<C>(pv2, back, lane, dim);
+            else {
+                Row<C> b;
+                b.load(pv2, lane, dim);
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) b.x[e] = A::add(b.x[e], back.x[e]);
+                b.store(pv2, lane, dim);
+            }
+        }
     }
 }
 
@@ -737,7 +869,8 @@ static __global__ void k_walk_debug(GraphDev g, uint64_t seed, uint64_t stream, 
 // Table init: (U - 0.5) / dim, U = k * 2^-32, k = word e of stream (seed, kInitStreamBase + table) for GLOBAL element e
 // (row-sharded tables: local row l is global row (l << shift) + rank, so the values do not depend on the sharding).
 template <typename T>
-__global__ void k_init_table(T* W, int64_t n_elems, int dim, uint64_t seed, uint64_t stream, int random, int shift, int rank) {
+__global__ void k_init_table(T* W, int64_t n_elems, int dim, uint64_t seed, uint64_t stream, int random, int shift, int rank,
+                             int64_t row0 /* local row of W[0] */) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n_elems; i += stride) {
@@ -746,7 +879,7 @@ __global__ void k_init_table(T* W, int64_t n_elems, int dim, uint64_t seed, uint
             continue;
         }
         const int64_t l = i / dim, d = i - l * dim;
-        const uint64_t ge = (uint64_t)(((l << shift) + rank) * dim + d);
+        const uint64_t ge = (uint64_t)((((l + row0) << shift) + rank) * dim + d);
         U4 r = philox_block(seed, stream, ge >> 2);
         const uint32_t lane = (uint32_t)(ge & 3);
         const uint32_t k = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;

@@ -168,14 +168,9 @@ int build_graph(smore_graph_s* g) {
 
 namespace {
 template <typename TH>
-int rows_io(smore_model_t m, int table, int64_t first, int64_t n, TH* host, bool to_device) {
-    if (!m || table < 0 || table >= m->n_tables || !host) return fail(SMORE_E_INVALID, "bad model/table/buffer");
-    if (first < 0 || n < 0 || first + n > m->rows) return fail(SMORE_E_INVALID, "row range out of bounds (the model holds %lld rows)", (long long)m->rows);
-    if (n == 0) return SMORE_OK;
-    if (int rc = ensure_device()) return rc;
+int rows_io_range(smore_model_t m, char* dptr, int64_t n, TH* host, bool to_device) {
     const int64_t cnt = n * (int64_t)m->dim;
     const bool same = (m->dtype == SMORE_F64) == (sizeof(TH) == 8);
-    char* dptr = (char*)m->tab[table] + (size_t)first * (size_t)m->dim * m->elem();
     if (same) {
         if (to_device) CU(cudaMemcpy(dptr, host, (size_t)cnt * sizeof(TH), cudaMemcpyHostToDevice));
         else CU(cudaMemcpy((void*)host, dptr, (size_t)cnt * sizeof(TH), cudaMemcpyDeviceToHost));
@@ -204,6 +199,18 @@ int rows_io(smore_model_t m, int table, int64_t first, int64_t n, TH* host, bool
     }
     cudaFree(stage);
     return rc;
+}
+
+template <typename TH>
+int rows_io(smore_model_t m, int table, int64_t first, int64_t n, TH* host, bool to_device) {
+    if (!m || table < 0 || table >= m->n_tables || !host) return fail(SMORE_E_INVALID, "bad model/table/buffer");
+    if (first < 0 || n < 0 || first + n > m->rows) return fail(SMORE_E_INVALID, "row range out of bounds (the model holds %lld rows)", (long long)m->rows);
+    if (n == 0) return SMORE_OK;
+    if (int rc = ensure_device()) return rc;
+    const int64_t first0 = first;
+    return for_row_ranges(m, table, first, n, [&](char* dptr, int64_t f, int64_t k) {
+        return rows_io_range<TH>(m, dptr, k, host + (size_t)(f - first0) * (size_t)m->dim, to_device);
+    });
 }
 }  // namespace
 
@@ -571,6 +578,7 @@ int smore_graph_shard_info(smore_graph_t g, int* rank, int* world, int64_t* n_lo
 int smore_model_ipc_handle(smore_model_t m, int table, void* handle64) {
     if (!m || table < 0 || table >= m->n_tables || !handle64) return fail(SMORE_E_INVALID, "bad argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!m->tab[table]) return fail(SMORE_E_INVALID, "table %d rotates between ranks (smore_model_rot_ipc_handles)", table);
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, m->tab[table]));
     memcpy(handle64, &h, 64);
@@ -639,13 +647,17 @@ void smore_model_destroy(smore_model_t m) { delete m; }
 int smore_model_init(smore_model_t m, int table, int random, uint64_t seed) {
     if (!m || table < 0 || table >= m->n_tables) return fail(SMORE_E_INVALID, "bad model/table");
     if (int rc = ensure_device()) return rc;
-    const int64_t n = m->rows * (int64_t)m->dim;
-    const int blocks = (int)std::min<int64_t>((n + 255) / 256 + 1, 148 * 16);
     const int sh = m->g->shift, rk = m->g->rank;  // a shard initialises its rows with the words of their GLOBAL position
-    if (m->dtype == SMORE_F64) k_init_table<double><<<blocks, 256>>>((double*)m->tab[table], n, m->dim, seed, kInitStreamBase + (uint64_t)table, random, sh, rk);
-    else k_init_table<float><<<blocks, 256>>>((float*)m->tab[table], n, m->dim, seed, kInitStreamBase + (uint64_t)table, random, sh, rk);
-    g_launches++;
-    CU(cudaGetLastError());
+    if (int rc = for_row_ranges(m, table, 0, m->rows, [&](char* dptr, int64_t first, int64_t k) -> int {
+            const int64_t n = k * (int64_t)m->dim;
+            const int blocks = (int)std::min<int64_t>((n + 255) / 256 + 1, 148 * 16);
+            if (m->dtype == SMORE_F64) k_init_table<double><<<blocks, 256>>>((double*)dptr, n, m->dim, seed, kInitStreamBase + (uint64_t)table, random, sh, rk, first);
+            else k_init_table<float><<<blocks, 256>>>((float*)dptr, n, m->dim, seed, kInitStreamBase + (uint64_t)table, random, sh, rk, first);
+            g_launches++;
+            CU(cudaGetLastError());
+            return SMORE_OK;
+        }))
+        return rc;
     CU(cudaDeviceSynchronize());
     return SMORE_OK;
 }
@@ -666,6 +678,7 @@ int smore_model_get_rows_f32(smore_model_t m, int table, int64_t first, int64_t 
 
 int smore_model_device_ptr(smore_model_t m, int table, void** ptr) {
     if (!m || table < 0 || table >= m->n_tables || !ptr) return fail(SMORE_E_INVALID, "bad model/table");
+    if (!m->tab[table]) return fail(SMORE_E_INVALID, "table %d rotates between ranks: it has no fixed device address (smore_model_rot_slot_ptrs)", table);
     *ptr = m->tab[table];
     return SMORE_OK;
 }
@@ -830,10 +843,13 @@ int smore_model_save_checkpoint(smore_model_t m, const char* path) {
     for (int t = 0; ok && t < m->n_tables; ++t)
         for (int64_t first = 0; ok && first < m->rows; first += chunk) {
             const int64_t n = std::min(chunk, m->rows - first);
-            cudaError_t e = cudaMemcpy(host.data(), (const char*)m->tab[t] + (size_t)first * row_bytes, (size_t)n * row_bytes, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) {
+            const int rc = for_row_ranges(m, t, first, n, [&](char* dptr, int64_t f0, int64_t k) -> int {
+                CU(cudaMemcpy(host.data() + (size_t)(f0 - first) * row_bytes, dptr, (size_t)k * row_bytes, cudaMemcpyDeviceToHost));
+                return SMORE_OK;
+            });
+            if (rc) {
                 fclose(f);
-                return fail(SMORE_E_CUDA, "checkpoint read-back: %s", cudaGetErrorString(e));
+                return rc;
             }
             ok = fwrite(host.data(), row_bytes, (size_t)n, f) == (size_t)n;
         }
@@ -867,10 +883,13 @@ int smore_model_load_checkpoint(smore_model_t m, const char* path) {
                 fclose(f);
                 return fail(SMORE_E_IO, "checkpoint %s is truncated", path);
             }
-            cudaError_t e = cudaMemcpy((char*)m->tab[t] + (size_t)first * row_bytes, host.data(), (size_t)n * row_bytes, cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) {
+            const int rc = for_row_ranges(m, t, first, n, [&](char* dptr, int64_t f0, int64_t k) -> int {
+                CU(cudaMemcpy(dptr, host.data() + (size_t)(f0 - first) * row_bytes, (size_t)k * row_bytes, cudaMemcpyHostToDevice));
+                return SMORE_OK;
+            });
+            if (rc) {
                 fclose(f);
-                return fail(SMORE_E_CUDA, "checkpoint upload: %s", cudaGetErrorString(e));
+                return rc;
             }
         }
     fclose(f);

@@ -10,10 +10,16 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
         using C = decltype(cfg);
         const bool cpp = p->semantics == SMORE_SEM_CPP;
         const int shard = m->g->world == 1 ? 0 : (m->replica[vtab] ? 2 : 1);
+        // peer-access mode, LINE-2: split samples by default (neg_mode 1 = the coupled round-1 scheme)
+        const bool split = shard == 1 && vtab != ctab && p->neg_mode != SMORE_PAIRING_COUPLED;
+        const char* rr = getenv("SMORE_ROW_RED");
+        const bool row_red = rr && atoi(rr) != 0 && shard == 0 && cpp && p->mode == SMORE_MODE_HOGWILD;
         void (*kern)(TrainArgs<T>) =
-            cpp ? (shard == 2 ? k_line<C, false, 2> : shard == 1 ? k_line<C, false, 1> : k_line<C, false, 0>)
-                : (shard == 2 ? k_line<C, true, 2> : shard == 1 ? k_line<C, true, 1> : k_line<C, true, 0>);
-        const size_t smem = batch_smem_bytes<T>(m->g->world > 1 ? 2 : cpp ? 0 : 1, p->negative_samples,
+            split ? k_line<C, false, 1, 2>
+            : row_red ? k_line<C, false, 0, 3>
+            : cpp ? (shard == 2 ? k_line<C, false, 2> : shard == 1 ? k_line<C, false, 1> : k_line<C, false, 0>)
+                  : (shard == 2 ? k_line<C, true, 2> : shard == 1 ? k_line<C, true, 1> : k_line<C, true, 0>);
+        const size_t smem = batch_smem_bytes<T>(m->g->world > 1 ? (split ? 3 : 2) : cpp ? 0 : 1, p->negative_samples,
                                                 shard == 1 ? C::EPL * 32 : 0);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
@@ -40,6 +46,54 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
     });
 }
 
+
+// Rotating shards (rotation.cu): one block = the sources of vertex sub-part q (rows resident in `vslot`) x the contexts
+// this rank owns. Every row the kernel touches is in local HBM, so this is the single-GPU kernel k_line<.., SHARD = 0> fed
+// by the block's edge table: ids are already ROW indices (source: row inside the sub-part, context / negatives: local row
+// of the context shard).
+template <typename T>
+int train_line_block_t(smore_model_s* m, const smore_train_params* p, int q, void* vslot, uint64_t n_samples) {
+    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
+        using C = decltype(cfg);
+        const bool cpp = p->semantics == SMORE_SEM_CPP;
+        const bool split = p->neg_mode != SMORE_PAIRING_COUPLED;
+        void (*kern)(TrainArgs<T>) = split ? k_line<C, false, 0, 2> : cpp ? k_line<C, false, 0> : k_line<C, true, 0>;
+        const size_t smem = batch_smem_bytes<T>(split ? 3 : 2, p->negative_samples, 0);
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        Launch L;
+        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
+        else if (int rc = pick_grid(kern, smem, p->max_warps, n_samples, L)) return rc;
+        const uint64_t jobs = n_samples / (uint64_t)L.warps;
+        if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
+        // p->total = samples of ALL ranks in this episode; the schedule (sched_total / sched_offset) is in the same global unit
+        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)n_samples, 0, 0, 1, p->total ? (double)n_samples / (double)p->total : 1.0);
+        const smore_graph_s* g = m->g;
+        const int64_t off = g->blk_off[(size_t)q];
+        a.g.edge_at = g->d_eat + off;
+        a.g.edge_src = g->d_esrc + off;
+        a.g.edge_dst = g->d_edst + off;
+        a.g.n_edge_local = (uint32_t)(g->blk_off[(size_t)q + 1] - off);
+        a.g.n_neg = (uint32_t)g->n_local;
+        a.g.neg_shift = a.g.neg_rank = 0;  // negatives are local rows of the context shard
+        a.g.vsrc_at = g->d_vsub + g->vsub_off[(size_t)q];
+        a.g.n_vsrc = (uint32_t)(g->vsub_off[(size_t)q + 1] - g->vsub_off[(size_t)q]);
+        a.Wv = (T*)vslot;
+        a.Wc = (T*)m->tab[1];
+        a.same_table = 0;
+        a.jobs = jobs;
+        m->st_samples = 0;
+        m->st_ms = 0;
+        if (jobs == 0 || a.g.n_edge_local == 0) return SMORE_OK;
+        Timer t;
+        if (int rc = t.start()) return rc;
+        kern<<<L.blocks, kBlockThreads, smem>>>(a);
+        g_launches++;
+        CU(cudaGetLastError());
+        if (int rc = t.stop(&m->st_ms)) return rc;
+        m->st_samples = jobs * (uint64_t)L.warps;
+        return collect_stats(m, L.warps);
+    });
+}
 
 // MF trainer (src/model/MF.cpp:50-98): LINE's sampling loop, one table in both roles, jobs = total / workers counted from 0.
 template <typename T>

@@ -2,6 +2,7 @@
 template int train_line_t<float>(smore_model_s*, const smore_train_params*);
 template int train_line_exchange_t<float>(smore_model_s**, int, const smore_train_params*, ExchTransport&);
 template int train_mf_t<float>(smore_model_s*, const smore_train_params*);
+template int train_line_block_t<float>(smore_model_s*, const smore_train_params*, int, void*, uint64_t);
 
 // Debug hook: how many distinct SMs does a kernel launched on the carved-out update stream actually run on?
 namespace {

@@ -65,3 +65,51 @@ def gather_table(model, table: int, V: int, group=None) -> np.ndarray | None:
     for r, part in enumerate(objs):
         full[owned_rows(V, r, world)] = part
     return full
+
+
+# ---- rotating shards (include/smore_b200.h "rotating shards") ---------------------------------------------------------
+def connect_rotation(model, group=None) -> None:
+    """One process per GPU: every rank opens the slot buffers of the NEXT rank of the ring (CUDA IPC)."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    handles = exchange_handles(model.rot_ipc_handles(), group)
+    nxt = (rank + 1) % world
+    model.rot_open_next(handles[192 * nxt:192 * (nxt + 1)])
+
+
+def connect_rotation_local(models) -> None:
+    """All shards in this process (several shards on one device; tests): plain device pointers."""
+    n = len(models)
+    ptrs = [m.rot_slot_ptrs() for m in models]
+    for r, m in enumerate(models):
+        m.rot_set_next_ptrs(ptrs[(r + 1) % n])
+
+
+def train_line_rotating(models, p, episodes, first_episode=0, barrier=None, world=None, rank0=0):
+    """Runs `episodes` episodes of the block-cyclic schedule. `models`: the shard(s) driven by this process -- [model] with
+    one process per GPU (then `barrier` must synchronise the ranks, e.g. torch.distributed.barrier), or all shards of the
+    ring in rank order (tests; no barrier needed). p.total = samples of ALL ranks per episode; p.sched_total (if set) is the
+    length of the whole LR schedule in samples and the offset advances by p.total per episode; sub-streams are
+    p.stream_base + ((episode * world + rank) << 20) + warp. Returns (samples, kernel milliseconds) per model."""
+    import copy
+
+    world = world or len(models)
+    done = [0] * len(models)
+    ms = [0.0] * len(models)
+    for e in range(first_episode, first_episode + episodes):
+        for m in models:
+            m.rot_send_begin(e)
+        for i, m in enumerate(models):
+            q = copy.copy(p)
+            q.stream_base = p.stream_base + ((e * world + rank0 + i) << 20)
+            if p.sched_total:
+                q.sched_offset = p.sched_offset + (e - first_episode) * p.total
+            st = m.train_line_episode(q, e)
+            done[i] += st["samples"]
+            ms[i] += st["kernel_ms"]
+        for m in models:
+            m.rot_send_end(e)
+        if barrier is not None:
+            barrier()
+    return done, ms

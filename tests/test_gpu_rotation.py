@@ -1,0 +1,180 @@
+"""GPU: rotating shards (include/smore_b200.h "rotating shards"; smore_b200/csrc/rotation.cu). The ring is emulated on ONE
+device: all shards live in this process and hand their sub-parts over with the same cudaMemcpyAsync calls, addressed by raw
+pointers instead of CUDA-IPC mappings; the last test runs two PROCESSES on one device over real IPC handles and gloo."""
+import os
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from oracle import bindings as B
+from smore_b200 import capi
+from smore_b200 import dist as sdist
+from tests import graphs
+from tests.test_gpu_sharded import _sbm
+
+pytestmark = pytest.mark.gpu
+
+
+def _ring(off, col, ww, V, dim, world, init_v, init_c, dtype=capi.F32):
+    ms = []
+    for r in range(world):
+        gr = capi.Graph.from_csr(off, col, ww)
+        gr.set_shard_rotating(r, world)
+        mr = capi.Model(gr, dim, 2, dtype)
+        rows = sdist.owned_rows(V, r, world)
+        mr.set_rows(0, init_v[rows]), mr.set_rows(1, init_c[rows])
+        mr.enable_rotation()
+        ms.append(mr)
+    sdist.connect_rotation_local(ms)
+    return ms
+
+
+def _collect(ms, V, dim, world):
+    Wv, Wc = np.zeros((V, dim)), np.zeros((V, dim))
+    for r, mr in enumerate(ms):
+        rows = sdist.owned_rows(V, r, world)
+        Wv[rows], Wc[rows] = mr.get_rows(0), mr.get_rows(1)
+    return Wv, Wc
+
+
+def _params(total, seed, max_warps=512):
+    p = capi.default_params()
+    p.semantics, p.mode, p.seed, p.alpha, p.total, p.negative_samples = capi.SEM_CPP, capi.MODE_HOGWILD, seed, 0.025, total, 5
+    p.max_warps = max_warps
+    return p
+
+
+def test_block_tables_cover_the_edge_distribution():
+    """The blocks of all ranks partition the CSR entries, their masses sum to 1, and a block only holds sources of its
+    sub-part and contexts of its rank (checked through the sampler hook on every block of every rank)."""
+    src, dst, w = graphs.random_graph(403, 6000, seed=81)
+    off, col, ww, _ = B.edges_to_csr(src, dst, w, 1)
+    V = len(off) - 1
+    for world in (2, 4, 8):
+        tot_mass, tot_edges = 0.0, 0
+        for r in range(world):
+            g = capi.Graph.from_csr(off, col, ww)
+            info = g.set_shard_rotating(r, world)
+            ri = g.rotation_info()
+            assert ri["n_sub"] == 2 * world and info["n_local"] == len(sdist.owned_rows(V, r, world))
+            tot_mass += ri["block_mass"].sum()
+            tot_edges += int(ri["block_edges"].sum())
+            assert abs(info["source_mass_fraction"] - ri["block_mass"].sum()) < 1e-12
+        assert abs(tot_mass - 1.0) < 1e-9 and tot_edges == len(col)
+
+
+def test_full_cycle_without_training_returns_every_row_home():
+    src, dst, w = graphs.random_graph(1001, 9000, seed=83)  # odd V: shards and halves of unequal size
+    off, col, ww, _ = B.edges_to_csr(src, dst, w, 1)
+    V, dim = len(off) - 1, 24
+    rng = np.random.default_rng(4)
+    init_v, init_c = rng.random((V, dim)), rng.random((V, dim))
+    for world in (2, 4, 8):
+        ms = _ring(off, col, ww, V, dim, world, init_v, init_c, capi.F64)
+        for e in range(2 * world):
+            for m in ms:
+                m.rot_send_begin(e)
+            for m in ms:
+                m.rot_send_end(e)
+            if e + 1 < 2 * world:
+                assert not ms[0].rot_position()["at_home"]
+                with pytest.raises(capi.SmoreError):
+                    ms[0].get_rows(0)  # mid-cycle the vertex rows of this rank are somewhere else
+        Wv, Wc = _collect(ms, V, dim, world)
+        assert np.array_equal(Wv, init_v) and np.array_equal(Wc, init_c)
+        # call-order errors are reported, not executed
+        with pytest.raises(capi.SmoreError):
+            ms[0].rot_send_end(2 * world)
+        with pytest.raises(capi.SmoreError):
+            ms[0].train_line(_params(1000, 1))
+
+
+def test_init_does_not_depend_on_the_sharding():
+    src, dst, w = graphs.random_graph(301, 4000, seed=63)
+    off, col, ww, _ = B.edges_to_csr(src, dst, w, 1)
+    V = len(off) - 1
+    g0 = capi.Graph.from_csr(off, col, ww)
+    full = capi.Model(g0, 8, 2, capi.F64)
+    full.init(0, True, 77)
+    W = full.get_rows(0)
+    for world in (2, 4):
+        for r in range(world):
+            g = capi.Graph.from_csr(off, col, ww)
+            g.set_shard_rotating(r, world)
+            m = capi.Model(g, 8, 2, capi.F64)
+            m.enable_rotation()
+            m.init(0, True, 77)  # initialised in the slot buffers
+            assert np.array_equal(m.get_rows(0), W[sdist.owned_rows(V, r, world)])
+
+
+def test_blocks_train_the_right_rows():
+    """K = 0, zero contexts, tiny alpha (the sigmoid LUT stays in its 0.5 bin), vertex row v = [(v+1), 1, (v+1)^2, ...] * scale:
+    a context row then holds sum_i a_i * row(source_i). Contexts fed by ONE source vertex (second moment == squared mean)
+    must have been fed by a neighbour -- wherever that vertex' sub-part was when the block ran."""
+    off, col, ww, *_ = _sbm()
+    V, dim = len(off) - 1, 32
+    adj = {v: set(col[off[v]:off[v + 1]].tolist()) for v in range(V)}
+    ids = np.arange(V) + 1.0
+    init_v = np.full((V, dim), 1e-4)
+    init_v[:, 0], init_v[:, 2] = ids * 1e-4, ids * ids * 1e-8
+    for world in (2, 4, 8):
+        ms = _ring(off, col, ww, V, dim, world, init_v, np.zeros((V, dim)), capi.F64)
+        episodes = 2 * world
+        p = _params(30000 // episodes, 9)
+        p.negative_samples, p.alpha = 0, 1e-6
+        done, _ = sdist.train_line_rotating(ms, p, episodes)
+        assert sum(done) > 20000
+        Wv, Wc = _collect(ms, V, dim, world)
+        assert np.abs(Wv - init_v).max() < 1e-9  # K = 0 and contexts ~ 0: vertex rows barely move, and none got lost
+        hit = np.flatnonzero(Wc[:, 1] > 0)
+        mean = Wc[hit, 0] / Wc[hit, 1]
+        var = Wc[hit, 2] / Wc[hit, 1] * 1e4 - mean * mean
+        single = np.abs(var) < 1e-6 * mean * mean + 1e-9
+        x = np.round(mean[single] - 1).astype(int)
+        good = np.array([xi in adj[c] for c, xi in zip(hit[single], x)])
+        remote = (x % world) != (hit[single] % world)
+        assert remote.sum() > 1000 and good[remote].mean() > 0.995, (world, remote.sum(), good[remote].mean())
+        assert good.mean() > 0.995
+
+
+def _ipc_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from tests.test_gpu_quality import evaluate
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    off, col, ww, test_s, test_d, train_adj = _sbm()
+    V, dim, total, cycles = len(off) - 1, 32, 12_000_000, 10
+    capi.check(capi.lib().smore_init(0))  # both ranks share device 0: IPC mappings work within one device too
+    g = capi.Graph.from_csr(off, col, ww)
+    g.set_shard_rotating(rank, world)
+    m = capi.Model(g, dim, 2, capi.F32)
+    m.init(0, True, 5), m.init(1, False, 5)
+    m.enable_rotation()
+    sdist.connect_rotation(m)
+    dist.barrier()
+    episodes = cycles * 2 * world
+    p = _params(total // episodes, 17)
+    p.sched_total = total
+    done, _ = sdist.train_line_rotating([m], p, episodes, barrier=dist.barrier, world=world, rank0=rank)
+    assert m.rot_position()["at_home"]
+    Wv, Wc = sdist.gather_table(m, 0, V), sdist.gather_table(m, 1, V)
+    if rank == 0:
+        a, r = evaluate(Wv.astype(np.float64), Wc.astype(np.float64), test_s, test_d, train_adj, np.random.default_rng(2))
+        out["auc"], out["recall"] = a, r
+    out[f"samples{rank}"] = done[0]
+    dist.barrier()
+    m.close()
+    dist.destroy_process_group()
+
+
+def test_two_processes_rotate_over_cuda_ipc():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ipc_worker, args=(world, 29671, out), nprocs=world, join=True)
+    print(dict(out))
+    assert out["samples0"] > 0 and out["samples1"] > 0
+    assert out["auc"] > 0.9  # every sub-part reached the other process and came back trained

@@ -101,7 +101,35 @@ def run_unsharded(prob, dim, total, seed, max_warps):
     return evaluate_full(m.get_rows(0), m.get_rows(1), off, col, test_s, test_d)
 
 
-def run_peer(prob, dim, total, seed, world, rounds, max_warps):
+def run_rotating(prob, dim, total, seed, world, cycles, max_warps, neg_mode):
+    """Rotating shards, all shards of the ring in this process: `cycles` cycles of 2*world episodes, one LR schedule."""
+    off, col, ww, test_s, test_d = prob
+    V = len(off) - 1
+    init = ((np.random.default_rng(1).random((V, dim)) - 0.5) / dim)
+    ms = []
+    for r in range(world):
+        gr = capi.Graph.from_csr(off, col, ww)
+        gr.set_shard_rotating(r, world)
+        mr = capi.Model(gr, dim, 2, capi.F32)
+        rows = sdist.owned_rows(V, r, world)
+        mr.set_rows(0, init[rows]), mr.set_rows(1, np.zeros((len(rows), dim)))
+        mr.enable_rotation()
+        ms.append(mr)
+    sdist.connect_rotation_local(ms)
+    episodes = cycles * 2 * world
+    p = params(total // episodes, seed, max_warps)
+    p.sched_total, p.sched_offset, p.neg_mode = total, 0, neg_mode
+    done, _ = sdist.train_line_rotating(ms, p, episodes)
+    assert 0.85 * total <= sum(done) <= 1.01 * total, (sum(done), total)
+    Wv, Wc = np.zeros((V, dim)), np.zeros((V, dim))
+    for r, mr in enumerate(ms):
+        assert mr.rot_position()["at_home"]
+        rows = sdist.owned_rows(V, r, world)
+        Wv[rows], Wc[rows] = mr.get_rows(0), mr.get_rows(1)
+    return evaluate_full(Wv, Wc, off, col, test_s, test_d)
+
+
+def run_peer(prob, dim, total, seed, world, rounds, max_warps, neg_mode=capi.PAIRING_COUPLED):
     """Peer-access mode, ranks launched one after the other in `rounds` rounds (one LR schedule over all of them)."""
     off, col, ww, test_s, test_d = prob
     V = len(off) - 1
@@ -121,6 +149,7 @@ def run_peer(prob, dim, total, seed, world, rounds, max_warps):
     for k in range(rounds):
         for r, mr in enumerate(ms):
             p = params(total // rounds, seed * 1000 + k, max_warps)
+            p.neg_mode = neg_mode
             p.stream_base = r * (1 << 20)
             p.sched_total, p.sched_offset = total, k * (total // rounds)
             mr.train_line(p)
@@ -139,6 +168,8 @@ def main():
     ap.add_argument("--rounds", type=int, default=20)
     ap.add_argument("--max-warps", type=int, default=512)
     ap.add_argument("--worlds", default="2,4,8")
+    ap.add_argument("--cycles", default="5,20")
+    ap.add_argument("--what", default="occupancy,peer,rotating", help="comma list of: occupancy, peer-r2a, peer, rotating")
     args = ap.parse_args()
     prob = make_problem()
     cells = []
@@ -152,17 +183,38 @@ def main():
         print(f"{name:60s} AUC {rec['auc_mean']:.4f} +- {rec['auc_sd']:.4f}   recall@10 {rec['rec_mean']:.4f} +- {rec['rec_sd']:.4f}",
               file=sys.stderr, flush=True)
 
-    for mw in sorted({args.max_warps, 0}):
-        cell(f"unsharded max_warps={mw}", lambda s: run_unsharded(prob, args.dim, args.total, 10 + s, mw))
-    for world in [int(x) for x in args.worlds.split(",")]:
-        for vred in (0, 1):
-            for gneg in (0, 1):
-                os.environ["SMORE_SHARD_VRED"] = str(vred)
-                os.environ["SMORE_SHARD_GLOBAL_NEG"] = str(gneg)
-                cell(f"peer world={world} vred={vred} global_neg={gneg} rounds={args.rounds}",
-                     lambda s: run_peer(prob, args.dim, args.total, 100 + s, world, args.rounds, args.max_warps))
-    os.environ.pop("SMORE_SHARD_VRED", None)
-    os.environ.pop("SMORE_SHARD_GLOBAL_NEG", None)
+    worlds = [int(x) for x in args.worlds.split(",")]
+    what = set(args.what.split(","))
+    if "occupancy" in what:
+        # how many concurrent warps does a 12 k-vertex table tolerate, with plain stores and with atomic row updates?
+        for red in (0, 1):
+            os.environ["SMORE_ROW_RED"] = str(red)
+            for mw in (256, 512, 1024, 2048, 0):
+                cell(f"unsharded max_warps={mw} row_red={red}", lambda s: run_unsharded(prob, args.dim, args.total, 10 + s, mw))
+        os.environ.pop("SMORE_ROW_RED", None)
+    else:
+        cell(f"unsharded max_warps={args.max_warps}", lambda s: run_unsharded(prob, args.dim, args.total, 10 + s, args.max_warps))
+    if "peer-r2a" in what:  # the round-2a matrix: write-back and negative-table ingredients of the coupled scheme
+        for world in worlds:
+            for vred in (0, 1):
+                for gneg in (0, 1):
+                    os.environ["SMORE_SHARD_VRED"] = str(vred)
+                    os.environ["SMORE_SHARD_GLOBAL_NEG"] = str(gneg)
+                    cell(f"peer world={world} vred={vred} global_neg={gneg} coupled rounds={args.rounds}",
+                         lambda s: run_peer(prob, args.dim, args.total, 100 + s, world, args.rounds, args.max_warps))
+        os.environ.pop("SMORE_SHARD_VRED", None)
+        os.environ.pop("SMORE_SHARD_GLOBAL_NEG", None)
+    if "peer" in what:
+        for world in worlds:
+            for nm, name in ((capi.PAIRING_COUPLED, "coupled"), (capi.PAIRING_SPLIT, "split")):
+                cell(f"peer world={world} {name} rounds={args.rounds}",
+                     lambda s: run_peer(prob, args.dim, args.total, 100 + s, world, args.rounds, args.max_warps, nm))
+    if "rotating" in what:
+        for world in worlds:
+            for nm, name in ((capi.PAIRING_COUPLED, "coupled"), (capi.PAIRING_SPLIT, "split")):
+                for cycles in [int(x) for x in args.cycles.split(",")]:
+                    cell(f"rotating world={world} {name} cycles={cycles}",
+                         lambda s: run_rotating(prob, args.dim, args.total, 200 + s, world, cycles, args.max_warps, nm))
 
 
 if __name__ == "__main__":
