@@ -4,18 +4,26 @@
   python bench.py --gpus N --steps K --warmup W            # our arm: CUDA hot path through the C ABI
   python bench.py --impl reference --steps K --warmup W    # reference arm: the reference's own CPU code
 
-Workload (config.workload): BASELINE.json configs[1] -- LINE 2nd order, dim 128, K = 5 negatives, synthetic power-law
-graph with 1M vertices / 10M weighted edges (undirected -> 20M CSR entries), C++-tree semantics, fp32 tables.
-A "step" is one Hogwild pass of `--batch` edge updates (default 2^24) over that graph. Tables (2 x 512 MB) plus graph
-(~0.5 GB) exceed the 126 MB L2, so no L2 flush is needed between steps.
+N = 1 (config.workload): BASELINE.json configs[1] -- LINE 2nd order, dim 128, K = 5 negatives, synthetic power-law graph
+with 1M vertices / 10M weighted edges (undirected -> 20M CSR entries), C++-tree semantics, fp32 tables. A "step" is one
+Hogwild pass of `--batch` edge updates (default 2^24). Tables (2 x 512 MB) plus graph (~0.5 GB) exceed the 126 MB L2, so
+no L2 flush is needed between steps.
 
-value : updates/s with graph + tables resident in HBM (timed: K train calls, CUDA events on the launching stream,
-        barrier + synchronize on both sides, max over ranks).
-e2e   : the same metric through the C ABI the way a host Train() call sees it: every step uploads both embedding
-        tables from pinned HOST memory, trains, and reads the vertex table back to the host.
-roofline : algorithmic bytes per update (2*(K+2)*D*4 + 76 = 7244 B) x updates / kernel time (the
-        library's own CUDA events around the kernel) against MEASURED_PEAKS.json hbm_gbs.
-cpu_baseline : the reference's CPU implementation timed on this box's host cores on a bounded sample.
+N > 1 (default --parallelism rotating): BASELINE.json configs[4] shape -- 12.5M vertices and 250M weighted edge lines PER
+GPU (N = 8: 100M vertices / 2B edges), generated on the device (smore_graph_create_synthetic_rotating), both tables
+row-sharded, the vertex shards travelling around the ring of GPUs in 2N sub-parts ("rotating shards"): every
+update runs out of local HBM with the single-GPU kernel while the sub-part trained in the previous episode moves to the
+next GPU over NVLink (copy engines). A "step" is one full cycle of 2N episodes of `--episode-batch` updates per GPU.
+
+value : updates/s with graph + tables resident in HBM (timed: K steps, CUDA events on the launching stream, barrier +
+        synchronize on both sides, max over ranks).
+e2e   : the same metric through the C ABI the way a host Train() call sees it: every step uploads both embedding tables
+        (this rank's shards) from pinned HOST memory, trains, and reads the vertex table back to the host; the read-back
+        of step i overlaps the upload of step i+1 where the data dependences allow it (different tables).
+roofline : algorithmic bytes per update (2*(K+2)*D*4 + 76 = 7244 B; sharded runs use split samples, one more
+        row: 2*(K+3)*D*4 + 84 = 8276 B) x updates / kernel time (the library's own CUDA events around the kernel) against
+        MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline : the reference's CPU implementation timed on this box's host cores on a bounded sample (N = 1 only).
 """
 import argparse
 import json
@@ -23,7 +31,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -33,6 +40,8 @@ sys.path.insert(0, ROOT)
 
 DIM, K, V_TARGET, N_EDGES, GRAPH_SEED = 128, 5, 1_000_000, 10_000_000, 20261018
 ALGO_BYTES = 2 * (K + 2) * DIM * 4 + 76
+ALGO_BYTES_SPLIT = 2 * (K + 3) * DIM * 4 + 84  # split samples (sharded modes): second vertex row + its alias draw
+V_PER_GPU, E_PER_GPU = 12_500_000, 250_000_000  # configs[4] / 8
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -40,9 +49,66 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def workload_name(V, E):
-    return (f"LINE-2 dim={DIM} K={K} Hogwild fp32, synthetic power-law graph V={V} E_lines={E // 2} "
-            f"(undirected, {E} CSR entries) [BASELINE configs[1]]")
+def physical_cores():
+    """(physical cores, logical cpus) of this host."""
+    logical = os.cpu_count() or 1
+    try:
+        cores = set()
+        phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("physical id"):
+                phys = line.split(":")[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":")[1].strip()
+            elif not line.strip():
+                if phys is not None and core is not None:
+                    cores.add((phys, core))
+                phys = core = None
+        if cores:
+            return len(cores), logical
+    except Exception:
+        pass
+    return logical, logical
+
+
+def graph_shape(args, world):
+    """(V, E_lines) the bench graph is generated with (V is the label range; configs[1] ends up with slightly fewer used)."""
+    if world == 1 or args.parallelism != "rotating":
+        return int(V_TARGET * args.scale), int(N_EDGES * args.scale)
+    return int(V_PER_GPU * args.scale) * world, int(E_PER_GPU * args.scale) * world
+
+
+def bench_config(args, world, V=None, E=None):
+    """The `config` object of the JSON line: identical for both arms (--impl ours / reference) at the same flags."""
+    lv, le = graph_shape(args, world)
+    if world == 1:
+        wl = (f"LINE-2 dim={DIM} K={K} Hogwild, synthetic power-law graph V={V if V else lv} E_lines={le} "
+              f"(undirected, {2 * le} CSR entries) [BASELINE configs[1]]")
+        par = "single GPU"
+        upd = args.batch
+        l2 = "working set per GPU (1.0 GB of table rows + >= 0.5 GB graph) exceeds the 126 MB L2; no flush between steps"
+    elif args.parallelism == "rotating":
+        wl = (f"LINE-2 dim={DIM} K={K} Hogwild, synthetic power-law graph V={lv} E_lines={le} (undirected), generated on the "
+              f"device: {lv // world} vertices / {le // world} edge lines per GPU [BASELINE configs[4] shape: 100M vertices / 2B edges at 8 GPUs]")
+        par = (f"tables row-sharded over {world} GPUs; context shards fixed, vertex shards rotating around the ring in {2 * world} "
+               f"sub-parts (block-cyclic episodes, every update out of local HBM, sub-parts moved by copy engines over NVLink "
+               f"behind the update kernel); split samples (shard-local negatives applied to an independently drawn vertex); "
+               f"host barrier per episode, no data-path collective")
+        upd = args.episode_batch * 2 * world
+        l2 = f"working set per GPU ({lv // world * DIM * 4 * 2.5 / 1e9:.1f} GB of table rows + block tables) exceeds the 126 MB L2; no flush between steps"
+    else:
+        wl = (f"LINE-2 dim={DIM} K={K} Hogwild, synthetic power-law graph V={V if V else lv} E_lines={le} "
+              f"(undirected, {2 * le} CSR entries) [BASELINE configs[1] graph at every N]")
+        par = {"sharded": f"tables row-sharded over {world} GPUs, context-owner computes, remote vertex rows over NVLink peer "
+                          f"mappings (CUDA IPC), split samples, no data-path collective",
+               "sharded-replica": f"row-sharded over {world} GPUs, vertex rows read from a local replica refreshed every step, "
+                                  f"deltas pushed with red.global.add",
+               "sharded-exchange": f"row-sharded over {world} GPUs, remote vertex rows moved in super-batches of {args.superbatch} "
+                                   f"samples/GPU by NCCL all-to-all",
+               "replicas": f"{world} independent replicas (weak scaling)"}[args.parallelism]
+        upd = args.batch
+        l2 = "working set per GPU exceeds the 126 MB L2; no flush between steps"
+    return {"workload": wl, "updates_per_step_per_gpu": upd, "parallelism": par, "l2": l2}
 
 
 def make_graph(scale=1.0):
@@ -54,42 +120,6 @@ def make_graph(scale=1.0):
     off, col, ww, labels = synth.csr_from_edges(src, dst, w, undirected=True)
     log(f"[bench] graph: V={len(off) - 1} E={len(col)} generated in {time.time() - t0:.1f}s")
     return (src, dst, w), (off, col, ww)
-
-
-def make_graph_torch(scale, device):
-    """Same generator as smore_b200.synth.power_law_edges + csr_from_edges(undirected), on the GPU (multi-GPU runs scale
-    the graph with the number of GPUs; 80M edges are generated in about a second instead of minutes of numpy). Vertex ids
-    are the labels themselves (no first-appearance relabelling: nothing is compared with the reference at N > 1)."""
-    import torch
-
-    t0 = time.time()
-    nv, ne = int(V_TARGET * scale), int(N_EDGES * scale)
-    gen = torch.Generator(device=device)
-    gen.manual_seed(GRAPH_SEED)
-    p = torch.arange(1, nv + 1, device=device, dtype=torch.float64) ** (-1.0 / 1.5)
-    cdf = torch.cumsum(p, 0)
-    cdf /= cdf[-1].clone()
-    perm = torch.randperm(nv, device=device, generator=gen)
-
-    def endpoints():
-        u = torch.rand(ne, device=device, dtype=torch.float64, generator=gen)
-        return perm[torch.searchsorted(cdf, u, right=True).clamp_(max=nv - 1)]
-
-    src, dst = endpoints(), endpoints()
-    w = torch.randint(1, 6, (ne,), device=device, generator=gen).to(torch.float64)
-    es = torch.stack([src, dst], 1).reshape(-1)
-    ed = torch.stack([dst, src], 1).reshape(-1)
-    ew = torch.stack([w, w], 1).reshape(-1)
-    order = torch.argsort(es, stable=True)
-    col = ed[order].to(torch.int32).cpu().numpy()
-    ww = ew[order].cpu().numpy()
-    off = torch.zeros(nv + 1, dtype=torch.int64, device=device)
-    off[1:] = torch.cumsum(torch.bincount(es, minlength=nv), 0)
-    off = off.cpu().numpy()
-    del src, dst, w, es, ed, ew, order, perm, cdf, p
-    torch.cuda.empty_cache()
-    log(f"[bench] graph (torch/GPU): V={nv} E={len(col)} generated in {time.time() - t0:.1f}s")
-    return None, (off, col, ww)
 
 
 class ClockSampler:
@@ -151,13 +181,15 @@ class ClockSampler:
 class CpuReference:
     """Reference CPU path on this box's host cores: the compiled reference (kind "reference": unmodified sources, its own
     flags -Ofast -fopenmp and its own RNG) when oracle/_ref travelled here, else the oracle restatement (kind "port").
-    The graph is ingested once; timed() then runs bounded samples of LINE::Train."""
+    The graph is ingested once; timed() then runs bounded samples of LINE::Train. Threads = all logical CPUs the box
+    offers (the reference's -threads flag); the physical core count is stated next to it."""
 
-    def __init__(self, edges, csr, cores=None):
+    def __init__(self, edges, csr, threads=None):
         from oracle import bindings as B
 
         self.B = B
-        self.cores = cores or os.cpu_count() or 1
+        self.phys, self.logical = physical_cores()
+        self.threads = threads or self.logical
         self.kind = "reference" if B.ref_available(fast=True) else "port"
         if self.kind == "reference":
             src, dst, w = edges
@@ -169,7 +201,7 @@ class CpuReference:
             os.unlink(tmp.name)
             log(f"[bench] reference ingested the graph in {time.time() - t0:.1f}s (V={self.ref.V})")
             t0 = time.time()
-            self.ref.train(1, K, alpha=0.025, workers=self.cores)  # LINE::Train granularity: sample_times x 1e6 updates
+            self.ref.train(1, K, alpha=0.025, workers=self.threads)  # LINE::Train granularity: sample_times x 1e6 updates
             self.sec_per_million = time.time() - t0
         else:
             off, col, ww = csr
@@ -177,23 +209,25 @@ class CpuReference:
             rng = np.random.RandomState(0)
             self.Wv = (rng.random_sample((self.g.V, DIM)) - 0.5) / DIM
             self.Wc = np.zeros((self.g.V, DIM))
-            t = self.g.time_line_cpp(self.Wv, self.Wc, K, 0.025, 1_000_000, 1, self.cores)
+            t = self.g.time_line_cpp(self.Wv, self.Wc, K, 0.025, 1_000_000, 1, self.threads)
             self.sec_per_million = t
 
     def timed(self, seconds_target):
         s = int(max(1, min(256, seconds_target / max(self.sec_per_million, 1e-3))))
         updates = s * 1_000_000
+        where = f"{self.threads} OpenMP threads on {self.phys} physical cores ({self.logical} logical CPUs)"
         if self.kind == "reference":
             t0 = time.time()
-            self.ref.train(s, K, alpha=0.025, workers=self.cores)
+            self.ref.train(s, K, alpha=0.025, workers=self.threads)
             dt = time.time() - t0
-            what = (f"LINE::Train(sample_times={s}) = {updates} updates on the same graph, {self.cores} OpenMP threads, "
-                    f"{dt:.1f}s (compiled from the unmodified reference sources with its own flags -Ofast -fopenmp)")
+            what = (f"LINE::Train(sample_times={s}) = {updates} updates on the configs[1] graph (V=1M / 10M edge lines, fp64 tables), "
+                    f"{where}, {dt:.1f}s (compiled from the unmodified reference sources with its own flags -Ofast -fopenmp)")
         else:
-            dt = self.g.time_line_cpp(self.Wv, self.Wc, K, 0.025, updates, 1, self.cores)
-            what = (f"{updates} updates of the oracle restatement (oracle/smore_oracle.cpp, -O2 -fopenmp), "
-                    f"{self.cores} threads, {dt:.1f}s")
-        return {"value": updates / dt, "unit": "updates/s", "cores": self.cores, "kind": self.kind, "sample": what}
+            dt = self.g.time_line_cpp(self.Wv, self.Wc, K, 0.025, updates, 1, self.threads)
+            what = (f"{updates} updates of the oracle restatement (oracle/smore_oracle.cpp, -O2 -fopenmp) on the configs[1] graph, "
+                    f"{where}, {dt:.1f}s")
+        return {"value": updates / dt, "unit": "updates/s", "cores": self.phys, "threads": self.threads, "kind": self.kind,
+                "sample": what}
 
 
 def cpu_baseline(edges, csr, seconds_target=12.0):
@@ -202,9 +236,12 @@ def cpu_baseline(edges, csr, seconds_target=12.0):
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    edges, csr = make_graph(args.scale)
+    # the CPU reference always trains the configs[1] graph: it cannot load the N > 1 workload (30 M-vertex hash limit,
+    # src/proNet.h:34); its per-update cost on the largest graph it loads is what the line reports (`cpu_baseline.sample`)
+    edges, csr = make_graph(args.scale if world == 1 else 1.0)
     cpu = CpuReference(edges, csr)
     per_step = max(3.0, min(15.0, 100.0 / max(1, args.steps + args.warmup)))
     vals, secs = [], []
@@ -217,12 +254,12 @@ def run_reference(args):
             secs.append(time.time() - t0)
     v = float(np.mean(vals)) if vals else base["value"]
     base["value"] = v
-    V, E = len(csr[0]) - 1, len(csr[1])
+    V = len(csr[0]) - 1
     print(json.dumps({
         "impl": "reference", "metric": "edge_updates_per_sec", "value": v, "unit": "updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)) if secs else None,
         "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(V, E)},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": bench_config(args, world, V=V),
         "cpu_baseline": base, "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
@@ -244,44 +281,46 @@ def run_ours(args):
     json_fd = os.dup(1)
     os.dup2(2, 1)
     if world > 1:
-        # NCCL writes its version / debug lines to stdout by default; stdout must carry exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.check(capi.lib().smore_init(local))
 
-    sharded = world > 1 and args.parallelism in ("sharded", "sharded-replica", "sharded-exchange")
-    exchange = sharded and args.parallelism == "sharded-exchange"
-    # N > 1, sharded: by default every N runs the SAME configs[1] graph (updates per GPU fixed: weak scaling in work).
-    # --grow-graph grows the graph with N instead (1M vertices / 10M edges per GPU, generated on the GPU). Measured
-    # (DESIGN.md section 7): growing helps at 2 GPUs (hub rows are hit half as often per second) but the randomly accessed
-    # PEER footprint then grows too, and fine-grained peer access falls off a cliff beyond ~1 GB of peer rows.
-    grow = sharded and args.grow_graph
-    if grow:
-        edges, csr = make_graph_torch(args.scale * world, torch.device("cuda", local))
+    mode = "single" if world == 1 else args.parallelism
+    rotating = mode == "rotating"
+    sharded = mode in ("sharded", "sharded-replica", "sharded-exchange")
+    exchange, replica = mode == "sharded-exchange", mode == "sharded-replica"
+    edges = csr = None
+    t0 = time.time()
+    if rotating:
+        lv, le = graph_shape(args, world)
+        g = capi.Graph.synthetic_rotating(lv, le, GRAPH_SEED, rank, world, semantics=capi.SEM_CPP)
+        ri = g.rotation_info()
+        log(f"[bench] rank {rank}: synthetic graph V={lv} E_lines={le} -> {int(ri['block_edges'].sum())} entries in {ri['n_sub']} blocks, "
+            f"mass {ri['block_mass'].sum():.4f}, built on the device in {time.time() - t0:.1f}s")
     else:
         edges, csr = make_graph(args.scale)
-    off, col, ww = csr
-    t0 = time.time()
-    g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP)
-    replica = sharded and args.parallelism == "sharded-replica"
-    if sharded:
-        # row-sharded store: this rank owns vertices v % world == rank, computes the samples whose positive
-        # context it owns, and reaches remote vertex rows over NVLink peer mappings. No data-path collective.
-        info = g.set_shard(rank, world)
-        log(f"[bench] rank {rank}: shard {info}")
-    log(f"[bench] rank {rank}: alias tables built + uploaded in {time.time() - t0:.1f}s")
+        off, col, ww = csr
+        t0 = time.time()
+        g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP)
+        if sharded:
+            info = g.set_shard(rank, world)
+            log(f"[bench] rank {rank}: shard {info}")
+        log(f"[bench] rank {rank}: alias tables built + uploaded in {time.time() - t0:.1f}s")
     m = capi.Model(g, DIM, 2, capi.F32)
     m.init(0, True, seed=1)
     m.init(1, False, seed=1)
-    if sharded:
-        from smore_b200 import dist as sdist
+    from smore_b200 import dist as sdist
 
+    if rotating:
+        m.enable_rotation()
+        sdist.connect_rotation(m)
+        dist.barrier()
+    elif sharded:
         if exchange:
-            # bulk-exchange mode: no peer mappings; the library's own NCCL communicator carries the row batches
             sdist.init_exchange()
             m.enable_exchange(args.superbatch, args.hot_threshold)
             if args.hot_threshold >= 0:
-                sdist.connect_peers(m)  # hot (hub) rows stay single-copy behind the peer mappings
+                sdist.connect_peers(m)
         else:
             sdist.connect_peers(m)
         if replica:
@@ -296,20 +335,31 @@ def run_ours(args):
 
     p = capi.default_params()
     p.semantics, p.mode, p.seed, p.alpha = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 0.025
-    # sharded: `total` is the GLOBAL update count of the step; each rank runs its mass share (~ batch per GPU)
-    p.negative_samples, p.order, p.total = K, 2, args.batch * (world if sharded else 1)
+    p.negative_samples, p.order = K, 2
     step_no = [0]
+    episodes_per_step = 2 * world
 
     def step():
-        # fresh Philox sub-streams every step (stream ids never repeat across steps / ranks)
-        p.stream_base = (step_no[0] * world + rank) * (1 << 20)
+        """-> (samples, kernel ms) of this rank"""
+        i = step_no[0]
         step_no[0] += 1
+        if rotating:
+            # one cycle: every vertex sub-part meets every context shard once; total = samples of all ranks per episode
+            p.total = args.episode_batch * world
+            p.stream_base = 0  # (train_line_rotating derives the sub-streams from the absolute episode number and the rank)
+            done, ms = sdist.train_line_rotating([m], p, episodes_per_step, first_episode=i * episodes_per_step,
+                                                 barrier=dist.barrier, world=world, rank0=rank)
+            return done[0], ms[0]
+        # sharded: `total` is the GLOBAL update count of the step; each rank runs its mass share (~ batch per GPU)
+        p.total = args.batch * (world if sharded else 1)
+        p.stream_base = (i * world + rank) * (1 << 20)  # fresh Philox sub-streams every step / rank
         if sharded:
             dist.barrier()  # ranks enter the step together (control plane only)
         if replica:
-            m.refresh_replica(0)  # pull the authoritative vertex rows (inside the timed region), then everyone trains
+            m.refresh_replica(0)
             dist.barrier()
-        return m.train_line(p)
+        st = m.train_line(p)
+        return st["samples"], st["kernel_ms"]
 
     # ---- value: inputs resident in HBM ----
     for _ in range(args.warmup):
@@ -323,9 +373,9 @@ def run_ours(args):
     updates = 0
     kernel_ms = 0.0
     for _ in range(args.steps):
-        st = step()
-        updates += st["samples"]
-        kernel_ms += st["kernel_ms"]
+        n, kms = step()
+        updates += n
+        kernel_ms += kms
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -334,6 +384,21 @@ def run_ours(args):
 
     # ---- e2e: host buffers in, host buffers out, every step ----
     V = m.rows  # local rows (== g.V unless sharded)
+    e2e_updates, e2e_ms = 0, float("nan")
+    e2e_skip = None
+    if not args.no_e2e:
+        try:
+            import psutil
+
+            need = 3 * V * DIM * 4 * world  # three pinned buffers per rank, all ranks on this host
+            avail = psutil.virtual_memory().available
+            if need > 0.6 * avail:
+                e2e_skip = f"skipped: {need / 1e9:.0f} GB of pinned host buffers needed, {avail / 1e9:.0f} GB of host RAM available"
+        except Exception:
+            pass
+    if e2e_skip:
+        args.no_e2e = True
+        log(f"[bench] e2e leg {e2e_skip}")
     if not args.no_e2e:
         hv = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
         hc = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
@@ -341,27 +406,31 @@ def run_ours(args):
         m.get_rows(1, out=hc.numpy())
         hout = torch.empty((V, DIM), dtype=torch.float32).pin_memory()
 
-    def e2e_step():
-        m.set_rows(0, hv.numpy())
-        m.set_rows(1, hc.numpy())
-        st = step()
-        m.get_rows(0, out=hout.numpy())
-        return st
+        def e2e_step():
+            # pipeline: the context-table upload overlaps the previous step's read-back of the vertex table (PCIe is full
+            # duplex); the vertex-table upload has to wait for that read-back (same device rows)
+            m.set_rows_async(1, hc.numpy())
+            m.wait_copies(uploads=False, readbacks=True)
+            m.set_rows_async(0, hv.numpy())
+            m.wait_copies(uploads=True, readbacks=False)
+            n, _ = step()
+            m.get_rows_async(0, hout.numpy())
+            return n
 
-    e2e_updates, e2e_ms = 0, float("nan")
-    if not args.no_e2e:
         e2e_step()
+        m.wait_copies()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            e2e_updates += e2e_step()["samples"]
+            e2e_updates += e2e_step()
+        m.wait_copies()
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)
 
-    stats = torch.tensor([ms, 0.0 if args.no_e2e else e2e_ms, float(updates), float(e2e_updates), kernel_ms, float(launches)], dtype=torch.float64,
-                         device="cuda")
+    stats = torch.tensor([ms, 0.0 if args.no_e2e else e2e_ms, float(updates), float(e2e_updates), kernel_ms, float(launches)],
+                         dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -379,12 +448,14 @@ def run_ours(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
-    # dominant kernel = k_line: per-rank algorithmic bytes / its own CUDA-event time
+    # dominant kernel = k_line: per-rank algorithmic bytes / its own CUDA-event time (max over ranks)
+    split = rotating or mode == "sharded"
+    algo = ALGO_BYTES_SPLIT if split else ALGO_BYTES
     per_rank_updates = updates / world
-    achieved = per_rank_updates * ALGO_BYTES / (kernel_ms * 1e-3) / 1e9
+    achieved = per_rank_updates * algo / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_k_line.json")
-    if os.path.exists(tp):
+    if world == 1 and os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
@@ -393,26 +464,14 @@ def run_ours(args):
         "metric": "edge_updates_per_sec", "value": updates / (ms * 1e-3), "unit": "updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(g.V, g.E) + (
-                       f" -- graph grown with the GPU count ({V_TARGET} vertices / {N_EDGES} edge lines per GPU)" if grow else ""),
-                   "updates_per_step_per_gpu": args.batch,
-                   "parallelism": "single GPU" if world == 1 else (
-                       f"tables row-sharded over {world} GPUs, context-owner computes, remote vertex rows over NVLink "
-                       f"peer mappings (CUDA IPC), no data-path collective"
-                       + (" [replica mode: vertex rows read from a local replica refreshed every step, deltas pushed with "
-                          "red.global.add]" if replica else "") if sharded and not exchange
-                       else f"tables row-sharded over {world} GPUs, context-owner computes, remote vertex rows moved in "
-                            f"super-batches of {args.superbatch} samples/GPU by NCCL all-to-all (request lists, rows out, "
-                            f"rows back), owner applies the deltas; vertices expected >= {args.hot_threshold} times per super-batch "
-                            f"stay single-copy behind NVLink peer mappings ({m.exchange_stats()['hot_vertices']} of {g.V})" if exchange
-                       else f"{world} independent replicas (weak scaling)"),
-                   "l2": "working set per GPU (1.0 GB of table rows + >= 0.5 GB graph) exceeds the 126 MB L2; no flush between steps"},
+        "config": bench_config(args, world, V=g.V),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "k_line<float,4,1>", "algorithmic_bytes_per_update": ALGO_BYTES,
-                     "peak_source": peak_src},
+                     "traffic": traffic, "kernel": "k_line<float,4,1>" + (" (split samples)" if split else ""),
+                     "algorithmic_bytes_per_update": algo, "peak_source": peak_src},
         "e2e": {"value": None if args.no_e2e else e2e_updates / (e2e_ms * 1e-3), "unit": "updates/s",
-                "h2d_bytes_per_step": 2 * V * DIM * 4, "d2h_bytes_per_step": V * DIM * 4,
-                "note": "per step: both tables uploaded from pinned host memory, Train call, vertex table read back"},
+                "h2d_bytes_per_step": 2 * V * DIM * 4 * world, "d2h_bytes_per_step": V * DIM * 4 * world,
+                "note": e2e_skip or ("per step and GPU: both table shards uploaded from pinned host memory, Train call(s), vertex "
+                                     "shard read back; the read-back overlaps the next step's context-table upload")},
         "gpu_launches": int(launches), "clocks": clk,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -431,13 +490,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1 << 24, help="edge updates per step per GPU")
-    ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = configs[1])")
+    ap.add_argument("--batch", type=int, default=1 << 24, help="edge updates per step per GPU (N = 1 and the peer-access modes)")
+    ap.add_argument("--episode-batch", type=int, default=1 << 23, help="rotating: edge updates per episode per GPU (a step = 2N episodes)")
+    ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = configs[1] / configs[4] per-GPU share)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the host-buffer (e2e) leg")
-    ap.add_argument("--grow-graph", action="store_true", help="N>1: grow the graph with N (1M vertices per GPU)")
-    ap.add_argument("--parallelism", default="sharded", choices=["sharded", "sharded-replica", "sharded-exchange", "replicas"],
-                    help="N>1 only")
+    ap.add_argument("--parallelism", default="rotating",
+                    choices=["rotating", "sharded", "sharded-replica", "sharded-exchange", "replicas"], help="N>1 only")
     ap.add_argument("--superbatch", type=int, default=1 << 20, help="sharded-exchange: samples per GPU and super-batch")
     ap.add_argument("--hot-threshold", type=float, default=64.0,
                     help="sharded-exchange: expected source draws per super-batch above which a vertex keeps a single copy (<0: none)")

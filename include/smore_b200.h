@@ -123,6 +123,13 @@ int smore_model_set_rows(smore_model_t m, int table, int64_t first, int64_t n, c
 int smore_model_get_rows(smore_model_t m, int table, int64_t first, int64_t n, double* host);
 int smore_model_set_rows_f32(smore_model_t m, int table, int64_t first, int64_t n, const float* host);
 int smore_model_get_rows_f32(smore_model_t m, int table, int64_t first, int64_t n, float* host);
+/* Asynchronous variants for hosts that pipeline their own staging (fp32 models, `host` in pinned memory): uploads and
+ * read-backs are queued on two internal copy streams, so the read-back of one Train() result overlaps the upload of the
+ * next call's inputs (PCIe is full duplex). The streams do not synchronise with the trainers: call
+ * smore_model_wait_copies(m, uploads, readbacks) before training on rows being uploaded / before reading `host`. */
+int smore_model_set_rows_f32_async(smore_model_t m, int table, int64_t first, int64_t n, const float* host);
+int smore_model_get_rows_f32_async(smore_model_t m, int table, int64_t first, int64_t n, float* host);
+int smore_model_wait_copies(smore_model_t m, int uploads, int readbacks);
 /* Raw device pointer of a table (row-major [V x dim] of dtype) for zero-copy consumers on the same device. */
 int smore_model_device_ptr(smore_model_t m, int table, void** ptr);
 void smore_model_destroy(smore_model_t m);
@@ -220,6 +227,21 @@ int smore_model_rot_slot_ptrs(smore_model_t m, void** ptrs3);
 int smore_model_rot_set_next_ptrs(smore_model_t m, void* const* ptrs3);
 int smore_rot_send_begin(smore_model_t m, int64_t episode);
 /* (smore_train_line_episode is declared with the trainers below) */
+
+/* ---- device-side construction (smore_b200/csrc/device_graph.cu) --------------------------------
+ * Parallel alias-table build on the GPU: the reference's AliasMethod (src/proNet.cpp:544-620, alias.go:10-90) is a
+ * sequential two-stack sweep; this is the prefix-sum / binary-search formulation of the same sweep, O(n log n) work, no
+ * sequential step. The table is a different valid alias table of the SAME distribution (another pairing order), so it is
+ * used where no reference table exists to match: the block edge tables, shard-local negative tables and sub-part vertex
+ * tables of the row-sharded store. thr[i] = ceil(prob_i * 2^32) (0xFFFFFFFF: the bucket never takes its alias). */
+int smore_alias_build_device(const double* weights, int64_t n, uint32_t* thr, uint32_t* alias);
+/* Synthetic power-law graph of BASELINE configs[4] shape, generated on the device straight into this rank's rotating-shard
+ * tables: V vertices, E_lines undirected edge lines, line i = a pure function of (seed, i): endpoints with
+ * P(rank r) ~ r^(-2/3) relabelled by a random bijection, integer weight U{1..5}, self loops dropped. No host CSR exists
+ * (the reference could not even load such a graph: src/proNet.h:34, src/random.cpp:5): only the rotating-shard trainer
+ * and the embedding store work on the returned handle. */
+int smore_graph_create_synthetic_rotating(int64_t V, int64_t E_lines, uint64_t seed, int semantics, int rank, int world,
+                                          smore_graph_t* out);
 int smore_rot_send_end(smore_model_t m, int64_t episode);
 int smore_rot_position(smore_model_t m, int64_t* episode, int* at_home, int* training_subpart);
 

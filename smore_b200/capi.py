@@ -37,6 +37,8 @@ EXPORTS = [
     "smore_graph_set_shard_rotating", "smore_graph_rotation_info", "smore_model_enable_rotation", "smore_model_rot_ipc_handles",
     "smore_model_rot_open_next", "smore_model_rot_slot_ptrs", "smore_model_rot_set_next_ptrs", "smore_rot_send_begin",
     "smore_train_line_episode", "smore_rot_send_end", "smore_rot_position",
+    "smore_alias_build_device", "smore_graph_create_synthetic_rotating",
+    "smore_model_set_rows_f32_async", "smore_model_get_rows_f32_async", "smore_model_wait_copies",
     "smore_train_line_group", "smore_exchange_stats", "smore_debug_sm_partition", "smore_model_save_weights", "smore_format_rows",
     "smore_model_load_pretrain", "smore_model_save_checkpoint", "smore_model_load_checkpoint", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
     "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf", "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
@@ -93,6 +95,9 @@ def lib():
         for name in ("smore_model_set_rows", "smore_model_get_rows", "smore_model_set_rows_f32",
                      "smore_model_get_rows_f32"):
             getattr(L, name).argtypes = [vp, C.c_int, i64, i64, vp]
+        L.smore_model_set_rows_f32_async.argtypes = [vp, C.c_int, i64, i64, vp]
+        L.smore_model_get_rows_f32_async.argtypes = [vp, C.c_int, i64, i64, vp]
+        L.smore_model_wait_copies.argtypes = [vp, C.c_int, C.c_int]
         L.smore_model_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
         L.smore_model_destroy.argtypes = [vp]
         L.smore_model_destroy.restype = None
@@ -116,6 +121,8 @@ def lib():
         L.smore_train_line_episode.argtypes = [vp, C.POINTER(TrainParams), i64]
         L.smore_rot_send_end.argtypes = [vp, i64]
         L.smore_rot_position.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.smore_alias_build_device.argtypes = [vp, i64, vp, vp]
+        L.smore_graph_create_synthetic_rotating.argtypes = [i64, i64, u64, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
         L.smore_dist_nccl_unique_id.argtypes = [vp]
         L.smore_dist_nccl_init.argtypes = [vp, C.c_int, C.c_int]
         L.smore_dist_nccl_shutdown.argtypes = []
@@ -202,6 +209,15 @@ def format_rows(rows, first_id=0, fmt=0) -> bytes:
     return buf.raw[:need]
 
 
+def alias_build_device(weights):
+    """(thr uint32[n], alias uint32[n]) of the GPU-built alias table for `weights` (include/smore_b200.h)."""
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    thr = np.zeros(len(w), dtype=np.uint32)
+    alias = np.zeros(len(w), dtype=np.uint32)
+    check(lib().smore_alias_build_device(_ptr(w), len(w), _ptr(thr), _ptr(alias)))
+    return thr, alias
+
+
 def kernel_launches() -> int:
     return int(lib().smore_kernel_launches())
 
@@ -230,6 +246,13 @@ class Graph:
         h = vp()
         check(lib().smore_graph_load_edge_list(os.fsencode(path), int(undirected), semantics, negative_method,
                                                C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def synthetic_rotating(cls, V, E_lines, seed, rank, world, semantics=SEM_CPP):
+        """Power-law graph generated on the device into this rank's rotating-shard tables (no host CSR)."""
+        h = vp()
+        check(lib().smore_graph_create_synthetic_rotating(V, E_lines, seed, semantics, rank, world, C.byref(h)))
         return cls(h)
 
     def close(self):
@@ -359,6 +382,18 @@ class Model:
         fn = lib().smore_model_get_rows_f32 if W.dtype == np.float32 else lib().smore_model_get_rows
         check(fn(self.h, table, first, n, _ptr(W)))
         return W
+
+    def set_rows_async(self, table, W, first=0):
+        """W: float32, C-contiguous, ideally pinned. Queued on the upload stream (wait_copies before training)."""
+        assert W.dtype == np.float32 and W.flags["C_CONTIGUOUS"]
+        check(lib().smore_model_set_rows_f32_async(self.h, table, first, W.shape[0], _ptr(W)))
+
+    def get_rows_async(self, table, out, first=0):
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
+        check(lib().smore_model_get_rows_f32_async(self.h, table, first, out.shape[0], _ptr(out)))
+
+    def wait_copies(self, uploads=True, readbacks=True):
+        check(lib().smore_model_wait_copies(self.h, int(uploads), int(readbacks)))
 
     def ipc_handle(self, table) -> bytes:
         buf = (C.c_ubyte * 64)()

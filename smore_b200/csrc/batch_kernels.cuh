@@ -278,8 +278,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_apply_delta(typename C::T* __
 // except the rows of HOT vertices (ExchDev::hot), which are reached through the peer mappings.
 // KIND: 0 = skip-gram pair update (LINE), 1 = MF: the same sampling loop around UpdateFactorizedPair (MF::Train,
 // src/model/MF.cpp:70-92, draws exactly what LINE::Train draws), 2 = LINE with split samples (row-sharded modes only:
-// update_pair_split, the K negatives go to a second, independently drawn vertex), 3 = LINE (C++ semantics) with atomic
-// row updates (red.global.add of every delta; experiment, SMORE_ROW_RED=1).
+// update_pair_split, the K negatives go to a second, independently drawn vertex).
 template <class C, bool GO, int SHARD, int KIND = 0>
 __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
     constexpr bool STAGED = SHARD == 1;
@@ -373,7 +372,6 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
             const bool same = SHARD == 2 ? false : a.same_table != 0;
             if constexpr (KIND == 1) update_factorized_pair<C, TV, TC>(tv, tc, a.dim, same, v1, my, nrows, alpha, a.lambda, lane);
             else if constexpr (KIND == 2) update_pair_split<C, TV, TC>(tv, tc, a.dim, lut, v1, sid[a.K + 2], my, nrows, alpha, lane, staged ? &vrow : nullptr, SHARD == 1 && a.vred != 0);
-            else if constexpr (KIND == 3) update_pair_cpp<C, TV, TC, false, true>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane);
             else if (!GO) update_pair_cpp<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush, SHARD == 1 && a.vred != 0);
             else update_pair_go<C, TV, TC, SHARD != 0>(tv, tc, a.dim, same, a.order == 1, lut, v1, my, nrows, alpha, lane, staged ? &vrow : nullptr, vpush, SHARD == 1 && a.vred != 0);
             st.count++;

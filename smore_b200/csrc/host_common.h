@@ -76,6 +76,7 @@ struct smore_graph_s {
     // sub-parts that travel around the ring of ranks; d_eat / d_esrc / d_edst then hold one edge table PER BLOCK
     // (sub-part q of the sources x this rank's contexts), block q at [blk_off[q], blk_off[q+1])
     bool rotating = false;
+    bool synthetic = false;           // generated on the device (device_graph.cu): no host CSR, names or host alias tables
     int nsub = 0;
     int64_t sub_cap = 0;              // rows of a slot buffer: first half of a shard = local rows [0, sub_cap)
     std::vector<int64_t> blk_off;     // nsub + 1
@@ -137,6 +138,7 @@ struct smore_model_s {
     void* replica[2] = {nullptr, nullptr};     // optional full-size local read replica of a sharded table
     smore_exchange_s* xch = nullptr;           // bulk-exchange mode of a sharded model (smore_model_enable_exchange)
     smore_rotation_s* rot = nullptr;           // rotating vertex table (smore_model_enable_rotation): tab[0] == nullptr then
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // smore_model_{set,get}_rows_f32_async
     WarpState* d_state = nullptr;
     int state_cap = 0;
     int32_t* d_keys = nullptr;
@@ -151,6 +153,8 @@ struct smore_model_s {
                 if (peer_opened[t][r]) cudaIpcCloseMemHandle(peer[t][r]);
         cudaFree(tab[0]); cudaFree(tab[1]); cudaFree(d_state); cudaFree(d_keys);
         cudaFree(replica[0]); cudaFree(replica[1]);
+        if (h2d_stream) cudaStreamDestroy(h2d_stream);
+        if (d2h_stream) cudaStreamDestroy(d2h_stream);
         delete xch;
         delete rot;
     }

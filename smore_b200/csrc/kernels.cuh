@@ -79,9 +79,16 @@ struct TrainArgs {
 // my_id: lane 0 holds the positive context, lane 1+n negative n; nrows = K+1 <= 32.
 // ---------------------------------------------------------------------------------------------------------------
 // CTX_CA: gather the context rows with ld.global.ca (hub rows served from L1; used when sharding concentrates them)
-// RED: every row takes its delta with red.global.add instead of a store of the updated copy (atomic Hogwild: concurrent
-// updates of a row are never lost, only computed from slightly stale values).
-template <class C, class TV, class TC, bool CTX_CA = false, bool RED = false>
+// Atomic rows (kAtomicRows<C>: the fp32 throughput tables): every row takes its DELTA with red.global.add.v4.f32 instead of
+// a store of the updated copy. Concurrent updates of a row are then never lost, only computed from slightly stale values --
+// with plain stores a table of 24 k rows trained by 3 552 resident warps loses so many updates that held-out AUC drops from
+// 0.92 to 0.81 (profiles/r2b_ab_sharded_quality.txt) -- and the kernel gets faster (803 vs 775 M updates/s on configs[1]:
+// the updated copy no longer has to stay in registers until the store, and the write needs no ownership of the line).
+// fp64 tables keep the store path: it reproduces the reference's in-place arithmetic bit for bit (DETERMINISTIC parity).
+template <class C>
+constexpr bool kAtomicRows = sizeof(typename C::T) == 4;
+
+template <class C, class TV, class TC, bool CTX_CA = false, bool RED = kAtomicRows<C>>
 __device__ __forceinline__ void update_pair_cpp(const TV& tv,
                                                 const TC& tc, int dim, bool same_table,
                                                 const typename C::T* lut, int v1, int my_id, int nrows,
@@ -152,11 +159,14 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
 #pragma unroll
             for (int e = 0; e < C::EPL; ++e) {
                 back.x[e] = A::madd(back.x[e], g, c.x[e]);
-                c.x[e] = A::madd(c.x[e], g, v.x[e]);
+                if constexpr (RED) c.x[e] = A::mul(g, v.x[e]);
+                else c.x[e] = A::madd(c.x[e], g, v.x[e]);
             }
-            c.store(pc, lane, dim);
+            // (a lane's accesses to one address stay in program order, so the next round's load sees this update)
+            if constexpr (RED) row_red_add<C>(pc, c, lane, dim);
+            else c.store(pc, lane, dim);
         }
-        if (vred) row_red_add<C>(pv, back, lane, dim);
+        if (RED || vred) row_red_add<C>(pv, back, lane, dim);
         else {
             Row<C> v;
             v.load(pv, lane, dim);
@@ -173,7 +183,7 @@ __device__ __forceinline__ void update_pair_cpp(const TV& tv,
 // skip_source, LINE.updateFirstOrder (internal/models/line/line.go:153-200). Negatives equal to the context (or the
 // source) are skipped; the positive context row is written last.
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, class TV, class TC, bool CTX_CA = false>
+template <class C, class TV, class TC, bool CTX_CA = false, bool RED = kAtomicRows<C>>
 __device__ __forceinline__ void update_pair_go(const TV& tv,
                                                 const TC& tc, int dim, bool same_table,
                                                bool skip_source, const typename C::T* lut, int v1, int my_id,
@@ -227,20 +237,27 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
 #pragma unroll
                     for (int e = 0; e < C::EPL; ++e) {
                         vgrad.x[e] = A::madd(vgrad.x[e], g, c[r].x[e]);
-                        c[r].x[e] = A::add(c[r].x[e], A::mul(g, v.x[e]));  // wContext[neg] += negGrad
+                        if constexpr (RED) c[r].x[e] = A::mul(g, v.x[e]);
+                        else c[r].x[e] = A::add(c[r].x[e], A::mul(g, v.x[e]));  // wContext[neg] += negGrad
                     }
-                    c[r].store(tc.row(ids[r]), lane, dim);
+                    if constexpr (RED) row_red_add<C>(tc.row(ids[r]), c[r], lane, dim);
+                    else c[r].store(tc.row(ids[r]), lane, dim);
                 }
             }
         }
+        if constexpr (RED) {
+            row_red_add<C>(pv, vgrad, lane, dim);
+            row_red_add<C>(pp, cgrad, lane, dim);
+        } else {
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) {
-            v.x[e] = A::add(v.x[e], vgrad.x[e]);
-            pos.x[e] = A::add(pos.x[e], cgrad.x[e]);
+            for (int e = 0; e < C::EPL; ++e) {
+                v.x[e] = A::add(v.x[e], vgrad.x[e]);
+                pos.x[e] = A::add(pos.x[e], cgrad.x[e]);
+            }
+            if (vred) row_red_add<C>(pv, vgrad, lane, dim);  // see update_pair_cpp
+            else v.store(pv, lane, dim);
+            pos.store(pp, lane, dim);
         }
-        if (vred) row_red_add<C>(pv, vgrad, lane, dim);  // see update_pair_cpp
-        else v.store(pv, lane, dim);
-        pos.store(pp, lane, dim);
         if (vpush) row_red_add<C>(vpush, vgrad, lane, dim);
     } else {
         Row<C> vgrad, cgrad;
@@ -266,13 +283,15 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
 #pragma unroll
             for (int e = 0; e < C::EPL; ++e) {
                 vgrad.x[e] = A::madd(vgrad.x[e], g, c.x[e]);
-                c.x[e] = A::add(c.x[e], A::mul(g, v.x[e]));
+                if constexpr (RED) c.x[e] = A::mul(g, v.x[e]);
+                else c.x[e] = A::add(c.x[e], A::mul(g, v.x[e]));
             }
-            c.store(pc, lane, dim);
+            if constexpr (RED) row_red_add<C>(pc, c, lane, dim);
+            else c.store(pc, lane, dim);
         }
         // per element: vertex row first, then context row (optimizer.go:54-57), through memory so that
         // a self pair on a shared table accumulates both.
-        if (vred) row_red_add<C>(pv, vgrad, lane, dim);
+        if (RED || vred) row_red_add<C>(pv, vgrad, lane, dim);
         else {
             Row<C> v;
             v.load(pv, lane, dim);
@@ -281,11 +300,14 @@ __device__ __forceinline__ void update_pair_go(const TV& tv,
             v.store(pv, lane, dim);
         }
         if (vpush) row_red_add<C>(vpush, vgrad, lane, dim);
-        Row<C> pos;
-        pos.load(pp, lane, dim);
+        if constexpr (RED) row_red_add<C>(pp, cgrad, lane, dim);
+        else {
+            Row<C> pos;
+            pos.load(pp, lane, dim);
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) pos.x[e] = A::add(pos.x[e], cgrad.x[e]);
-        pos.store(pp, lane, dim);
+            for (int e = 0; e < C::EPL; ++e) pos.x[e] = A::add(pos.x[e], cgrad.x[e]);
+            pos.store(pp, lane, dim);
+        }
     }
 }
 
@@ -306,6 +328,7 @@ __device__ __forceinline__ void update_pair_split(const TV& tv, const TC& tc, in
                                                   const Row<C>* vpre, bool vred) {
     using T = typename C::T;
     using A = Ar<T>;
+    constexpr bool RED = kAtomicRows<C>;
     const bool active = lane < nrows;
     const unsigned peers = __match_any_sync(kFull, active ? my_id : (-1 - lane));
     const bool dup = __any_sync(kFull, active && __popc(peers) > 1) || v1 == v2;
@@ -313,29 +336,35 @@ __device__ __forceinline__ void update_pair_split(const TV& tv, const TC& tc, in
     T* pv2 = tv.row(v2);
     const int ctx = __shfl_sync(kFull, my_id, 0);
     T* pp = tc.row(ctx);
+    // one pair: row `c` of the context table against vertex row `v`; the vertex delta accumulates in `back`
+    auto pair = [&](const Row<C>& v, Row<C>& c, T* pc, T label, T f, Row<C>& back) {
+        const T g = A::mul(A::sub(label, fast_sigmoid<T>(lut, f)), alpha);
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) {
+            back.x[e] = A::madd(back.x[e], g, c.x[e]);
+            if constexpr (RED) c.x[e] = A::mul(g, v.x[e]);
+            else c.x[e] = A::madd(c.x[e], g, v.x[e]);
+        }
+        if constexpr (RED) row_red_add<C>(pc, c, lane, dim);
+        else c.store(pc, lane, dim);
+    };
+    auto vertex = [&](Row<C>& v, T* pv, const Row<C>& back) {
+        if (RED || vred) row_red_add<C>(pv, back, lane, dim);
+        else {
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
+            v.store(pv, lane, dim);
+        }
+    };
     if (!dup) {
-        Row<C> a, b, pos;
+        Row<C> a, b, pos, back;
         if (vpre) a = *vpre;
         else a.load(pv1, lane, dim);
         b.load(pv2, lane, dim);
         pos.load(pp, lane, dim);
-        {   // positive pair: v1 <-> ctx
-            const T g = A::mul(A::sub((T)1, fast_sigmoid<T>(lut, dot(a, pos))), alpha);
-            Row<C> d;
-#pragma unroll
-            for (int e = 0; e < C::EPL; ++e) {
-                d.x[e] = A::mul(g, pos.x[e]);
-                pos.x[e] = A::madd(pos.x[e], g, a.x[e]);
-            }
-            pos.store(pp, lane, dim);
-            if (vred) row_red_add<C>(pv1, d, lane, dim);
-            else {
-#pragma unroll
-                for (int e = 0; e < C::EPL; ++e) a.x[e] = A::add(a.x[e], d.x[e]);
-                a.store(pv1, lane, dim);
-            }
-        }
-        Row<C> back;
+        back.zero();
+        pair(a, pos, pp, (T)1, dot(a, pos), back);  // positive pair: v1 <-> ctx
+        vertex(a, pv1, back);
         back.zero();
         for (int base = 1; base < nrows; base += kCtxChunk) {
             Row<C> c[kCtxChunk];
@@ -348,47 +377,21 @@ __device__ __forceinline__ void update_pair_split(const TV& tv, const TC& tc, in
             T f[kCtxChunk];
             dots<C, kCtxChunk>(b, c, nrows - base, f);
 #pragma unroll
-            for (int r = 0; r < kCtxChunk; ++r) {
-                if (base + r < nrows) {
-                    const T g = A::mul(A::sub((T)0, fast_sigmoid<T>(lut, f[r])), alpha);
-#pragma unroll
-                    for (int e = 0; e < C::EPL; ++e) {
-                        back.x[e] = A::madd(back.x[e], g, c[r].x[e]);
-                        c[r].x[e] = A::madd(c[r].x[e], g, b.x[e]);
-                    }
-                    c[r].store(tc.row(ids[r]), lane, dim);
-                }
-            }
+            for (int r = 0; r < kCtxChunk; ++r)
+                if (base + r < nrows) pair(b, c[r], tc.row(ids[r]), (T)0, f[r], back);
         }
-        if (nrows > 1) {
-            if (vred) row_red_add<C>(pv2, back, lane, dim);
-            else {
-#pragma unroll
-                for (int e = 0; e < C::EPL; ++e) b.x[e] = A::add(b.x[e], back.x[e]);
-                b.store(pv2, lane, dim);
-            }
-        }
+        if (nrows > 1) vertex(b, pv2, back);
     } else {
         // some rows coincide: one pair at a time through memory
+        Row<C> back;
         {
-            Row<C> a, pos, d;
+            Row<C> a, pos;
             a.load(pv1, lane, dim);
             pos.load(pp, lane, dim);
-            const T g = A::mul(A::sub((T)1, fast_sigmoid<T>(lut, dot(a, pos))), alpha);
-#pragma unroll
-            for (int e = 0; e < C::EPL; ++e) {
-                d.x[e] = A::mul(g, pos.x[e]);
-                pos.x[e] = A::madd(pos.x[e], g, a.x[e]);
-            }
-            pos.store(pp, lane, dim);
-            if (vred) row_red_add<C>(pv1, d, lane, dim);
-            else {
-#pragma unroll
-                for (int e = 0; e < C::EPL; ++e) a.x[e] = A::add(a.x[e], d.x[e]);
-                a.store(pv1, lane, dim);
-            }
+            back.zero();
+            pair(a, pos, pp, (T)1, dot(a, pos), back);
+            vertex(a, pv1, back);
         }
-        Row<C> back;
         back.zero();
         for (int r = 1; r < nrows; ++r) {
             const int cid = __shfl_sync(kFull, my_id, r);
@@ -396,23 +399,12 @@ __device__ __forceinline__ void update_pair_split(const TV& tv, const TC& tc, in
             Row<C> b, c;
             b.load(pv2, lane, dim);
             c.load(pc, lane, dim);
-            const T g = A::mul(A::sub((T)0, fast_sigmoid<T>(lut, dot(b, c))), alpha);
-#pragma unroll
-            for (int e = 0; e < C::EPL; ++e) {
-                back.x[e] = A::madd(back.x[e], g, c.x[e]);
-                c.x[e] = A::madd(c.x[e], g, b.x[e]);
-            }
-            c.store(pc, lane, dim);
+            pair(b, c, pc, (T)0, dot(b, c), back);
         }
         if (nrows > 1) {
-            if (vred) row_red_add<C>(pv2, back, lane, dim);
-            else {
-                Row<C> b;
-                b.load(pv2, lane, dim);
-#pragma unroll
-                for (int e = 0; e < C::EPL; ++e) b.x[e] = A::add(b.x[e], back.x[e]);
-                b.store(pv2, lane, dim);
-            }
+            Row<C> b;
+            if (!(RED || vred)) b.load(pv2, lane, dim);
+            vertex(b, pv2, back);
         }
     }
 }
@@ -614,9 +606,11 @@ __device__ __forceinline__ void update_community_step(const TV& tv, const TC& tc
                     for (int e = 0; e < C::EPL; ++e) {
                         const T ce = c[r].x[e];
                         back.x[e] = A::add(back.x[e], A::mul(alpha, A::sub(A::mul(g, ce), A::mul(reg, v.x[e]))));
-                        c[r].x[e] = A::add(ce, A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce))));
+                        const T dc = A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce)));
+                        c[r].x[e] = kAtomicRows<C> ? dc : A::add(ce, dc);
                     }
-                    c[r].store(tc.row(ids[r]), lane, dim);
+                    if constexpr (kAtomicRows<C>) row_red_add<C>(tc.row(ids[r]), c[r], lane, dim);
+                    else c[r].store(tc.row(ids[r]), lane, dim);
                 }
             }
         }
@@ -632,14 +626,19 @@ __device__ __forceinline__ void update_community_step(const TV& tv, const TC& tc
             for (int e = 0; e < C::EPL; ++e) {
                 const T ce = c.x[e];
                 back.x[e] = A::add(back.x[e], A::mul(alpha, A::sub(A::mul(g, ce), A::mul(reg, v.x[e]))));
-                c.x[e] = A::add(ce, A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce))));
+                const T dc = A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce)));
+                c.x[e] = kAtomicRows<C> ? dc : A::add(ce, dc);
             }
-            c.store(pc, lane, dim);
+            if constexpr (kAtomicRows<C>) row_red_add<C>(pc, c, lane, dim);
+            else c.store(pc, lane, dim);
         }
     }
+    if constexpr (kAtomicRows<C>) row_red_add<C>(pv, back, lane, dim);
+    else {
 #pragma unroll
-    for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
-    v.store(pv, lane, dim);
+        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
+        v.store(pv, lane, dim);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -683,15 +682,20 @@ __device__ __forceinline__ void update_factorized_pair(const TV& tv, const TC& t
                     for (int e = 0; e < C::EPL; ++e) {
                         const T ce = c[r].x[e];
                         back.x[e] = A::add(back.x[e], A::mul(alpha, A::sub(A::mul(g, ce), A::mul(reg, v.x[e]))));
-                        c[r].x[e] = A::add(ce, A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce))));
+                        const T dc = A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce)));
+                        c[r].x[e] = kAtomicRows<C> ? dc : A::add(ce, dc);
                     }
-                    c[r].store(tc.row(ids[r]), lane, dim);
+                    if constexpr (kAtomicRows<C>) row_red_add<C>(tc.row(ids[r]), c[r], lane, dim);
+                    else c[r].store(tc.row(ids[r]), lane, dim);
                 }
             }
         }
+        if constexpr (kAtomicRows<C>) row_red_add<C>(pv, back, lane, dim);
+        else {
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
-        v.store(pv, lane, dim);
+            for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
+            v.store(pv, lane, dim);
+        }
     } else {
         for (int r = 0; r < nrows; ++r) {
             const int cid = __shfl_sync(kFull, my_id, r);
@@ -705,15 +709,20 @@ __device__ __forceinline__ void update_factorized_pair(const TV& tv, const TC& t
             for (int e = 0; e < C::EPL; ++e) {
                 const T ce = c.x[e];
                 back.x[e] = A::add(back.x[e], A::mul(alpha, A::sub(A::mul(g, ce), A::mul(reg, v.x[e]))));
-                c.x[e] = A::add(ce, A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce))));
+                const T dc = A::mul(alpha, A::sub(A::mul(g, v.x[e]), A::mul(reg, ce)));
+                c.x[e] = kAtomicRows<C> ? dc : A::add(ce, dc);
             }
-            c.store(pc, lane, dim);
+            if constexpr (kAtomicRows<C>) row_red_add<C>(pc, c, lane, dim);
+            else c.store(pc, lane, dim);
         }
-        Row<C> v;
-        v.load(pv, lane, dim);
+        if constexpr (kAtomicRows<C>) row_red_add<C>(pv, back, lane, dim);
+        else {
+            Row<C> v;
+            v.load(pv, lane, dim);
 #pragma unroll
-        for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
-        v.store(pv, lane, dim);
+            for (int e = 0; e < C::EPL; ++e) v.x[e] = A::add(v.x[e], back.x[e]);
+            v.store(pv, lane, dim);
+        }
     }
 }
 

@@ -326,6 +326,7 @@ int smore_edge_list_to_csr(const char* path, int undirected, int64_t* V, int64_t
 
 int smore_graph_set_field(smore_graph_t g, const int32_t* field) {
     if (!g || !field) return fail(SMORE_E_INVALID, "null argument");
+    if (g->synthetic) return fail(SMORE_E_UNSUPPORTED, "this graph was generated on the device (no host CSR / reference tables): only the rotating-shard trainer works on it");
     g->field.assign(field, field + g->V);
     g->has_field = true;
     CU(cudaMemcpy(g->d_field, g->field.data(), (size_t)g->V * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -362,6 +363,7 @@ int smore_graph_info(smore_graph_t g, int64_t* V, int64_t* E, int64_t* n_lines) 
 
 int smore_graph_get_csr(smore_graph_t g, int64_t* row_off, int32_t* col, double* weight) {
     if (!g) return fail(SMORE_E_INVALID, "null graph");
+    if (g->synthetic) return fail(SMORE_E_UNSUPPORTED, "this graph was generated on the device (no host CSR / reference tables): only the rotating-shard trainer works on it");
     if (row_off) memcpy(row_off, g->row_off.data(), g->row_off.size() * sizeof(int64_t));
     if (col) memcpy(col, g->col.data(), g->col.size() * sizeof(int32_t));
     if (weight) memcpy(weight, g->w.data(), g->w.size() * sizeof(double));
@@ -375,6 +377,7 @@ const char* smore_graph_vertex_name(smore_graph_t g, int64_t vid) {
 
 int smore_graph_get_alias(smore_graph_t g, int which, double* prob, int64_t* alias) {
     if (!g) return fail(SMORE_E_INVALID, "null graph");
+    if (g->synthetic) return fail(SMORE_E_UNSUPPORTED, "this graph was generated on the device (no host CSR / reference tables): only the rotating-shard trainer works on it");
     const AliasHost* t = which == SMORE_AT_VERTEX ? &g->vertex_at : which == SMORE_AT_NEGATIVE ? &g->negative_at : which == SMORE_AT_CONTEXT ? &g->ctx_at : nullptr;
     if (!t) return fail(SMORE_E_INVALID, "bad table selector");
     if (which == SMORE_AT_CONTEXT && g->sem != SMORE_SEM_CPP) return fail(SMORE_E_UNSUPPORTED, "context alias table exists only under C++ semantics");
@@ -385,6 +388,7 @@ int smore_graph_get_alias(smore_graph_t g, int which, double* prob, int64_t* ali
 
 int smore_graph_get_field(smore_graph_t g, int32_t* field) {
     if (!g || !field) return fail(SMORE_E_INVALID, "null argument");
+    if (g->synthetic) return fail(SMORE_E_UNSUPPORTED, "this graph was generated on the device (no host CSR / reference tables): only the rotating-shard trainer works on it");
     memcpy(field, g->field.data(), g->field.size() * sizeof(int32_t));
     return SMORE_OK;
 }
@@ -394,6 +398,7 @@ void smore_graph_destroy(smore_graph_t g) { delete g; }
 int smore_sample_debug(smore_graph_t g, int which, uint64_t seed, uint64_t stream, int64_t n, const int64_t* arg,
                        int64_t* out, uint64_t* words_used) {
     if (!g || !out || n < 0) return fail(SMORE_E_INVALID, "bad argument");
+    if (g->synthetic) return fail(SMORE_E_UNSUPPORTED, "this graph was generated on the device (no host CSR / reference tables): only the rotating-shard trainer works on it");
     if (which < 0 || which > 3) return fail(SMORE_E_INVALID, "bad sampler selector");
     if (which == SMORE_SAMPLE_TARGET && !arg) return fail(SMORE_E_INVALID, "TARGET needs source vertices");
     if (int rc = ensure_device()) return rc;
@@ -420,6 +425,7 @@ int smore_sample_debug(smore_graph_t g, int which, uint64_t seed, uint64_t strea
 int smore_walk_debug(smore_graph_t g, uint64_t seed, uint64_t stream, int64_t start, int steps, int mode, int w0, int w1,
                      int64_t* walk, int64_t* walk_len, int64_t* pair_v, int64_t* pair_c, int64_t cap, int64_t* n_pairs) {
     if (!g || !walk || !walk_len || !n_pairs) return fail(SMORE_E_INVALID, "null argument");
+    if (g->synthetic) return fail(SMORE_E_UNSUPPORTED, "this graph was generated on the device (no host CSR / reference tables): only the rotating-shard trainer works on it");
     if (start < 0 || start >= g->V) return fail(SMORE_E_INVALID, "start out of range");
     if (steps < 0 || steps + 1 > kMaxWalkLen) return fail(SMORE_E_UNSUPPORTED, "walk_steps must be < %d", kMaxWalkLen);
     if (mode == 0 && (w0 < 1 || w0 > 255)) return fail(SMORE_E_INVALID, "window must be in [1,255]");
@@ -476,6 +482,7 @@ int smore_model_create(smore_graph_t g, int dim, int n_tables, int dtype, smore_
 // ---- row sharding across the GPUs of one box (one process per GPU) ---------------------------------------------------
 int smore_graph_set_shard(smore_graph_t g, int rank, int world) {
     if (!g) return fail(SMORE_E_INVALID, "null graph");
+    if (g->synthetic) return fail(SMORE_E_UNSUPPORTED, "this graph was generated on the device (no host CSR / reference tables): only the rotating-shard trainer works on it");
     if (world < 1 || world > kMaxWorld || (world & (world - 1))) return fail(SMORE_E_INVALID, "world must be 1, 2, 4 or 8");
     if (rank < 0 || rank >= world) return fail(SMORE_E_INVALID, "rank out of range");
     if (g->n_models > 0) return fail(SMORE_E_INVALID, "%d model(s) were already created on this graph: their row counts are fixed at creation, shard the graph first", g->n_models);
@@ -603,6 +610,7 @@ int smore_model_open_peers(smore_model_t m, int table, const void* handles) {
 int smore_model_enable_replica(smore_model_t m, int table) {
     if (!m || table < 0 || table >= m->n_tables) return fail(SMORE_E_INVALID, "bad model/table");
     if (m->g->world == 1) return fail(SMORE_E_INVALID, "replicas only make sense on a row-sharded graph");
+    if (m->g->rotating) return fail(SMORE_E_INVALID, "the graph is set up for rotating shards");
     if (((size_t)m->dim * m->elem()) % 16) return fail(SMORE_E_UNSUPPORTED, "replica rows must be a multiple of 16 bytes");
     if (int rc = ensure_device()) return rc;
     if (!m->replica[table]) {
@@ -674,6 +682,41 @@ int smore_model_set_rows_f32(smore_model_t m, int table, int64_t first, int64_t 
 }
 int smore_model_get_rows_f32(smore_model_t m, int table, int64_t first, int64_t n, float* host) {
     return rows_io<float>(m, table, first, n, host, false);
+}
+
+// Asynchronous row transfers for hosts that pipeline their own staging (bench.py's end-to-end leg: the read-back of step i
+// overlaps the upload of step i+1 -- PCIe is full duplex). fp32 models only, no dtype conversion; `host` should be pinned
+// (page-locked) memory, otherwise the copies degrade to synchronous ones. Uploads and read-backs run on two internal
+// streams that do not synchronise with the trainers: call smore_model_wait_copies before training on rows that are being
+// uploaded, and before touching host memory that is being filled.
+static int async_rows(smore_model_t m, int table, int64_t first, int64_t n, float* host, bool to_device) {
+    if (!m || table < 0 || table >= m->n_tables || !host) return fail(SMORE_E_INVALID, "bad model/table/buffer");
+    if (m->dtype != SMORE_F32) return fail(SMORE_E_UNSUPPORTED, "asynchronous row transfers exist for fp32 models only");
+    if (first < 0 || n < 0 || first + n > m->rows) return fail(SMORE_E_INVALID, "row range out of bounds (the model holds %lld rows)", (long long)m->rows);
+    if (n == 0) return SMORE_OK;
+    if (int rc = ensure_device()) return rc;
+    cudaStream_t& st = to_device ? m->h2d_stream : m->d2h_stream;
+    if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t row_bytes = (size_t)m->dim * sizeof(float);
+    const int64_t first0 = first;
+    return for_row_ranges(m, table, first, n, [&](char* dptr, int64_t f, int64_t k) -> int {
+        char* h = (char*)host + (size_t)(f - first0) * row_bytes;
+        if (to_device) CU(cudaMemcpyAsync(dptr, h, (size_t)k * row_bytes, cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpyAsync(h, dptr, (size_t)k * row_bytes, cudaMemcpyDeviceToHost, st));
+        return SMORE_OK;
+    });
+}
+int smore_model_set_rows_f32_async(smore_model_t m, int table, int64_t first, int64_t n, const float* host) {
+    return async_rows(m, table, first, n, const_cast<float*>(host), true);
+}
+int smore_model_get_rows_f32_async(smore_model_t m, int table, int64_t first, int64_t n, float* host) {
+    return async_rows(m, table, first, n, host, false);
+}
+int smore_model_wait_copies(smore_model_t m, int uploads, int readbacks) {
+    if (!m) return fail(SMORE_E_INVALID, "null model");
+    if (uploads && m->h2d_stream) CU(cudaStreamSynchronize(m->h2d_stream));
+    if (readbacks && m->d2h_stream) CU(cudaStreamSynchronize(m->d2h_stream));
+    return SMORE_OK;
 }
 
 int smore_model_device_ptr(smore_model_t m, int table, void** ptr) {
@@ -927,6 +970,7 @@ int smore_model_enable_exchange(smore_model_t m, int64_t superbatch, double hot_
     if (!m) return fail(SMORE_E_INVALID, "null model");
     smore_graph_s* g = m->g;
     if (g->world == 1) return fail(SMORE_E_INVALID, "the exchange mode only makes sense on a row-sharded graph");
+    if (g->rotating || g->synthetic) return fail(SMORE_E_INVALID, "the graph is set up for rotating shards");
     if (superbatch <= 0) superbatch = 1 << 20;
     if (superbatch > (1ll << 27)) return fail(SMORE_E_INVALID, "superbatch must be <= 2^27 samples");
     if (int rc = ensure_device()) return rc;

@@ -12,11 +12,8 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
         const int shard = m->g->world == 1 ? 0 : (m->replica[vtab] ? 2 : 1);
         // peer-access mode, LINE-2: split samples by default (neg_mode 1 = the coupled round-1 scheme)
         const bool split = shard == 1 && vtab != ctab && p->neg_mode != SMORE_PAIRING_COUPLED;
-        const char* rr = getenv("SMORE_ROW_RED");
-        const bool row_red = rr && atoi(rr) != 0 && shard == 0 && cpp && p->mode == SMORE_MODE_HOGWILD;
         void (*kern)(TrainArgs<T>) =
             split ? k_line<C, false, 1, 2>
-            : row_red ? k_line<C, false, 0, 3>
             : cpp ? (shard == 2 ? k_line<C, false, 2> : shard == 1 ? k_line<C, false, 1> : k_line<C, false, 0>)
                   : (shard == 2 ? k_line<C, true, 2> : shard == 1 ? k_line<C, true, 1> : k_line<C, true, 0>);
         const size_t smem = batch_smem_bytes<T>(m->g->world > 1 ? (split ? 3 : 2) : cpp ? 0 : 1, p->negative_samples,

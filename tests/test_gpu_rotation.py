@@ -121,10 +121,10 @@ def test_blocks_train_the_right_rows():
     for world in (2, 4, 8):
         ms = _ring(off, col, ww, V, dim, world, init_v, np.zeros((V, dim)), capi.F64)
         episodes = 2 * world
-        p = _params(30000 // episodes, 9)
+        p = _params(60000 // episodes, 9, max_warps=64)  # (a block runs floor(samples / warps) samples per warp)
         p.negative_samples, p.alpha = 0, 1e-6
         done, _ = sdist.train_line_rotating(ms, p, episodes)
-        assert sum(done) > 20000
+        assert sum(done) > 50000
         Wv, Wc = _collect(ms, V, dim, world)
         assert np.abs(Wv - init_v).max() < 1e-9  # K = 0 and contexts ~ 0: vertex rows barely move, and none got lost
         hit = np.flatnonzero(Wc[:, 1] > 0)
