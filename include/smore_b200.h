@@ -255,9 +255,14 @@ int smore_model_save_weights(smore_model_t m, int table, const char* path, int f
  * On a row-sharded model each rank keeps the rows it owns. */
 int smore_model_load_pretrain(smore_model_t m, int table, const char* path, int64_t* rows_loaded);
 /* Binary snapshot of every table of this rank (raw rows in the stored element type + a header that pins V, dim, dtype,
- * rank/world): save / resume for long runs -- the reference can import text embeddings but not resume. */
+ * rank/world, and -- format version 2 -- the training position, see smore_model_progress): save / resume for long runs -- the reference can import text embeddings but not resume. */
 int smore_model_save_checkpoint(smore_model_t m, const char* path);
 int smore_model_load_checkpoint(smore_model_t m, const char* path);
+/* Where training stands (after the last train call, or as restored by load_checkpoint): the Philox key, the first sampler
+ * stream no call has used yet, the length of the LR schedule and how much of it is done (units of params.total). To
+ * resume, continue with the same seed, stream_base = next_stream, sched_total and sched_offset = sched_done; a version-1
+ * checkpoint (tables only) restores 0 / 0 / 0 / 0: a warm start. Any pointer may be NULL. */
+int smore_model_progress(smore_model_t m, uint64_t* seed, uint64_t* next_stream, uint64_t* sched_total, uint64_t* sched_done);
 /* The writer's formatter on host rows (no device involved; multi-threaded): `<first_id + r> v0 v1 ...\n` per row, in the
  * number format of the chosen reference writer. Returns the byte count of the text (written to `out` when it fits in
  * `cap`; call with out = NULL to size the buffer) or a negative error. */

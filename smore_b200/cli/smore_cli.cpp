@@ -9,6 +9,7 @@
 // as Go's flag package does). Extra flags: -semantics {go,cpp} (which tree's maths; default go where a Go CLI exists),
 // -mode {hogwild,deterministic}, -seed N, -dtype {f32,f64}. -threads is accepted and ignored: the workers are GPU warps.
 // The Go toolchain is not available in the build image; INTEGRATION.md has the cgo binding that calls the same ABI.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -201,7 +202,25 @@ int main(int argc, char** argv) {
         if (smore_model_load_pretrain(m, t, a.str(key, "").c_str(), &n)) return die("LoadPreTrain");
         printf("\t# of Pre-train:\t\t%lld\n", (long long)n);
     }
-    if (a.has("resume") && smore_model_load_checkpoint(m, a.str("resume", "").c_str())) return die("LoadCheckpoint");
+    // -resume: continue the interrupted run where its checkpoint left it (same seed, unused sampler streams, same LR
+    // schedule); a checkpoint without a position (format version 1) or of another schedule is a warm start
+    uint64_t resume_done = 0, resume_stream = 0;
+    if (a.has("resume")) {
+        if (smore_model_load_checkpoint(m, a.str("resume", "").c_str())) return die("LoadCheckpoint");
+        uint64_t ck_seed = 0, ck_stream = 0, ck_total = 0, ck_done = 0;
+        smore_model_progress(m, &ck_seed, &ck_stream, &ck_total, &ck_done);
+        const bool walk = model == "deepwalk" || model == "walklets";
+        if (!walk && ck_total == p.total && ck_done > 0 && ck_done < ck_total) {
+            resume_done = ck_done;
+            resume_stream = ck_stream;
+            if (!a.has("seed")) p.seed = ck_seed;
+            printf("\tresume:\t\t\t%llu of %llu samples done, continuing on stream %llu\n", (unsigned long long)ck_done,
+                   (unsigned long long)ck_total, (unsigned long long)ck_stream);
+        } else {
+            printf("\tresume:\t\t\ttables only (checkpoint holds %llu of %llu, this run is %llu): warm start\n",
+                   (unsigned long long)ck_done, (unsigned long long)ck_total, (unsigned long long)p.total);
+        }
+    }
 
     printf("Model:\n\t[%s] (%s semantics, %s, %s)\n", model.c_str(), sem_s.c_str(),
            p.mode == SMORE_MODE_HOGWILD ? "hogwild" : "deterministic", dtype == SMORE_F64 ? "f64" : "f32");
@@ -224,8 +243,12 @@ int main(int argc, char** argv) {
     double ms = 0;
     const bool walk_model = model == "deepwalk" || model == "walklets";
     const int chunks = (p.mode == SMORE_MODE_HOGWILD && !walk_model && p.total >= 2000000) ? 20 : 1;
+    const long ckpt_every = a.num("checkpoint_every", 0);  // chunks between intermediate checkpoints (0: only at the end)
     double last_alpha = p.alpha;
-    for (int c = 0; c < chunks; ++c) {
+    const int first_chunk = chunks > 1 ? (int)(resume_done / (p.total / chunks)) : 0;
+    // -max_chunks N: stop after N chunks of this invocation (time-sliced jobs: continue later with -resume <checkpoint>)
+    const int last_chunk = a.has("max_chunks") ? std::min<long>(chunks, first_chunk + a.num("max_chunks", chunks)) : chunks;
+    for (int c = first_chunk; c < last_chunk; ++c) {
         // Hogwild: the run is cut into chunks of one LR schedule so that the reference's progress line can be printed
         // (LINE.cpp:185); the deterministic mode stays one call (one worker, the reference's exact loop).
         smore_train_params q = p;
@@ -233,9 +256,12 @@ int main(int argc, char** argv) {
             q.total = p.total / chunks;
             q.sched_total = p.total;
             q.sched_offset = (uint64_t)c * q.total;
-            q.stream_base = p.stream_base + (uint64_t)c * (1ull << 24);
+            q.stream_base = std::max<uint64_t>(p.stream_base + (uint64_t)c * (1ull << 24), resume_stream);
         }
         if (train_once(q)) return die("Train");
+        if (ckpt_every > 0 && a.has("checkpoint") && (c + 1) % ckpt_every == 0 && c + 1 < chunks &&
+            smore_model_save_checkpoint(m, a.str("checkpoint", "").c_str()))
+            return die("SaveCheckpoint");
         uint64_t s1 = 0, p1 = 0;
         double ms1 = 0;
         smore_train_stats(m, &s1, &p1, nullptr, nullptr, &ms1);
@@ -250,7 +276,8 @@ int main(int argc, char** argv) {
             fflush(stdout);
         }
     }
-    printf("\tAlpha: %.6f\tProgress: 100.00 %%\n", last_alpha);
+    if (last_chunk == chunks) printf("\tAlpha: %.6f\tProgress: 100.00 %%\n", last_alpha);
+    else printf("\tAlpha: %.6f\tProgress: %.2f %% (stopped by -max_chunks)\n", last_alpha, 100.0 * last_chunk / chunks);
     printf("\t%llu samples, %llu pair updates in %.1f ms on the device (%.1f M updates/s)\n",
            (unsigned long long)samples, (unsigned long long)pairs, ms, ms > 0 ? pairs / ms / 1e3 : 0.0);
 

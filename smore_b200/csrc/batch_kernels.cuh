@@ -426,7 +426,20 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go
             T sc[2];
             dots<C, 2>(v, pn2, 2, sc);  // posScore, negScore (optimizer.go:95-100)
             const T gc = A::mul(alpha, fast_sigmoid<T>(lut, A::sub(sc[1], sc[0])));
-            if (!valias) {
+            if constexpr (kAtomicRows<C>) {
+                // fp32 tables: the three rows take their deltas with red.global.add (kernels.cuh, kAtomicRows): nothing is lost
+                // when many warps hit the same popular item row, and coinciding rows simply receive both deltas
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) {
+                    const T ve = v.x[e], pe = p.x[e], ne = n.x[e];
+                    v.x[e] = A::msub(A::mul(gc, A::sub(pe, ne)), la, ve);  // grad - (lambda*alpha)*w
+                    p.x[e] = A::msub(A::mul(gc, ve), la, pe);
+                    n.x[e] = A::msub(A::mul(-gc, ve), la, ne);
+                }
+                row_red_add<C>(pv, v, lane, dim);
+                row_red_add<C>(pp, p, lane, dim);
+                row_red_add<C>(pn, n, lane, dim);
+            } else if (!valias) {
 #pragma unroll
                 for (int e = 0; e < C::EPL; ++e) {
                     const T vg = A::mul(gc, A::sub(p.x[e], n.x[e]));
@@ -494,7 +507,43 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_cp
             const T cv = A::mul(alpha, (T)0.025);
             T* pv = W + (size_t)v1 * dim;
             T* pi = W + (size_t)v2 * dim;
-            if (!dup) {
+            if constexpr (kAtomicRows<C>) {
+                // fp32 tables: every row takes its delta with red.global.add; the item row's running value is tracked in
+                // registers across the five rounds (coinciding rows just receive several deltas)
+                Row<C> v, ri, rj[5], verr, di;
+                v.load_ca(pv, lane, dim);
+                ri.load_ca(pi, lane, dim);
+#pragma unroll
+                for (int n = 0; n < 5; ++n) rj[n].load_ca(W + (size_t)sid[2 + n] * dim, lane, dim);
+                pin(v);
+                pin(ri);
+#pragma unroll
+                for (int n = 0; n < 5; ++n) pin(rj[n]);  // all seven gathers in flight before the first round
+                verr.zero();
+                di.zero();
+#pragma unroll
+                for (int n = 0; n < 5; ++n) {
+                    Row<C> cvec;
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = A::sub(ri.x[e], rj[n].x[e]);
+                    const T f = dot(v, cvec);
+                    const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f)), alpha);
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) {
+                        verr.x[e] = A::madd(verr.x[e], gg, cvec.x[e]);
+                        const T cerr = A::mul(gg, v.x[e]);
+                        const T d = A::msub(cerr, c, ri.x[e]);  // item row: -c*w + cerr
+                        di.x[e] = A::add(di.x[e], d);
+                        ri.x[e] = A::add(ri.x[e], d);
+                        rj[n].x[e] = A::sub(A::mul(-c, rj[n].x[e]), cerr);  // negative row: -c*w - cerr
+                    }
+                    row_red_add<C>(W + (size_t)sid[2 + n] * dim, rj[n], lane, dim);
+                }
+                row_red_add<C>(pi, di, lane, dim);
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) v.x[e] = A::msub(verr.x[e], cv, v.x[e]);
+                row_red_add<C>(pv, v, lane, dim);
+            } else if (!dup) {
                 Row<C> v, ri, rj[5], verr;
                 v.load_ca(pv, lane, dim);
                 ri.load_ca(pi, lane, dim);
@@ -583,6 +632,55 @@ __global__ void __launch_bounds__(kBlockThreads) k_skewopt(TrainArgs<typename C:
             Row<C> verr;
             verr.zero();
             int update = 0;
+            if constexpr (kAtomicRows<C>) {
+                // fp32 tables, FAST path: user and item rows gathered once, the 16 negatives four at a time, every row takes
+                // its delta with red.global.add; the item row's running value is tracked in registers across the rounds
+                const T c = A::mul(alpha, (T)0.01);
+                Row<C> v, ri, di;
+                v.load(pv, lane, dim);
+                ri.load(pi, lane, dim);
+                di.zero();
+                for (int n0 = 0; n0 < kSbprRounds; n0 += 4) {
+                    Row<C> rj[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) rj[r].load(W + (size_t)sid[2 + n0 + r] * dim, lane, dim);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) pin(rj[r]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        Row<C> cvec;
+#pragma unroll
+                        for (int e = 0; e < C::EPL; ++e) cvec.x[e] = A::sub(ri.x[e], rj[r].x[e]);
+                        const T f = dot(v, cvec);
+                        T g = A::div(A::sub(f, a.xi), a.omega);  // Opt_SBPRSGD (src/proNet.cpp:1070-1098)
+                        if (g > (T)2) continue;
+                        if (g < (T)-2) g = (T)-2;
+                        T g_in = (T)1;
+                        for (int i = 0; i < a.eta; ++i) g_in = A::mul(g_in, g);
+                        const T chain = A::div(g_in, g);
+                        g = A::mul(A::div(A::mul(fast_sigmoid<T>(lut, A::mul((T)-1, g_in)), chain), a.omega), alpha);
+                        if (!(g == g)) continue;  // g == 0 exactly: the reference's 0/0; no update instead of a NaN row
+                        ++update;
+#pragma unroll
+                        for (int e = 0; e < C::EPL; ++e) {
+                            verr.x[e] = A::madd(verr.x[e], g, cvec.x[e]);
+                            const T cerr = A::mul(g, v.x[e]);
+                            const T d = A::msub(cerr, c, ri.x[e]);
+                            di.x[e] = A::add(di.x[e], d);
+                            ri.x[e] = A::add(ri.x[e], d);
+                            rj[r].x[e] = A::sub(A::mul(-c, rj[r].x[e]), cerr);
+                        }
+                        row_red_add<C>(W + (size_t)sid[2 + n0 + r] * dim, rj[r], lane, dim);
+                    }
+                }
+                if (update != 0) {
+                    row_red_add<C>(pi, di, lane, dim);
+                    const T inv = A::div((T)1, (T)update);
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) v.x[e] = A::msub(A::mul(verr.x[e], inv), c, v.x[e]);
+                    row_red_add<C>(pv, v, lane, dim);
+                }
+            } else {
             for (int n = 0; n < kSbprRounds; ++n)
                 if (sbpr_round<C>(pv, pi, W + (size_t)sid[2 + n] * dim, dim, lane, lut, alpha, a.xi, a.omega, a.eta, verr)) ++update;
             if (update != 0) {
@@ -592,6 +690,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_skewopt(TrainArgs<typename C:
                     stv(pv + idx, A::msub(ldv(pv + idx), c, ldv(pv + idx)));
                     stv(pv + idx, A::add(ldv(pv + idx), A::div(verr.x[e], up)));
                 });
+            }
             }
             st.count++;
             st.pairs += kSbprRounds;

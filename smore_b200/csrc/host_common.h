@@ -143,6 +143,8 @@ struct smore_model_s {
     int state_cap = 0;
     int32_t* d_keys = nullptr;
     int64_t keys_cap = 0;
+    // training position after the last train call (saved in checkpoints: smore_model_progress)
+    uint64_t ck_seed = 0, ck_next_stream = 0, ck_sched_total = 0, ck_sched_done = 0;
     // stats of the last train call
     uint64_t st_samples = 0, st_pairs = 0, st_words0 = 0, st_tries = 0;
     double st_ms = 0;
@@ -186,6 +188,18 @@ namespace {
 struct Launch {
     int blocks = 0, warps = 0;
 };
+
+// Hogwild concurrency policy. Every resident warp is one lock-free worker; the reference runs at most a few dozen of them
+// on tables of any size, this backend runs 3 552 per GPU. fp32 rows take their updates atomically (kernels.cuh,
+// kAtomicRows), so concurrent updates of a row are never lost -- but they are all computed from the same slightly stale
+// values, which multiplies the effective step of a row by the number of workers that hit it at once. On a table with
+// millions of rows that number is ~0; on a toy table of a few hundred rows it is dozens and the linear models (MF) diverge.
+// Unless the caller fixes max_warps, the grid is therefore capped at one warp per 8 table rows the trainer touches
+// (never below 64): no effect from ~30 k rows up, i.e. on every BASELINE config.
+inline int effective_max_warps(const smore_train_params* p, int64_t rows_touched) {
+    if (p->max_warps > 0) return p->max_warps;
+    return (int)std::min<int64_t>(std::max<int64_t>(64, rows_touched / 8), 1 << 30);
+}
 
 template <class K>
 int pick_grid(K kernel, size_t smem, int max_warps, uint64_t work_items, Launch& out, int sms_override = 0) {
@@ -329,6 +343,12 @@ TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps,
 }
 
 int init_state(smore_model_s* m, int warps, uint64_t count0, double alpha, const smore_train_params* p = nullptr) {
+    if (p) {  // where the run stands once this call returns (walk models: sched units are walks, recorded by the trainer)
+        m->ck_seed = p->seed;
+        m->ck_next_stream = std::max<uint64_t>(m->ck_next_stream, p->stream_base + (uint64_t)warps);
+        m->ck_sched_total = p->sched_total ? p->sched_total : p->total;
+        m->ck_sched_done = (p->sched_total ? p->sched_offset : 0) + p->total;
+    }
     if (p && p->sched_total && p->sched_offset) {  // resume a longer schedule: alpha_t = alpha * max(1e-4, 1 - done/total)
         const double a = alpha * (1.0 - (double)p->sched_offset / (double)p->sched_total);
         alpha = a < alpha * 0.0001 ? alpha * 0.0001 : a;

@@ -193,7 +193,22 @@ __global__ void __launch_bounds__(kBlockThreads) k_warp(TrainArgs<typename C::T>
                         const T c = A::mul(alpha, (T)0.0025);
                         // Opt_BPRSGD recomputes f from the same (unchanged) rows, so f[r] is its value (:1380 -> :1059)
                         const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f[r])), alpha);
-                        if (j != v2 && j != v1 && v1 != v2) {
+                        if constexpr (kAtomicRows<C>) {
+                            // fp32 tables: the three rows take their deltas with red.global.add; the negative's row is
+                            // item - difference, no reload
+#pragma unroll
+                            for (int e = 0; e < C::EPL; ++e) {
+                                const T verr = A::mul(gg, cvec[r].x[e]);
+                                const T cerr = A::mul(gg, v.x[e]);
+                                const T rje = A::sub(ri.x[e], cvec[r].x[e]);
+                                cvec[r].x[e] = A::sub(A::mul(-c, rje), cerr);  // negative row: -c*w - cerr
+                                ri.x[e] = A::msub(cerr, c, ri.x[e]);           // item row:     -c*w + cerr
+                                v.x[e] = A::msub(verr, c, v.x[e]);             // user row:     -c*w + verr
+                            }
+                            row_red_add<C>(pi, ri, lane, dim);
+                            row_red_add<C>(pj, cvec[r], lane, dim);
+                            row_red_add<C>(pv, v, lane, dim);
+                        } else if (j != v2 && j != v1 && v1 != v2) {
                             Row<C> rj;
                             rj.load_ca(pj, lane, dim);  // only the difference was kept; the row is an L2 hit now
 #pragma unroll
@@ -320,7 +335,47 @@ __global__ void __launch_bounds__(kBlockThreads) k_hoprec(TrainArgs<typename C::
             Row<C> verr;
             verr.zero();
             T up = 0;
-            if (!dup) {
+            if constexpr (kAtomicRows<C>) {
+                // fp32 tables: deltas with red.global.add, the item row's running value tracked in registers
+                Row<C> v, ri, rj[5], di;
+                v.load_ca(pv, lane, dim);
+                ri.load_ca(pi, lane, dim);
+#pragma unroll
+                for (int r = 0; r < 5; ++r) rj[r].load_ca(W + jid[r] * dim, lane, dim);
+                pin(v);
+                pin(ri);
+#pragma unroll
+                for (int r = 0; r < 5; ++r) pin(rj[r]);
+                di.zero();
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    Row<C> cvec;
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = A::sub(ri.x[e], rj[r].x[e]);
+                    const T f = dot(v, cvec);
+                    if (!(f > margin)) {
+                        const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f)), alpha);
+                        up += (T)1;
+#pragma unroll
+                        for (int e = 0; e < C::EPL; ++e) {
+                            verr.x[e] = A::madd(verr.x[e], gg, cvec.x[e]);
+                            const T cerr = A::mul(gg, v.x[e]);
+                            const T d = A::msub(cerr, cdec, ri.x[e]);
+                            di.x[e] = A::add(di.x[e], d);
+                            ri.x[e] = A::add(ri.x[e], d);
+                            rj[r].x[e] = A::sub(A::mul(-cdec, rj[r].x[e]), cerr);
+                        }
+                        row_red_add<C>(W + jid[r] * dim, rj[r], lane, dim);
+                    }
+                }
+                if (up > (T)0) {
+                    row_red_add<C>(pi, di, lane, dim);
+                    const T inv = A::div((T)1, up);
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) v.x[e] = A::msub(A::mul(verr.x[e], inv), cv, v.x[e]);
+                    row_red_add<C>(pv, v, lane, dim);
+                }
+            } else if (!dup) {
                 Row<C> v, ri, rj[5];
                 v.load_ca(pv, lane, dim);
                 ri.load_ca(pi, lane, dim);

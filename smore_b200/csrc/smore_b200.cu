@@ -859,6 +859,11 @@ struct CkptHeader {
     int64_t V, rows;
     int32_t rank, world;
 };
+// version 2 appends the training position, so that a checkpoint is a RESUME point and not only a warm start: the Philox
+// key, the first sampler stream no call has used yet, and where the LR schedule stands (units of `total`)
+struct CkptProgress {
+    uint64_t seed, next_stream, sched_total, sched_done;
+};
 constexpr char kCkptMagic[8] = {'S', 'M', 'O', 'R', 'E', 'B', '2', '\0'};
 }  // namespace
 
@@ -871,7 +876,7 @@ int smore_model_save_checkpoint(smore_model_t m, const char* path) {
     if (!f) return fail(SMORE_E_IO, "cannot create %s", path);
     CkptHeader h{};
     memcpy(h.magic, kCkptMagic, 8);
-    h.version = 1;
+    h.version = 2;
     h.dtype = (uint32_t)m->dtype;
     h.n_tables = (uint32_t)m->n_tables;
     h.dim = (uint32_t)m->dim;
@@ -880,6 +885,8 @@ int smore_model_save_checkpoint(smore_model_t m, const char* path) {
     h.rank = m->g->rank;
     h.world = m->g->world;
     bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    const CkptProgress pr{m->ck_seed, m->ck_next_stream, m->ck_sched_total, m->ck_sched_done};
+    ok = ok && fwrite(&pr, sizeof(pr), 1, f) == 1;
     const size_t row_bytes = (size_t)m->dim * m->elem();
     const int64_t chunk = std::max<int64_t>(1, (int64_t)((64ull << 20) / row_bytes));
     std::vector<char> host((size_t)chunk * row_bytes);
@@ -906,9 +913,14 @@ int smore_model_load_checkpoint(smore_model_t m, const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) return fail(SMORE_E_IO, "cannot open %s", path);
     CkptHeader h{};
-    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, kCkptMagic, 8) != 0 || h.version != 1) {
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, kCkptMagic, 8) != 0 || (h.version != 1 && h.version != 2)) {
         fclose(f);
         return fail(SMORE_E_IO, "%s is not a smore_b200 checkpoint", path);
+    }
+    CkptProgress pr{0, 0, 0, 0};  // a version-1 file holds tables only: loading it is a warm start (progress stays 0 / 0)
+    if (h.version == 2 && fread(&pr, sizeof(pr), 1, f) != 1) {
+        fclose(f);
+        return fail(SMORE_E_IO, "checkpoint %s is truncated", path);
     }
     if ((int)h.dtype != m->dtype || (int)h.n_tables != m->n_tables || (int)h.dim != m->dim || h.V != m->g->V || h.rows != m->rows ||
         h.rank != m->g->rank || h.world != m->g->world) {
@@ -936,6 +948,19 @@ int smore_model_load_checkpoint(smore_model_t m, const char* path) {
             }
         }
     fclose(f);
+    m->ck_seed = pr.seed;
+    m->ck_next_stream = pr.next_stream;
+    m->ck_sched_total = pr.sched_total;
+    m->ck_sched_done = pr.sched_done;
+    return SMORE_OK;
+}
+
+int smore_model_progress(smore_model_t m, uint64_t* seed, uint64_t* next_stream, uint64_t* sched_total, uint64_t* sched_done) {
+    if (!m) return fail(SMORE_E_INVALID, "null model");
+    if (seed) *seed = m->ck_seed;
+    if (next_stream) *next_stream = m->ck_next_stream;
+    if (sched_total) *sched_total = m->ck_sched_total;
+    if (sched_done) *sched_done = m->ck_sched_done;
     return SMORE_OK;
 }
 

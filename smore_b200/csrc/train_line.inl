@@ -21,7 +21,7 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
-        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
+        else if (int rc = pick_grid(kern, smem, effective_max_warps(p, m->rows * (vtab == ctab ? 1 : 2)), p->total, L)) return rc;
         // row-sharded: this rank draws sources from its own vertices only and runs its share of the global total
         const uint64_t total_local = m->g->world == 1 ? p->total : (uint64_t)llround((double)p->total * m->g->src_mass_frac);
         // jobs = total / workers (LINE.cpp:124); the C++ loop starts count at 1 and runs while count < jobs
@@ -59,7 +59,7 @@ int train_line_block_t(smore_model_s* m, const smore_train_params* p, int q, voi
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
-        else if (int rc = pick_grid(kern, smem, p->max_warps, n_samples, L)) return rc;
+        else if (int rc = pick_grid(kern, smem, effective_max_warps(p, m->g->sub_rows[(size_t)q] + m->rows), n_samples, L)) return rc;
         const uint64_t jobs = n_samples / (uint64_t)L.warps;
         if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
         // p->total = samples of ALL ranks in this episode; the schedule (sched_total / sched_offset) is in the same global unit
@@ -102,7 +102,7 @@ int train_mf_t(smore_model_s* m, const smore_train_params* p) {
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
-        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
+        else if (int rc = pick_grid(kern, smem, effective_max_warps(p, m->rows), p->total, L)) return rc;
         const uint64_t trips = p->total / (uint64_t)L.warps;
         if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
         TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)p->total, 1, 0, 0);
@@ -214,7 +214,7 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
         cudaStream_t sc = g_xs.sc, su = g_xs.su;
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
-        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L, g_xs.su_sms)) return rc;
+        else if (int rc = pick_grid(kern, smem, effective_max_warps(p, m0->rows * 2), p->total, L, g_xs.su_sms)) return rc;
         const size_t row_bytes = (size_t)m0->dim * sizeof(T);
         const uint64_t wps = (uint64_t)batch_wps(2, p->negative_samples);
         const uint64_t per_sb = (uint64_t)m0->xch->superbatch * (uint64_t)world;

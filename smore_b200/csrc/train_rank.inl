@@ -13,7 +13,7 @@ int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind) {
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
-        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
+        else if (int rc = pick_grid(kern, smem, effective_max_warps(p, m->rows * (kind == RANK_BPR && !cpp ? 2 : 1)), p->total, L)) return rc;
         // BPR.cpp:73-85 / WARP.cpp / HBPR.cpp: jobs = total / workers, count from 0; bpr.go: sample_times*MaxLine trips
         const uint64_t trips = p->total / (uint64_t)L.warps;
         if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;

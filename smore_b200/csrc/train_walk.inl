@@ -11,7 +11,7 @@ int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets) {
         const int64_t V = m->g->V;
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
-        else if (int rc = pick_grid(kern, smem, p->max_warps, (uint64_t)V, L)) return rc;
+        else if (int rc = pick_grid(kern, smem, effective_max_warps(p, m->rows * 2), (uint64_t)V, L)) return rc;
         const double total = (double)((unsigned long long)p->walk_times * (unsigned long long)V);
         if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
         TrainArgs<T> a = base_args<T>(m, p, L.warps, total, 0, 0, 1);
@@ -70,7 +70,7 @@ int train_hpe_t(smore_model_s* m, const smore_train_params* p) {
         const size_t smem = smem_line<T>();
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
-        else if (int rc = pick_grid(kern, smem, p->max_warps, p->total, L)) return rc;
+        else if (int rc = pick_grid(kern, smem, effective_max_warps(p, m->rows * 2), p->total, L)) return rc;
         const uint64_t trips = p->total / (uint64_t)L.warps;
         if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
         TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)p->total, 1, 0, 1);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Reference-path quality numbers for the §8f models (HPE, MF, Skew-OPT) on the planted-partition graph of the LINE
-quality gate (tests/test_gpu_quality.py): the oracle restatement -- pinned bit-exactly against the compiled reference --
+quality gate (tests/test_zz_gpu_quality_gates.py): the oracle restatement -- pinned bit-exactly against the compiled reference --
 trained on one stream, then held-out AUC / recall@10. Written to tests/golden/quality_baselines_v1.json so that the
 Hogwild GPU gates of these models ("within 0.5 % of the reference path") have their CPU side precomputed.
 
@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import bindings as B  # noqa: E402
 from smore_b200 import synth  # noqa: E402
-from tests.test_gpu_quality import evaluate, sbm_graph  # noqa: E402
+from tests.quality import evaluate_sampled as evaluate, sbm_graph  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "quality_baselines_v1.json")
 SEED = 20261018

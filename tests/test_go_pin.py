@@ -1,0 +1,100 @@
+"""CPU: the Go-semantics half of the oracle (oracle/smore_oracle.cpp) against a SECOND, independently written restatement
+of the Go sources (tests/golden/go_restatement.py -> tests/golden/golden_go_v1.npz), bit for bit, plus hand-computed
+known answers on the README graph. There is no Go toolchain in this image (parity with a Go BUILD stays unpinned); two
+restatements written separately from the same sources agreeing exactly is the evidence available without one."""
+import os
+
+import numpy as np
+
+from oracle import bindings as B
+from tests import graphs
+from tests.golden import go_restatement as GO
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_go_v1.npz"))
+SEED = 20261018
+
+
+def _oracle(src, dst, w, undirected):
+    off, col, ww, ids = B.edges_to_csr(src, dst, w, undirected)
+    return B.OracleGraph(B.SEM_GO, off, col, ww, max_line=len(src)), ids
+
+
+def _check_tables(og, tag):
+    p, a = og.alias(0)
+    assert np.array_equal(p, G[f"{tag}_vertex_prob"]) and np.array_equal(a, G[f"{tag}_vertex_alias"])
+    p, a = og.alias(1)
+    assert np.array_equal(p, G[f"{tag}_negative_prob"]) and np.array_equal(a, G[f"{tag}_negative_alias"])
+    assert np.array_equal(og.sample(0, SEED, 1, 2000)[0], G[f"{tag}_source"])
+    assert np.array_equal(og.sample(1, SEED, 2, 2000)[0], G[f"{tag}_negative"])
+    st, words = og.sample(3, SEED, 3, 2000)
+    assert np.array_equal(st, G[f"{tag}_source_target"]) and words == int(G[f"{tag}_source_target_words"])
+
+
+def test_readme_graph_known_answers_by_hand():
+    """Directed README graph: out-degrees [8,0,0,6,0,4] (userA, itemA, itemC, userB, itemB, userC). BuildAliasMethod(power 1):
+    norm = d * 6 / 18 = [8/3, 0, 0, 2, 0, 4/3]; small = [1,2,4], large = [0,3,5]; popping from the back pairs
+    4<-5, 5<-3, 2<-3, 3<-0, 1<-0 and leaves 0: prob = [1, 0, 0, 1/3, 0, 1/3], alias = [0, 0, 3, 0, 5, 3]."""
+    src, dst, w = graphs.readme_graph()
+    pn = GO.ProNet(src.tolist(), dst.tolist(), w.tolist(), False)
+    assert pn.out_degree == [8.0, 0.0, 0.0, 6.0, 0.0, 4.0] and pn.in_degree == [0.0, 8.0, 5.0, 0.0, 5.0, 0.0]
+    prob, alias = pn.vertex_at
+    assert alias == [0, 0, 3, 0, 5, 3]
+    assert np.allclose(prob, [1, 0, 0, 1 / 3, 0, 1 / 3], rtol=0, atol=1e-15)
+    # the table encodes d / 18 exactly up to rounding
+    p = np.array(prob) / 6
+    for i, a in enumerate(alias):
+        p[a] += (1 - prob[i]) / 6
+    assert np.allclose(p, np.array(pn.out_degree) / 18, atol=1e-15)
+    # sigmoid table: 1001 entries, exact end points and centre (pronet.go:90-95)
+    assert len(pn.sigmoid) == 1001 and pn.sigmoid[500] == 0.5 and pn.fast_sigmoid(8.0) == pn.sigmoid[1000]
+    assert pn.fast_sigmoid(-8.0000001) == 0.0 and pn.fast_sigmoid(8.0000001) == 1.0
+    # the oracle agrees with the hand computation too
+    og, _ = _oracle(src, dst, w, 0)
+    p2, a2 = og.alias(0)
+    assert a2.tolist() == alias and np.array_equal(p2, np.array(prob))
+    assert np.array_equal(og.sigmoid_table(), G["sigmoid"])
+
+
+def test_tables_and_samplers_match_the_python_restatement():
+    src, dst, w = graphs.readme_graph()
+    for und in (0, 1):
+        og, _ = _oracle(src, dst, w, und)
+        _check_tables(og, f"readme{und}")
+        do, di = og.degrees()
+        assert np.array_equal(do, G[f"readme{und}_out_degree"]) and np.array_equal(di, G[f"readme{und}_in_degree"])
+    og, _ = _oracle(G["g60_src"], G["g60_dst"], G["g60_w"], 1)
+    _check_tables(og, "g60")
+    og, _ = _oracle(G["bip_src"], G["bip_dst"], G["bip_w"], 0)
+    _check_tables(og, "bip")
+
+
+def test_line_bpr_deepwalk_embeddings_match_the_python_restatement():
+    og, _ = _oracle(G["g60_src"], G["g60_dst"], G["g60_w"], 1)
+    for order in (2, 1):
+        a, c = G["g60_init_v"].copy(), G["g60_init_c"].copy()
+        total = int(G[f"g60_line{order}_total"])
+        pos = og.train_line_go(a, c, order, 5, 0.025, total, SEED, 0)
+        assert pos == int(G[f"g60_line{order}_words"])
+        assert np.array_equal(a, G[f"g60_line{order}_v"]) and np.array_equal(c, G[f"g60_line{order}_c"])
+    a, c = G["g60_init_v"].copy(), G["g60_init_c"].copy()
+    wt, ws, win, K = (int(x) for x in G["g60_dw_args"])
+    pos, pairs = og.train_deepwalk_go(a, c, wt, ws, win, K, 0.025, SEED, 0)
+    assert pos == int(G["g60_dw_words"]) and pairs == int(G["g60_dw_pairs"])
+    assert np.array_equal(a, G["g60_dw_v"]) and np.array_equal(c, G["g60_dw_c"])
+    og, _ = _oracle(G["bip_src"], G["bip_dst"], G["bip_w"], 0)
+    a, c = G["bip_init_v"].copy(), G["bip_init_c"].copy()
+    total = int(G["bip_bpr_total"])
+    pos = og.train_bpr_go(a, c, 0.025, 0.001, total, SEED, 0)
+    assert pos == int(G["bip_bpr_words"])
+    assert np.array_equal(a, G["bip_bpr_v"]) and np.array_equal(c, G["bip_bpr_c"])
+
+
+def test_fixture_is_reproducible_from_the_restatement():
+    """Re-runs the cheapest entry: the committed .npz is what go_restatement.py produces."""
+    pn = GO.ProNet(G["bip_src"].tolist(), G["bip_dst"].tolist(), G["bip_w"].tolist(), False)
+    a, c = G["bip_init_v"].tolist(), G["bip_init_c"].tolist()
+    pos = GO.train_bpr(pn, a, c, 8, 5000, 5000, 0.025, 0.001, GO.Words(SEED, 0))
+    og, _ = _oracle(G["bip_src"], G["bip_dst"], G["bip_w"], 0)
+    a2, c2 = G["bip_init_v"].copy(), G["bip_init_c"].copy()
+    assert og.train_bpr_go(a2, c2, 0.025, 0.001, 5000, SEED, 0) == pos
+    assert np.array_equal(np.array(a), a2) and np.array_equal(np.array(c), c2)

@@ -94,15 +94,23 @@ def test_checkpoint_roundtrip_and_resume(tmp_path, dtype):
     a = capi.Model(g, dim, 2, dtype)
     a.init(0, True, 1), a.init(1, False, 1)
     a.train_line(p)
+    assert a.progress() == {"seed": 3, "next_stream": 1, "sched_total": 60_000, "sched_done": 30_000}
     ck = str(tmp_path / "half.ckpt")
     a.save_checkpoint(ck)
     p2 = capi.default_params()
-    p2.mode, p2.seed, p2.total, p2.sched_total, p2.sched_offset, p2.stream_base = capi.MODE_DETERMINISTIC, 3, 30_000, 60_000, 30_000, 1 << 24
+    p2.mode, p2.seed, p2.total, p2.sched_total, p2.sched_offset, p2.stream_base = capi.MODE_DETERMINISTIC, 3, 30_000, 60_000, 30_000, 1
     a.train_line(p2)
-    # ... equals: first chunk, checkpoint, NEW model, resume, second chunk
+    assert a.progress()["sched_done"] == 60_000 and a.progress()["next_stream"] == 2
+    # ... equals: first chunk, checkpoint, NEW model, resume from the position the checkpoint carries, second chunk
     b = capi.Model(g, dim, 2, dtype)
+    assert b.progress()["sched_total"] == 0
     b.load_checkpoint(ck)
-    b.train_line(p2)
+    pos = b.progress()
+    assert pos == {"seed": 3, "next_stream": 1, "sched_total": 60_000, "sched_done": 30_000}
+    p3 = capi.default_params()
+    p3.mode, p3.seed, p3.total = capi.MODE_DETERMINISTIC, pos["seed"], pos["sched_total"] - pos["sched_done"]
+    p3.sched_total, p3.sched_offset, p3.stream_base = pos["sched_total"], pos["sched_done"], pos["next_stream"]
+    b.train_line(p3)
     assert np.array_equal(a.get_rows(0), b.get_rows(0)) and np.array_equal(a.get_rows(1), b.get_rows(1))
     # a checkpoint only fits the model it was taken from
     with pytest.raises(capi.SmoreError):
@@ -133,3 +141,12 @@ def test_cli_load_v_and_checkpoint_flags(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run(base + ["-save", rep2, "-resume", rep1], capture_output=True, text=True)
     assert r.returncode != 0 and "not a smore_b200 checkpoint" in r.stderr
+    # an interrupted Hogwild run continues where its checkpoint left it: schedule position and unused sampler streams
+    line = [os.path.join(BIN, "line"), "-train", net, "-dimensions", "16", "-sample_times", "2", "-semantics", "cpp"]
+    r = subprocess.run(line + ["-save", rep1, "-checkpoint", ck, "-max_chunks", "8"], capture_output=True, text=True)
+    assert r.returncode == 0 and "stopped by -max_chunks" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run(line + ["-save", rep2, "-resume", ck], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "resume:\t\t\t800000 of 2000000 samples done" in r.stdout and "Progress: 100.00 %" in r.stdout, r.stdout
+    done = [l for l in r.stdout.split("\n") if "samples," in l][0]
+    assert 1_100_000 < int(done.split()[0]) <= 1_200_000, done  # only the remaining 12 of 20 chunks ran

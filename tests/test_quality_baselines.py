@@ -8,7 +8,7 @@ import numpy as np
 
 from oracle import bindings as B
 from smore_b200 import synth
-from tests.test_gpu_quality import evaluate, sbm_graph
+from tests.quality import evaluate_sampled as evaluate, sbm_graph
 
 Q = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "quality_baselines_v1.json")))
 
@@ -33,4 +33,4 @@ def test_skewopt_baseline_reproduces():
     W = (np.random.default_rng(1).random((V, Q["dim"])) - 0.5) / Q["dim"] + m["init_offset"]
     g.train_skewopt_cpp(W, m["xi"], m["omega"], m["eta"], m["alpha"], m["total"], Q["seed"], 0)
     a, r = evaluate(W, W, test_s, test_d, train_adj, np.random.default_rng(2))
-    assert abs(a - m["auc"]) < 1e-12 and abs(r - m["recall_at_10"]) < 1e-12
+    assert abs(a - m["auc"]) < 1e-6 and abs(r - m["recall_at_10"]) < 1e-6  # (libm / BLAS may differ in the last bits between machines)

@@ -38,8 +38,34 @@ def sbm_graph(n_comm, comm_size, deg, p_in, seed):
     return src[keep], dst[keep], w[keep]
 
 
-def make_problem(n_comm=150, comm_size=80, deg=24):
-    src, dst, w = sbm_graph(n_comm=n_comm, comm_size=comm_size, deg=deg, p_in=0.85, seed=5)
+def sbm_powerlaw_graph(n_comm, comm_size, deg, p_in, seed, expo=0.8):
+    """Planted partition with heterogeneous degrees: both endpoints are drawn by a fitness ~ rank^-expo (random ranks), so
+    most vertices have a handful of neighbours (fewer than the number of shards) and a few hubs have thousands."""
+    rng = np.random.default_rng(seed)
+    V = n_comm * comm_size
+    n_edges = V * deg // 2
+    fit = (np.arange(1, V + 1, dtype=np.float64) ** -expo)[rng.permutation(V)]
+    cdf = np.cumsum(fit) / fit.sum()
+    src = np.searchsorted(cdf, rng.random(n_edges)).clip(max=V - 1)
+    inside = rng.random(n_edges) < p_in
+    # inside a community: fitness-weighted choice among its members
+    f2 = fit.reshape(n_comm, comm_size)
+    ccdf = np.cumsum(f2, axis=1) / f2.sum(axis=1, keepdims=True)
+    comm = src // comm_size
+    u = rng.random(n_edges)
+    dst_in = comm * comm_size + (ccdf[comm] < u[:, None]).sum(axis=1).clip(max=comm_size - 1)
+    dst_out = np.searchsorted(cdf, rng.random(n_edges)).clip(max=V - 1)
+    dst = np.where(inside, dst_in, dst_out)
+    keep = src != dst
+    w = rng.integers(1, 4, n_edges).astype(np.float64)
+    return src[keep], dst[keep], w[keep]
+
+
+def make_problem(n_comm=150, comm_size=80, deg=24, powerlaw=False):
+    if powerlaw:
+        src, dst, w = sbm_powerlaw_graph(n_comm=n_comm, comm_size=comm_size, deg=deg, p_in=0.85, seed=5)
+    else:
+        src, dst, w = sbm_graph(n_comm=n_comm, comm_size=comm_size, deg=deg, p_in=0.85, seed=5)
     (ts, td, tw), (hs, hd, _) = synth.split_edges(src, dst, w, 0.10, seed=6)
     off, col, ww, labels = synth.csr_from_edges(ts, td, tw, True)
     lab2id = {int(l): i for i, l in enumerate(labels)}
@@ -170,8 +196,14 @@ def main():
     ap.add_argument("--worlds", default="2,4,8")
     ap.add_argument("--cycles", default="5,20")
     ap.add_argument("--what", default="occupancy,peer,rotating", help="comma list of: occupancy, peer-r2a, peer, rotating")
+    ap.add_argument("--powerlaw", action="store_true", help="heterogeneous degrees (most vertices have fewer neighbours than shards)")
+    ap.add_argument("--deg", type=int, default=24)
     args = ap.parse_args()
-    prob = make_problem()
+    prob = make_problem(deg=args.deg, powerlaw=args.powerlaw)
+    if args.powerlaw:
+        d = np.diff(prob[0])
+        print(f"power-law SBM: V={len(d)} entries={d.sum()} median degree {np.median(d):.0f}, "
+              f"{(d <= 4).mean() * 100:.0f}% of the vertices have <= 4 neighbours, max {d.max()}", file=sys.stderr)
     cells = []
 
     def cell(name, fn):

@@ -79,7 +79,7 @@ def main():
                 run(f"bpr_cpp_d{dim}_c1", m, m.train_bpr, p, 14 * dim * 4 + 60, "samples", a.steps, a.warmup)
 
     # ---- a large bipartite graph (configs[3] scaled): BPR at dim 128 out of L2, WARP, HOP-Rec ----
-    if want("bpr_go_big") or want("warp") or want("hoprec") or want("bpr_cpp_big"):
+    if want("bpr_go_big") or want("warp") or want("hoprec") or want("bpr_cpp_big") or want("mf") or want("skewopt"):
         nu, ni, ne = int(1_000_000 * a.scale), int(200_000 * a.scale), int(20_000_000 * a.scale)
         t0 = time.time()
         src, dst, w = synth.bipartite_edges(nu, ni, ne, 9, zipf_s=a.zipf)
@@ -93,9 +93,25 @@ def main():
             p.semantics, p.mode, p.seed, p.total, p.lambda_ = capi.SEM_GO, capi.MODE_HOGWILD, 1, 1 << 25, 0.001
             run(f"bpr_go_d{dim}_big", m, m.train_bpr, p, 6 * dim * 4 + 40, "samples", a.steps, a.warmup)
             del m, g
-        if want("bpr_cpp_big") or want("warp"):
+        if want("bpr_cpp_big") or want("warp") or want("mf") or want("skewopt"):
             off, col, ww, _ = synth.csr_from_edges(src, dst, w, False)
             g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP, negative_method=capi.NEG_NO_DEGREES)
+            if want("mf"):
+                m = capi.Model(g, dim, 1, capi.F32)
+                m.init(0, True, 1)
+                p = capi.default_params()
+                p.semantics, p.mode, p.seed, p.total, p.lambda_ = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 1 << 24, 0.01
+                # MF::Train = LINE's sampling loop around UpdateFactorizedPair: 1 + (1 + K) rows R+W
+                run(f"mf_d{dim}_big", m, m.train_mf, p, 2 * 7 * dim * 4 + 76, "samples", a.steps, a.warmup)
+            if want("skewopt"):
+                m = capi.Model(g, dim, 1, capi.F32)
+                m.init(0, True, 1)
+                p = capi.default_params()
+                p.semantics, p.mode, p.seed, p.total = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 1 << 23
+                # UpdateSBPRPair: user + item + 16 negatives read; written: the accepted rounds' negatives + item + user
+                # (mean_tries = accepted rounds per sample)
+                run(f"skewopt_d{dim}_big", m, m.train_skewopt, p, lambda acc: (18 + acc + 2) * dim * 4 + 150, "samples",
+                    a.steps, a.warmup)
             if want("bpr_cpp_big"):
                 m = capi.Model(g, dim, 1, capi.F32)
                 m.init(0, True, 1)
