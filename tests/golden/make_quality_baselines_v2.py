@@ -24,10 +24,17 @@ DIM = 32
 
 
 def main():
+    only = set(sys.argv[1].split(",")) if len(sys.argv) > 1 else None  # e.g. `hpe,mf`: recompute those, keep the rest
     res = {"seed": SEED, "dim": DIM, "init": "table t: default_rng(1 + 2 t), (U - 0.5) / dim (LINE C++ context: zeros)",
            "problems": {"sbm": "tests/quality.py sbm_problem() -- 12 000 vertices, 150 communities, degree 24",
                         "bipartite": "tests/quality.py bipartite_problem() -- 4 000 users x 2 000 items, 100 communities, 20 interactions per user"},
            "models": {}}
+
+    if only and os.path.exists(OUT):
+        res["models"] = json.load(open(OUT))["models"]
+
+    def want(name):
+        return only is None or name in only
 
     def record(name, t0, **kw):
         res["models"][name] = dict(kw, seconds=round(time.time() - t0, 1))
@@ -39,61 +46,90 @@ def main():
     init_v = (np.random.default_rng(1).random((V, DIM)) - 0.5) / DIM
     init_c = (np.random.default_rng(3).random((V, DIM)) - 0.5) / DIM
     g = B.OracleGraph(B.SEM_CPP, off, col, ww)
-    t0 = time.time()
-    a, c = init_v.copy(), np.zeros((V, DIM))
-    g.train_line_cpp(a, c, 5, 0.025, 12_000_000, SEED, 0)
-    auc, rec = Q.evaluate_full(a, c, off, col, ts, td)
-    record("line_cpp", t0, total=12_000_000, negative_samples=5, alpha=0.025, auc=auc, recall_at_10=rec)
-    gg = B.OracleGraph(B.SEM_GO, off, col, ww, max_line=len(col) // 2)
-    t0 = time.time()
-    a, c = init_v.copy(), init_c.copy()
-    gg.train_line_go(a, c, 2, 5, 0.025, 12_000_000, SEED, 0)
-    auc, rec = Q.evaluate_full(a, c, off, col, ts, td)
-    record("line_go", t0, total=12_000_000, negative_samples=5, alpha=0.025, auc=auc, recall_at_10=rec)
-    t0 = time.time()
-    a, c = init_v.copy(), init_c.copy()
-    _, pairs = g.train_walk_cpp(0, a, c, 8, 40, 5, 0, 5, 0.025, SEED, 0)
-    auc, rec = Q.evaluate_full(a, c, off, col, ts, td)
-    record("deepwalk_cpp", t0, walk_times=8, walk_steps=40, window=5, negative_samples=5, alpha=0.025, pairs=int(pairs), auc=auc,
-           recall_at_10=rec)
+    if want("line_cpp"):
+        t0 = time.time()
+        a, c = init_v.copy(), np.zeros((V, DIM))
+        g.train_line_cpp(a, c, 5, 0.025, 12_000_000, SEED, 0)
+        auc, rec = Q.evaluate_full(a, c, off, col, ts, td)
+        record("line_cpp", t0, total=12_000_000, negative_samples=5, alpha=0.025, auc=auc, recall_at_10=rec)
+    if want("line_go"):
+        gg = B.OracleGraph(B.SEM_GO, off, col, ww, max_line=len(col) // 2)
+        t0 = time.time()
+        a, c = init_v.copy(), init_c.copy()
+        gg.train_line_go(a, c, 2, 5, 0.025, 12_000_000, SEED, 0)
+        auc, rec = Q.evaluate_full(a, c, off, col, ts, td)
+        record("line_go", t0, total=12_000_000, negative_samples=5, alpha=0.025, auc=auc, recall_at_10=rec)
+    if want("deepwalk_cpp"):
+        t0 = time.time()
+        a, c = init_v.copy(), init_c.copy()
+        _, pairs = g.train_walk_cpp(0, a, c, 8, 40, 5, 0, 5, 0.025, SEED, 0)
+        auc, rec = Q.evaluate_full(a, c, off, col, ts, td)
+        record("deepwalk_cpp", t0, walk_times=8, walk_steps=40, window=5, negative_samples=5, alpha=0.025, pairs=int(pairs), auc=auc,
+               recall_at_10=rec)
+    # the §8f models, same parameters as tests/golden/quality_baselines_v1.json but evaluated on EVERY held-out source (the v1
+    # numbers use 1500 sources: a standard error of ~0.005 on recall@10, as large as the gate)
+    if want("hpe"):
+        t0 = time.time()
+        a, c = init_v.copy(), init_c.copy()
+        g.train_hpe_cpp(a, c, 5, 5, 0.01, 0.025, 3_000_000, SEED, 0)
+        auc, rec = Q.evaluate_full(a, c, off, col, ts, td)
+        record("hpe", t0, walk_steps=5, negative_samples=5, reg=0.01, alpha=0.025, total=3_000_000, auc=auc, recall_at_10=rec)
+    gnd = B.OracleGraph(B.SEM_CPP, off, col, ww, neg_method=B.NEG_NO_DEGREES)
+    if want("mf"):
+        t0 = time.time()
+        a = init_v.copy()
+        gnd.train_mf_cpp(a, 5, 0.01, 0.025, 12_000_000, SEED, 0)
+        auc, rec = Q.evaluate_full(a, a, off, col, ts, td)
+        record("mf", t0, negative_samples=5, reg=0.01, alpha=0.025, total=12_000_000, auc=auc, recall_at_10=rec)
+    if want("skewopt"):
+        t0 = time.time()
+        a = init_v.copy() + 0.01
+        gnd.train_skewopt_cpp(a, 10.0, 3.0, 3, 0.025, 3_000_000, SEED, 0)
+        auc, rec = Q.evaluate_full(a, a, off, col, ts, td)
+        record("skewopt", t0, xi=10.0, omega=3.0, eta=3, alpha=0.025, total=3_000_000, init_offset=0.01, auc=auc, recall_at_10=rec)
 
     # ---- ranking models on the planted-preference problem ----
     off, col, ww, tu, ti, is_item, field = Q.bipartite_problem()
     V = len(off) - 1
     init_v = (np.random.default_rng(1).random((V, DIM)) - 0.5) / DIM
     init_c = (np.random.default_rng(3).random((V, DIM)) - 0.5) / DIM
-    gg = B.OracleGraph(B.SEM_GO, off, col, ww, max_line=len(col))
-    t0 = time.time()
-    a, c = init_v.copy(), init_c.copy()
-    gg.train_bpr_go(a, c, 0.025, 0.001, 4_000_000, SEED, 0)
-    record("bpr_go", t0, total=4_000_000, alpha=0.025, lam=0.001, auc=Q.evaluate_bipartite(a, c, tu, ti, is_item))
+    if want("bpr_go"):
+        gg = B.OracleGraph(B.SEM_GO, off, col, ww, max_line=len(col))
+        t0 = time.time()
+        a, c = init_v.copy(), init_c.copy()
+        gg.train_bpr_go(a, c, 0.025, 0.001, 4_000_000, SEED, 0)
+        record("bpr_go", t0, total=4_000_000, alpha=0.025, lam=0.001, auc=Q.evaluate_bipartite(a, c, tu, ti, is_item))
     gn = B.OracleGraph(B.SEM_CPP, off, col, ww, neg_method=B.NEG_NO_DEGREES)
-    t0 = time.time()
-    a = init_v.copy()
-    gn.train_bpr_cpp(a, 0.025, 3_000_000, SEED, 0)
-    record("bpr_cpp", t0, total=3_000_000, alpha=0.025, auc=Q.evaluate_bipartite(a, a, tu, ti, is_item))
-    t0 = time.time()
-    a = init_v.copy()
-    _, tries = gn.train_warp_cpp(a, 0.025, 3_000_000, SEED, 0)
-    record("warp", t0, total=3_000_000, alpha=0.025, mean_tries=tries / 3_000_000, auc=Q.evaluate_bipartite(a, a, tu, ti, is_item))
-    off2, col2, ww2, tu2, ti2, is_item2, field2 = Q.bipartite_problem(undirected=True)
-    gh = B.OracleGraph(B.SEM_CPP, off2, col2, ww2, neg_method=B.NEG_NO_DEGREES)
-    gh.set_field(field2)
-    t0 = time.time()
-    V2 = len(off2) - 1
-    a = (np.random.default_rng(1).random((V2, DIM)) - 0.5) / DIM
-    gh.train_hoprec_cpp(a, 3, 0.025, 1_000_000, SEED, 0)
-    record("hoprec", t0, total=1_000_000, walk_steps=3, alpha=0.025, auc=Q.evaluate_bipartite(a, a, tu2, ti2, is_item2))
+    if want("bpr_cpp"):
+        t0 = time.time()
+        a = init_v.copy()
+        gn.train_bpr_cpp(a, 0.025, 3_000_000, SEED, 0)
+        record("bpr_cpp", t0, total=3_000_000, alpha=0.025, auc=Q.evaluate_bipartite(a, a, tu, ti, is_item))
+    if want("warp"):
+        t0 = time.time()
+        a = init_v.copy()
+        _, tries = gn.train_warp_cpp(a, 0.025, 3_000_000, SEED, 0)
+        record("warp", t0, total=3_000_000, alpha=0.025, mean_tries=tries / 3_000_000, auc=Q.evaluate_bipartite(a, a, tu, ti, is_item))
+    if want("hoprec"):
+        off2, col2, ww2, tu2, ti2, is_item2, field2 = Q.bipartite_problem(undirected=True)
+        gh = B.OracleGraph(B.SEM_CPP, off2, col2, ww2, neg_method=B.NEG_NO_DEGREES)
+        gh.set_field(field2)
+        t0 = time.time()
+        V2 = len(off2) - 1
+        a = (np.random.default_rng(1).random((V2, DIM)) - 0.5) / DIM
+        gh.train_hoprec_cpp(a, 3, 0.025, 1_000_000, SEED, 0)
+        record("hoprec", t0, total=1_000_000, walk_steps=3, alpha=0.025, auc=Q.evaluate_bipartite(a, a, tu2, ti2, is_item2))
     # ---- the bench instantiation (dim 128) on a graph large enough for every resident warp (80 000 table rows) ----
-    off, col, ww, ts, td = Q.sbm_problem(n_comm=500, comm_size=80, deg=24, seed=31)
-    V = len(off) - 1
-    g = B.OracleGraph(B.SEM_CPP, off, col, ww)
-    t0 = time.time()
-    a, c = (np.random.default_rng(1).random((V, 128)) - 0.5) / 128, np.zeros((V, 128))
-    g.train_line_cpp(a, c, 5, 0.025, 40_000_000, SEED, 0)
-    auc, rec = Q.evaluate_full(a, c, off, col, ts, td)
-    record("line_cpp_d128_40k", t0, problem="sbm_problem(n_comm=500, comm_size=80, deg=24, seed=31)", dim=128, total=40_000_000,
-           negative_samples=5, alpha=0.025, auc=auc, recall_at_10=rec)
+    if want("line_cpp_d128_40k"):
+        off, col, ww, ts, td = Q.sbm_problem(n_comm=500, comm_size=80, deg=24, seed=31)
+        V = len(off) - 1
+        g = B.OracleGraph(B.SEM_CPP, off, col, ww)
+        t0 = time.time()
+        a, c = (np.random.default_rng(1).random((V, 128)) - 0.5) / 128, np.zeros((V, 128))
+        g.train_line_cpp(a, c, 5, 0.025, 40_000_000, SEED, 0)
+        auc, rec = Q.evaluate_full(a, c, off, col, ts, td)
+        record("line_cpp_d128_40k", t0, problem="sbm_problem(n_comm=500, comm_size=80, deg=24, seed=31)", dim=128, total=40_000_000,
+               negative_samples=5, alpha=0.025, auc=auc, recall_at_10=rec)
     json.dump(res, open(OUT, "w"), indent=1)
     print("wrote", OUT)
 
