@@ -20,8 +20,8 @@ value : updates/s with graph + tables resident in HBM (timed: K steps, CUDA even
 e2e   : the same metric through the C ABI the way a host Train() call sees it: every step uploads both embedding tables
         (this rank's shards) from pinned HOST memory, trains, and reads the vertex table back to the host; the read-back
         of step i overlaps the upload of step i+1 where the data dependences allow it (different tables).
-roofline : algorithmic bytes per update (2*(K+2)*D*4 + 76 = 7244 B; sharded runs use split samples, one more
-        row: 2*(K+3)*D*4 + 84 = 8276 B) x updates / kernel time (the library's own CUDA events around the kernel) against
+roofline : algorithmic bytes per update (2*(K+2)*D*4 + 76 = 7244 B; with --split-samples one more row:
+        2*(K+3)*D*4 + 84 = 8276 B) x updates / kernel time (the library's own CUDA events around the kernel) against
         MEASURED_PEAKS.json hbm_gbs.
 cpu_baseline : the reference's CPU implementation timed on this box's host cores on a bounded sample (N = 1 only).
 """
@@ -92,15 +92,16 @@ def bench_config(args, world, V=None, E=None):
               f"device: {lv // world} vertices / {le // world} edge lines per GPU [BASELINE configs[4] shape: 100M vertices / 2B edges at 8 GPUs]")
         par = (f"tables row-sharded over {world} GPUs; context shards fixed, vertex shards rotating around the ring in {2 * world} "
                f"sub-parts (block-cyclic episodes, every update out of local HBM, sub-parts moved by copy engines over NVLink "
-               f"behind the update kernel); split samples (shard-local negatives applied to an independently drawn vertex); "
-               f"host barrier per episode, no data-path collective")
+               f"behind the update kernel); shard-local negatives"
+               + (" applied to an independently drawn vertex (split samples)" if args.split_samples else "")
+               + "; host barrier per episode, no data-path collective")
         upd = args.episode_batch * 2 * world
         l2 = f"working set per GPU ({lv // world * DIM * 4 * 2.5 / 1e9:.1f} GB of table rows + block tables) exceeds the 126 MB L2; no flush between steps"
     else:
         wl = (f"LINE-2 dim={DIM} K={K} Hogwild, synthetic power-law graph V={V if V else lv} E_lines={le} "
               f"(undirected, {2 * le} CSR entries) [BASELINE configs[1] graph at every N]")
         par = {"sharded": f"tables row-sharded over {world} GPUs, context-owner computes, remote vertex rows over NVLink peer "
-                          f"mappings (CUDA IPC), split samples, no data-path collective",
+                          f"mappings (CUDA IPC), no data-path collective",
                "sharded-replica": f"row-sharded over {world} GPUs, vertex rows read from a local replica refreshed every step, "
                                   f"deltas pushed with red.global.add",
                "sharded-exchange": f"row-sharded over {world} GPUs, remote vertex rows moved in super-batches of {args.superbatch} "
@@ -336,6 +337,7 @@ def run_ours(args):
     p = capi.default_params()
     p.semantics, p.mode, p.seed, p.alpha = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 0.025
     p.negative_samples, p.order = K, 2
+    p.neg_mode = capi.PAIRING_SPLIT if args.split_samples else capi.PAIRING_COUPLED
     step_no = [0]
     episodes_per_step = 2 * world
 
@@ -455,7 +457,7 @@ def run_ours(args):
     else:
         peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
     # dominant kernel = k_line: per-rank algorithmic bytes / its own CUDA-event time (max over ranks)
-    split = rotating or mode == "sharded"
+    split = args.split_samples and (rotating or mode == "sharded")
     algo = ALGO_BYTES_SPLIT if split else ALGO_BYTES
     per_rank_updates = updates / world
     achieved = per_rank_updates * algo / (kernel_ms * 1e-3) / 1e9
@@ -503,6 +505,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the host-buffer (e2e) leg")
     ap.add_argument("--parallelism", default="rotating",
                     choices=["rotating", "sharded", "sharded-replica", "sharded-exchange", "replicas"], help="N>1 only")
+    ap.add_argument("--split-samples", action="store_true",
+                    help="sharded modes: apply the negatives to an independently drawn vertex (one more row per update)")
     ap.add_argument("--superbatch", type=int, default=1 << 20, help="sharded-exchange: samples per GPU and super-batch")
     ap.add_argument("--hot-threshold", type=float, default=64.0,
                     help="sharded-exchange: expected source draws per super-batch above which a vertex keeps a single copy (<0: none)")

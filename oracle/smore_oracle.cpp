@@ -1028,18 +1028,25 @@ int orc_write_edge_list(const char* path, const int64_t* src, const int64_t* dst
     return 0;
 }
 
-// ---- multi-threaded Hogwild timing leg (bench.py cpu_baseline "port"): LINE-2 C++ semantics, one stream per thread,
-// per-thread schedule as in LINE.cpp:162-191 with `workers` threads.
+// ---- multi-threaded Hogwild leg (bench.py cpu_baseline "port"; the CPU side of the large-graph quality gate): LINE-2,
+// C++ semantics, one stream per thread, and the reference's schedule exactly as LINE.cpp:162-191 runs it with `workers`
+// threads: every worker counts from 1 to jobs = total / workers and, every MONITOR of ITS samples, reads the shared
+// progress counter for its new alpha and then bumps it by MONITOR (the counter is a plain shared variable in the reference;
+// relaxed atomics here).
 double orc_time_line_cpp(void* h, double* Wv, double* Wc, int dim, int K, double alpha, uint64_t total, uint64_t seed,
                          int workers);
 
 }  // extern "C"
 
 #include <omp.h>
+
+#include <atomic>
 extern "C" double orc_time_line_cpp(void* h, double* Wv, double* Wc, int dim, int K, double alpha, uint64_t total,
                                     uint64_t seed, int workers) {
     Graph* g = (Graph*)h;
     unsigned long long jobs = total / workers;
+    const double alpha_min = alpha * 0.0001;
+    std::atomic<unsigned long long> current_sample{0};
     double t0 = omp_get_wtime();
 #pragma omp parallel for num_threads(workers)
     for (int wk = 0; wk < workers; ++wk) {
@@ -1052,6 +1059,11 @@ extern "C" double orc_time_line_cpp(void* h, double* Wv, double* Wc, int dim, in
             int64_t v2 = g->target_sample(v1, d);
             g->update_pair_cpp(Wv, Wc, v1, v2, dim, K, cur, d, be);
             count++;
+            if (count % MONITOR == 0) {
+                cur = alpha * (1.0 - (double)current_sample.load(std::memory_order_relaxed) / (double)total);
+                current_sample.fetch_add(MONITOR, std::memory_order_relaxed);
+                if (cur < alpha_min) cur = alpha_min;
+            }
         }
     }
     return omp_get_wtime() - t0;

@@ -324,8 +324,9 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
         off = (off + 15) & ~(size_t)15;
         vstage = reinterpret_cast<T*>(smem_raw + off) + (size_t)wib * kStageDepth * kRowElems;
     }
-    for (uint64_t done = 0; done < a.jobs; done += 32) {
-        const int nb = (int)min((uint64_t)32, a.jobs - done);
+    const uint64_t my_jobs = a.jobs + (w < a.jobs_rem ? 1u : 0u);
+    for (uint64_t done = 0; done < my_jobs; done += 32) {
+        const int nb = (int)min((uint64_t)32, my_jobs - done);
         batch_sample<GO>(a.g, b, a.seed, stream, st, nb, lane);
         if constexpr (SHARD == 3) {
             // remote source: k_line_requests filed it in the hash; its row now sits in the staging table

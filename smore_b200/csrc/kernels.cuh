@@ -61,6 +61,7 @@ struct TrainArgs {
     WarpState* state;
     int n_warps;
     uint64_t jobs;  // loop trips per warp in this launch
+    int jobs_rem;   // ... plus one more for warps w < jobs_rem (block trainer: no sample of a small block is lost to rounding)
     int K;
     int order;
     T lambda;

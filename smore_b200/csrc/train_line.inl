@@ -10,8 +10,8 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
         using C = decltype(cfg);
         const bool cpp = p->semantics == SMORE_SEM_CPP;
         const int shard = m->g->world == 1 ? 0 : (m->replica[vtab] ? 2 : 1);
-        // peer-access mode, LINE-2: split samples by default (neg_mode 1 = the coupled round-1 scheme)
-        const bool split = shard == 1 && vtab != ctab && p->neg_mode != SMORE_PAIRING_COUPLED;
+        // peer-access mode, LINE-2: split samples on request (neg_mode; the default is the reference's pairing)
+        const bool split = shard == 1 && vtab != ctab && p->neg_mode == SMORE_PAIRING_SPLIT;
         void (*kern)(TrainArgs<T>) =
             split ? k_line<C, false, 1, 2>
             : cpp ? (shard == 2 ? k_line<C, false, 2> : shard == 1 ? k_line<C, false, 1> : k_line<C, false, 0>)
@@ -53,7 +53,7 @@ int train_line_block_t(smore_model_s* m, const smore_train_params* p, int q, voi
     return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
         using C = decltype(cfg);
         const bool cpp = p->semantics == SMORE_SEM_CPP;
-        const bool split = p->neg_mode != SMORE_PAIRING_COUPLED;
+        const bool split = p->neg_mode == SMORE_PAIRING_SPLIT;
         void (*kern)(TrainArgs<T>) = split ? k_line<C, false, 0, 2> : cpp ? k_line<C, false, 0> : k_line<C, true, 0>;
         const size_t smem = batch_smem_bytes<T>(split ? 3 : 2, p->negative_samples, 0);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -78,16 +78,17 @@ int train_line_block_t(smore_model_s* m, const smore_train_params* p, int q, voi
         a.Wc = (T*)m->tab[1];
         a.same_table = 0;
         a.jobs = jobs;
+        a.jobs_rem = p->mode == SMORE_MODE_DETERMINISTIC ? 0 : (int)(n_samples % (uint64_t)L.warps);  // nothing lost to rounding
         m->st_samples = 0;
         m->st_ms = 0;
-        if (jobs == 0 || a.g.n_edge_local == 0) return SMORE_OK;
+        if (n_samples == 0 || a.g.n_edge_local == 0) return SMORE_OK;
         Timer t;
         if (int rc = t.start()) return rc;
         kern<<<L.blocks, kBlockThreads, smem>>>(a);
         g_launches++;
         CU(cudaGetLastError());
         if (int rc = t.stop(&m->st_ms)) return rc;
-        m->st_samples = jobs * (uint64_t)L.warps;
+        m->st_samples = jobs * (uint64_t)L.warps + (uint64_t)a.jobs_rem;
         return collect_stats(m, L.warps);
     });
 }
