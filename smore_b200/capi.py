@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsmore_b200.so")
+LIB_PATH = os.environ.get("SMORE_B200_LIB") or os.path.join(HERE, "lib", "libsmore_b200.so")  # (override: experiment builds)
 
 SEM_CPP, SEM_GO = 0, 1
 NEG_DEGREES, NEG_IN_DEGREES, NEG_NO_DEGREES = 0, 1, 2

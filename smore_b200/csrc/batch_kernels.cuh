@@ -38,9 +38,12 @@ inline size_t batch_smem_bytes(int go, int K, int stage_row_elems = 0) {
 }
 
 // resident CTAs per SM the register allocator must allow: 3 while a row costs <= 16 B per lane (fp32 dim <= 128)
+#ifndef SMORE_LINE_MINBLOCKS
+#define SMORE_LINE_MINBLOCKS 3
+#endif
 template <class C>
 constexpr int batch_min_blocks() {
-    return C::EPL * (int)sizeof(typename C::T) <= 16 ? 3 : C::EPL * (int)sizeof(typename C::T) <= 32 ? 2 : 1;
+    return C::EPL * (int)sizeof(typename C::T) <= 16 ? SMORE_LINE_MINBLOCKS : C::EPL * (int)sizeof(typename C::T) <= 32 ? 2 : 1;
 }
 
 struct Batch {
