@@ -120,34 +120,46 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
 
 // L2 prefetch of every row of one sample (ids row `pid`: slot 0 lives in the vertex table, the others in the context
 // table). Rows of a peer shard are skipped: peer addresses bypass the local L2.
+// SMORE_PREFETCH_MODE: 1 = one prefetch.global.L2 per 128 B line (round 1; ncu shows each of them as a ONE-sector request:
+// lts__t_sectors_srcunit_tex_op_read = 112 row sectors + 8 sampler sectors + 28 per update), 2 = one
+// cp.async.bulk.prefetch.L2 per row (the whole 512 B row in one instruction, issued by one lane per row), 3 = one
+// prefetch.global.L2 per 32 B sector, 0 = none.
+#ifndef SMORE_PREFETCH_MODE
+#define SMORE_PREFETCH_MODE 2
+#endif
+__device__ __forceinline__ void prefetch_row(const void* row, int row_bytes, int lane_in_row, int lanes_per_row) {
+#if SMORE_PREFETCH_MODE == 2
+    if (lane_in_row == 0) {
+        if ((row_bytes & 15) == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(row_bytes) : "memory");
+        else
+            for (int o = 0; o < row_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)row + o));
+    }
+#elif SMORE_PREFETCH_MODE == 3
+    for (int o = lane_in_row * 32; o < row_bytes; o += lanes_per_row * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)row + o));
+#elif SMORE_PREFETCH_MODE == 1
+    for (int o = lane_in_row * 128; o < row_bytes; o += lanes_per_row * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)row + o));
+#endif
+}
+// lanes are dealt to the rows of the sample in groups of 4 (8 rows per pass)
 template <typename T, class TV, class TC>
 __device__ __forceinline__ void prefetch_sample(const TV& tv, const TC& tc, int rank, const int* pid,
                                                 int idw, int lane, int vslot2 = -1 /* split samples: slot of the 2nd vertex */) {
-    const int lines_per_row = (tv.dim * (int)sizeof(T) + 127) >> 7;
-    const int total = idw * lines_per_row;
-    for (int t = lane; t < total; t += 32) {
-        const int r = t / lines_per_row, ln = t - r * lines_per_row;
+    const int row_bytes = tv.dim * (int)sizeof(T);
+    for (int r = lane >> 2; r < idw; r += 8) {
         const int id = pid[r];
         const bool vrow = r == 0 || r == vslot2;
         // (a negative id in slot 0 is a staging row of the exchange mode: ExchView; negative elsewhere = no row)
-        if (vrow ? (id < 0 || (id & tv.mask) == (rank & tv.mask)) : (id >= 0 && (id & tc.mask) == (rank & tc.mask))) {
-            const char* p = reinterpret_cast<const char*>(vrow ? tv.row(id) : tc.row(id)) + (ln << 7);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        }
+        if (vrow ? (id < 0 || (id & tv.mask) == (rank & tv.mask)) : (id >= 0 && (id & tc.mask) == (rank & tc.mask)))
+            prefetch_row(vrow ? tv.row(id) : tc.row(id), row_bytes, lane & 3, 4);
     }
 }
 
 template <typename T>
 __device__ __forceinline__ void prefetch_local(const T* Wv, const T* Wc, const int* pid, int idw, int dim, int lane) {
-    const int lines_per_row = (dim * (int)sizeof(T) + 127) >> 7;
-    const int total = idw * lines_per_row;
-    for (int t = lane; t < total; t += 32) {
-        const int r = t / lines_per_row, ln = t - r * lines_per_row;
+    const int row_bytes = dim * (int)sizeof(T);
+    for (int r = lane >> 2; r < idw; r += 8) {
         const int id = pid[r];
-        if (id >= 0) {
-            const char* p = reinterpret_cast<const char*>((r == 0 ? Wv : Wc) + (size_t)id * dim) + (ln << 7);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        }
+        if (id >= 0) prefetch_row((r == 0 ? Wv : Wc) + (size_t)id * dim, row_bytes, lane & 3, 4);
     }
 }
 

@@ -231,6 +231,38 @@ def test_sharded_line(mode, world):
     check(f"{mode} world={world}", res[:, 1].mean(), ref["recall_at_10"], "recall@10")
 
 
+@pytest.mark.parametrize("sb,hot", [(1 << 13, -1.0), (1 << 15, 12.0)])
+def test_exchange_mode_line(sb, hot):
+    """Bulk-exchange mode, 4 shards in one process: pure exchange with super-batches of 2^13 samples per shard, and the
+    best-connected quarter of the vertices kept single-copy behind the peer pointers (hot threshold 12)."""
+    off, col, ww, ts, td = sbm()
+    V, ref, world = len(off) - 1, Q2["models"]["line_cpp"], 4
+    Wv, Wc = init_tables(V, context_zero=True)
+    ms = []
+    for r in range(world):
+        g = capi.Graph.from_csr(off, col, ww)
+        g.set_shard(r, world)
+        m = capi.Model(g, DIM, 2, capi.F32)
+        rows = sdist.owned_rows(V, r, world)
+        m.set_rows(0, Wv[rows]), m.set_rows(1, Wc[rows])
+        m.enable_exchange(sb, hot)
+        ms.append(m)
+    if hot >= 0:
+        for t in range(2):
+            ptrs = [m.device_ptr(t) for m in ms]
+            for m in ms:
+                m.set_peer_ptrs(t, ptrs)
+    stats = capi.train_line_group(ms, hogwild(seed=100, total=ref["total"], negative_samples=5, max_warps=512))
+    assert 0.9 * ref["total"] <= sum(s["samples"] for s in stats) <= ref["total"]
+    Wv2, Wc2 = np.zeros((V, DIM)), np.zeros((V, DIM))
+    for r, m in enumerate(ms):
+        rows = sdist.owned_rows(V, r, world)
+        Wv2[rows], Wc2[rows] = m.get_rows(0), m.get_rows(1)
+    a, rec = Q.evaluate_full(Wv2, Wc2, off, col, ts, td)
+    check(f"exchange sb={sb} hot={hot}", a, ref["auc"])
+    check(f"exchange sb={sb} hot={hot}", rec, ref["recall_at_10"], "recall@10")
+
+
 # ---- the configuration bench.py times: dim 128 (RowCfg<float,4,1>), every resident warp -------------------------------
 def test_full_occupancy_dim128_trained_to_convergence():
     """40 000 vertices (80 000 table rows: the occupancy policy lets all 3 552 warps run), dim 128, 1000 updates per vertex,
