@@ -213,8 +213,8 @@ int smore_exchange_stats(smore_model_t m, uint64_t* superbatches, uint64_t* rows
  *        smore_rot_send_begin(m, e);  smore_train_line_episode(m, &p, e);  smore_rot_send_end(m, e);  <host barrier>
  * The barrier is the host's (torch.distributed / MPI / a Go channel): the library makes no cross-process call here.
  * get_rows / set_rows / init / checkpoints address LOCAL rows as for any sharded model and are valid whenever the model is
- * at home (episode % (2*world) == 0, after the barrier); smore_train_line_episode may be skipped in an episode (e.g. to
- * finish a partial cycle). LINE order 2 only (order 1 uses one table in both roles). */
+ * at home (episode % (2*world) == 0, after the barrier); smore_train_*_episode may be skipped in an episode (e.g. to
+ * finish a partial cycle). Trainers: LINE order 2 and the Go BPR (models with separate vertex / context tables). */
 int smore_graph_set_shard_rotating(smore_graph_t g, int rank, int world);
 /* n_sub = 2*world; block_mass[q] / block_edges[q] (n_sub entries each, may be NULL): this rank's blocks by ring index q. */
 int smore_graph_rotation_info(smore_graph_t g, int* n_sub, int64_t* sub_cap, double* block_mass, int64_t* block_edges);
@@ -319,6 +319,10 @@ int smore_train_line_group(const smore_model_t* shards, int n, const smore_train
  * runs its block's share, total * 2*world * mass(q, rank)); p->sched_total / sched_offset in the same global unit;
  * p->stream_base must differ between ranks and episodes. */
 int smore_train_line_episode(smore_model_t m, const smore_train_params* p, int64_t episode);
+/* Same for the Go BPR (bpr.go:84-131, UpdateBPRPair optimizer.go:87-117): users live in the rotating vertex table, items in
+ * the fixed context table; one block = users of the resident sub-part x items this rank owns, negatives among the rank's
+ * own vertices. (The C++ BPR / WARP / HOP-Rec train ONE table in both roles and cannot be cut this way.) */
+int smore_train_bpr_episode(smore_model_t m, const smore_train_params* p, int64_t episode);
 /* BPR::Train (src/model/BPR.cpp:55-107, 5-negative UpdateBPRPair proNet.cpp:1406-1455) /
  * BPR.Train (internal/models/bpr/bpr.go:61-131, optimizer.go:87-117). */
 int smore_train_bpr(smore_model_t m, const smore_train_params* p);

@@ -36,7 +36,7 @@ EXPORTS = [
     "smore_model_enable_exchange", "smore_dist_nccl_unique_id", "smore_dist_nccl_init", "smore_dist_nccl_shutdown",
     "smore_graph_set_shard_rotating", "smore_graph_rotation_info", "smore_model_enable_rotation", "smore_model_rot_ipc_handles",
     "smore_model_rot_open_next", "smore_model_rot_slot_ptrs", "smore_model_rot_set_next_ptrs", "smore_rot_send_begin",
-    "smore_train_line_episode", "smore_rot_send_end", "smore_rot_position",
+    "smore_train_line_episode", "smore_train_bpr_episode", "smore_rot_send_end", "smore_rot_position",
     "smore_alias_build_device", "smore_graph_create_synthetic_rotating",
     "smore_model_set_rows_f32_async", "smore_model_get_rows_f32_async", "smore_model_wait_copies",
     "smore_train_line_group", "smore_exchange_stats", "smore_debug_sm_partition", "smore_model_save_weights", "smore_format_rows",
@@ -119,6 +119,7 @@ def lib():
         L.smore_model_rot_set_next_ptrs.argtypes = [vp, vp]
         L.smore_rot_send_begin.argtypes = [vp, i64]
         L.smore_train_line_episode.argtypes = [vp, C.POINTER(TrainParams), i64]
+        L.smore_train_bpr_episode.argtypes = [vp, C.POINTER(TrainParams), i64]
         L.smore_rot_send_end.argtypes = [vp, i64]
         L.smore_rot_position.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.smore_alias_build_device.argtypes = [vp, i64, vp, vp]
@@ -454,6 +455,10 @@ class Model:
 
     def train_line_episode(self, p, episode):
         check(lib().smore_train_line_episode(self.h, C.byref(p), episode))
+        return self.stats()
+
+    def train_bpr_episode(self, p, episode):
+        check(lib().smore_train_bpr_episode(self.h, C.byref(p), episode))
         return self.stats()
 
     def rot_send_end(self, episode):

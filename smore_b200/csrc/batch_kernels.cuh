@@ -120,12 +120,17 @@ __device__ __forceinline__ void batch_sample(const GraphDev& g, const Batch& b, 
 
 // L2 prefetch of every row of one sample (ids row `pid`: slot 0 lives in the vertex table, the others in the context
 // table). Rows of a peer shard are skipped: peer addresses bypass the local L2.
-// SMORE_PREFETCH_MODE: 1 = one prefetch.global.L2 per 128 B line (round 1; ncu shows each of them as a ONE-sector request:
-// lts__t_sectors_srcunit_tex_op_read = 112 row sectors + 8 sampler sectors + 28 per update), 2 = one
-// cp.async.bulk.prefetch.L2 per row (the whole 512 B row in one instruction, issued by one lane per row), 3 = one
-// prefetch.global.L2 per 32 B sector, 0 = none.
+// SMORE_PREFETCH_MODE: 0 = none (default since round 2), 1 = one prefetch.global.L2 per 128 B line (round 1; ncu shows each
+// of them as a ONE-sector request), 2 = one cp.async.bulk.prefetch.L2 per row (the whole 512 B row in one instruction),
+// 3 = one prefetch.global.L2 per 32 B sector.
+// Measured with the atomic-row kernels (profiles/r2h_prefetch_modes.txt): every prefetch flavour LOSES to none -- the block
+// kernel at the configs[4] footprint 592 M updates/s with any of them vs 674 M/s without (ncu: 4.9 KB of DRAM reads per
+// update instead of the 3.8 KB the rows and sampler entries account for: prefetched sectors are evicted before the demand
+// load arrives and fetched twice), BPR C++ 0.87 -> 0.95 of the HBM peak, MF 0.80 -> 0.84, configs[1] LINE +1..4 %. Round 1's
+// kernels (whole-row stores) gained 4 % from mode 1; with `red` updates the rows no longer wait in registers for the store,
+// the 24 resident warps per SM cover the DRAM latency on their own, and the prefetches only add traffic.
 #ifndef SMORE_PREFETCH_MODE
-#define SMORE_PREFETCH_MODE 2
+#define SMORE_PREFETCH_MODE 0
 #endif
 __device__ __forceinline__ void prefetch_row(const void* row, int row_bytes, int lane_in_row, int lanes_per_row) {
 #if SMORE_PREFETCH_MODE == 2
@@ -411,12 +416,14 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go
     const int wib = threadIdx.x >> 5;
     const int w = blockIdx.x * kWarpsPerBlock + wib;
     if (w >= a.n_warps) return;
-    const Batch b = batch_init<T>(1, 1, wib);
+    // (rotating shards: the block's edge table replaces the source -> target draws, as in k_line)
+    const Batch b = batch_init<T>(a.g.edge_at ? 2 : 1, 1, wib);
     WarpState st = a.state[w];
     const uint64_t stream = a.stream_base + (uint64_t)w;
     const int dim = a.dim;
-    for (uint64_t done = 0; done < a.jobs; done += 32) {
-        const int nb = (int)min((uint64_t)32, a.jobs - done);
+    const uint64_t my_jobs = a.jobs + (w < a.jobs_rem ? 1u : 0u);
+    for (uint64_t done = 0; done < my_jobs; done += 32) {
+        const int nb = (int)min((uint64_t)32, my_jobs - done);
         batch_sample<true>(a.g, b, a.seed, stream, st, nb, lane);
         for (int s = 0; s < nb; ++s) {
             if (s + kLinePrefetch < nb) prefetch_local<T>(a.Wv, a.Wc, b.ids + (s + kLinePrefetch) * b.idw, b.idw, dim, lane);

@@ -387,4 +387,6 @@ int train_mf_t(smore_model_s* m, const smore_train_params* p);
 template <typename T>
 int train_line_block_t(smore_model_s* m, const smore_train_params* p, int q, void* vslot, uint64_t n_samples);
 template <typename T>
+int train_bpr_block_t(smore_model_s* m, const smore_train_params* p, int q, void* vslot, uint64_t n_samples);
+template <typename T>
 int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind);

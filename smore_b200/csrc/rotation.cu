@@ -297,28 +297,34 @@ int smore_rot_send_begin(smore_model_t m, int64_t episode) {
     return SMORE_OK;
 }
 
-// Step 2 of 3: one block of LINE updates out of local HBM. p->total = samples of ALL ranks in this episode; this rank runs
+// Step 2 of 3: one block of updates out of local HBM. p->total = samples of ALL ranks in this episode; this rank runs
 // total * 2G * mass(q, rank) of them (every block's share of a cycle), sched_total / sched_offset are global sample counts.
-int smore_train_line_episode(smore_model_t m, const smore_train_params* p, int64_t episode) {
+static int train_episode(smore_model_t m, const smore_train_params* p, int64_t episode, bool bpr) {
     if (!m || !p || !m->rot) return fail(SMORE_E_INVALID, "rotation not enabled on this model");
     smore_rotation_s* r = m->rot;
     if (episode != r->episode || !r->sending || r->trained)
-        return fail(SMORE_E_INVALID, "train_line_episode(%lld): call order is send_begin, train_line_episode, send_end (model at episode %lld)", (long long)episode, (long long)r->episode);
+        return fail(SMORE_E_INVALID, "train episode %lld: call order is send_begin, train_*_episode, send_end (model at episode %lld)", (long long)episode, (long long)r->episode);
     if (p->semantics != m->g->sem) return fail(SMORE_E_INVALID, "params.semantics (%d) != graph semantics (%d)", p->semantics, m->g->sem);
     if (p->mode != SMORE_MODE_DETERMINISTIC && p->mode != SMORE_MODE_HOGWILD) return fail(SMORE_E_INVALID, "bad mode");
     if (!(p->alpha > 0)) return fail(SMORE_E_INVALID, "alpha must be > 0");
-    if (p->order != 2) return fail(SMORE_E_UNSUPPORTED, "rotating shards: LINE order 2 only (order 1 shares one table between both roles)");
-    if (p->negative_samples < 0 || p->negative_samples > 31) return fail(SMORE_E_UNSUPPORTED, "negative_samples must be in [0,31]");
+    if (bpr && p->semantics != SMORE_SEM_GO)
+        return fail(SMORE_E_UNSUPPORTED, "rotating shards: the Go BPR (user and item tables) only; the C++ BPR trains ONE table in both roles");
+    if (!bpr && p->order != 2) return fail(SMORE_E_UNSUPPORTED, "rotating shards: LINE order 2 only (order 1 shares one table between both roles)");
+    if (!bpr && (p->negative_samples < 0 || p->negative_samples > 31)) return fail(SMORE_E_UNSUPPORTED, "negative_samples must be in [0,31]");
     if (int rc = ensure_device()) return rc;
     const smore_graph_s* g = m->g;
     const int q = ring_q(g->rank, episode, g->nsub);
     const uint64_t n = (uint64_t)llround((double)p->total * (double)g->nsub * g->blk_mass[(size_t)q]);
-    int rc = m->dtype == SMORE_F64 ? train_line_block_t<double>(m, p, q, r->slot[episode % 3], n)
-                                   : train_line_block_t<float>(m, p, q, r->slot[episode % 3], n);
+    void* slot = r->slot[episode % 3];
+    int rc;
+    if (bpr) rc = m->dtype == SMORE_F64 ? train_bpr_block_t<double>(m, p, q, slot, n) : train_bpr_block_t<float>(m, p, q, slot, n);
+    else rc = m->dtype == SMORE_F64 ? train_line_block_t<double>(m, p, q, slot, n) : train_line_block_t<float>(m, p, q, slot, n);
     if (rc) return rc;
     r->trained = true;
     return SMORE_OK;
 }
+int smore_train_line_episode(smore_model_t m, const smore_train_params* p, int64_t episode) { return train_episode(m, p, episode, false); }
+int smore_train_bpr_episode(smore_model_t m, const smore_train_params* p, int64_t episode) { return train_episode(m, p, episode, true); }
 
 // Step 3 of 3: wait for this rank's outgoing copy. The HOST then synchronises the ranks (a barrier of its own transport):
 // after it, every rank's I(e) holds the sub-part of episode e+1 and every O(e) may be overwritten.

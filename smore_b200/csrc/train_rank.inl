@@ -31,3 +31,45 @@ int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind) {
         return collect_stats(m, L.warps);
     });
 }
+
+
+// Rotating shards, Go BPR (bpr.go:84-131 restricted to one block): users of the resident vertex sub-part x the items this
+// rank owns, negatives among the rank's own vertices. Same structure as train_line_block_t (train_line.inl).
+template <typename T>
+int train_bpr_block_t(smore_model_s* m, const smore_train_params* p, int q, void* vslot, uint64_t n_samples) {
+    return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
+        using C = decltype(cfg);
+        void (*kern)(TrainArgs<T>) = k_bpr_go<C>;
+        const size_t smem = batch_smem_bytes<T>(2, 1);
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        Launch L;
+        if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
+        else if (int rc = pick_grid(kern, smem, effective_max_warps(p, m->g->sub_rows[(size_t)q] + m->rows), n_samples, L)) return rc;
+        if (int rc = init_state(m, L.warps, 0, p->alpha, p)) return rc;
+        TrainArgs<T> a = base_args<T>(m, p, L.warps, (double)n_samples, 0, 0, 1, p->total ? (double)n_samples / (double)p->total : 1.0);
+        const smore_graph_s* g = m->g;
+        const int64_t off = g->blk_off[(size_t)q];
+        a.g.edge_at = g->d_eat + off;
+        a.g.edge_src = g->d_esrc + off;
+        a.g.edge_dst = g->d_edst + off;
+        a.g.n_edge_local = (uint32_t)(g->blk_off[(size_t)q + 1] - off);
+        a.g.n_neg = (uint32_t)g->n_local;
+        a.g.neg_shift = a.g.neg_rank = 0;
+        a.Wv = (T*)vslot;
+        a.Wc = (T*)m->tab[1];
+        a.same_table = 0;
+        a.jobs = n_samples / (uint64_t)L.warps;
+        a.jobs_rem = p->mode == SMORE_MODE_DETERMINISTIC ? 0 : (int)(n_samples % (uint64_t)L.warps);
+        m->st_samples = 0;
+        m->st_ms = 0;
+        if (n_samples == 0 || a.g.n_edge_local == 0) return SMORE_OK;
+        Timer t;
+        if (int rc = t.start()) return rc;
+        kern<<<L.blocks, kBlockThreads, smem>>>(a);
+        g_launches++;
+        CU(cudaGetLastError());
+        if (int rc = t.stop(&m->st_ms)) return rc;
+        m->st_samples = a.jobs * (uint64_t)L.warps + (uint64_t)a.jobs_rem;
+        return collect_stats(m, L.warps);
+    });
+}

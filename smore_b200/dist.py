@@ -86,12 +86,13 @@ def connect_rotation_local(models) -> None:
         m.rot_set_next_ptrs(ptrs[(r + 1) % n])
 
 
-def train_line_rotating(models, p, episodes, first_episode=0, barrier=None, world=None, rank0=0):
+def train_line_rotating(models, p, episodes, first_episode=0, barrier=None, world=None, rank0=0, trainer="line"):
     """Runs `episodes` episodes of the block-cyclic schedule. `models`: the shard(s) driven by this process -- [model] with
     one process per GPU (then `barrier` must synchronise the ranks, e.g. torch.distributed.barrier), or all shards of the
     ring in rank order (tests; no barrier needed). p.total = samples of ALL ranks per episode; p.sched_total (if set) is the
     length of the whole LR schedule in samples and the offset advances by p.total per episode; sub-streams are
-    p.stream_base + ((episode * world + rank) << 20) + warp. Returns (samples, kernel milliseconds) per model."""
+    p.stream_base + ((episode * world + rank) << 20) + warp. trainer: "line" or "bpr" (the Go BPR). Returns (samples,
+    kernel milliseconds) per model."""
     import copy
 
     world = world or len(models)
@@ -105,7 +106,7 @@ def train_line_rotating(models, p, episodes, first_episode=0, barrier=None, worl
             q.stream_base = p.stream_base + ((e * world + rank0 + i) << 20)
             if p.sched_total:
                 q.sched_offset = p.sched_offset + (e - first_episode) * p.total
-            st = m.train_line_episode(q, e)
+            st = m.train_bpr_episode(q, e) if trainer == "bpr" else m.train_line_episode(q, e)
             done[i] += st["samples"]
             ms[i] += st["kernel_ms"]
         for m in models:

@@ -231,6 +231,33 @@ def test_sharded_line(mode, world):
     check(f"{mode} world={world}", res[:, 1].mean(), ref["recall_at_10"], "recall@10")
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_rotating_bpr_go(world):
+    """The Go BPR on rotating shards (users travel, items stay): held-out AUC against the single-stream reference path."""
+    off, col, ww, tu, ti, is_item, _ = bip()
+    V, ref = len(off) - 1, Q2["models"]["bpr_go"]
+    Wv, Wc = init_tables(V)
+    ms = []
+    for r in range(world):
+        g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_GO, n_lines=len(col))
+        g.set_shard_rotating(r, world)
+        m = capi.Model(g, DIM, 2, capi.F32)
+        rows = sdist.owned_rows(V, r, world)
+        m.set_rows(0, Wv[rows]), m.set_rows(1, Wc[rows])
+        m.enable_rotation()
+        ms.append(m)
+    sdist.connect_rotation_local(ms)
+    episodes = 20 * 2 * world
+    p = hogwild(capi.SEM_GO, seed=31, total=ref["total"] // episodes, lambda_=ref["lam"], sched_total=ref["total"])
+    done, _ = sdist.train_line_rotating(ms, p, episodes, trainer="bpr")
+    assert 0.95 * ref["total"] <= sum(done) <= 1.01 * ref["total"]
+    Wv2, Wc2 = np.zeros((V, DIM)), np.zeros((V, DIM))
+    for r, m in enumerate(ms):
+        rows = sdist.owned_rows(V, r, world)
+        Wv2[rows], Wc2[rows] = m.get_rows(0), m.get_rows(1)
+    check(f"rotating BPR Go world={world}", Q.evaluate_bipartite(Wv2, Wc2, tu, ti, is_item), ref["auc"])
+
+
 @pytest.mark.parametrize("sb,hot", [(1 << 13, -1.0), (1 << 15, 12.0)])
 def test_exchange_mode_line(sb, hot):
     """Bulk-exchange mode, 4 shards in one process: pure exchange with super-batches of 2^13 samples per shard, and the
