@@ -425,6 +425,67 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go
     for (uint64_t done = 0; done < my_jobs; done += 32) {
         const int nb = (int)min((uint64_t)32, my_jobs - done);
         batch_sample<true>(a.g, b, a.seed, stream, st, nb, lane);
+        if constexpr (kAtomicRows<C>) {
+            // fp32 tables. A sample touches only three rows (1.5 KB at dim 128): one sample per warp at a time leaves the
+            // memory system idle (ncu r2g: 41 % of DRAM peak, 61 % of the stall samples waiting on the row gathers), so the rows
+            // of G consecutive samples are gathered together and the samples then applied in stream order. Every row takes its
+            // delta with red.global.add (kernels.cuh, kAtomicRows): nothing is lost when many warps hit the same popular item
+            // row, and coinciding rows simply receive both deltas.
+            using A = Ar<T>;
+            constexpr int G = C::EPL <= 4 ? 4 : 2;
+            for (int s0 = 0; s0 < nb; s0 += G) {
+                Row<C> v[G], p[G], n[G];
+                int iu[G], ip[G], in_[G];  // (ids, not pointers: 12 ints instead of 24 address registers)
+                bool ok[G];
+#pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    ok[k] = s0 + k < nb;
+                    if (ok[k]) {
+                        const int* sid = b.ids + (s0 + k) * b.idw;
+                        ok[k] = sid[1] >= 0;
+                        if (ok[k]) {
+                            iu[k] = sid[0];
+                            ip[k] = sid[1];
+                            in_[k] = sid[2];
+                            v[k].load_ca(a.Wv + (size_t)iu[k] * dim, lane, dim);
+                            p[k].load_ca(a.Wc + (size_t)ip[k] * dim, lane, dim);
+                            n[k].load_ca(a.Wc + (size_t)in_[k] * dim, lane, dim);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < G; ++k)
+                    if (ok[k]) {
+                        pin(v[k]);
+                        pin(p[k]);
+                        pin(n[k]);
+                    }
+#pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    if (!ok[k]) continue;
+                    const T alpha = (T)st.alpha;
+                    const T la = A::mul(a.lambda, alpha);
+                    Row<C> pn2[2] = {p[k], n[k]};
+                    T sc[2];
+                    dots<C, 2>(v[k], pn2, 2, sc);  // posScore, negScore (optimizer.go:95-100)
+                    const T gc = A::mul(alpha, fast_sigmoid<T>(lut, A::sub(sc[1], sc[0])));
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) {
+                        const T ve = v[k].x[e], pe = p[k].x[e], ne = n[k].x[e];
+                        v[k].x[e] = A::msub(A::mul(gc, A::sub(pe, ne)), la, ve);  // grad - (lambda*alpha)*w
+                        p[k].x[e] = A::msub(A::mul(gc, ve), la, pe);
+                        n[k].x[e] = A::msub(A::mul(-gc, ve), la, ne);
+                    }
+                    row_red_add<C>(a.Wv + (size_t)iu[k] * dim, v[k], lane, dim);
+                    row_red_add<C>(a.Wc + (size_t)ip[k] * dim, p[k], lane, dim);
+                    row_red_add<C>(a.Wc + (size_t)in_[k] * dim, n[k], lane, dim);
+                    st.count++;
+                    st.pairs++;
+                    sched_tick(st, a.sched);
+                }
+            }
+            continue;
+        }
         for (int s = 0; s < nb; ++s) {
             if (s + kLinePrefetch < nb) prefetch_local<T>(a.Wv, a.Wc, b.ids + (s + kLinePrefetch) * b.idw, b.idw, dim, lane);
             const int* sid = b.ids + s * b.idw;
@@ -449,20 +510,7 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go
             T sc[2];
             dots<C, 2>(v, pn2, 2, sc);  // posScore, negScore (optimizer.go:95-100)
             const T gc = A::mul(alpha, fast_sigmoid<T>(lut, A::sub(sc[1], sc[0])));
-            if constexpr (kAtomicRows<C>) {
-                // fp32 tables: the three rows take their deltas with red.global.add (kernels.cuh, kAtomicRows): nothing is lost
-                // when many warps hit the same popular item row, and coinciding rows simply receive both deltas
-#pragma unroll
-                for (int e = 0; e < C::EPL; ++e) {
-                    const T ve = v.x[e], pe = p.x[e], ne = n.x[e];
-                    v.x[e] = A::msub(A::mul(gc, A::sub(pe, ne)), la, ve);  // grad - (lambda*alpha)*w
-                    p.x[e] = A::msub(A::mul(gc, ve), la, pe);
-                    n.x[e] = A::msub(A::mul(-gc, ve), la, ne);
-                }
-                row_red_add<C>(pv, v, lane, dim);
-                row_red_add<C>(pp, p, lane, dim);
-                row_red_add<C>(pn, n, lane, dim);
-            } else if (!valias) {
+            if (!valias) {
 #pragma unroll
                 for (int e = 0; e < C::EPL; ++e) {
                     const T vg = A::mul(gc, A::sub(p.x[e], n.x[e]));
