@@ -408,6 +408,9 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
 // Go BPR: BPR.Train (internal/models/bpr/bpr.go:84-131) + UpdateBPRPair (pkg/pronet/optimizer.go:87-117).
 // 5 words per sample (K = 1); ids row = user, pos, neg. Users live in Wv, items in Wc.
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef SMORE_BPR_GROUP
+#define SMORE_BPR_GROUP 1
+#endif
 template <class C>
 __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go(TrainArgs<typename C::T> a) {
     using T = typename C::T;
@@ -426,63 +429,64 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_bpr_go
         const int nb = (int)min((uint64_t)32, my_jobs - done);
         batch_sample<true>(a.g, b, a.seed, stream, st, nb, lane);
         if constexpr (kAtomicRows<C>) {
-            // fp32 tables. A sample touches only three rows (1.5 KB at dim 128): one sample per warp at a time leaves the
-            // memory system idle (ncu r2g: 41 % of DRAM peak, 61 % of the stall samples waiting on the row gathers), so the rows
-            // of G consecutive samples are gathered together and the samples then applied in stream order. Every row takes its
-            // delta with red.global.add (kernels.cuh, kAtomicRows): nothing is lost when many warps hit the same popular item
-            // row, and coinciding rows simply receive both deltas.
+            // fp32 tables: every row takes its delta with red.global.add (kernels.cuh, kAtomicRows). On a Zipf catalogue the
+            // few hottest ITEM rows bound the kernel: each of the 3 552 warps sends its own `red` to the same 512 bytes, and
+            // same-address atomics serialise in the L2 slice (measured: throughput x share of the top item = ~100 M row
+            // updates/s on Zipf(1.0), 1.8 G samples/s on a flat catalogue). The 32 samples of a batch are therefore grouped
+            // by positive item (__match_any_sync): the item row is gathered ONCE per group, carried in registers from one
+            // member to the next (each member sees its predecessors' updates, as a sequential worker would) and written back
+            // with ONE `red` of the accumulated delta. Samples of different items keep their stream order.
             using A = Ar<T>;
-            constexpr int G = C::EPL <= 4 ? 4 : 2;
-            for (int s0 = 0; s0 < nb; s0 += G) {
-                Row<C> v[G], p[G], n[G];
-                int iu[G], ip[G], in_[G];  // (ids, not pointers: 12 ints instead of 24 address registers)
-                bool ok[G];
-#pragma unroll
-                for (int k = 0; k < G; ++k) {
-                    ok[k] = s0 + k < nb;
-                    if (ok[k]) {
-                        const int* sid = b.ids + (s0 + k) * b.idw;
-                        ok[k] = sid[1] >= 0;
-                        if (ok[k]) {
-                            iu[k] = sid[0];
-                            ip[k] = sid[1];
-                            in_[k] = sid[2];
-                            v[k].load_ca(a.Wv + (size_t)iu[k] * dim, lane, dim);
-                            p[k].load_ca(a.Wc + (size_t)ip[k] * dim, lane, dim);
-                            n[k].load_ca(a.Wc + (size_t)in_[k] * dim, lane, dim);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < G; ++k)
-                    if (ok[k]) {
-                        pin(v[k]);
-                        pin(p[k]);
-                        pin(n[k]);
-                    }
-#pragma unroll
-                for (int k = 0; k < G; ++k) {
-                    if (!ok[k]) continue;
+            int my_user = 0, my_pos = -1 - lane, my_neg = 0;
+            if (lane < nb) {
+                const int* sid = b.ids + lane * b.idw;
+                my_user = sid[0];
+                if (sid[1] >= 0) my_pos = sid[1];
+                my_neg = sid[2];
+            }
+            unsigned todo = __ballot_sync(kFull, my_pos >= 0);
+            // (one warp = the DETERMINISTIC mode: the samples keep the reference's order one by one)
+            const unsigned my_grp = (SMORE_BPR_GROUP && a.n_warps > 1) ? __match_any_sync(kFull, my_pos) : 1u << lane;
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                unsigned grp = __shfl_sync(kFull, my_grp, leader) & todo;
+                todo &= ~grp;
+                T* pp = a.Wc + (size_t)__shfl_sync(kFull, my_pos, leader) * dim;
+                Row<C> p, dp;
+                p.load_ca(pp, lane, dim);
+                dp.zero();
+                while (grp) {
+                    const int s = __ffs(grp) - 1;
+                    grp &= grp - 1;
+                    T* pv = a.Wv + (size_t)__shfl_sync(kFull, my_user, s) * dim;
+                    T* pn = a.Wc + (size_t)__shfl_sync(kFull, my_neg, s) * dim;
+                    Row<C> v, n;
+                    v.load_ca(pv, lane, dim);
+                    n.load_ca(pn, lane, dim);
+                    pin(v);
+                    pin(n);
                     const T alpha = (T)st.alpha;
                     const T la = A::mul(a.lambda, alpha);
-                    Row<C> pn2[2] = {p[k], n[k]};
+                    Row<C> pn2[2] = {p, n};
                     T sc[2];
-                    dots<C, 2>(v[k], pn2, 2, sc);  // posScore, negScore (optimizer.go:95-100)
+                    dots<C, 2>(v, pn2, 2, sc);  // posScore, negScore (optimizer.go:95-100)
                     const T gc = A::mul(alpha, fast_sigmoid<T>(lut, A::sub(sc[1], sc[0])));
 #pragma unroll
                     for (int e = 0; e < C::EPL; ++e) {
-                        const T ve = v[k].x[e], pe = p[k].x[e], ne = n[k].x[e];
-                        v[k].x[e] = A::msub(A::mul(gc, A::sub(pe, ne)), la, ve);  // grad - (lambda*alpha)*w
-                        p[k].x[e] = A::msub(A::mul(gc, ve), la, pe);
-                        n[k].x[e] = A::msub(A::mul(-gc, ve), la, ne);
+                        const T ve = v.x[e], pe = p.x[e], ne = n.x[e];
+                        v.x[e] = A::msub(A::mul(gc, A::sub(pe, ne)), la, ve);  // grad - (lambda*alpha)*w
+                        const T d = A::msub(A::mul(gc, ve), la, pe);
+                        dp.x[e] = A::add(dp.x[e], d);
+                        p.x[e] = A::add(pe, d);
+                        n.x[e] = A::msub(A::mul(-gc, ve), la, ne);
                     }
-                    row_red_add<C>(a.Wv + (size_t)iu[k] * dim, v[k], lane, dim);
-                    row_red_add<C>(a.Wc + (size_t)ip[k] * dim, p[k], lane, dim);
-                    row_red_add<C>(a.Wc + (size_t)in_[k] * dim, n[k], lane, dim);
+                    row_red_add<C>(pv, v, lane, dim);
+                    row_red_add<C>(pn, n, lane, dim);
                     st.count++;
                     st.pairs++;
                     sched_tick(st, a.sched);
                 }
+                row_red_add<C>(pp, dp, lane, dim);
             }
             continue;
         }

@@ -505,8 +505,16 @@ __device__ __forceinline__ void draw_windows(DrawRing& ring, int len, int window
 
 // DeepWalk / Walklets: DeepWalk::Train (src/model/DeepWalk.cpp:133-150), Walklets::Train (Walklets.cpp:42-60),
 // DeepWalk.Train (deepwalk.go:110-134). One warp per walk; pairs are enumerated in-warp and never touch HBM.
+#ifndef SMORE_WALK_MINBLOCKS
+#define SMORE_WALK_MINBLOCKS 2
+#endif
+// resident CTAs per SM the register allocator must allow for the walk-type kernels (rows <= 16 B per lane: fp32 dim <= 128)
 template <class C>
-__global__ void __launch_bounds__(kBlockThreads) k_walk(TrainArgs<typename C::T> a) {
+constexpr int walk_min_blocks() {
+    return C::EPL * (int)sizeof(typename C::T) <= 16 ? SMORE_WALK_MINBLOCKS : C::EPL * (int)sizeof(typename C::T) <= 32 ? 2 : 1;
+}
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_walk(TrainArgs<typename C::T> a) {
     using T = typename C::T;
     uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
     T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
@@ -732,7 +740,7 @@ __device__ __forceinline__ void update_factorized_pair(const TV& tv, const TC& t
 // v1). The number of words a sample consumes depends on the walk (a sink ends it), so draws come from the sequential
 // ring, one warp = one reference worker.
 template <class C>
-__global__ void __launch_bounds__(kBlockThreads) k_hpe(TrainArgs<typename C::T> a) {
+__global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_hpe(TrainArgs<typename C::T> a) {
     using T = typename C::T;
     uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
     T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
