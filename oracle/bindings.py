@@ -116,6 +116,11 @@ class Oracle:
             L.orc_train_deepwalk_go.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64, u64, u64,
                                                 i64, vp]
             L.orc_train_deepwalk_go.restype = u64
+            L.orc_train_node2vec_go.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64, f64, f64, u64, u64,
+                                                i64, vp]
+            L.orc_train_node2vec_go.restype = u64
+            L.orc_biased_walk_go.argtypes = [vp, i64, C.c_int, f64, f64, u64, u64, vp, vp]
+            L.orc_biased_walk_go.restype = i64
             L.orc_update_pair_cpp.argtypes = [vp, vp, vp, i64, i64, C.c_int, C.c_int, f64, u64, u64]
             L.orc_update_pair_cpp.restype = u64
             L.orc_update_bpr_pair_cpp.argtypes = [vp, vp, i64, i64, i64, C.c_int, f64, u64, u64]
@@ -267,6 +272,18 @@ class OracleGraph:
         pos = self.L.orc_train_deepwalk_go(self.h, _ptr(Wv), _ptr(Wc), Wv.shape[1], walk_times, walk_steps, window, K,
                                            alpha, seed, stream, max_walks, C.byref(pairs))
         return pos, pairs.value
+
+    def train_node2vec_go(self, Wv, Wc, walk_times, walk_steps, window, K, alpha, p, q, seed, stream=0, max_walks=-1):
+        pairs = u64(0)
+        pos = self.L.orc_train_node2vec_go(self.h, _ptr(Wv), _ptr(Wc), Wv.shape[1], walk_times, walk_steps, window, K,
+                                           alpha, p, q, seed, stream, max_walks, C.byref(pairs))
+        return pos, pairs.value
+
+    def biased_walk_go(self, start, steps, p, q, seed, stream=0):
+        out = np.zeros(steps + 1, dtype=np.int64)
+        words = u64(0)
+        n = self.L.orc_biased_walk_go(self.h, start, steps, p, q, seed, stream, _ptr(out), C.byref(words))
+        return out[:n], words.value
 
     def update_pair_cpp(self, Wv, Wc, v, c, K, alpha, seed, stream=0):
         return self.L.orc_update_pair_cpp(self.h, _ptr(Wv), _ptr(Wc), v, c, Wv.shape[1], K, alpha, seed, stream)

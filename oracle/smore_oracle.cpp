@@ -253,6 +253,49 @@ struct Graph {
             }
         }
     }
+    // node2vec (Go tree only): internal/models/node2vec/node2vec.go:113-173. areNeighbors is a linear scan of prev's adjacency.
+    bool are_neighbors(int64_t a, int64_t b) const {
+        for (int64_t e = off[a]; e < off[a + 1]; ++e)
+            if (col[e] == b) return true;
+        return false;
+    }
+    int64_t biased_target_sample(int64_t prev, int64_t cur, double p, double q, Draws& d, std::vector<double>& bw) const {
+        int64_t branch = off[cur + 1] - off[cur];
+        if (branch == 0) return -1;
+        bw.resize((size_t)branch);
+        double total = 0.0;
+        for (int64_t i = 0; i < branch; ++i) {
+            int64_t nb = col[off[cur] + i];
+            double bias;
+            if (nb == prev) bias = 1.0 / p;
+            else if (are_neighbors(prev, nb)) bias = 1.0;
+            else bias = 1.0 / q;
+            bw[(size_t)i] = w[off[cur] + i] * bias;
+            total += bw[(size_t)i];
+        }
+        if (total == 0) return col[off[cur] + d.index(branch)];
+        double r = d.prob() * total;
+        double cum = 0.0;
+        for (int64_t i = 0; i < branch; ++i) {
+            cum += bw[(size_t)i];
+            if (r <= cum) return col[off[cur] + i];
+        }
+        return col[off[cur + 1] - 1];
+    }
+    void biased_random_walk(int64_t start, int steps, double p, double q, Draws& d, std::vector<int64_t>& walk,
+                            std::vector<double>& bw) const {  // node2vec.go:82-110
+        walk.clear();
+        walk.push_back(start);
+        if (steps == 0) return;
+        int64_t first = target_sample(start, d);
+        if (first == -1) return;
+        walk.push_back(first);
+        for (int i = 1; i < steps; ++i) {
+            int64_t nxt = biased_target_sample(walk[walk.size() - 2], walk.back(), p, q, d, bw);
+            if (nxt == -1) break;
+            walk.push_back(nxt);
+        }
+    }
     void skip_grams(const std::vector<int64_t>& walk, int window, Draws& d, std::vector<int64_t>& pv,
                     std::vector<int64_t>& pc) const {
         pv.clear(); pc.clear();
@@ -989,6 +1032,53 @@ uint64_t orc_train_deepwalk_go(void* h, double* Wv, double* Wc, int dim, int wal
 done:
     if (pairs_out) *pairs_out = pairs;
     return d.s.pos;
+}
+
+// Go node2vec: internal/models/node2vec/node2vec.go:176-260 (one worker): DeepWalk.Train with the biased second-order walk.
+uint64_t orc_train_node2vec_go(void* h, double* Wv, double* Wc, int dim, int walk_times, int walk_steps, int window,
+                               int K, double alpha, double p, double q, uint64_t seed, uint64_t stream, int64_t max_walks,
+                               uint64_t* pairs_out) {
+    Graph* g = (Graph*)h;
+    Draws d(seed, stream);
+    int64_t total = (int64_t)walk_times * g->V, count = 0;
+    double alpha_min = alpha * 0.0001, cur = alpha;
+    unsigned long long pairs = 0;
+    std::vector<int64_t> keys(g->V), walk, pv, pc;
+    std::vector<double> a, b, c, bw;
+    for (int t = 0; t < walk_times; ++t) {
+        for (int64_t v = 0; v < g->V; ++v) keys[v] = v;
+        for (int64_t v = 0; v < g->V; ++v) {
+            int64_t j = v + d.shuffle_index(g->V - v);
+            std::swap(keys[v], keys[j]);
+        }
+        for (int64_t v = 0; v < g->V; ++v) {
+            if (max_walks >= 0 && count >= max_walks) goto done;
+            g->biased_random_walk(keys[v], walk_steps, p, q, d, walk, bw);
+            g->skip_grams(walk, window, d, pv, pc);
+            for (size_t i = 0; i < pv.size(); ++i) g->update_pair_go(Wv, Wc, pv[i], pc[i], dim, K, cur, d, a, b, c);
+            pairs += pv.size();
+            count++;
+            if (count % MONITOR == 0) {
+                cur = alpha * (1.0 - (double)count / (double)total);
+                if (cur < alpha_min) cur = alpha_min;
+            }
+        }
+    }
+done:
+    if (pairs_out) *pairs_out = pairs;
+    return d.s.pos;
+}
+// one biased walk from `start` (parity hook)
+int64_t orc_biased_walk_go(void* h, int64_t start, int steps, double p, double q, uint64_t seed, uint64_t stream, int64_t* out,
+                           uint64_t* words) {
+    Graph* g = (Graph*)h;
+    Draws d(seed, stream);
+    std::vector<int64_t> walk;
+    std::vector<double> bw;
+    g->biased_random_walk(start, steps, p, q, d, walk, bw);
+    for (size_t i = 0; i < walk.size(); ++i) out[i] = walk[i];
+    if (words) *words = d.s.pos;
+    return (int64_t)walk.size();
 }
 
 // ---- step-level entry points (unit parity with the compiled reference's Update*Pair) ------------------------

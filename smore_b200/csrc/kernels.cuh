@@ -506,7 +506,7 @@ __device__ __forceinline__ void draw_windows(DrawRing& ring, int len, int window
 // DeepWalk / Walklets: DeepWalk::Train (src/model/DeepWalk.cpp:133-150), Walklets::Train (Walklets.cpp:42-60),
 // DeepWalk.Train (deepwalk.go:110-134). One warp per walk; pairs are enumerated in-warp and never touch HBM.
 #ifndef SMORE_WALK_MINBLOCKS
-#define SMORE_WALK_MINBLOCKS 2
+#define SMORE_WALK_MINBLOCKS 3
 #endif
 // resident CTAs per SM the register allocator must allow for the walk-type kernels (rows <= 16 B per lane: fp32 dim <= 128)
 template <class C>

@@ -288,3 +288,72 @@ def train_deepwalk(pn, wv, wc, dim, walk_times, walk_steps, window, K, alpha, rn
             count += 1
             cur = _schedule(count, total, alpha, cur)
     return rng.pos, pairs
+
+
+# ---- node2vec (internal/models/node2vec/node2vec.go) -----------------------------------------------------------------
+def are_neighbors(pn, vid1, vid2):  # node2vec.go:165-173 (a linear scan there)
+    return vid2 in pn.graph.get(vid1, [])
+
+
+def biased_target_sample(pn, prev, current, p, q, rng):  # node2vec.go:113-162
+    neighbors = pn.graph.get(current, [])
+    if not neighbors:
+        return -1
+    weights = pn.edge[current]
+    biased = []
+    total = 0.0
+    for i, nb in enumerate(neighbors):
+        base = weights[i] if weights else 1.0
+        if nb == prev:
+            bias = 1.0 / p
+        elif are_neighbors(pn, prev, nb):
+            bias = 1.0
+        else:
+            bias = 1.0 / q
+        biased.append(base * bias)
+        total += biased[i]
+    if total == 0:
+        return neighbors[rng.intn(len(neighbors))]
+    r = rng.float64() * total
+    cum = 0.0
+    for i, w in enumerate(biased):
+        cum += w
+        if r <= cum:
+            return neighbors[i]
+    return neighbors[-1]
+
+
+def biased_random_walk(pn, start, steps, p, q, rng):  # node2vec.go:82-110
+    walk = [start]
+    if steps == 0:
+        return walk
+    first = pn.target_sample(start, rng)
+    if first == -1:
+        return walk
+    walk.append(first)
+    for _ in range(1, steps):
+        nxt = biased_target_sample(pn, walk[-2], walk[-1], p, q, rng)
+        if nxt == -1:
+            break
+        walk.append(nxt)
+    return walk
+
+
+def train_node2vec(pn, wv, wc, dim, walk_times, walk_steps, window, K, alpha, p, q, rng, shuffle):
+    """Node2Vec.Train (node2vec.go:176-260), one worker: DeepWalk.Train with the biased walk."""
+    total = walk_times * pn.max_vid
+    cur, count, pairs = alpha, 0, 0
+    for _ in range(walk_times):
+        keys = list(range(pn.max_vid))
+        for vid in range(pn.max_vid):
+            j = vid + shuffle.intn(pn.max_vid - vid)
+            keys[vid], keys[j] = keys[j], keys[vid]
+        for vid in range(pn.max_vid):
+            walk = biased_random_walk(pn, keys[vid], walk_steps, p, q, rng)
+            vs, cs = pn.skip_grams(walk, window)
+            for v, c in zip(vs, cs):
+                pn.update_pair(wv, wc, v, c, dim, K, cur, rng)
+            pairs += len(vs)
+            count += 1
+            cur = _schedule(count, total, alpha, cur)
+    return rng.pos, pairs
