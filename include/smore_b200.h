@@ -297,6 +297,8 @@ typedef struct {
      * gate at 2 / 4 / 8 shards; on heavy-tailed graphs split keeps ~1 point more recall@10 when rotating-shard episodes
      * are long (many samples per vertex per episode). Ignored on unsharded graphs. */
     int neg_mode;
+    /* node2vec (cmd/node2vec/main.go:21-22): return parameter p, in-out parameter q */
+    double n2v_p, n2v_q;
 } smore_train_params;
 #define SMORE_PAIRING_AUTO 0
 #define SMORE_PAIRING_COUPLED 1
@@ -333,6 +335,10 @@ int smore_train_hoprec(smore_model_t m, const smore_train_params* p);
 /* DeepWalk::Train (src/model/DeepWalk.cpp:98-155) / DeepWalk.Train (internal/models/deepwalk/deepwalk.go:61-141):
  * on-device RandomWalk + SkipGrams + UpdatePairs. */
 int smore_train_deepwalk(smore_model_t m, const smore_train_params* p);
+/* Node2Vec.Train (internal/models/node2vec/node2vec.go:82-260; Go tree only): DeepWalk.Train with the biased second-order
+ * walk -- first step TargetSample, then per step weight * (1/p for the previous vertex | 1 for a neighbour of it | 1/q) summed
+ * and scanned in adjacency order, one draw per step -- fixed full window, UpdatePairs. params.n2v_p / n2v_q. */
+int smore_train_node2vec(smore_model_t m, const smore_train_params* p);
 /* HPE::Train (src/model/HPE.cpp:93-147): SourceSample -> TargetSample -> UpdateCommunity (src/proNet.cpp:3018-3054, the
  * context walks on for walk_steps steps; Opt_SigmoidRegSGD :1332-1351 with reg = params.lambda) -> UpdatePair with the
  * roles swapped. C++ only (the Go hpe model is LINE-2 with UpdatePair, hpe.go:97-107: use smore_train_line). */

@@ -41,7 +41,7 @@ EXPORTS = [
     "smore_model_set_rows_f32_async", "smore_model_get_rows_f32_async", "smore_model_wait_copies",
     "smore_train_line_group", "smore_exchange_stats", "smore_debug_sm_partition", "smore_model_save_weights", "smore_format_rows",
     "smore_model_load_pretrain", "smore_model_save_checkpoint", "smore_model_load_checkpoint", "smore_model_progress", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
-    "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf", "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_stats",
+    "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf", "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_node2vec", "smore_train_stats",
 ]
 
 
@@ -56,6 +56,7 @@ class TrainParams(C.Structure):
         ("walk_times", C.c_int), ("walk_steps", C.c_int), ("window_min", C.c_int), ("window_max", C.c_int),
         ("max_warps", C.c_int), ("max_walks", i64), ("sched_total", u64), ("sched_offset", u64),
         ("xi", f64), ("omega", f64), ("eta", C.c_int), ("neg_mode", C.c_int),
+        ("n2v_p", f64), ("n2v_q", f64),
     ]
 
 
@@ -139,7 +140,7 @@ def lib():
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
         L.smore_train_params_default.restype = None
         for name in ("smore_train_line", "smore_train_bpr", "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf",
-                     "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets"):
+                     "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_node2vec"):
             getattr(L, name).argtypes = [vp, C.POINTER(TrainParams)]
         L.smore_train_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(f64),
                                         C.POINTER(f64)]
@@ -506,6 +507,7 @@ class Model:
     def train_skewopt(self, p): return self._train(lib().smore_train_skewopt, p)
     def train_deepwalk(self, p): return self._train(lib().smore_train_deepwalk, p)
     def train_walklets(self, p): return self._train(lib().smore_train_walklets, p)
+    def train_node2vec(self, p): return self._train(lib().smore_train_node2vec, p)
 
     def stats(self):
         s, pr, w0, ms, tr = u64(), u64(), u64(), f64(), f64()

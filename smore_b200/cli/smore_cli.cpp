@@ -70,7 +70,7 @@ int die(const char* what) {
 
 void usage() {
     printf("[smore_b200]\n\tB200-native SMORe trainers (LINE, DeepWalk, Walklets, BPR, WARP, HOP-Rec)\n\n"
-           "Usage:\n\tsmore <line|deepwalk|walklets|bpr|warp|hoprec|hpe|mf|skewopt> -train net.txt -save rep.txt [options]\n\n"
+           "Usage:\n\tsmore <line|deepwalk|walklets|node2vec|bpr|warp|hoprec|hpe|mf|skewopt> -train net.txt -save rep.txt [options]\n\n"
            "Options Description:\n"
            "\t-train <string>\n\t\tTrain the Network data\n"
            "\t-save <string>\n\t\tSave the representation data\n"
@@ -81,6 +81,7 @@ void usage() {
            "\t-order <int>\n\t\tLINE: order of proximity (1 or 2); default is 2\n"
            "\t-sample_times <int>\n\t\tNumber of training samples (cpp: *Million, go: *edge lines); default is 10\n"
            "\t-walk_times <int> -walk_steps <int> -window_size <int> -window_min <int> -window_max <int>\n"
+           "\t-p <float> -q <float>\n\t\tnode2vec return / in-out parameters; defaults 1, 1 (window 10, walk_steps 80)\n"
            "\t-lambda <float>\n\t\tGo BPR regularisation; default is 0.001\n"
            "\t-reg <float>\n\t\tHPE / MF regularisation; default is 0.01\n"
            "\t-xi <float> -omega <float> -eta <int>\n\t\tSkew-OPT margin shift / scale / power; defaults 10, 3, 3\n"
@@ -98,7 +99,7 @@ int main(int argc, char** argv) {
     int first = 1;
     const char* base = strrchr(argv[0], '/');
     base = base ? base + 1 : argv[0];
-    for (const char* m : {"line", "deepwalk", "walklets", "bpr", "warp", "hoprec", "hpe", "mf", "skewopt"})
+    for (const char* m : {"line", "deepwalk", "walklets", "node2vec", "bpr", "warp", "hoprec", "hpe", "mf", "skewopt"})
         if (!strcmp(base, m)) model = m;
     if (model.empty()) {
         if (argc < 2 || argv[1][0] == '-') {
@@ -113,13 +114,17 @@ int main(int argc, char** argv) {
         return 0;
     }
     Args a = parse(argc, argv, first);
-    const bool has_go_cli = model == "line" || model == "deepwalk" || model == "bpr";
+    const bool has_go_cli = model == "line" || model == "deepwalk" || model == "bpr" || model == "node2vec";
     if (!has_go_cli && model != "walklets" && model != "warp" && model != "hoprec" && model != "hpe" && model != "mf" && model != "skewopt") {
         fprintf(stderr, "smore: unknown model '%s'\n", model.c_str());
         return 1;
     }
     const std::string sem_s = a.str("semantics", has_go_cli ? "go" : "cpp");
     const int sem = sem_s == "go" ? SMORE_SEM_GO : SMORE_SEM_CPP;
+    if (sem == SMORE_SEM_CPP && model == "node2vec") {
+        fprintf(stderr, "smore: node2vec exists only in the Go tree; use -semantics go\n");
+        return 1;
+    }
     if (sem == SMORE_SEM_GO && !has_go_cli) {
         fprintf(stderr, "smore: %s exists only in the C++ tree; use -semantics cpp\n", model.c_str());
         return 1;
@@ -167,9 +172,12 @@ int main(int argc, char** argv) {
     p.eta = (int)a.num("eta", 3);
     p.walk_times = (int)a.num("walk_times", 10);
     // cli/deepwalk.cpp:56 defaults walk_steps to 5 (sic), cli/walklets.cpp:54 and cmd/deepwalk/main.go:20 to 40
-    p.walk_steps = (int)a.num("walk_steps", model == "hoprec" || model == "hpe" ? 5 : (model == "deepwalk" && sem == SMORE_SEM_CPP ? 5 : 40));
+    // cmd/node2vec/main.go:18-22: window_size 10, walk_steps 80, p = q = 1
+    p.walk_steps = (int)a.num("walk_steps", model == "node2vec" ? 80 : model == "hoprec" || model == "hpe" ? 5 : (model == "deepwalk" && sem == SMORE_SEM_CPP ? 5 : 40));
     p.window_min = (int)a.num("window_min", model == "walklets" ? 2 : 1);
-    p.window_max = (int)a.num(model == "walklets" ? "window_max" : "window_size", 5);
+    p.window_max = (int)a.num(model == "walklets" ? "window_max" : "window_size", model == "node2vec" ? 10 : 5);
+    p.n2v_p = a.real("p", 1.0);
+    p.n2v_q = a.real("q", 1.0);
     // LINE.cpp:119 (sample_times * 1e6) vs line.go:85 (sample_times * MaxLine)
     p.total = sem == SMORE_SEM_CPP ? (uint64_t)sample_times * 1000000ull : (uint64_t)sample_times * (uint64_t)n_lines;
 
@@ -209,7 +217,7 @@ int main(int argc, char** argv) {
         if (smore_model_load_checkpoint(m, a.str("resume", "").c_str())) return die("LoadCheckpoint");
         uint64_t ck_seed = 0, ck_stream = 0, ck_total = 0, ck_done = 0;
         smore_model_progress(m, &ck_seed, &ck_stream, &ck_total, &ck_done);
-        const bool walk = model == "deepwalk" || model == "walklets";
+        const bool walk = model == "deepwalk" || model == "walklets" || model == "node2vec";
         if (!walk && ck_total == p.total && ck_done > 0 && ck_done < ck_total) {
             resume_done = ck_done;
             resume_stream = ck_stream;
@@ -232,6 +240,7 @@ int main(int argc, char** argv) {
         if (model == "line") return smore_train_line(m, &q);
         if (model == "deepwalk") return smore_train_deepwalk(m, &q);
         if (model == "walklets") return smore_train_walklets(m, &q);
+        if (model == "node2vec") return smore_train_node2vec(m, &q);
         if (model == "bpr") return smore_train_bpr(m, &q);
         if (model == "warp") return smore_train_warp(m, &q);
         if (model == "hpe") return smore_train_hpe(m, &q);
@@ -241,7 +250,7 @@ int main(int argc, char** argv) {
     };
     uint64_t samples = 0, pairs = 0;
     double ms = 0;
-    const bool walk_model = model == "deepwalk" || model == "walklets";
+    const bool walk_model = model == "deepwalk" || model == "walklets" || model == "node2vec";
     const int chunks = (p.mode == SMORE_MODE_HOGWILD && !walk_model && p.total >= 2000000) ? 20 : 1;
     const long ckpt_every = a.num("checkpoint_every", 0);  // chunks between intermediate checkpoints (0: only at the end)
     double last_alpha = p.alpha;

@@ -30,6 +30,8 @@ struct GraphDev {
     const uint2* ctx_at;       // E   C++ semantics: per-vertex sub-tables, alias already a vertex id
     const double* prefix;      // E   Go semantics: running sum of weights inside each vertex' slice
     const int32_t* field;      // V   (HOP-Rec)
+    const int32_t* col_sorted; // E   node2vec: every adjacency slice sorted ascending (membership tests by binary search)
+    const double* w;           // E   node2vec: raw edge weights in adjacency order
     int sem;                   // SMORE_SEM_*
     // Row sharding (multi-GPU, one process per GPU): vertex v is owned by rank v & (world-1), its local row is
     // v >> shard_shift. The rank that owns the POSITIVE CONTEXT of a sample computes it: edge_at is an alias table over

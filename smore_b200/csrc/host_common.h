@@ -70,6 +70,8 @@ struct smore_graph_s {
     int64_t n_edge_local = 0;
     double* d_prefix = nullptr;
     int32_t* d_field = nullptr;
+    int32_t* d_col_sorted = nullptr;  // node2vec: adjacency slices sorted ascending (built on first use)
+    double* d_w = nullptr;            // node2vec: raw edge weights on the device
     double* d_lut64 = nullptr;
     float* d_lut32 = nullptr;
     // rotating shards (smore_graph_set_shard_rotating; rotation.cu): the vertex table is cut into nsub = 2*world
@@ -91,6 +93,7 @@ struct smore_graph_s {
         g.row_off = d_row_off; g.col = d_col;
         g.vertex_at = d_vat; g.negative_at = d_nat; g.ctx_at = d_cat;
         g.prefix = d_prefix; g.field = d_field; g.sem = sem;
+        g.col_sorted = d_col_sorted; g.w = d_w;
         g.n_neg = (uint32_t)(n_neg ? n_neg : n_local);
         g.neg_shift = neg_global ? 0 : shift; g.neg_rank = neg_global ? 0 : rank;
         g.edge_at = d_eat; g.edge_src = d_esrc; g.edge_dst = d_edst; g.n_edge_local = (uint32_t)n_edge_local;
@@ -101,7 +104,7 @@ struct smore_graph_s {
     ~smore_graph_s() {
         cudaFree(d_row_off); cudaFree(d_col); cudaFree(d_vat); cudaFree(d_nat); cudaFree(d_cat);
         cudaFree(d_prefix); cudaFree(d_field); cudaFree(d_lut64); cudaFree(d_lut32);
-        cudaFree(d_eat); cudaFree(d_esrc); cudaFree(d_edst); cudaFree(d_vsub);
+        cudaFree(d_eat); cudaFree(d_esrc); cudaFree(d_edst); cudaFree(d_vsub); cudaFree(d_col_sorted); cudaFree(d_w);
     }
 };
 
@@ -378,7 +381,7 @@ int train_line_t(smore_model_s* m, const smore_train_params* p);
 template <typename T>
 int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p, ExchTransport& tr);
 template <typename T>
-int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets);
+int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets, int n2v = 0);
 template <typename T>
 int train_hpe_t(smore_model_s* m, const smore_train_params* p);
 template <typename T>

@@ -72,6 +72,8 @@ struct TrainArgs {
     ExchDev x;  // bulk-exchange mode only
     T xi, omega;  // Skew-OPT
     int eta;
+    int n2v;   // node2vec: biased second-order walks (1/p, 1/q below)
+    double n2v_pinv, n2v_qinv;
     int vred;  // row-sharded peer-access mode: vertex rows take their delta with red.global.add instead of a full-row store
 };
 
@@ -492,6 +494,113 @@ __device__ __forceinline__ int random_walk(const GraphDev& g, DrawRing& ring, in
     return len;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// node2vec (Go tree only): biasedRandomWalk / biasedTargetSample / areNeighbors (internal/models/node2vec/node2vec.go:82-173).
+// The first step is a plain TargetSample; every further step weighs the neighbours of the current vertex by
+// weight * bias (bias = 1/p for the previous vertex, 1 for a neighbour of the previous vertex, 1/q otherwise), sums them in
+// adjacency order and scans `r <= cum`: one word per step. The warp computes the biased weights 32 neighbours at a time
+// (membership in the previous vertex' adjacency by binary search in a sorted copy: the reference scans linearly, the answer
+// is the same) and lane 0 accumulates them in adjacency order -- the same fp64 additions in the same order as the
+// reference, so the boundary decisions are the reference's. `buf`: 32 doubles of shared memory owned by this warp.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_neighbor_sorted(const GraphDev& g, int64_t a, int32_t b) {
+    int64_t lo = __ldg(g.row_off + a);
+    const int64_t end = __ldg(g.row_off + a + 1);
+    int64_t hi = end;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(g.col_sorted + mid) < b) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo < end && __ldg(g.col_sorted + lo) == b;
+}
+
+__device__ __forceinline__ double biased_weight(const GraphDev& g, int64_t e, int64_t prev, double pinv, double qinv) {
+    const int32_t nb = __ldg(g.col + e);
+    const double bias = nb == (int32_t)prev ? pinv : (is_neighbor_sorted(g, prev, nb) ? 1.0 : qinv);
+    return __dmul_rn(__ldg(g.w + e), bias);
+}
+
+__device__ __forceinline__ int biased_walk(const GraphDev& g, DrawRing& ring, int64_t start, int steps, int32_t* walk,
+                                           double* buf, int lane, double pinv, double qinv) {
+    if (lane == 0) walk[0] = (int32_t)start;
+    if (steps == 0) {
+        __syncwarp();
+        return 1;
+    }
+    ring.ensure();
+    int64_t first = -1;
+    uint32_t used = 0;
+    if (lane == 0) {
+        int u;
+        first = target_sample(g, start, ring.peek(0), ring.peek(1), u);
+        used = (uint32_t)u;
+    }
+    first = __shfl_sync(kFull, first, 0);
+    used = __shfl_sync(kFull, used, 0);
+    if (first < 0) {
+        __syncwarp();
+        return 1;
+    }
+    ring.advance(used);
+    if (lane == 0) walk[1] = (int32_t)first;
+    int len = 2;
+    int64_t prev = start, cur = first;
+    for (int i = 1; i < steps; ++i) {
+        const int64_t off = __ldg(g.row_off + cur);
+        const int64_t deg = __ldg(g.row_off + cur + 1) - off;
+        if (deg == 0) break;
+        ring.ensure();
+        double total = 0.0;
+        for (int64_t c0 = 0; c0 < deg; c0 += 32) {
+            buf[lane] = c0 + lane < deg ? biased_weight(g, off + c0 + lane, prev, pinv, qinv) : 0.0;
+            __syncwarp();
+            if (lane == 0) {
+                const int n = (int)min((int64_t)32, deg - c0);
+                for (int k = 0; k < n; ++k) total = __dadd_rn(total, buf[k]);
+            }
+            __syncwarp();
+        }
+        total = __shfl_sync(kFull, total, 0);
+        const uint32_t word = ring.peek(0);
+        ring.advance(1u);
+        int64_t pick = deg - 1;  // falls back to the last neighbour (node2vec.go:161)
+        if (total == 0.0) pick = (int64_t)index_draw(word, (uint32_t)deg);
+        else {
+            const double r = __dmul_rn((double)word * (1.0 / 4294967296.0), total);
+            double cum = 0.0;
+            for (int64_t c0 = 0; c0 < deg; c0 += 32) {
+                buf[lane] = c0 + lane < deg ? biased_weight(g, off + c0 + lane, prev, pinv, qinv) : 0.0;
+                __syncwarp();
+                int hit = -1;
+                if (lane == 0) {
+                    const int n = (int)min((int64_t)32, deg - c0);
+                    for (int k = 0; k < n; ++k) {
+                        cum = __dadd_rn(cum, buf[k]);
+                        if (r <= cum) {
+                            hit = k;
+                            break;
+                        }
+                    }
+                }
+                hit = __shfl_sync(kFull, hit, 0);
+                __syncwarp();
+                if (hit >= 0) {
+                    pick = c0 + hit;
+                    break;
+                }
+            }
+        }
+        const int64_t nxt = (int64_t)__ldg(g.col + off + pick);
+        if (lane == 0) walk[len] = (int32_t)nxt;
+        ++len;
+        prev = cur;
+        cur = nxt;
+    }
+    __syncwarp();
+    return len;
+}
+
 // SkipGrams' per-centre window draw (src/proNet.cpp:783): reduce[i] = index(window)+1, one word per position.
 __device__ __forceinline__ void draw_windows(DrawRing& ring, int len, int window, uint8_t* reduce, int lane) {
     for (int i0 = 0; i0 < len; i0 += 128) {
@@ -536,7 +645,9 @@ __global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_walk(Tr
     const int nrows = a.K + 1;
     for (int64_t wi = w; wi < a.n_walks; wi += a.n_warps) {
         int64_t start = (int64_t)__ldg(a.keys + wi);
-        int len = random_walk(g, ring, start, a.steps, walk, lane);
+        // (the Go tree draws no windows, so node2vec's per-warp scratch of 32 doubles shares the bytes of `reduce`)
+        int len = a.n2v ? biased_walk(g, ring, start, a.steps, walk, reinterpret_cast<double*>(reduce), lane, a.n2v_pinv, a.n2v_qinv)
+                        : random_walk(g, ring, start, a.steps, walk, lane);
         if (!go && !a.walklets) draw_windows(ring, len, a.w1, reduce, lane);
         T alpha = (T)st.alpha;
         for (int i = 0; i < len; ++i) {

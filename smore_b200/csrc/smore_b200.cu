@@ -241,6 +241,8 @@ void smore_train_params_default(smore_train_params* p) {
     p->window_min = 1;
     p->window_max = 5;
     p->max_walks = -1;
+    p->n2v_p = 1.0;  // cmd/node2vec/main.go:21-22
+    p->n2v_q = 1.0;
     p->xi = 10.0;  // cli/skewopt.cpp:53-54
     p->omega = 3.0;
     p->eta = 3;
@@ -1068,6 +1070,26 @@ static int train_walk_common(smore_model_t m, const smore_train_params* p, int w
     return m->dtype == SMORE_F64 ? train_walk_t<double>(m, p, walklets) : train_walk_t<float>(m, p, walklets);
 }
 int smore_train_deepwalk(smore_model_t m, const smore_train_params* p) { return train_walk_common(m, p, 0); }
+// Node2Vec.Train (internal/models/node2vec/node2vec.go:176-260): DeepWalk.Train with the biased second-order walk.
+int smore_train_node2vec(smore_model_t m, const smore_train_params* p) {
+    if (int rc = check_train(m, p, 2)) return rc;
+    if (p->semantics != SMORE_SEM_GO) return fail(SMORE_E_UNSUPPORTED, "node2vec exists only in the Go tree");
+    if (p->negative_samples < 0 || p->negative_samples > 31) return fail(SMORE_E_UNSUPPORTED, "negative_samples must be in [0,31]");
+    if (p->walk_steps < 0 || p->walk_steps + 1 > kMaxWalkLen) return fail(SMORE_E_UNSUPPORTED, "walk_steps must be < %d", kMaxWalkLen);
+    if (p->window_max < 1 || p->window_max > 255) return fail(SMORE_E_INVALID, "window must be in [1,255]");
+    if (p->walk_times < 1) return fail(SMORE_E_INVALID, "walk_times must be >= 1");
+    if (!(p->n2v_p > 0) || !(p->n2v_q > 0)) return fail(SMORE_E_INVALID, "node2vec: p and q must be > 0");
+    smore_graph_s* g = m->g;
+    if (!g->d_col_sorted) {  // first use: sorted adjacency slices (membership tests) and the raw weights go to the device
+        std::vector<int32_t> sorted(g->col);
+        parallel_for(g->V, 1 << 12, [&](int64_t vb, int64_t ve, int) {
+            for (int64_t v = vb; v < ve; ++v) std::sort(sorted.begin() + g->row_off[(size_t)v], sorted.begin() + g->row_off[(size_t)v + 1]);
+        });
+        if (int rc = dev_alloc_copy(&g->d_col_sorted, sorted.data(), sorted.size())) return rc;
+        if (int rc = dev_alloc_copy(&g->d_w, g->w.data(), g->w.size())) return rc;
+    }
+    return m->dtype == SMORE_F64 ? train_walk_t<double>(m, p, 0, 1) : train_walk_t<float>(m, p, 0, 1);
+}
 int smore_train_walklets(smore_model_t m, const smore_train_params* p) { return train_walk_common(m, p, 1); }
 
 int smore_train_hpe(smore_model_t m, const smore_train_params* p) {

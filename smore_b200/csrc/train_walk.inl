@@ -2,7 +2,7 @@
 #include "host_common.h"
 
 template <typename T>
-int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets) {
+int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets, int n2v) {
     return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
         using C = decltype(cfg);
         auto kern = k_walk<C>;
@@ -19,6 +19,13 @@ int train_walk_t(smore_model_s* m, const smore_train_params* p, int walklets) {
         a.w0 = p->window_min;
         a.w1 = p->window_max;
         a.walklets = walklets;
+        a.n2v = n2v;
+        if (n2v) {
+            a.n2v_pinv = 1.0 / p->n2v_p;  // the reference divides per neighbour (node2vec.go:133,139): the same IEEE quotient
+            a.n2v_qinv = 1.0 / p->n2v_q;
+            a.g.col_sorted = m->g->d_col_sorted;
+            a.g.w = m->g->d_w;
+        }
         if (m->keys_cap < V) {
             cudaFree(m->d_keys);
             m->d_keys = nullptr;

@@ -73,6 +73,18 @@ def main():
     pos, pairs = GO.train_deepwalk(pn, a, c, dim, 2, 12, 3, 5, 0.025, rng, sh)
     G["g60_dw_v"], G["g60_dw_c"], G["g60_dw_words"], G["g60_dw_pairs"] = np.array(a), np.array(c), pos, pairs
     G["g60_dw_args"] = np.array([2, 12, 3, 5])
+    # node2vec (Go tree only): biased second-order walks, p = 0.5 (returns likely), q = 2 (BFS-like)
+    a, c = Wv.tolist(), Wc.tolist()
+    rng, sh = GO.Words(SEED, 0), GO.Words(SEED, SHUFFLE_STREAM)
+    pos, pairs = GO.train_node2vec(pn, a, c, dim, 2, 12, 3, 5, 0.025, 0.5, 2.0, rng, sh)
+    G["g60_n2v_v"], G["g60_n2v_c"], G["g60_n2v_words"], G["g60_n2v_pairs"] = np.array(a), np.array(c), pos, pairs
+    G["g60_n2v_args"] = np.array([2, 12, 3, 5, 0.5, 2.0])
+    walks = []
+    for start in range(0, pn.max_vid, 5):
+        rng = GO.Words(SEED, 100 + start)
+        wk = GO.biased_random_walk(pn, start, 20, 4.0, 0.25, rng)
+        walks.append(np.array([start, rng.pos, len(wk)] + wk + [-1] * (21 - len(wk)), dtype=np.int64))
+    G["g60_n2v_walks"] = np.stack(walks)  # rows: start, words consumed, length, the walk (p = 4, q = 0.25, 20 steps, stream 100 + start)
 
     # ---- a 40 x 25 bipartite graph, directed (cmd/bpr default): BPR ----
     src, dst, w = graphs.bipartite_graph(40, 25, 500, seed=73)
@@ -87,6 +99,12 @@ def main():
     total = 30000
     pos = GO.train_bpr(pn, a, c, dim, total, total, 0.025, 0.001, rng)
     G["bip_bpr_v"], G["bip_bpr_c"], G["bip_bpr_words"], G["bip_bpr_total"] = np.array(a), np.array(c), pos, total
+    # node2vec on the DIRECTED bipartite graph: every item is a sink, walks stop after one step (node2vec.go:100-104)
+    a, c = Wv.tolist(), Wc.tolist()
+    rng, sh = GO.Words(SEED, 0), GO.Words(SEED, SHUFFLE_STREAM)
+    pos, pairs = GO.train_node2vec(pn, a, c, dim, 3, 10, 4, 5, 0.025, 2.0, 0.5, rng, sh)
+    G["bip_n2v_v"], G["bip_n2v_c"], G["bip_n2v_words"], G["bip_n2v_pairs"] = np.array(a), np.array(c), pos, pairs
+    G["bip_n2v_args"] = np.array([3, 10, 4, 5, 2.0, 0.5])
     np.savez_compressed(OUT, **G)
     print("wrote", OUT, {k: (v.shape if hasattr(v, "shape") else v) for k, v in G.items() if "words" in k or "pairs" in k})
 

@@ -89,6 +89,23 @@ def test_line_bpr_deepwalk_embeddings_match_the_python_restatement():
     assert np.array_equal(a, G["bip_bpr_v"]) and np.array_equal(c, G["bip_bpr_c"])
 
 
+def test_node2vec_matches_the_python_restatement():
+    """Go-only model: biased second-order walks (node2vec.go:82-173) and the training loop, incl. a directed graph whose
+    walks stop at sinks after one step."""
+    og, _ = _oracle(G["g60_src"], G["g60_dst"], G["g60_w"], 1)
+    for row in G["g60_n2v_walks"]:
+        start, words, n = int(row[0]), int(row[1]), int(row[2])
+        walk, used = og.biased_walk_go(start, 20, 4.0, 0.25, SEED, 100 + start)
+        assert used == words and walk.tolist() == row[3:3 + n].tolist()
+    for tag, und in (("g60", 1), ("bip", 0)):
+        og, _ = _oracle(G[f"{tag}_src"], G[f"{tag}_dst"], G[f"{tag}_w"], und)
+        wt, ws, win, K, p, q = G[f"{tag}_n2v_args"]
+        a, c = G[f"{tag}_init_v"].copy(), G[f"{tag}_init_c"].copy()
+        pos, pairs = og.train_node2vec_go(a, c, int(wt), int(ws), int(win), int(K), 0.025, float(p), float(q), SEED, 0)
+        assert pos == int(G[f"{tag}_n2v_words"]) and pairs == int(G[f"{tag}_n2v_pairs"])
+        assert np.array_equal(a, G[f"{tag}_n2v_v"]) and np.array_equal(c, G[f"{tag}_n2v_c"])
+
+
 def test_fixture_is_reproducible_from_the_restatement():
     """Re-runs the cheapest entry: the committed .npz is what go_restatement.py produces."""
     pn = GO.ProNet(G["bip_src"].tolist(), G["bip_dst"].tolist(), G["bip_w"].tolist(), False)

@@ -2,6 +2,7 @@
 (tests/golden/go_restatement.py -> golden_go_v1.npz): alias tables and sampler replays bit-exact, deterministic fp64
 embeddings of LINE order 1 / 2, BPR and DeepWalk bit-identical (north-star bar: 1e-5 relative)."""
 import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -78,3 +79,39 @@ def test_bpr():
     st = m.train_bpr(_params(total=int(G["bip_bpr_total"]), lambda_=0.001))
     assert st["words_stream0"] == int(G["bip_bpr_words"])
     assert np.array_equal(m.get_rows(0), G["bip_bpr_v"]) and np.array_equal(m.get_rows(1), G["bip_bpr_c"])
+
+
+@pytest.mark.parametrize("tag,und", [("g60", 1), ("bip", 0)])
+def test_node2vec(tag, und):
+    """Go-only model (internal/models/node2vec): deterministic fp64 embeddings bit-identical to the Python restatement, on
+    an undirected graph with hubs and parallel edges and on a directed one whose walks stop at sinks."""
+    g = _graph(G[f"{tag}_src"], G[f"{tag}_dst"], G[f"{tag}_w"], und)
+    wt, ws, win, K, p, q = G[f"{tag}_n2v_args"]
+    m = capi.Model(g, 8, 2, capi.F64)
+    m.set_rows(0, G[f"{tag}_init_v"]), m.set_rows(1, G[f"{tag}_init_c"])
+    st = m.train_node2vec(_params(walk_times=int(wt), walk_steps=int(ws), window_min=1, window_max=int(win), negative_samples=int(K),
+                                  n2v_p=float(p), n2v_q=float(q)))
+    assert st["words_stream0"] == int(G[f"{tag}_n2v_words"]) and st["pair_updates"] == int(G[f"{tag}_n2v_pairs"])
+    assert np.array_equal(m.get_rows(0), G[f"{tag}_n2v_v"]) and np.array_equal(m.get_rows(1), G[f"{tag}_n2v_c"])
+    # C++ semantics have no node2vec
+    gc = capi.Graph.from_csr(*B.edges_to_csr(G[f"{tag}_src"], G[f"{tag}_dst"], G[f"{tag}_w"], und)[:3])
+    mc = capi.Model(gc, 8, 2, capi.F64)
+    pc = capi.default_params()
+    with pytest.raises(capi.SmoreError):
+        mc.train_node2vec(pc)
+
+
+def test_node2vec_cli(tmp_path):
+    """cmd/node2vec/main.go flags (-p -q, window 10, walk_steps 80) and the Go "%.6f" writer."""
+    net, rep = str(tmp_path / "net.txt"), str(tmp_path / "rep.txt")
+    B.write_edge_list(net, G["g60_src"], G["g60_dst"], G["g60_w"])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([os.path.join(root, "smore_b200", "bin", "node2vec"), "-train", net, "-save", rep, "-dimensions", "16",
+                        "-walk_times", "2", "-p", "0.5", "-q", "2", "-threads", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = open(rep).read().split("\n")
+    n, dim = map(int, lines[0].split())
+    assert dim == 16 and len(lines) == n + 2 and len(lines[1].split(" ")) == 17 and len(lines[1].split(" ")[1].split(".")[1]) == 6
+    r = subprocess.run([os.path.join(root, "smore_b200", "bin", "node2vec"), "-train", net, "-save", rep, "-semantics", "cpp"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "only in the Go tree" in r.stderr

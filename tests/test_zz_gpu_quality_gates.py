@@ -119,6 +119,31 @@ def test_deepwalk_cpp():
     check("DeepWalk", r, ref["recall_at_10"], "recall@10")
 
 
+@pytest.mark.parametrize("model", ["deepwalk_go", "node2vec_go", "node2vec_unbiased"])
+def test_go_walk_models(model):
+    """DeepWalk under Go semantics (fixed full window, random contexts) and node2vec (Go tree only): biased walks with
+    p = 0.5 / q = 2 against their own reference-path baseline, and p = q = 1 -- where the biased walk is distributed like
+    the plain one -- against DeepWalk's."""
+    off, col, ww, ts, td = sbm()
+    V = len(off) - 1
+    ref = Q2["models"]["node2vec_go" if model == "node2vec_go" else "deepwalk_go"]
+    Wv, Wc = init_tables(V)
+    g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_GO, n_lines=len(col) // 2)
+    m = capi.Model(g, DIM, 2, capi.F32)
+    m.set_rows(0, Wv), m.set_rows(1, Wc)
+    p = hogwild(capi.SEM_GO, walk_times=ref["walk_times"], walk_steps=ref["walk_steps"], window_min=1, window_max=ref["window"],
+                negative_samples=5)
+    if model == "deepwalk_go":
+        st = m.train_deepwalk(p)
+    else:
+        p.n2v_p, p.n2v_q = (ref["p"], ref["q"]) if model == "node2vec_go" else (1.0, 1.0)
+        st = m.train_node2vec(p)
+    assert 0.9 * ref["pairs"] < st["pair_updates"] < 1.1 * ref["pairs"]
+    a, r = Q.evaluate_full(m.get_rows(0), m.get_rows(1), off, col, ts, td)
+    check(model, a, ref["auc"])
+    check(model, r, ref["recall_at_10"], "recall@10")
+
+
 def test_hpe():
     off, col, ww, ts, td = sbm()
     V, ref = len(off) - 1, Q2["models"]["hpe"]
