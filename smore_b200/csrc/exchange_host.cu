@@ -93,6 +93,7 @@ struct NcclApi {
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclCommAbort) CommAbort = nullptr;  // optional
     ncclComm_t comm = nullptr;
     int rank = -1, world = 0;
 } g_nccl;
@@ -109,6 +110,7 @@ int nccl_load() {
     SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(GroupStart); SYM(GroupEnd); SYM(Send); SYM(Recv);
     SYM(GetErrorString);
 #undef SYM
+    g_nccl.CommAbort = (decltype(g_nccl.CommAbort))dlsym(so, "ncclCommAbort");
     g_nccl.so = so;
     return SMORE_OK;
 }
@@ -120,6 +122,38 @@ int nccl_load() {
     } while (0)
 
 struct NcclTransport : ExchTransport {
+    DevBuf status;  // [2][kW] int32: what I tell each peer, what each peer tells me
+    int agree(int local_rc) override {
+        // (a rank that could not even allocate these 64 bytes cannot take part: its peers then wait in the receive below
+        // until the job's launcher notices the dead rank -- the one failure this protocol does not cover)
+        if (int rc = status.ensure(2 * kW * sizeof(int))) return rc;
+        if (!g_nccl.comm) return fail(SMORE_E_INVALID, "NCCL communicator was aborted by an earlier failure: call smore_dist_nccl_init again");
+        int host[2 * kW];
+        for (int r = 0; r < 2 * kW; ++r) host[r] = local_rc;
+        CU(cudaMemcpy(status.p, host, sizeof(host), cudaMemcpyHostToDevice));
+        int* d = (int*)status.p;
+        NC(g_nccl.GroupStart());
+        for (int r = 0; r < g_nccl.world; ++r) {
+            if (r == g_nccl.rank) continue;
+            NC(g_nccl.Send(d + r, 1, ncclInt32, r, g_nccl.comm, 0));
+            NC(g_nccl.Recv(d + kW + r, 1, ncclInt32, r, g_nccl.comm, 0));
+        }
+        NC(g_nccl.GroupEnd());
+        CU(cudaMemcpy(host, status.p, sizeof(host), cudaMemcpyDeviceToHost));
+        if (local_rc) return local_rc;
+        for (int r = 0; r < g_nccl.world; ++r)
+            if (r != g_nccl.rank && host[kW + r] != SMORE_OK)
+                return fail(host[kW + r], "exchange mode: rank %d failed to set up (%s); no rank trains", r, "see that rank's smore_last_error");
+        return SMORE_OK;
+    }
+    void abort() override {
+        if (!g_nccl.comm) return;
+        if (g_nccl.CommAbort) g_nccl.CommAbort(g_nccl.comm);
+        else g_nccl.CommDestroy(g_nccl.comm);
+        g_nccl.comm = nullptr;
+        g_nccl.rank = -1;
+        g_nccl.world = 0;
+    }
     int counts(smore_model_s** ms, int n, int b, cudaStream_t st) override {
         if (n != 1) return fail(SMORE_E_INVALID, "the NCCL transport drives exactly one shard per process");
         ExchSet* x = &ms[0]->xch->set[b];

@@ -48,6 +48,11 @@ struct ExchTransport {
     // device cnt_out of set b of every shard -> host cnt_out / cnt_in / off_out / off_in (synchronises `st` only)
     virtual int counts(smore_model_s** ms, int n, int b, cudaStream_t st) = 0;
     virtual int a2a(smore_model_s** ms, int n, int b, int what, size_t row_bytes, cudaStream_t st) = 0;
+    // Collective: every rank passes the outcome of its set-up; returns SMORE_OK only when every rank passed SMORE_OK
+    // (in-process shards: nothing to agree on).
+    virtual int agree(int local_rc) { return local_rc; }
+    // Called after a failed exchange: make queued transfers end so that the streams can be drained.
+    virtual void abort() {}
 };
 
 ExchTransport* exch_local_transport();

@@ -197,7 +197,32 @@ struct ExchStreams {
         return SMORE_OK;
     }
 };
-ExchStreams g_xs;
+// One set per device: a process that drives shards on several devices (or switches device between calls) must not launch on
+// streams / wait on events that belong to another device.
+int exch_streams(ExchStreams** out) {
+    static std::mutex mu;
+    static std::map<int, ExchStreams> per_dev;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    ExchStreams& xs = per_dev[dev];
+    if (int rc = xs.init()) return rc;
+    *out = &xs;
+    return SMORE_OK;
+}
+// Timing events of a verbose run: destroyed on every exit path.
+struct EventBag {
+    std::vector<cudaEvent_t> v;
+    cudaEvent_t make() {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        v.push_back(e);
+        return e;
+    }
+    ~EventBag() {
+        for (cudaEvent_t e : v) cudaEventDestroy(e);
+    }
+};
 }  // namespace
 
 template <typename T>
@@ -211,7 +236,9 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
         void (*kern)(TrainArgs<T>) = cpp ? k_line<C, false, 3> : k_line<C, true, 3>;
         const size_t smem = batch_smem_bytes<T>(2, p->negative_samples, 0);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (int rc = g_xs.init()) return rc;
+        ExchStreams* xsp = nullptr;
+        if (int rc = exch_streams(&xsp)) return rc;
+        ExchStreams& g_xs = *xsp;
         cudaStream_t sc = g_xs.sc, su = g_xs.su;
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
@@ -227,7 +254,11 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
             uint32_t hmask;
         };
         std::vector<Shard> sh((size_t)n);
-        for (int i = 0; i < n; ++i) {
+        // Set-up allocates EVERYTHING the super-batches will need, sized for the worst case (a request list holds unique
+        // rows: at most min(samples of the super-batch, rows the owner holds) per requester), so that no rank can run out of
+        // memory between two collectives; the ranks then agree on the outcome BEFORE the first exchange (tr.agree), and a
+        // rank whose set-up failed makes every rank return instead of leaving its peers inside an all-to-all.
+        auto setup = [&](int i) -> int {
             smore_model_s* m = ms[i];
             smore_exchange_s* x = m->xch;
             const uint64_t total_local = (uint64_t)llround((double)p->total * m->g->src_mass_frac);
@@ -245,6 +276,10 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
             if (hsize > (1ull << 30)) return fail(SMORE_E_INVALID, "super-batch too large");
             s.hmask = (uint32_t)(hsize - 1);
             x->req_stride = (int64_t)sb_samples;
+            // all ranks together draw total / nsb samples per super-batch (each rounds its share up to a multiple of its warps)
+            const uint64_t all_sb = (uint64_t)((double)p->total / (double)nsb) + (uint64_t)L.warps * (uint64_t)world;
+            const size_t out_max = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(sb_samples, (uint64_t)(m->g->V - m->rows)));
+            const size_t in_max = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(all_sb, (uint64_t)(world - 1) * (uint64_t)m->rows));
             for (int b = 0; b < 2; ++b) {
                 ExchSet& e = x->set[b];
                 if (int rc = e.hkey.ensure(hsize * 4)) return rc;
@@ -252,26 +287,33 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
                 if (int rc = e.req.ensure((size_t)world * sb_samples * 4)) return rc;
                 if (int rc = e.cnt.ensure(2 * kMaxWorld * 4)) return rc;
                 if (int rc = e.off.ensure(kMaxWorld * 4)) return rc;
+                if (int rc = e.wrk.ensure(out_max * row_bytes)) return rc;
+                if (int rc = e.req_in.ensure(in_max * 4)) return rc;
+                if (int rc = e.sent.ensure(in_max * row_bytes)) return rc;
+                if (int rc = e.back.ensure(in_max * row_bytes)) return rc;
             }
             if (int rc = x->errors.ensure(sizeof(int))) return rc;
             CU(cudaMemset(x->errors.p, 0, sizeof(int)));
             x->st_rows_moved = 0;
             x->st_superbatches = nsb;
-        }
+            return SMORE_OK;
+        };
+        int setup_rc = SMORE_OK;
+        for (int i = 0; i < n && !setup_rc; ++i) setup_rc = setup(i);
+        if (int rc = tr.agree(setup_rc)) return setup_rc ? setup_rc : rc;
         // SMORE_VERBOSE: device time of the phases on the communication stream, summed over the super-batches
         const bool verbose = getenv("SMORE_VERBOSE") != nullptr;
         enum { P_REQ, P_COUNTS, P_A2A_REQ, P_GATHER, P_ROWS_OUT, P_WAIT_UPD, P_ROWS_BACK, P_APPLY, P_N };
         static const char* const pname[P_N] = {"requests", "counts", "a2a(req)", "gather", "a2a(rows out)", "wait(update)",
                                                "a2a(rows back)", "apply"};
-        std::vector<cudaEvent_t> pev, uev;
+        EventBag pev, uev;  // (destroyed on every exit path)
         std::vector<int> pkind;
         auto mark = [&](int kind) {  // end of phase `kind` on sc (kind < 0: start marker)
             if (!verbose) return;
-            cudaEvent_t e;
-            cudaEventCreate(&e);
-            cudaEventRecord(e, sc);
-            pev.push_back(e);
-            pkind.push_back(kind);
+            if (cudaEvent_t e = pev.make()) {
+                cudaEventRecord(e, sc);
+                pkind.push_back(kind);
+            }
         };
         auto dev_of = [&](int i, int b) {
             smore_exchange_s* x = ms[i]->xch;
@@ -311,11 +353,10 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
                 smore_exchange_s* x = ms[i]->xch;
                 ExchSet& e = x->set[b];
                 const size_t n_out = (size_t)e.off_out[kMaxWorld], n_in = (size_t)e.off_in[kMaxWorld];
-                // (a buffer that has to grow is reallocated: cudaFree waits for the whole device, rare after super-batch 0)
-                if (int rc = e.wrk.ensure(std::max<size_t>(n_out, 1) * row_bytes)) return rc;
-                if (int rc = e.req_in.ensure(std::max<size_t>(n_in, 1) * 4)) return rc;
-                if (int rc = e.sent.ensure(std::max<size_t>(n_in, 1) * row_bytes)) return rc;
-                if (int rc = e.back.ensure(std::max<size_t>(n_in, 1) * row_bytes)) return rc;
+                // the buffers were sized for the worst case in set-up: nothing is allocated between two collectives
+                if (n_out * row_bytes > e.wrk.cap || n_in * row_bytes > e.sent.cap || n_in * 4 > e.req_in.cap)
+                    return fail(SMORE_E_CUDA, "exchange mode: rank %d got %zu request rows in / %zu out, above the set-up bound (internal error)",
+                                ms[i]->g->rank, n_in, n_out);
                 int32_t off32[kMaxWorld];
                 for (int r = 0; r < kMaxWorld; ++r) off32[r] = (int32_t)e.off_out[r];
                 CU(cudaMemcpyAsync(e.off.p, off32, sizeof(off32), cudaMemcpyHostToDevice, sc));
@@ -344,9 +385,9 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
             CU(cudaStreamWaitEvent(su, g_xs.ready[b], 0));
             cudaEvent_t u0 = nullptr, u1 = nullptr;
             if (verbose) {
-                cudaEventCreate(&u0);
-                cudaEventCreate(&u1);
-                cudaEventRecord(u0, su);
+                u0 = uev.make();
+                u1 = uev.make();
+                if (u0) cudaEventRecord(u0, su);
             }
             for (int i = 0; i < n; ++i) {
                 Shard& s = sh[(size_t)i];
@@ -358,11 +399,7 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
                     s.done += s.a.jobs;
                 }
             }
-            if (verbose) {
-                cudaEventRecord(u1, su);
-                uev.push_back(u0);
-                uev.push_back(u1);
-            }
+            if (u1) cudaEventRecord(u1, su);
             CU(cudaEventRecord(g_xs.updated[b], su));
             return SMORE_OK;
         };
@@ -393,12 +430,26 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
         CU(cudaDeviceSynchronize());
         Timer t;
         if (int rc = t.start()) return rc;
-        if (int rc = prep(0)) return rc;
-        for (uint64_t sb = 0; sb < nsb; ++sb) {
-            if (int rc = update(sb)) return rc;
-            if (sb + 1 < nsb)
-                if (int rc = prep(sb + 1)) return rc;
-            if (int rc = finish(sb)) return rc;
+        // A failure past this point is a CUDA / NCCL error (nothing else can fail: see set-up). The transport is torn down
+        // (NCCL: ncclCommAbort, so that this rank's queued sends / receives end and its streams drain; peers see the
+        // communicator fail instead of waiting for rows that will never come) and both streams are drained before the
+        // buffers they use can be freed.
+        auto pipeline = [&]() -> int {
+            if (int rc = prep(0)) return rc;
+            for (uint64_t sb = 0; sb < nsb; ++sb) {
+                if (int rc = update(sb)) return rc;
+                if (sb + 1 < nsb)
+                    if (int rc = prep(sb + 1)) return rc;
+                if (int rc = finish(sb)) return rc;
+            }
+            return SMORE_OK;
+        };
+        if (int rc = pipeline()) {
+            tr.abort();
+            cudaStreamSynchronize(su);
+            cudaStreamSynchronize(sc);
+            cudaGetLastError();
+            return rc;
         }
         CU(cudaEventRecord(g_xs.all_done, su));
         CU(cudaStreamWaitEvent(0, g_xs.all_done, 0));
@@ -408,24 +459,22 @@ int train_line_exchange_t(smore_model_s** ms, int n, const smore_train_params* p
         if (int rc = t.stop(&ms_total)) return rc;
         if (verbose) {
             double sum[P_N] = {};
-            for (size_t k = 1; k < pev.size(); ++k)
+            for (size_t k = 1; k < pev.v.size() && k < pkind.size(); ++k)
                 if (pkind[k] >= 0) {
                     float f = 0;
-                    cudaEventElapsedTime(&f, pev[k - 1], pev[k]);
+                    cudaEventElapsedTime(&f, pev.v[k - 1], pev.v[k]);
                     sum[pkind[k]] += f;
                 }
             fprintf(stderr, "[smore_b200] exchange rank %d: %llu super-batches in %.2f ms; communication stream:", m0->g->rank,
                     (unsigned long long)nsb, ms_total);
             for (int k = 0; k < P_N; ++k) fprintf(stderr, " %s %.2f", pname[k], sum[k]);
             double upd = 0;
-            for (size_t k = 0; k + 1 < uev.size(); k += 2) {
+            for (size_t k = 0; k + 1 < uev.v.size(); k += 2) {
                 float f = 0;
-                cudaEventElapsedTime(&f, uev[k], uev[k + 1]);
+                cudaEventElapsedTime(&f, uev.v[k], uev.v[k + 1]);
                 upd += f;
             }
             fprintf(stderr, " ms; update stream: k_line %.2f ms\n", upd);
-            for (cudaEvent_t e : uev) cudaEventDestroy(e);
-            for (cudaEvent_t e : pev) cudaEventDestroy(e);
         }
         for (int i = 0; i < n; ++i) {
             ms[i]->st_ms = ms_total;

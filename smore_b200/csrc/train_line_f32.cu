@@ -19,7 +19,9 @@ __global__ void k_probe_smid(unsigned* bitmap, int spin) {
 extern "C" int smore_debug_sm_partition(int reserve, int* total_sms, int* partition_sms, int* sms_seen) {
     if (int rc = ensure_device()) return rc;
     setenv("SMORE_EXCH_RESERVE_SMS", std::to_string(reserve).c_str(), 1);
-    if (int rc = g_xs.init()) return rc;
+    ExchStreams* xsp = nullptr;
+    if (int rc = exch_streams(&xsp)) return rc;
+    ExchStreams& g_xs = *xsp;
     int dev = 0, sms = 0;
     CU(cudaGetDevice(&dev));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

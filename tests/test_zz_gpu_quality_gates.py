@@ -129,17 +129,22 @@ def test_go_walk_models(model):
     ref = Q2["models"]["node2vec_go" if model == "node2vec_go" else "deepwalk_go"]
     Wv, Wc = init_tables(V)
     g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_GO, n_lines=len(col) // 2)
-    m = capi.Model(g, DIM, 2, capi.F32)
-    m.set_rows(0, Wv), m.set_rows(1, Wc)
-    p = hogwild(capi.SEM_GO, walk_times=ref["walk_times"], walk_steps=ref["walk_steps"], window_min=1, window_max=ref["window"],
-                negative_samples=5)
-    if model == "deepwalk_go":
-        st = m.train_deepwalk(p)
-    else:
-        p.n2v_p, p.n2v_q = (ref["p"], ref["q"]) if model == "node2vec_go" else (1.0, 1.0)
-        st = m.train_node2vec(p)
-    assert 0.9 * ref["pairs"] < st["pair_updates"] < 1.1 * ref["pairs"]
-    a, r = Q.evaluate_full(m.get_rows(0), m.get_rows(1), off, col, ts, td)
+
+    def run(seed):
+        m = capi.Model(g, DIM, 2, capi.F32)
+        m.set_rows(0, Wv), m.set_rows(1, Wc)
+        p = hogwild(capi.SEM_GO, seed=seed, walk_times=ref["walk_times"], walk_steps=ref["walk_steps"], window_min=1,
+                    window_max=ref["window"], negative_samples=5)
+        if model == "deepwalk_go":
+            st = m.train_deepwalk(p)
+        else:
+            p.n2v_p, p.n2v_q = (ref["p"], ref["q"]) if model == "node2vec_go" else (1.0, 1.0)
+            st = m.train_node2vec(p)
+        assert 0.9 * ref["pairs"] < st["pair_updates"] < 1.1 * ref["pairs"]
+        return Q.evaluate_full(m.get_rows(0), m.get_rows(1), off, col, ts, td)
+
+    # (both sides are 3-run means here: one run's recall@10 moves by +-0.003 on the GPU and +-0.002 on the CPU path)
+    a, r = mean_of(run)
     check(model, a, ref["auc"])
     check(model, r, ref["recall_at_10"], "recall@10")
 
