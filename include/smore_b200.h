@@ -263,6 +263,15 @@ int smore_model_load_checkpoint(smore_model_t m, const char* path);
  * resume, continue with the same seed, stream_base = next_stream, sched_total and sched_offset = sched_done; a version-1
  * checkpoint (tables only) restores 0 / 0 / 0 / 0: a warm start. Any pointer may be NULL. */
 int smore_model_progress(smore_model_t m, uint64_t* seed, uint64_t* next_stream, uint64_t* sched_total, uint64_t* sched_done);
+/* Live progress of the train call that is running on `m` -- the ONE entry point that may be called from another thread
+ * while a smore_train_* call on the same handle blocks. Replaces the progress line the reference's workers
+ * print every MONITOR samples (src/model/LINE.cpp:179-187, line.go:133-142: "Alpha: %.6f  Progress: %.3f %%"): warp 0 of
+ * the training grid stores its view of the schedule -- units done (samples; walks for the walk models; this rank's share
+ * on a row-sharded graph), the learning rate in force -- into host-mapped memory at every LR refresh, and this call only
+ * reads that memory (no CUDA call, no lock). `total` is the length of the LR schedule (params.sched_total or .total),
+ * `running` is 1 between the start of a train call and its return; after the call `done` is what the call really
+ * finished. Before the first train call everything reads 0. Any pointer may be NULL. */
+int smore_progress(smore_model_t m, uint64_t* done, uint64_t* total, double* alpha, int* running);
 /* The writer's formatter on host rows (no device involved; multi-threaded): `<first_id + r> v0 v1 ...\n` per row, in the
  * number format of the chosen reference writer. Returns the byte count of the text (written to `out` when it fits in
  * `cap`; call with out = NULL to size the buffer) or a negative error. */

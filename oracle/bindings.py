@@ -116,6 +116,8 @@ class Oracle:
             L.orc_train_deepwalk_go.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64, u64, u64,
                                                 i64, vp]
             L.orc_train_deepwalk_go.restype = u64
+            L.orc_train_deepwalk_go_streams.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64, u64, C.c_int, vp]
+            L.orc_train_deepwalk_go_streams.restype = u64
             L.orc_train_node2vec_go.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64, f64, f64, u64, u64,
                                                 i64, vp]
             L.orc_train_node2vec_go.restype = u64
@@ -272,6 +274,13 @@ class OracleGraph:
         pos = self.L.orc_train_deepwalk_go(self.h, _ptr(Wv), _ptr(Wc), Wv.shape[1], walk_times, walk_steps, window, K,
                                            alpha, seed, stream, max_walks, C.byref(pairs))
         return pos, pairs.value
+
+    def train_deepwalk_go_streams(self, Wv, Wc, walk_times, walk_steps, window, K, alpha, seed, n_streams):
+        """Diagnostic: the device's W-stream work split of the Go DeepWalk loop, run sequentially (not a reference path)."""
+        pairs = u64(0)
+        self.L.orc_train_deepwalk_go_streams(self.h, _ptr(Wv), _ptr(Wc), Wv.shape[1], walk_times, walk_steps, window, K,
+                                             alpha, seed, n_streams, C.byref(pairs))
+        return pairs.value
 
     def train_node2vec_go(self, Wv, Wc, walk_times, walk_steps, window, K, alpha, p, q, seed, stream=0, max_walks=-1):
         pairs = u64(0)

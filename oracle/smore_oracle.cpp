@@ -1034,6 +1034,44 @@ done:
     return d.s.pos;
 }
 
+// Diagnostic (tools/go_walk_streams_probe.py): the DEVICE's work split of the Go DeepWalk loop, run sequentially -- W
+// independent draw streams, walk i of an epoch on stream i % W, each stream with the device's tick rule for the shared
+// schedule (device_core.cuh sched_tick) -- i.e. the Hogwild kernel minus the concurrency. Not a reference path.
+uint64_t orc_train_deepwalk_go_streams(void* h, double* Wv, double* Wc, int dim, int walk_times, int walk_steps, int window,
+                                       int K, double alpha, uint64_t seed, int W, uint64_t* pairs_out) {
+    Graph* g = (Graph*)h;
+    std::vector<Draws> d;
+    for (int w = 0; w < W; ++w) d.emplace_back(seed, (uint64_t)w);
+    const double total = (double)((int64_t)walk_times * g->V), alpha_min = alpha * 0.0001;
+    std::vector<uint64_t> count((size_t)W, 0), next_tick((size_t)W, ((uint64_t)MONITOR + W - 1) / W);
+    std::vector<double> cur((size_t)W, alpha);
+    unsigned long long pairs = 0;
+    std::vector<int64_t> keys(g->V), walk, pv, pc;
+    std::vector<double> a, b, c;
+    for (int t = 0; t < walk_times; ++t) {
+        for (int64_t v = 0; v < g->V; ++v) keys[v] = v;
+        for (int64_t v = 0; v < g->V; ++v) {
+            int64_t j = v + d[0].shuffle_index(g->V - v);
+            std::swap(keys[v], keys[j]);
+        }
+        for (int64_t v = 0; v < g->V; ++v) {
+            const size_t w = (size_t)(v % W);
+            g->random_walk(keys[v], walk_steps, d[w], walk);
+            g->skip_grams(walk, window, d[w], pv, pc);
+            for (size_t i = 0; i < pv.size(); ++i) g->update_pair_go(Wv, Wc, pv[i], pc[i], dim, K, cur[w], d[w], a, b, c);
+            pairs += pv.size();
+            count[w]++;
+            if (count[w] >= next_tick[w]) {
+                const uint64_t tk = count[w] * (uint64_t)W / MONITOR;
+                cur[w] = std::max(alpha_min, alpha * (1.0 - (double)(tk * MONITOR) / total));
+                next_tick[w] = ((tk + 1) * MONITOR + W - 1) / W;
+            }
+        }
+    }
+    if (pairs_out) *pairs_out = pairs;
+    return 0;
+}
+
 // Go node2vec: internal/models/node2vec/node2vec.go:176-260 (one worker): DeepWalk.Train with the biased second-order walk.
 uint64_t orc_train_node2vec_go(void* h, double* Wv, double* Wc, int dim, int walk_times, int walk_steps, int window,
                                int K, double alpha, double p, double q, uint64_t seed, uint64_t stream, int64_t max_walks,

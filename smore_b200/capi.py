@@ -40,7 +40,7 @@ EXPORTS = [
     "smore_alias_build_device", "smore_graph_create_synthetic_rotating",
     "smore_model_set_rows_f32_async", "smore_model_get_rows_f32_async", "smore_model_wait_copies",
     "smore_train_line_group", "smore_exchange_stats", "smore_debug_sm_partition", "smore_model_save_weights", "smore_format_rows",
-    "smore_model_load_pretrain", "smore_model_save_checkpoint", "smore_model_load_checkpoint", "smore_model_progress", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
+    "smore_model_load_pretrain", "smore_model_save_checkpoint", "smore_model_load_checkpoint", "smore_model_progress", "smore_progress", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
     "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf", "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_node2vec", "smore_train_stats",
 ]
 
@@ -135,6 +135,7 @@ def lib():
         L.smore_model_save_checkpoint.argtypes = [vp, C.c_char_p]
         L.smore_model_load_checkpoint.argtypes = [vp, C.c_char_p]
         L.smore_model_progress.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+        L.smore_progress.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.smore_format_rows.argtypes = [vp, i64, C.c_int, i64, C.c_int, vp, i64]
         L.smore_format_rows.restype = i64
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
@@ -493,6 +494,12 @@ class Model:
         a, b, c, d = u64(), u64(), u64(), u64()
         check(lib().smore_model_progress(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return {"seed": a.value, "next_stream": b.value, "sched_total": c.value, "sched_done": d.value}
+
+    def live_progress(self):
+        """smore_progress: callable from another thread while a train call on this model blocks (ctypes releases the GIL)."""
+        a, b, al, r = u64(), u64(), C.c_double(), C.c_int()
+        check(lib().smore_progress(self.h, C.byref(a), C.byref(b), C.byref(al), C.byref(r)))
+        return {"done": a.value, "total": b.value, "alpha": al.value, "running": bool(r.value)}
 
     def _train(self, fn, p):
         check(fn(self.h, C.byref(p)))

@@ -10,11 +10,14 @@
 // -mode {hogwild,deterministic}, -seed N, -dtype {f32,f64}. -threads is accepted and ignored: the workers are GPU warps.
 // The Go toolchain is not available in the build image; INTEGRATION.md has the cgo binding that calls the same ABI.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/smore_b200.h"
@@ -267,7 +270,25 @@ int main(int argc, char** argv) {
             q.sched_offset = (uint64_t)c * q.total;
             q.stream_base = std::max<uint64_t>(p.stream_base + (uint64_t)c * (1ull << 24), resume_stream);
         }
-        if (train_once(q)) return die("Train");
+        // the reference's workers print "Alpha / Progress" every MONITOR samples (LINE.cpp:179-187); here a host thread
+        // polls smore_progress -- the one call that is safe next to the blocking train call -- and prints the same line
+        std::atomic<bool> stop{false};
+        std::thread poll([&] {
+            while (!stop.load(std::memory_order_acquire)) {
+                uint64_t done = 0, total = 0;
+                double alpha = 0;
+                int running = 0;
+                if (smore_progress(m, &done, &total, &alpha, &running) == 0 && running && total) {
+                    printf("\tAlpha: %.6f\tProgress: %.3f %%%c", alpha, 100.0 * (double)done / (double)total, 13);
+                    fflush(stdout);
+                }
+                std::this_thread::sleep_for(std::chrono::milliseconds(100));
+            }
+        });
+        const int train_rc = train_once(q);
+        stop.store(true, std::memory_order_release);
+        poll.join();
+        if (train_rc) return die("Train");
         if (ckpt_every > 0 && a.has("checkpoint") && (c + 1) % ckpt_every == 0 && c + 1 < chunks &&
             smore_model_save_checkpoint(m, a.str("checkpoint", "").c_str()))
             return die("SaveCheckpoint");

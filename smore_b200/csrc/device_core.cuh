@@ -494,6 +494,9 @@ struct Sched {
     uint64_t W;
     int lag;
     double offset;  // samples of the (possibly longer) schedule already done before this call; 0 for a whole run
+    // host-mapped {schedule units done, alpha bits}: warp 0 of the grid stores its estimate at every tick, smore_progress
+    // reads it from any host thread while the train call blocks (the reference's progress line, LINE.cpp:179-187)
+    unsigned long long* live;
 };
 
 struct WarpState {
@@ -512,6 +515,11 @@ __device__ __forceinline__ void sched_tick(WarpState& st, const Sched& s) {
         double amin = s.alpha0 * 0.0001;
         st.alpha = a < amin ? amin : a;
         st.next_tick = ((t + 1) * kMonitor + s.W - 1) / s.W;
+        if (s.live && blockIdx.x == 0 && threadIdx.x == 0) {
+            volatile unsigned long long* live = s.live;
+            live[0] = (unsigned long long)s.offset + t * (unsigned long long)kMonitor;
+            live[1] = (unsigned long long)__double_as_longlong(st.alpha);
+        }
     }
 }
 

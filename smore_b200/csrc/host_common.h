@@ -152,6 +152,9 @@ struct smore_model_s {
     // stats of the last train call
     uint64_t st_samples = 0, st_pairs = 0, st_words0 = 0, st_tries = 0;
     double st_ms = 0;
+    // live progress (smore_progress): host-mapped {done, alpha bits, total, running}; schedule units done before this call
+    unsigned long long* live = nullptr;
+    unsigned long long live_offset = 0;
     size_t elem() const { return dtype == SMORE_F64 ? 8 : 4; }
     ~smore_model_s() {
         for (int t = 0; t < 2; ++t)
@@ -163,6 +166,7 @@ struct smore_model_s {
         if (d2h_stream) cudaStreamDestroy(d2h_stream);
         delete xch;
         delete rot;
+        if (live) cudaFreeHost(live);
     }
 };
 
@@ -298,6 +302,13 @@ int collect_stats(smore_model_s* m, int warps) {
         m->st_tries += s.tries;
     }
     m->st_words0 = st[0].pos;
+    if (m->live) {  // the call is over: what the LAST tick saw -> where the schedule really stands
+        unsigned long long bits;
+        memcpy(&bits, &st[0].alpha, sizeof(bits));
+        __atomic_store_n(&m->live[1], bits, __ATOMIC_RELAXED);
+        __atomic_store_n(&m->live[0], m->live_offset + (unsigned long long)m->st_samples, __ATOMIC_RELAXED);
+        __atomic_store_n(&m->live[3], 0ull, __ATOMIC_RELEASE);
+    }
     return SMORE_OK;
 }
 
@@ -332,7 +343,30 @@ TrainArgs<T> base_args(smore_model_s* m, const smore_train_params* p, int warps,
     a.stream_base = p->stream_base;
     // a call may be one chunk of a longer LR schedule (sched_total / sched_offset, in the same units as `total`)
     const double sched_total = p->sched_total ? (double)p->sched_total * scale : total;
-    a.sched = Sched{p->alpha, sched_total, (uint64_t)warps, lag, (double)p->sched_offset * scale};
+    a.sched = Sched{p->alpha, sched_total, (uint64_t)warps, lag, (double)p->sched_offset * scale, nullptr};
+    if (!m->live) {
+        unsigned long long* fresh = nullptr;
+        if (cudaHostAlloc((void**)&fresh, 4 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
+            memset(fresh, 0, 4 * sizeof(unsigned long long));
+            __atomic_store_n(&m->live, fresh, __ATOMIC_RELEASE);  // (smore_progress may be polling from another thread)
+        } else {
+            cudaGetLastError();  // no mapped memory: training runs, smore_progress reads zeros
+        }
+    }
+    if (m->live) {  // {done, alpha bits, total, running}
+        double a0 = p->alpha;
+        if (p->sched_total && p->sched_offset) a0 = std::max(a0 * 1e-4, a0 * (1.0 - (double)p->sched_offset / (double)p->sched_total));
+        unsigned long long bits;
+        memcpy(&bits, &a0, sizeof(bits));
+        m->live_offset = (unsigned long long)a.sched.offset;
+        __atomic_store_n(&m->live[0], m->live_offset, __ATOMIC_RELAXED);
+        __atomic_store_n(&m->live[1], bits, __ATOMIC_RELAXED);
+        __atomic_store_n(&m->live[2], (unsigned long long)sched_total, __ATOMIC_RELAXED);
+        __atomic_store_n(&m->live[3], 1ull, __ATOMIC_RELEASE);
+        unsigned long long* dev = nullptr;
+        if (cudaHostGetDevicePointer((void**)&dev, m->live, 0) == cudaSuccess) a.sched.live = dev;
+        else cudaGetLastError();
+    }
     a.state = m->d_state;
     a.n_warps = warps;
     a.K = p->negative_samples;

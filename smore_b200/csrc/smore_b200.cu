@@ -966,6 +966,22 @@ int smore_model_progress(smore_model_t m, uint64_t* seed, uint64_t* next_stream,
     return SMORE_OK;
 }
 
+int smore_progress(smore_model_t m, uint64_t* done, uint64_t* total, double* alpha, int* running) {
+    // no CUDA call, no lock, no thread-local state besides the error string: safe next to a blocking train call on `m`
+    if (!m) return fail(SMORE_E_INVALID, "null model");
+    unsigned long long* live = __atomic_load_n(&m->live, __ATOMIC_ACQUIRE);
+    unsigned long long v[4] = {0, 0, 0, 0};
+    if (live) {
+        v[3] = __atomic_load_n(&live[3], __ATOMIC_ACQUIRE);
+        for (int k = 0; k < 3; ++k) v[k] = __atomic_load_n(&live[k], __ATOMIC_RELAXED);
+    }
+    if (done) *done = std::min<uint64_t>(v[0], v[2]);
+    if (total) *total = v[2];
+    if (alpha) memcpy(alpha, &v[1], sizeof(double));
+    if (running) *running = (int)v[3];
+    return SMORE_OK;
+}
+
 int64_t smore_format_rows(const double* rows, int64_t n, int dim, int64_t first_id, int format, char* out, int64_t cap) {
     if (!rows || n < 0 || dim <= 0 || (format != 0 && format != 1)) return fail(SMORE_E_INVALID, "bad argument");
     std::vector<std::string> parts((size_t)host_threads());
