@@ -116,6 +116,10 @@ class Oracle:
             L.orc_train_deepwalk_go.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64, u64, u64,
                                                 i64, vp]
             L.orc_train_deepwalk_go.restype = u64
+            L.orc_train_cpr_go.argtypes = [vp, vp, vp, vp, vp, C.c_int, f64, f64, f64, f64, u64, u64, u64, u64]
+            L.orc_train_cpr_go.restype = u64
+            L.orc_train_tpr_go.argtypes = [vp, vp, vp, vp, vp, C.c_int, f64, f64, f64, u64, u64, u64, u64]
+            L.orc_train_tpr_go.restype = u64
             L.orc_train_deepwalk_go_streams.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64, u64, C.c_int, vp]
             L.orc_train_deepwalk_go_streams.restype = u64
             L.orc_train_node2vec_go.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64, f64, f64, u64, u64,
@@ -274,6 +278,16 @@ class OracleGraph:
         pos = self.L.orc_train_deepwalk_go(self.h, _ptr(Wv), _ptr(Wc), Wv.shape[1], walk_times, walk_steps, window, K,
                                            alpha, seed, stream, max_walks, C.byref(pairs))
         return pos, pairs.value
+
+    def train_cpr_go(self, source, U, T, S, alpha, user_reg, item_reg, margin, iterations, total, seed, stream=0):
+        """self = the target-domain graph, source = the source-domain OracleGraph; S is read-only."""
+        return self.L.orc_train_cpr_go(self.h, source.h, _ptr(U), _ptr(T), _ptr(S), U.shape[1], alpha, user_reg, item_reg, margin,
+                                       iterations, total, seed, stream)
+
+    def train_tpr_go(self, words, U, I, Wd, alpha, lam, text_weight, iterations, total, seed, stream=0):
+        """self = the user-item graph, words = the item-word OracleGraph."""
+        return self.L.orc_train_tpr_go(self.h, words.h, _ptr(U), _ptr(I), _ptr(Wd), U.shape[1], alpha, lam, text_weight,
+                                       iterations, total, seed, stream)
 
     def train_deepwalk_go_streams(self, Wv, Wc, walk_times, walk_steps, window, K, alpha, seed, n_streams):
         """Diagnostic: the device's W-stream work split of the Go DeepWalk loop, run sequentially (not a reference path)."""

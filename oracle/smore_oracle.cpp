@@ -999,6 +999,147 @@ uint64_t orc_train_bpr_go(void* h, double* Wv, double* Wc, int dim, double alpha
     return d.s.pos;
 }
 
+// Go CPR: internal/models/cpr/cpr.go:127-282 (one worker). `h` is the target-domain graph, `hs` the source-domain graph;
+// U (user rows) and T (target-domain item rows) are trained, S (source-domain item rows) is only read. A user is looked up
+// in BOTH graphs by its target-graph vid (cpr.go:53-59, :72-78, :148-169).
+uint64_t orc_train_cpr_go(void* h, void* hs, double* U, double* T, const double* S, int dim, double alpha, double user_reg,
+                          double item_reg, double margin, uint64_t iterations, uint64_t total_, uint64_t seed, uint64_t stream) {
+    Graph* g = (Graph*)h;
+    Graph* gs = (Graph*)hs;
+    Draws d(seed, stream);
+    const double alpha_min = alpha * 0.0001;
+    double cur = alpha;
+    const int64_t total = (int64_t)total_;
+    int64_t count = 0;
+    std::vector<double> uv(dim), ug(dim), pg(dim), ng(dim);
+    for (uint64_t it = 0; it < iterations; ++it) {
+        const int64_t u = g->source_sample(d);
+        const int64_t p = g->target_sample(u, d);
+        if (p == -1) continue;  // (no count++: cpr.go:214-216)
+        // transformUser (:127-172)
+        for (int k = 0; k < dim; ++k) uv[k] = 0.0;
+        double cnt = 0.0;
+        for (int k = 0; k < dim; ++k) uv[k] += U[u * dim + k];
+        cnt += 1.0;
+        for (int64_t e = g->off[u]; e < g->off[u + 1]; ++e) {
+            const double* r = T + (int64_t)g->col[e] * dim;
+            for (int k = 0; k < dim; ++k) uv[k] += r[k];
+            cnt += 1.0;
+        }
+        if (u < gs->V)
+            for (int64_t e = gs->off[u]; e < gs->off[u + 1]; ++e) {
+                const double* r = S + (int64_t)gs->col[e] * dim;
+                for (int k = 0; k < dim; ++k) uv[k] += r[k];
+                cnt += 1.0;
+            }
+        for (int k = 0; k < dim; ++k) uv[k] /= cnt;
+        const int64_t n = g->negative_sample(d);
+        double* ru = U + u * dim;
+        double* rp = T + p * dim;
+        double* rn = T + n * dim;
+        double ps = 0.0, ns = 0.0;
+        for (int k = 0; k < dim; ++k) {
+            ps += uv[k] * rp[k];
+            ns += uv[k] * rn[k];
+        }
+        const double diff = ps - ns;
+        if (diff < margin) {
+            const double gc = cur * g->fast_sigmoid(-(diff - margin));
+            for (int k = 0; k < dim; ++k) {
+                pg[k] = gc * uv[k];
+                ng[k] = -gc * uv[k];
+                ug[k] = gc * (rp[k] - rn[k]);
+            }
+            for (int k = 0; k < dim; ++k) {
+                ru[k] -= cur * user_reg * ru[k];
+                ru[k] += ug[k];
+                rp[k] -= cur * item_reg * rp[k];
+                rp[k] += pg[k];
+                rn[k] -= cur * item_reg * rn[k];
+                rn[k] += ng[k];
+            }
+        }
+        count++;
+        if (count % MONITOR == 0) {
+            cur = alpha * (1.0 - (double)count / (double)total);
+            if (cur < alpha_min) cur = alpha_min;
+        }
+    }
+    return d.s.pos;
+}
+
+// Go TPR: internal/models/tpr/tpr.go:101-262 (one worker). `h` is the user-item graph, `hw` the item-word graph (an item
+// is looked up there by its user-item vid, :108); U / I are the user / item rows (both V_ui), Wd the word rows (V_iw).
+uint64_t orc_train_tpr_go(void* h, void* hw, double* U, double* I, double* Wd, int dim, double alpha, double lambda,
+                          double text_weight, uint64_t iterations, uint64_t total_, uint64_t seed, uint64_t stream) {
+    Graph* g = (Graph*)h;
+    Graph* gw = (Graph*)hw;
+    Draws d(seed, stream);
+    const double alpha_min = alpha * 0.0001;
+    double cur = alpha;
+    const int64_t total = (int64_t)total_;
+    int64_t count = 0;
+    std::vector<double> pv(dim), nv(dim), ug(dim), pg(dim), ng(dim);
+    auto enriched = [&](int64_t item, std::vector<double>& out) {  // :101-121
+        const double* ri = I + item * dim;
+        for (int k = 0; k < dim; ++k) out[k] = (1.0 - text_weight) * ri[k];
+        const int64_t nw = item < gw->V ? gw->off[item + 1] - gw->off[item] : 0;
+        if (nw > 0) {
+            for (int64_t e = gw->off[item]; e < gw->off[item + 1]; ++e) {
+                const double* rw = Wd + (int64_t)gw->col[e] * dim;
+                for (int k = 0; k < dim; ++k) out[k] += (text_weight / (double)nw) * rw[k];
+            }
+        } else {
+            for (int k = 0; k < dim; ++k) out[k] = ri[k];
+        }
+    };
+    auto push_words = [&](int64_t item, const std::vector<double>& grad) {  // :216-232
+        const int64_t nw = item < gw->V ? gw->off[item + 1] - gw->off[item] : 0;
+        if (nw <= 0) return;
+        const double ww = text_weight / (double)nw;
+        for (int64_t e = gw->off[item]; e < gw->off[item + 1]; ++e) {
+            double* rw = Wd + (int64_t)gw->col[e] * dim;
+            for (int k = 0; k < dim; ++k) rw[k] += ww * grad[k] - lambda * cur * rw[k];
+        }
+    };
+    for (uint64_t it = 0; it < iterations; ++it) {
+        const int64_t u = g->source_sample(d);
+        if (u == -1) continue;
+        const int64_t p = g->target_sample(u, d);
+        if (p == -1) continue;
+        const int64_t n = g->negative_sample(d);
+        enriched(p, pv);
+        enriched(n, nv);
+        double* ru = U + u * dim;
+        double ps = 0.0, ns = 0.0;
+        for (int k = 0; k < dim; ++k) {
+            ps += ru[k] * pv[k];
+            ns += ru[k] * nv[k];
+        }
+        const double gc = cur * g->fast_sigmoid(ns - ps);
+        for (int k = 0; k < dim; ++k) {
+            ug[k] = gc * (pv[k] - nv[k]);
+            pg[k] = gc * ru[k];
+            ng[k] = -gc * ru[k];
+        }
+        for (int k = 0; k < dim; ++k) ru[k] += ug[k] - lambda * cur * ru[k];
+        double* rp = I + p * dim;
+        double* rn = I + n * dim;
+        for (int k = 0; k < dim; ++k) {
+            rp[k] += (1.0 - text_weight) * pg[k] - lambda * cur * rp[k];
+            rn[k] += (1.0 - text_weight) * ng[k] - lambda * cur * rn[k];
+        }
+        push_words(p, pg);
+        push_words(n, ng);
+        count++;
+        if (count % MONITOR == 0) {
+            cur = alpha * (1.0 - (double)count / (double)total);
+            if (cur < alpha_min) cur = alpha_min;
+        }
+    }
+    return d.s.pos;
+}
+
 // Go DeepWalk: internal/models/deepwalk/deepwalk.go:61-141 (one worker). rand.Int63n(n) := shuffle-stream index draw.
 uint64_t orc_train_deepwalk_go(void* h, double* Wv, double* Wc, int dim, int walk_times, int walk_steps, int window,
                                int K, double alpha, uint64_t seed, uint64_t stream, int64_t max_walks,
@@ -1039,6 +1180,9 @@ done:
 // schedule (device_core.cuh sched_tick) -- i.e. the Hogwild kernel minus the concurrency. Not a reference path.
 uint64_t orc_train_deepwalk_go_streams(void* h, double* Wv, double* Wc, int dim, int walk_times, int walk_steps, int window,
                                        int K, double alpha, uint64_t seed, int W, uint64_t* pairs_out) {
+    // W < 0: -W schedule slots fed by ONE draw stream (separates the effect of the schedule split from the draw split)
+    const bool one_stream = W < 0;
+    if (one_stream) W = -W;
     Graph* g = (Graph*)h;
     std::vector<Draws> d;
     for (int w = 0; w < W; ++w) d.emplace_back(seed, (uint64_t)w);
@@ -1056,9 +1200,10 @@ uint64_t orc_train_deepwalk_go_streams(void* h, double* Wv, double* Wc, int dim,
         }
         for (int64_t v = 0; v < g->V; ++v) {
             const size_t w = (size_t)(v % W);
-            g->random_walk(keys[v], walk_steps, d[w], walk);
-            g->skip_grams(walk, window, d[w], pv, pc);
-            for (size_t i = 0; i < pv.size(); ++i) g->update_pair_go(Wv, Wc, pv[i], pc[i], dim, K, cur[w], d[w], a, b, c);
+            Draws& dw = d[one_stream ? 0 : w];
+            g->random_walk(keys[v], walk_steps, dw, walk);
+            g->skip_grams(walk, window, dw, pv, pc);
+            for (size_t i = 0; i < pv.size(); ++i) g->update_pair_go(Wv, Wc, pv[i], pc[i], dim, K, cur[w], dw, a, b, c);
             pairs += pv.size();
             count[w]++;
             if (count[w] >= next_tick[w]) {

@@ -1,6 +1,7 @@
 """SECOND, independent restatement of the Go tree's hot path -- TEST INFRASTRUCTURE, written from the Go sources only
 (pkg/pronet/alias.go:10-106, pkg/pronet/pronet.go:90-109 / :195-333, pkg/pronet/optimizer.go:8-117,
-internal/models/line/line.go:73-206, internal/models/bpr/bpr.go:61-131, internal/models/deepwalk/deepwalk.go:61-141),
+internal/models/line/line.go:73-206, internal/models/bpr/bpr.go:61-131, internal/models/deepwalk/deepwalk.go:61-141,
+internal/models/node2vec/node2vec.go:82-173, internal/models/cpr/cpr.go:127-282, internal/models/tpr/tpr.go:101-262),
 without consulting oracle/smore_oracle.cpp: plain Python floats (IEEE doubles, one operation at a time, the Go statement
 order), no numpy in the arithmetic. No Go toolchain exists in this image, so the Go-semantics kernels cannot be pinned
 against the Go binaries; what this file buys is that two independently written restatements (this one and the C++ oracle)
@@ -357,3 +358,117 @@ def train_node2vec(pn, wv, wc, dim, walk_times, walk_steps, window, K, alpha, p,
             count += 1
             cur = _schedule(count, total, alpha, cur)
     return rng.pos, pairs
+
+
+# ---- CPR / TPR (Go tree only): a second graph and a third table --------------------------------------------------------
+def cpr_transform_user(target, source, user_embed, target_embed, source_embed, user, dim):  # cpr.go:127-172
+    out = [0.0] * dim
+    count = 0.0
+    for d in range(dim):
+        out[d] += user_embed[user][d]
+    count += 1.0
+    for item in target.graph.get(user, []):  # userToTarget: vids of the target graph with neighbours (cpr.go:53-59)
+        if item < len(target_embed):
+            for d in range(dim):
+                out[d] += target_embed[item][d]
+            count += 1.0
+    if user < source.max_vid:  # userToSource is filled for vid < sourceGraph.MaxVid only (cpr.go:72-78)
+        for item in source.graph.get(user, []):
+            if item < len(source_embed):
+                for d in range(dim):
+                    out[d] += source_embed[item][d]
+                count += 1.0
+    if count > 0:
+        for d in range(dim):
+            out[d] /= count
+    return out
+
+
+def train_cpr(target, source, user_embed, target_embed, source_embed, dim, iterations, total, alpha, user_reg, item_reg, margin, rng):
+    """CPR.Train (cpr.go:175-282), one worker, `iterations` trips of a run of `total` samples. The source-domain item rows
+    are only ever read. A trip whose user has no target-domain neighbour is skipped WITHOUT counting (cpr.go:214-216)."""
+    cur, count = alpha, 0
+    for _ in range(iterations):
+        user = target.source_sample(rng)
+        pos = target.target_sample(user, rng)
+        if pos == -1:
+            continue
+        uv = cpr_transform_user(target, source, user_embed, target_embed, source_embed, user, dim)
+        neg = target.negative_sample(rng)
+        ps = ns = 0.0
+        for d in range(dim):
+            ps += uv[d] * target_embed[pos][d]
+            ns += uv[d] * target_embed[neg][d]
+        diff = ps - ns
+        if diff < margin:
+            g = cur * target.fast_sigmoid(-(diff - margin))
+            pg, ng, ug = [0.0] * dim, [0.0] * dim, [0.0] * dim
+            for d in range(dim):
+                pg[d] = g * uv[d]
+                ng[d] = -g * uv[d]
+                ug[d] = g * (target_embed[pos][d] - target_embed[neg][d])
+            for d in range(dim):
+                user_embed[user][d] -= cur * user_reg * user_embed[user][d]
+                user_embed[user][d] += ug[d]
+                target_embed[pos][d] -= cur * item_reg * target_embed[pos][d]
+                target_embed[pos][d] += pg[d]
+                target_embed[neg][d] -= cur * item_reg * target_embed[neg][d]
+                target_embed[neg][d] += ng[d]
+        count += 1
+        cur = _schedule(count, total, alpha, cur)
+    return rng.pos
+
+
+def tpr_item_vector(iw, item_embed, word_embed, item, dim, text_weight):  # tpr.go:101-121
+    out = [(1.0 - text_weight) * item_embed[item][d] for d in range(dim)]
+    words = iw.graph.get(item, [])
+    if len(words) > 0:
+        for word in words:
+            for d in range(dim):
+                out[d] += (text_weight / float(len(words))) * word_embed[word][d]
+    else:
+        out = [item_embed[item][d] for d in range(dim)]
+    return out
+
+
+def train_tpr(ui, iw, user_embed, item_embed, word_embed, dim, iterations, total, alpha, lam, text_weight, rng):
+    """TPR.Train (tpr.go:124-262), one worker. Items are looked up in the item-word graph by their user-item vid."""
+    cur, count = alpha, 0
+    for _ in range(iterations):
+        user = ui.source_sample(rng)
+        pos = ui.target_sample(user, rng)
+        if pos == -1:
+            continue
+        neg = ui.negative_sample(rng)
+        pv = tpr_item_vector(iw, item_embed, word_embed, pos, dim, text_weight)
+        nv = tpr_item_vector(iw, item_embed, word_embed, neg, dim, text_weight)
+        ps = ns = 0.0
+        for d in range(dim):
+            ps += user_embed[user][d] * pv[d]
+            ns += user_embed[user][d] * nv[d]
+        coef = cur * ui.fast_sigmoid(ns - ps)
+        ug, pg, ng = [0.0] * dim, [0.0] * dim, [0.0] * dim
+        for d in range(dim):
+            ug[d] = coef * (pv[d] - nv[d])
+            pg[d] = coef * user_embed[user][d]
+            ng[d] = -coef * user_embed[user][d]
+        for d in range(dim):
+            user_embed[user][d] += ug[d] - lam * cur * user_embed[user][d]
+        for d in range(dim):
+            item_embed[pos][d] += (1.0 - text_weight) * pg[d] - lam * cur * item_embed[pos][d]
+            item_embed[neg][d] += (1.0 - text_weight) * ng[d] - lam * cur * item_embed[neg][d]
+        pw = iw.graph.get(pos, [])
+        if len(pw) > 0:
+            ww = text_weight / float(len(pw))
+            for word in pw:
+                for d in range(dim):
+                    word_embed[word][d] += ww * pg[d] - lam * cur * word_embed[word][d]
+        nw = iw.graph.get(neg, [])
+        if len(nw) > 0:
+            ww = text_weight / float(len(nw))
+            for word in nw:
+                for d in range(dim):
+                    word_embed[word][d] += ww * ng[d] - lam * cur * word_embed[word][d]
+        count += 1
+        cur = _schedule(count, total, alpha, cur)
+    return rng.pos

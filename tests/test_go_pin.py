@@ -115,3 +115,34 @@ def test_fixture_is_reproducible_from_the_restatement():
     a2, c2 = G["bip_init_v"].copy(), G["bip_init_c"].copy()
     assert og.train_bpr_go(a2, c2, 0.025, 0.001, 5000, SEED, 0) == pos
     assert np.array_equal(np.array(a), a2) and np.array_equal(np.array(c), c2)
+
+
+# ---- CPR / TPR (Go tree only; two graphs, three tables): tests/golden/golden_go_aux_v1.npz ---------------------------------
+GA = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_go_aux_v1.npz"))
+
+
+def test_cpr_matches_the_python_restatement():
+    tg, _ = _oracle(GA["cpr_t_src"], GA["cpr_t_dst"], GA["cpr_t_w"], 1)
+    sg, _ = _oracle(GA["cpr_s_src"], GA["cpr_s_dst"], GA["cpr_s_w"], 1)
+    for tag in ("cpr", "cpr_m0"):
+        alpha, ureg, ireg, margin, total = GA[f"{tag}_args"]
+        U, T, S = GA["cpr_init_u"].copy(), GA["cpr_init_t"].copy(), GA["cpr_init_s"].copy()
+        words = tg.train_cpr_go(sg, U, T, S, alpha, ureg, ireg, margin, int(total), int(total), SEED, 0)
+        assert words == int(GA[f"{tag}_words"])
+        assert np.array_equal(U, GA[f"{tag}_u"]) and np.array_equal(T, GA[f"{tag}_t"])
+        assert np.array_equal(S, GA["cpr_init_s"])  # the source-domain rows are only read (cpr.go:160-167)
+    assert not np.array_equal(GA["cpr_u"], GA["cpr_init_u"])
+    # the gating margin really gates: fewer rows moved than with the default margin of 8
+    moved = lambda a, b: int((np.abs(a - b).max(axis=1) > 0).sum())
+    assert moved(GA["cpr_m0_t"], GA["cpr_init_t"]) <= moved(GA["cpr_t"], GA["cpr_init_t"])
+
+
+def test_tpr_matches_the_python_restatement():
+    ui, _ = _oracle(GA["tpr_ui_src"], GA["tpr_ui_dst"], GA["tpr_ui_w"], 1)
+    iw, _ = _oracle(GA["tpr_iw_src"], GA["tpr_iw_dst"], GA["tpr_iw_w"], 0)
+    alpha, lam, tw, total = GA["tpr_args"]
+    U, I, W = GA["tpr_init_u"].copy(), GA["tpr_init_i"].copy(), GA["tpr_init_w"].copy()
+    words = ui.train_tpr_go(iw, U, I, W, alpha, lam, tw, int(total), int(total), SEED, 0)
+    assert words == int(GA["tpr_words"])
+    assert np.array_equal(U, GA["tpr_u"]) and np.array_equal(I, GA["tpr_i"]) and np.array_equal(W, GA["tpr_w"])
+    assert not np.array_equal(W, GA["tpr_init_w"])  # word rows are trained (tpr.go:216-232)
