@@ -308,6 +308,9 @@ typedef struct {
     int neg_mode;
     /* node2vec (cmd/node2vec/main.go:21-22): return parameter p, in-out parameter q */
     double n2v_p, n2v_q;
+    /* CPR (cmd/cpr/main.go:22-24): item regularisation and BPR margin (user regularisation = lambda); TPR (tpr.go:38,
+     * cmd/tpr/main.go): weight of the text component of an item vector */
+    double item_reg, margin, text_weight;
 } smore_train_params;
 #define SMORE_PAIRING_AUTO 0
 #define SMORE_PAIRING_COUPLED 1
@@ -348,6 +351,26 @@ int smore_train_deepwalk(smore_model_t m, const smore_train_params* p);
  * walk -- first step TargetSample, then per step weight * (1/p for the previous vertex | 1 for a neighbour of it | 1/q) summed
  * and scanned in adjacency order, one draw per step -- fixed full window, UpdatePairs. params.n2v_p / n2v_q. */
 int smore_train_node2vec(smore_model_t m, const smore_train_params* p);
+/* ---- CPR / TPR (Go tree only): models over TWO graphs and THREE tables ------------------------------------------------
+ * The model is created on the FIRST graph (CPR: target domain, TPR: user-item graph; SMORE_SEM_GO) with two tables of V rows
+ * -- table 0: users, table 1: items -- and the SECOND graph is attached as bare adjacency (CSR over its own vids, reference
+ * insertion order) together with the third table of V_aux rows (CPR: source-domain item rows, only read; TPR: word rows,
+ * trained). As in the reference a vertex of the first graph is looked up in the second BY ITS VID (cpr.go:148-169,
+ * tpr.go:108): the caller must load the two edge lists so that shared entities get equal vids, exactly as it must for the
+ * Go binaries. `rows` (V_aux x dim doubles) may be NULL: the table is then drawn (U - 0.5) / dim from `seed`.
+ * Replaces CPR.LoadSourceDomain + Init (cpr.go:64-125) / TPR.LoadItemWordGraph + Init (tpr.go:49-99). */
+int smore_model_attach_aux(smore_model_t m, int64_t V_aux, const int64_t* row_off, const int32_t* col, const double* rows,
+                           uint64_t seed);
+int smore_model_get_aux_rows(smore_model_t m, int64_t first, int64_t n, double* host);
+/* CPR.Train (internal/models/cpr/cpr.go:175-282): SourceSample -> TargetSample -> transformUser (mean of the user row, the
+ * rows of its target-domain neighbours and of its source-domain neighbours, :127-172) -> NegativeSample -> margin-gated BPR
+ * step on the user row and the two target-domain item rows. params.total samples (update_times x 10^6), alpha, lambda =
+ * user_reg, item_reg, margin. */
+int smore_train_cpr(smore_model_t m, const smore_train_params* p);
+/* TPR.Train (internal/models/tpr/tpr.go:124-262): BPR on text-enriched item vectors ((1 - text_weight) x item row +
+ * text_weight x mean of the item's word rows, :101-121); updates the user row, both item rows and every word row of both
+ * items. params.total samples (sample_times x MaxLine), alpha, lambda, text_weight. */
+int smore_train_tpr(smore_model_t m, const smore_train_params* p);
 /* HPE::Train (src/model/HPE.cpp:93-147): SourceSample -> TargetSample -> UpdateCommunity (src/proNet.cpp:3018-3054, the
  * context walks on for walk_steps steps; Opt_SigmoidRegSGD :1332-1351 with reg = params.lambda) -> UpdatePair with the
  * roles swapped. C++ only (the Go hpe model is LINE-2 with UpdatePair, hpe.go:97-107: use smore_train_line). */

@@ -41,7 +41,7 @@ EXPORTS = [
     "smore_model_set_rows_f32_async", "smore_model_get_rows_f32_async", "smore_model_wait_copies",
     "smore_train_line_group", "smore_exchange_stats", "smore_debug_sm_partition", "smore_model_save_weights", "smore_format_rows",
     "smore_model_load_pretrain", "smore_model_save_checkpoint", "smore_model_load_checkpoint", "smore_model_progress", "smore_progress", "smore_train_params_default", "smore_train_line", "smore_train_bpr",
-    "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf", "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_node2vec", "smore_train_stats",
+    "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf", "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_node2vec", "smore_train_stats", "smore_model_attach_aux", "smore_model_get_aux_rows", "smore_train_cpr", "smore_train_tpr",
 ]
 
 
@@ -56,7 +56,7 @@ class TrainParams(C.Structure):
         ("walk_times", C.c_int), ("walk_steps", C.c_int), ("window_min", C.c_int), ("window_max", C.c_int),
         ("max_warps", C.c_int), ("max_walks", i64), ("sched_total", u64), ("sched_offset", u64),
         ("xi", f64), ("omega", f64), ("eta", C.c_int), ("neg_mode", C.c_int),
-        ("n2v_p", f64), ("n2v_q", f64),
+        ("n2v_p", f64), ("n2v_q", f64), ("item_reg", f64), ("margin", f64), ("text_weight", f64),
     ]
 
 
@@ -135,13 +135,16 @@ def lib():
         L.smore_model_save_checkpoint.argtypes = [vp, C.c_char_p]
         L.smore_model_load_checkpoint.argtypes = [vp, C.c_char_p]
         L.smore_model_progress.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+        L.smore_model_attach_aux.argtypes = [vp, i64, vp, vp, vp, u64]
+        L.smore_model_get_aux_rows.argtypes = [vp, i64, i64, vp]
         L.smore_progress.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.smore_format_rows.argtypes = [vp, i64, C.c_int, i64, C.c_int, vp, i64]
         L.smore_format_rows.restype = i64
         L.smore_train_params_default.argtypes = [C.POINTER(TrainParams)]
         L.smore_train_params_default.restype = None
         for name in ("smore_train_line", "smore_train_bpr", "smore_train_warp", "smore_train_hoprec", "smore_train_hpe", "smore_train_mf",
-                     "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_node2vec"):
+                     "smore_train_skewopt", "smore_train_deepwalk", "smore_train_walklets", "smore_train_node2vec", "smore_train_cpr",
+                     "smore_train_tpr"):
             getattr(L, name).argtypes = [vp, C.POINTER(TrainParams)]
         L.smore_train_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(f64),
                                         C.POINTER(f64)]
@@ -515,6 +518,26 @@ class Model:
     def train_deepwalk(self, p): return self._train(lib().smore_train_deepwalk, p)
     def train_walklets(self, p): return self._train(lib().smore_train_walklets, p)
     def train_node2vec(self, p): return self._train(lib().smore_train_node2vec, p)
+    def train_cpr(self, p): return self._train(lib().smore_train_cpr, p)
+    def train_tpr(self, p): return self._train(lib().smore_train_tpr, p)
+
+    def attach_aux(self, row_off, col, rows=None, seed=0):
+        """CPR / TPR: adjacency of the second graph (CSR over its own vids) + the third table (None: random init)."""
+        off = np.ascontiguousarray(row_off, dtype=np.int64)
+        cl = np.ascontiguousarray(col, dtype=np.int32)
+        self.aux_V = len(off) - 1
+        r = None
+        if rows is not None:
+            r = np.ascontiguousarray(rows, dtype=np.float64)
+            assert r.shape == (self.aux_V, self.dim)
+        check(lib().smore_model_attach_aux(self.h, self.aux_V, off.ctypes.data_as(vp), cl.ctypes.data_as(vp),
+                                           r.ctypes.data_as(vp) if r is not None else None, seed))
+
+    def get_aux_rows(self, first=0, n=None):
+        n = self.aux_V - first if n is None else n
+        out = np.empty((n, self.dim), dtype=np.float64)
+        check(lib().smore_model_get_aux_rows(self.h, first, n, out.ctypes.data_as(vp)))
+        return out
 
     def stats(self):
         s, pr, w0, ms, tr = u64(), u64(), u64(), f64(), f64()

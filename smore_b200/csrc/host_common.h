@@ -152,6 +152,11 @@ struct smore_model_s {
     // stats of the last train call
     uint64_t st_samples = 0, st_pairs = 0, st_words0 = 0, st_tries = 0;
     double st_ms = 0;
+    // CPR / TPR: adjacency of the second graph (over ITS vids) and the third table, aux_V x dim in the model's dtype
+    int64_t* d_aux_off = nullptr;
+    int32_t* d_aux_col = nullptr;
+    int64_t aux_V = 0, aux_E = 0;
+    void* aux_tab = nullptr;
     // live progress (smore_progress): host-mapped {done, alpha bits, total, running}; schedule units done before this call
     unsigned long long* live = nullptr;
     unsigned long long live_offset = 0;
@@ -167,6 +172,7 @@ struct smore_model_s {
         delete xch;
         delete rot;
         if (live) cudaFreeHost(live);
+        cudaFree(d_aux_off); cudaFree(d_aux_col); cudaFree(aux_tab);
     }
 };
 

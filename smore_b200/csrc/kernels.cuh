@@ -75,6 +75,13 @@ struct TrainArgs {
     int n2v;   // node2vec: biased second-order walks (1/p, 1/q below)
     double n2v_pinv, n2v_qinv;
     int vred;  // row-sharded peer-access mode: vertex rows take their delta with red.global.add instead of a full-row store
+    // CPR / TPR (Go tree): adjacency of the SECOND graph over its own vids and the third table (CPR: source-domain item rows,
+    // read only; TPR: word rows, trained); a vertex of the first graph is looked up there by its vid (cpr.go:148-169, tpr.go:108)
+    const int64_t* aux_off;
+    const int32_t* aux_col;
+    int64_t aux_V;
+    T* aux_tab;
+    T item_reg, margin, text_w;
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@
 
 namespace smore {
 
-enum RankKind { RANK_BPR = 0, RANK_WARP = 1, RANK_HOPREC = 2, RANK_SKEWOPT = 3 };
+enum RankKind { RANK_BPR = 0, RANK_WARP = 1, RANK_HOPREC = 2, RANK_SKEWOPT = 3, RANK_CPR = 4, RANK_TPR = 5 };
 
 template <typename T>
 __device__ __forceinline__ T ldv(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
@@ -429,6 +429,296 @@ __global__ void __launch_bounds__(kBlockThreads) k_hoprec(TrainArgs<typename C::
             }
             st.pairs += 5;
         }
+        st.count++;
+        sched_tick(st, a.sched);
+    }
+    st.pos = ring.pos;
+    if (lane == 0) a.state[w] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CPR and TPR (Go tree only): pairwise ranking where one side of the score is AGGREGATED on the fly from the rows of a
+// vertex' neighbours, in a second graph as well as in the first. One warp per sample, lane-parallel over the dimension:
+// every per-dimension sum runs in the reference's order (adjacency order), so the fp64 deterministic mode reproduces the
+// restatements bit for bit; the fp32 Hogwild mode pushes row deltas with red.global.add like every other trainer.
+// ---------------------------------------------------------------------------------------------------------------
+// acc += sum of tab[col[e]] for e in [beg, end), four gathers in flight; returns the number of rows added
+template <class C>
+__device__ __forceinline__ int add_neighbour_rows(Row<C>& acc, const typename C::T* tab, const int32_t* __restrict__ col, int64_t beg,
+                                                  int64_t end, int dim, int lane) {
+    using A = Ar<typename C::T>;
+    for (int64_t e0 = beg; e0 < end; e0 += 32) {
+        const int nb = (int)min((int64_t)32, end - e0);
+        const int my = lane < nb ? __ldg(col + e0 + lane) : 0;
+        for (int r0 = 0; r0 < nb; r0 += 4) {
+            Row<C> rr[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int id = __shfl_sync(kFull, my, (r0 + r) & 31);
+                if (r0 + r < nb) rr[r].load(tab + (size_t)id * dim, lane, dim);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r0 + r < nb) {
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) acc.x[e] = A::add(acc.x[e], rr[r].x[e]);
+                }
+        }
+    }
+    return (int)(end - beg);
+}
+
+// CPR.Train (internal/models/cpr/cpr.go:175-282) with transformUser (:127-172). Wv = user rows, Wc = target-domain item rows,
+// aux_tab = source-domain item rows. lambda = user_reg. A sample whose user has no target-domain neighbour is skipped
+// without counting (:214-216).
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_cpr(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
+    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
+    const T* lut = stage_lut<T>(a.lut, lut_s);
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    DrawRing ring;
+    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
+    const GraphDev& g = a.g;
+    const int dim = a.dim;
+    for (uint64_t it = 0; it < a.jobs; ++it) {
+        ring.ensure();
+        int64_t u = -1, p = -1, n = -1;
+        int used = 0;
+        if (lane == 0) {
+            u = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
+            p = target_sample(g, u, ring.peek(2), ring.peek(3), used);
+            if (p >= 0) n = (int64_t)negative_sample(g, ring.peek(2u + (uint32_t)used), ring.peek(3u + (uint32_t)used));
+        }
+        u = __shfl_sync(kFull, u, 0);
+        p = __shfl_sync(kFull, p, 0);
+        n = __shfl_sync(kFull, n, 0);
+        used = __shfl_sync(kFull, used, 0);
+        if (p < 0) {
+            ring.advance(2u + (uint32_t)used);
+            continue;
+        }
+        ring.advance(4u + (uint32_t)used);
+        const T alpha = (T)st.alpha;
+        T* pu = a.Wv + (size_t)u * dim;
+        T* pp = a.Wc + (size_t)p * dim;
+        T* pn = a.Wc + (size_t)n * dim;
+        Row<C> ru, rp, rn, uv;
+        ru.load(pu, lane, dim);
+        rp.load(pp, lane, dim);
+        rn.load(pn, lane, dim);
+        // transformUser: (user + target-domain neighbours + source-domain neighbours) / count, summed from 0.0 in that order
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) uv.x[e] = A::add((T)0, ru.x[e]);
+        int cnt = 1;
+        cnt += add_neighbour_rows<C>(uv, a.Wc, g.col, __ldg(g.row_off + u), __ldg(g.row_off + u + 1), dim, lane);
+        if (u < a.aux_V) cnt += add_neighbour_rows<C>(uv, a.aux_tab, a.aux_col, __ldg(a.aux_off + u), __ldg(a.aux_off + u + 1), dim, lane);
+        const T fc = (T)cnt;
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) uv.x[e] = A::div(uv.x[e], fc);
+        Row<C> two[2] = {rp, rn};
+        T sc[2];
+        dots<C, 2>(uv, two, 2, sc);
+        const T diff = A::sub(sc[0], sc[1]);
+        if (diff < a.margin) {
+            const T gc = A::mul(alpha, fast_sigmoid<T>(lut, A::sub((T)0, A::sub(diff, a.margin))));
+            const T cu = A::mul(alpha, a.lambda), ci = A::mul(alpha, a.item_reg);
+            if constexpr (kAtomicRows<C>) {
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) {
+                    const T pg = A::mul(gc, uv.x[e]);
+                    const T ug = A::mul(gc, A::sub(rp.x[e], rn.x[e]));
+                    ru.x[e] = A::msub(ug, cu, ru.x[e]);           // -(alpha*user_reg)*w + ug
+                    rp.x[e] = A::msub(pg, ci, rp.x[e]);           // -(alpha*item_reg)*w + pg
+                    rn.x[e] = A::sub(A::mul(-ci, rn.x[e]), pg);   // -(alpha*item_reg)*w - pg
+                }
+                row_red_add<C>(pu, ru, lane, dim);
+                row_red_add<C>(pp, rp, lane, dim);
+                row_red_add<C>(pn, rn, lane, dim);
+            } else {
+                const bool same = p == n;
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) {
+                    const T pg = A::mul(gc, uv.x[e]);
+                    const T ng = A::mul(-gc, uv.x[e]);
+                    const T ug = A::mul(gc, A::sub(rp.x[e], rn.x[e]));
+                    ru.x[e] = A::add(A::msub(ru.x[e], cu, ru.x[e]), ug);
+                    rp.x[e] = A::add(A::msub(rp.x[e], ci, rp.x[e]), pg);
+                    const T nc = same ? rp.x[e] : rn.x[e];  // pos == neg: the second pair of statements sees the first (:251-258)
+                    rn.x[e] = A::add(A::msub(nc, ci, nc), ng);
+                }
+                ru.store(pu, lane, dim);
+                if (!same) rp.store(pp, lane, dim);
+                rn.store(pn, lane, dim);
+            }
+            st.pairs++;
+        }
+        st.count++;
+        sched_tick(st, a.sched);
+    }
+    st.pos = ring.pos;
+    if (lane == 0) a.state[w] = st;
+}
+
+// getTextEnrichedItemEmbedding (tpr.go:101-121): (1 - tw) * item + sum over the item's words of (tw / #words) * word, or the
+// item row itself when the item has no words. `ri` returns the item's base row, `nw` its number of words.
+template <class C>
+__device__ __forceinline__ void tpr_enriched(const TrainArgs<typename C::T>& a, int64_t item, Row<C>& ri, Row<C>& out, int64_t& beg,
+                                             int& nw, int lane) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    const int dim = a.dim;
+    ri.load(a.Wc + (size_t)item * dim, lane, dim);
+    beg = 0;
+    nw = 0;
+    if (item < a.aux_V) {
+        beg = __ldg(a.aux_off + item);
+        nw = (int)(__ldg(a.aux_off + item + 1) - beg);
+    }
+    if (nw <= 0) {
+        out = ri;
+        return;
+    }
+    const T base = A::sub((T)1, a.text_w);
+    const T wq = A::div(a.text_w, (T)nw);
+#pragma unroll
+    for (int e = 0; e < C::EPL; ++e) out.x[e] = A::mul(base, ri.x[e]);
+    for (int e0 = 0; e0 < nw; e0 += 32) {
+        const int nb = min(32, nw - e0);
+        const int my = lane < nb ? __ldg(a.aux_col + beg + e0 + lane) : 0;
+        for (int r0 = 0; r0 < nb; r0 += 4) {
+            Row<C> rr[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int id = __shfl_sync(kFull, my, (r0 + r) & 31);
+                if (r0 + r < nb) rr[r].load(a.aux_tab + (size_t)id * dim, lane, dim);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r0 + r < nb) {
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) out.x[e] = A::madd(out.x[e], wq, rr[r].x[e]);
+                }
+        }
+    }
+}
+
+// word rows of one item: w += (tw / #words) * grad - (lambda * alpha) * w, one word after the other (tpr.go:216-232)
+template <class C>
+__device__ __forceinline__ void tpr_push_words(const TrainArgs<typename C::T>& a, int64_t beg, int nw, const Row<C>& grad,
+                                               typename C::T la, int lane) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    if (nw <= 0) return;
+    const int dim = a.dim;
+    const T ww = A::div(a.text_w, (T)nw);
+    for (int e0 = 0; e0 < nw; e0 += 32) {
+        const int nb = min(32, nw - e0);
+        const int my = lane < nb ? __ldg(a.aux_col + beg + e0 + lane) : 0;
+        for (int r = 0; r < nb; ++r) {
+            T* pw = a.aux_tab + (size_t)__shfl_sync(kFull, my, r) * dim;
+            Row<C> rw;
+            rw.load(pw, lane, dim);
+#pragma unroll
+            for (int e = 0; e < C::EPL; ++e) {
+                const T d = A::msub(A::mul(ww, grad.x[e]), la, rw.x[e]);
+                rw.x[e] = kAtomicRows<C> ? d : A::add(rw.x[e], d);
+            }
+            if constexpr (kAtomicRows<C>) row_red_add<C>(pw, rw, lane, dim);
+            else rw.store(pw, lane, dim);  // (a repeated word is re-read by the lanes that wrote it: program order)
+        }
+    }
+}
+
+// TPR.Train (internal/models/tpr/tpr.go:124-262). Wv = user rows, Wc = item rows (both over the user-item graph's vids),
+// aux_tab = word rows over the item-word graph's vids.
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads) k_tpr(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    uint32_t* rings = reinterpret_cast<uint32_t*>(smem_raw);
+    T* lut_s = reinterpret_cast<T*>(smem_raw + kWarpsPerBlock * 256 * sizeof(uint32_t));
+    const T* lut = stage_lut<T>(a.lut, lut_s);
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * kWarpsPerBlock + wib;
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    DrawRing ring;
+    ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
+    const GraphDev& g = a.g;
+    const int dim = a.dim;
+    for (uint64_t it = 0; it < a.jobs; ++it) {
+        ring.ensure();
+        int64_t u = -1, p = -1, n = -1;
+        int used = 0;
+        if (lane == 0) {
+            u = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
+            p = target_sample(g, u, ring.peek(2), ring.peek(3), used);
+            if (p >= 0) n = (int64_t)negative_sample(g, ring.peek(2u + (uint32_t)used), ring.peek(3u + (uint32_t)used));
+        }
+        u = __shfl_sync(kFull, u, 0);
+        p = __shfl_sync(kFull, p, 0);
+        n = __shfl_sync(kFull, n, 0);
+        used = __shfl_sync(kFull, used, 0);
+        if (p < 0) {
+            ring.advance(2u + (uint32_t)used);
+            continue;
+        }
+        ring.advance(4u + (uint32_t)used);
+        const T alpha = (T)st.alpha;
+        const T la = A::mul(a.lambda, alpha);
+        T* pu = a.Wv + (size_t)u * dim;
+        T* pp = a.Wc + (size_t)p * dim;
+        T* pn = a.Wc + (size_t)n * dim;
+        Row<C> ru, rp, rn, two[2];
+        int64_t pbeg, nbeg;
+        int pnw, nnw;
+        ru.load(pu, lane, dim);
+        tpr_enriched<C>(a, p, rp, two[0], pbeg, pnw, lane);
+        tpr_enriched<C>(a, n, rn, two[1], nbeg, nnw, lane);
+        T sc[2];
+        dots<C, 2>(ru, two, 2, sc);
+        const T gc = A::mul(alpha, fast_sigmoid<T>(lut, A::sub(sc[1], sc[0])));
+        const T base = A::sub((T)1, a.text_w);
+        Row<C> pg, ng;
+        const bool same = p == n;
+#pragma unroll
+        for (int e = 0; e < C::EPL; ++e) {
+            const T ug = A::mul(gc, A::sub(two[0].x[e], two[1].x[e]));
+            pg.x[e] = A::mul(gc, ru.x[e]);
+            ng.x[e] = A::mul(-gc, ru.x[e]);
+            const T du = A::msub(ug, la, ru.x[e]);
+            const T dp = A::msub(A::mul(base, pg.x[e]), la, rp.x[e]);
+            if constexpr (kAtomicRows<C>) {
+                ru.x[e] = du;
+                rp.x[e] = dp;
+                rn.x[e] = A::msub(A::mul(base, ng.x[e]), la, rn.x[e]);
+            } else {
+                ru.x[e] = A::add(ru.x[e], du);
+                rp.x[e] = A::add(rp.x[e], dp);
+                const T nc = same ? rp.x[e] : rn.x[e];  // pos == neg: the negative's statement sees the positive's (:211-212)
+                rn.x[e] = A::add(nc, A::msub(A::mul(base, ng.x[e]), la, nc));
+            }
+        }
+        if constexpr (kAtomicRows<C>) {
+            row_red_add<C>(pu, ru, lane, dim);
+            row_red_add<C>(pp, rp, lane, dim);
+            row_red_add<C>(pn, rn, lane, dim);
+        } else {
+            ru.store(pu, lane, dim);
+            if (!same) rp.store(pp, lane, dim);
+            rn.store(pn, lane, dim);
+        }
+        tpr_push_words<C>(a, pbeg, pnw, pg, la, lane);
+        tpr_push_words<C>(a, nbeg, nnw, ng, la, lane);
+        st.pairs++;
         st.count++;
         sched_tick(st, a.sched);
     }

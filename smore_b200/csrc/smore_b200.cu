@@ -243,6 +243,9 @@ void smore_train_params_default(smore_train_params* p) {
     p->max_walks = -1;
     p->n2v_p = 1.0;  // cmd/node2vec/main.go:21-22
     p->n2v_q = 1.0;
+    p->item_reg = 0.01;    // cmd/cpr/main.go:22-24
+    p->margin = 8.0;
+    p->text_weight = 0.5;  // tpr.go:38
     p->xi = 10.0;  // cli/skewopt.cpp:53-54
     p->omega = 3.0;
     p->eta = 3;
@@ -1133,6 +1136,75 @@ int smore_train_skewopt(smore_model_t m, const smore_train_params* p) {
     if (p->eta < 1 || p->eta > 15) return fail(SMORE_E_INVALID, "eta must be in [1,15]");
     if (!(p->omega != 0)) return fail(SMORE_E_INVALID, "omega must be non-zero");
     return m->dtype == SMORE_F64 ? train_ranking_t<double>(m, p, RANK_SKEWOPT) : train_ranking_t<float>(m, p, RANK_SKEWOPT);
+}
+
+// ---- CPR / TPR (Go tree only): a second graph and a third table ------------------------------------------------------
+int smore_model_attach_aux(smore_model_t m, int64_t V_aux, const int64_t* row_off, const int32_t* col, const double* rows,
+                           uint64_t seed) {
+    if (!m || V_aux < 1 || !row_off) return fail(SMORE_E_INVALID, "bad model / auxiliary graph");
+    if (m->g->world != 1) return fail(SMORE_E_UNSUPPORTED, "CPR / TPR run on unsharded graphs");
+    const int64_t E = row_off[V_aux];
+    if (row_off[0] != 0 || E < 0 || (E > 0 && !col)) return fail(SMORE_E_INVALID, "bad auxiliary CSR");
+    for (int64_t v = 0; v < V_aux; ++v)
+        if (row_off[v + 1] < row_off[v]) return fail(SMORE_E_INVALID, "auxiliary row_off must be non-decreasing");
+    for (int64_t e = 0; e < E; ++e)
+        if (col[e] < 0 || col[e] >= V_aux) return fail(SMORE_E_INVALID, "auxiliary col[%lld] = %d is not a vertex", (long long)e, col[e]);
+    if (int rc = ensure_device()) return rc;
+    cudaFree(m->d_aux_off); cudaFree(m->d_aux_col); cudaFree(m->aux_tab);
+    m->d_aux_off = nullptr; m->d_aux_col = nullptr; m->aux_tab = nullptr;
+    m->aux_V = V_aux;
+    m->aux_E = E;
+    if (int rc = dev_alloc_copy(&m->d_aux_off, row_off, (size_t)V_aux + 1)) return rc;
+    const int32_t none = 0;
+    if (int rc = dev_alloc_copy(&m->d_aux_col, E ? col : &none, (size_t)std::max<int64_t>(E, 1))) return rc;
+    const size_t cnt = (size_t)V_aux * (size_t)m->dim;
+    CU(cudaMalloc(&m->aux_tab, cnt * m->elem()));
+    if (rows) {
+        if (m->dtype == SMORE_F64) {
+            CU(cudaMemcpy(m->aux_tab, rows, cnt * sizeof(double), cudaMemcpyHostToDevice));
+        } else {
+            std::vector<float> f(cnt);
+            parallel_for((int64_t)cnt, 1 << 16, [&](int64_t b, int64_t e, int) {
+                for (int64_t i = b; i < e; ++i) f[(size_t)i] = (float)rows[i];
+            });
+            CU(cudaMemcpy(m->aux_tab, f.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    } else {  // (U - 0.5) / dim like every Go table (cpr.go:118-124, tpr.go:92-98), the init stream of a third table
+        const int blocks = (int)std::min<size_t>((cnt + 255) / 256, 148 * 8);
+        if (m->dtype == SMORE_F64) k_init_table<double><<<blocks, 256>>>((double*)m->aux_tab, (int64_t)cnt, m->dim, seed, kInitStreamBase + 2, 1, 0, 0, 0);
+        else k_init_table<float><<<blocks, 256>>>((float*)m->aux_tab, (int64_t)cnt, m->dim, seed, kInitStreamBase + 2, 1, 0, 0, 0);
+        g_launches++;
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+    }
+    return SMORE_OK;
+}
+
+int smore_model_get_aux_rows(smore_model_t m, int64_t first, int64_t n, double* host) {
+    if (!m || !m->aux_tab || !host) return fail(SMORE_E_INVALID, "no auxiliary table attached / null buffer");
+    if (first < 0 || n < 0 || first + n > m->aux_V) return fail(SMORE_E_INVALID, "row range out of bounds (the auxiliary table holds %lld rows)", (long long)m->aux_V);
+    const size_t cnt = (size_t)n * (size_t)m->dim;
+    if (cnt == 0) return SMORE_OK;
+    if (m->dtype == SMORE_F64) {
+        CU(cudaMemcpy(host, (const double*)m->aux_tab + (size_t)first * m->dim, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<float> f(cnt);
+        CU(cudaMemcpy(f.data(), (const float*)m->aux_tab + (size_t)first * m->dim, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < cnt; ++i) host[i] = (double)f[i];
+    }
+    return SMORE_OK;
+}
+
+static int train_aux_common(smore_model_t m, const smore_train_params* p, int kind, const char* name) {
+    if (int rc = check_train(m, p, 2)) return rc;
+    if (p->semantics != SMORE_SEM_GO) return fail(SMORE_E_UNSUPPORTED, "%s exists only in the Go tree", name);
+    if (!m->aux_tab) return fail(SMORE_E_INVALID, "%s: call smore_model_attach_aux first (second graph + third table)", name);
+    return m->dtype == SMORE_F64 ? train_ranking_t<double>(m, p, kind) : train_ranking_t<float>(m, p, kind);
+}
+int smore_train_cpr(smore_model_t m, const smore_train_params* p) { return train_aux_common(m, p, RANK_CPR, "CPR"); }
+int smore_train_tpr(smore_model_t m, const smore_train_params* p) {
+    if (p && !(p->text_weight >= 0 && p->text_weight <= 1)) return fail(SMORE_E_INVALID, "text_weight must be in [0,1]");
+    return train_aux_common(m, p, RANK_TPR, "TPR");
 }
 
 int smore_train_warp(smore_model_t m, const smore_train_params* p) {

@@ -115,3 +115,95 @@ def test_node2vec_cli(tmp_path):
     r = subprocess.run([os.path.join(root, "smore_b200", "bin", "node2vec"), "-train", net, "-save", rep, "-semantics", "cpp"],
                        capture_output=True, text=True)
     assert r.returncode != 0 and "only in the Go tree" in r.stderr
+
+
+# ---- CPR / TPR (Go tree only): two graphs, three tables -- tests/golden/golden_go_aux_v1.npz ------------------------------
+GA = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_go_aux_v1.npz"))
+
+
+def _aux_csr(src, dst, w, undirected):
+    off, col, _, _ = B.edges_to_csr(src, dst, w, undirected)
+    return off, col
+
+
+@pytest.mark.parametrize("tag", ["cpr", "cpr_m0"])
+def test_cpr(tag):
+    """internal/models/cpr: deterministic fp64 rows bit-identical to the Python restatement (default margin 8 and a margin
+    that gates updates); the source-domain rows are only read."""
+    g = _graph(GA["cpr_t_src"], GA["cpr_t_dst"], GA["cpr_t_w"], 1)
+    V = GA["cpr_init_t"].shape[0]
+    alpha, ureg, ireg, margin, total = GA[f"{tag}_args"]
+    m = capi.Model(g, 8, 2, capi.F64)
+    m.set_rows(0, GA["cpr_init_u"][:V]), m.set_rows(1, GA["cpr_init_t"])
+    m.attach_aux(*_aux_csr(GA["cpr_s_src"], GA["cpr_s_dst"], GA["cpr_s_w"], 1), rows=GA["cpr_init_s"])
+    st = m.train_cpr(_params(total=int(total), alpha=float(alpha), lambda_=float(ureg), item_reg=float(ireg), margin=float(margin)))
+    assert st["words_stream0"] == int(GA[f"{tag}_words"])
+    assert np.array_equal(m.get_rows(0), GA[f"{tag}_u"][:V]) and np.array_equal(m.get_rows(1), GA[f"{tag}_t"])
+    assert np.array_equal(GA[f"{tag}_u"][V:], GA["cpr_init_u"][V:])  # user rows past the target graph are never trained
+    assert np.array_equal(m.get_aux_rows(), GA["cpr_init_s"])
+
+
+def test_tpr():
+    """internal/models/tpr: user, item AND word rows bit-identical to the Python restatement."""
+    g = _graph(GA["tpr_ui_src"], GA["tpr_ui_dst"], GA["tpr_ui_w"], 1)
+    alpha, lam, tw, total = GA["tpr_args"]
+    m = capi.Model(g, 8, 2, capi.F64)
+    m.set_rows(0, GA["tpr_init_u"]), m.set_rows(1, GA["tpr_init_i"])
+    m.attach_aux(*_aux_csr(GA["tpr_iw_src"], GA["tpr_iw_dst"], GA["tpr_iw_w"], 0), rows=GA["tpr_init_w"])
+    st = m.train_tpr(_params(total=int(total), alpha=float(alpha), lambda_=float(lam), text_weight=float(tw)))
+    assert st["words_stream0"] == int(GA["tpr_words"])
+    assert np.array_equal(m.get_rows(0), GA["tpr_u"]) and np.array_equal(m.get_rows(1), GA["tpr_i"])
+    assert np.array_equal(m.get_aux_rows(), GA["tpr_w"])
+
+
+@pytest.mark.parametrize("model", ["cpr", "tpr"])
+def test_cpr_tpr_fp32_and_hogwild(model):
+    """The fp32 path that Hogwild runs (red.global.add row deltas): one stream against the oracle within 2e-3 relative to
+    the row scale, then a Hogwild run at the library's occupancy moves every table without producing a NaN; a model without
+    an attached second graph, and C++ semantics, are refused."""
+    a, b = ("cpr_t", "cpr_s") if model == "cpr" else ("tpr_ui", "tpr_iw")
+    und_b = 1 if model == "cpr" else 0
+    g = _graph(GA[f"{a}_src"], GA[f"{a}_dst"], GA[f"{a}_w"], 1)
+    og = B.OracleGraph(B.SEM_GO, *B.edges_to_csr(GA[f"{a}_src"], GA[f"{a}_dst"], GA[f"{a}_w"], 1)[:3], max_line=len(GA[f"{a}_src"]))
+    ob = B.OracleGraph(B.SEM_GO, *B.edges_to_csr(GA[f"{b}_src"], GA[f"{b}_dst"], GA[f"{b}_w"], und_b)[:3], max_line=len(GA[f"{b}_src"]))
+    if model == "cpr":
+        V = GA["cpr_init_t"].shape[0]
+        t0, t1, t2 = GA["cpr_init_u"][:V].copy(), GA["cpr_init_t"].copy(), GA["cpr_init_s"].copy()
+    else:
+        t0, t1, t2 = GA["tpr_init_u"].copy(), GA["tpr_init_i"].copy(), GA["tpr_init_w"].copy()
+    total = 20000
+    m = capi.Model(g, 8, 2, capi.F32)
+    with pytest.raises(capi.SmoreError):
+        (m.train_cpr if model == "cpr" else m.train_tpr)(_params(total=100))
+    m.set_rows(0, t0), m.set_rows(1, t1)
+    m.attach_aux(*_aux_csr(GA[f"{b}_src"], GA[f"{b}_dst"], GA[f"{b}_w"], und_b), rows=t2)
+    p = _params(total=total, alpha=0.05, lambda_=0.01, item_reg=0.01, margin=8.0, text_weight=0.5)
+    r0, r1, r2 = t0.copy(), t1.copy(), t2.copy()
+    if model == "cpr":
+        m.train_cpr(p)
+        og.train_cpr_go(ob, r0, r1, r2, 0.05, 0.01, 0.01, 8.0, total, total, SEED, 0)
+    else:
+        m.train_tpr(p)
+        og.train_tpr_go(ob, r0, r1, r2, 0.05, 0.01, 0.5, total, total, SEED, 0)
+    for got, want in ((m.get_rows(0), r0), (m.get_rows(1), r1), (m.get_aux_rows(), r2)):
+        assert np.abs(got - want).max() < 2e-3 * max(np.abs(want).max(), 1e-3)
+    # Hogwild
+    h = capi.Model(g, 8, 2, capi.F32)
+    h.set_rows(0, t0), h.set_rows(1, t1)
+    h.attach_aux(*_aux_csr(GA[f"{b}_src"], GA[f"{b}_dst"], GA[f"{b}_w"], und_b), rows=t2)
+    p.mode, p.total = capi.MODE_HOGWILD, 200_000
+    st = (h.train_cpr if model == "cpr" else h.train_tpr)(p)
+    assert st["samples"] > 0.9 * p.total
+    for got, init in ((h.get_rows(0), t0), (h.get_rows(1), t1)):
+        assert np.isfinite(got).all() and not np.array_equal(got, init)
+    aux = h.get_aux_rows()
+    assert np.isfinite(aux).all() and (np.array_equal(aux, t2) if model == "cpr" else not np.array_equal(aux, t2))
+    # random third table when no rows are given; C++ semantics have neither model
+    h.attach_aux(*_aux_csr(GA[f"{b}_src"], GA[f"{b}_dst"], GA[f"{b}_w"], und_b), rows=None, seed=5)
+    r = h.get_aux_rows()
+    assert np.abs(r).max() <= 0.5 / 8 and r.std() > 0.01
+    gc = capi.Graph.from_csr(*B.edges_to_csr(GA[f"{a}_src"], GA[f"{a}_dst"], GA[f"{a}_w"], 1)[:3])
+    mc = capi.Model(gc, 8, 2, capi.F32)
+    mc.attach_aux(*_aux_csr(GA[f"{b}_src"], GA[f"{b}_dst"], GA[f"{b}_w"], und_b))
+    with pytest.raises(capi.SmoreError):
+        (mc.train_cpr if model == "cpr" else mc.train_tpr)(capi.default_params())

@@ -56,9 +56,9 @@ def hogwild(sem=capi.SEM_CPP, seed=13, **kw):
 SEEDS = (13, 14, 15)  # single-model gates: mean of 3 Hogwild runs (one run's recall@10 has a standard deviation of ~0.003)
 
 
-def mean_of(run):
-    """run(seed) -> (auc, recall) or auc; returns the mean over SEEDS."""
-    return np.mean(np.array([run(sd) for sd in SEEDS], dtype=np.float64), axis=0)
+def mean_of(run, seeds=SEEDS):
+    """run(seed) -> (auc, recall) or auc; returns the mean over `seeds`."""
+    return np.mean(np.array([run(sd) for sd in seeds], dtype=np.float64), axis=0)
 
 
 def check(name, got, want, what="AUC"):
@@ -143,8 +143,11 @@ def test_go_walk_models(model):
         assert 0.9 * ref["pairs"] < st["pair_updates"] < 1.1 * ref["pairs"]
         return Q.evaluate_full(m.get_rows(0), m.get_rows(1), off, col, ts, td)
 
-    # (both sides are 3-run means here: one run's recall@10 moves by +-0.003 on the GPU and +-0.002 on the CPU path)
-    a, r = mean_of(run)
+    # Both sides are means here: the walk models draw few, long, correlated sample groups (72 000 walks), and one run's
+    # recall@10 has a standard deviation of 0.002-0.003 on the CPU path (8 seeds: 0.0996-0.1074, quality_baselines_v2.json)
+    # and up to 0.004 on the GPU (profiles/r2m_go_walk_probe.jsonl). tools/go_walk_streams_probe.py shows that the GPU's
+    # numbers are reproduced by the oracle when it splits the walks over the same number of draw streams sequentially.
+    a, r = mean_of(run, seeds=range(13, 19))
     check(model, a, ref["auc"])
     check(model, r, ref["recall_at_10"], "recall@10")
 
