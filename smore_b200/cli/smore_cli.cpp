@@ -73,7 +73,11 @@ int die(const char* what) {
 
 void usage() {
     printf("[smore_b200]\n\tB200-native SMORe trainers (LINE, DeepWalk, Walklets, BPR, WARP, HOP-Rec)\n\n"
-           "Usage:\n\tsmore <line|deepwalk|walklets|node2vec|bpr|warp|hoprec|hpe|mf|skewopt> -train net.txt -save rep.txt [options]\n\n"
+           "Usage:\n\tsmore <line|deepwalk|walklets|node2vec|bpr|warp|hoprec|hpe|mf|skewopt> -train net.txt -save rep.txt [options]\n"
+           "\tsmore cpr -train_target t.txt -train_source s.txt -save_user u.txt -save_target t.rep -save_source s.rep\n"
+           "\t          [-update_times 10 -alpha 0.1 -user_reg 0.01 -item_reg 0.01 -margin 8]\n"
+           "\tsmore tpr -train_ui ui.txt -train_iw iw.txt -save_user u.txt -save_item i.txt -save_word w.txt\n"
+           "\t          [-sample_times 10 -alpha 0.025 -lambda 0.025 -text_weight 0.5]\n\n"
            "Options Description:\n"
            "\t-train <string>\n\t\tTrain the Network data\n"
            "\t-save <string>\n\t\tSave the representation data\n"
@@ -95,6 +99,136 @@ void usage() {
            "\t-semantics <go|cpp> -mode <hogwild|deterministic> -seed <int> -dtype <f32|f64> -device <int>\n");
 }
 
+
+// CPR / TPR (Go tree only; cmd/cpr/main.go, cmd/tpr/main.go): two edge lists, three output files.
+int write_named_rows(const std::string& path, smore_graph_t names, const std::vector<double>& rows, int64_t n, int dim) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) {
+        fprintf(stderr, "smore: cannot write %s\n", path.c_str());
+        return 1;
+    }
+    fprintf(f, "%lld %d\n", (long long)n, dim);
+    for (int64_t v = 0; v < n; ++v) {
+        const char* nm = smore_graph_vertex_name(names, v);
+        fputs(nm ? nm : "", f);
+        for (int d = 0; d < dim; ++d) fprintf(f, " %.6f", rows[(size_t)v * dim + d]);
+        fputc('\n', f);
+    }
+    fclose(f);
+    return 0;
+}
+
+int run_two_graph(const std::string& model, Args& a) {
+    const bool cpr = model == "cpr";
+    const std::string f1 = a.str(cpr ? "train_target" : "train_ui", ""), f2 = a.str(cpr ? "train_source" : "train_iw", "");
+    const std::string s0 = a.str("save_user", ""), s1 = a.str(cpr ? "save_target" : "save_item", ""),
+                      s2 = a.str(cpr ? "save_source" : "save_word", "");
+    if (f1.empty() || f2.empty()) {
+        fprintf(stderr, cpr ? "smore: cpr needs -train_target and -train_source\n" : "smore: tpr needs -train_ui and -train_iw\n");
+        return 1;
+    }
+    if (a.str("semantics", "go") != "go") {
+        fprintf(stderr, "smore: %s exists only in the Go tree; use -semantics go\n", model.c_str());
+        return 1;
+    }
+    const int dim = (int)a.num("dimensions", 64);
+    const bool undirected = a.flag("undirected", true);
+    const int dtype = a.str("dtype", "f32") == "f64" ? SMORE_F64 : SMORE_F32;
+    if (smore_init((int)a.num("device", 0))) return die("init");
+    smore_graph_t g1 = nullptr, g2 = nullptr;
+    printf(cpr ? "Loading target domain...\n" : "Loading user-item graph...\n");
+    if (smore_graph_load_edge_list(f1.c_str(), undirected, SMORE_SEM_GO, SMORE_NEG_DEGREES, &g1)) return die("LoadEdgeList");
+    printf(cpr ? "Loading source domain...\n" : "Loading item-word graph...\n");
+    if (smore_graph_load_edge_list(f2.c_str(), undirected, SMORE_SEM_GO, SMORE_NEG_DEGREES, &g2)) return die("LoadEdgeList");
+    int64_t V1 = 0, E1 = 0, L1 = 0, V2 = 0, E2 = 0, L2 = 0;
+    smore_graph_info(g1, &V1, &E1, &L1);
+    smore_graph_info(g2, &V2, &E2, &L2);
+    std::vector<int64_t> off2((size_t)V2 + 1);
+    std::vector<int32_t> col2((size_t)std::max<int64_t>(E2, 1));
+    if (smore_graph_get_csr(g2, off2.data(), col2.data(), nullptr)) return die("second graph");
+
+    smore_train_params p;
+    smore_train_params_default(&p);
+    p.semantics = SMORE_SEM_GO;
+    p.mode = a.str("mode", "hogwild") == "deterministic" ? SMORE_MODE_DETERMINISTIC : SMORE_MODE_HOGWILD;
+    p.seed = (uint64_t)a.num("seed", 1);
+    if (cpr) {  // cmd/cpr/main.go:19-24
+        p.total = (uint64_t)a.num("update_times", 10) * 1000000ull;
+        p.alpha = a.real("alpha", 0.1);
+        p.lambda = a.real("user_reg", 0.01);
+        p.item_reg = a.real("item_reg", 0.01);
+        p.margin = a.real("margin", 8.0);
+    } else {  // cmd/tpr/main.go:19-22
+        p.total = (uint64_t)a.num("sample_times", 10) * (uint64_t)L1;
+        p.alpha = a.real("alpha", 0.025);
+        p.lambda = a.real("lambda", 0.025);
+        p.text_weight = a.real("text_weight", 0.5);
+    }
+    smore_model_t m = nullptr;
+    if (smore_model_create(g1, dim, 2, dtype, &m)) return die("Init");
+    if (smore_model_init(m, 0, 1, p.seed) || smore_model_init(m, 1, 1, p.seed)) return die("Init");
+    if (smore_model_attach_aux(m, V2, off2.data(), col2.data(), nullptr, p.seed)) return die("Init");
+    printf("Model Setting:\n\tdimension:\t\t%d\n", dim);
+    if (cpr) {
+        printf("\tmax_user_id:\t\t%lld\n\ttarget_items:\t\t%lld\n\tsource_items:\t\t%lld\n", (long long)std::max(V1, V2), (long long)V1, (long long)V2);
+        if (V2 > V1)
+            printf("\t(the reference also keeps %lld user rows past the target graph: never trained, unnamed, not written here)\n",
+                   (long long)(V2 - V1));
+        printf("Model:\n\t[CPR: Cross-Domain Preference Ranking]\nLearning Parameters:\n\tupdate_times:\t\t%ld\n\talpha:\t\t\t%.6f\n"
+               "\tuser_reg:\t\t%.6f\n\titem_reg:\t\t%.6f\n\tmargin:\t\t\t%.6f\n", a.num("update_times", 10), p.alpha, p.lambda, p.item_reg, p.margin);
+    } else {
+        printf("\ttext_weight:\t\t%.2f\n\tnum_users:\t\t%lld\n\tnum_items:\t\t%lld\n\tnum_words:\t\t%lld\n", p.text_weight, (long long)V1,
+               (long long)V1, (long long)V2);
+        printf("Model:\n\t[TPR: Text-aware Preference Ranking]\nLearning Parameters:\n\tsample_times:\t\t%ld\n\talpha:\t\t\t%.6f\n"
+               "\tlambda:\t\t\t%.6f\n", a.num("sample_times", 10), p.alpha, p.lambda);
+    }
+    if (a.has("threads")) printf("\tworkers:\t\t-threads %ld ignored: workers are GPU warps\n", a.num("threads", 1));
+    printf("Start Training:\n");
+    std::atomic<bool> stop{false};
+    std::thread poll([&] {
+        while (!stop.load(std::memory_order_acquire)) {
+            uint64_t done = 0, total = 0;
+            double alpha = 0;
+            int running = 0;
+            if (smore_progress(m, &done, &total, &alpha, &running) == 0 && running && total) {
+                printf("\tAlpha: %.6f\tProgress: %.3f %%%c", alpha, 100.0 * (double)done / (double)total, 13);
+                fflush(stdout);
+            }
+            std::this_thread::sleep_for(std::chrono::milliseconds(100));
+        }
+    });
+    const int rc = cpr ? smore_train_cpr(m, &p) : smore_train_tpr(m, &p);
+    stop.store(true, std::memory_order_release);
+    poll.join();
+    if (rc) return die("Train");
+    uint64_t samples = 0, pairs = 0;
+    double ms = 0, alpha_end = 0;
+    smore_train_stats(m, &samples, &pairs, nullptr, nullptr, &ms);
+    smore_progress(m, nullptr, nullptr, &alpha_end, nullptr);
+    printf("\tAlpha: %.6f\tProgress: 100.00 %%\n", alpha_end);
+    printf("\t%llu samples, %llu updates in %.1f ms on the device (%.1f M samples/s)\n", (unsigned long long)samples,
+           (unsigned long long)pairs, ms, ms > 0 ? samples / ms / 1e3 : 0.0);
+    printf("Save Model:\n");
+    if (!s0.empty()) {
+        if (smore_model_save_weights(m, 0, s0.c_str(), 1)) return die("SaveWeights");
+        printf("\tSave users to <%s>\n", s0.c_str());
+    }
+    if (!s1.empty()) {
+        if (smore_model_save_weights(m, 1, s1.c_str(), 1)) return die("SaveWeights");
+        printf("\tSave %s to <%s>\n", cpr ? "target items" : "items", s1.c_str());
+    }
+    if (!s2.empty()) {
+        std::vector<double> rows((size_t)V2 * (size_t)dim);
+        if (smore_model_get_aux_rows(m, 0, V2, rows.data())) return die("SaveWeights");
+        if (write_named_rows(s2, g2, rows, V2, dim)) return 1;
+        printf("\tSave %s to <%s>\n", cpr ? "source items" : "words", s2.c_str());
+    }
+    smore_model_destroy(m);
+    smore_graph_destroy(g1);
+    smore_graph_destroy(g2);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -102,7 +236,7 @@ int main(int argc, char** argv) {
     int first = 1;
     const char* base = strrchr(argv[0], '/');
     base = base ? base + 1 : argv[0];
-    for (const char* m : {"line", "deepwalk", "walklets", "node2vec", "bpr", "warp", "hoprec", "hpe", "mf", "skewopt"})
+    for (const char* m : {"line", "deepwalk", "walklets", "node2vec", "bpr", "warp", "hoprec", "hpe", "mf", "skewopt", "cpr", "tpr"})
         if (!strcmp(base, m)) model = m;
     if (model.empty()) {
         if (argc < 2 || argv[1][0] == '-') {
@@ -117,6 +251,7 @@ int main(int argc, char** argv) {
         return 0;
     }
     Args a = parse(argc, argv, first);
+    if (model == "cpr" || model == "tpr") return run_two_graph(model, a);
     const bool has_go_cli = model == "line" || model == "deepwalk" || model == "bpr" || model == "node2vec";
     if (!has_go_cli && model != "walklets" && model != "warp" && model != "hoprec" && model != "hpe" && model != "mf" && model != "skewopt") {
         fprintf(stderr, "smore: unknown model '%s'\n", model.c_str());

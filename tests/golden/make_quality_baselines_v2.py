@@ -144,6 +144,28 @@ def main():
         a = (np.random.default_rng(1).random((V2, DIM)) - 0.5) / DIM
         gh.train_hoprec_cpp(a, 3, 0.025, 1_000_000, SEED, 0)
         record("hoprec", t0, total=1_000_000, walk_steps=3, alpha=0.025, auc=Q.evaluate_bipartite(a, a, tu2, ti2, is_item2))
+    # ---- the Go tree's two-graph models (CPR, TPR) on the planted-preference problem + a second graph ----
+    for kind in ("cpr", "tpr"):
+        if not want(kind):
+            continue
+        off, col, ww, tu, ti, is_item, aoff, acol = Q.two_graph_problem(kind)
+        V, Va = len(off) - 1, len(aoff) - 1
+        g1 = B.OracleGraph(B.SEM_GO, off, col, ww, max_line=len(col) // 2)
+        g2 = B.OracleGraph(B.SEM_GO, aoff, acol, np.ones(len(acol)), max_line=len(acol))
+        U = (np.random.default_rng(1).random((V, DIM)) - 0.5) / DIM
+        I = (np.random.default_rng(3).random((V, DIM)) - 0.5) / DIM
+        A = (np.random.default_rng(5).random((Va, DIM)) - 0.5) / DIM
+        t0 = time.time()
+        if kind == "cpr":  # cmd/cpr/main.go defaults: alpha 0.1, regs 0.01, margin 8
+            total = 3_000_000
+            g1.train_cpr_go(g2, U, I, A, 0.1, 0.01, 0.01, 8.0, total, total, SEED, 0)
+            record(kind, t0, total=total, alpha=0.1, user_reg=0.01, item_reg=0.01, margin=8.0,
+                   auc=Q.evaluate_two_graph(kind, U, I, A, off, col, aoff, acol, tu, ti, is_item))
+        else:  # cmd/tpr/main.go defaults: alpha 0.025, lambda 0.025, text_weight 0.5
+            total = 4_000_000
+            g1.train_tpr_go(g2, U, I, A, 0.025, 0.025, 0.5, total, total, SEED, 0)
+            record(kind, t0, total=total, alpha=0.025, lam=0.025, text_weight=0.5,
+                   auc=Q.evaluate_two_graph(kind, U, I, A, off, col, aoff, acol, tu, ti, is_item))
     # ---- the bench instantiation (dim 128) on a graph large enough for every resident warp (80 000 table rows) ----
     if want("line_cpp_d128_40k"):
         off, col, ww, ts, td = Q.sbm_problem(n_comm=500, comm_size=80, deg=24, seed=31)

@@ -33,7 +33,7 @@ def sbm_problem(n_comm=150, comm_size=80, deg=24, seed=5):
     return off, col, ww, lab2id[hs[ok]], lab2id[hd[ok]]
 
 
-def bipartite_problem(n_comm=100, users_per=40, items_per=20, deg=20, p_in=0.8, seed=11, undirected=False):
+def bipartite_problem(n_comm=100, users_per=40, items_per=20, deg=20, p_in=0.8, seed=11, undirected=False, with_labels=False):
     """Planted preferences: the users of community c pick items of community c with probability p_in, any item otherwise.
     -> (row_off, col, w, test_user, test_item, is_item[V], field[V]) in vertex ids; 10 % of the interactions held out."""
     rng = np.random.default_rng(seed)
@@ -51,7 +51,59 @@ def bipartite_problem(n_comm=100, users_per=40, items_per=20, deg=20, p_in=0.8, 
     lab2id[labels] = np.arange(len(labels))
     ok = (lab2id[hs] >= 0) & (lab2id[hd] >= 0)
     is_item = labels >= nu
+    if with_labels:
+        return off, col, ww, lab2id[hs[ok]], lab2id[hd[ok]], is_item, is_item.astype(np.int32), labels
     return off, col, ww, lab2id[hs[ok]], lab2id[hd[ok]], is_item, is_item.astype(np.int32)
+
+
+def two_graph_problem(kind, n_comm=100, users_per=40, items_per=20, seed=11):
+    """The planted-preference problem (undirected, as cmd/cpr and cmd/tpr load it) plus the SECOND graph of the Go tree's
+    two-graph models, as bare adjacency over vids that extend the first graph's (shared entities keep their vids, which is
+    what cpr.go:148-169 / tpr.go:108 rely on):
+      "cpr": every user also has 6 source-domain items, 80 % from its community's 15 (aux vids V ..);
+      "tpr": every item lists 4 words, 3 of its community's 5 topic words and 1 random word (aux vids V ..).
+    -> (off, col, w, test_user, test_item, is_item, aux_off, aux_col)."""
+    off, col, ww, tu, ti, is_item, _, labels = bipartite_problem(n_comm, users_per, items_per, seed=seed, undirected=True,
+                                                                 with_labels=True)
+    rng = np.random.default_rng(seed + 7)
+    V, nu = len(labels), n_comm * users_per
+    lists = [[] for _ in range(V)]
+    if kind == "cpr":
+        per, n_aux = 15, n_comm * 15
+        for v in np.flatnonzero(~is_item):
+            c = labels[v] // users_per
+            inside = rng.random(6) < 0.8
+            lists[v] = (V + np.where(inside, c * per + rng.integers(0, per, 6), rng.integers(0, n_aux, 6))).tolist()
+    else:
+        per, n_aux = 5, n_comm * 5
+        for v in np.flatnonzero(is_item):
+            c = (labels[v] - nu) // items_per
+            lists[v] = (V + np.concatenate([c * per + rng.choice(per, 3, replace=False), rng.integers(0, n_aux, 1)])).tolist()
+    aux_off = np.zeros(V + n_aux + 1, dtype=np.int64)
+    aux_off[1:V + 1] = np.cumsum([len(x) for x in lists])
+    aux_off[V + 1:] = aux_off[V]
+    aux_col = np.array([x for lst in lists for x in lst], dtype=np.int32)
+    return off, col, ww, tu, ti, is_item, aux_off, aux_col
+
+
+def evaluate_two_graph(kind, U, I, A, off, col, aux_off, aux_col, test_u, test_i, is_item, text_weight=0.5, seed=2):
+    """Held-out AUC under each model's own score: CPR ranks items by transformUser(u) . item (cpr.go:127-172, :225-229),
+    TPR by user . text-enriched item (tpr.go:101-121, :186-190)."""
+    U, I, A = (np.asarray(x, dtype=np.float64) for x in (U, I, A))
+    V = len(off) - 1
+
+    def row_sums(table, o, c, n_rows):
+        out = np.zeros((n_rows, table.shape[1]))
+        np.add.at(out, np.repeat(np.arange(n_rows), np.diff(o[:n_rows + 1])), table[c[:o[n_rows]]])
+        return out
+
+    if kind == "cpr":
+        cnt = 1.0 + np.diff(off) + np.diff(aux_off[:V + 1])
+        users = (U + row_sums(I, off, col, V) + row_sums(A, aux_off, aux_col, V)) / cnt[:, None]
+        return evaluate_bipartite(users, I, test_u, test_i, is_item, seed)
+    nw = np.diff(aux_off[:V + 1])
+    enriched = np.where(nw[:, None] > 0, (1.0 - text_weight) * I + text_weight * row_sums(A, aux_off, aux_col, V) / np.maximum(nw, 1)[:, None], I)
+    return evaluate_bipartite(U, enriched, test_u, test_i, is_item, seed)
 
 
 def auc(pos, neg):

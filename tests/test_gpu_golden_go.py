@@ -197,7 +197,8 @@ def test_cpr_tpr_fp32_and_hogwild(model):
     for got, init in ((h.get_rows(0), t0), (h.get_rows(1), t1)):
         assert np.isfinite(got).all() and not np.array_equal(got, init)
     aux = h.get_aux_rows()
-    assert np.isfinite(aux).all() and (np.array_equal(aux, t2) if model == "cpr" else not np.array_equal(aux, t2))
+    t2f = t2.astype(np.float32).astype(np.float64)  # (CPR only reads its third table)
+    assert np.isfinite(aux).all() and (np.array_equal(aux, t2f) if model == "cpr" else not np.array_equal(aux, t2f))
     # random third table when no rows are given; C++ semantics have neither model
     h.attach_aux(*_aux_csr(GA[f"{b}_src"], GA[f"{b}_dst"], GA[f"{b}_w"], und_b), rows=None, seed=5)
     r = h.get_aux_rows()
@@ -207,3 +208,36 @@ def test_cpr_tpr_fp32_and_hogwild(model):
     mc.attach_aux(*_aux_csr(GA[f"{b}_src"], GA[f"{b}_dst"], GA[f"{b}_w"], und_b))
     with pytest.raises(capi.SmoreError):
         (mc.train_cpr if model == "cpr" else mc.train_tpr)(capi.default_params())
+
+
+def test_cpr_and_tpr_cli(tmp_path):
+    """cmd/cpr/main.go and cmd/tpr/main.go: two edge lists in, three "%.6f" files out, rows named by the graph they belong to."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t, s = str(tmp_path / "t.txt"), str(tmp_path / "s.txt")
+    B.write_edge_list(t, GA["cpr_t_src"], GA["cpr_t_dst"], GA["cpr_t_w"])
+    B.write_edge_list(s, GA["cpr_s_src"], GA["cpr_s_dst"], GA["cpr_s_w"])
+    outs = [str(tmp_path / f"{k}.rep") for k in ("user", "target", "source")]
+    r = subprocess.run([os.path.join(root, "smore_b200", "bin", "cpr"), "-train_target", t, "-train_source", s, "-save_user", outs[0],
+                        "-save_target", outs[1], "-save_source", outs[2], "-dimensions", "16", "-update_times", "1", "-threads", "2"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "[CPR: Cross-Domain Preference Ranking]" in r.stdout and "Progress: 100.00 %" in r.stdout
+    Vt, Vs = GA["cpr_init_t"].shape[0], GA["cpr_init_s"].shape[0]
+    for path, rows in zip(outs, (Vt, Vt, Vs)):
+        lines = open(path).read().split("\n")
+        assert lines[0] == f"{rows} 16" and len(lines) == rows + 2
+        assert len(lines[1].split(" ")) == 17 and len(lines[1].split(" ")[1].split(".")[1]) == 6
+    assert open(outs[0]).read().split("\n")[1].split(" ")[0] == f"v{GA['cpr_t_src'][0]}"  # first name of the target graph
+    assert open(outs[2]).read().split("\n")[2].split(" ")[0] == f"v{GA['cpr_s_dst'][0]}"  # second name of the source graph
+    ui, iw = str(tmp_path / "ui.txt"), str(tmp_path / "iw.txt")
+    B.write_edge_list(ui, GA["tpr_ui_src"], GA["tpr_ui_dst"], GA["tpr_ui_w"])
+    B.write_edge_list(iw, GA["tpr_iw_src"], GA["tpr_iw_dst"], GA["tpr_iw_w"])
+    outs = [str(tmp_path / f"{k}.rep") for k in ("u", "i", "w")]
+    r = subprocess.run([os.path.join(root, "smore_b200", "bin", "tpr"), "-train_ui", ui, "-train_iw", iw, "-save_user", outs[0],
+                        "-save_item", outs[1], "-save_word", outs[2], "-dimensions", "16", "-sample_times", "20"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "[TPR: Text-aware Preference Ranking]" in r.stdout
+    assert open(outs[2]).read().split("\n")[0] == f"{GA['tpr_init_w'].shape[0]} 16"
+    r = subprocess.run([os.path.join(root, "smore_b200", "bin", "tpr"), "-train_ui", ui, "-save_user", outs[0]], capture_output=True, text=True)
+    assert r.returncode != 0 and "-train_iw" in r.stderr

@@ -75,7 +75,7 @@ def test_progress_of_a_chunk_of_a_longer_schedule_and_of_walks():
     q.mode, q.seed, q.walk_times, q.walk_steps, q.window_min, q.window_max = capi.MODE_HOGWILD, 3, 2, 10, 1, 3
     st = m.train_deepwalk(q)
     end = m.live_progress()
-    assert end["total"] == 2 * 20_000 and end["done"] == st["samples"] == 2 * 20_000  # units: walks
+    assert end["total"] == end["done"] == st["samples"] and 39_000 < end["total"] <= 40_000  # units: walks (walk_times x V)
 
 
 def test_cli_prints_the_reference_progress_line(tmp_path):

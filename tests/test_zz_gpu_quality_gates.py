@@ -218,6 +218,35 @@ def test_bpr_go():
     check("BPR Go", Q.evaluate_bipartite(m.get_rows(0), m.get_rows(1), tu, ti, is_item), ref["auc"])
 
 
+@pytest.mark.parametrize("kind", ["cpr", "tpr"])
+def test_two_graph_models(kind):
+    """CPR / TPR (Go tree only): Hogwild fp32 at the library's occupancy against the one-stream reference path, each under
+    its own score (transformed user . item / user . text-enriched item), cmd/cpr and cmd/tpr default parameters."""
+    off, col, ww, tu, ti, is_item, aoff, acol = Q.two_graph_problem(kind)
+    V, Va, ref = len(off) - 1, len(aoff) - 1, Q2["models"][kind]
+    U0 = (np.random.default_rng(1).random((V, DIM)) - 0.5) / DIM
+    I0 = (np.random.default_rng(3).random((V, DIM)) - 0.5) / DIM
+    A0 = (np.random.default_rng(5).random((Va, DIM)) - 0.5) / DIM
+    g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_GO, n_lines=len(col) // 2)
+
+    def run(seed):
+        m = capi.Model(g, DIM, 2, capi.F32)
+        m.set_rows(0, U0), m.set_rows(1, I0)
+        m.attach_aux(aoff, acol, rows=A0)
+        if kind == "cpr":
+            p = hogwild(capi.SEM_GO, seed=seed, total=ref["total"], lambda_=ref["user_reg"], item_reg=ref["item_reg"], margin=ref["margin"])
+            p.alpha = ref["alpha"]
+            st = m.train_cpr(p)
+        else:
+            p = hogwild(capi.SEM_GO, seed=seed, total=ref["total"], lambda_=ref["lam"], text_weight=ref["text_weight"])
+            p.alpha = ref["alpha"]
+            st = m.train_tpr(p)
+        assert st["samples"] > 0.99 * ref["total"]
+        return Q.evaluate_two_graph(kind, m.get_rows(0), m.get_rows(1), m.get_aux_rows(), off, col, aoff, acol, tu, ti, is_item)
+
+    check(kind.upper(), float(mean_of(run)), ref["auc"])
+
+
 @pytest.mark.parametrize("name", ["bpr_cpp", "warp"])
 def test_cpp_ranking(name):
     off, col, ww, tu, ti, is_item, _ = bip()
