@@ -42,6 +42,48 @@ def run(name, model, fn, p, bytes_per_unit, unit_key, steps, warmup):
                       "mean_tries": tries}), flush=True)
 
 
+def device_bipartite_csr(nu, ni, ne, seed, zipf_s, undirected):
+    """configs[3]-sized bipartite CSR built with torch ON THE GPU (the numpy generator + first-appearance relabelling of
+    smore_b200/synth.py needs ~10 minutes of host sorting at 500 M interactions): users uniform, items Zipf(s) over a random
+    permutation, integer weights 1..5; vids are the labels themselves (users [0, nu), items [nu, nu + ni)), entries of a row
+    in generation order. -> (row_off int64, col int32, w float64, field int32) as numpy arrays."""
+    import torch
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    cdf = torch.cumsum(torch.arange(1, ni + 1, device=dev, dtype=torch.float64) ** (-zipf_s), 0)
+    cdf /= cdf[-1].clone()
+    perm = torch.randperm(ni, device=dev, generator=gen)
+    chunks_u, chunks_i, chunks_w = [], [], []
+    step = 1 << 26
+    for lo in range(0, ne, step):
+        n = min(step, ne - lo)
+        chunks_u.append(torch.randint(0, nu, (n,), device=dev, generator=gen, dtype=torch.int32))
+        r = torch.rand(n, device=dev, generator=gen, dtype=torch.float64)
+        chunks_i.append((nu + perm[torch.searchsorted(cdf, r, right=True).clamp_(max=ni - 1)]).to(torch.int32))
+        chunks_w.append(torch.randint(1, 6, (n,), device=dev, generator=gen, dtype=torch.int8))
+    u, it, w = torch.cat(chunks_u), torch.cat(chunks_i), torch.cat(chunks_w)
+    del chunks_u, chunks_i, chunks_w
+    if undirected:
+        es, ed, w = torch.cat([u, it]), torch.cat([it, u]), torch.cat([w, w])
+    else:
+        es, ed = u, it
+    del u, it
+    V = nu + ni
+    es_sorted, order = torch.sort(es, stable=True)
+    del es
+    col = ed[order].cpu().numpy()
+    ww = w[order].to(torch.float64).cpu().numpy()
+    del ed, w, order
+    off = torch.zeros(V + 1, dtype=torch.int64, device=dev)
+    off[1:] = torch.cumsum(torch.bincount(es_sorted.to(torch.int64), minlength=V), 0)
+    off = off.cpu().numpy()
+    del es_sorted
+    torch.cuda.empty_cache()
+    field = (np.arange(V) >= nu).astype(np.int32)
+    return off, col, ww, field
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
@@ -49,6 +91,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--only", default="")
     ap.add_argument("--zipf", type=float, default=1.0, help="item popularity exponent of the bipartite graphs")
+    ap.add_argument("--c4-full", action="store_true",
+                    help="BASELINE.json configs[3] at its named size: 10 M users x 2 M items, 500 M interactions (WARP, C++ BPR "
+                         "directed: 500 M CSR entries; HOP-Rec undirected: 1 B), generated on the GPU")
     a = ap.parse_args()
     only = set(a.only.split(",")) if a.only else None
 
@@ -77,6 +122,41 @@ def main():
                 p = capi.default_params()
                 p.semantics, p.mode, p.seed, p.total = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 1 << 24
                 run(f"bpr_cpp_d{dim}_c1", m, m.train_bpr, p, 14 * dim * 4 + 60, "samples", a.steps, a.warmup)
+
+    # ---- configs[3] at the named size ----
+    if a.c4_full:
+        nu, ni, ne, dim = 10_000_000, 2_000_000, 500_000_000, 128
+        for und, names in ((False, ("bpr_cpp", "warp")), (True, ("hoprec",))):
+            if not any(want(n) for n in names):
+                continue
+            t0 = time.time()
+            off, col, ww, field = device_bipartite_csr(nu, ni, ne, 9, a.zipf, und)
+            t1 = time.time()
+            g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_CPP, negative_method=capi.NEG_NO_DEGREES)
+            print(json.dumps({"graph": "configs[3]", "undirected": und, "V": nu + ni, "csr_entries": int(len(col)),
+                              "generate_s": round(t1 - t0, 1), "alias_build_and_upload_s": round(time.time() - t1, 1)}), flush=True)
+            del off, col, ww
+            if und:
+                g.set_field(field)
+            for nm in names:
+                if not want(nm):
+                    continue
+                m = capi.Model(g, dim, 1, capi.F32)
+                m.init(0, True, 1)
+                p = capi.default_params()
+                p.semantics, p.mode, p.seed = capi.SEM_CPP, capi.MODE_HOGWILD, 1
+                if nm == "bpr_cpp":
+                    p.total = 1 << 24
+                    run("bpr_cpp_d128_c4", m, m.train_bpr, p, 14 * dim * 4 + 60, "samples", a.steps, a.warmup)
+                elif nm == "warp":
+                    p.total = 1 << 24
+                    run("warp_d128_c4", m, m.train_warp, p, lambda tr: (2 + tr) * dim * 4 + 3 * dim * 4 + 40, "samples", a.steps, a.warmup)
+                else:
+                    p.total, p.walk_steps = 1 << 22, 5
+                    run("hoprec_d128_c4", m, m.train_hoprec, p, 5 * 14 * dim * 4, "samples", a.steps, a.warmup)
+                del m
+            del g
+        return
 
     # ---- a large bipartite graph (configs[3] scaled): BPR at dim 128 out of L2, WARP, HOP-Rec ----
     if want("bpr_go_big") or want("warp") or want("hoprec") or want("bpr_cpp_big") or want("mf") or want("skewopt"):
@@ -137,6 +217,40 @@ def main():
             p.semantics, p.mode, p.seed, p.total, p.walk_steps = capi.SEM_CPP, capi.MODE_HOGWILD, 1, 1 << 22, 5
             # per hop: user + item + 5 negatives read, up to all 7 written: counted per FBPR round-group ("pair_updates"/5)
             run(f"hoprec_d{dim}_big", m, m.train_hoprec, p, 5 * 14 * dim * 4, "samples", a.steps, a.warmup)
+
+    # ---- the Go tree's two-graph models on a planted-preference graph (200 k users x 100 k items, 3.6 M interactions,
+    #      undirected as cmd/cpr / cmd/tpr load it) + their second graph; dim 128 ----
+    if want("cpr") or want("tpr"):
+        sys.path.insert(0, ROOT)
+        from tests import quality as Q
+        for kind in ("cpr", "tpr"):
+            if not want(kind):
+                continue
+            off, col, ww, _, _, _, aoff, acol = Q.two_graph_problem(kind, n_comm=int(5000 * a.scale))
+            V = len(off) - 1
+            g = capi.Graph.from_csr(off, col, ww, semantics=capi.SEM_GO, n_lines=len(col) // 2)
+            m = capi.Model(g, 128, 2, capi.F32)
+            m.init(0, True, 1), m.init(1, True, 2)
+            m.attach_aux(aoff, acol, rows=None, seed=3)
+            p = capi.default_params()
+            p.semantics, p.mode, p.seed, p.total = capi.SEM_GO, capi.MODE_HOGWILD, 1, 1 << 22
+            d1 = np.diff(off).astype(np.float64)
+            d2 = np.diff(aoff[:V + 1]).astype(np.float64)
+            if kind == "cpr":
+                # rows per sample: user + pos + neg read and written, + the user's neighbours in both graphs read;
+                # users are drawn ~ out-degree, so E[neighbours] = sum d1 (d1 + d2) / sum d1
+                p.alpha, p.lambda_, p.item_reg, p.margin = 0.1, 0.01, 0.01, 8.0
+                rows = 6 + float((d1 * (d1 + d2)).sum() / d1.sum())
+                run(f"cpr_d128", m, m.train_cpr, p, rows * 128 * 4 + 40, "samples", a.steps, a.warmup)
+            else:
+                # user + 2 items read and written; each item's words read for the enriched vector, read again and written
+                # by the update: positives ~ in-degree given a degree-drawn user (~ d1), negatives ~ d1^0.75
+                p.alpha, p.lambda_, p.text_weight = 0.025, 0.025, 0.5
+                pos_w = float((d1 * d2).sum() / d1.sum())
+                neg_w = float((d1 ** 0.75 * d2).sum() / (d1 ** 0.75).sum())
+                rows = 6 + 3 * (pos_w + neg_w)
+                run(f"tpr_d128", m, m.train_tpr, p, rows * 128 * 4 + 40, "samples", a.steps, a.warmup)
+            del m, g
 
     # ---- configs[1] under Go semantics (CDF-scan neighbour sampling -> binary search over prefix sums, random contexts) ----
     if want("line_go") or want("line_cpp") or want("hpe"):
