@@ -252,6 +252,112 @@ __global__ void __launch_bounds__(kBlockThreads) k_warp(TrainArgs<typename C::T>
     if (lane == 0) a.state[w] = st;
 }
 
+// WARP, fp32 Hogwild throughput path. k_warp above follows the reference's draw order word for word, which makes one
+// sample a chain of ~13 dependent memory round trips (alias entry -> CSR record -> context alias -> neighbour id -> two
+// rows -> per batch of 4 candidates: alias entries -> rows): 0.61 of the HBM roofline. Hogwild runs are compared with the
+// reference statistically, not word for word, so this kernel gives every sample a FIXED 68-word slice of its warp's stream
+// (source 2, target 2, 32 candidates x 2; nothing lives in a shared-memory ring, every lane computes the Philox block it
+// needs) and reorganises the chain:
+//   * the (user, item) pairs of 8 consecutive samples are drawn by 8 lanes at once;
+//   * all 32 candidate negatives of a sample are looked up at once, one lane each, together with the user and item rows;
+//   * candidate rows are gathered four at a time, the next four already in flight while the current four are scored.
+// Same update as k_warp's atomic path: the first candidate with f < 1 triggers one BPR step on three rows (red.global.add).
+constexpr int kWarpGroup = 8;
+constexpr int kWarpWords = 68;  // words of its stream a sample owns (a multiple of 4: slices start on Philox blocks)
+
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_warp_fast(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    const GraphDev& g = a.g;
+    const int dim = a.dim;
+    T* W = a.Wv;
+    const uint64_t stream = a.stream_base + (uint64_t)w;
+    const uint64_t s_base = (st.pos + kWarpWords - 1) / kWarpWords;  // samples this stream has already served
+    for (uint64_t it0 = 0; it0 < a.jobs; it0 += kWarpGroup) {
+        const int ng = (int)min((uint64_t)kWarpGroup, a.jobs - it0);
+        int64_t mu = -1, mi = -1;
+        if (lane < ng) {
+            const U4 r = philox_block(a.seed, stream, (uint64_t)(kWarpWords / 4) * (s_base + it0 + (uint64_t)lane));
+            mu = (int64_t)source_sample(g, r.x, r.y);
+            int used;
+            mi = target_sample(g, mu, r.z, r.w, used);
+        }
+        for (int k = 0; k < ng; ++k) {
+            const int64_t v1 = __shfl_sync(kFull, mu, k);
+            const int64_t v2 = __shfl_sync(kFull, mi, k);
+            if (v2 < 0) continue;
+            T* pv = W + v1 * dim;
+            T* pi = W + v2 * dim;
+            Row<C> v, ri;
+            v.load_ca(pv, lane, dim);
+            ri.load_ca(pi, lane, dim);
+            // candidate `lane`: words 4 + 2*lane, 5 + 2*lane of the sample's slice
+            const U4 r = philox_block(a.seed, stream, (uint64_t)(kWarpWords / 4) * (s_base + it0 + (uint64_t)k) + 1u + (uint64_t)(lane >> 1));
+            const int64_t cand = (int64_t)negative_sample(g, (lane & 1) ? r.z : r.x, (lane & 1) ? r.w : r.y);
+            const T alpha = (T)st.alpha;
+            Row<C> bufA[kWarpBatch], bufB[kWarpBatch];
+            auto gather = [&](Row<C>(&rows)[kWarpBatch], int base) {
+#pragma unroll
+                for (int q = 0; q < kWarpBatch; ++q) rows[q].load_ca(W + __shfl_sync(kFull, cand, base + q) * dim, lane, dim);
+            };
+            int scanned = 0;
+            bool hit = false;
+            auto score = [&](Row<C>(&rows)[kWarpBatch], int base) {
+                T f[kWarpBatch];
+#pragma unroll
+                for (int q = 0; q < kWarpBatch; ++q) {
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) rows[q].x[e] = A::sub(ri.x[e], rows[q].x[e]);  // item - candidate
+                }
+                dots<C, kWarpBatch>(v, rows, kWarpBatch, f);
+#pragma unroll
+                for (int q = 0; q < kWarpBatch; ++q) {
+                    if (hit) continue;
+                    ++scanned;
+                    if (f[q] < (T)1) {
+                        hit = true;
+                        T* pj = W + __shfl_sync(kFull, cand, base + q) * dim;
+                        const T c = A::mul(alpha, (T)0.0025);
+                        const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f[q])), alpha);
+#pragma unroll
+                        for (int e = 0; e < C::EPL; ++e) {
+                            const T verr = A::mul(gg, rows[q].x[e]);
+                            const T cerr = A::mul(gg, v.x[e]);
+                            const T rje = A::sub(ri.x[e], rows[q].x[e]);
+                            rows[q].x[e] = A::sub(A::mul(-c, rje), cerr);
+                            ri.x[e] = A::msub(cerr, c, ri.x[e]);
+                            v.x[e] = A::msub(verr, c, v.x[e]);
+                        }
+                        row_red_add<C>(pi, ri, lane, dim);
+                        row_red_add<C>(pj, rows[q], lane, dim);
+                        row_red_add<C>(pv, v, lane, dim);
+                    }
+                }
+            };
+            gather(bufA, 0);
+            for (int base = 0; base < 32 && !hit; base += 2 * kWarpBatch) {
+                gather(bufB, base + kWarpBatch);  // in flight while bufA is scored
+                score(bufA, base);
+                if (hit) break;
+                if (base + 2 * kWarpBatch < 32) gather(bufA, base + 2 * kWarpBatch);
+                score(bufB, base + kWarpBatch);
+            }
+            st.count++;
+            st.pairs++;
+            st.tries += (uint64_t)scanned;
+            sched_tick(st, a.sched);
+        }
+    }
+    st.pos = (s_base + a.jobs) * kWarpWords;
+    if (lane == 0) a.state[w] = st;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // HOP-Rec: HBPR::Train (src/model/HBPR.cpp:93-126) + UpdateFBPRPair (src/proNet.cpp:1458-1515).
 // Per sampled user: for hop w = 1..walk_steps: item at hop w, field-matched negative, 5 margin-gated BPR rounds

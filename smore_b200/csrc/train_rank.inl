@@ -9,7 +9,14 @@ int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind) {
         void (*kern)(TrainArgs<T>) = kind == RANK_WARP ? k_warp<C> : kind == RANK_HOPREC ? k_hoprec<C> : kind == RANK_SKEWOPT ? k_skewopt<C>
                                      : kind == RANK_CPR ? k_cpr<C> : kind == RANK_TPR ? k_tpr<C>
                                      : cpp ? k_bpr_cpp<C> : k_bpr_go<C>;
-        const size_t smem = kind == RANK_SKEWOPT ? batch_smem_bytes<T>(0, kSbprRounds)
+        bool warp_fast = false;
+        if constexpr (sizeof(T) == 4) {  // WARP, fp32 Hogwild: the restructured kernel (ranking_kernels.cuh, k_warp_fast)
+            if (kind == RANK_WARP && p->mode != SMORE_MODE_DETERMINISTIC && !getenv("SMORE_WARP_EXACT_STREAM")) {
+                kern = k_warp_fast<C>;
+                warp_fast = true;
+            }
+        }
+        const size_t smem = warp_fast ? 1008 * sizeof(T) : kind == RANK_SKEWOPT ? batch_smem_bytes<T>(0, kSbprRounds)
                             : kind != RANK_BPR ? smem_line<T>() : cpp ? batch_smem_bytes<T>(0, 5) : batch_smem_bytes<T>(1, 1);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
