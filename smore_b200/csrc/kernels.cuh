@@ -923,6 +923,92 @@ __global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_hpe(Tra
     if (lane == 0) a.state[w] = st;
 }
 
+// HPE, fp32 Hogwild throughput path. k_hpe above consumes its stream word for word like the reference worker, which chains
+// ~24 dependent memory round trips per sample (source, target, then per step: the next context, K alias entries, the rows).
+// None of HPE's draws depends on an embedding, so under Hogwild -- compared with the reference statistically, not word for
+// word -- every sample gets a FIXED slice of its warp's stream and the chain is reorganised:
+//   * 8 lanes draw 8 consecutive samples at once, each walking its own context chain (source, target, steps - 1 more hops);
+//   * the (steps + 1) * K negatives of a sample are looked up at once, one lane each (needs (steps + 1) * K <= 32);
+//   * the update steps then run back to back with every id already in registers.
+// Slice layout (words): [0,4) source + target, [4, 4 + 2 (steps - 1)) the further hops, then from the next multiple of 4 on
+// two words per negative: step 0's K, step 1's K, ..., the final UpdatePair's K.
+constexpr int kHpeGroup = 8;
+constexpr int kHpeMaxSteps = 6;
+__host__ __device__ constexpr int hpe_neg_offset(int steps) { return (4 + 2 * (steps - 1) + 3) & ~3; }
+__host__ __device__ constexpr int hpe_slice_words(int steps, int K) { return (hpe_neg_offset(steps) + 2 * (steps + 1) * K + 3) & ~3; }
+
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_hpe_fast(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
+    const DirectView<T> tv{a.Wv, a.dim}, tc{a.Wc, a.dim};
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    const GraphDev& g = a.g;
+    const int K = a.K, nrows = a.K + 1, steps = a.steps;
+    const uint64_t stream = a.stream_base + (uint64_t)w;
+    const uint64_t slice = (uint64_t)hpe_slice_words(steps, K);
+    const uint64_t s_base = (st.pos + slice - 1) / slice;  // samples this stream has already served
+    const uint32_t neg_blk0 = (uint32_t)hpe_neg_offset(steps) >> 2;
+    for (uint64_t it0 = 0; it0 < a.jobs; it0 += kHpeGroup) {
+        const int ng = (int)min((uint64_t)kHpeGroup, a.jobs - it0);
+        int m1 = -1, mc[kHpeMaxSteps];
+#pragma unroll
+        for (int s = 0; s < kHpeMaxSteps; ++s) mc[s] = -1;
+        if (lane < ng) {
+            const uint64_t blk = (slice >> 2) * (s_base + it0 + (uint64_t)lane);
+            U4 r = philox_block(a.seed, stream, blk);
+            m1 = (int)source_sample(g, r.x, r.y);
+            int used;
+            int64_t ctx = target_sample(g, (int64_t)m1, r.z, r.w, used);
+            mc[0] = (int)ctx;
+#pragma unroll
+            for (int s = 1; s < kHpeMaxSteps; ++s) {
+                if (s < steps && ctx >= 0) {  // (a sink ends the walk: proNet.cpp:3033)
+                    if (s & 1) r = philox_block(a.seed, stream, blk + 1u + (uint32_t)((s - 1) >> 1));
+                    ctx = target_sample(g, ctx, (s & 1) ? r.x : r.z, (s & 1) ? r.y : r.w, used);
+                    mc[s] = (int)ctx;
+                }
+            }
+        }
+        for (int k = 0; k < ng; ++k) {
+            const int v1 = __shfl_sync(kFull, m1, k);
+            int cdist = -1;  // lane s: the context of step s (runtime-indexed by shuffle: one copy of the update code)
+#pragma unroll
+            for (int s = 0; s < kHpeMaxSteps; ++s) {
+                const int c = __shfl_sync(kFull, mc[s], k);
+                if (lane == s) cdist = c;
+            }
+            const int v2 = __shfl_sync(kFull, cdist, 0);
+            if (v2 >= 0) {
+                // negative `lane` of this sample (lanes < (steps + 1) * K)
+                int neg = 0;
+                if (lane < (steps + 1) * K) {
+                    const U4 r = philox_block(a.seed, stream, (slice >> 2) * (s_base + it0 + (uint64_t)k) + neg_blk0 + (uint32_t)(lane >> 1));
+                    neg = (int)negative_sample(g, (lane & 1) ? r.z : r.x, (lane & 1) ? r.w : r.y);
+                }
+                const T alpha = (T)st.alpha;
+                for (int s = 0; s < steps; ++s) {
+                    const int c = __shfl_sync(kFull, cdist, s);
+                    if (c < 0) break;
+                    const int nid = __shfl_sync(kFull, neg, (s * K + lane - 1) & 31);
+                    update_community_step<C>(tv, tc, a.dim, lut, v1, lane == 0 ? c : nid, nrows, alpha, a.lambda, lane);
+                    st.pairs++;
+                }
+                const int nid = __shfl_sync(kFull, neg, (steps * K + lane - 1) & 31);
+                update_pair_cpp<C>(tv, tc, a.dim, false, lut, v2, lane == 0 ? v1 : nid, nrows, alpha, lane);
+                st.pairs++;
+            }
+            st.count++;
+            sched_tick(st, a.sched);
+        }
+    }
+    st.pos = (s_base + a.jobs) * slice;
+    if (lane == 0) a.state[w] = st;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Parity hooks
 // ---------------------------------------------------------------------------------------------------------------

@@ -302,12 +302,36 @@ __global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_warp_fa
             const int64_t cand = (int64_t)negative_sample(g, (lane & 1) ? r.z : r.x, (lane & 1) ? r.w : r.y);
             const T alpha = (T)st.alpha;
             Row<C> bufA[kWarpBatch], bufB[kWarpBatch];
+            // candidates base .. base + 3 (candidate 32 does not exist: its slot re-reads candidate 31 and is never scored)
             auto gather = [&](Row<C>(&rows)[kWarpBatch], int base) {
 #pragma unroll
-                for (int q = 0; q < kWarpBatch; ++q) rows[q].load_ca(W + __shfl_sync(kFull, cand, base + q) * dim, lane, dim);
+                for (int q = 0; q < kWarpBatch; ++q)
+                    rows[q].load_ca(W + __shfl_sync(kFull, cand, min(base + q, 31)) * dim, lane, dim);
             };
             int scanned = 0;
             bool hit = false;
+            auto step = [&](Row<C>& rj, T f, int idx) {  // rj holds item - candidate; f = user . (item - candidate)
+                if (hit || idx >= 32) return;
+                ++scanned;
+                if (f < (T)1) {
+                    hit = true;
+                    T* pj = W + __shfl_sync(kFull, cand, idx) * dim;
+                    const T c = A::mul(alpha, (T)0.0025);
+                    const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f)), alpha);
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) {
+                        const T verr = A::mul(gg, rj.x[e]);
+                        const T cerr = A::mul(gg, v.x[e]);
+                        const T rje = A::sub(ri.x[e], rj.x[e]);
+                        rj.x[e] = A::sub(A::mul(-c, rje), cerr);
+                        ri.x[e] = A::msub(cerr, c, ri.x[e]);
+                        v.x[e] = A::msub(verr, c, v.x[e]);
+                    }
+                    row_red_add<C>(pi, ri, lane, dim);
+                    row_red_add<C>(pj, rj, lane, dim);
+                    row_red_add<C>(pv, v, lane, dim);
+                }
+            };
             auto score = [&](Row<C>(&rows)[kWarpBatch], int base) {
                 T f[kWarpBatch];
 #pragma unroll
@@ -317,36 +341,26 @@ __global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_warp_fa
                 }
                 dots<C, kWarpBatch>(v, rows, kWarpBatch, f);
 #pragma unroll
-                for (int q = 0; q < kWarpBatch; ++q) {
-                    if (hit) continue;
-                    ++scanned;
-                    if (f[q] < (T)1) {
-                        hit = true;
-                        T* pj = W + __shfl_sync(kFull, cand, base + q) * dim;
-                        const T c = A::mul(alpha, (T)0.0025);
-                        const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f[q])), alpha);
-#pragma unroll
-                        for (int e = 0; e < C::EPL; ++e) {
-                            const T verr = A::mul(gg, rows[q].x[e]);
-                            const T cerr = A::mul(gg, v.x[e]);
-                            const T rje = A::sub(ri.x[e], rows[q].x[e]);
-                            rows[q].x[e] = A::sub(A::mul(-c, rje), cerr);
-                            ri.x[e] = A::msub(cerr, c, ri.x[e]);
-                            v.x[e] = A::msub(verr, c, v.x[e]);
-                        }
-                        row_red_add<C>(pi, ri, lane, dim);
-                        row_red_add<C>(pj, rows[q], lane, dim);
-                        row_red_add<C>(pv, v, lane, dim);
-                    }
-                }
+                for (int q = 0; q < kWarpBatch; ++q) step(rows[q], f[q], base + q);
             };
-            gather(bufA, 0);
-            for (int base = 0; base < 32 && !hit; base += 2 * kWarpBatch) {
-                gather(bufB, base + kWarpBatch);  // in flight while bufA is scored
-                score(bufA, base);
-                if (hit) break;
-                if (base + 2 * kWarpBatch < 32) gather(bufA, base + 2 * kWarpBatch);
-                score(bufB, base + kWarpBatch);
+            // the caller's negative (candidate 0) alone first, gathered together with the user and item rows: early in
+            // training nearly every sample stops here, and speculative gathers would double its traffic
+            {
+                Row<C> r0;
+                r0.load_ca(W + __shfl_sync(kFull, cand, 0) * dim, lane, dim);
+#pragma unroll
+                for (int e = 0; e < C::EPL; ++e) r0.x[e] = A::sub(ri.x[e], r0.x[e]);
+                step(r0, dot<C>(v, r0), 0);
+            }
+            if (!hit) {
+                gather(bufA, 1);
+                for (int base = 1; base < 32 && !hit; base += 2 * kWarpBatch) {
+                    if (base + kWarpBatch < 32) gather(bufB, base + kWarpBatch);  // in flight while bufA is scored
+                    score(bufA, base);
+                    if (hit || base + kWarpBatch >= 32) break;
+                    if (base + 2 * kWarpBatch < 32) gather(bufA, base + 2 * kWarpBatch);
+                    score(bufB, base + kWarpBatch);
+                }
             }
             st.count++;
             st.pairs++;

@@ -73,8 +73,15 @@ template <typename T>
 int train_hpe_t(smore_model_s* m, const smore_train_params* p) {
     return dispatch_dim<T>(m->dim, [&](auto cfg) -> int {
         using C = decltype(cfg);
-        auto kern = k_hpe<C>;
-        const size_t smem = smem_line<T>();
+        void (*kern)(TrainArgs<T>) = k_hpe<C>;
+        size_t smem = smem_line<T>();
+        if constexpr (sizeof(T) == 4) {  // fp32 Hogwild: the restructured kernel (kernels.cuh, k_hpe_fast)
+            if (p->mode != SMORE_MODE_DETERMINISTIC && p->walk_steps >= 1 && p->walk_steps <= kHpeMaxSteps &&
+                (p->walk_steps + 1) * p->negative_samples <= 32 && !getenv("SMORE_HPE_EXACT_STREAM")) {
+                kern = k_hpe_fast<C>;
+                smem = 1008 * sizeof(T);
+            }
+        }
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
         else if (int rc = pick_grid(kern, smem, effective_max_warps(p, m->rows * 2), p->total, L)) return rc;
