@@ -556,6 +556,180 @@ __global__ void __launch_bounds__(kBlockThreads) k_hoprec(TrainArgs<typename C::
     if (lane == 0) a.state[w] = st;
 }
 
+// HOP-Rec, fp32 Hogwild throughput path (same idea as k_warp_fast / k_hpe_fast). k_hoprec consumes its stream word for word:
+// per hop the item's neighbour chain, then five rejection loops one after the other (each has to know how many words the
+// previous one used), then the rows -- about 90 dependent memory round trips per sample. Here every sample owns a FIXED
+// slice of its warp's stream,
+//   [0, 32)    user: up to 16 alias attempts (p, idx) until field 0            (HBPR.cpp:97-99)
+//   [32, 52)   the walk: hop 1 one TargetSample, hops 2..5 two each            (HBPR.cpp:100, 105-109)
+//   then per hop 192 words: 32 alias attempts (idx, p) for the caller's negative (field of the item, HBPR.cpp:110-112)
+//                           and 4 x 32 one-word attempts for the uniform negatives of rounds 1..4 (proNet.cpp:1477-1482)
+// (a rejection loop that finds nothing in its 32 attempts -- probability (5/6)^32 on a 5 : 1 user : item mix -- continues on
+// an overflow stream), which lets 8 lanes draw the user and the whole item chain of 8 consecutive samples at once and makes
+// the 25 rejection loops of a sample independent of each other: the five of a hop are resolved together, their Philox
+// blocks computed once per warp and handed round by shuffles.
+constexpr int kHopGroup = 8;
+constexpr int kHopMaxSteps = 5;
+constexpr uint32_t kHopUserWords = 32, kHopWalkOff = 32, kHopNegOff = 52, kHopHopWords = 192;
+__host__ __device__ constexpr uint32_t hop_slice_words(int steps) { return kHopNegOff + kHopHopWords * (uint32_t)steps; }
+constexpr uint64_t kHopOverflowStream = 1ull << 40;
+
+template <class C>
+__global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_hoprec_fast(TrainArgs<typename C::T> a) {
+    using T = typename C::T;
+    using A = Ar<T>;
+    const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (w >= a.n_warps) return;
+    WarpState st = a.state[w];
+    const GraphDev& g = a.g;
+    const int dim = a.dim, steps = a.steps;
+    T* W = a.Wv;
+    const uint32_t V32 = (uint32_t)g.V;
+    const uint64_t stream = a.stream_base + (uint64_t)w;
+    const uint64_t slice_blocks = (uint64_t)(hop_slice_words(steps) >> 2);
+    const uint64_t s_base = (st.pos + hop_slice_words(steps) - 1) / hop_slice_words(steps);
+    for (uint64_t it0 = 0; it0 < a.jobs; it0 += kHopGroup) {
+        const int ng = (int)min((uint64_t)kHopGroup, a.jobs - it0);
+        // ---- 8 lanes: user + item chain of 8 samples ----
+        int m_user = -1, m_item[kHopMaxSteps];
+#pragma unroll
+        for (int h = 0; h < kHopMaxSteps; ++h) m_item[h] = -1;
+        if (lane < ng) {
+            const uint64_t sidx = s_base + it0 + (uint64_t)lane;
+            const uint64_t blk = slice_blocks * sidx;
+            for (uint32_t att = 0; m_user < 0; ++att) {
+                U4 r;
+                if (att < kHopUserWords / 2) r = philox_block(a.seed, stream, blk + (att >> 1));
+                else r = philox_block(a.seed, stream + kHopOverflowStream, sidx * 4096u + (att >> 1));
+                const int c = (int)source_sample(g, (att & 1) ? r.z : r.x, (att & 1) ? r.w : r.y);
+                if (__ldg(g.field + c) == 0) m_user = c;
+            }
+            int64_t c = m_user;
+            int used;
+            U4 r = philox_block(a.seed, stream, blk + (kHopWalkOff >> 2));
+            c = target_sample(g, c, r.x, r.y, used);
+            m_item[0] = (int)c;
+            // hops 2..5: words 2 + 4 (h - 1) .. + 3 of the walk region, i.e. (z, w) of one block and (x, y) of the next
+#pragma unroll
+            for (int h = 1; h < kHopMaxSteps; ++h) {
+                if (h < steps && c >= 0) {
+                    const U4 r2 = philox_block(a.seed, stream, blk + (kHopWalkOff >> 2) + (uint32_t)h);
+                    c = target_sample(g, c, r.z, r.w, used);
+                    if (c >= 0) c = target_sample(g, c, r2.x, r2.y, used);
+                    r = r2;
+                    m_item[h] = (int)c;
+                }
+            }
+        }
+        for (int k = 0; k < ng; ++k) {
+            const int vid = __shfl_sync(kFull, m_user, k);
+            int idist = -1;  // lane h: the item of hop h + 1
+#pragma unroll
+            for (int h = 0; h < kHopMaxSteps; ++h) {
+                const int c = __shfl_sync(kFull, m_item[h], k);
+                if (lane == h) idist = c;
+            }
+            const uint64_t sidx = s_base + it0 + (uint64_t)k;
+            const uint64_t blk = slice_blocks * sidx;
+            T* pv = W + (size_t)vid * dim;
+            for (int hop = 1; hop <= steps; ++hop) {
+                const int cid = __shfl_sync(kFull, idist, hop - 1);
+                if (cid < 0) break;  // sink: the reference would index row -1; abandon the sample
+                const int cfield = __ldg(g.field + cid);
+                // the hop's 192 words = 48 Philox blocks: lane L computes blocks L and (L < 16) 32 + L
+                const uint64_t hblk = blk + (kHopNegOff >> 2) + (uint64_t)(hop - 1) * (kHopHopWords >> 2);
+                const U4 ra = philox_block(a.seed, stream, hblk + (uint64_t)lane);
+                U4 rb = ra;
+                if (lane < 16) rb = philox_block(a.seed, stream, hblk + 32u + (uint64_t)lane);
+                int jid[5];
+                // region 0 (words 0..63, blocks 0..15): attempt t = words 2t, 2t+1 = block t/2, (x,y) or (z,w)
+                // regions 1..4 (words 64 + 32 (r-1) + t, blocks 16 + 8 (r-1) + t/4): one word per attempt
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    int cand;
+                    if (r == 0) {
+                        const int src = lane >> 1;
+                        const uint32_t x = __shfl_sync(kFull, ra.x, src), y = __shfl_sync(kFull, ra.y, src);
+                        const uint32_t z = __shfl_sync(kFull, ra.z, src), q = __shfl_sync(kFull, ra.w, src);
+                        cand = (int)negative_sample(g, (lane & 1) ? z : x, (lane & 1) ? q : y);
+                    } else {
+                        const int b = 16 + 8 * (r - 1) + (lane >> 2);  // block index inside the hop: < 32 lives in ra, else in rb
+                        const int src = b & 31;
+                        const uint32_t xa = __shfl_sync(kFull, ra.x, src), ya = __shfl_sync(kFull, ra.y, src);
+                        const uint32_t za = __shfl_sync(kFull, ra.z, src), qa = __shfl_sync(kFull, ra.w, src);
+                        const uint32_t xb = __shfl_sync(kFull, rb.x, src), yb = __shfl_sync(kFull, rb.y, src);
+                        const uint32_t zb = __shfl_sync(kFull, rb.z, src), qb = __shfl_sync(kFull, rb.w, src);
+                        const bool hi = b >= 32;
+                        const int e = lane & 3;
+                        const uint32_t wd = e == 0 ? (hi ? xb : xa) : e == 1 ? (hi ? yb : ya) : e == 2 ? (hi ? zb : za) : (hi ? qb : qa);
+                        cand = (int)index_draw(wd, V32);
+                    }
+                    unsigned acc = __ballot_sync(kFull, __ldg(g.field + cand) == cfield);
+                    for (uint32_t round = 1; !acc; ++round) {  // (rare) nothing in 32 attempts: overflow stream
+                        const U4 ro = philox_block(a.seed, stream + kHopOverflowStream,
+                                                   (sidx * 64u + (uint64_t)(hop * 8 + r)) * 4096u + 2048u + round * 32u + (uint32_t)lane);
+                        cand = r == 0 ? (int)negative_sample(g, ro.x, ro.y) : (int)index_draw(ro.x, V32);
+                        acc = __ballot_sync(kFull, __ldg(g.field + cand) == cfield);
+                    }
+                    jid[r] = __shfl_sync(kFull, cand, __ffs(acc) - 1);
+                }
+                const T alpha = (T)(st.alpha / (double)hop);  // _alpha/w, margin/w (HBPR.cpp:113)
+                const T margin = (T)(1.0 / (double)hop);
+                const T cdec = A::mul(alpha, (T)0.0025);
+                const T cv = A::mul(alpha, (T)0.025);
+                T* pi = W + (size_t)cid * dim;
+                Row<C> v, ri, rj[5], di, verr;
+                v.load_ca(pv, lane, dim);
+                ri.load_ca(pi, lane, dim);
+#pragma unroll
+                for (int r = 0; r < 5; ++r) rj[r].load_ca(W + (size_t)jid[r] * dim, lane, dim);
+                pin(v);
+                pin(ri);
+#pragma unroll
+                for (int r = 0; r < 5; ++r) pin(rj[r]);
+                di.zero();
+                verr.zero();
+                T up = 0;
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    Row<C> cvec;
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) cvec.x[e] = A::sub(ri.x[e], rj[r].x[e]);
+                    const T f = dot(v, cvec);
+                    if (!(f > margin)) {
+                        const T gg = A::mul(fast_sigmoid<T>(lut, A::sub((T)0, f)), alpha);
+                        up += (T)1;
+#pragma unroll
+                        for (int e = 0; e < C::EPL; ++e) {
+                            verr.x[e] = A::madd(verr.x[e], gg, cvec.x[e]);
+                            const T cerr = A::mul(gg, v.x[e]);
+                            const T d = A::msub(cerr, cdec, ri.x[e]);
+                            di.x[e] = A::add(di.x[e], d);
+                            ri.x[e] = A::add(ri.x[e], d);
+                            rj[r].x[e] = A::sub(A::mul(-cdec, rj[r].x[e]), cerr);
+                        }
+                        row_red_add<C>(W + (size_t)jid[r] * dim, rj[r], lane, dim);
+                    }
+                }
+                if (up > (T)0) {
+                    row_red_add<C>(pi, di, lane, dim);
+                    const T inv = A::div((T)1, up);
+#pragma unroll
+                    for (int e = 0; e < C::EPL; ++e) v.x[e] = A::msub(A::mul(verr.x[e], inv), cv, v.x[e]);
+                    row_red_add<C>(pv, v, lane, dim);
+                }
+                st.pairs += 5;
+            }
+            st.count++;
+            sched_tick(st, a.sched);
+        }
+    }
+    st.pos = (s_base + a.jobs) * hop_slice_words(steps);
+    if (lane == 0) a.state[w] = st;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // CPR and TPR (Go tree only): pairwise ranking where one side of the score is AGGREGATED on the fly from the rows of a
 // vertex' neighbours, in a second graph as well as in the first. One warp per sample, lane-parallel over the dimension:

@@ -16,6 +16,13 @@ int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind) {
                 warp_fast = true;
             }
         }
+        if constexpr (sizeof(T) == 4) {  // HOP-Rec, fp32 Hogwild: k_hoprec_fast
+            if (kind == RANK_HOPREC && p->mode != SMORE_MODE_DETERMINISTIC && p->walk_steps >= 1 && p->walk_steps <= kHopMaxSteps &&
+                !getenv("SMORE_HOPREC_EXACT_STREAM")) {
+                kern = k_hoprec_fast<C>;
+                warp_fast = true;  // (same shared-memory footprint: the sigmoid table only)
+            }
+        }
         const size_t smem = warp_fast ? 1008 * sizeof(T) : kind == RANK_SKEWOPT ? batch_smem_bytes<T>(0, kSbprRounds)
                             : kind != RANK_BPR ? smem_line<T>() : cpp ? batch_smem_bytes<T>(0, 5) : batch_smem_bytes<T>(1, 1);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
