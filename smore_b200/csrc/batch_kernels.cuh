@@ -37,6 +37,27 @@ inline size_t batch_smem_bytes(int go, int K, int stage_row_elems = 0) {
     return base + (size_t)kWarpsPerBlock * kStageDepth * (size_t)stage_row_elems * sizeof(T);
 }
 
+// SMORE_LINE_PIPE (EXPERIMENT, off): the unsharded C++ LINE kernel fetches ALL rows of the next samples -- vertex row + K + 1
+// context rows -- with cp.async into a per-warp ring of shared-memory stages, so that the bytes a warp keeps in flight do not
+// drop to zero during the dots and the reds and cost no register. Measured (profiles/r2t_line_pipe_ab.txt): one stage at 3
+// resident CTAs 382 M updates/s (the staged rows still have to sit in registers for the dots: spills), three stages at 2
+// resident CTAs (48 samples in flight per SM instead of 24) 629 M/s, against 784 M/s for plain 128-bit loads into registers;
+// 519 vs 675 M/s at the configs[4] per-GPU footprint. The register-resident gather is already at what the memory system
+// takes from one SM; the ring only removes warps. Kept compilable for the next look (-DSMORE_LINE_PIPE=1).
+#ifndef SMORE_LINE_PIPE
+#define SMORE_LINE_PIPE 0
+#endif
+constexpr int kPipeRows = 7;   // vertex + kCtxChunk context rows
+constexpr int kPipeDepth = 3;  // stages per warp: the rows of the next two samples are in flight while one is computed
+template <class C>
+__host__ __device__ constexpr bool line_pipe_cfg() {  // fp32 rows of <= 512 bytes (dim <= 128): 2 CTAs x 8 warps x 3 stages x 3.5 KB = 168 KB per SM
+    return SMORE_LINE_PIPE && sizeof(typename C::T) == 4 && C::EPL <= 4;
+}
+template <class C>
+inline size_t line_pipe_bytes() {
+    return line_pipe_cfg<C>() ? (size_t)kWarpsPerBlock * kPipeDepth * kPipeRows * (size_t)(C::EPL * 32) * sizeof(typename C::T) : 0;
+}
+
 // resident CTAs per SM the register allocator must allow: 3 while a row costs <= 16 B per lane (fp32 dim <= 128)
 #ifndef SMORE_LINE_MINBLOCKS
 #define SMORE_LINE_MINBLOCKS 3
@@ -299,8 +320,12 @@ __global__ void __launch_bounds__(kBlockThreads) k_apply_delta(typename C::T* __
 // KIND: 0 = skip-gram pair update (LINE), 1 = MF: the same sampling loop around UpdateFactorizedPair (MF::Train,
 // src/model/MF.cpp:70-92, draws exactly what LINE::Train draws), 2 = LINE with split samples (row-sharded modes only:
 // update_pair_split, the K negatives go to a second, independently drawn vertex).
+template <class C, bool GO, int SHARD, int KIND>
+__host__ __device__ constexpr bool line_pipe() {
+    return line_pipe_cfg<C>() && SHARD == 0 && KIND == 0 && !GO;
+}
 template <class C, bool GO, int SHARD, int KIND = 0>
-__global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
+__global__ void __launch_bounds__(kBlockThreads, line_pipe<C, GO, SHARD, KIND>() ? 2 : batch_min_blocks<C>()) k_line(TrainArgs<typename C::T> a) {
     constexpr bool STAGED = SHARD == 1;
     using T = typename C::T;
     const T* lut = stage_lut<T>(a.lut, reinterpret_cast<T*>(smem_raw));
@@ -344,10 +369,85 @@ __global__ void __launch_bounds__(kBlockThreads, batch_min_blocks<C>()) k_line(T
         off = (off + 15) & ~(size_t)15;
         vstage = reinterpret_cast<T*>(smem_raw + off) + (size_t)wib * kStageDepth * kRowElems;
     }
+    constexpr bool PIPE = line_pipe<C, GO, SHARD, KIND>();
+    T* pstage = nullptr;
+    if constexpr (PIPE) {
+        size_t off = 1008 * sizeof(T) + (size_t)kWarpsPerBlock * (size_t)(batch_wbuf_words(bmode, a.K) + 32 * batch_idw(bmode, a.K)) * 4;
+        off = (off + 15) & ~(size_t)15;
+        pstage = reinterpret_cast<T*>(smem_raw + off) + (size_t)wib * kPipeDepth * kPipeRows * kRowElems;
+    }
+    // (one warp = the DETERMINISTIC mode: every sample must see its predecessor's updates, nothing is fetched ahead)
+    const bool pipe = PIPE && nrows <= kCtxChunk && !a.same_table && a.n_warps > 1;
     const uint64_t my_jobs = a.jobs + (w < a.jobs_rem ? 1u : 0u);
     for (uint64_t done = 0; done < my_jobs; done += 32) {
         const int nb = (int)min((uint64_t)32, my_jobs - done);
         batch_sample<GO>(a.g, b, a.seed, stream, st, nb, lane);
+        if constexpr (PIPE) {
+            if (pipe) {
+                // every lane copies (and later reads) only the 16-byte pieces it owns: cp.async.wait_group is all the
+                // synchronisation the stage needs
+                auto issue = [&](int s) {
+                    if (s < nb) {
+                        const int* sid = b.ids + s * b.idw;
+                        T* stg = pstage + (s % kPipeDepth) * (kPipeRows * kRowElems);
+                        if (sid[1] >= 0) {
+                            row_stage_async<C>(stg, tv.row(sid[0]), lane, a.dim);
+                            for (int r = 0; r < nrows; ++r) row_stage_async<C>(stg + (1 + r) * kRowElems, tc.row(sid[1 + r]), lane, a.dim);
+                        }
+                    }
+                    cp_async_commit();
+                };
+#pragma unroll
+                for (int s = 0; s < kPipeDepth - 1; ++s) issue(s);
+                for (int s = 0; s < nb; ++s) {
+                    const int* sid = b.ids + s * b.idw;
+                    const int v1 = sid[0];
+                    const int v2 = sid[1];
+                    const int my = lane < nrows ? sid[1 + lane] : (-1 - lane);
+                    issue(s + kPipeDepth - 1);  // into the stage sample s - 1 has just left
+                    cp_async_wait<kPipeDepth - 1>();
+                    const T* stg = pstage + (s % kPipeDepth) * (kPipeRows * kRowElems);
+                    Row<C> v, c[kCtxChunk];
+                    if (v2 >= 0) {
+                        row_from_smem<C>(v, stg, lane, a.dim);
+#pragma unroll
+                        for (int r = 0; r < kCtxChunk; ++r)
+                            if (r < nrows) row_from_smem<C>(c[r], stg + (1 + r) * kRowElems, lane, a.dim);
+                    }
+                    if (v2 < 0) continue;
+                    const T alpha = (T)st.alpha;
+                    const unsigned peers = __match_any_sync(kFull, my);
+                    if (__any_sync(kFull, lane < nrows && __popc(peers) > 1)) {
+                        // a context row repeats inside the sample: the ordered path through memory
+                        update_pair_cpp<C, TV, TC, false>(tv, tc, a.dim, false, lut, v1, my, nrows, alpha, lane);
+                    } else {
+                        using A = Ar<T>;
+                        Row<C> back;
+                        back.zero();
+                        T f[kCtxChunk];
+                        dots<C, kCtxChunk>(v, c, nrows, f);
+#pragma unroll
+                        for (int r = 0; r < kCtxChunk; ++r) {
+                            if (r < nrows) {
+                                const T g = A::mul(A::sub(r == 0 ? (T)1 : (T)0, fast_sigmoid<T>(lut, f[r])), alpha);
+#pragma unroll
+                                for (int e = 0; e < C::EPL; ++e) {
+                                    back.x[e] = A::madd(back.x[e], g, c[r].x[e]);
+                                    c[r].x[e] = A::mul(g, v.x[e]);
+                                }
+                                row_red_add<C>(tc.row(sid[1 + r]), c[r], lane, a.dim);
+                            }
+                        }
+                        row_red_add<C>(tv.row(v1), back, lane, a.dim);
+                    }
+                    st.count++;
+                    st.pairs++;
+                    sched_tick(st, a.sched);
+                }
+                cp_async_wait<0>();
+                continue;
+            }
+        }
         if constexpr (SHARD == 3) {
             // remote source: k_line_requests filed it in the hash; its row now sits in the staging table
             if (lane < nb) {

@@ -12,12 +12,16 @@ int train_line_t(smore_model_s* m, const smore_train_params* p) {
         const int shard = m->g->world == 1 ? 0 : (m->replica[vtab] ? 2 : 1);
         // peer-access mode, LINE-2: split samples on request (neg_mode; the default is the reference's pairing)
         const bool split = shard == 1 && vtab != ctab && p->neg_mode == SMORE_PAIRING_SPLIT;
+        // the cp.async row pipeline (batch_kernels.cuh, SMORE_LINE_PIPE) serves the Hogwild C++ LINE-2 loop with K <= 5;
+        // everything else runs the same kernel without it (KIND = 4: three resident CTAs instead of two)
+        const bool pipe = line_pipe_cfg<C>() && cpp && shard == 0 && vtab != ctab && p->negative_samples + 1 <= kCtxChunk &&
+                          p->mode != SMORE_MODE_DETERMINISTIC;
         void (*kern)(TrainArgs<T>) =
             split ? k_line<C, false, 1, 2>
-            : cpp ? (shard == 2 ? k_line<C, false, 2> : shard == 1 ? k_line<C, false, 1> : k_line<C, false, 0>)
+            : cpp ? (shard == 2 ? k_line<C, false, 2> : shard == 1 ? k_line<C, false, 1> : pipe ? k_line<C, false, 0> : k_line<C, false, 0, 4>)
                   : (shard == 2 ? k_line<C, true, 2> : shard == 1 ? k_line<C, true, 1> : k_line<C, true, 0>);
         const size_t smem = batch_smem_bytes<T>(m->g->world > 1 ? (split ? 3 : 2) : cpp ? 0 : 1, p->negative_samples,
-                                                shard == 1 ? C::EPL * 32 : 0);
+                                                shard == 1 ? C::EPL * 32 : 0) + (pipe ? line_pipe_bytes<C>() : 0);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
@@ -54,8 +58,9 @@ int train_line_block_t(smore_model_s* m, const smore_train_params* p, int q, voi
         using C = decltype(cfg);
         const bool cpp = p->semantics == SMORE_SEM_CPP;
         const bool split = p->neg_mode == SMORE_PAIRING_SPLIT;
-        void (*kern)(TrainArgs<T>) = split ? k_line<C, false, 0, 2> : cpp ? k_line<C, false, 0> : k_line<C, true, 0>;
-        const size_t smem = batch_smem_bytes<T>(split ? 3 : 2, p->negative_samples, 0);
+        const bool pipe = line_pipe_cfg<C>() && cpp && !split && p->negative_samples + 1 <= kCtxChunk && p->mode != SMORE_MODE_DETERMINISTIC;
+        void (*kern)(TrainArgs<T>) = split ? k_line<C, false, 0, 2> : cpp ? (pipe ? k_line<C, false, 0> : k_line<C, false, 0, 4>) : k_line<C, true, 0>;
+        const size_t smem = batch_smem_bytes<T>(split ? 3 : 2, p->negative_samples, 0) + (pipe ? line_pipe_bytes<C>() : 0);
         if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         Launch L;
         if (p->mode == SMORE_MODE_DETERMINISTIC) { L.blocks = 1; L.warps = 1; }
