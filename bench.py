@@ -18,8 +18,10 @@ next GPU over NVLink (copy engines). A "step" is one full cycle of 2N episodes o
 value : updates/s with graph + tables resident in HBM (timed: K steps, CUDA events on the launching stream, barrier +
         synchronize on both sides, max over ranks).
 e2e   : the same metric through the C ABI the way a host Train() call sees it: every step uploads both embedding tables
-        (this rank's shards) from pinned HOST memory, trains, and reads the vertex table back to the host; the read-back
-        of step i overlaps the upload of step i+1 where the data dependences allow it (different tables).
+        (this rank's shards) from pinned HOST memory, trains, and reads the vertex table back to the host. N = 1: two
+        model instances alternate, so the uploads of step i+1 and the read-back of step i-1 run on the copy engines while
+        step i trains (an input pipeline: every step still moves all of its bytes). N > 1: the read-back of step i
+        overlaps the context-table upload of step i+1.
 roofline : algorithmic bytes per update (2*(K+2)*D*4 + 76 = 7244 B; with --split-samples one more row:
         2*(K+3)*D*4 + 84 = 8276 B) x updates / kernel time (the library's own CUDA events around the kernel) against
         MEASURED_PEAKS.json hbm_gbs.
@@ -398,7 +400,7 @@ def run_ours(args):
         try:
             import psutil
 
-            need = 3 * V * DIM * 4 * world  # three pinned buffers per rank, all ranks on this host
+            need = (4 if world == 1 else 3) * V * DIM * 4 * world  # pinned buffers per rank, all ranks on this host
             avail = psutil.virtual_memory().available
             if need > 0.6 * avail:
                 e2e_skip = f"skipped: {need / 1e9:.0f} GB of pinned host buffers needed, {avail / 1e9:.0f} GB of host RAM available"
@@ -412,27 +414,69 @@ def run_ours(args):
         hc = torch.empty((V, DIM), dtype=torch.float32, pin_memory=True)
         m.get_rows(0, out=hv.numpy())
         m.get_rows(1, out=hc.numpy())
-        hout = torch.empty((V, DIM), dtype=torch.float32, pin_memory=True)
+        if world == 1:
+            # Two model instances on the one graph, used alternately: the uploads of step i + 1 (into the idle instance) and
+            # the read-back of step i - 1 run on the copy engines WHILE step i trains -- an input pipeline, nothing more:
+            # every step still uploads both of its tables from pinned host memory and reads its result back. The library
+            # orders an instance's uploads after its pending read-backs on the device, so the host never blocks on a copy
+            # before launching the next train call.
+            m2 = capi.Model(g, DIM, 2, capi.F32)
+            inst = [m, m2]
+            houts = [torch.empty((V, DIM), dtype=torch.float32, pin_memory=True) for _ in inst]
+            e2e_no = [0]
 
-        def e2e_step():
-            # pipeline: the context-table upload overlaps the previous step's read-back of the vertex table (PCIe is full
-            # duplex); the vertex-table upload has to wait for that read-back (same device rows)
-            m.set_rows_async(1, hc.numpy())
-            m.wait_copies(uploads=False, readbacks=True)
-            m.set_rows_async(0, hv.numpy())
-            m.wait_copies(uploads=True, readbacks=False)
-            n, _ = step()
-            m.get_rows_async(0, hout.numpy())
-            return n
+            def upload(mm):
+                mm.set_rows_async(1, hc.numpy())
+                mm.set_rows_async(0, hv.numpy())
+
+            def train_on(mm):
+                i = step_no[0]
+                step_no[0] += 1
+                p.total = args.batch
+                p.stream_base = (i * world + rank) * (1 << 20)
+                return mm.train_line(p)["samples"]
+
+            def e2e_step():
+                i = e2e_no[0]
+                e2e_no[0] += 1
+                cur, nxt = inst[i & 1], inst[(i + 1) & 1]
+                upload(nxt)                                      # step i + 1's inputs: in flight while step i trains
+                cur.wait_copies(uploads=True, readbacks=False)   # step i's inputs (enqueued one step ago)
+                n = train_on(cur)
+                cur.get_rows_async(0, houts[i & 1].numpy())      # step i's result: in flight while step i + 1 trains
+                return n
+
+            upload(inst[0])
+
+            def wait_all():
+                for mm in inst:
+                    mm.wait_copies()
+        else:
+            hout = torch.empty((V, DIM), dtype=torch.float32, pin_memory=True)
+
+            def e2e_step():
+                # pipeline: the context-table upload overlaps the previous step's read-back of the vertex table (PCIe is full
+                # duplex); the vertex-table upload has to wait for that read-back (same device rows)
+                m.set_rows_async(1, hc.numpy())
+                m.wait_copies(uploads=False, readbacks=True)
+                m.set_rows_async(0, hv.numpy())
+                m.wait_copies(uploads=True, readbacks=False)
+                n, _ = step()
+                m.get_rows_async(0, hout.numpy())
+                return n
+
+            def wait_all():
+                m.wait_copies()
 
         e2e_step()
-        m.wait_copies()
-        barrier()
+        e2e_step()
+        wait_all()
+        barrier()  # (world == 1: the next step's inputs were enqueued one step ago, as for every step of the timed region)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
             e2e_updates += e2e_step()
-        m.wait_copies()
+        wait_all()
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)
@@ -479,7 +523,10 @@ def run_ours(args):
         "e2e": {"value": None if args.no_e2e else e2e_updates / (e2e_ms * 1e-3), "unit": "updates/s",
                 "h2d_bytes_per_step": 2 * V * DIM * 4 * world, "d2h_bytes_per_step": V * DIM * 4 * world,
                 "note": e2e_skip or ("per step and GPU: both table shards uploaded from pinned host memory, Train call(s), vertex "
-                                     "shard read back; the read-back overlaps the next step's context-table upload")},
+                                     "shard read back; " +
+                                     ("two model instances alternate: the uploads of step i+1 and the read-back of step i-1 run "
+                                      "on the copy engines while step i trains" if world == 1 else
+                                      "the read-back overlaps the next step's context-table upload"))},
         "gpu_launches": int(launches), "clocks": clk,
     }
     if world == 1 and not args.no_cpu_baseline:

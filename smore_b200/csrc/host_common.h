@@ -143,6 +143,7 @@ struct smore_model_s {
     smore_exchange_s* xch = nullptr;           // bulk-exchange mode of a sharded model (smore_model_enable_exchange)
     smore_rotation_s* rot = nullptr;           // rotating vertex table (smore_model_enable_rotation): tab[0] == nullptr then
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // smore_model_{set,get}_rows_f32_async
+    cudaEvent_t h2d_event = nullptr, d2h_event = nullptr;     // last copy enqueued on each (cross-stream ordering)
     WarpState* d_state = nullptr;
     int state_cap = 0;
     int32_t* d_keys = nullptr;
@@ -169,6 +170,8 @@ struct smore_model_s {
         cudaFree(replica[0]); cudaFree(replica[1]);
         if (h2d_stream) cudaStreamDestroy(h2d_stream);
         if (d2h_stream) cudaStreamDestroy(d2h_stream);
+        if (h2d_event) cudaEventDestroy(h2d_event);
+        if (d2h_event) cudaEventDestroy(d2h_event);
         delete xch;
         delete rot;
         if (live) cudaFreeHost(live);

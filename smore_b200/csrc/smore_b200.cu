@@ -702,12 +702,20 @@ static int async_rows(smore_model_t m, int table, int64_t first, int64_t n, floa
     if (int rc = ensure_device()) return rc;
     cudaStream_t& st = to_device ? m->h2d_stream : m->d2h_stream;
     if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    // Device-side ordering between the two copy streams of ONE model: an upload is ordered after the read-backs issued before
+    // it (it may overwrite the rows they are still reading) and a read-back after the uploads issued before it -- so a host
+    // that double-buffers two models never has to block on a copy before it can launch the next train call.
+    cudaEvent_t& mine = to_device ? m->h2d_event : m->d2h_event;
+    cudaEvent_t& other = to_device ? m->d2h_event : m->h2d_event;
+    if (!mine) CU(cudaEventCreateWithFlags(&mine, cudaEventDisableTiming));
+    if (other) CU(cudaStreamWaitEvent(st, other, 0));
     const size_t row_bytes = (size_t)m->dim * sizeof(float);
     const int64_t first0 = first;
     return for_row_ranges(m, table, first, n, [&](char* dptr, int64_t f, int64_t k) -> int {
         char* h = (char*)host + (size_t)(f - first0) * row_bytes;
         if (to_device) CU(cudaMemcpyAsync(dptr, h, (size_t)k * row_bytes, cudaMemcpyHostToDevice, st));
         else CU(cudaMemcpyAsync(h, dptr, (size_t)k * row_bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(mine, st));
         return SMORE_OK;
     });
 }

@@ -146,3 +146,31 @@ def test_chunked_schedule_continues_the_learning_rate():
         m.train_line(det(capi.SEM_CPP, total=5000, sched_total=10**9, sched_offset=offset))
         moved.append(np.abs(m.get_rows(0) - Wv).max())
     assert moved[0] > 1e-4 and moved[1] < moved[0] * 1e-3
+
+
+def test_async_row_copies_are_ordered_on_the_device():
+    """smore_model_{set,get}_rows_f32_async: an upload is ordered after the read-backs of the same model issued before it (and a
+    read-back after earlier uploads) by events between the two copy streams -- the host does not have to wait in between.
+    bench.py's end-to-end leg relies on it to double-buffer two model instances."""
+    import torch
+
+    src, dst, w = graphs.random_graph(5000, 40000, seed=3)
+    off, col, ww, _ = B.edges_to_csr(src, dst, w, 1)
+    g = capi.Graph.from_csr(off, col, ww)
+    V, dim = len(off) - 1, 128
+    m = capi.Model(g, dim, 2, capi.F32)
+    a = torch.full((V, dim), 1.0, dtype=torch.float32).pin_memory()
+    b = torch.full((V, dim), 2.0, dtype=torch.float32).pin_memory()
+    out1 = torch.zeros((V, dim), dtype=torch.float32).pin_memory()
+    out2 = torch.zeros((V, dim), dtype=torch.float32).pin_memory()
+    for _ in range(20):  # no host wait between the calls
+        m.set_rows_async(0, a.numpy())
+        m.get_rows_async(0, out1.numpy())   # must see `a`
+        m.set_rows_async(0, b.numpy())      # must not overtake the read-back above
+        m.get_rows_async(0, out2.numpy())   # must see `b`
+        m.wait_copies()
+        assert float(out1.min()) == 1.0 == float(out1.max())
+        assert float(out2.min()) == 2.0 == float(out2.max())
+        out1.zero_(), out2.zero_()
+    with pytest.raises(capi.SmoreError):
+        m.set_rows_async(0, a.numpy()[: V - 1], first=2)
