@@ -765,7 +765,9 @@ __device__ __forceinline__ int add_neighbour_rows(Row<C>& acc, const typename C:
 // CPR.Train (internal/models/cpr/cpr.go:175-282) with transformUser (:127-172). Wv = user rows, Wc = target-domain item rows,
 // aux_tab = source-domain item rows. lambda = user_reg. A sample whose user has no target-domain neighbour is skipped
 // without counting (:214-216).
-template <class C>
+// FAST (fp32 Hogwild): the (user, positive, negative) triples of 8 consecutive samples are drawn by 8 lanes at once from fixed
+// 8-word slices of the warp's stream (source 2 words, target 1, negative 2) instead of one after the other by lane 0.
+template <class C, bool FAST = false>
 __global__ void __launch_bounds__(kBlockThreads) k_cpr(TrainArgs<typename C::T> a) {
     using T = typename C::T;
     using A = Ar<T>;
@@ -781,24 +783,45 @@ __global__ void __launch_bounds__(kBlockThreads) k_cpr(TrainArgs<typename C::T> 
     ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
     const GraphDev& g = a.g;
     const int dim = a.dim;
+    const uint64_t fast_base = (st.pos + 7) / 8;  // FAST: samples this stream has already served (8-word slices)
+    int64_t gu = -1, gp = -1, gn = -1;
     for (uint64_t it = 0; it < a.jobs; ++it) {
-        ring.ensure();
         int64_t u = -1, p = -1, n = -1;
-        int used = 0;
-        if (lane == 0) {
-            u = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
-            p = target_sample(g, u, ring.peek(2), ring.peek(3), used);
-            if (p >= 0) n = (int64_t)negative_sample(g, ring.peek(2u + (uint32_t)used), ring.peek(3u + (uint32_t)used));
+        if constexpr (FAST) {
+            if ((it & 7) == 0) {  // lanes 0..7 draw the triples of samples it .. it + 7
+                gu = gp = gn = -1;
+                if (lane < 8 && it + (uint64_t)lane < a.jobs) {
+                    const uint64_t blk = 2 * (fast_base + it + (uint64_t)lane);
+                    const U4 r0 = philox_block(a.seed, a.stream_base + (uint64_t)w, blk);
+                    const U4 r1 = philox_block(a.seed, a.stream_base + (uint64_t)w, blk + 1);
+                    int used;
+                    gu = (int64_t)source_sample(g, r0.x, r0.y);
+                    gp = target_sample(g, gu, r0.z, r0.w, used);
+                    gn = (int64_t)negative_sample(g, r1.x, r1.y);
+                }
+            }
+            u = __shfl_sync(kFull, gu, (int)(it & 7));
+            p = __shfl_sync(kFull, gp, (int)(it & 7));
+            n = __shfl_sync(kFull, gn, (int)(it & 7));
+            if (p < 0) continue;
+        } else {
+            ring.ensure();
+            int used = 0;
+            if (lane == 0) {
+                u = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
+                p = target_sample(g, u, ring.peek(2), ring.peek(3), used);
+                if (p >= 0) n = (int64_t)negative_sample(g, ring.peek(2u + (uint32_t)used), ring.peek(3u + (uint32_t)used));
+            }
+            u = __shfl_sync(kFull, u, 0);
+            p = __shfl_sync(kFull, p, 0);
+            n = __shfl_sync(kFull, n, 0);
+            used = __shfl_sync(kFull, used, 0);
+            if (p < 0) {
+                ring.advance(2u + (uint32_t)used);
+                continue;
+            }
+            ring.advance(4u + (uint32_t)used);
         }
-        u = __shfl_sync(kFull, u, 0);
-        p = __shfl_sync(kFull, p, 0);
-        n = __shfl_sync(kFull, n, 0);
-        used = __shfl_sync(kFull, used, 0);
-        if (p < 0) {
-            ring.advance(2u + (uint32_t)used);
-            continue;
-        }
-        ring.advance(4u + (uint32_t)used);
         const T alpha = (T)st.alpha;
         T* pu = a.Wv + (size_t)u * dim;
         T* pp = a.Wc + (size_t)p * dim;
@@ -856,7 +879,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_cpr(TrainArgs<typename C::T> 
         st.count++;
         sched_tick(st, a.sched);
     }
-    st.pos = ring.pos;
+    st.pos = FAST ? (fast_base + a.jobs) * 8 : ring.pos;
     if (lane == 0) a.state[w] = st;
 }
 
@@ -932,7 +955,7 @@ __device__ __forceinline__ void tpr_push_words(const TrainArgs<typename C::T>& a
 
 // TPR.Train (internal/models/tpr/tpr.go:124-262). Wv = user rows, Wc = item rows (both over the user-item graph's vids),
 // aux_tab = word rows over the item-word graph's vids.
-template <class C>
+template <class C, bool FAST = false>
 __global__ void __launch_bounds__(kBlockThreads) k_tpr(TrainArgs<typename C::T> a) {
     using T = typename C::T;
     using A = Ar<T>;
@@ -948,24 +971,45 @@ __global__ void __launch_bounds__(kBlockThreads) k_tpr(TrainArgs<typename C::T> 
     ring.init(rings + wib * 256, a.seed, a.stream_base + (uint64_t)w, st.pos, lane);
     const GraphDev& g = a.g;
     const int dim = a.dim;
+    const uint64_t fast_base = (st.pos + 7) / 8;  // FAST: samples this stream has already served (8-word slices)
+    int64_t gu = -1, gp = -1, gn = -1;
     for (uint64_t it = 0; it < a.jobs; ++it) {
-        ring.ensure();
         int64_t u = -1, p = -1, n = -1;
-        int used = 0;
-        if (lane == 0) {
-            u = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
-            p = target_sample(g, u, ring.peek(2), ring.peek(3), used);
-            if (p >= 0) n = (int64_t)negative_sample(g, ring.peek(2u + (uint32_t)used), ring.peek(3u + (uint32_t)used));
+        if constexpr (FAST) {
+            if ((it & 7) == 0) {  // lanes 0..7 draw the triples of samples it .. it + 7
+                gu = gp = gn = -1;
+                if (lane < 8 && it + (uint64_t)lane < a.jobs) {
+                    const uint64_t blk = 2 * (fast_base + it + (uint64_t)lane);
+                    const U4 r0 = philox_block(a.seed, a.stream_base + (uint64_t)w, blk);
+                    const U4 r1 = philox_block(a.seed, a.stream_base + (uint64_t)w, blk + 1);
+                    int used;
+                    gu = (int64_t)source_sample(g, r0.x, r0.y);
+                    gp = target_sample(g, gu, r0.z, r0.w, used);
+                    gn = (int64_t)negative_sample(g, r1.x, r1.y);
+                }
+            }
+            u = __shfl_sync(kFull, gu, (int)(it & 7));
+            p = __shfl_sync(kFull, gp, (int)(it & 7));
+            n = __shfl_sync(kFull, gn, (int)(it & 7));
+            if (p < 0) continue;
+        } else {
+            ring.ensure();
+            int used = 0;
+            if (lane == 0) {
+                u = (int64_t)source_sample(g, ring.peek(0), ring.peek(1));
+                p = target_sample(g, u, ring.peek(2), ring.peek(3), used);
+                if (p >= 0) n = (int64_t)negative_sample(g, ring.peek(2u + (uint32_t)used), ring.peek(3u + (uint32_t)used));
+            }
+            u = __shfl_sync(kFull, u, 0);
+            p = __shfl_sync(kFull, p, 0);
+            n = __shfl_sync(kFull, n, 0);
+            used = __shfl_sync(kFull, used, 0);
+            if (p < 0) {
+                ring.advance(2u + (uint32_t)used);
+                continue;
+            }
+            ring.advance(4u + (uint32_t)used);
         }
-        u = __shfl_sync(kFull, u, 0);
-        p = __shfl_sync(kFull, p, 0);
-        n = __shfl_sync(kFull, n, 0);
-        used = __shfl_sync(kFull, used, 0);
-        if (p < 0) {
-            ring.advance(2u + (uint32_t)used);
-            continue;
-        }
-        ring.advance(4u + (uint32_t)used);
         const T alpha = (T)st.alpha;
         const T la = A::mul(a.lambda, alpha);
         T* pu = a.Wv + (size_t)u * dim;
@@ -1016,7 +1060,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_tpr(TrainArgs<typename C::T> 
         st.count++;
         sched_tick(st, a.sched);
     }
-    st.pos = ring.pos;
+    st.pos = FAST ? (fast_base + a.jobs) * 8 : ring.pos;
     if (lane == 0) a.state[w] = st;
 }
 

@@ -16,6 +16,10 @@ int train_ranking_t(smore_model_s* m, const smore_train_params* p, int kind) {
                 warp_fast = true;
             }
         }
+        if constexpr (sizeof(T) == 4) {  // CPR / TPR, fp32 Hogwild: group sampling (ranking_kernels.cuh, FAST)
+            if (kind >= RANK_CPR && p->mode != SMORE_MODE_DETERMINISTIC && !getenv("SMORE_AUX_EXACT_STREAM"))
+                kern = kind == RANK_CPR ? k_cpr<C, true> : k_tpr<C, true>;
+        }
         if constexpr (sizeof(T) == 4) {  // HOP-Rec, fp32 Hogwild: k_hoprec_fast
             if (kind == RANK_HOPREC && p->mode != SMORE_MODE_DETERMINISTIC && p->walk_steps >= 1 && p->walk_steps <= kHopMaxSteps &&
                 !getenv("SMORE_HOPREC_EXACT_STREAM")) {
