@@ -593,9 +593,9 @@ __global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_hoprec_
     for (uint64_t it0 = 0; it0 < a.jobs; it0 += kHopGroup) {
         const int ng = (int)min((uint64_t)kHopGroup, a.jobs - it0);
         // ---- 8 lanes: user + item chain of 8 samples ----
-        int m_user = -1, m_item[kHopMaxSteps];
+        int m_user = -1, m_item[kHopMaxSteps], m_field[kHopMaxSteps];
 #pragma unroll
-        for (int h = 0; h < kHopMaxSteps; ++h) m_item[h] = -1;
+        for (int h = 0; h < kHopMaxSteps; ++h) m_item[h] = -1, m_field[h] = 0;
         if (lane < ng) {
             const uint64_t sidx = s_base + it0 + (uint64_t)lane;
             const uint64_t blk = slice_blocks * sidx;
@@ -622,59 +622,72 @@ __global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_hoprec_
                     m_item[h] = (int)c;
                 }
             }
+#pragma unroll
+            for (int h = 0; h < kHopMaxSteps; ++h)
+                if (m_item[h] >= 0) m_field[h] = __ldg(g.field + m_item[h]);
         }
         for (int k = 0; k < ng; ++k) {
             const int vid = __shfl_sync(kFull, m_user, k);
-            int idist = -1;  // lane h: the item of hop h + 1
+            int idist = -1, fdist = 0;  // lane h: the item of hop h + 1 and its field
 #pragma unroll
             for (int h = 0; h < kHopMaxSteps; ++h) {
                 const int c = __shfl_sync(kFull, m_item[h], k);
-                if (lane == h) idist = c;
+                const int f = __shfl_sync(kFull, m_field[h], k);
+                if (lane == h) idist = c, fdist = f;
             }
             const uint64_t sidx = s_base + it0 + (uint64_t)k;
             const uint64_t blk = slice_blocks * sidx;
             T* pv = W + (size_t)vid * dim;
-            for (int hop = 1; hop <= steps; ++hop) {
-                const int cid = __shfl_sync(kFull, idist, hop - 1);
-                if (cid < 0) break;  // sink: the reference would index row -1; abandon the sample
-                const int cfield = __ldg(g.field + cid);
+            // the five negatives of hop `hop` (item field cfield); jid[r] is warp-uniform
+            auto resolve = [&](int hop, int cfield, int (&jid)[5]) {
                 // the hop's 192 words = 48 Philox blocks: lane L computes blocks L and (L < 16) 32 + L
                 const uint64_t hblk = blk + (kHopNegOff >> 2) + (uint64_t)(hop - 1) * (kHopHopWords >> 2);
                 const U4 ra = philox_block(a.seed, stream, hblk + (uint64_t)lane);
                 U4 rb = ra;
                 if (lane < 16) rb = philox_block(a.seed, stream, hblk + 32u + (uint64_t)lane);
-                int jid[5];
                 // region 0 (words 0..63, blocks 0..15): attempt t = words 2t, 2t+1 = block t/2, (x,y) or (z,w)
                 // regions 1..4 (words 64 + 32 (r-1) + t, blocks 16 + 8 (r-1) + t/4): one word per attempt
+                int cand[5];
+                {
+                    const int src = lane >> 1;
+                    const uint32_t x = __shfl_sync(kFull, ra.x, src), y = __shfl_sync(kFull, ra.y, src);
+                    const uint32_t z = __shfl_sync(kFull, ra.z, src), q = __shfl_sync(kFull, ra.w, src);
+                    cand[0] = (int)negative_sample(g, (lane & 1) ? z : x, (lane & 1) ? q : y);
+                }
+#pragma unroll
+                for (int r = 1; r < 5; ++r) {
+                    const int b = 16 + 8 * (r - 1) + (lane >> 2);  // block index inside the hop: < 32 lives in ra, else in rb
+                    const int src = b & 31;
+                    const uint32_t xa = __shfl_sync(kFull, ra.x, src), ya = __shfl_sync(kFull, ra.y, src);
+                    const uint32_t za = __shfl_sync(kFull, ra.z, src), qa = __shfl_sync(kFull, ra.w, src);
+                    const uint32_t xb = __shfl_sync(kFull, rb.x, src), yb = __shfl_sync(kFull, rb.y, src);
+                    const uint32_t zb = __shfl_sync(kFull, rb.z, src), qb = __shfl_sync(kFull, rb.w, src);
+                    const bool hi = b >= 32;
+                    const int e = lane & 3;
+                    const uint32_t wd = e == 0 ? (hi ? xb : xa) : e == 1 ? (hi ? yb : ya) : e == 2 ? (hi ? zb : za) : (hi ? qb : qa);
+                    cand[r] = (int)index_draw(wd, V32);
+                }
+                int fld[5];
+#pragma unroll
+                for (int r = 0; r < 5; ++r) fld[r] = __ldg(g.field + cand[r]);  // five independent look-ups in flight
 #pragma unroll
                 for (int r = 0; r < 5; ++r) {
-                    int cand;
-                    if (r == 0) {
-                        const int src = lane >> 1;
-                        const uint32_t x = __shfl_sync(kFull, ra.x, src), y = __shfl_sync(kFull, ra.y, src);
-                        const uint32_t z = __shfl_sync(kFull, ra.z, src), q = __shfl_sync(kFull, ra.w, src);
-                        cand = (int)negative_sample(g, (lane & 1) ? z : x, (lane & 1) ? q : y);
-                    } else {
-                        const int b = 16 + 8 * (r - 1) + (lane >> 2);  // block index inside the hop: < 32 lives in ra, else in rb
-                        const int src = b & 31;
-                        const uint32_t xa = __shfl_sync(kFull, ra.x, src), ya = __shfl_sync(kFull, ra.y, src);
-                        const uint32_t za = __shfl_sync(kFull, ra.z, src), qa = __shfl_sync(kFull, ra.w, src);
-                        const uint32_t xb = __shfl_sync(kFull, rb.x, src), yb = __shfl_sync(kFull, rb.y, src);
-                        const uint32_t zb = __shfl_sync(kFull, rb.z, src), qb = __shfl_sync(kFull, rb.w, src);
-                        const bool hi = b >= 32;
-                        const int e = lane & 3;
-                        const uint32_t wd = e == 0 ? (hi ? xb : xa) : e == 1 ? (hi ? yb : ya) : e == 2 ? (hi ? zb : za) : (hi ? qb : qa);
-                        cand = (int)index_draw(wd, V32);
-                    }
-                    unsigned acc = __ballot_sync(kFull, __ldg(g.field + cand) == cfield);
+                    unsigned acc = __ballot_sync(kFull, fld[r] == cfield);
+                    int cnd = cand[r];
                     for (uint32_t round = 1; !acc; ++round) {  // (rare) nothing in 32 attempts: overflow stream
                         const U4 ro = philox_block(a.seed, stream + kHopOverflowStream,
                                                    (sidx * 64u + (uint64_t)(hop * 8 + r)) * 4096u + 2048u + round * 32u + (uint32_t)lane);
-                        cand = r == 0 ? (int)negative_sample(g, ro.x, ro.y) : (int)index_draw(ro.x, V32);
-                        acc = __ballot_sync(kFull, __ldg(g.field + cand) == cfield);
+                        cnd = r == 0 ? (int)negative_sample(g, ro.x, ro.y) : (int)index_draw(ro.x, V32);
+                        acc = __ballot_sync(kFull, __ldg(g.field + cnd) == cfield);
                     }
-                    jid[r] = __shfl_sync(kFull, cand, __ffs(acc) - 1);
+                    jid[r] = __shfl_sync(kFull, cnd, __ffs(acc) - 1);
                 }
+            };
+            int jid[5], jnext[5];
+            int cid = __shfl_sync(kFull, idist, 0);
+            if (cid >= 0) resolve(1, __shfl_sync(kFull, fdist, 0), jid);
+            for (int hop = 1; hop <= steps; ++hop) {
+                if (cid < 0) break;  // sink: the reference would index row -1; abandon the sample
                 const T alpha = (T)(st.alpha / (double)hop);  // _alpha/w, margin/w (HBPR.cpp:113)
                 const T margin = (T)(1.0 / (double)hop);
                 const T cdec = A::mul(alpha, (T)0.0025);
@@ -689,6 +702,9 @@ __global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_hoprec_
                 pin(ri);
 #pragma unroll
                 for (int r = 0; r < 5; ++r) pin(rj[r]);
+                // while the seven rows are in flight: the ids of the next hop
+                const int cnext = hop < steps ? __shfl_sync(kFull, idist, hop) : -1;
+                if (cnext >= 0) resolve(hop + 1, __shfl_sync(kFull, fdist, hop), jnext);
                 di.zero();
                 verr.zero();
                 T up = 0;
@@ -721,6 +737,9 @@ __global__ void __launch_bounds__(kBlockThreads, walk_min_blocks<C>()) k_hoprec_
                     row_red_add<C>(pv, v, lane, dim);
                 }
                 st.pairs += 5;
+                cid = cnext;
+#pragma unroll
+                for (int r = 0; r < 5; ++r) jid[r] = jnext[r];
             }
             st.count++;
             sched_tick(st, a.sched);
