@@ -36,9 +36,9 @@ def ncu_csv(rep, page):
 def main():
     tag, launches, rep = sys.argv[1:4]
     kernel = sys.argv[4] if len(sys.argv) > 4 else "k_line"
-    # 1. launch list
-    rows = [r for r in csv.reader(open(launches)) if len(r) > 10]
-    with open(os.path.join(HERE, f"{tag}_launches.csv"), "w") as f:
+    # 1. launch list ("-": none for this capture)
+    rows = [r for r in csv.reader(open(launches)) if len(r) > 10] if launches != "-" else []
+    with open(os.path.join(HERE, f"{tag}_launches.csv") if rows else os.devnull, "w") as f:
         f.write("id,kernel,grid,block,gpu__time_duration_ns\n")
         total = {}
         for r in rows[1:]:
