@@ -1175,7 +1175,7 @@ done:
     return d.s.pos;
 }
 
-// Diagnostic (tools/go_walk_streams_probe.py): the DEVICE's work split of the Go DeepWalk loop, run sequentially -- W
+// Diagnostic (tests/probes/go_walk_streams_probe.py): the DEVICE's work split of the Go DeepWalk loop, run sequentially -- W
 // independent draw streams, walk i of an epoch on stream i % W, each stream with the device's tick rule for the shared
 // schedule (device_core.cuh sched_tick) -- i.e. the Hogwild kernel minus the concurrency. Not a reference path.
 uint64_t orc_train_deepwalk_go_streams(void* h, double* Wv, double* Wc, int dim, int walk_times, int walk_steps, int window,

@@ -68,7 +68,7 @@ def main():
                recall_at_10=rec)
     if want("deepwalk_go") or want("node2vec_go"):
         # The Go walk models' recall@10 moves with the draw seed on this problem (27 M pair updates from 72 000 walks: few,
-        # long, correlated sample groups): one-stream runs range over 0.099-0.108 (tools/go_walk_streams_probe.py,
+        # long, correlated sample groups): one-stream runs range over 0.099-0.108 (tests/probes/go_walk_streams_probe.py,
         # profiles/r2m_*), so these two baselines are the MEAN over eight one-stream runs, seeds 1..8.
         gg = B.OracleGraph(B.SEM_GO, off, col, ww, max_line=len(col) // 2)
         walk_seeds = tuple(range(1, 9))

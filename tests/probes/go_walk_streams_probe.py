@@ -3,7 +3,7 @@
 without any concurrency -- move recall@10 on the quality gate's problem? (tools/go_walk_probe.py is the GPU side.)"""
 import sys, os, json
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import bindings as B  # noqa: E402
 from tests import quality as Q  # noqa: E402

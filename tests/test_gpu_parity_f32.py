@@ -127,6 +127,22 @@ def test_walk_models_f32(sem, walklets):
     assert rel_err(m.get_rows(0), a) < REL_TOL and rel_err(m.get_rows(1), c) < REL_TOL
 
 
+def test_node2vec_f32():
+    """Go tree only: the biased second-order walk (fp64 weights inside, whatever the table type) feeding fp32 pair updates."""
+    src, dst, w = graphs.random_graph(150, 700, seed=37)
+    og, dg, _ = make(src, dst, w, 1, capi.SEM_GO)
+    dim = 128
+    Wv, Wc = graphs.init_tables(og.V, dim, seed=7)
+    a, c = Wv.copy(), Wc.copy()
+    wt, ws, max_walks = 1, 20, 40
+    pos, pairs = og.train_node2vec_go(a, c, wt, ws, 5, 5, 0.025, 0.5, 2.0, SEED, 0, max_walks)
+    m = _model(dg, dim, 2, Wv, Wc)
+    p = params(capi.SEM_GO, walk_times=wt, walk_steps=ws, window_min=1, window_max=5, max_walks=max_walks, n2v_p=0.5, n2v_q=2.0)
+    st = m.train_node2vec(p)
+    assert st["words_stream0"] == pos and st["pair_updates"] == pairs
+    assert rel_err(m.get_rows(0), a) < REL_TOL and rel_err(m.get_rows(1), c) < REL_TOL
+
+
 def test_hpe_f32():
     src, dst, w = graphs.random_graph(300, 4000, seed=47)
     og, dg, _ = make(src, dst, w, 1, capi.SEM_CPP)

@@ -145,7 +145,7 @@ def test_go_walk_models(model):
 
     # Both sides are means here: the walk models draw few, long, correlated sample groups (72 000 walks), and one run's
     # recall@10 has a standard deviation of 0.002-0.003 on the CPU path (8 seeds: 0.0996-0.1074, quality_baselines_v2.json)
-    # and up to 0.004 on the GPU (profiles/r2m_go_walk_probe.jsonl). tools/go_walk_streams_probe.py shows that the GPU's
+    # and up to 0.004 on the GPU (profiles/r2m_go_walk_probe.jsonl). tests/probes/go_walk_streams_probe.py shows that the GPU's
     # numbers are reproduced by the oracle when it splits the walks over the same number of draw streams sequentially.
     a, r = mean_of(run, seeds=range(13, 19))
     check(model, a, ref["auc"])
