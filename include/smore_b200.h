@@ -125,7 +125,9 @@ int smore_model_set_rows_f32(smore_model_t m, int table, int64_t first, int64_t 
 int smore_model_get_rows_f32(smore_model_t m, int table, int64_t first, int64_t n, float* host);
 /* Asynchronous variants for hosts that pipeline their own staging (fp32 models, `host` in pinned memory): uploads and
  * read-backs are queued on two internal copy streams, so the read-back of one Train() result overlaps the upload of the
- * next call's inputs (PCIe is full duplex). The streams do not synchronise with the trainers: call
+ * next call's inputs (PCIe is full duplex). Within one model the two streams are ordered on the device PER TABLE: an upload
+ * waits for the read-backs of the same table issued before it and a read-back for the earlier uploads of that table; copies
+ * of different tables never wait on each other. The streams do not synchronise with the trainers: call
  * smore_model_wait_copies(m, uploads, readbacks) before training on rows being uploaded / before reading `host`. */
 int smore_model_set_rows_f32_async(smore_model_t m, int table, int64_t first, int64_t n, const float* host);
 int smore_model_get_rows_f32_async(smore_model_t m, int table, int64_t first, int64_t n, float* host);

@@ -143,7 +143,8 @@ struct smore_model_s {
     smore_exchange_s* xch = nullptr;           // bulk-exchange mode of a sharded model (smore_model_enable_exchange)
     smore_rotation_s* rot = nullptr;           // rotating vertex table (smore_model_enable_rotation): tab[0] == nullptr then
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // smore_model_{set,get}_rows_f32_async
-    cudaEvent_t h2d_event = nullptr, d2h_event = nullptr;     // last copy enqueued on each (cross-stream ordering)
+    cudaEvent_t h2d_event[2] = {nullptr, nullptr};            // last upload / read-back enqueued PER TABLE (cross-stream
+    cudaEvent_t d2h_event[2] = {nullptr, nullptr};            // ordering: copies of different tables never wait on each other)
     WarpState* d_state = nullptr;
     int state_cap = 0;
     int32_t* d_keys = nullptr;
@@ -161,6 +162,7 @@ struct smore_model_s {
     // live progress (smore_progress): host-mapped {done, alpha bits, total, running}; schedule units done before this call
     unsigned long long* live = nullptr;
     unsigned long long live_offset = 0;
+    unsigned long long* h_stats = nullptr;  // host-mapped {pairs, tries, words of warp 0, alpha bits}: collect_stats
     size_t elem() const { return dtype == SMORE_F64 ? 8 : 4; }
     ~smore_model_s() {
         for (int t = 0; t < 2; ++t)
@@ -170,11 +172,14 @@ struct smore_model_s {
         cudaFree(replica[0]); cudaFree(replica[1]);
         if (h2d_stream) cudaStreamDestroy(h2d_stream);
         if (d2h_stream) cudaStreamDestroy(d2h_stream);
-        if (h2d_event) cudaEventDestroy(h2d_event);
-        if (d2h_event) cudaEventDestroy(d2h_event);
+        for (int t = 0; t < 2; ++t) {
+            if (h2d_event[t]) cudaEventDestroy(h2d_event[t]);
+            if (d2h_event[t]) cudaEventDestroy(d2h_event[t]);
+        }
         delete xch;
         delete rot;
         if (live) cudaFreeHost(live);
+        if (h_stats) cudaFreeHost(h_stats);
         cudaFree(d_aux_off); cudaFree(d_aux_col); cudaFree(aux_tab);
     }
 };
@@ -302,18 +307,66 @@ struct Timer {
     }
 };
 
-int collect_stats(smore_model_s* m, int warps) {
-    std::vector<WarpState> st((size_t)warps);
-    CU(cudaMemcpy(st.data(), m->d_state, st.size() * sizeof(WarpState), cudaMemcpyDeviceToHost));
-    m->st_pairs = m->st_tries = 0;
-    for (auto& s : st) {
-        m->st_pairs += s.pairs;
-        m->st_tries += s.tries;
+// The train calls keep clear of the copy engines: a host that pipelines its own row transfers next to a train call
+// (smore_model_{set,get}_rows_f32_async) would otherwise see the call's small state copies queue behind a 0.5 GB upload on
+// the same engine. The per-warp state is therefore initialised by a kernel, and its statistics are reduced by a kernel into
+// four host-mapped words {pairs, tries, stream position of warp 0, alpha bits of warp 0}.
+__global__ void k_fill_state(WarpState* st, int n, WarpState proto) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st[i] = proto;
+}
+__global__ void k_reduce_state(const WarpState* st, int n, unsigned long long* out) {
+    __shared__ unsigned long long s_pairs, s_tries;
+    if (threadIdx.x == 0) s_pairs = s_tries = 0;
+    __syncthreads();
+    unsigned long long pairs = 0, tries = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        pairs += st[i].pairs;
+        tries += st[i].tries;
     }
-    m->st_words0 = st[0].pos;
-    if (m->live) {  // the call is over: what the LAST tick saw -> where the schedule really stands
-        unsigned long long bits;
+    atomicAdd(&s_pairs, pairs);
+    atomicAdd(&s_tries, tries);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out[0] = s_pairs;
+        out[1] = s_tries;
+        out[2] = st[0].pos;
+        out[3] = (unsigned long long)__double_as_longlong(st[0].alpha);
+        __threadfence_system();
+    }
+}
+
+int collect_stats(smore_model_s* m, int warps) {
+    unsigned long long bits;
+    if (!m->h_stats && cudaHostAlloc((void**)&m->h_stats, 4 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        m->h_stats = nullptr;
+    }
+    unsigned long long* dev = nullptr;
+    if (m->h_stats && cudaHostGetDevicePointer((void**)&dev, m->h_stats, 0) != cudaSuccess) {
+        cudaGetLastError();
+        dev = nullptr;
+    }
+    if (dev) {
+        k_reduce_state<<<1, 256>>>(m->d_state, warps, dev);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(0));
+        m->st_pairs = m->h_stats[0];
+        m->st_tries = m->h_stats[1];
+        m->st_words0 = m->h_stats[2];
+        bits = m->h_stats[3];
+    } else {  // no mapped host memory on this platform: read the states back
+        std::vector<WarpState> st((size_t)warps);
+        CU(cudaMemcpy(st.data(), m->d_state, st.size() * sizeof(WarpState), cudaMemcpyDeviceToHost));
+        m->st_pairs = m->st_tries = 0;
+        for (auto& s : st) {
+            m->st_pairs += s.pairs;
+            m->st_tries += s.tries;
+        }
+        m->st_words0 = st[0].pos;
         memcpy(&bits, &st[0].alpha, sizeof(bits));
+    }
+    if (m->live) {  // the call is over: what the LAST tick saw -> where the schedule really stands
         __atomic_store_n(&m->live[1], bits, __ATOMIC_RELAXED);
         __atomic_store_n(&m->live[0], m->live_offset + (unsigned long long)m->st_samples, __ATOMIC_RELAXED);
         __atomic_store_n(&m->live[3], 0ull, __ATOMIC_RELEASE);
@@ -327,7 +380,15 @@ constexpr size_t kL1GatherMinTableBytes = 256ull << 20;
 int set_l1_gather(const smore_model_s* m) {
     int on = (size_t)m->rows * (size_t)m->dim * m->elem() >= kL1GatherMinTableBytes ? 1 : 0;
     if (const char* e = getenv("SMORE_L1_GATHER")) on = atoi(e) != 0;
-    CU(cudaMemcpyToSymbol(c_l1_gather, &on, sizeof(int)));
+    // (c_l1_gather is a per-translation-unit symbol and this function is too: the cache below is per TU and per device)
+    static int last_on = -1, last_dev = -1;
+    int dev = -1;
+    CU(cudaGetDevice(&dev));
+    if (on != last_on || dev != last_dev) {
+        CU(cudaMemcpyToSymbol(c_l1_gather, &on, sizeof(int)));
+        last_on = on;
+        last_dev = dev;
+    }
     return SMORE_OK;
 }
 
@@ -400,12 +461,10 @@ int init_state(smore_model_s* m, int warps, uint64_t count0, double alpha, const
         const double a = alpha * (1.0 - (double)p->sched_offset / (double)p->sched_total);
         alpha = a < alpha * 0.0001 ? alpha * 0.0001 : a;
     }
-    std::vector<WarpState> st((size_t)warps);
-    for (int w = 0; w < warps; ++w) {
-        st[(size_t)w] = WarpState{0, count0, ((uint64_t)kMonitor + (uint64_t)warps - 1) / (uint64_t)warps, alpha, 0, 0};
-    }
+    const WarpState proto{0, count0, ((uint64_t)kMonitor + (uint64_t)warps - 1) / (uint64_t)warps, alpha, 0, 0};
     if (int rc = ensure_state(m, warps)) return rc;
-    CU(cudaMemcpy(m->d_state, st.data(), st.size() * sizeof(WarpState), cudaMemcpyHostToDevice));
+    k_fill_state<<<(warps + 255) / 256, 256>>>(m->d_state, warps, proto);  // (a kernel, not a copy: see collect_stats)
+    CU(cudaGetLastError());
     return SMORE_OK;
 }
 

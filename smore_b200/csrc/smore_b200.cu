@@ -702,11 +702,12 @@ static int async_rows(smore_model_t m, int table, int64_t first, int64_t n, floa
     if (int rc = ensure_device()) return rc;
     cudaStream_t& st = to_device ? m->h2d_stream : m->d2h_stream;
     if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    // Device-side ordering between the two copy streams of ONE model: an upload is ordered after the read-backs issued before
-    // it (it may overwrite the rows they are still reading) and a read-back after the uploads issued before it -- so a host
-    // that double-buffers two models never has to block on a copy before it can launch the next train call.
-    cudaEvent_t& mine = to_device ? m->h2d_event : m->d2h_event;
-    cudaEvent_t& other = to_device ? m->d2h_event : m->h2d_event;
+    // Device-side ordering between the two copy streams of ONE model, per TABLE: an upload is ordered after the read-backs of
+    // the same table issued before it (it may overwrite the rows they are still reading) and a read-back after the uploads of
+    // that table issued before it -- so a host that double-buffers two models never has to block on a copy before it can
+    // launch the next train call, and the upload of one table runs next to the read-back of the other (PCIe is full duplex).
+    cudaEvent_t& mine = to_device ? m->h2d_event[table] : m->d2h_event[table];
+    cudaEvent_t& other = to_device ? m->d2h_event[table] : m->h2d_event[table];
     if (!mine) CU(cudaEventCreateWithFlags(&mine, cudaEventDisableTiming));
     if (other) CU(cudaStreamWaitEvent(st, other, 0));
     const size_t row_bytes = (size_t)m->dim * sizeof(float);

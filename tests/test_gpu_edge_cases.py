@@ -149,9 +149,10 @@ def test_chunked_schedule_continues_the_learning_rate():
 
 
 def test_async_row_copies_are_ordered_on_the_device():
-    """smore_model_{set,get}_rows_f32_async: an upload is ordered after the read-backs of the same model issued before it (and a
-    read-back after earlier uploads) by events between the two copy streams -- the host does not have to wait in between.
-    bench.py's end-to-end leg relies on it to double-buffer two model instances."""
+    """smore_model_{set,get}_rows_f32_async: an upload is ordered after the read-backs of the same TABLE issued before it (and a
+    read-back after earlier uploads of that table) by events between the two copy streams -- the host does not have to wait in
+    between, and copies of the other table are free to run next to them. bench.py's end-to-end leg relies on it to
+    double-buffer two model instances."""
     import torch
 
     src, dst, w = graphs.random_graph(5000, 40000, seed=3)
@@ -163,14 +164,23 @@ def test_async_row_copies_are_ordered_on_the_device():
     b = torch.full((V, dim), 2.0, dtype=torch.float32).pin_memory()
     out1 = torch.zeros((V, dim), dtype=torch.float32).pin_memory()
     out2 = torch.zeros((V, dim), dtype=torch.float32).pin_memory()
+    c = torch.full((V, dim), 3.0, dtype=torch.float32).pin_memory()
+    out3 = torch.zeros((V, dim), dtype=torch.float32).pin_memory()
+    out4 = torch.zeros((V, dim), dtype=torch.float32).pin_memory()
     for _ in range(20):  # no host wait between the calls
         m.set_rows_async(0, a.numpy())
+        m.set_rows_async(1, c.numpy())
         m.get_rows_async(0, out1.numpy())   # must see `a`
         m.set_rows_async(0, b.numpy())      # must not overtake the read-back above
+        m.get_rows_async(1, out3.numpy())   # the other table, interleaved: must see `c`
+        m.set_rows_async(1, a.numpy())      # must not overtake the read-back of table 1
         m.get_rows_async(0, out2.numpy())   # must see `b`
+        m.get_rows_async(1, out4.numpy())   # must see `a`
         m.wait_copies()
         assert float(out1.min()) == 1.0 == float(out1.max())
         assert float(out2.min()) == 2.0 == float(out2.max())
-        out1.zero_(), out2.zero_()
+        assert float(out3.min()) == 3.0 == float(out3.max())
+        assert float(out4.min()) == 1.0 == float(out4.max())
+        out1.zero_(), out2.zero_(), out3.zero_(), out4.zero_()
     with pytest.raises(capi.SmoreError):
         m.set_rows_async(0, a.numpy()[: V - 1], first=2)
