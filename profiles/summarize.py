@@ -42,7 +42,7 @@ def main():
         f.write("id,kernel,grid,block,gpu__time_duration_ns\n")
         total = {}
         for r in rows[1:]:
-            name = re.sub(r"smore::", "", r[4])
+            name = re.sub(r"smore::|<unnamed>::", "", r[4])
             f.write(f"{r[0]},\"{name}\",\"{r[8]}\",\"{r[7]}\",{r[-1]}\n")
             short = name.split("<")[0].replace("void ", "")
             total[short] = total.get(short, 0) + float(r[-1])
