@@ -58,3 +58,41 @@ def test_product_never_touches_oracle():
                 for line in open(os.path.join(dirpath, f), errors="ignore").read().splitlines():
                     if re.search(r"^\s*(#\s*include|import|from)\b.*oracle", line) or "libsmore_oracle" in line or "libsmore_ref" in line:
                         raise AssertionError(f"{f}: {line}")
+
+
+def test_argument_validation_happens_before_any_device_work():
+    """Shape and argument checks of the C ABI run before the library touches a device (or the caller's arrays), so they are
+    the same with and without a GPU: every call below must come back with SMORE_E_INVALID and a message, never crash
+    (round-1 advisor finding: smore_graph_create copied the caller's arrays before validating V / E)."""
+    import ctypes as C
+
+    L = capi.lib()
+    vp = C.c_void_p
+    off = np.array([0, 1, 2], dtype=np.int64)
+    col = np.array([1, 0], dtype=np.int32)
+    w = np.ones(2)
+    P = lambda a: a.ctypes.data_as(vp)  # noqa: E731
+    h = vp()
+
+    def invalid(rc, pattern):
+        assert rc == -1, rc  # SMORE_E_INVALID (include/smore_b200.h)
+        assert re.search(pattern, L.smore_last_error().decode()), L.smore_last_error()
+
+    invalid(L.smore_graph_create(2, 2, None, P(col), P(w), 2, capi.SEM_CPP, capi.NEG_DEGREES, C.byref(h)), "null")
+    invalid(L.smore_graph_create(2, 2, P(off), None, P(w), 2, capi.SEM_CPP, capi.NEG_DEGREES, C.byref(h)), "null")
+    invalid(L.smore_graph_create(2, 2, P(off), P(col), P(w), 2, capi.SEM_CPP, capi.NEG_DEGREES, None), "null")
+    invalid(L.smore_graph_create(2, 2, P(off), P(col), P(w), 2, 7, capi.NEG_DEGREES, C.byref(h)), "semantics")
+    invalid(L.smore_graph_create(2, 2, P(off), P(col), P(w), 2, capi.SEM_CPP, 9, C.byref(h)), "negative_method")
+    invalid(L.smore_graph_create(0, 2, P(off), P(col), P(w), 2, capi.SEM_CPP, capi.NEG_DEGREES, C.byref(h)), "V=0")
+    invalid(L.smore_graph_create(-3, 2, P(off), P(col), P(w), 2, capi.SEM_CPP, capi.NEG_DEGREES, C.byref(h)), "V=-3")
+    invalid(L.smore_graph_create(1 << 31, 2, P(off), P(col), P(w), 2, capi.SEM_CPP, capi.NEG_DEGREES, C.byref(h)), "out of range")
+    invalid(L.smore_graph_create(2, -1, P(off), P(col), P(w), 2, capi.SEM_CPP, capi.NEG_DEGREES, C.byref(h)), "E=-1")
+    invalid(L.smore_graph_create(2, 1 << 32, P(off), P(col), P(w), 2, capi.SEM_CPP, capi.NEG_DEGREES, C.byref(h)), "out of range")
+    invalid(L.smore_graph_create(2, 3, P(off), P(col), P(w), 3, capi.SEM_CPP, capi.NEG_DEGREES, C.byref(h)), "row_off")
+    assert not h.value
+    invalid(L.smore_graph_load_edge_list(None, 1, capi.SEM_CPP, capi.NEG_DEGREES, C.byref(h)), "null")
+    invalid(L.smore_graph_load_edge_list(b"/tmp/x", 1, 5, capi.NEG_DEGREES, C.byref(h)), "semantics")
+    # null handles
+    invalid(L.smore_model_wait_copies(None, 1, 1), "null")
+    invalid(L.smore_rot_send_begin(None, 0), "rotation")
+    invalid(L.smore_model_set_rows_f32_async(None, 0, 0, 1, P(w)), "bad model")
