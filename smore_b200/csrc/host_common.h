@@ -381,9 +381,11 @@ int set_l1_gather(const smore_model_s* m) {
     int on = (size_t)m->rows * (size_t)m->dim * m->elem() >= kL1GatherMinTableBytes ? 1 : 0;
     if (const char* e = getenv("SMORE_L1_GATHER")) on = atoi(e) != 0;
     // (c_l1_gather is a per-translation-unit symbol and this function is too: the cache below is per TU and per device)
+    static std::mutex mu;  // (train calls on different handles may come from different host threads)
     static int last_on = -1, last_dev = -1;
     int dev = -1;
     CU(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
     if (on != last_on || dev != last_dev) {
         CU(cudaMemcpyToSymbol(c_l1_gather, &on, sizeof(int)));
         last_on = on;
